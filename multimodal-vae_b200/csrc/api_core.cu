@@ -1,0 +1,65 @@
+// Error state, environment knobs and the generic GEMM entry of the C ABI (include/mvae_b200.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/mvae_b200.h"
+#include "common.cuh"
+
+namespace mvae {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
+  return 2;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  if (s == nullptr || *s == 0) return dflt;
+  return atoi(s);
+}
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" {
+
+const char* mvae_last_error(void) { return g_err; }
+
+int mvae_abi_version(void) { return MVAE_ABI_VERSION; }
+
+int mvae_device_check(int device) {
+  cudaDeviceProp prop;
+  MVAE_CUDA(cudaGetDeviceProperties(&prop, device));
+  MVAE_REQUIRE(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+               prop.minor);
+  return 0;
+}
+
+int mvae_gemm(const mvae_gemm_args* a, void* stream) {
+  MVAE_REQUIRE(a != nullptr, "mvae_gemm: null args");
+  GemmDesc g;
+  g.kind = a->dtype;
+  g.M = a->M; g.N = a->N; g.K = a->K;
+  g.A = a->A; g.lda = a->lda; g.a_mn = a->a_major;
+  g.B = a->B; g.ldb = a->ldb; g.b_mn = a->b_major;
+  g.block_n = a->block_n; g.split_k = a->split_k; g.stages = a->stages;
+  g.epi.kind = a->accumulate ? EPI_ATOMIC : EPI_STORE;
+  g.epi.C = a->C; g.epi.ldc = a->ldc; g.epi.c_dtype = a->c_dtype;
+  g.epi.bias = a->bias;
+  g.epi.stat0 = a->col_sum; g.epi.stat1 = a->col_sumsq;
+  g.epi.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : (1 << 30);
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Shared host/device declarations for the MVAE B200 library (internal; the public C ABI is
+// include/mvae_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace mvae {
+
+// Error plumbing: every C-ABI entry returns 0 on success; the message of the last failure on
+// the calling thread is kept for mvae_last_error().
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define MVAE_CUDA(expr)                                                  \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return ::mvae::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define MVAE_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      ::mvae::set_error(__VA_ARGS__); \
+      return 1;                      \
+    }                                \
+  } while (0)
+
+// Storage type of activations / gradients: 0 = fp32 (TF32 tensor path), 1 = bf16.
+enum : int { MVAE_F32 = 0, MVAE_BF16 = 1 };
+
+// ---------------------------------------------------------------- GEMM (tcgen05)
+enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_BCE = 2, EPI_DGRAD_BN = 3 };
+
+struct GemmEpilogue {
+  int kind = EPI_STORE;
+  void* C = nullptr;        // [M, N] row-major, leading dimension ldc (elements)
+  long long ldc = 0;
+  int c_dtype = MVAE_F32;   // EPI_ATOMIC requires fp32
+  const float* bias = nullptr;  // [N]
+  // Column statistics, accumulated with atomics into [groups][N] fp32 buffers; group = row / rows_per_group.
+  //   EPI_STORE    : stat0 += sum(y), stat1 += sum(y*y)            (BatchNorm batch statistics)
+  //   EPI_BCE      : stat0 += sum(dlogit)  (stat0 is a single [N] bias gradient, no groups)
+  //   EPI_DGRAD_BN : stat0 += sum(dyhat), stat1 += sum(dyhat * xhat)
+  float* stat0 = nullptr;
+  float* stat1 = nullptr;
+  int rows_per_group = 1 << 30;
+  // EPI_BCE: logits never leave the SM. target is [target_rows, N] (activation dtype), row m reads
+  // target[m % target_rows]; group g = m / rows_per_group has weight bce_scale[g] (= lambda / (B*N));
+  // loss[g] += sum softplus(x) - t*x  (unscaled; the caller scales), dlogit = bce_scale[g]*(sigmoid(x)-t).
+  const void* target = nullptr;
+  long long ldt = 0;
+  int target_rows = 1;
+  float bce_scale[4] = {0, 0, 0, 0};
+  float* loss = nullptr;   // [groups]
+  void* probs = nullptr;   // optional sigmoid(x) output, same layout/dtype as C
+  // EPI_DGRAD_BN: C = acc * 1[gamma*xhat+beta > 0], xhat = (hpre - mean[g])*rstd[g]
+  const void* hpre = nullptr;
+  long long ldh = 0;
+  const float* bn_mean = nullptr;  // [groups][N]
+  const float* bn_rstd = nullptr;  // [groups][N]
+  const float* bn_gamma = nullptr; // [N]
+  const float* bn_beta = nullptr;  // [N]
+};
+
+struct GemmDesc {
+  int kind = MVAE_F32;  // operand storage: fp32 (kind::tf32) or bf16 (kind::f16)
+  int M = 0, N = 0, K = 0;
+  // A is logically [M, K], B is logically [N, K]; C = A * B^T.
+  // major = 0: contraction index contiguous (row-major [rows, K]);
+  // major = 1: row index contiguous (stored as [K, rows] row-major).
+  const void* A = nullptr;
+  long long lda = 0;
+  int a_mn = 0;
+  const void* B = nullptr;
+  long long ldb = 0;
+  int b_mn = 0;
+  int block_n = 0;  // 0 = auto
+  int split_k = 0;  // 0 = auto (only EPI_ATOMIC may split)
+  int stages = 0;   // 0 = auto
+  GemmEpilogue epi;
+};
+
+int launch_gemm(const GemmDesc& g, cudaStream_t stream);
+
+// Tuning knobs readable from the environment (debug / bench sweeps only).
+int env_int(const char* name, int dflt);
+
+}  // namespace mvae
