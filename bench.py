@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the MVAE training step (BASELINE.json metric: "MVAE train samples/sec (fwd+bwd ELBO)").
+
+    python bench.py --gpus 1 --steps K --warmup W                 # this repo's CUDA path
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W         # the reference's CPU path (oracle port)
+
+One "step" = one full three-term ELBO training step (forward, backward, Adam) on one batch of synthetic
+MNIST-shaped data (config[1] of BASELINE.json: MNIST MVAE, n_latents=64, batch 4096 per GPU).  Prints ONE
+JSON line (rank 0).  Timing rules followed: >= 3 warm-up steps, device-side CUDA events, barrier + synchronize
+on both sides, max over ranks, inputs rotate through a pool larger than L2, clocks sampled during the timed
+region.  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LATENTS = 64
+BATCH_PER_GPU = 4096
+L2_BYTES = 126 * 1024 * 1024
+# algorithmic work per sample per step for the reference MNIST architecture
+F_ALG_PER_SAMPLE = 9_254_920          # FLOP on tensor cores (encoders once, decoders x3, fwd + dgrad + wgrad)
+Q_TAIL_PER_SAMPLE = 29_880            # bytes of the fused PoE/reparam/KL + BCE/CE tail, fp32 I/O
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _sample(self):
+        nv = self.nv
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        for k, bit in names.items():
+            if r & bit:
+                self.reasons.add(k)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if self.nv is not None and not self.samples:
+            try:
+                self._sample()
+            except Exception:
+                pass
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def synthetic_pool(batch, n_slots, seed, device, torch):
+    """Pool of distinct synthetic batches: uint8 MNIST-shaped images and labels (SURVEY 8d shapes)."""
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.randint(0, 256, (n_slots, batch, 784), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 10, (n_slots, batch), generator=g, dtype=torch.int64)
+    return imgs, labels
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the step, timed on the host cores.  The reference is a set of
+    Python scripts over PyTorch ATen (nothing to compile); /root/reference is absent on the GPU box, so the
+    arm runs oracle/mnist_oracle.py - the line-by-line restatement pinned to the reference's golden vectors."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mnist_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = BATCH_PER_GPU
+    state = O.init_state(N_LATENTS, seed=1234)
+    image, text, noises = O.synthetic_batch(B, N_LATENTS, 0)
+    mom = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    # bounded sample: at ~0.25 s per step the whole run must end within minutes
+    steps = min(args.steps, 40)
+    warmup = min(args.warmup, 3)
+    p = state
+    step_no = 0
+
+    def one():
+        nonlocal p, step_no
+        step_no += 1
+        _, grads, bufs, _ = O.train_step(p, image, text, [torch.randn_like(n) for n in noises])
+        p = O.adam_step(p, grads, mom, vel, step_no)
+        p.update(bufs)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    line = {
+        "impl": "reference", "metric": "MVAE train samples/sec (fwd+bwd ELBO)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MNIST MVAE n_latents=64 batch=4096 3-term ELBO step (fwd+bwd+Adam), CPU oracle port",
+                   "batch": B, "n_latents": N_LATENTS},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d steps of batch %d after %d warm-up" % (steps, B, warmup)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline(torch, budget_s=12.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mnist_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = BATCH_PER_GPU
+    state = O.init_state(N_LATENTS, seed=1234)
+    image, text, noises = O.synthetic_batch(B, N_LATENTS, 0)
+    mom = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    p, n, t_used = state, 0, 0.0
+    for i in range(2):
+        _, grads, bufs, _ = O.train_step(p, image, text, noises)
+    while t_used < budget_s and n < 40:
+        t0 = time.perf_counter()
+        _, grads, bufs, _ = O.train_step(p, image, text, noises)
+        p = O.adam_step(p, grads, mom, vel, n + 1)
+        p.update(bufs)
+        t_used += time.perf_counter() - t0
+        n += 1
+    return {"value": B * n / t_used, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d steps of batch %d (oracle/mnist_oracle.py, fp32, %d threads)" % (n, B, torch.get_num_threads())}
+
+
+# ------------------------------------------------------------------------------------------- device arm
+def run_device(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import mvae_b200
+    from mvae_b200 import MVAE, MVAETrainer
+    from mvae_b200.parallel import DataParallelTrainer
+
+    B = args.batch
+    model = MVAE(N_LATENTS, precision=args.precision, device=dev, seed=1234 + rank)
+    if world > 1:
+        trainer = DataParallelTrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph)
+    else:
+        trainer = MVAETrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph)
+
+    es = 2 if args.precision == "bf16" else 4
+    n_slots = max(4, (2 * L2_BYTES + B * 784 * es - 1) // (B * 784 * es))
+    imgs_u8, labels = synthetic_pool(B, n_slots, 100 + rank, dev, torch)
+    pool_x = [model.to_act(imgs_u8[i].to(dev)) for i in range(n_slots)]   # resident in HBM, storage dtype
+    pool_y = [labels[i].to(dev) for i in range(n_slots)]
+    host_x = [imgs_u8[i].pin_memory() for i in range(min(n_slots, 8))]
+    host_y = [labels[i].pin_memory() for i in range(min(n_slots, 8))]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lib = mvae_b200._lib.load()
+    # ---- device-resident throughput ("value")
+    for i in range(max(args.warmup, 3)):
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = lib.mvae_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    eager_launches = int(lib.mvae_launch_count() - l0)
+    per_step_launches = trainer.last_graph_launches if not args.no_graph else eager_launches // max(args.steps, 1)
+    final_loss = [float(v) for v in losses[:, 0].tolist()]
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned uint8 images + int64 labels -> loss on host)
+    e2e_steps = max(3, min(args.steps, 200))
+    for i in range(3):
+        l, _ = trainer.step(host_x[i % len(host_x)], host_y[i % len(host_y)])
+        l.cpu()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(e2e_steps):
+        l, _ = trainer.step(host_x[i % len(host_x)], host_y[i % len(host_y)])
+        l_host = l.to("cpu", non_blocking=False)   # the step's result read back every step
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = B * world * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- live per-kernel durations (CUDA events around every launch, rank 0)
+    peaks = load_peaks()
+    tt, klw = trainer._norm(("joint", "image", "text"), B, 1.0)
+    prof_runs = []
+    for i in range(5):
+        prof_runs.append(model.profile(pool_x[i % n_slots], pool_y[i % n_slots], tt, ((1.0, 1.0),) * 3, klw, backward=True,
+                                       zero_grad=True, adam=trainer.adam))
+    agg = {}
+    for run in prof_runs[1:]:
+        for label, ms in run:
+            kind = label.split(":")[0].split("#")[0]
+            agg[kind] = agg.get(kind, 0.0) + ms / (len(prof_runs) - 1)
+    gemm_ms = sum(v for k, v in agg.items() if k.startswith("gemm"))
+    gemm_launches = sum(1 for label, _ in prof_runs[-1] if label.startswith("gemm"))
+    serial_ms = sum(agg.values())
+    flops = F_ALG_PER_SAMPLE * B
+    achieved_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
+    t_roof_us = flops / (peaks["bf16_tflops"] * 1e12) * 1e6 + Q_TAIL_PER_SAMPLE * B / (peaks["hbm_gbs"] * 1e9) * 1e6
+    ms_per_step = ms_total / args.steps
+
+    line = {
+        "metric": "MVAE train samples/sec (fwd+bwd ELBO)",
+        "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "tf32", "data": "synthetic",
+        "config": {"workload": "MNIST MVAE (784-400-200-2n MLP + label text, BatchNorm+ReLU), n_latents=64, "
+                               "batch %d per GPU, fused PoE + 3-term subsampled ELBO, fwd+bwd+Adam" % B,
+                   "batch_per_gpu": B, "global_batch": B * world, "n_latents": N_LATENTS, "parallelism": "dp%d" % world,
+                   "l2_policy": "inputs rotate through a pool of %d distinct batches (%.0f MB > 2x L2)" % (
+                       n_slots, n_slots * B * 784 * es / 1e6),
+                   "cuda_graph": not args.no_graph, "precision": args.precision},
+        "final_loss_terms": final_loss,
+        "gpu_launches": per_step_launches * args.steps,
+        "gpu_launches_per_step": per_step_launches,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * 784 + B * 8,
+                "d2h_bytes_per_step": 3 * 4 * 4, "steps": e2e_steps,
+                "path": "MVAETrainer.step(pinned uint8 images, int64 labels) -> losses.cpu()"},
+        "roofline": {"bound": "tensor", "kernel": "mvae::gemm_kernel (tcgen05/TMA GEMM, %d launches per step)" % gemm_launches,
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "traffic": None, "peak_source": peaks["source"] + (" (sustained bf16; tf32 = half)"),
+                     "flops_per_step": flops, "kernel_ms_per_step": gemm_ms},
+        "step_roofline": {"t_roof_us": t_roof_us, "t_measured_us": ms_per_step * 1e3,
+                          "frac": t_roof_us / (ms_per_step * 1e3),
+                          "definition": "SURVEY 8d: F_alg/bf16 burst peak + Q_tail/HBM peak"},
+        "kernel_ms_per_step_serialised": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])},
+        "serialised_ms_per_step": serial_ms,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(torch)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_device(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -64,8 +64,99 @@ typedef struct mvae_gemm_args {
   int block_n;        /* 0 = auto */
   int split_k;        /* 0 = auto */
   int stages;         /* 0 = auto */
+  void* debug_times;  /* NULL, or device int64 [ctas][8] receiving %globaltimer stamps (bring-up only) */
 } mvae_gemm_args;
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * MNIST MVAE (mnist/model.py:14-170).  All parameters live in ONE flat fp32 buffer (so that the data-
+ * parallel gradient all-reduce and Adam are single flat operations); float BatchNorm buffers live in a
+ * second flat buffer; num_batches_tracked is an int64[6] array in state_dict order.  The table below is
+ * queried by the host to build views named exactly like the reference's state_dict keys.
+ */
+typedef struct mvae_tensor_info {
+  char name[64];   /* reference state_dict key, e.g. "image_encoder.net.0.weight" */
+  int kind;        /* 0 parameter (offset into params/grads/adam buffers, in floats)
+                      1 float buffer: running_mean / running_var (offset into the buffer array)
+                      2 num_batches_tracked (index into the int64 array) */
+  int ndim;
+  int64_t shape[2];
+  int64_t offset;
+} mvae_tensor_info;
+int mvae_mnist_num_tensors(void);
+int mvae_mnist_tensor_info(int n_latents, int index, mvae_tensor_info* out);
+
+typedef struct mvae_mnist_size_info {
+  int64_t param_floats;     /* length of the flat params / grads / adam_m / adam_v (/ bf16 mirror) buffers */
+  int64_t buffer_floats;    /* length of the flat running-statistics buffer */
+  int64_t num_bn;           /* length of the num_batches_tracked array */
+  int64_t workspace_bytes;  /* activation workspace for (batch, n_latents, dtype), up to 3 terms */
+} mvae_mnist_size_info;
+int mvae_mnist_sizes(int n_latents, int batch, int dtype, mvae_mnist_size_info* out);
+
+#define MVAE_TERM_JOINT 0 /* vae(image, text)  mnist/train.py:136 */
+#define MVAE_TERM_IMAGE 1 /* vae(image=image)  mnist/train.py:137 */
+#define MVAE_TERM_TEXT 2  /* vae(text=text)    mnist/train.py:138 */
+
+/* One training step = mnist/train.py:132-153: zero_grad, the (up to) three forwards, the three
+ * loss_function calls (mnist/train.py:64-81) summed, backward, optimizer.step().
+ *   loss_t = lambda_image[t] * BCE_mean(recon_image_t, image) + lambda_text[t] * NLL_mean(recon_text_t, text)
+ *            + kl_weight[t] * -0.5 * sum(1 + logvar_t - mu_t^2 - exp(logvar_t))
+ * (the reference's MNIST step is kl_weight = 3 / (784 * batch), all lambdas 1; weak supervision
+ * mnist/modal_weak.py:76-97 drops terms).  `eps` injects the N(0,1) draws of reparametrize
+ * (mnist/model.py:27) for parity; NULL draws them in-kernel (Philox keyed by seed and step). */
+typedef struct mvae_mnist_step_args {
+  int batch, n_latents, dtype;
+  int n_terms;
+  int term_type[3];
+  float lambda_image[3], lambda_text[3], kl_weight[3];
+  int poe_mode, prior_expert;
+  float poe_eps;
+  const void* image;        /* [batch, 784] in `dtype` storage, values in [0,1] */
+  const int64_t* text;      /* [batch] labels 0..9 */
+  const float* eps;         /* [n_terms, batch, n_latents] or NULL */
+  uint64_t seed;
+  float* params;            /* flat fp32 parameters */
+  void* params_bf16;        /* bf16 mirror (same element offsets); required for MVAE_DT_BF16 */
+  float* buffers;           /* flat running_mean / running_var */
+  int64_t* num_batches_tracked; /* [6] or NULL */
+  float* grads;             /* flat fp32 gradients (accumulated into) */
+  int do_backward, zero_grad, do_adam;
+  float* adam_m; float* adam_v;
+  int* adam_step;           /* device int: incremented at the start of every call (also the Philox step) */
+  float lr, beta1, beta2, adam_eps, grad_scale;
+  void* workspace; int64_t workspace_bytes;
+  float* out_losses;        /* device [n_terms][4]: total, image BCE, text NLL, KL (already weighted) or NULL */
+  void* out_recon_image;    /* optional [n_terms*batch, 784] probabilities, `dtype` storage */
+  float* out_recon_text;    /* optional [n_terms*batch, 10] log-probabilities */
+  float* out_mu;            /* optional [n_terms, batch, n_latents] */
+  float* out_logvar;
+} mvae_mnist_step_args;
+int mvae_mnist_step(const mvae_mnist_step_args* args, void* stream);
+
+/* Measurement aids.  mvae_launch_count: kernels launched by this library so far (monotonic).
+ * mvae_mnist_step_profile: runs one step on `stream` only (no side stream) with a CUDA-event pair around every
+ * launch; after a stream synchronise returns up to max_entries (label, milliseconds) pairs. */
+long long mvae_launch_count(void);
+int mvae_mnist_step_profile(const mvae_mnist_step_args* args, void* stream, int max_entries, char* labels,
+                            int label_stride, float* ms_out, int* n_out);
+
+/* torch.optim.Adam defaults semantics (mnist/train.py:118,153) over a flat buffer; *step_counter is the
+ * 1-based step (device memory).  grads are multiplied by grad_scale first (1/world_size after an all-reduce). */
+int mvae_adam_step(float* params, float* grads, float* m, float* v, void* params_bf16, int64_t count, float lr,
+                   float beta1, float beta2, float eps, const int* step_counter, float grad_scale, int zero_grad,
+                   void* stream);
+int mvae_cast_f32_to_bf16(const float* in, void* out, int64_t count, void* stream);
+/* uint8 pixels -> [0,1] activations (image.view(-1,784) of ToTensor(), mnist/train.py:106,131) */
+int mvae_u8_to_act(const uint8_t* in, float* out_f32, void* out_bf16, int64_t count, float scale, void* stream);
+
+/* ProductOfExperts (mnist/model.py:173-185) for M experts with an optional per-sample presence mask
+ * [M, batch] (1 = present).  mu/logvar: [M, batch, dim]; outputs [batch, dim]. */
+int mvae_poe_forward(int mode, int prior_expert, float eps, int n_experts, int64_t batch, int dim, const float* mu,
+                     const float* logvar, const float* mask, float* out_mu, float* out_logvar, void* stream);
+int mvae_poe_backward(int mode, int prior_expert, float eps, int n_experts, int64_t batch, int dim, const float* mu,
+                      const float* logvar, const float* mask, const float* d_out_mu, const float* d_out_logvar,
+                      float* d_mu, float* d_logvar, void* stream);
 
 #ifdef __cplusplus
 }

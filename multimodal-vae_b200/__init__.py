@@ -1,4 +1,10 @@
-"""mvae_b200 - B200-native MVAE training step."""
-from . import _lib  # noqa: F401
+"""mvae_b200 - B200-native MVAE training step.
 
-__all__ = ["_lib"]
+    from mvae_b200 import MVAE, MultimodalVAE, MVAETrainer
+"""
+from . import _lib  # noqa: F401
+from .mnist import MVAE, MultimodalVAE, MVAETrainer, TERMS  # noqa: F401
+
+from .parallel import DataParallelTrainer  # noqa: F401
+
+__all__ = ["MVAE", "MultimodalVAE", "MVAETrainer", "DataParallelTrainer", "TERMS", "_lib"]

@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("bias", c_void_p), ("accumulate", c_int),
         ("col_sum", c_void_p), ("col_sumsq", c_void_p), ("rows_per_group", c_int),
         ("block_n", c_int), ("split_k", c_int), ("stages", c_int),
+        ("debug_times", c_void_p),
     ]
 
 
@@ -47,6 +48,9 @@ def load():
             _build.build()
         lib = C.CDLL(_build.LIB_PATH)
         lib.mvae_last_error.restype = C.c_char_p
+        lib.mvae_launch_count.restype = C.c_longlong
+        lib.mvae_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                       c_float, c_float, c_void_p, c_float, c_int, c_void_p]
         _lib = lib
         return lib
 
@@ -60,3 +64,42 @@ def check(rc: int, what: str = "") -> None:
 def ptr(t) -> int | None:
     """Device pointer of a torch tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+c_uint64 = C.c_uint64
+
+
+class TensorInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("kind", c_int), ("ndim", c_int), ("shape", c_int64 * 2),
+                ("offset", c_int64)]
+
+
+class MnistSizeInfo(C.Structure):
+    _fields_ = [("param_floats", c_int64), ("buffer_floats", c_int64), ("num_bn", c_int64),
+                ("workspace_bytes", c_int64)]
+
+
+class MnistStepArgs(C.Structure):
+    _fields_ = [
+        ("batch", c_int), ("n_latents", c_int), ("dtype", c_int),
+        ("n_terms", c_int),
+        ("term_type", c_int * 3),
+        ("lambda_image", c_float * 3), ("lambda_text", c_float * 3), ("kl_weight", c_float * 3),
+        ("poe_mode", c_int), ("prior_expert", c_int),
+        ("poe_eps", c_float),
+        ("image", c_void_p), ("text", c_void_p), ("eps", c_void_p),
+        ("seed", c_uint64),
+        ("params", c_void_p), ("params_bf16", c_void_p), ("buffers", c_void_p),
+        ("num_batches_tracked", c_void_p), ("grads", c_void_p),
+        ("do_backward", c_int), ("zero_grad", c_int), ("do_adam", c_int),
+        ("adam_m", c_void_p), ("adam_v", c_void_p), ("adam_step", c_void_p),
+        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("adam_eps", c_float), ("grad_scale", c_float),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("out_losses", c_void_p), ("out_recon_image", c_void_p), ("out_recon_text", c_void_p),
+        ("out_mu", c_void_p), ("out_logvar", c_void_p),
+    ]
+
+
+DT_F32, DT_BF16 = 0, 1
+POE_REF, POE_PRECISION = 0, 1
+TERM_JOINT, TERM_IMAGE, TERM_TEXT = 0, 1, 2

@@ -59,6 +59,7 @@ int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   g.epi.bias = a->bias;
   g.epi.stat0 = a->col_sum; g.epi.stat1 = a->col_sumsq;
   g.epi.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : (1 << 30);
+  g.dbg = reinterpret_cast<long long*>(a->debug_times);
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

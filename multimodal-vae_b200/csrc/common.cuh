@@ -80,6 +80,7 @@ struct GemmDesc {
   int block_n = 0;  // 0 = auto
   int split_k = 0;  // 0 = auto (only EPI_ATOMIC may split)
   int stages = 0;   // 0 = auto
+  long long* dbg = nullptr;  // device buffer [ctas][8] of %globaltimer stamps (bring-up only)
   GemmEpilogue epi;
 };
 

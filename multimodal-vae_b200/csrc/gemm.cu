@@ -3,10 +3,11 @@
 //
 //   C[M,N] = A[M,K] * B[N,K]^T        (fp32 accumulate in TMEM)
 //
-// One CTA = one 128 x block_n output tile (UMMA M=128, N=block_n, cta_group::1), 6 warps:
+// One CTA = one 128 x block_n output tile (UMMA M=128, N=block_n, cta_group::1), 8 warps:
 //   warp 0   : TMA producer (one elected lane) - A/B tiles into a SWIZZLE_128B smem ring
 //   warp 1   : MMA issuer   (one elected lane) - tcgen05.mma kind::tf32 / kind::f16(bf16)
-//   warps 2-5: epilogue     - tcgen05.ld TMEM -> registers -> padded smem tile -> row pass with
+//   warp 2   : TMEM allocation
+//   all 8    : epilogue - tcgen05.ld TMEM -> registers -> padded smem tile -> row pass with
 //              coalesced global I/O and per-column statistics.
 // Both operands may be K-major (contraction contiguous: forward) or MN-major (row index
 // contiguous: dgrad's weight, wgrad's activations/gradients), so no transposed copies of
@@ -30,7 +31,7 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kAStageBytes = kBlockM * 128;  // 16 KB: 128 rows x 128 B (either major)
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kStagePad = 4;  // staging row stride = block_n + 4 words -> conflict-free float4 rows
 
@@ -45,6 +46,7 @@ struct GemmKParams {
   int b_tx_bytes;     // bytes TMA actually writes per stage for B
   int vec_ok;         // all epilogue tensors allow 4-element vector access
   int stat_group_stride;
+  long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
   GemmEpilogue epi;
 };
 
@@ -101,12 +103,132 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, bool vec, int n_valid, 
       if (i < n_valid) p[i] = __float2bfloat16_rn(v[i]);
   }
 }
-__device__ __forceinline__ void store4_dyn(void* base, long long off, int dtype, bool vec, int n_valid,
-                                           const float (&v)[4]) {
-  if (dtype == MVAE_F32)
-    store4(reinterpret_cast<float*>(base) + off, vec, n_valid, v);
-  else
-    store4(reinterpret_cast<__nv_bfloat16*>(base) + off, vec, n_valid, v);
+// One thread's share of the epilogue row pass: `rows` consecutive rows starting at global row m, 4 consecutive
+// columns starting at global column cn (nv of them valid), values read from the fp32 staging tile at saddr.
+// kFast = all 4 columns valid and every tensor is vector-aligned: the loop body is branch-free so that the
+// compiler can software-pipeline the shared loads over the unrolled rows.
+template <int kKind, int kEpi, typename CT, bool kFast>
+__device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t saddr, int ldst, int m, int rows, int cn,
+                                              int nv, int lane, float* s_loss) {
+  using act_t = typename ActT<kKind>::type;
+  const GemmEpilogue& e = p.epi;
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  float bias[4], g_mean[4], g_rstd[4], g_gamma[4], g_beta[4];
+  float lsum = 0.f, g_scale = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    bias[i] = (e.bias != nullptr && i < nv) ? e.bias[cn + i] : 0.f;
+    g_mean[i] = g_rstd[i] = g_gamma[i] = g_beta[i] = 0.f;
+    if (kEpi == EPI_DGRAD_BN && i < nv) {
+      g_gamma[i] = e.bn_gamma[cn + i];
+      g_beta[i] = e.bn_beta[cn + i];
+    }
+  }
+  int g = m / e.rows_per_group;
+  int seg_left = static_cast<int>(min(static_cast<long long>(g + 1) * e.rows_per_group - m, 1ll << 20));
+  int trow = (kEpi == EPI_BCE) ? (m % e.target_rows) : 0;
+  CT* cptr = reinterpret_cast<CT*>(e.C) + static_cast<long long>(m) * e.ldc + cn;
+  CT* pptr = (kEpi == EPI_BCE && e.probs != nullptr) ? reinterpret_cast<CT*>(e.probs) + static_cast<long long>(m) * e.ldc + cn
+                                                     : nullptr;
+  const act_t* hptr =
+      (kEpi == EPI_DGRAD_BN) ? reinterpret_cast<const act_t*>(e.hpre) + static_cast<long long>(m) * e.ldh + cn : nullptr;
+  int done = 0;
+  while (done < rows) {
+    const int seg = min(rows - done, seg_left);
+    if (kEpi == EPI_BCE) g_scale = e.bce_scale[g & 3];
+    if (kEpi == EPI_DGRAD_BN) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < nv) {
+          g_mean[i] = e.bn_mean[static_cast<long long>(g) * p.N + cn + i];
+          g_rstd[i] = e.bn_rstd[static_cast<long long>(g) * p.N + cn + i];
+        }
+    }
+#pragma unroll 4
+    for (int it = 0; it < seg; ++it) {
+      float v[4];
+      ptx::lds128(saddr, v);
+      saddr += ldst * 4;
+      if constexpr (kEpi == EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[i] += bias[i];
+          acc0[i] += v[i];
+          acc1[i] = fmaf(v[i], v[i], acc1[i]);
+        }
+        store4(cptr, kFast, nv, v);
+      } else if constexpr (kEpi == EPI_ATOMIC) {
+        if constexpr (kFast && sizeof(CT) == 4) {
+          ptx::red_add_v4(reinterpret_cast<float*>(cptr), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i < nv) atomicAdd(reinterpret_cast<float*>(cptr) + i, v[i]);
+        }
+      } else if constexpr (kEpi == EPI_BCE) {
+        // BCE on logits: loss = softplus(x) - t*x, d/dx = sigmoid(x) - t  (reference: sigmoid then
+        // F.binary_cross_entropy, mnist/model.py:135 + mnist/train.py:70; identical for |x| < ~17).
+        float tg[4], d[4], pr[4];
+        load4(reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(trow) * e.ldt + cn, kFast, nv, tg);
+        if (++trow == e.target_rows) trow = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float x = v[i] + bias[i];
+          const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));  // exp(-|x|) in (0, 1]
+          const float inv = ptx::rcp_approx(1.f + ex);                        // sigmoid(|x|) in [0.5, 1)
+          const float pz = x >= 0.f ? inv : ex * inv;
+          pr[i] = pz;
+          d[i] = g_scale * (pz - tg[i]);
+          if (kFast || i < nv) {
+            // softplus(x) - t*x = max(x,0) - t*x + log(1+exp(-|x|)),  log(1+exp(-|x|)) = -ln(inv)
+            const float sp = fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[i], x, fmaxf(x, 0.f)));
+            lsum = fmaf(g_scale, sp, lsum);
+            acc0[i] += d[i];
+          }
+        }
+        store4(cptr, kFast, nv, d);
+        if (pptr != nullptr) {
+          store4(pptr, kFast, nv, pr);
+          pptr += e.ldc;
+        }
+      } else if constexpr (kEpi == EPI_DGRAD_BN) {
+        // dyhat = dh * 1[relu input > 0]; the relu input is recomputed with the forward's own expression.
+        float h[4], d[4];
+        load4(hptr, kFast, nv, h);
+        hptr += e.ldh;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float xh = (h[i] - g_mean[i]) * g_rstd[i];
+          const float y = fmaf(g_gamma[i], xh, g_beta[i]);
+          d[i] = y > 0.f ? v[i] : 0.f;
+          acc0[i] += d[i];
+          acc1[i] = fmaf(d[i], xh, acc1[i]);
+        }
+        store4(cptr, kFast, nv, d);
+      }
+      cptr += e.ldc;
+    }
+    // ---- statistics-group boundary (or end of this warp's rows): publish the column partials
+    if (e.stat0 != nullptr) {
+      const long long goff = static_cast<long long>(g) * p.stat_group_stride;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i < nv) {
+          atomicAdd(e.stat0 + goff + cn + i, acc0[i]);
+          if (e.stat1 != nullptr) atomicAdd(e.stat1 + goff + cn + i, acc1[i]);
+        }
+        acc0[i] = 0.f;
+        acc1[i] = 0.f;
+      }
+    }
+    if (kEpi == EPI_BCE) {
+      atomicAdd(s_loss + (g & 3), lsum);  // CTA-level partial in shared memory; one global atomic per CTA later
+      lsum = 0.f;
+    }
+    done += seg;
+    ++g;
+    seg_left = e.rows_per_group;
+  }
 }
 
 template <int kKind, int kEpi>
@@ -128,6 +250,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_loss[4];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -141,6 +264,17 @@ __global__ void __launch_bounds__(kGemmThreads)
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(p.block_n)) tmem_cols <<= 1;
 
+  long long* dbg = p.dbg ? p.dbg + 8ll * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  auto stamp = [&](int slot) {
+    if (dbg != nullptr) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      dbg[slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
+
+  if (threadIdx.x < 4) s_loss[threadIdx.x] = 0.f;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -159,6 +293,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -194,6 +329,7 @@ __global__ void __launch_bounds__(kGemmThreads)
         const uint32_t ph = (i / S) & 1;
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
+        if (i == 0) stamp(2);
         const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
         const uint32_t b_base = a_base + kAStageBytes;
 #pragma unroll
@@ -210,169 +346,72 @@ __global__ void __launch_bounds__(kGemmThreads)
         ptx::umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
       ptx::umma_commit(&accum_bar);  // accumulator complete
+      stamp(3);
     }
-  } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const GemmEpilogue& e = p.epi;
-    float* stage = reinterpret_cast<float*>(smem);  // aliases the (drained) operand ring
-    const int ldst = p.block_n + kStagePad;
+  }
+  __syncwarp();  // producer / MMA warps reconverge before joining the epilogue
 
-    ptx::mbar_wait(&accum_bar, 0);
-    ptx::tc_fence_after();
-    {
-      const int row = q * 32 + lane;
-      float* dst_row = stage + row * ldst;
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-        ptx::tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(dst_row + c);
+  // -------------------------------------------------------------- epilogue (all 8 warps)
+  // (1) TMEM -> registers -> padded fp32 smem tile.  Warps w and w+4 share TMEM lane quarter w&3 and take
+  //     alternate 16-column chunks.  The tile aliases the operand ring, which is fully drained by now.
+  const GemmEpilogue& e = p.epi;
+  const uint32_t stage_addr = ptx::smem_u32(smem);
+  const int ldst = p.block_n + kStagePad;  // words
+  ptx::mbar_wait(&accum_bar, 0);
+  ptx::tc_fence_after();
+  if (threadIdx.x == 64) stamp(4);
+  {
+    const int q = warp & 3;
+    const uint32_t row_addr = stage_addr + static_cast<uint32_t>((q * 32 + lane) * ldst) * 4u;
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = (warp >> 2) * 16; c < p.block_n; c += 32) {
+      uint32_t v[16];
+      ptx::tmem_ld16(t_base + c, v);
+      ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
-      }
+      for (int j = 0; j < 4; ++j) ptx::sts128(row_addr + (c + 4 * j) * 4, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
-    ptx::tc_fence_before();
-    ptx::named_bar_sync(1, 128);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 64) stamp(5);
 
-    // Row pass: this warp owns 32 consecutive rows, each lane 4 consecutive columns per 128-col chunk.
-    const int ew = warp - 2;
-    const bool vec = p.vec_ok != 0;
-    const int nch = (p.block_n + 127) / 128;
-    float acc0[2][4], acc1[2][4], bias[2][4];
-    float g_mean[2][4], g_rstd[2][4], g_gamma[2][4], g_beta[2][4];
-    float lsum = 0.f, g_scale = 0.f;
-    int nval[2], coln[2];
+  // (2) Row pass: warp w owns rows [16w, 16w+16); lane owns 4 consecutive columns per 128-column chunk, so
+  //     every global access is a full 512-B (fp32) / 256-B (bf16) line per warp and the per-column
+  //     statistics accumulate in registers.  A flush (atomics) happens at each statistics-group boundary.
+  {
+    const int r_begin = warp * 16;
+    const int rows_here = min(16, p.M - m0 - r_begin);
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int col = ch * 128 + lane * 4;
-      coln[ch] = n0 + col;
+      const int cn = n0 + col;
       int nv = 0;
-      if (ch < nch && col < p.block_n) nv = min(4, p.N - coln[ch]);
-      nval[ch] = nv < 0 ? 0 : nv;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc0[ch][i] = 0.f;
-        acc1[ch][i] = 0.f;
-        bias[ch][i] = (e.bias != nullptr && i < nval[ch]) ? e.bias[coln[ch] + i] : 0.f;
-        g_mean[ch][i] = g_rstd[ch][i] = g_gamma[ch][i] = g_beta[ch][i] = 0.f;
-        if (kEpi == EPI_DGRAD_BN && i < nval[ch]) {
-          g_gamma[ch][i] = e.bn_gamma[coln[ch] + i];
-          g_beta[ch][i] = e.bn_beta[coln[ch] + i];
-        }
+      if (col < p.block_n) nv = min(4, p.N - cn);
+      if (nv <= 0 || rows_here <= 0) continue;
+      const uint32_t saddr = stage_addr + static_cast<uint32_t>(r_begin * ldst + col) * 4u;
+      const bool fast = (nv == 4) && (p.vec_ok != 0);
+      if (e.c_dtype == MVAE_F32) {
+        if (fast)
+          epilogue_rows<kKind, kEpi, float, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, s_loss);
+        else
+          epilogue_rows<kKind, kEpi, float, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, s_loss);
+      } else {
+        if (fast)
+          epilogue_rows<kKind, kEpi, __nv_bfloat16, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, s_loss);
+        else
+          epilogue_rows<kKind, kEpi, __nv_bfloat16, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, s_loss);
       }
     }
-
-    auto flush = [&](int g) {
-      if (e.stat0 != nullptr) {
-        const long long goff = static_cast<long long>(g) * p.stat_group_stride;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nval[ch]) {
-              atomicAdd(e.stat0 + goff + coln[ch] + i, acc0[ch][i]);
-              if (e.stat1 != nullptr) atomicAdd(e.stat1 + goff + coln[ch] + i, acc1[ch][i]);
-            }
-            acc0[ch][i] = 0.f;
-            acc1[ch][i] = 0.f;
-          }
-        }
-      }
-      if (kEpi == EPI_BCE) {
-        float s = lsum;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0 && e.loss != nullptr) atomicAdd(e.loss + g, s);
-        lsum = 0.f;
-      }
-    };
-
-    int cur_g = -1;
-    for (int rr = 0; rr < 32; ++rr) {
-      const int r = ew * 32 + rr;
-      const int m = m0 + r;
-      if (m >= p.M) break;
-      const int g = m / e.rows_per_group;
-      if (g != cur_g) {
-        if (cur_g >= 0) flush(cur_g);
-        cur_g = g;
-        if (kEpi == EPI_BCE) g_scale = e.bce_scale[g & 3];
-        if (kEpi == EPI_DGRAD_BN) {
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (i < nval[ch]) {
-                g_mean[ch][i] = e.bn_mean[static_cast<long long>(g) * p.N + coln[ch] + i];
-                g_rstd[ch][i] = e.bn_rstd[static_cast<long long>(g) * p.N + coln[ch] + i];
-              }
-        }
-      }
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        if (nval[ch] == 0) continue;
-        const int col = ch * 128 + lane * 4;
-        const float4 t = *reinterpret_cast<const float4*>(stage + r * ldst + col);
-        float v[4] = {t.x, t.y, t.z, t.w};
-        const long long coff = static_cast<long long>(m) * e.ldc + coln[ch];
-        if constexpr (kEpi == EPI_STORE) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            v[i] += bias[ch][i];
-            acc0[ch][i] += v[i];
-            acc1[ch][i] += v[i] * v[i];
-          }
-          store4_dyn(e.C, coff, e.c_dtype, vec, nval[ch], v);
-        } else if constexpr (kEpi == EPI_ATOMIC) {
-          float* c = reinterpret_cast<float*>(e.C) + coff;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nval[ch]) atomicAdd(c + i, v[i]);
-        } else if constexpr (kEpi == EPI_BCE) {
-          float tg[4], d[4], pr[4];
-          const act_t* tp =
-              reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(m % e.target_rows) * e.ldt + coln[ch];
-          load4(tp, vec, nval[ch], tg);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float x = v[i] + bias[ch][i];
-            const float ex = __expf(-fabsf(x));
-            const float inv = 1.f / (1.f + ex);
-            const float pz = x >= 0.f ? inv : ex * inv;
-            pr[i] = pz;
-            d[i] = g_scale * (pz - tg[i]);
-            if (i < nval[ch]) {
-              lsum += g_scale * (fmaxf(x, 0.f) - tg[i] * x + log1pf(ex));
-              acc0[ch][i] += d[i];
-            }
-          }
-          store4_dyn(e.C, coff, e.c_dtype, vec, nval[ch], d);
-          if (e.probs != nullptr) store4_dyn(e.probs, coff, e.c_dtype, vec, nval[ch], pr);
-        } else if constexpr (kEpi == EPI_DGRAD_BN) {
-          float h[4], d[4];
-          const act_t* hp = reinterpret_cast<const act_t*>(e.hpre) + static_cast<long long>(m) * e.ldh + coln[ch];
-          load4(hp, vec, nval[ch], h);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float xh = (h[i] - g_mean[ch][i]) * g_rstd[ch][i];
-            const float y = fmaf(g_gamma[ch][i], xh, g_beta[ch][i]);
-            d[i] = y > 0.f ? v[i] : 0.f;
-            acc0[ch][i] += d[i];
-            acc1[ch][i] += d[i] * xh;
-          }
-          store4_dyn(e.C, coff, e.c_dtype, vec, nval[ch], d);
-        }
-      }
-    }
-    if (cur_g >= 0) flush(cur_g);
+    if (threadIdx.x == 64) stamp(6);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (kEpi == EPI_BCE && threadIdx.x < 4 && p.epi.loss != nullptr && s_loss[threadIdx.x] != 0.f)
+    atomicAdd(p.epi.loss + threadIdx.x, s_loss[threadIdx.x]);
   if (warp == 2) ptx::tmem_dealloc(tmem_base, tmem_cols);
+  if (threadIdx.x == 64) stamp(7);
 }
 
 // ---------------------------------------------------------------- host side
@@ -451,48 +490,78 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   const int tiles_m = ceil_div(g.M, kBlockM);
   const int kb_total = ceil_div(g.K, BK);
 
-  // ---- tile width: fewest N tiles that still give the machine enough CTAs
-  int block_n = g.block_n;
+  // ---- tile width / split-K / pipeline depth from a small cost model fitted to measured sweeps on B200
+  // (tools/gemm_sweep.py): these problems are bound by L2->SM operand streaming (~77 GB/s per SM, ~10 TB/s
+  // chip-wide), not by the tensor pipe, and the epilogue of one CTA only overlaps with the main loop of
+  // ANOTHER CTA on the same SM - so shallow rings (2 stages) with 2-3 co-resident CTAs beat deep rings.
+  const bool atomic = e.kind == EPI_ATOMIC;
+  const int sms = 148;
+  auto plan_for = [&](int bn, int& split_o, int& stages_o, int& dyn_o, int& bstage_o, int& btx_o) -> double {
+    const int tn = ceil_div(g.N, bn);
+    const long long tiles = static_cast<long long>(tiles_m) * tn;
+    int split = g.split_k;
+    if (!atomic) split = 1;
+    if (split <= 0) split = ceil_div(env_int("MVAE_GEMM_SPLIT_TARGET", 148), tiles);
+    if (split > kb_total) split = kb_total;
+    if (split < 1) split = 1;
+    const int kbps = ceil_div(kb_total, split);
+    split = ceil_div(kb_total, kbps);
+    const long long ctas = tiles * split;
+    const int b_boxes = ceil_div(bn, BK);
+    const int b_tx = g.b_mn ? b_boxes * BK * 128 : bn * 128;
+    const int b_stage = (b_tx + 1023) / 1024 * 1024;
+    const int stage_bytes = kAStageBytes + b_stage;
+    const int staging = kBlockM * (bn + kStagePad) * 4;
+    int stages = g.stages > 0 ? g.stages : env_int("MVAE_GEMM_STAGES", ctas > sms ? 2 : 4);
+    if (stages > kbps) stages = kbps;
+    if (stages > kMaxStages) stages = kMaxStages;
+    const int max_dyn = 227 * 1024 - 2048;
+    while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
+    int dyn = stages * stage_bytes;
+    if (dyn < staging) dyn = staging;
+    dyn += 1024;
+    split_o = split; stages_o = stages; dyn_o = dyn; bstage_o = b_stage; btx_o = b_tx;
+    if (dyn > max_dyn + 1024) return 1e30;
+    int tmem_cols = 32;
+    while (tmem_cols < bn) tmem_cols <<= 1;
+    int occ = (227 * 1024) / (dyn + 1024);
+    if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    const double slots = static_cast<double>(sms) * occ;
+    const double waves = static_cast<double>((ctas + static_cast<long long>(slots) - 1) / static_cast<long long>(slots));
+    // operand bytes streamed from L2 by all CTAs
+    const double bytes = (static_cast<double>(tn) * g.M + static_cast<double>(tiles_m) * tn * bn) * g.K * esz;
+    const double active_sms = ctas < sms ? static_cast<double>(ctas) : static_cast<double>(sms);
+    const double t_load = bytes / (77e9 * active_sms) * 1e6;            // us
+    const double t_epi = (0.35 + 0.0105 * bn) * (atomic ? 1.3 : 1.0);   // us per CTA
+    const double per_sm_ctas = static_cast<double>(ctas) / active_sms;
+    // with co-residency the epilogues hide behind other CTAs' loads; one epilogue is always exposed
+    const double t_epi_total = occ > 1 ? t_epi * (1.0 + 0.35 * (per_sm_ctas - 1.0)) : t_epi * per_sm_ctas;
+    const double quant = waves * slots / static_cast<double>(ctas);     // tail-wave inefficiency
+    return (t_load * (ctas > sms ? (0.5 + 0.5 * quant) : 1.0)) + t_epi_total + 1.2;
+  };
+  int block_n = g.block_n, split = 1, stages = 2, dyn = 0, b_stage = 0, b_tx = 0;
   if (block_n <= 0) {
-    const int target_ctas = env_int("MVAE_GEMM_TARGET_CTAS", 120);
-    int nt = ceil_div(g.N, 256);
-    for (;; ++nt) {
-      block_n = 16 * ceil_div(ceil_div(g.N, nt), 16);
-      int splits_possible = (e.kind == EPI_ATOMIC) ? kb_total : 1;
-      if (static_cast<long long>(tiles_m) * nt * splits_possible >= target_ctas) break;
-      if (block_n <= 48) break;
+    double best = 1e30;
+    const int n_cap = 16 * ceil_div(g.N, 16);
+    for (int bn = 32; bn <= 256; bn += 16) {
+      if (bn > n_cap && bn != 32) break;
+      int sp, st, dy, bs, bt;
+      const double t = plan_for(bn, sp, st, dy, bs, bt);
+      if (t < best) {
+        best = t;
+        block_n = bn;
+      }
     }
   }
   MVAE_REQUIRE(block_n >= 16 && block_n <= 256 && block_n % 16 == 0, "gemm: block_n %d invalid", block_n);
+  MVAE_REQUIRE(plan_for(block_n, split, stages, dyn, b_stage, b_tx) < 1e29, "gemm: tile %d does not fit in shared memory", block_n);
   const int tiles_n = ceil_div(g.N, block_n);
-
-  // ---- split-K (wgrad): enough CTAs to cover the chip about once
-  int split = g.split_k;
-  if (e.kind != EPI_ATOMIC) split = 1;
-  if (split <= 0) {
-    const int target = env_int("MVAE_GEMM_SPLIT_TARGET", 148);
-    split = ceil_div(target, static_cast<long long>(tiles_m) * tiles_n);
-  }
-  if (split > kb_total) split = kb_total;
-  if (split < 1) split = 1;
   const int kb_per_split = ceil_div(kb_total, split);
-  split = ceil_div(kb_total, kb_per_split);
-
-  // ---- smem ring
-  const int b_boxes = ceil_div(block_n, BK);
-  const int b_tx = g.b_mn ? b_boxes * BK * 128 : block_n * 128;
-  const int b_stage = (b_tx + 1023) / 1024 * 1024;
-  const int stage_bytes = kAStageBytes + b_stage;
-  const int staging = kBlockM * (block_n + kStagePad) * 4;
-  int stages = g.stages > 0 ? g.stages : env_int("MVAE_GEMM_STAGES", 4);
-  if (stages > kb_per_split) stages = kb_per_split;
-  if (stages > kMaxStages) stages = kMaxStages;
-  const int max_dyn = 227 * 1024 - 2048;
-  while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
-  int dyn = stages * stage_bytes;
-  if (dyn < staging) dyn = staging;
-  dyn += 1024;
-  MVAE_REQUIRE(dyn <= max_dyn + 1024, "gemm: smem %d too large", dyn);
+  if (env_int("MVAE_GEMM_VERBOSE", 0))
+    fprintf(stderr, "[mvae gemm] %dx%dx%d kind=%d epi=%d a_mn=%d b_mn=%d -> block_n=%d split=%d stages=%d smem=%d grid=%dx%dx%d\n",
+            g.M, g.N, g.K, g.kind, e.kind, g.a_mn, g.b_mn, block_n, split, stages, dyn, tiles_n, tiles_m, split);
 
   CUtensorMap ta, tb;
   if (!g.a_mn) {
@@ -517,6 +586,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.b_tx_bytes = b_tx;
   kp.epi = e;
   kp.stat_group_stride = (e.kind == EPI_BCE) ? 0 : g.N;
+  kp.dbg = g.dbg;
   auto al = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   const int ea = 16 / 4 * (e.c_dtype == MVAE_F32 ? 4 : 2);  // bytes for a 4-element vector of C
   bool vec = (e.ldc % 4 == 0) && al(e.C, ea) && al(e.probs, ea);

@@ -1,0 +1,884 @@
+// The memory-bound "tail" of the MVAE step, one fused kernel per direction:
+//
+//   forward : encoder outputs -> ProductOfExperts (all ELBO terms at once: joint / image-only /
+//             text-only) -> reparametrize -> z for the decoders, KL partials, and the text
+//             decoder's first Linear (its input z is already in registers).
+//   backward: dz (from the image decoder dgrad) + the text decoder's BatchNorm/Linear backward ->
+//             reparametrize / KL / PoE backward -> gradient at the encoder outputs, summed over terms.
+//
+// One warp owns one sample (row) for ALL terms, lanes own latent pairs (float2, coalesced 256 B per
+// row for n = 64), warp shuffles reduce across the latent axis, shared-memory atomics reduce across
+// the rows of a block, one global atomic per address per block finishes.
+//
+// Reference: ProductOfExperts mnist/model.py:173-185, reparametrize :24-30, forward :53-84,
+// KL term of loss_function mnist/train.py:79-80, TextDecoder first Linear mnist/model.py:162.
+// Also here: the small text-side kernels (TextEncoder mnist/model.py:138-153 evaluated per label,
+// TextDecoder BN/ReLU/Linear/log_softmax :163-170 with the NLL of mnist/train.py:73) and the
+// standalone masked ProductOfExperts op.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "../../include/mvae_b200.h"
+
+namespace mvae {
+
+namespace {
+
+constexpr int kTailThreads = 256;
+constexpr int kTailWarps = kTailThreads / 32;
+constexpr int kTD = 10;  // text decoder width / number of classes
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// Two standard normals for element pair `pair_index` of the step.
+__device__ __forceinline__ float2 normal_pair(unsigned long long seed, uint32_t step, unsigned long long pair_index) {
+  uint32_t r[4];
+  philox4x32(static_cast<uint32_t>(pair_index), static_cast<uint32_t>(pair_index >> 32), step, 0x6d766165u,
+             static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float u1 = (static_cast<float>(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(rad * c, rad * s);
+}
+
+// ---------------------------------------------------------------- PoE on one latent element, M <= 2 experts
+// Everything the backward needs is kept so that no transcendental is evaluated twice:
+// exp(logvar) == pd_var and exp(logvar/2) == sqrt(pd_var) by construction.
+struct Poe {
+  float mu, logvar, pd_var;
+  float var[2], inv[2];  // var_i = exp(logvar_i) + eps, 1/var_i
+  float invS;            // REF: 1/sum(var_i); PRECISION: 1/sum(1/var_i) (+1 with the prior expert)
+};
+// present[i]: expert i takes part.  REF: mnist/model.py:180-185 (variance-weighted mu).
+template <bool kNeedLogvar>
+__device__ __forceinline__ Poe poe_eval(int mode, int prior, float eps, const float (&m)[2], const float (&lv)[2],
+                                        const bool (&present)[2]) {
+  Poe r;
+  r.var[0] = r.var[1] = 1.f;
+  r.inv[0] = r.inv[1] = 1.f;
+  float num = 0.f, S = 0.f, P = (mode == MVAE_POE_PRECISION && prior) ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (present[i]) {
+      const float var = expf(lv[i]) + eps;
+      const float inv = 1.f / var;
+      r.var[i] = var;
+      r.inv[i] = inv;
+      num += m[i] * (mode == MVAE_POE_REF ? var : inv);
+      S += var;
+      P += inv;
+    }
+  r.pd_var = 1.f / P;
+  if (mode == MVAE_POE_REF) {
+    r.invS = 1.f / S;
+    r.mu = num * r.invS;
+  } else {
+    r.invS = r.pd_var;
+    r.mu = num * r.pd_var;
+  }
+  r.logvar = kNeedLogvar ? logf(r.pd_var) : 0.f;
+  return r;
+}
+// Gradients w.r.t. expert i's (mu_i, logvar_i) given d(mu), d(logvar) of the product.
+__device__ __forceinline__ void poe_grad(int mode, float eps, const Poe& r, int i, float m_i, float dmu, float dlv,
+                                         float& dm_i, float& dlv_i) {
+  const float e = r.var[i] - eps;  // d var_i / d logvar_i = exp(logvar_i) (the eps is additive)
+  if (mode == MVAE_POE_REF) {
+    dm_i = dmu * r.var[i] * r.invS;
+    const float dvar = dmu * (m_i - r.mu) * r.invS + dlv * r.pd_var * r.inv[i] * r.inv[i];
+    dlv_i = dvar * e;
+  } else {
+    dm_i = dmu * r.inv[i] * r.invS;
+    const float dT = (dmu * (m_i - r.mu) - dlv) * r.invS;
+    dlv_i = -dT * r.inv[i] * r.inv[i] * e;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_pair(T* p, float a, float b) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
+  } else {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+  }
+}
+
+// ================================================================= tail forward
+// One warp per (term, sample): lanes own latent pairs.
+template <typename ZT>
+__global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a) {
+  __shared__ float s_stat[kMaxGroups][2][kTD];
+  __shared__ float s_kl[kMaxGroups];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kMaxGroups * 2 * kTD; i += blockDim.x) (&s_stat[0][0][0])[i] = 0.f;
+  if (threadIdx.x < kMaxGroups) s_kl[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const int n = a.n, two_n = 2 * a.n;
+  const uint32_t step = a.step_ptr != nullptr ? static_cast<uint32_t>(*a.step_ptr) : 0u;
+  const long long items = static_cast<long long>(a.G) * a.B;
+
+  for (long long it = blockIdx.x * kTailWarps + warp; it < items; it += static_cast<long long>(gridDim.x) * kTailWarps) {
+    const int g = static_cast<int>(it / a.B);
+    const int b = static_cast<int>(it - static_cast<long long>(g) * a.B);
+    const int ty = a.group_type[g];
+    const bool present[2] = {ty != TERM_TEXT, ty != TERM_IMAGE};
+    const int label = present[1] ? static_cast<int>(a.labels[b]) : 0;
+    float t1[kTD];
+#pragma unroll
+    for (int j = 0; j < kTD; ++j) t1[j] = 0.f;
+    float klacc = 0.f;
+    for (int k = lane * 2; k < n; k += 64) {
+      float mi[2] = {0.f, 0.f}, li[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f}, lt[2] = {0.f, 0.f};
+      if (present[0]) {
+        const float2 m2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + k);
+        const float2 l2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + n + k);
+        mi[0] = m2.x; mi[1] = m2.y; li[0] = l2.x; li[1] = l2.y;
+      }
+      if (present[1]) {
+        const float2 m2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + k);
+        const float2 l2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + n + k);
+        mt[0] = m2.x; mt[1] = m2.y; lt[0] = l2.x; lt[1] = l2.y;
+      }
+      float2 e2 = make_float2(0.f, 0.f);
+      if (a.training) {
+        if (a.eps != nullptr)
+          e2 = *reinterpret_cast<const float2*>(a.eps + it * n + k);
+        else
+          e2 = normal_pair(a.seed, step, (it * n + k) >> 1);
+      }
+      const float ee[2] = {e2.x, e2.y};
+      float zz[2], mm[2], ll[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float m[2] = {mi[c], mt[c]};
+        const float lv[2] = {li[c], lt[c]};
+        const Poe r = poe_eval<true>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
+        mm[c] = r.mu;
+        ll[c] = r.logvar;
+        // reparametrize (mnist/model.py:25-28): std = exp(0.5*logvar) = sqrt(pd_var); z = eps*std + mu
+        zz[c] = a.training ? ee[c] * sqrtf(r.pd_var) + r.mu : r.mu;
+        // KL integrand of mnist/train.py:79 (exp(logvar) = pd_var)
+        klacc += 1.f + r.logvar - r.mu * r.mu - r.pd_var;
+      }
+      store_pair(reinterpret_cast<ZT*>(a.z) + it * n + k, zz[0], zz[1]);
+      if (a.mu != nullptr) {
+        *reinterpret_cast<float2*>(a.mu + it * n + k) = make_float2(mm[0], mm[1]);
+        *reinterpret_cast<float2*>(a.logvar + it * n + k) = make_float2(ll[0], ll[1]);
+      }
+      if (a.wt1 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) {
+          const float2 w = *reinterpret_cast<const float2*>(a.wt1 + j * n + k);
+          t1[j] = fmaf(zz[0], w.x, fmaf(zz[1], w.y, t1[j]));
+        }
+      }
+    }
+    if (a.wt1 != nullptr) {
+      float mine = 0.f;
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) {
+        const float sum = warp_sum(t1[j]);
+        if (lane == j) mine = sum;
+      }
+      if (lane < kTD) {
+        const float v = mine + a.bt1[lane];
+        a.t1pre[it * kTD + lane] = v;
+        atomicAdd(&s_stat[g][0][lane], v);
+        atomicAdd(&s_stat[g][1][lane], v * v);
+      }
+    }
+    const float ks = warp_sum(klacc);
+    if (lane == 0) atomicAdd(&s_kl[g], ks);
+  }
+  __syncthreads();
+  if (a.wt1 != nullptr)
+    for (int i = threadIdx.x; i < a.G * 2 * kTD; i += blockDim.x) {
+      const int g = i / (2 * kTD), w = (i / kTD) % 2, j = i % kTD;
+      if (s_stat[g][w][j] != 0.f) atomicAdd((w == 0 ? a.t1_sum : a.t1_sumsq) + g * kTD + j, s_stat[g][w][j]);
+    }
+  if (threadIdx.x < a.G && a.kl != nullptr && s_kl[threadIdx.x] != 0.f)
+    atomicAdd(a.kl + threadIdx.x, -0.5f * a.kl_weight[threadIdx.x] * s_kl[threadIdx.x]);
+}
+
+// ================================================================= tail backward
+// Block = kBwdRows samples x G terms, one warp per (sample, term); the terms' contributions to one sample's
+// encoder-output gradient are combined through shared memory (no global atomics on activations).
+constexpr int kBwdRows = 4;
+template <typename ZT>
+__global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows) tail_bwd_kernel(const TailArgs a, int smem_floats) {
+  extern __shared__ float sm[];
+  // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] | combine [rows][G][2n]
+  const int n = a.n, two_n = 2 * a.n;
+  float* s_tab = sm;
+  float* s_w1 = s_tab + kTD * two_n;
+  float* s_eb = s_w1 + kTD * n;
+  float* s_co = s_eb + two_n;  // per group: mean, rstd, c0 = S0/B, c1 = S1/B
+  float* s_cb = s_co + kMaxGroups * 4 * kTD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.G;
+  const int wrow = warp / G, g = warp - wrow * G;
+  for (int i = threadIdx.x; i < smem_floats; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const bool text_dec = a.t1_dyhat != nullptr;
+  if (text_dec && threadIdx.x < G * kTD) {
+    const int gg = threadIdx.x / kTD, j = threadIdx.x % kTD;
+    const float mean = a.t1_sum[gg * kTD + j] / a.B;
+    const float var = fmaxf(a.t1_sumsq[gg * kTD + j] / a.B - mean * mean, 0.f);
+    s_co[(gg * 4 + 0) * kTD + j] = mean;
+    s_co[(gg * 4 + 1) * kTD + j] = rsqrtf(var + 1e-5f);
+    s_co[(gg * 4 + 2) * kTD + j] = a.t1_s0[gg * kTD + j] / a.B;
+    s_co[(gg * 4 + 3) * kTD + j] = a.t1_s1[gg * kTD + j] / a.B;
+  }
+  __syncthreads();
+  const uint32_t step = a.step_ptr != nullptr ? static_cast<uint32_t>(*a.step_ptr) : 0u;
+  const int ty = a.group_type[g];
+  const bool present[2] = {ty != TERM_TEXT, ty != TERM_IMAGE};
+  const float c_kl = a.kl_weight[g];
+
+  // Per-lane register accumulators for the latent pair of the first 64-column pass (covers n <= 64 entirely);
+  // later passes (n > 64) fall back to shared atomics.
+  float r_w1[kTD][2], r_eb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) r_w1[j][0] = r_w1[j][1] = 0.f;
+
+  const int row_blocks = (a.B + kBwdRows - 1) / kBwdRows;
+  for (int rb = blockIdx.x; rb < row_blocks; rb += gridDim.x) {
+    const int b = rb * kBwdRows + wrow;
+    const bool active = b < a.B;
+    const long long row = static_cast<long long>(g) * a.B + b;
+    if (active) {
+      const int label = present[1] ? static_cast<int>(a.labels[b]) : 0;
+      // text decoder: gradient at its first Linear's output (BatchNorm backward apply); every lane computes all ten
+      float dtb[kTD];
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) {
+        dtb[j] = 0.f;
+        if (text_dec) {
+          const float x = a.t1pre[row * kTD + j];
+          const float xh = (x - s_co[(g * 4 + 0) * kTD + j]) * s_co[(g * 4 + 1) * kTD + j];
+          const float dy = a.t1_dyhat[row * kTD + j];
+          dtb[j] = a.t1_gamma[j] * s_co[(g * 4 + 1) * kTD + j] *
+                   (dy - s_co[(g * 4 + 2) * kTD + j] - xh * s_co[(g * 4 + 3) * kTD + j]);
+        }
+      }
+      for (int k = lane * 2; k < n; k += 64) {
+        const bool first_pass = k < 64;
+        float mi[2] = {0.f, 0.f}, li[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f}, lt[2] = {0.f, 0.f};
+        if (present[0]) {
+          const float2 m2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + k);
+          const float2 l2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + n + k);
+          mi[0] = m2.x; mi[1] = m2.y; li[0] = l2.x; li[1] = l2.y;
+        }
+        if (present[1]) {
+          const float2 m2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + k);
+          const float2 l2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + n + k);
+          mt[0] = m2.x; mt[1] = m2.y; lt[0] = l2.x; lt[1] = l2.y;
+        }
+        float2 e2 = make_float2(0.f, 0.f);
+        if (a.training) {
+          if (a.eps != nullptr)
+            e2 = *reinterpret_cast<const float2*>(a.eps + row * n + k);
+          else
+            e2 = normal_pair(a.seed, step, (row * n + k) >> 1);
+        }
+        const float ee[2] = {e2.x, e2.y};
+        float2 dz2 = make_float2(0.f, 0.f);
+        if (a.dz != nullptr) dz2 = *reinterpret_cast<const float2*>(a.dz + row * n + k);
+        float dzz[2] = {dz2.x, dz2.y};
+        Poe r[2];
+        float zz[2], sd[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float m[2] = {mi[c], mt[c]};
+          const float lv[2] = {li[c], lt[c]};
+          r[c] = poe_eval<false>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
+          sd[c] = sqrtf(r[c].pd_var);
+          zz[c] = a.training ? ee[c] * sd[c] + r[c].mu : r[c].mu;
+        }
+        // text decoder first Linear: dz += dT1 * Wt1, dWt1 += dT1^T z
+        if (text_dec) {
+#pragma unroll
+          for (int j = 0; j < kTD; ++j) {
+            const float dj = dtb[j];
+            const float2 w = *reinterpret_cast<const float2*>(a.wt1 + j * n + k);
+            dzz[0] = fmaf(dj, w.x, dzz[0]);
+            dzz[1] = fmaf(dj, w.y, dzz[1]);
+            if (first_pass) {
+              r_w1[j][0] = fmaf(dj, zz[0], r_w1[j][0]);
+              r_w1[j][1] = fmaf(dj, zz[1], r_w1[j][1]);
+            } else {
+              atomicAdd(&s_w1[j * n + k], dj * zz[0]);
+              atomicAdd(&s_w1[j * n + k + 1], dj * zz[1]);
+            }
+          }
+        }
+        float2 dmu_up = make_float2(0.f, 0.f), dlv_up = make_float2(0.f, 0.f);
+        if (a.dmu_up != nullptr) dmu_up = *reinterpret_cast<const float2*>(a.dmu_up + row * n + k);
+        if (a.dlogvar_up != nullptr) dlv_up = *reinterpret_cast<const float2*>(a.dlogvar_up + row * n + k);
+        const float dmu_u[2] = {dmu_up.x, dmu_up.y}, dlv_u[2] = {dlv_up.x, dlv_up.y};
+        float d_mi[2] = {0.f, 0.f}, d_li[2] = {0.f, 0.f}, d_mt[2] = {0.f, 0.f}, d_lt[2] = {0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          // z = mu + eps*exp(logvar/2);  KL = c * -0.5 * sum(1 + logvar - mu^2 - exp(logvar))
+          const float dmu = dzz[c] + dmu_u[c] + c_kl * r[c].mu;
+          float dlv = dlv_u[c] + 0.5f * c_kl * (r[c].pd_var - 1.f);
+          if (a.training) dlv += dzz[c] * 0.5f * ee[c] * sd[c];
+          if (present[0]) poe_grad(a.poe_mode, a.poe_eps, r[c], 0, mi[c], dmu, dlv, d_mi[c], d_li[c]);
+          if (present[1]) poe_grad(a.poe_mode, a.poe_eps, r[c], 1, mt[c], dmu, dlv, d_mt[c], d_lt[c]);
+        }
+        if (present[0]) {
+          float* cb = s_cb + (wrow * kMaxGroups + g) * two_n;
+          cb[k] = d_mi[0]; cb[k + 1] = d_mi[1]; cb[n + k] = d_li[0]; cb[n + k + 1] = d_li[1];
+        }
+        if (present[1] && a.d_txt_table != nullptr) {
+          atomicAdd(&s_tab[label * two_n + k], d_mt[0]);
+          atomicAdd(&s_tab[label * two_n + k + 1], d_mt[1]);
+          atomicAdd(&s_tab[label * two_n + n + k], d_lt[0]);
+          atomicAdd(&s_tab[label * two_n + n + k + 1], d_lt[1]);
+        }
+      }
+    }
+    __syncthreads();
+    // combine the terms' contributions to this sample's image-expert gradient (warp g == 0 of each sample)
+    if (active && g == 0 && a.enc_img != nullptr && a.d_enc != nullptr) {
+      ZT* de = reinterpret_cast<ZT*>(a.d_enc) + static_cast<long long>(b) * two_n;
+      for (int k = lane * 2; k < n; k += 64) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int gg = 0; gg < G; ++gg) {
+          if (a.group_type[gg] == TERM_TEXT) continue;
+          const float* cb = s_cb + (wrow * kMaxGroups + gg) * two_n;
+          v[0] += cb[k]; v[1] += cb[k + 1]; v[2] += cb[n + k]; v[3] += cb[n + k + 1];
+        }
+        store_pair(de + k, v[0], v[1]);
+        store_pair(de + n + k, v[2], v[3]);
+        if (k < 64) {
+          r_eb[0] += v[0]; r_eb[1] += v[1]; r_eb[2] += v[2]; r_eb[3] += v[3];
+        } else {
+          atomicAdd(&s_eb[k], v[0]);
+          atomicAdd(&s_eb[k + 1], v[1]);
+          atomicAdd(&s_eb[n + k], v[2]);
+          atomicAdd(&s_eb[n + k + 1], v[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  {
+    const int k = lane * 2;
+    if (k < n) {
+      if (text_dec) {
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) {
+          atomicAdd(&s_w1[j * n + k], r_w1[j][0]);
+          atomicAdd(&s_w1[j * n + k + 1], r_w1[j][1]);
+        }
+      }
+      if (g == 0) {
+        atomicAdd(&s_eb[k], r_eb[0]);
+        atomicAdd(&s_eb[k + 1], r_eb[1]);
+        atomicAdd(&s_eb[n + k], r_eb[2]);
+        atomicAdd(&s_eb[n + k + 1], r_eb[3]);
+      }
+    }
+  }
+  __syncthreads();
+  if (a.d_txt_table != nullptr)
+    for (int i = threadIdx.x; i < kTD * two_n; i += blockDim.x)
+      if (s_tab[i] != 0.f) atomicAdd(a.d_txt_table + i, s_tab[i]);
+  if (text_dec && a.d_wt1 != nullptr)
+    for (int i = threadIdx.x; i < kTD * n; i += blockDim.x) atomicAdd(a.d_wt1 + i, s_w1[i]);
+  if (a.d_enc_bias != nullptr && a.enc_img != nullptr)
+    for (int i = threadIdx.x; i < two_n; i += blockDim.x) atomicAdd(a.d_enc_bias + i, s_eb[i]);
+  // BatchNorm affine gradients of the text decoder: dgamma = sum_g S1, dbeta = sum_g S0 (block 0 only)
+  if (text_dec && blockIdx.x == 0 && threadIdx.x < kTD && a.d_t1_gamma != nullptr) {
+    float dg = 0.f, db = 0.f;
+    for (int gg = 0; gg < G; ++gg) {
+      dg += a.t1_s1[gg * kTD + threadIdx.x];
+      db += a.t1_s0[gg * kTD + threadIdx.x];
+    }
+    a.d_t1_gamma[threadIdx.x] += dg;
+    a.d_t1_beta[threadIdx.x] += db;
+  }
+}
+
+// ================================================================= text decoder (BN -> ReLU -> Linear -> log_softmax -> NLL)
+// One thread per decoder row.  Forward + (optionally) the fused NLL loss and the backward down to the
+// BatchNorm output: dyhat, its two per-group column sums, and the gradients of the second Linear.
+__global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
+  __shared__ float s_mean[kMaxGroups][kTD], s_rstd[kMaxGroups][kTD];
+  __shared__ float s_w2[kTD][kTD], s_b2[kTD], s_gamma[kTD], s_beta[kTD];
+  __shared__ float s_dw2[kTD][kTD], s_db2[kTD], s_s0[kMaxGroups][kTD], s_s1[kMaxGroups][kTD], s_ce[kMaxGroups];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid < a.G * kTD) {
+    const int g = tid / kTD, j = tid % kTD;
+    float mean, rstd;
+    if (a.training) {
+      mean = a.t1_sum[tid] / a.B;
+      const float var = fmaxf(a.t1_sumsq[tid] / a.B - mean * mean, 0.f);
+      rstd = rsqrtf(var + a.bn_eps);
+    } else {
+      mean = a.running_mean[j];
+      rstd = rsqrtf(a.running_var[j] + a.bn_eps);
+    }
+    s_mean[g][j] = mean;
+    s_rstd[g][j] = rstd;
+  }
+  if (tid < kTD * kTD) {
+    s_w2[tid / kTD][tid % kTD] = a.w2[tid];
+    s_dw2[tid / kTD][tid % kTD] = 0.f;
+  }
+  if (tid < kTD) {
+    s_b2[tid] = a.b2[tid];
+    s_gamma[tid] = a.gamma[tid];
+    s_beta[tid] = a.beta[tid];
+    s_db2[tid] = 0.f;
+  }
+  if (tid < kMaxGroups * kTD) {
+    (&s_s0[0][0])[tid] = 0.f;
+    (&s_s1[0][0])[tid] = 0.f;
+  }
+  if (tid < kMaxGroups) s_ce[tid] = 0.f;
+  __syncthreads();
+  // running statistics: one update per group, in group order (block 0)
+  if (a.training && blockIdx.x == 0 && tid < kTD && a.running_mean != nullptr) {
+    float rm = a.running_mean[tid], rv = a.running_var[tid];
+    for (int g = 0; g < a.G; ++g) {
+      const float mean = s_mean[g][tid];
+      const float var = fmaxf(a.t1_sumsq[g * kTD + tid] / a.B - mean * mean, 0.f);
+      const float unb = a.B > 1 ? var * (static_cast<float>(a.B) / (a.B - 1)) : var;
+      rm = (1.f - a.momentum) * rm + a.momentum * mean;
+      rv = (1.f - a.momentum) * rv + a.momentum * unb;
+    }
+    a.running_mean[tid] = rm;
+    a.running_var[tid] = rv;
+  }
+  const long long rows = static_cast<long long>(a.G) * a.B;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x) + tid;
+  const bool valid = row < rows;
+  const int g = valid ? static_cast<int>(row / a.B) : 0;
+  float xh[kTD], t1[kTD], lp[kTD], dl[kTD], dy[kTD];
+  float ce = 0.f;
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) xh[j] = t1[j] = lp[j] = dl[j] = dy[j] = 0.f;
+  if (valid) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kTD; ++j) {
+      xh[j] = (a.t1pre[row * kTD + j] - s_mean[g][j]) * s_rstd[g][j];
+      t1[j] = fmaxf(fmaf(s_gamma[j], xh[j], s_beta[j]), 0.f);
+    }
+#pragma unroll
+    for (int o = 0; o < kTD; ++o) {
+      float acc = s_b2[o];
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) acc = fmaf(s_w2[o][j], t1[j], acc);
+      lp[o] = acc;
+      mx = fmaxf(mx, acc);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int o = 0; o < kTD; ++o) se += expf(lp[o] - mx);
+    const float lse = mx + logf(se);
+#pragma unroll
+    for (int o = 0; o < kTD; ++o) lp[o] -= lse;  // log_softmax (mnist/model.py:170)
+    if (a.logp != nullptr) {
+#pragma unroll
+      for (int o = 0; o < kTD; ++o) a.logp[row * kTD + o] = lp[o];
+    }
+    if (a.backward) {
+      if (a.fused_loss) {
+        const int label = static_cast<int>(a.labels[row % a.B]);
+        const float sc = a.ce_scale[g];
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) {
+          dl[o] = sc * (expf(lp[o]) - (o == label ? 1.f : 0.f));
+          if (o == label) ce = -sc * lp[o];  // F.nll_loss mean (mnist/train.py:73)
+        }
+      } else {
+        float su = 0.f;
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) su += a.dlogp_up[row * kTD + o];
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) dl[o] = a.dlogp_up[row * kTD + o] - expf(lp[o]) * su;
+      }
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int o = 0; o < kTD; ++o) acc = fmaf(dl[o], s_w2[o][j], acc);
+        dy[j] = t1[j] > 0.f ? acc : 0.f;
+        a.dyhat[row * kTD + j] = dy[j];
+      }
+    }
+  }
+  if (a.backward) {
+    // block-level reductions: warp shuffle, then one shared atomic per warp per value
+#pragma unroll
+    for (int o = 0; o < kTD; ++o) {
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) {
+        const float s = warp_sum(dl[o] * t1[j]);
+        if (lane == 0) atomicAdd(&s_dw2[o][j], s);
+      }
+      const float sb = warp_sum(dl[o]);
+      if (lane == 0) atomicAdd(&s_db2[o], sb);
+    }
+    // a warp may straddle a group boundary: reduce per group with a mask on the group id
+    for (int gg = 0; gg < a.G; ++gg) {
+      const bool mine = valid && g == gg;
+      if (__any_sync(0xffffffffu, mine)) {
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) {
+          const float s0 = warp_sum(mine ? dy[j] : 0.f);
+          const float s1 = warp_sum(mine ? dy[j] * xh[j] : 0.f);
+          if (lane == 0) {
+            atomicAdd(&s_s0[gg][j], s0);
+            atomicAdd(&s_s1[gg][j], s1);
+          }
+        }
+        const float c = warp_sum(mine ? ce : 0.f);
+        if (lane == 0) atomicAdd(&s_ce[gg], c);
+      }
+    }
+    __syncthreads();
+    if (tid < kTD * kTD && a.d_w2 != nullptr) atomicAdd(a.d_w2 + tid, s_dw2[tid / kTD][tid % kTD]);
+    if (tid < kTD && a.d_b2 != nullptr) atomicAdd(a.d_b2 + tid, s_db2[tid]);
+    if (tid < a.G * kTD) {
+      atomicAdd(a.s0 + tid, (&s_s0[0][0])[tid]);
+      atomicAdd(a.s1 + tid, (&s_s1[0][0])[tid]);
+    }
+    if (tid < a.G && a.ce != nullptr && a.fused_loss) atomicAdd(a.ce + tid, s_ce[tid]);
+  }
+}
+
+// ================================================================= text encoder, evaluated per LABEL
+// Embedding(10,50) -> BatchNorm1d(50) -> ReLU -> Linear(50, 2n) has only ten distinct inputs, so the batch
+// statistics are count-weighted sums over the ten embedding rows and the output is a [10, 2n] table the tail
+// kernel gathers from.  Single block.
+constexpr int kEmb = 50;
+__global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
+  __shared__ float s_cnt[kTD];
+  __shared__ float s_h[kTD][kEmb];
+  float* sv_cnt = a.save;
+  float* sv_xh = a.save + kTD;
+  float* sv_h = sv_xh + kTD * kEmb;
+  float* sv_mean = sv_h + kTD * kEmb;
+  float* sv_rstd = sv_mean + kEmb;
+  const int tid = threadIdx.x;
+  if (tid < kTD) s_cnt[tid] = 0.f;
+  __syncthreads();
+  {
+    float local[kTD];
+#pragma unroll
+    for (int l = 0; l < kTD; ++l) local[l] = 0.f;
+    for (int i = tid; i < a.B; i += blockDim.x) {
+      const int lab = static_cast<int>(a.labels[i]);
+#pragma unroll
+      for (int l = 0; l < kTD; ++l) local[l] += (lab == l) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < kTD; ++l) {
+      const float s = warp_sum(local[l]);
+      if ((tid & 31) == 0) atomicAdd(&s_cnt[l], s);
+    }
+  }
+  __syncthreads();
+  if (tid < kTD) sv_cnt[tid] = s_cnt[tid];
+  if (tid < kEmb) {
+    const int f = tid;
+    float mean, rstd;
+    if (a.training) {
+      float s = 0.f;
+      for (int l = 0; l < kTD; ++l) s += s_cnt[l] * a.emb[l * kEmb + f];
+      mean = s / a.B;
+      float v = 0.f;
+      for (int l = 0; l < kTD; ++l) {
+        const float d = a.emb[l * kEmb + f] - mean;
+        v += s_cnt[l] * d * d;
+      }
+      const float var = v / a.B;
+      rstd = rsqrtf(var + a.bn_eps);
+      if (a.running_mean != nullptr) {
+        const float unb = a.B > 1 ? var * (static_cast<float>(a.B) / (a.B - 1)) : var;
+        float rm = a.running_mean[f], rv = a.running_var[f];
+        for (int u = 0; u < a.updates; ++u) {
+          rm = (1.f - a.momentum) * rm + a.momentum * mean;
+          rv = (1.f - a.momentum) * rv + a.momentum * unb;
+        }
+        a.running_mean[f] = rm;
+        a.running_var[f] = rv;
+      }
+    } else {
+      mean = a.running_mean[f];
+      rstd = rsqrtf(a.running_var[f] + a.bn_eps);
+    }
+    sv_mean[f] = mean;
+    sv_rstd[f] = rstd;
+    for (int l = 0; l < kTD; ++l) {
+      const float xh = (a.emb[l * kEmb + f] - mean) * rstd;
+      const float h = fmaxf(fmaf(a.gamma[f], xh, a.beta[f]), 0.f);
+      sv_xh[l * kEmb + f] = xh;
+      sv_h[l * kEmb + f] = h;
+      s_h[l][f] = h;
+    }
+  }
+  __syncthreads();
+  const int two_n = 2 * a.n;
+  for (int i = tid; i < kTD * two_n; i += blockDim.x) {
+    const int l = i / two_n, o = i % two_n;
+    float acc = a.b[o];
+    for (int f = 0; f < kEmb; ++f) acc = fmaf(s_h[l][f], a.w[o * kEmb + f], acc);
+    a.table[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256) textenc_bwd_kernel(const TextEncArgs a) {
+  __shared__ float s_dh[kTD][kEmb];
+  const float* sv_cnt = a.save;
+  const float* sv_xh = a.save + kTD;
+  const float* sv_h = sv_xh + kTD * kEmb;
+  const float* sv_rstd = sv_h + kTD * kEmb + kEmb;
+  const int tid = threadIdx.x;
+  const int two_n = 2 * a.n;
+  // Linear(50 -> 2n): dW[o][f] = sum_l dT[l][o] h[l][f]; db[o] = sum_l dT[l][o]; dh[l][f] = sum_o dT[l][o] W[o][f]
+  for (int i = tid; i < two_n * kEmb; i += blockDim.x) {
+    const int o = i / kEmb, f = i % kEmb;
+    float acc = 0.f;
+    for (int l = 0; l < kTD; ++l) acc = fmaf(a.d_table[l * two_n + o], sv_h[l * kEmb + f], acc);
+    a.d_w[i] += acc;
+  }
+  for (int o = tid; o < two_n; o += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < kTD; ++l) acc += a.d_table[l * two_n + o];
+    a.d_b[o] += acc;
+  }
+  for (int i = tid; i < kTD * kEmb; i += blockDim.x) {
+    const int l = i / kEmb, f = i % kEmb;
+    float acc = 0.f;
+    for (int o = 0; o < two_n; ++o) acc = fmaf(a.d_table[l * two_n + o], a.w[o * kEmb + f], acc);
+    s_dh[l][f] = sv_h[i] > 0.f ? acc : 0.f;  // ReLU mask; this is dyhat aggregated over the label's samples
+  }
+  __syncthreads();
+  if (tid < kEmb) {
+    const int f = tid;
+    float s0 = 0.f, s1 = 0.f;
+    for (int l = 0; l < kTD; ++l) {
+      s0 += s_dh[l][f];
+      s1 += s_dh[l][f] * sv_xh[l * kEmb + f];
+    }
+    a.d_gamma[f] += s1;
+    a.d_beta[f] += s0;
+    const float gr = a.gamma[f] * sv_rstd[f];
+    for (int l = 0; l < kTD; ++l) {
+      const float c = sv_cnt[l] / a.B;
+      a.d_emb[l * kEmb + f] += gr * (s_dh[l][f] - c * s0 - c * sv_xh[l * kEmb + f] * s1);
+    }
+  }
+}
+
+// ================================================================= standalone masked PoE
+__global__ void __launch_bounds__(256)
+    poe_fwd_kernel(int mode, int prior, float eps, int M, long long B, int D, const float* __restrict__ mu,
+                   const float* __restrict__ logvar, const float* __restrict__ mask, float* __restrict__ out_mu,
+                   float* __restrict__ out_logvar) {
+  const long long total = B * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / D;
+    float num = 0.f, S = (mode == MVAE_POE_PRECISION && prior) ? 1.f : 0.f, P = 0.f;
+    for (int e = 0; e < M; ++e) {
+      const float w = mask != nullptr ? mask[e * B + b] : 1.f;
+      if (w == 0.f) continue;
+      const float var = expf(logvar[e * total + i]) + eps;
+      if (mode == MVAE_POE_REF) {
+        num += mu[e * total + i] * var;
+        S += var;
+        P += 1.f / var;
+      } else {
+        const float t = w / var;
+        num += mu[e * total + i] * t;
+        S += t;
+      }
+    }
+    if (mode == MVAE_POE_REF) {
+      out_mu[i] = num / S;
+      const float pd_var = 1.f / P;
+      out_logvar[i] = logf(pd_var);
+    } else {
+      out_mu[i] = num / S;
+      out_logvar[i] = logf(1.f / S);
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+    poe_bwd_kernel(int mode, int prior, float eps, int M, long long B, int D, const float* __restrict__ mu,
+                   const float* __restrict__ logvar, const float* __restrict__ mask, const float* __restrict__ dom,
+                   const float* __restrict__ dol, float* __restrict__ dmu, float* __restrict__ dlv) {
+  const long long total = B * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / D;
+    float num = 0.f, S = (mode == MVAE_POE_PRECISION && prior) ? 1.f : 0.f, P = 0.f;
+    for (int e = 0; e < M; ++e) {
+      const float w = mask != nullptr ? mask[e * B + b] : 1.f;
+      if (w == 0.f) continue;
+      const float var = expf(logvar[e * total + i]) + eps;
+      if (mode == MVAE_POE_REF) {
+        num += mu[e * total + i] * var;
+        S += var;
+        P += 1.f / var;
+      } else {
+        const float t = w / var;
+        num += mu[e * total + i] * t;
+        S += t;
+      }
+    }
+    const float pm = num / S;
+    const float g_mu = dom != nullptr ? dom[i] : 0.f;
+    const float g_lv = dol != nullptr ? dol[i] : 0.f;
+    for (int e = 0; e < M; ++e) {
+      const float w = mask != nullptr ? mask[e * B + b] : 1.f;
+      float o_m = 0.f, o_l = 0.f;
+      if (w != 0.f) {
+        const float ex = expf(logvar[e * total + i]);
+        const float var = ex + eps;
+        if (mode == MVAE_POE_REF) {
+          o_m = g_mu * var / S;
+          const float dvar = g_mu * (mu[e * total + i] - pm) / S + g_lv / (P * var * var);
+          o_l = dvar * ex;
+        } else {
+          const float t = w / var;
+          o_m = g_mu * t / S;
+          const float dT = g_mu * (mu[e * total + i] - pm) / S - g_lv / S;
+          o_l = -dT * (w / (var * var)) * ex;
+        }
+      }
+      dmu[e * total + i] = o_m;
+      dlv[e * total + i] = o_l;
+    }
+  }
+}
+
+int check_tail(const TailArgs& a) {
+  MVAE_REQUIRE(a.B > 0 && a.n > 0 && a.n % 2 == 0, "tail: B=%d n=%d (n must be even)", a.B, a.n);
+  MVAE_REQUIRE(a.G >= 1 && a.G <= kMaxGroups, "tail: G=%d out of range", a.G);
+  for (int g = 0; g < a.G; ++g) {
+    const int t = a.group_type[g];
+    MVAE_REQUIRE(t >= 0 && t <= 2, "tail: bad term type %d", t);
+    MVAE_REQUIRE(t == TERM_TEXT || a.enc_img != nullptr, "tail: term %d needs the image expert", g);
+    MVAE_REQUIRE(t == TERM_IMAGE || (a.txt_table != nullptr && a.labels != nullptr), "tail: term %d needs the text expert", g);
+  }
+  return 0;
+}
+
+}  // namespace
+
+int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
+  if (check_tail(a)) return 1;
+  MVAE_REQUIRE(a.z != nullptr, "tail_forward: z output missing");
+  MVAE_REQUIRE(a.wt1 == nullptr || (a.bt1 && a.t1pre && a.t1_sum && a.t1_sumsq), "tail_forward: text decoder buffers missing");
+  const long long items = static_cast<long long>(a.G) * a.B;
+  int blocks = static_cast<int>(std::min<long long>((items + kTailWarps - 1) / kTailWarps, 148 * 8));
+  if (blocks < 1) blocks = 1;
+  if (a.z_dtype == MVAE_F32)
+    tail_fwd_kernel<float><<<blocks, kTailThreads, 0, st>>>(a);
+  else
+    tail_fwd_kernel<__nv_bfloat16><<<blocks, kTailThreads, 0, st>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
+  if (check_tail(a)) return 1;
+  const int smem_floats =
+      kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD + kBwdRows * kMaxGroups * 2 * a.n;
+  const int smem = smem_floats * 4;
+  MVAE_REQUIRE(smem <= 48 * 1024, "tail_backward: n=%d too large for the shared accumulators", a.n);
+  const int row_blocks = (a.B + kBwdRows - 1) / kBwdRows;
+  int blocks = std::min(row_blocks, 148 * 4);
+  const int threads = 32 * a.G * kBwdRows;
+  if (a.z_dtype == MVAE_F32)
+    tail_bwd_kernel<float><<<blocks, threads, smem, st>>>(a, smem_floats);
+  else
+    tail_bwd_kernel<__nv_bfloat16><<<blocks, threads, smem, st>>>(a, smem_floats);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
+  MVAE_REQUIRE(a.B > 0 && a.G >= 1 && a.G <= kMaxGroups, "textdec: B=%d G=%d", a.B, a.G);
+  MVAE_REQUIRE(a.t1pre && a.gamma && a.beta && a.w2 && a.b2, "textdec: missing inputs");
+  MVAE_REQUIRE(!a.training || (a.t1_sum && a.t1_sumsq), "textdec: batch statistics missing");
+  MVAE_REQUIRE(a.training || (a.running_mean && a.running_var), "textdec: running statistics missing");
+  if (a.backward) {
+    MVAE_REQUIRE(a.dyhat && a.s0 && a.s1, "textdec: backward outputs missing");
+    MVAE_REQUIRE(a.fused_loss ? a.labels != nullptr : a.dlogp_up != nullptr, "textdec: labels / upstream gradient missing");
+  }
+  const long long rows = static_cast<long long>(a.G) * a.B;
+  const int blocks = static_cast<int>((rows + 255) / 256);
+  textdec_kernel<<<blocks, 256, 0, st>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_textenc_forward(const TextEncArgs& a, cudaStream_t st) {
+  MVAE_REQUIRE(a.B > 0 && a.n > 0 && a.labels && a.emb && a.gamma && a.beta && a.w && a.b && a.table && a.save,
+               "textenc_forward: missing arguments");
+  textenc_fwd_kernel<<<1, 256, 0, st>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_textenc_backward(const TextEncArgs& a, cudaStream_t st) {
+  MVAE_REQUIRE(a.d_table && a.d_emb && a.d_gamma && a.d_beta && a.d_w && a.d_b && a.save && a.w && a.gamma,
+               "textenc_backward: missing arguments");
+  textenc_bwd_kernel<<<1, 256, 0, st>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_poe_forward(int mode, int prior, float eps, int M, long long B, int D, const float* mu, const float* logvar,
+                       const float* mask, float* out_mu, float* out_logvar, cudaStream_t st) {
+  MVAE_REQUIRE(M >= 1 && B > 0 && D > 0 && mu && logvar && out_mu && out_logvar, "poe_forward: bad arguments");
+  const long long total = B * D;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  poe_fwd_kernel<<<blocks, 256, 0, st>>>(mode, prior, eps, M, B, D, mu, logvar, mask, out_mu, out_logvar);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_poe_backward(int mode, int prior, float eps, int M, long long B, int D, const float* mu, const float* logvar,
+                        const float* mask, const float* d_out_mu, const float* d_out_logvar, float* d_mu,
+                        float* d_logvar, cudaStream_t st) {
+  MVAE_REQUIRE(M >= 1 && B > 0 && D > 0 && mu && logvar && d_mu && d_logvar, "poe_backward: bad arguments");
+  const long long total = B * D;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  poe_bwd_kernel<<<blocks, 256, 0, st>>>(mode, prior, eps, M, B, D, mu, logvar, mask, d_out_mu, d_out_logvar, d_mu,
+                                         d_logvar);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mvae

@@ -1,0 +1,349 @@
+"""MNIST MVAE on the B200-native library: module surface of the reference + the fused train step.
+
+Reference surface kept (mnist/model.py, mnist/train.py):
+    MVAE / MultimodalVAE(n_latents).forward(image=None, text=None) -> (recon_image, recon_text, mu, logvar)
+    state_dict keys identical to the reference's (image_encoder.net.0.weight, ...)
+The hot path is `MVAETrainer.step(image, text)`: ONE C-ABI call (mvae_mnist_step) that enqueues the whole
+three-term ELBO step - forward, backward, Adam - as hand-written sm_100a kernels, optionally replayed as a
+CUDA graph.  There is no PyTorch fallback: without the CUDA library every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+TERMS = {"joint": _lib.TERM_JOINT, "image": _lib.TERM_IMAGE, "text": _lib.TERM_TEXT}
+_DTYPES = {"tf32": _lib.DT_F32, "fp32": _lib.DT_F32, "bf16": _lib.DT_BF16}
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def tensor_table(n_latents: int):
+    """[(name, kind, shape, offset)] in the reference's state_dict order, from the C library."""
+    lib = _lib.load()
+    out = []
+    for i in range(lib.mvae_mnist_num_tensors()):
+        ti = _lib.TensorInfo()
+        _lib.check(lib.mvae_mnist_tensor_info(n_latents, i, C.byref(ti)), "mvae_mnist_tensor_info")
+        shape = tuple(int(ti.shape[d]) for d in range(ti.ndim))
+        out.append((ti.name.decode(), int(ti.kind), shape, int(ti.offset)))
+    return out
+
+
+def sizes(n_latents: int, batch: int, dtype: int) -> _lib.MnistSizeInfo:
+    si = _lib.MnistSizeInfo()
+    _lib.check(_lib.load().mvae_mnist_sizes(n_latents, batch, dtype, C.byref(si)), "mvae_mnist_sizes")
+    return si
+
+
+class _Leaf(nn.Module):
+    """Parameter/buffer holder standing in for nn.Linear / nn.BatchNorm1d / nn.Embedding (keys only)."""
+
+
+class _Net(nn.Module):
+    pass
+
+
+class _Block(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.net = _Net()
+
+
+class MVAE(nn.Module):
+    """Drop-in for the reference's MultimodalVAE (mnist/model.py:14-96).
+
+    All parameters are views into one flat fp32 device buffer (`flat_params`), gradients into `flat_grads`.
+    `precision`: "tf32" (fp32 storage, tensor cores in tf32; the parity path) or "bf16".
+    """
+
+    def __init__(self, n_latents: int = 20, precision: str = "tf32", device: Optional[torch.device] = None,
+                 poe_mode: str = "ref", prior_expert: bool = False, seed: int = 0):
+        super().__init__()
+        if precision not in _DTYPES:
+            raise ValueError("precision must be one of %s" % sorted(_DTYPES))
+        self.n_latents = int(n_latents)
+        self.precision = precision
+        self.dtype_code = _DTYPES[precision]
+        self.poe_mode = {"ref": _lib.POE_REF, "precision": _lib.POE_PRECISION}[poe_mode]
+        self.prior_expert = bool(prior_expert)
+        self.noise_seed = int(seed)
+        need = 8 if self.dtype_code == _lib.DT_BF16 else 4
+        if self.n_latents % need:
+            raise ValueError("n_latents must be a multiple of %d for precision=%s (TMA 16-byte rows)" % (need, precision))
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("mvae_b200 has no CPU path: a CUDA (sm_100) device is required")
+        _lib.check(_lib.load().mvae_device_check(dev.index or 0), "mvae_device_check")
+        self.device_ = dev
+        si = sizes(self.n_latents, 2, self.dtype_code)
+        self.flat_params = torch.zeros(si.param_floats, device=dev, dtype=torch.float32)
+        self.flat_grads = torch.zeros(si.param_floats, device=dev, dtype=torch.float32)
+        self.flat_buffers = torch.zeros(si.buffer_floats, device=dev, dtype=torch.float32)
+        self.flat_nbt = torch.zeros(si.num_bn, device=dev, dtype=torch.int64)
+        self.flat_params_bf16 = (torch.zeros(si.param_floats, device=dev, dtype=torch.bfloat16)
+                                 if self.dtype_code == _lib.DT_BF16 else None)
+        self._table = tensor_table(self.n_latents)
+        self.image_encoder, self.image_decoder = _Block(), _Block()
+        self.text_encoder, self.text_decoder = _Block(), _Block()
+        for name, kind, shape, off in self._table:
+            block, _, idx, leaf = name.split(".")
+            net = getattr(self, block).net
+            if not hasattr(net, idx):
+                net.add_module(idx, _Leaf())
+            holder = getattr(net, idx)
+            numel = 1
+            for s in shape:
+                numel *= s
+            if kind == 0:
+                p = nn.Parameter(self.flat_params[off:off + numel].view(shape))
+                p.grad = self.flat_grads[off:off + numel].view(shape)
+                holder.register_parameter(leaf, p)
+            elif kind == 1:
+                holder.register_buffer(leaf, self.flat_buffers[off:off + numel].view(shape))
+            else:
+                holder.register_buffer(leaf, self.flat_nbt[off])
+        self.reset_parameters()
+        self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+
+    # ------------------------------------------------------------------ parameters
+    @torch.no_grad()
+    def reset_parameters(self, seed: Optional[int] = None) -> None:
+        """PyTorch default initialisers of nn.Linear / nn.Embedding / nn.BatchNorm1d."""
+        g = torch.Generator().manual_seed(1234 if seed is None else seed)
+        sd = self.state_dict()
+        for name, kind, shape, _ in self._table:
+            t = sd[name]
+            if kind == 2:
+                t.zero_()
+            elif name.endswith("running_mean"):
+                t.zero_()
+            elif name.endswith("running_var"):
+                t.fill_(1.0)
+            elif ".net.1." in name or ".net.4." in name:
+                t.fill_(1.0 if name.endswith("weight") else 0.0)
+            elif name == "text_encoder.net.0.weight":
+                t.copy_(torch.randn(shape, generator=g))
+            else:
+                fan_in = shape[1] if len(shape) == 2 else sd[name[:-4] + "weight"].shape[1]
+                bound = 1.0 / fan_in ** 0.5
+                t.copy_((torch.rand(shape, generator=g) * 2 - 1) * bound)
+        self.sync_low_precision()
+
+    def sync_low_precision(self) -> None:
+        """Refresh the bf16 mirror of the parameters (after load_state_dict or any manual edit)."""
+        if self.flat_params_bf16 is not None:
+            _lib.check(_lib.load().mvae_cast_f32_to_bf16(
+                C.c_void_p(self.flat_params.data_ptr()), C.c_void_p(self.flat_params_bf16.data_ptr()),
+                C.c_int64(self.flat_params.numel()), _stream_ptr()), "mvae_cast_f32_to_bf16")
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=False)
+        self.sync_low_precision()
+        return out
+
+    # ------------------------------------------------------------------ workspace / conversions
+    def workspace(self, batch: int) -> torch.Tensor:
+        key = (batch, self.dtype_code)
+        if key not in self._ws:
+            si = sizes(self.n_latents, batch, self.dtype_code)
+            self._ws[key] = torch.empty(si.workspace_bytes + 256, device=self.device_, dtype=torch.uint8)
+        ws = self._ws[key]
+        off = (-ws.data_ptr()) % 256
+        return ws[off:]
+
+    def act_dtype(self) -> torch.dtype:
+        return torch.float32 if self.dtype_code == _lib.DT_F32 else torch.bfloat16
+
+    def to_act(self, image: torch.Tensor) -> torch.Tensor:
+        """image.view(-1, 784) in the storage dtype of the tensor-core path (mnist/train.py:131)."""
+        x = image.reshape(-1, 784)
+        if x.dtype == torch.uint8:
+            out = torch.empty(x.shape, device=self.device_, dtype=self.act_dtype())
+            xd = x.to(self.device_, non_blocking=True).contiguous()
+            f32 = out.data_ptr() if self.dtype_code == _lib.DT_F32 else None
+            b16 = out.data_ptr() if self.dtype_code == _lib.DT_BF16 else None
+            _lib.check(_lib.load().mvae_u8_to_act(C.c_void_p(xd.data_ptr()), C.c_void_p(f32), C.c_void_p(b16),
+                                                  C.c_int64(xd.numel()), C.c_float(1.0 / 255.0), _stream_ptr()),
+                       "mvae_u8_to_act")
+            return out
+        x = x.to(self.device_, non_blocking=True)
+        if x.dtype == self.act_dtype():
+            return x.contiguous()
+        if x.dtype == torch.float32 and self.dtype_code == _lib.DT_BF16:
+            x = x.contiguous()
+            out = torch.empty(x.shape, device=self.device_, dtype=torch.bfloat16)
+            _lib.check(_lib.load().mvae_cast_f32_to_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                         C.c_int64(x.numel()), _stream_ptr()), "mvae_cast_f32_to_bf16")
+            return out
+        raise TypeError("image dtype %s not supported for precision %s" % (x.dtype, self.precision))
+
+    # ------------------------------------------------------------------ the C call
+    def _build_args(self, image, text, terms: Sequence[int], lambdas, kl_weights, eps=None, backward=False,
+                    zero_grad=True, adam=None, outputs=False, grad_scale=1.0, losses=None):
+        B = image.shape[0]
+        G = len(terms)
+        if image.dtype != self.act_dtype() or not image.is_contiguous() or image.shape[1] != 784:
+            raise ValueError("image must be a contiguous [B, 784] %s tensor (use MVAE.to_act)" % self.act_dtype())
+        if text.dtype != torch.int64 or text.shape[0] != B:
+            raise ValueError("text must be an int64 [B] tensor")
+        a = _lib.MnistStepArgs()
+        a.batch, a.n_latents, a.dtype, a.n_terms = B, self.n_latents, self.dtype_code, G
+        for g in range(G):
+            a.term_type[g] = terms[g]
+            a.lambda_image[g], a.lambda_text[g] = float(lambdas[g][0]), float(lambdas[g][1])
+            a.kl_weight[g] = float(kl_weights[g])
+        a.poe_mode, a.prior_expert, a.poe_eps = self.poe_mode, int(self.prior_expert), 1e-8
+        a.image, a.text = image.data_ptr(), text.data_ptr()
+        a.eps = None if eps is None else eps.data_ptr()
+        a.seed = self.noise_seed
+        a.params = self.flat_params.data_ptr()
+        a.params_bf16 = None if self.flat_params_bf16 is None else self.flat_params_bf16.data_ptr()
+        a.buffers = self.flat_buffers.data_ptr()
+        a.num_batches_tracked = self.flat_nbt.data_ptr()
+        a.grads = self.flat_grads.data_ptr()
+        a.do_backward, a.zero_grad = int(backward), int(zero_grad)
+        a.adam_step = self._step_counter.data_ptr()
+        a.grad_scale = float(grad_scale)
+        if adam is not None:
+            a.do_adam = 1
+            a.adam_m, a.adam_v = adam["m"].data_ptr(), adam["v"].data_ptr()
+            a.lr, a.beta1, a.beta2, a.adam_eps = adam["lr"], adam["betas"][0], adam["betas"][1], adam["eps"]
+        ws = self.workspace(B)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        if losses is None:
+            losses = torch.empty(G, 4, device=self.device_, dtype=torch.float32)
+        a.out_losses = losses.data_ptr()
+        outs = None
+        if outputs:
+            ri = torch.empty(G * B, 784, device=self.device_, dtype=self.act_dtype())
+            rt = torch.empty(G * B, 10, device=self.device_, dtype=torch.float32)
+            mu = torch.empty(G, B, self.n_latents, device=self.device_, dtype=torch.float32)
+            lv = torch.empty_like(mu)
+            a.out_recon_image, a.out_recon_text = ri.data_ptr(), rt.data_ptr()
+            a.out_mu, a.out_logvar = mu.data_ptr(), lv.data_ptr()
+            outs = (ri, rt, mu, lv)
+        return a, losses, outs
+
+    def _run(self, image, text, terms, lambdas, kl_weights, **kw):
+        a, losses, outs = self._build_args(image, text, terms, lambdas, kl_weights, **kw)
+        _lib.check(_lib.load().mvae_mnist_step(C.byref(a), _stream_ptr()), "mvae_mnist_step")
+        return losses, outs
+
+    def profile(self, image, text, terms, lambdas, kl_weights, **kw):
+        """One step with a CUDA-event pair around every kernel launch: [(label, milliseconds)]."""
+        a, _, _ = self._build_args(image, text, terms, lambdas, kl_weights, **kw)
+        n_max, stride = 96, 64
+        labels = C.create_string_buffer(n_max * stride)
+        ms = (C.c_float * n_max)()
+        n = C.c_int(0)
+        _lib.check(_lib.load().mvae_mnist_step_profile(C.byref(a), _stream_ptr(), n_max, labels, stride, ms,
+                                                       C.byref(n)), "mvae_mnist_step_profile")
+        raw = labels.raw
+        return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, image=None, text=None):
+        """MultimodalVAE.forward (mnist/model.py:53-84): (recon_image probs, recon_text log-probs, mu, logvar).
+
+        Train mode uses batch statistics (and advances the running statistics) and samples z; this entry does
+        not build an autograd graph - training goes through MVAETrainer.step, which fuses the three terms."""
+        assert image is not None or text is not None
+        if not self.training:
+            raise NotImplementedError("eval-mode forward (running statistics) is the next row of SURVEY 8f")
+        term = TERMS["joint"] if (image is not None and text is not None) else (
+            TERMS["image"] if image is not None else TERMS["text"])
+        B = image.shape[0] if image is not None else text.shape[0]
+        x = self.to_act(image) if image is not None else torch.zeros(B, 784, device=self.device_, dtype=self.act_dtype())
+        y = (text.to(self.device_).long().contiguous() if text is not None
+             else torch.zeros(B, device=self.device_, dtype=torch.int64))
+        _, outs = self._run(x, y, [term], [(0.0, 0.0)], [0.0], outputs=True)
+        ri, rt, mu, lv = outs
+        return ri.float(), rt, mu[0], lv[0]
+
+
+MultimodalVAE = MVAE  # the reference's class name (mnist/model.py:14)
+
+
+class MVAETrainer:
+    """The fused three-term ELBO step of mnist/train.py:127-153 (and the weak-supervision variants
+    mnist/modal_weak.py:69-100) as one launch sequence, with Adam state living next to the flat parameters."""
+
+    def __init__(self, model: MVAE, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 use_cuda_graph: bool = False, grad_scale: float = 1.0):
+        self.model = model
+        self.adam = {"m": torch.zeros_like(model.flat_params), "v": torch.zeros_like(model.flat_params),
+                     "lr": lr, "betas": betas, "eps": eps}
+        self.use_cuda_graph = use_cuda_graph
+        self.grad_scale = grad_scale
+        self._graphs = {}
+        self.last_graph_launches = 0
+
+    @staticmethod
+    def mnist_kl_weight(batch: int, annealing_factor: float = 1.0) -> float:
+        """KLD /= batch_size * (784 / 3)   (mnist/train.py:80)."""
+        return annealing_factor * 3.0 / (784.0 * batch)
+
+    def _norm(self, terms, batch, annealing_factor):
+        tt = [TERMS[t] if isinstance(t, str) else int(t) for t in terms]
+        return tt, [self.mnist_kl_weight(batch, annealing_factor)] * len(tt)
+
+    def step(self, image, text, eps=None, terms=("joint", "image", "text"), lambdas=((1.0, 1.0),) * 3,
+             annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True):
+        """One training step.  Returns (losses [n_terms, 4] device tensor: total / image / text / KL per term,
+        outputs or None).  `image`: [B,784] (or [B,1,28,28]) uint8 / float32 / storage dtype, host or device."""
+        m = self.model
+        x = m.to_act(image)
+        y = text.to(m.device_, non_blocking=True).long().contiguous()
+        if eps is not None:
+            eps = eps.to(m.device_, torch.float32).contiguous()
+        if self.use_cuda_graph and not outputs:
+            return self._graph_step(x, y, eps, tuple(terms), tuple(map(tuple, lambdas)), annealing_factor, update,
+                                    zero_grad), None
+        tt, klw = self._norm(terms, x.shape[0], annealing_factor)
+        return m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=zero_grad,
+                      adam=self.adam if update else None, outputs=outputs, grad_scale=self.grad_scale)
+
+    def _graph_step(self, x, y, eps, terms, lambdas, annealing_factor, update, zero_grad):
+        """Replay of the step as one CUDA graph (static input buffers; one graph per configuration)."""
+        m = self.model
+        key = (x.shape[0], terms, lambdas, float(annealing_factor), bool(update), bool(zero_grad), eps is not None)
+        ent = self._graphs.get(key)
+        if ent is None:
+            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            se = torch.empty_like(eps) if eps is not None else None
+            sx.copy_(x)
+            sy.copy_(y)
+            if se is not None:
+                se.copy_(eps)
+            losses = torch.empty(len(terms), 4, device=m.device_, dtype=torch.float32)
+            tt, klw = self._norm(terms, x.shape[0], annealing_factor)
+            kw = dict(eps=se, backward=True, zero_grad=zero_grad, adam=self.adam if update else None,
+                      grad_scale=self.grad_scale, losses=losses)
+            # capture does not execute: the caller-visible step happens at the first replay below
+            m.workspace(x.shape[0])
+            torch.cuda.synchronize()
+            lib = _lib.load()
+            before = lib.mvae_launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                m._run(sx, sy, tt, lambdas, klw, **kw)
+            ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses,
+                   "launches": int(lib.mvae_launch_count() - before)}
+            self._graphs[key] = ent
+        else:
+            ent["x"].copy_(x, non_blocking=True)
+            ent["y"].copy_(y, non_blocking=True)
+            if eps is not None:
+                ent["eps"].copy_(eps, non_blocking=True)
+        ent["graph"].replay()
+        self.last_graph_launches = ent["launches"]
+        return ent["losses"]

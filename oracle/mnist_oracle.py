@@ -116,9 +116,48 @@ def sample_flat(t: torch.Tensor, max_n: int = 512) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- layers
+# Optional emulation of the tensor-core operand rounding of the CUDA path (None = exact fp32 like the
+# reference).  With "tf32" every GEMM operand - forward, dgrad and wgrad - is rounded to a 10-bit mantissa
+# (round-to-nearest-even) before an exact product, which is what TMA + tcgen05 kind::tf32 do; the parity tests
+# use it to separate LOGIC errors (must vanish against this oracle) from the intrinsic tf32 rounding noise
+# (visible against the exact oracle, amplified by the mean-subtraction of BatchNorm's backward).
+MATMUL_EMULATION: Optional[str] = None
+
+
+def round_tf32(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        return x
+    i = x.contiguous().view(torch.int32)
+    r = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32)
+
+
+def _round_operand(x):
+    if MATMUL_EMULATION == "tf32":
+        return round_tf32(x)
+    if MATMUL_EMULATION == "bf16":
+        return x.to(torch.bfloat16).to(x.dtype)
+    return x
+
+
+class _EmulatedMatmul(torch.autograd.Function):
+    """y = x W^T with operand rounding in all three GEMMs (forward, dgrad, wgrad)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        return _round_operand(x) @ _round_operand(w).t()
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dyr = _round_operand(dy)
+        return dyr @ _round_operand(w), dyr.t() @ _round_operand(x)
+
+
 def linear(x, w, b=None):
     """nn.Linear: y = x W^T + b."""
-    y = x @ w.t()
+    y = x @ w.t() if MATMUL_EMULATION is None else _EmulatedMatmul.apply(x, w)
     return y if b is None else y + b
 
 

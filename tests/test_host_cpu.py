@@ -1,0 +1,112 @@
+"""CPU-side tests (no GPU): the C ABI loads and exports every declared symbol, the parameter layout matches the
+reference's state_dict, host-side data-parallel logic works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+
+import mnist_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mvae_b200
+    from mvae_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "mvae_b200.h")).read()
+    names = set(re.findall(r"\b(mvae_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 14
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert lib.mvae_abi_version() == 1
+
+
+def test_layout_matches_reference_state_dict():
+    import mvae_b200
+    from mvae_b200 import mnist
+    for n in (8, 20, 64):
+        table = mnist.tensor_table(n)
+        shapes = O.param_shapes(n)
+        assert [t[0] for t in table] == list(shapes.keys())   # same keys, same order as the reference
+        for name, kind, shape, off in table:
+            assert tuple(shape) == tuple(shapes[name]), name
+            assert (kind != 0) == O.is_buffer(name)
+        si = mnist.sizes(n, 128, 0)
+        n_params = sum(int(torch.tensor(s).prod()) if len(s) else 1 for k, s in shapes.items() if not O.is_buffer(k))
+        assert si.param_floats >= n_params and si.param_floats % 64 == 0
+    assert sum(int(torch.tensor(s).prod()) for k, s in O.param_shapes(64).items() if not O.is_buffer(k)) == 838020
+
+
+def test_errors_are_reported_not_swallowed():
+    import mvae_b200
+    from mvae_b200 import _lib
+    lib = _lib.load()
+    si = _lib.MnistSizeInfo()
+    assert lib.mvae_mnist_sizes(7, 128, 0, C.byref(si)) != 0
+    assert b"n_latents" in lib.mvae_last_error()
+    with pytest.raises(_lib.MvaeError):
+        _lib.check(lib.mvae_mnist_sizes(64, 1, 0, C.byref(si)), "sizes")
+
+
+def test_no_cpu_fallback():
+    """The product must fail loudly without a CUDA device instead of computing on the CPU."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mvae_b200
+    with pytest.raises(Exception):
+        mvae_b200.MVAE(8, device=torch.device("cpu"))
+    with pytest.raises(Exception):
+        mvae_b200.MVAE(8)
+
+
+def test_bucket_planner():
+    from mvae_b200.parallel import plan_buckets
+    assert plan_buckets([10, 10, 10], 25) == [(0, 20), (20, 30)]
+    assert plan_buckets([100], 10) == [(0, 100)]
+    assert plan_buckets([], 10) == []
+    b = plan_buckets([3, 5, 7, 2, 9], 10)
+    assert b[0][0] == 0 and b[-1][1] == 26 and all(x[1] == y[0] for x, y in zip(b, b[1:]))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import mvae_b200
+    from mvae_b200.parallel import allreduce_flat_, plan_buckets
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    # gradient averaging over equal shards == gradient of the global mean (the identity the DP step relies on)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(8, 5, generator=g)
+    w = torch.randn(5, 3, generator=g, requires_grad=True)
+    shard = x[rank * 4:(rank + 1) * 4]
+    (shard @ w).pow(2).mean().backward()
+    flat = w.grad.reshape(-1).clone()
+    allreduce_flat_(flat, buckets=plan_buckets([7, 8], 8))
+    flat /= world
+    w2 = w.detach().clone().requires_grad_(True)
+    (x @ w2).pow(2).mean().backward()
+    ok = torch.allclose(flat, w2.grad.reshape(-1), atol=1e-6)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_averaging_gloo_world2():
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

