@@ -138,6 +138,9 @@ int mvae_mnist_step(const mvae_mnist_step_args* args, void* stream);
  * mvae_mnist_step_profile: runs one step on `stream` only (no side stream) with a CUDA-event pair around every
  * launch; after a stream synchronise returns up to max_entries (label, milliseconds) pairs. */
 long long mvae_launch_count(void);
+/* Byte offset of a named intermediate buffer inside the step workspace (-1 if unknown); names as in
+ * csrc/mnist_step.cu::Plan (h1pre, g2pre, dlog, dy2, dz, denc, ...).  Tests and bring-up only. */
+long long mvae_mnist_workspace_offset(const char* name, int batch, int n_latents, int dtype);
 int mvae_mnist_step_profile(const mvae_mnist_step_args* args, void* stream, int max_entries, char* labels,
                             int label_stride, float* ms_out, int* n_out);
 

@@ -49,6 +49,8 @@ def load():
         lib = C.CDLL(_build.LIB_PATH)
         lib.mvae_last_error.restype = C.c_char_p
         lib.mvae_launch_count.restype = C.c_longlong
+        lib.mvae_mnist_workspace_offset.restype = C.c_longlong
+        lib.mvae_mnist_workspace_offset.argtypes = [C.c_char_p, c_int, c_int, c_int]
         lib.mvae_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                        c_float, c_float, c_void_p, c_float, c_int, c_void_p]
         _lib = lib

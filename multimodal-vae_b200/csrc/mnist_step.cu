@@ -563,6 +563,20 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
 
 long long mvae_launch_count(void) { return g_launches; }
 
+// Byte offset of a named workspace buffer (tests / bring-up: lets the host inspect intermediate tensors).
+long long mvae_mnist_workspace_offset(const char* name, int batch, int n_latents, int dtype) {
+  const Plan p = make_plan(batch, n_latents, dtype);
+#define MVAE_OFF(f) if (strcmp(name, #f) == 0) return p.f;
+  MVAE_OFF(st_e1) MVAE_OFF(st_e2) MVAE_OFF(st_d1) MVAE_OFF(st_d2) MVAE_OFF(st_t1)
+  MVAE_OFF(sb_e1) MVAE_OFF(sb_e2) MVAE_OFF(sb_d1) MVAE_OFF(sb_d2) MVAE_OFF(sb_t1)
+  MVAE_OFF(losses) MVAE_OFF(d_txt_table) MVAE_OFF(sv_e1) MVAE_OFF(sv_e2) MVAE_OFF(sv_d1) MVAE_OFF(sv_d2)
+  MVAE_OFF(txt_table) MVAE_OFF(h1pre) MVAE_OFF(h1) MVAE_OFF(h2pre) MVAE_OFF(h2) MVAE_OFF(enc) MVAE_OFF(z)
+  MVAE_OFF(t1pre) MVAE_OFF(g1pre) MVAE_OFF(g1) MVAE_OFF(g2pre) MVAE_OFF(g2) MVAE_OFF(dlog) MVAE_OFF(dyt)
+  MVAE_OFF(dy2) MVAE_OFF(dy1) MVAE_OFF(dz) MVAE_OFF(denc) MVAE_OFF(dye2) MVAE_OFF(dye1)
+#undef MVAE_OFF
+  return -1;
+}
+
 int mvae_mnist_step_profile(const mvae_mnist_step_args* a, void* stream_v, int max_entries, char* labels, int label_stride,
                             float* ms_out, int* n_out) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);

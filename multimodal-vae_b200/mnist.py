@@ -160,6 +160,18 @@ class MVAE(nn.Module):
         off = (-ws.data_ptr()) % 256
         return ws[off:]
 
+    def debug_buffer(self, name: str, batch: int, shape, dtype=None) -> torch.Tensor:
+        """View of a named intermediate buffer of the last step (tests / bring-up)."""
+        off = _lib.load().mvae_mnist_workspace_offset(name.encode(), batch, self.n_latents, self.dtype_code)
+        if off < 0:
+            raise KeyError(name)
+        dtype = dtype or self.act_dtype()
+        numel = 1
+        for s_ in shape:
+            numel *= s_
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        return self.workspace(batch)[off:off + nbytes].view(dtype).view(shape)
+
     def act_dtype(self) -> torch.dtype:
         return torch.float32 if self.dtype_code == _lib.DT_F32 else torch.bfloat16
 

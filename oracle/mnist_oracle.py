@@ -155,10 +155,35 @@ class _EmulatedMatmul(torch.autograd.Function):
         return dyr @ _round_operand(w), dyr.t() @ _round_operand(x)
 
 
-def linear(x, w, b=None):
+# Linear layers the CUDA path runs on tensor cores (operand rounding applies); the text encoder / decoder
+# Linears run in plain fp32 inside the tail kernels.
+TENSOR_CORE_LINEARS = ("image_encoder.net.0", "image_encoder.net.3", "image_encoder.net.6", "image_decoder.net.0",
+                       "image_decoder.net.3", "image_decoder.net.6")
+
+# Forward substitution for the backward-consistency test: {(tag, term): tensor}.  When set, the value of the
+# tagged forward tensor is REPLACED by the given one (straight-through: gradients flow as if it had been
+# computed here).  Gradients of a ReLU network are discontinuous in the forward activations - two valid tf32
+# evaluations that differ by 1e-4 flip a handful of ReLU units and move inner-layer gradients by ~1 % - so the
+# tight logic check feeds the device's own forward tensors in and compares the backward given THOSE.
+FORWARD_OVERRIDE: Optional[Dict[Tuple[str, int], torch.Tensor]] = None
+CURRENT_TERM = 0
+
+
+def _override(h, tag):
+    if FORWARD_OVERRIDE is None:
+        return h
+    v = FORWARD_OVERRIDE.get((tag, CURRENT_TERM))
+    if v is None:
+        return h
+    return h + (v.to(h.dtype) - h).detach()
+
+
+def linear(x, w, b=None, tag: Optional[str] = None):
     """nn.Linear: y = x W^T + b."""
-    y = x @ w.t() if MATMUL_EMULATION is None else _EmulatedMatmul.apply(x, w)
-    return y if b is None else y + b
+    emulate = MATMUL_EMULATION is not None and (tag is None or tag in TENSOR_CORE_LINEARS)
+    y = _EmulatedMatmul.apply(x, w) if emulate else x @ w.t()
+    y = y if b is None else y + b
+    return _override(y, tag) if tag is not None else y
 
 
 def batchnorm_train(x, gamma, beta, st: Optional[State] = None, prefix: str = ""):
@@ -189,11 +214,11 @@ def _bn(x, p: State, st: Optional[State], prefix: str, training: bool):
 
 def image_encoder(p: State, x, st=None, training=True):
     """mnist/model.py:99-117."""
-    h = linear(x, p["image_encoder.net.0.weight"], p["image_encoder.net.0.bias"])
+    h = linear(x, p["image_encoder.net.0.weight"], p["image_encoder.net.0.bias"], "image_encoder.net.0")
     h = torch.relu(_bn(h, p, st, "image_encoder.net.1", training))
-    h = linear(h, p["image_encoder.net.3.weight"], p["image_encoder.net.3.bias"])
+    h = linear(h, p["image_encoder.net.3.weight"], p["image_encoder.net.3.bias"], "image_encoder.net.3")
     h = torch.relu(_bn(h, p, st, "image_encoder.net.4", training))
-    h = linear(h, p["image_encoder.net.6.weight"], p["image_encoder.net.6.bias"])
+    h = linear(h, p["image_encoder.net.6.weight"], p["image_encoder.net.6.bias"], "image_encoder.net.6")
     n = h.shape[1] // 2
     return h[:, :n], h[:, n:]
 
@@ -202,25 +227,25 @@ def text_encoder(p: State, text, st=None, training=True):
     """mnist/model.py:138-153."""
     h = p["text_encoder.net.0.weight"][text]
     h = torch.relu(_bn(h, p, st, "text_encoder.net.1", training))
-    h = linear(h, p["text_encoder.net.3.weight"], p["text_encoder.net.3.bias"])
+    h = linear(h, p["text_encoder.net.3.weight"], p["text_encoder.net.3.bias"], "text_encoder.net.3")
     n = h.shape[1] // 2
     return h[:, :n], h[:, n:]
 
 
 def image_decoder_logits(p: State, z, st=None, training=True):
     """mnist/model.py:120-134 (everything before the sigmoid of :135)."""
-    h = linear(z, p["image_decoder.net.0.weight"], p["image_decoder.net.0.bias"])
+    h = linear(z, p["image_decoder.net.0.weight"], p["image_decoder.net.0.bias"], "image_decoder.net.0")
     h = torch.relu(_bn(h, p, st, "image_decoder.net.1", training))
-    h = linear(h, p["image_decoder.net.3.weight"], p["image_decoder.net.3.bias"])
+    h = linear(h, p["image_decoder.net.3.weight"], p["image_decoder.net.3.bias"], "image_decoder.net.3")
     h = torch.relu(_bn(h, p, st, "image_decoder.net.4", training))
-    return linear(h, p["image_decoder.net.6.weight"], p["image_decoder.net.6.bias"])
+    return linear(h, p["image_decoder.net.6.weight"], p["image_decoder.net.6.bias"], "image_decoder.net.6")
 
 
 def text_decoder_logits(p: State, z, st=None, training=True):
     """mnist/model.py:156-169 (everything before the log_softmax of :170)."""
-    h = linear(z, p["text_decoder.net.0.weight"], p["text_decoder.net.0.bias"])
+    h = linear(z, p["text_decoder.net.0.weight"], p["text_decoder.net.0.bias"], "text_decoder.net.0")
     h = torch.relu(_bn(h, p, st, "text_decoder.net.1", training))
-    return linear(h, p["text_decoder.net.3.weight"], p["text_decoder.net.3.bias"])
+    return linear(h, p["text_decoder.net.3.weight"], p["text_decoder.net.3.bias"], "text_decoder.net.3")
 
 
 def product_of_experts(mu, logvar, eps: float = POE_EPS):
@@ -269,7 +294,7 @@ def forward(p: State, image=None, text=None, noise=None, st=None, training=True)
         m, l = text_encoder(p, text, st, training)
         mus.append(m); lvs.append(l)
     mu, logvar = product_of_experts(torch.stack(mus, 0), torch.stack(lvs, 0))
-    z = reparametrize(mu, logvar, noise, training)
+    z = _override(reparametrize(mu, logvar, noise, training), "z")
     img_logits = image_decoder_logits(p, z, st, training)
     txt_logits = text_decoder_logits(p, z, st, training)
     return torch.sigmoid(img_logits), torch.log_softmax(txt_logits, dim=1), mu, logvar, img_logits, txt_logits
@@ -309,11 +334,13 @@ def train_step_losses(p: State, image, text, noises: Sequence[torch.Tensor], st:
     losses: List[torch.Tensor] = []
     outs = []
     args = ((image, text), (image, None), (None, text))
+    global CURRENT_TERM
     for k in range(3):
         if not terms[k]:
             losses.append(torch.zeros((), dtype=image.dtype))
             outs.append(None)
             continue
+        CURRENT_TERM = k
         ri, rt, mu, lv, il, tl = forward(p, args[k][0], args[k][1], noises[k], st, True)
         losses.append(loss_function(mu, lv, ri, image, rt, text, lambdas[k][0], lambdas[k][1]))
         outs.append((ri, rt, mu, lv, il, tl))

@@ -1,15 +1,19 @@
 """GPU parity of the fused MNIST MVAE step (through the C ABI) against the CPU oracle and the golden
-vectors of the real reference.  Tolerances:
+vectors of the real reference.  Tolerances and what they mean:
 
 * losses: 2e-5 relative (tf32) - the loss path is fp32 except the GEMM operands.
-* forward outputs (recon_image, recon_text, mu, logvar): relative L2 <= 1e-3 (tf32), the north-star bound.
-* gradients, LOGIC check: against the oracle run with tf32 operand rounding emulated in every GEMM
-  (oracle.MATMUL_EMULATION = "tf32"): relative L2 <= 8e-3 per tensor (measured: <= 4e-3; the residue is
-  rounding-mode / accumulation-order noise, again amplified by BatchNorm at small batch).
-* gradients, PRECISION check: against the exact-fp32 oracle / reference golden: relative L2 <= 6e-2 (tf32).
-  The excess over 1e-3 is intrinsic tf32 rounding, amplified where BatchNorm's backward subtracts the batch
-  mean of the gradient (DESIGN.md "Numerics"); it is not a logic error, as the first check shows.
-* bf16: losses 2e-4, gradients relative L2 <= 0.2; the bf16 criterion proper is the training-curve test below.
+* forward outputs (recon_image, recon_text, mu, logvar): relative L2 <= 1e-3 / 2e-3 (tf32), the north-star bound.
+* gradients, LOGIC check ("backward given the device's forward"): the oracle is run with the device's own
+  forward intermediates substituted (oracle.FORWARD_OVERRIDE) and tf32 operand rounding emulated in every
+  tensor-core GEMM; every gradient must then agree to relative L2 <= 1.5e-3 (measured <= 6.7e-4: the residue
+  is round(dy_joint + dy_image) on the device, where each encoder runs once, vs round(dy_joint) +
+  round(dy_image) in the reference's two passes).
+* gradients, PRECISION check against the exact-fp32 oracle / reference golden: relative L2 <= 6e-2 (tf32).
+  Gradients of a ReLU network are discontinuous in the forward activations: two valid tf32 evaluations of the
+  forward differ by ~1e-4, which flips a handful of ReLU units and moves the inner-layer gradients by
+  sqrt(fraction flipped) ~ 1-3 %.  Any tf32 implementation shows this (the oracle with emulated tf32 GEMMs is
+  as far from the exact oracle as the device is); it is not a logic error, as the first check shows.
+* bf16: losses 2e-4, gradients relative L2 <= 0.2 / logic 8e-2; the bf16 criterion proper is the training-curve test.
 """
 import os
 
@@ -18,52 +22,20 @@ import pytest
 import torch
 
 import mnist_oracle as O
+from helpers import NAMES, device_forward_override, oracle_step, rel_l2, run_device_step
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = ("joint", "image", "text")
 
 
-def rel_l2(a, b):
-    a = a.detach().double().cpu()
-    b = b.detach().double().cpu()
-    return float((a - b).norm() / (b.norm() + 1e-30))
-
-
-def run_device_step(state, image, text, noises, n, precision, terms=NAMES, lambdas=((1., 1.),) * 3, update=False):
-    import mvae_b200
-    m = mvae_b200.MVAE(n, precision=precision)
-    m.load_state_dict(state)
-    tr = mvae_b200.MVAETrainer(m)
-    idx = [NAMES.index(t) for t in terms]
-    eps = torch.stack([noises[i] for i in idx]).cuda()
-    losses, outs = tr.step(image.cuda(), text.cuda(), eps=eps, terms=terms, lambdas=lambdas, update=update, outputs=True)
-    torch.cuda.synchronize()
-    return m, tr, losses.cpu(), outs
-
-
-def oracle_step(state, image, text, noises, terms=NAMES, lambdas=((1., 1.),) * 3, emulate=None):
-    mask = tuple(t in terms for t in NAMES)
-    full = [(0., 0.)] * 3
-    k = 0
-    for i in range(3):
-        if mask[i]:
-            full[i] = lambdas[k]
-            k += 1
-    O.MATMUL_EMULATION = emulate
-    try:
-        return O.train_step(state, image, text, noises, tuple(full), mask)
-    finally:
-        O.MATMUL_EMULATION = None
-
-
-@pytest.mark.parametrize("B,n,seed", [(24, 8, 3), (100, 64, 0), (130, 20, 5), (512, 64, 1)])
+@pytest.mark.parametrize("B,n,seed", [(24, 8, 3), (100, 64, 0), (130, 24, 5), (512, 64, 1)])
 def test_tf32_step_matches_oracle(B, n, seed):
     state = O.perturbed_state(n, seed)
     image, text, noises = O.synthetic_batch(B, n, seed)
     m, _, dl, outs = run_device_step(state, image, text, noises, n, "tf32")
     losses, grads, bufs, o_outs = oracle_step(state, image, text, noises)
-    _, grads_e, _, _ = oracle_step(state, image, text, noises, emulate="tf32")
+    _, grads_g, _, _ = oracle_step(state, image, text, noises, emulate="tf32",
+                                   override=device_forward_override(m, B, text))
     np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=2e-5)
     ri, rt, mu, lv = outs
     for g in range(3):
@@ -77,7 +49,7 @@ def test_tf32_step_matches_oracle(B, n, seed):
         if name in O.PRE_BN_BIASES:
             assert float(p.grad.abs().max()) < 1e-6, name  # exactly-zero gradient (BatchNorm removes the mean)
             continue
-        assert rel_l2(p.grad, grads_e[name]) < 8e-3, ("logic", name, rel_l2(p.grad, grads_e[name]))
+        assert rel_l2(p.grad, grads_g[name]) < 1.5e-3, ("logic", name, rel_l2(p.grad, grads_g[name]))
         assert rel_l2(p.grad, grads[name]) < 6e-2, ("precision", name, rel_l2(p.grad, grads[name]))
     for k, v in bufs.items():
         if k.endswith("num_batches_tracked"):
@@ -131,11 +103,14 @@ def test_bf16_step_close_to_oracle():
     image, text, noises = O.synthetic_batch(B, n, seed)
     m, _, dl, _ = run_device_step(state, image, text, noises, n, "bf16")
     losses, grads, _, _ = oracle_step(state, image, text, noises)
+    _, grads_g, _, _ = oracle_step(state, image, text, noises, emulate="bf16",
+                                   override=device_forward_override(m, B, text))
     np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=2e-4)
     for name, p in m.named_parameters():
         if name in O.PRE_BN_BIASES:
             continue
-        assert rel_l2(p.grad, grads[name]) < 0.2, (name, rel_l2(p.grad, grads[name]))
+        assert rel_l2(p.grad, grads_g[name]) < 8e-2, ("logic", name, rel_l2(p.grad, grads_g[name]))
+        assert rel_l2(p.grad, grads[name]) < 0.2, ("precision", name, rel_l2(p.grad, grads[name]))
 
 
 def test_adam_update_matches_oracle():
@@ -151,11 +126,21 @@ def test_adam_update_matches_oracle():
     for k, v in new.items():
         if O.is_buffer(k) or k in O.PRE_BN_BIASES:
             continue
-        # first Adam step moves every weight by ~lr*sign(g): compare the update, not the weight
+        # the first Adam step moves every weight by lr * g/(|g| + eps): where |g| is far above the tf32 noise the
+        # device update must be lr*sign(g) like the oracle's
         du = (sd[k].cpu() - state[k]).double()
         dr = (v - state[k]).double()
-        big = grads[k].abs() > 1e-3 * grads[k].abs().max()
-        assert float((du - dr)[big].abs().max()) < 2e-5, k
+        big = grads[k].abs() > 0.2 * grads[k].abs().max()
+        assert float((du - dr)[big].abs().max()) < 5e-5, k
+    # and the optimizer kernel itself, exactly: feed the DEVICE gradients of this very step to the oracle's Adam
+    dev_grads = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
+    mom = {k: torch.zeros_like(v) for k, v in grads.items()}
+    vel = {k: torch.zeros_like(v) for k, v in grads.items()}
+    new2 = O.adam_step(state, dev_grads, mom, vel, 1)
+    for k, v in new2.items():
+        if O.is_buffer(k):
+            continue
+        assert float((sd[k].cpu() - v).abs().max()) < 2e-6, k
 
 
 def test_term_masking_and_zero_lambda():

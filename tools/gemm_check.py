@@ -39,14 +39,26 @@ def run(dt, M, N, K, a_mn, b_mn, acc=False, stats=False, bias=False, block_n=0, 
     _lib.check(rc, "mvae_gemm")
     torch.cuda.synchronize()
     ref = A.double() @ B.double().t()
+    if dt == 0:
+        def rt(x):
+            i = x.contiguous().view(torch.int32)
+            return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+        ref_e = rt(A).double() @ rt(B).double().t()
+        if bias:
+            ref_e = ref_e + bias_t.double()
+        if acc:
+            ref_e = ref_e + 1.0
+        emu_err = ((Cout.double() - ref_e).abs().max() / ref_e.abs().max()).item()
+    else:
+        emu_err = float("nan")
     if bias:
         ref = ref + bias_t.double()
     if acc:
         ref = ref + 1.0
     err = (Cout.double() - ref).abs().max().item()
     scale = ref.abs().max().item()
-    msg = "dt=%d M=%5d N=%4d K=%5d a_mn=%d b_mn=%d acc=%d bn=%3d sk=%2d  max_abs_err=%.3e (ref max %.2e) rel=%.2e" % (
-        dt, M, N, K, a_mn, b_mn, acc, block_n, split_k, err, scale, err / scale)
+    msg = "dt=%d M=%5d N=%4d K=%5d a_mn=%d b_mn=%d acc=%d bn=%3d sk=%2d  max_abs_err=%.3e (ref max %.2e) rel=%.2e vs_tf32_emulation=%.2e" % (
+        dt, M, N, K, a_mn, b_mn, acc, block_n, split_k, err, scale, err / scale, emu_err)
     ok = err / scale < (2e-3 if dt == 0 else 1e-2)
     if stats:
         y = Cout.double()
