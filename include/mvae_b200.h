@@ -67,6 +67,9 @@ typedef struct mvae_gemm_args {
   void* debug_times;  /* NULL, or device int64 [ctas][8] receiving %globaltimer stamps (bring-up only) */
 } mvae_gemm_args;
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
+/* Bring-up: GEMM launches whose epilogue kind (0 store, 1 atomic, 2 BCE, 3 dgrad-BN) equals epilogue_kind write
+ * eight %globaltimer stamps per CTA into the device buffer (NULL switches it off). */
+void mvae_debug_gemm_times(void* device_int64_buffer, int epilogue_kind);
 
 /* ------------------------------------------------------------------------------------------
  * MNIST MVAE (mnist/model.py:14-170).  All parameters live in ONE flat fp32 buffer (so that the data-

@@ -46,6 +46,10 @@ int mvae_device_check(int device) {
   return 0;
 }
 
+void mvae_debug_gemm_times(void* device_int64_buffer, int epilogue_kind) {
+  set_gemm_debug_times(device_int64_buffer, epilogue_kind);
+}
+
 int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   MVAE_REQUIRE(a != nullptr, "mvae_gemm: null args");
   GemmDesc g;

@@ -85,6 +85,7 @@ struct GemmDesc {
 };
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
+void set_gemm_debug_times(void* ptr, int epi_kind);
 
 // Tuning knobs readable from the environment (debug / bench sweeps only).
 int env_int(const char* name, int dflt);

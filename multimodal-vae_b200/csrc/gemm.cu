@@ -45,6 +45,8 @@ struct GemmKParams {
   int b_stage_bytes;  // smem bytes reserved per stage for B (multiple of 1024)
   int b_tx_bytes;     // bytes TMA actually writes per stage for B
   int vec_ok;         // all epilogue tensors allow 4-element vector access
+  int aux_off;        // byte offset (dynamic smem) of the prefetched auxiliary tile, or -1
+  int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
   long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
   GemmEpilogue epi;
@@ -66,11 +68,12 @@ __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float
 template <typename T>
 __device__ __forceinline__ void load4(const T* p, bool vec, int n_valid, float (&o)[4]) {
   if (vec && n_valid >= 4) {
+    // read-only path (ld.global.nc): lets the compiler hoist these loads above the epilogue's global stores
     if constexpr (sizeof(T) == 4) {
-      float4 t = *reinterpret_cast<const float4*>(p);
+      float4 t = __ldg(reinterpret_cast<const float4*>(p));
       o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
     } else {
-      uint2 t = *reinterpret_cast<const uint2*>(p);
+      uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
       __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
       __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
       o[0] = __low2float(a); o[1] = __high2float(a); o[2] = __low2float(b); o[3] = __high2float(b);
@@ -109,7 +112,8 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, bool vec, int n_valid, 
 // compiler can software-pipeline the shared loads over the unrolled rows.
 template <int kKind, int kEpi, typename CT, bool kFast>
 __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t saddr, int ldst, int m, int rows, int cn,
-                                              int nv, int lane, float* s_loss) {
+                                              int nv, int lane, float (&loss_acc)[4], uint32_t aux_saddr,
+                                              int aux_ld_bytes, float* s_red_col) {
   using act_t = typename ActT<kKind>::type;
   const GemmEpilogue& e = p.epi;
   float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
@@ -144,72 +148,105 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
           g_rstd[i] = e.bn_rstd[static_cast<long long>(g) * p.N + cn + i];
         }
     }
-#pragma unroll 4
-    for (int it = 0; it < seg; ++it) {
-      float v[4];
-      ptx::lds128(saddr, v);
-      saddr += ldst * 4;
-      if constexpr (kEpi == EPI_STORE) {
+    // Rows in batches of kRB: issue every load of the batch (staging tile + auxiliary tensor) first, then the
+    // math and the stores - with 8 warps per CTA the latency has to be hidden by ILP, not by occupancy.
+    constexpr int kRB = 4;
+    for (int it = 0; it < seg; it += kRB) {
+      float v[kRB][4], aux[kRB][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          v[i] += bias[i];
-          acc0[i] += v[i];
-          acc1[i] = fmaf(v[i], v[i], acc1[i]);
-        }
-        store4(cptr, kFast, nv, v);
-      } else if constexpr (kEpi == EPI_ATOMIC) {
-        if constexpr (kFast && sizeof(CT) == 4) {
-          ptx::red_add_v4(reinterpret_cast<float*>(cptr), v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i < nv) atomicAdd(reinterpret_cast<float*>(cptr) + i, v[i]);
-        }
-      } else if constexpr (kEpi == EPI_BCE) {
-        // BCE on logits: loss = softplus(x) - t*x, d/dx = sigmoid(x) - t  (reference: sigmoid then
-        // F.binary_cross_entropy, mnist/model.py:135 + mnist/train.py:70; identical for |x| < ~17).
-        float tg[4], d[4], pr[4];
-        load4(reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(trow) * e.ldt + cn, kFast, nv, tg);
-        if (++trow == e.target_rows) trow = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float x = v[i] + bias[i];
-          const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));  // exp(-|x|) in (0, 1]
-          const float inv = ptx::rcp_approx(1.f + ex);                        // sigmoid(|x|) in [0.5, 1)
-          const float pz = x >= 0.f ? inv : ex * inv;
-          pr[i] = pz;
-          d[i] = g_scale * (pz - tg[i]);
-          if (kFast || i < nv) {
-            // softplus(x) - t*x = max(x,0) - t*x + log(1+exp(-|x|)),  log(1+exp(-|x|)) = -ln(inv)
-            const float sp = fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[i], x, fmaxf(x, 0.f)));
-            lsum = fmaf(g_scale, sp, lsum);
-            acc0[i] += d[i];
+      for (int u = 0; u < kRB; ++u) {
+        if (it + u < seg) {
+          ptx::lds128(saddr + u * ldst * 4, v[u]);
+          if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN) {
+            if (kFast && aux_saddr != 0) {
+              ptx::lds_act4<act_t>(aux_saddr + (it + u) * aux_ld_bytes, aux[u]);  // prefetched during the main loop
+            } else if constexpr (kEpi == EPI_BCE) {
+              int tr_u = trow + u;
+              if (tr_u >= e.target_rows) tr_u -= e.target_rows;
+              load4(reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(tr_u) * e.ldt + cn, kFast, nv, aux[u]);
+            } else {
+              load4(hptr + static_cast<long long>(u) * e.ldh, kFast, nv, aux[u]);
+            }
           }
         }
-        store4(cptr, kFast, nv, d);
-        if (pptr != nullptr) {
-          store4(pptr, kFast, nv, pr);
-          pptr += e.ldc;
-        }
-      } else if constexpr (kEpi == EPI_DGRAD_BN) {
-        // dyhat = dh * 1[relu input > 0]; the relu input is recomputed with the forward's own expression.
-        float h[4], d[4];
-        load4(hptr, kFast, nv, h);
-        hptr += e.ldh;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float xh = (h[i] - g_mean[i]) * g_rstd[i];
-          const float y = fmaf(g_gamma[i], xh, g_beta[i]);
-          d[i] = y > 0.f ? v[i] : 0.f;
-          acc0[i] += d[i];
-          acc1[i] = fmaf(d[i], xh, acc1[i]);
-        }
-        store4(cptr, kFast, nv, d);
       }
-      cptr += e.ldc;
+#pragma unroll
+      for (int u = 0; u < kRB; ++u) {
+        if (it + u >= seg) break;
+        CT* crow = cptr + static_cast<long long>(u) * e.ldc;
+        if constexpr (kEpi == EPI_STORE) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[u][i] += bias[i];
+            acc0[i] += v[u][i];
+            acc1[i] = fmaf(v[u][i], v[u][i], acc1[i]);
+          }
+          store4(crow, kFast, nv, v[u]);
+        } else if constexpr (kEpi == EPI_ATOMIC) {
+          if constexpr (kFast && sizeof(CT) == 4) {
+            ptx::red_add_v4(reinterpret_cast<float*>(crow), v[u]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < nv) atomicAdd(reinterpret_cast<float*>(crow) + i, v[u][i]);
+          }
+        } else if constexpr (kEpi == EPI_BCE) {
+          // BCE on logits: loss = softplus(x) - t*x, d/dx = sigmoid(x) - t  (reference: sigmoid then
+          // F.binary_cross_entropy, mnist/model.py:135 + mnist/train.py:70; identical for |x| < ~17).
+          float d[4], pr[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x = v[u][i] + bias[i];
+            const float tg = aux[u][i];
+            const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));  // exp(-|x|) in (0, 1]
+            // sigmoid(|x|) = 1/(1+ex) in [0.5, 1) on the FMA pipe (the SFU is the bottleneck of this pass):
+            // linear seed on d in [1,2] (max rel. error 1/17) + three Newton steps r <- r*(2 - d*r)  -> 1e-9
+            const float dd = 1.f + ex;
+            float inv = fmaf(-0.47058823529f, dd, 1.41176470588f);
+            inv = inv * fmaf(-dd, inv, 2.f);
+            inv = inv * fmaf(-dd, inv, 2.f);
+            inv = inv * fmaf(-dd, inv, 2.f);
+            const float pz = x >= 0.f ? inv : ex * inv;
+            pr[i] = pz;
+            d[i] = g_scale * (pz - tg);
+            if (kFast || i < nv) {
+              // softplus(x) - t*x = max(x,0) - t*x + log(1+exp(-|x|)),  log(1+exp(-|x|)) = -ln(inv)
+              const float sp = fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg, x, fmaxf(x, 0.f)));
+              lsum += sp;
+              acc0[i] += d[i];
+            }
+          }
+          store4(crow, kFast, nv, d);
+          if (pptr != nullptr) store4(pptr + static_cast<long long>(u) * e.ldc, kFast, nv, pr);
+        } else if constexpr (kEpi == EPI_DGRAD_BN) {
+          // dyhat = dh * 1[relu input > 0]; the relu input is recomputed with the forward's own expression.
+          float d[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float xh = (aux[u][i] - g_mean[i]) * g_rstd[i];
+            const float y = fmaf(g_gamma[i], xh, g_beta[i]);
+            d[i] = y > 0.f ? v[u][i] : 0.f;
+            acc0[i] += d[i];
+            acc1[i] = fmaf(d[i], xh, acc1[i]);
+          }
+          store4(crow, kFast, nv, d);
+        }
+      }
+      const int adv = min(kRB, seg - it);  // a segment may end inside a batch (statistics-group boundary)
+      saddr += adv * ldst * 4;
+      cptr += static_cast<long long>(adv) * e.ldc;
+      if constexpr (kEpi == EPI_BCE) {
+        trow += adv;
+        if (trow >= e.target_rows) trow -= e.target_rows;
+        if (pptr != nullptr) pptr += static_cast<long long>(adv) * e.ldc;
+      }
+      if constexpr (kEpi == EPI_DGRAD_BN) hptr += static_cast<long long>(adv) * e.ldh;
     }
+    if constexpr (kEpi == EPI_BCE) lsum *= g_scale;
     // ---- statistics-group boundary (or end of this warp's rows): publish the column partials
-    if (e.stat0 != nullptr) {
+    // (s_red_col != nullptr: the whole tile belongs to one statistics group - partials go to shared memory
+    //  and the CTA issues ONE global reduction per column afterwards instead of one per warp)
+    if (e.stat0 != nullptr && s_red_col == nullptr) {
       const long long goff = static_cast<long long>(g) * p.stat_group_stride;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -222,12 +259,20 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
       }
     }
     if (kEpi == EPI_BCE) {
-      atomicAdd(s_loss + (g & 3), lsum);  // CTA-level partial in shared memory; one global atomic per CTA later
+      loss_acc[g & 3] += lsum;  // per-thread partial per term; reduced per warp / per CTA by the caller
       lsum = 0.f;
     }
     done += seg;
+    if (aux_saddr != 0) aux_saddr += seg * aux_ld_bytes;
     ++g;
     seg_left = e.rows_per_group;
+  }
+  if (e.stat0 != nullptr && s_red_col != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      s_red_col[i] = acc0[i];
+      s_red_col[8 * p.block_n + i] = acc1[i];
+    }
   }
 }
 
@@ -275,6 +320,10 @@ __global__ void __launch_bounds__(kGemmThreads)
   if (threadIdx.x == 0) stamp(0);
 
   if (threadIdx.x < 4) s_loss[threadIdx.x] = 0.f;
+  if (p.red_off >= 0) {
+    float* z = reinterpret_cast<float*>(smem + p.red_off);
+    for (int i = threadIdx.x; i < 16 * p.block_n; i += kGemmThreads) z[i] = 0.f;
+  }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -294,6 +343,37 @@ __global__ void __launch_bounds__(kGemmThreads)
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) stamp(1);
+
+  // Auxiliary epilogue operand (BCE: the target image tile; dgrad: the pre-BatchNorm activations): every thread
+  // copies exactly the elements its own row pass will consume into shared memory with cp.async NOW, so the
+  // L2 latency is hidden behind the main loop (the epilogue threads are otherwise idle until the accumulator is done).
+  if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN) {
+    if (p.aux_off >= 0) {
+      const GemmEpilogue& ee = p.epi;
+      const act_t* src = reinterpret_cast<const act_t*>(kEpi == EPI_BCE ? ee.target : ee.hpre);
+      const long long ld = kEpi == EPI_BCE ? ee.ldt : ee.ldh;
+      const int aux_ld = p.block_n * ESZ;
+      const uint32_t aux_base = ptx::smem_u32(smem) + p.aux_off;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int col = ch * 128 + lane * 4;
+        const int cn = n0 + col;
+        if (col < p.block_n && cn + 3 < p.N) {
+          int m = m0 + warp * 16;
+          int srow = kEpi == EPI_BCE ? m % ee.target_rows : m;
+          for (int rr = 0; rr < 16 && m < p.M; ++rr, ++m) {
+            ptx::cp_async<4 * ESZ>(aux_base + (warp * 16 + rr) * aux_ld + col * ESZ, src + static_cast<long long>(srow) * ld + cn);
+            if (kEpi == EPI_BCE) {
+              if (++srow == ee.target_rows) srow = 0;
+            } else {
+              ++srow;
+            }
+          }
+        }
+      }
+      ptx::cp_async_commit();
+    }
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -382,6 +462,13 @@ __global__ void __launch_bounds__(kGemmThreads)
   {
     const int r_begin = warp * 16;
     const int rows_here = min(16, p.M - m0 - r_begin);
+    float loss_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.aux_off >= 0) ptx::cp_async_wait_all();  // this thread's own prefetched auxiliary elements
+    // one statistics group for the whole tile (always true for the un-grouped BCE bias gradient)?
+    const int g_first = m0 / e.rows_per_group;
+    const int g_last = (min(m0 + kBlockM, p.M) - 1) / e.rows_per_group;
+    const bool cta_reduce = p.red_off >= 0 && e.stat0 != nullptr && (g_first == g_last || p.stat_group_stride == 0);
+    float* s_red = reinterpret_cast<float*>(smem + (p.red_off >= 0 ? p.red_off : 0));
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int col = ch * 128 + lane * 4;
@@ -391,16 +478,47 @@ __global__ void __launch_bounds__(kGemmThreads)
       if (nv <= 0 || rows_here <= 0) continue;
       const uint32_t saddr = stage_addr + static_cast<uint32_t>(r_begin * ldst + col) * 4u;
       const bool fast = (nv == 4) && (p.vec_ok != 0);
+      const int aux_ld = p.block_n * ESZ;
+      const uint32_t aux_sa =
+          (p.aux_off >= 0) ? stage_addr + static_cast<uint32_t>(p.aux_off + r_begin * aux_ld + col * ESZ) : 0u;
+      float* red_col = cta_reduce ? s_red + warp * p.block_n + col : nullptr;
       if (e.c_dtype == MVAE_F32) {
         if (fast)
-          epilogue_rows<kKind, kEpi, float, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, s_loss);
+          epilogue_rows<kKind, kEpi, float, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, loss_acc, aux_sa, aux_ld, red_col);
         else
-          epilogue_rows<kKind, kEpi, float, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, s_loss);
+          epilogue_rows<kKind, kEpi, float, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, loss_acc, 0u, 0, red_col);
       } else {
         if (fast)
-          epilogue_rows<kKind, kEpi, __nv_bfloat16, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, s_loss);
+          epilogue_rows<kKind, kEpi, __nv_bfloat16, true>(p, saddr, ldst, m0 + r_begin, rows_here, cn, 4, lane, loss_acc, aux_sa, aux_ld, red_col);
         else
-          epilogue_rows<kKind, kEpi, __nv_bfloat16, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, s_loss);
+          epilogue_rows<kKind, kEpi, __nv_bfloat16, false>(p, saddr, ldst, m0 + r_begin, rows_here, cn, nv, lane, loss_acc, 0u, 0, red_col);
+      }
+    }
+    if (kEpi == EPI_BCE) {
+      // all lanes are converged here: warp-reduce the per-term loss partials, one shared atomic per warp per term
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float v = loss_acc[t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0.f) atomicAdd(&s_loss[t], v);
+      }
+    }
+    if (cta_reduce) {
+      __syncthreads();
+      const long long goff = static_cast<long long>(g_first) * p.stat_group_stride;
+      for (int c = threadIdx.x; c < p.block_n; c += kGemmThreads) {
+        const int n = n0 + c;
+        if (n < p.N) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            a0 += s_red[w * p.block_n + c];
+            a1 += s_red[(8 + w) * p.block_n + c];
+          }
+          atomicAdd(e.stat0 + goff + n, a0);
+          if (e.stat1 != nullptr) atomicAdd(e.stat1 + goff + n, a1);
+        }
       }
     }
     if (threadIdx.x == 64) stamp(6);
@@ -474,6 +592,14 @@ int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b
 
 }  // namespace
 
+// Bring-up aid: timestamps of the next launches with epilogue kind `g_dbg_epi` go to `g_dbg_times`.
+static long long* g_dbg_times = nullptr;
+static int g_dbg_epi = -1;
+void set_gemm_debug_times(void* ptr, int epi_kind) {
+  g_dbg_times = static_cast<long long*>(ptr);
+  g_dbg_epi = epi_kind;
+}
+
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   const int esz = g.kind == MVAE_F32 ? 4 : 2;
   const int BK = 128 / esz;
@@ -496,6 +622,15 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   // ANOTHER CTA on the same SM - so shallow rings (2 stages) with 2-3 co-resident CTAs beat deep rings.
   const bool atomic = e.kind == EPI_ATOMIC;
   const int sms = 148;
+  static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
+  auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+  bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
+  if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz);
+  if (e.kind == EPI_DGRAD_BN) aux_ok = aux_ok && (e.ldh % 4 == 0) && al0(e.hpre, 4 * esz);
+  auto aux_bytes = [&](int bn) -> int { return aux_ok ? kBlockM * bn * esz : 0; };
+  static const int use_red = env_int("MVAE_GEMM_CTA_REDUCE", 1);
+  const bool red_ok = use_red != 0 && e.stat0 != nullptr && e.kind != EPI_ATOMIC;
+  auto red_bytes = [&](int bn) -> int { return red_ok ? 16 * bn * 4 : 0; };
   auto plan_for = [&](int bn, int& split_o, int& stages_o, int& dyn_o, int& bstage_o, int& btx_o) -> double {
     const int tn = ceil_div(g.N, bn);
     const long long tiles = static_cast<long long>(tiles_m) * tn;
@@ -519,6 +654,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
     int dyn = stages * stage_bytes;
     if (dyn < staging) dyn = staging;
+    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn);
     dyn += 1024;
     split_o = split; stages_o = stages; dyn_o = dyn; bstage_o = b_stage; btx_o = b_tx;
     if (dyn > max_dyn + 1024) return 1e30;
@@ -534,7 +670,12 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     const double bytes = (static_cast<double>(tn) * g.M + static_cast<double>(tiles_m) * tn * bn) * g.K * esz;
     const double active_sms = ctas < sms ? static_cast<double>(ctas) : static_cast<double>(sms);
     const double t_load = bytes / (77e9 * active_sms) * 1e6;            // us
-    const double t_epi = (0.35 + 0.0105 * bn) * (atomic ? 1.3 : 1.0);   // us per CTA
+    // epilogue time per CTA (us), measured: the plain store pass is ~10 ns per column; the BCE pass is bound
+    // by SFU issue (3 MUFU per element, 16 rows x chunks per warp, independent of how many lanes are active:
+    // ~5.5 us up to 128 columns, ~9 us beyond); the dgrad pass reads one more tensor
+    double t_epi = (0.35 + 0.0105 * bn) * (atomic ? 1.3 : 1.0);
+    if (e.kind == EPI_BCE) t_epi = bn <= 128 ? 6.5 : 12.0;
+    if (e.kind == EPI_DGRAD_BN) t_epi = 0.5 + 0.016 * bn;
     const double per_sm_ctas = static_cast<double>(ctas) / active_sms;
     // with co-residency the epilogues hide behind other CTAs' loads; one epilogue is always exposed
     const double t_epi_total = occ > 1 ? t_epi * (1.0 + 0.35 * (per_sm_ctas - 1.0)) : t_epi * per_sm_ctas;
@@ -542,6 +683,12 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     return (t_load * (ctas > sms ? (0.5 + 0.5 * quant) : 1.0)) + t_epi_total + 1.2;
   };
   int block_n = g.block_n, split = 1, stages = 2, dyn = 0, b_stage = 0, b_tx = 0;
+  if (block_n <= 0) {
+    // sweep aid: MVAE_GEMM_BN_EPI2=112 forces the tile width of every BCE-epilogue GEMM, etc.
+    char name[32];
+    snprintf(name, sizeof(name), "MVAE_GEMM_BN_EPI%d", e.kind);
+    block_n = env_int(name, 0);
+  }
   if (block_n <= 0) {
     double best = 1e30;
     const int n_cap = 16 * ceil_div(g.N, 16);
@@ -586,7 +733,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   kp.b_tx_bytes = b_tx;
   kp.epi = e;
   kp.stat_group_stride = (e.kind == EPI_BCE) ? 0 : g.N;
-  kp.dbg = g.dbg;
+  kp.dbg = g.dbg != nullptr ? g.dbg : (g_dbg_epi == e.kind ? g_dbg_times : nullptr);
   auto al = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   const int ea = 16 / 4 * (e.c_dtype == MVAE_F32 ? 4 : 2);  // bytes for a 4-element vector of C
   bool vec = (e.ldc % 4 == 0) && al(e.C, ea) && al(e.probs, ea);
@@ -594,6 +741,8 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_BCE) vec = vec && (e.ldt % 4 == 0) && al(e.target, aa);
   if (e.kind == EPI_DGRAD_BN) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
   kp.vec_ok = vec ? 1 : 0;
+  kp.aux_off = (aux_ok && vec) ? (dyn - 1024 - aux_bytes(block_n) - red_bytes(block_n)) : -1;
+  kp.red_off = red_ok ? (dyn - 1024 - red_bytes(block_n)) : -1;
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");
   if (e.kind == EPI_DGRAD_BN)
     MVAE_REQUIRE(e.hpre && e.bn_mean && e.bn_rstd && e.bn_gamma && e.bn_beta, "gemm: dgrad-BN epilogue needs BN state");

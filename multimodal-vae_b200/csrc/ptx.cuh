@@ -145,6 +145,31 @@ __device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
                : "memory");
 }
 
+// cp.async (LDGSTS): asynchronous global -> shared copy of kBytes (4, 8 or 16) per thread.
+template <int kBytes>
+__device__ __forceinline__ void cp_async(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_dst), "l"(gmem_src), "n"(kBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// four activation elements (fp32: 16 B, bf16: 8 B) from shared memory as floats
+template <typename T>
+__device__ __forceinline__ void lds_act4(uint32_t addr, float (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                 : "r"(addr)
+                 : "memory");
+  } else {
+    uint32_t a, b;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+    v[0] = __uint_as_float(a << 16);
+    v[1] = __uint_as_float(a & 0xffff0000u);
+    v[2] = __uint_as_float(b << 16);
+    v[3] = __uint_as_float(b & 0xffff0000u);
+  }
+}
+
 // 16-byte vector reduction (sm_90+): four fp32 adds to consecutive addresses in one L2 operation.
 __device__ __forceinline__ void red_add_v4(float* addr, const float (&v)[4]) {
   asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]),

@@ -227,15 +227,18 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
 // encoder-output gradient are combined through shared memory (no global atomics on activations).
 constexpr int kBwdRows = 4;
 template <typename ZT>
-__global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows) tail_bwd_kernel(const TailArgs a, int smem_floats) {
+__global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel(const TailArgs a, int smem_floats) {
   extern __shared__ float sm[];
-  // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] | combine [rows][G][2n]
+  // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] |
+  //         image-expert combine [rows][G][2n] | text-expert combine [rows][G][2n] | labels [rows]
   const int n = a.n, two_n = 2 * a.n;
   float* s_tab = sm;
   float* s_w1 = s_tab + kTD * two_n;
   float* s_eb = s_w1 + kTD * n;
   float* s_co = s_eb + two_n;  // per group: mean, rstd, c0 = S0/B, c1 = S1/B
   float* s_cb = s_co + kMaxGroups * 4 * kTD;
+  float* s_ct = s_cb + kBwdRows * kMaxGroups * two_n;
+  int* s_lab = reinterpret_cast<int*>(s_ct + kBwdRows * kMaxGroups * two_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = a.G;
   const int wrow = warp / G, g = warp - wrow * G;
@@ -352,15 +355,27 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows) tail_bwd_kernel(co
           float* cb = s_cb + (wrow * kMaxGroups + g) * two_n;
           cb[k] = d_mi[0]; cb[k + 1] = d_mi[1]; cb[n + k] = d_li[0]; cb[n + k + 1] = d_li[1];
         }
-        if (present[1] && a.d_txt_table != nullptr) {
-          atomicAdd(&s_tab[label * two_n + k], d_mt[0]);
-          atomicAdd(&s_tab[label * two_n + k + 1], d_mt[1]);
-          atomicAdd(&s_tab[label * two_n + n + k], d_lt[0]);
-          atomicAdd(&s_tab[label * two_n + n + k + 1], d_lt[1]);
+        if (present[1]) {
+          float* ct = s_ct + (wrow * kMaxGroups + g) * two_n;
+          ct[k] = d_mt[0]; ct[k + 1] = d_mt[1]; ct[n + k] = d_lt[0]; ct[n + k + 1] = d_lt[1];
+          if (lane == 0) s_lab[wrow] = label;
         }
       }
     }
     __syncthreads();
+    // text expert: scatter-add by label without atomics - thread t owns column t of the [10][2n] table
+    if (a.d_txt_table != nullptr && a.txt_table != nullptr) {
+      for (int t = threadIdx.x; t < two_n; t += blockDim.x) {
+        for (int r = 0; r < kBwdRows; ++r) {
+          if (rb * kBwdRows + r >= a.B) break;
+          const int lab = s_lab[r];
+          float v = 0.f;
+          for (int gg = 0; gg < G; ++gg)
+            if (a.group_type[gg] != TERM_IMAGE) v += s_ct[(r * kMaxGroups + gg) * two_n + t];
+          s_tab[lab * two_n + t] += v;
+        }
+      }
+    }
     // combine the terms' contributions to this sample's image-expert gradient (warp g == 0 of each sample)
     if (active && g == 0 && a.enc_img != nullptr && a.d_enc != nullptr) {
       ZT* de = reinterpret_cast<ZT*>(a.d_enc) + static_cast<long long>(b) * two_n;
@@ -812,12 +827,12 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
 
 int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
   if (check_tail(a)) return 1;
-  const int smem_floats =
-      kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD + kBwdRows * kMaxGroups * 2 * a.n;
+  const int smem_floats = kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD +
+                          2 * kBwdRows * kMaxGroups * 2 * a.n + kBwdRows;
   const int smem = smem_floats * 4;
   MVAE_REQUIRE(smem <= 48 * 1024, "tail_backward: n=%d too large for the shared accumulators", a.n);
   const int row_blocks = (a.B + kBwdRows - 1) / kBwdRows;
-  int blocks = std::min(row_blocks, 148 * 4);
+  int blocks = std::min(row_blocks, 148 * 2);
   const int threads = 32 * a.G * kBwdRows;
   if (a.z_dtype == MVAE_F32)
     tail_bwd_kernel<float><<<blocks, threads, smem, st>>>(a, smem_floats);
