@@ -31,6 +31,12 @@ F_ALG_PER_SAMPLE = 9_254_920          # FLOP on tensor cores (encoders once, dec
 Q_TAIL_PER_SAMPLE = 29_880            # bytes of the fused PoE/reparam/KL + BCE/CE tail, fp32 I/O
 
 
+def log(msg):
+    if os.environ.get("MVAE_BENCH_VERBOSE"):
+        sys.stderr.write("[bench r%s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.time() % 1000, msg))
+        sys.stderr.flush()
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -189,7 +195,9 @@ def run_device(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        log("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
+        log("init done")
 
     import mvae_b200
     from mvae_b200 import MVAE, MVAETrainer
@@ -210,6 +218,7 @@ def run_device(args):
     host_x = [imgs_u8[i].pin_memory() for i in range(min(n_slots, 8))]
     host_y = [labels[i].pin_memory() for i in range(min(n_slots, 8))]
     torch.cuda.synchronize()
+    log("pools ready")
 
     def barrier():
         if world > 1:
@@ -227,7 +236,9 @@ def run_device(args):
     # ---- device-resident throughput ("value")
     for i in range(max(args.warmup, 3)):
         losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
+    log("warmup done")
     barrier()
+    log("barrier done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = lib.mvae_launch_count()
@@ -236,8 +247,10 @@ def run_device(args):
     for i in range(args.steps):
         losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
     e1.record()
+    log("timed loop enqueued")
     barrier()
     clocks = sampler.stop()
+    log("timed loop done")
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     eager_launches = int(lib.mvae_launch_count() - l0)
     per_step_launches = trainer.last_graph_launches if not args.no_graph else eager_launches // max(args.steps, 1)
@@ -259,11 +272,27 @@ def run_device(args):
     t1.record()
     barrier()
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    log("e2e done")
     e2e_value = B * world * e2e_steps / (e2e_ms * 1e-3)
 
-    if rank != 0:
-        if world > 1:
+    def teardown():
+        """Release the captured graphs (they hold the NCCL communicator) before destroying the process group;
+        a watchdog makes sure a rank can never hang at exit once its JSON line is out."""
+        if world == 1:
+            return
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        try:
+            trainer._dp_graphs.clear()
+            trainer._graphs.clear()
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
             dist.destroy_process_group()
+        except Exception:
+            pass
+
+    if rank != 0:
+        teardown()
         return 0
 
     # ---- live per-kernel durations (CUDA events around every launch, rank 0)
@@ -318,8 +347,7 @@ def run_device(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(torch)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
     return 0
 
 
@@ -340,4 +368,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os._exit(rc)   # NCCL + CUDA-graph teardown order is not worth a hang at interpreter exit
+    sys.exit(rc)
