@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 1
+#define MVAE_ABI_VERSION 2
 
 #define MVAE_DT_F32 0
 #define MVAE_DT_BF16 1
@@ -134,6 +134,16 @@ typedef struct mvae_mnist_step_args {
   float* out_recon_text;    /* optional [n_terms*batch, 10] log-probabilities */
   float* out_mu;            /* optional [n_terms, batch, n_latents] */
   float* out_logvar;
+  /* --- module-surface extensions (all zero / NULL for the fused training step) --- */
+  int eval_mode;            /* 1: vae.eval() - BatchNorm running statistics, z = mu (mnist/model.py:29-30), no updates */
+  int phase;                /* 0: forward (+ backward if do_backward); 2: backward only from the upstream gradients
+                               below, reusing the workspace of the preceding forward (autograd path of forward()) */
+  const float* z_in;        /* optional [n_terms*batch, n_latents]: decode these latents (decode_image / decode_text,
+                               mnist/model.py:35-42), encoders and PoE are skipped */
+  const void* d_recon_image;/* phase 2: gradient w.r.t. the recon_image probabilities, `dtype` storage, or NULL */
+  const float* d_recon_text;/* phase 2: gradient w.r.t. the recon_text log-probabilities, or NULL */
+  const float* d_mu;        /* phase 2: gradient w.r.t. mu [n_terms, batch, n_latents], or NULL */
+  const float* d_logvar;
 } mvae_mnist_step_args;
 int mvae_mnist_step(const mvae_mnist_step_args* args, void* stream);
 
@@ -155,6 +165,24 @@ int mvae_adam_step(float* params, float* grads, float* m, float* v, void* params
 int mvae_cast_f32_to_bf16(const float* in, void* out, int64_t count, void* stream);
 /* uint8 pixels -> [0,1] activations (image.view(-1,784) of ToTensor(), mnist/train.py:106,131) */
 int mvae_u8_to_act(const uint8_t* in, float* out_f32, void* out_bf16, int64_t count, float scale, void* stream);
+
+/* loss_function (mnist/train.py:64-81) on the module outputs, for callers of forward() + loss_function():
+ *   lambda_image * BCE_mean(recon_image, image) + lambda_text * NLL_mean(recon_text, text) + kl_weight * KL
+ * recon_image / image: [batch, n_pixels] probabilities / targets (image_dtype storage) or both NULL;
+ * recon_text: [batch, n_classes] log-probabilities + text int64 [batch], or both NULL.
+ * forward writes out4 = {total, image term, text term, KL term} (device); backward scales by *grad_out. */
+typedef struct mvae_elbo_loss_args {
+  int image_dtype;
+  int64_t batch;
+  int n_pixels, n_classes, n_latents;
+  const void* recon_image; const void* image;
+  const float* recon_text; const int64_t* text;
+  const float* mu; const float* logvar;
+  float lambda_image, lambda_text, kl_weight;
+} mvae_elbo_loss_args;
+int mvae_elbo_loss_forward(const mvae_elbo_loss_args* args, float* out4, void* stream);
+int mvae_elbo_loss_backward(const mvae_elbo_loss_args* args, const float* grad_out, void* d_recon_image,
+                            float* d_recon_text, float* d_mu, float* d_logvar, void* stream);
 
 /* ProductOfExperts (mnist/model.py:173-185) for M experts with an optional per-sample presence mask
  * [M, batch] (1 = present).  mu/logvar: [M, batch, dim]; outputs [batch, dim]. */

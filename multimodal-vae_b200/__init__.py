@@ -3,8 +3,9 @@
     from mvae_b200 import MVAE, MultimodalVAE, MVAETrainer
 """
 from . import _lib  # noqa: F401
-from .mnist import MVAE, MultimodalVAE, MVAETrainer, TERMS  # noqa: F401
+from .mnist import MVAE, MultimodalVAE, MVAETrainer, HostPipeline, TERMS  # noqa: F401
 
 from .parallel import DataParallelTrainer  # noqa: F401
+from .functional import ProductOfExperts, elbo_loss, loss_function  # noqa: F401
 
-__all__ = ["MVAE", "MultimodalVAE", "MVAETrainer", "DataParallelTrainer", "TERMS", "_lib"]
+__all__ = ["MVAE", "MultimodalVAE", "MVAETrainer", "HostPipeline", "DataParallelTrainer", "ProductOfExperts", "elbo_loss", "loss_function", "TERMS", "_lib"]

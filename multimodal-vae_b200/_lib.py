@@ -49,6 +49,8 @@ def load():
         lib = C.CDLL(_build.LIB_PATH)
         lib.mvae_last_error.restype = C.c_char_p
         lib.mvae_launch_count.restype = C.c_longlong
+        lib.mvae_poe_forward.argtypes = [c_int, c_int, c_float, c_int, c_int64, c_int] + [c_void_p] * 6
+        lib.mvae_poe_backward.argtypes = [c_int, c_int, c_float, c_int, c_int64, c_int] + [c_void_p] * 8
         lib.mvae_mnist_workspace_offset.restype = C.c_longlong
         lib.mvae_mnist_workspace_offset.argtypes = [C.c_char_p, c_int, c_int, c_int]
         lib.mvae_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
@@ -99,6 +101,17 @@ class MnistStepArgs(C.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("out_losses", c_void_p), ("out_recon_image", c_void_p), ("out_recon_text", c_void_p),
         ("out_mu", c_void_p), ("out_logvar", c_void_p),
+        ("eval_mode", c_int), ("phase", c_int), ("z_in", c_void_p),
+        ("d_recon_image", c_void_p), ("d_recon_text", c_void_p), ("d_mu", c_void_p), ("d_logvar", c_void_p),
+    ]
+
+
+class ElboLossArgs(C.Structure):
+    _fields_ = [
+        ("image_dtype", c_int), ("batch", c_int64), ("n_pixels", c_int), ("n_classes", c_int), ("n_latents", c_int),
+        ("recon_image", c_void_p), ("image", c_void_p), ("recon_text", c_void_p), ("text", c_void_p),
+        ("mu", c_void_p), ("logvar", c_void_p),
+        ("lambda_image", c_float), ("lambda_text", c_float), ("kl_weight", c_float),
     ]
 
 

@@ -133,10 +133,19 @@ __global__ void __launch_bounds__(kEwThreads)
     const int cnt = gr1 - gr0;
     const float inv_cnt = 1.f / cnt;
     float mean[N], rstd[N], s_[N], ss_[N];
-    ldc<N>(sum + g * F + f, s_);
-    ldc<N>(sumsq + g * F + f, ss_);
+    if (sum == nullptr) {
+      // eval mode (vae.eval()): normalise with the running statistics, update nothing
+      ldc<N>(running_mean + f, mean);
+      ldc<N>(running_var + f, ss_);
+#pragma unroll
+      for (int i = 0; i < N; ++i) rstd[i] = rsqrtf(ss_[i] + eps);
+    } else {
+      ldc<N>(sum + g * F + f, s_);
+      ldc<N>(sumsq + g * F + f, ss_);
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+      if (sum == nullptr) break;
       const float s = s_[i], ss = ss_[i];
       mean[i] = s * inv_cnt;
       const float var = fmaxf(ss * inv_cnt - mean[i] * mean[i], 0.f);
@@ -401,34 +410,27 @@ int launch_adam(float* p, float* g, float* m, float* v, void* p16, long long n, 
 
 // Start of a step: bump the device-side step counter and clear the accumulators (statistics, loss partials,
 // and - when the caller asks - the flat gradient buffer) that the step's kernels add into with atomics.
-__global__ void __launch_bounds__(kEwThreads) step_prep_kernel(int* step_ptr, float4* zero_buf, long long n4) {
+struct NbtInc {
+  long long v[6];
+};
+__global__ void __launch_bounds__(kEwThreads)
+    step_prep_kernel(int* step_ptr, float4* zero_buf, long long n4, long long* nbt, NbtInc inc) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr != nullptr) *step_ptr += 1;
+  if (blockIdx.x == 0 && threadIdx.x < 6 && nbt != nullptr) nbt[threadIdx.x] += inc.v[threadIdx.x];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     zero_buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, cudaStream_t st) {
+int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
+                     cudaStream_t st) {
   MVAE_REQUIRE(zero_n % 4 == 0, "step_prep: zero_n=%lld must be a multiple of 4", zero_n);
   const long long n4 = zero_n / 4;
   int blocks = static_cast<int>(std::min<long long>((n4 + kEwThreads - 1) / kEwThreads, 2ll * sm_count()));
   if (blocks < 1) blocks = 1;
-  step_prep_kernel<<<blocks, kEwThreads, 0, st>>>(step_ptr, reinterpret_cast<float4*>(zero_buf), n4);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// num_batches_tracked += inc for the six BatchNorm layers (device-side so that graph replays keep counting).
-struct NbtInc {
-  long long v[6];
-};
-__global__ void nbt_update_kernel(long long* nbt, NbtInc inc) {
-  if (threadIdx.x < 6) nbt[threadIdx.x] += inc.v[threadIdx.x];
-}
-int launch_nbt_update(long long* nbt, const long long (&inc)[6], cudaStream_t st) {
   NbtInc i;
   for (int k = 0; k < 6; ++k) i.v[k] = inc[k];
-  nbt_update_kernel<<<1, 32, 0, st>>>(nbt, i);
+  step_prep_kernel<<<blocks, kEwThreads, 0, st>>>(step_ptr, reinterpret_cast<float4*>(zero_buf), n4, nbt, i);
   MVAE_CUDA(cudaGetLastError());
   return 0;
 }
@@ -446,6 +448,56 @@ __global__ void loss_pack_kernel(const float* __restrict__ acc, float* __restric
 }
 int launch_loss_pack(const float* acc, float* out, int G, cudaStream_t st) {
   loss_pack_kernel<<<1, 32, 0, st>>>(acc, out, G);
+  MVAE_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- sigmoid backward (module / autograd path)
+// dlogit = d(prob) * p * (1 - p) for recon_image = sigmoid(logits) (mnist/model.py:135); also the last Linear's
+// bias gradient (column sums).  One thread owns 4 columns and a slab of rows.
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads)
+    sigmoid_bwd_kernel(const T* __restrict__ dp, const T* __restrict__ p, T* __restrict__ dl, int rows, int F,
+                       float* __restrict__ dbias) {
+  const int q = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int tr = threadIdx.x >> 6;
+  if (q * 4 >= F) return;
+  const int f = q * 4;
+  const int slab = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * slab, r1 = min(rows, r0 + slab);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = r0 + tr; r < r1; r += kEwThreads / 64) {
+    float a[4], b[4], o[4];
+    ld4(dp + static_cast<long long>(r) * F + f, a);
+    ld4(p + static_cast<long long>(r) * F + f, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      o[i] = a[i] * b[i] * (1.f - b[i]);
+      acc[i] += o[i];
+    }
+    st4(dl + static_cast<long long>(r) * F + f, o);
+  }
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(dbias + f + i, acc[i]);
+  }
+}
+
+int launch_sigmoid_backward(int dtype, const void* dprob, const void* prob, void* dlogit, int rows, int F, float* dbias,
+                            cudaStream_t st) {
+  MVAE_REQUIRE(F % 4 == 0 && rows > 0, "sigmoid_backward: rows=%d F=%d", rows, F);
+  const int gx = (F / 4 + 63) / 64;
+  int gy = (2 * sm_count() + gx - 1) / gx;
+  if (gy > (rows + 3) / 4) gy = (rows + 3) / 4;
+  if (gy < 1) gy = 1;
+  const dim3 grid(gx, gy, 1);
+  if (dtype == MVAE_F32)
+    sigmoid_bwd_kernel<float><<<grid, kEwThreads, 0, st>>>(static_cast<const float*>(dprob), static_cast<const float*>(prob),
+                                                           static_cast<float*>(dlogit), rows, F, dbias);
+  else
+    sigmoid_bwd_kernel<__nv_bfloat16><<<grid, kEwThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dprob), static_cast<const __nv_bfloat16*>(prob),
+        static_cast<__nv_bfloat16*>(dlogit), rows, F, dbias);
   MVAE_CUDA(cudaGetLastError());
   return 0;
 }

@@ -18,9 +18,11 @@ int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s
 int launch_u8_to_act(const uint8_t* in, float* o32, void* o16, long long n, float scale, cudaStream_t st);
 int launch_adam(float* p, float* g, float* m, float* v, void* p16, long long n, float lr, float b1, float b2, float eps,
                 const int* step_ptr, float grad_scale, int zero_grad, cudaStream_t st);
-int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, cudaStream_t st);
-int launch_nbt_update(long long* nbt, const long long (&inc)[6], cudaStream_t st);
+int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
+                     cudaStream_t st);
 int launch_loss_pack(const float* acc, float* out, int G, cudaStream_t st);
+int launch_sigmoid_backward(int dtype, const void* dprob, const void* prob, void* dlogit, int rows, int F, float* dbias,
+                            cudaStream_t st);
 
 // ---- tail.cu
 enum : int { TERM_JOINT = 0, TERM_IMAGE = 1, TERM_TEXT = 2 };
@@ -41,6 +43,7 @@ struct TailArgs {
   unsigned long long seed = 0;
   const int* step_ptr = nullptr;
   int training = 1;  // 0: z = mu (mnist/model.py:29-30)
+  const float* z_in = nullptr;  // [G*B, n]: latents given by the caller (decode only; experts are ignored)
   float kl_weight[kMaxGroups] = {0, 0, 0};
   // text decoder layer 1 (Linear n -> 10), fused because z is in registers here
   const float* wt1 = nullptr;  // [10, n]

@@ -353,6 +353,17 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   MVAE_REQUIRE(a->image != nullptr && a->text != nullptr, "mnist_step: image and text are both needed (targets)");
   const bool bwd = a->do_backward != 0;
   MVAE_REQUIRE(!bwd || a->grads != nullptr, "mnist_step: backward needs the gradient buffer");
+  // phase 0: forward (+ backward when do_backward); phase 2: backward only, driven by upstream gradients of the
+  // module outputs (the forward of the same workspace must have run before - autograd path of MVAE.forward)
+  const bool fwd = a->phase != 2;
+  const bool module_bwd = a->phase == 2;
+  const bool training = a->eval_mode == 0;
+  MVAE_REQUIRE(fwd || bwd, "mnist_step: phase 2 needs do_backward");
+  MVAE_REQUIRE(training || !bwd, "mnist_step: backward needs train mode");
+  MVAE_REQUIRE(!module_bwd || a->d_recon_image == nullptr || a->out_recon_image != nullptr,
+               "mnist_step: phase 2 needs the saved recon_image probabilities");
+  const bool decode_only = a->z_in != nullptr;
+  if (decode_only) n_img = n_txt = 0;  // latents are given: no encoders, no PoE
 
   const Ptrs W{static_cast<char*>(a->workspace)};
   float* prm = a->params;
@@ -368,14 +379,15 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   const int R = G * B;
 
   // ---- step start: device step counter, num_batches_tracked, accumulators, (optionally) gradients
-  MVAE_STEP(launch_step_prep(a->adam_step, W.at<float>(P.acc_off), P.acc_floats, st), "launch_step_prep#1");
-  if (bwd && a->zero_grad)
-    MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, st));
-  if (a->num_batches_tracked != nullptr) {
+  {
     // BN order in the layout: ie.1, ie.4, id.1, id.4, te.1, td.1
-    const long long inc[6] = {n_img, n_img, G, G, n_txt, G};
-    MVAE_STEP(launch_nbt_update(reinterpret_cast<long long*>(a->num_batches_tracked), inc, st), "launch_nbt_update#2");
+    const long long t_ = training ? 1 : 0;
+    const long long inc[6] = {t_ * n_img, t_ * n_img, t_ * G, t_ * G, t_ * n_txt, t_ * G};
+    if (fwd) MVAE_STEP(launch_step_prep(a->adam_step, W.at<float>(P.acc_off), P.acc_floats,
+                                        reinterpret_cast<long long*>(a->num_batches_tracked), inc, st), "launch_step_prep");
   }
+  if (fwd && bwd && a->zero_grad)
+    MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, st));
 
   float* st_e1 = W.at<float>(P.st_e1); float* st_e2 = W.at<float>(P.st_e2);
   float* st_d1 = W.at<float>(P.st_d1); float* st_d2 = W.at<float>(P.st_d2); float* st_t1 = W.at<float>(P.st_t1);
@@ -393,26 +405,26 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   te.gamma = pf("text_encoder.net.1.weight"); te.beta = pf("text_encoder.net.1.bias");
   te.w = pf("text_encoder.net.3.weight"); te.b = pf("text_encoder.net.3.bias");
   te.running_mean = bf("text_encoder.net.1.running_mean"); te.running_var = bf("text_encoder.net.1.running_var");
-  te.updates = n_txt; te.momentum = mom; te.bn_eps = bn_eps; te.training = 1;
+  te.updates = n_txt; te.momentum = mom; te.bn_eps = bn_eps; te.training = training ? 1 : 0;
   te.table = W.at<float>(P.txt_table); te.save = W.at<float>(P.txt_save);
   if (dep(st, s2)) return 1;  // fork: the per-label text encoder runs beside the image encoder
-  if (n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s2), "launch_textenc_forward");
+  if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s2), "launch_textenc_forward");
 
   if (n_img > 0) {
     // ImageEncoder (mnist/model.py:99-117), once for all terms that use it
-    MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
-                 pf("image_encoder.net.0.bias"), st_e1, st_e1 + 400, 1 << 30, st), "gemm_fwd:image_encoder.net.0.weight#3");
-    MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, st_e1, st_e1 + 400,
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
+                 pf("image_encoder.net.0.bias"), training ? st_e1 : nullptr, training ? st_e1 + 400 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.0.weight#3");
+    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
                           pf("image_encoder.net.1.weight"), pf("image_encoder.net.1.bias"), sv_e1, sv_e1 + 400,
                           bf("image_encoder.net.1.running_mean"), bf("image_encoder.net.1.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.1.weight#4");
-    MVAE_STEP(gemm_fwd(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
-                 pf("image_encoder.net.3.bias"), st_e2, st_e2 + 200, 1 << 30, st), "gemm_fwd:image_encoder.net.3.weight#5");
-    MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, st_e2, st_e2 + 200,
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
+                 pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.3.weight#5");
+    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
                           pf("image_encoder.net.4.weight"), pf("image_encoder.net.4.bias"), sv_e2, sv_e2 + 200,
                           bf("image_encoder.net.4.running_mean"), bf("image_encoder.net.4.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.4.weight#6");
-    MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
                  pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.6.weight#7");
   }
   if (dep(s2, st)) return 1;  // join: the tail needs both experts
@@ -427,39 +439,41 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   ta.enc_img = n_img > 0 ? W.at<float>(P.enc) : nullptr;
   ta.txt_table = n_txt > 0 ? W.at<float>(P.txt_table) : nullptr;
   ta.labels = reinterpret_cast<const long long*>(a->text);
-  ta.eps = a->eps; ta.seed = a->seed; ta.step_ptr = a->adam_step; ta.training = 1;
+  ta.eps = a->eps; ta.seed = a->seed; ta.step_ptr = a->adam_step; ta.training = training ? 1 : 0;
+  ta.z_in = a->z_in;
   ta.wt1 = pf("text_decoder.net.0.weight"); ta.bt1 = pf("text_decoder.net.0.bias");
   ta.z = W.at<void>(P.z); ta.mu = a->out_mu; ta.logvar = a->out_logvar;
   ta.kl = losses + 2 * kMaxGroups;
   ta.t1pre = W.at<float>(P.t1pre); ta.t1_sum = st_t1; ta.t1_sumsq = st_t1 + G * 10;
-  MVAE_STEP(launch_tail_forward(ta, st), "launch_tail_forward#8");
+  if (fwd) MVAE_STEP(launch_tail_forward(ta, st), "launch_tail_forward#8");
 
   TextDecArgs td;
   td.B = B; td.G = G;
   td.t1pre = W.at<float>(P.t1pre); td.t1_sum = st_t1; td.t1_sumsq = st_t1 + G * 10;
   td.gamma = pf("text_decoder.net.1.weight"); td.beta = pf("text_decoder.net.1.bias");
   td.running_mean = bf("text_decoder.net.1.running_mean"); td.running_var = bf("text_decoder.net.1.running_var");
-  td.momentum = mom; td.bn_eps = bn_eps; td.training = 1;
+  td.momentum = mom; td.bn_eps = bn_eps; td.training = training ? 1 : 0;
   td.w2 = pf("text_decoder.net.3.weight"); td.b2 = pf("text_decoder.net.3.bias");
   td.labels = reinterpret_cast<const long long*>(a->text);
   for (int t = 0; t < G; ++t) td.ce_scale[t] = a->lambda_text[t] / static_cast<float>(B);
-  td.fused_loss = 1; td.backward = bwd ? 1 : 0;
+  td.fused_loss = module_bwd ? 0 : 1; td.backward = (bwd && !module_bwd) ? 1 : 0;
+  td.dlogp_up = a->d_recon_text;
   td.logp = a->out_recon_text; td.ce = losses + kMaxGroups;
   td.dyhat = W.at<float>(P.dyt); td.s0 = sb_t1; td.s1 = sb_t1 + G * 10;
   td.d_w2 = gf("text_decoder.net.3.weight"); td.d_b2 = gf("text_decoder.net.3.bias");
   if (dep(st, s2)) return 1;  // fork: text decoder beside the image decoder
-  MVAE_STEP(launch_textdec(td, s2), "launch_textdec");
+  if (fwd) MVAE_STEP(launch_textdec(td, s2), "launch_textdec");
 
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
-  MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
-               pf("image_decoder.net.0.bias"), st_d1, st_d1 + G * 200, B, st), "gemm_fwd:image_decoder.net.0.weight#9");
-  MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, st_d1, st_d1 + G * 200,
+  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
+               pf("image_decoder.net.0.bias"), training ? st_d1 : nullptr, training ? st_d1 + G * 200 : nullptr, B, st), "gemm_fwd:image_decoder.net.0.weight#9");
+  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
                         pf("image_decoder.net.1.weight"), pf("image_decoder.net.1.bias"), sv_d1, sv_d1 + G * 200,
                         bf("image_decoder.net.1.running_mean"), bf("image_decoder.net.1.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.1.weight#10");
-  MVAE_STEP(gemm_fwd(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
-               pf("image_decoder.net.3.bias"), st_d2, st_d2 + G * 400, B, st), "gemm_fwd:image_decoder.net.3.weight#11");
-  MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, st_d2, st_d2 + G * 400,
+  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
+               pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st), "gemm_fwd:image_decoder.net.3.weight#11");
+  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
@@ -478,11 +492,24 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     for (int t = 0; t < G; ++t) g.epi.bce_scale[t] = a->lambda_image[t] / (static_cast<float>(B) * 784.f);
     g.epi.loss = losses;
     g.epi.probs = a->out_recon_image;
-    MVAE_STEP(launch_gemm(g, st), "gemm_fwd_bce:image_decoder.net.6.weight");
+    if (fwd) MVAE_STEP(launch_gemm(g, st), "gemm_fwd_bce:image_decoder.net.6.weight");
   }
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist
   // ================================================================ backward
   if (bwd) {
+    if (module_bwd) {
+      // autograd path: dlogits = d(recon_image) * p * (1 - p) from the probabilities the forward returned
+      // (+ the last Linear's bias gradient), and the text decoder's backward from d(log-probs)
+      if (a->d_recon_image != nullptr) {
+        MVAE_STEP(launch_sigmoid_backward(dt, a->d_recon_image, a->out_recon_image, W.at<void>(P.dlog), R, 784,
+                                          gf("image_decoder.net.6.bias"), st), "launch_sigmoid_backward");
+      } else {
+        MVAE_CUDA(cudaMemsetAsync(W.at<void>(P.dlog), 0, static_cast<size_t>(R) * 784 * (dt == MVAE_DT_F32 ? 4 : 2), st));
+      }
+      td.backward = 1;
+      MVAE_STEP(launch_textdec(td, st), "launch_textdec(bwd)");
+      if (dep(st, s2)) return 1;
+    }
     // ---- image decoder
     MVAE_STEP(gemm_dgrad(dt, R, 400, 784, W.at<void>(P.dlog), wop("image_decoder.net.6.weight"), W.at<void>(P.dy2), dt,
                    W.at<void>(P.g2pre), sv_d2, sv_d2 + G * 400, pf("image_decoder.net.4.weight"),
@@ -506,7 +533,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
 
     // ---- tail backward (text decoder front + reparametrize + KL + PoE)
     ta.dz = W.at<float>(P.dz);
-    ta.dmu_up = nullptr; ta.dlogvar_up = nullptr;
+    ta.dmu_up = a->d_mu; ta.dlogvar_up = a->d_logvar;
     ta.t1_dyhat = W.at<float>(P.dyt); ta.t1_s0 = sb_t1; ta.t1_s1 = sb_t1 + G * 10;
     ta.t1_gamma = pf("text_decoder.net.1.weight");
     ta.d_enc = W.at<void>(P.denc);

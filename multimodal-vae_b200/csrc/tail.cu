@@ -56,11 +56,18 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long seed, uint32_t 
              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
   const float u1 = (static_cast<float>(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float rad = sqrtf(-2.0f * logf(u1));
+  const float rad = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(rad * c, rad * s);
 }
+
+// Fast SFU forms (ex2/lg2/rcp.approx + one FMA): relative error ~1e-6 for the magnitudes that occur here
+// (|logvar| < ~20), far inside the parity tolerances; the tail kernels are instruction-bound, these cut the
+// transcendental cost 5x.
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.f, x); }
 
 // ---------------------------------------------------------------- PoE on one latent element, M <= 2 experts
 // Everything the backward needs is kept so that no transcendental is evaluated twice:
@@ -81,23 +88,23 @@ __device__ __forceinline__ Poe poe_eval(int mode, int prior, float eps, const fl
 #pragma unroll
   for (int i = 0; i < 2; ++i)
     if (present[i]) {
-      const float var = expf(lv[i]) + eps;
-      const float inv = 1.f / var;
+      const float var = fexp(lv[i]) + eps;
+      const float inv = frcp(var);
       r.var[i] = var;
       r.inv[i] = inv;
       num += m[i] * (mode == MVAE_POE_REF ? var : inv);
       S += var;
       P += inv;
     }
-  r.pd_var = 1.f / P;
+  r.pd_var = frcp(P);
   if (mode == MVAE_POE_REF) {
-    r.invS = 1.f / S;
+    r.invS = frcp(S);
     r.mu = num * r.invS;
   } else {
     r.invS = r.pd_var;
     r.mu = num * r.pd_var;
   }
-  r.logvar = kNeedLogvar ? logf(r.pd_var) : 0.f;
+  r.logvar = kNeedLogvar ? flog(r.pd_var) : 0.f;
   return r;
 }
 // Gradients w.r.t. expert i's (mu_i, logvar_i) given d(mu), d(logvar) of the product.
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
     const int g = static_cast<int>(it / a.B);
     const int b = static_cast<int>(it - static_cast<long long>(g) * a.B);
     const int ty = a.group_type[g];
-    const bool present[2] = {ty != TERM_TEXT, ty != TERM_IMAGE};
+    const bool present[2] = {ty != TERM_TEXT && a.enc_img != nullptr, ty != TERM_IMAGE && a.txt_table != nullptr};
     const int label = present[1] ? static_cast<int>(a.labels[b]) : 0;
     float t1[kTD];
 #pragma unroll
@@ -169,18 +176,24 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
           e2 = normal_pair(a.seed, step, (it * n + k) >> 1);
       }
       const float ee[2] = {e2.x, e2.y};
-      float zz[2], mm[2], ll[2];
+      float zz[2] = {0.f, 0.f}, mm[2] = {0.f, 0.f}, ll[2] = {0.f, 0.f};
+      if (a.z_in != nullptr) {  // decode_image / decode_text: the caller's latents, no experts
+        const float2 zi = *reinterpret_cast<const float2*>(a.z_in + it * n + k);
+        zz[0] = zi.x;
+        zz[1] = zi.y;
+      } else {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float m[2] = {mi[c], mt[c]};
-        const float lv[2] = {li[c], lt[c]};
-        const Poe r = poe_eval<true>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
-        mm[c] = r.mu;
-        ll[c] = r.logvar;
-        // reparametrize (mnist/model.py:25-28): std = exp(0.5*logvar) = sqrt(pd_var); z = eps*std + mu
-        zz[c] = a.training ? ee[c] * sqrtf(r.pd_var) + r.mu : r.mu;
-        // KL integrand of mnist/train.py:79 (exp(logvar) = pd_var)
-        klacc += 1.f + r.logvar - r.mu * r.mu - r.pd_var;
+        for (int c = 0; c < 2; ++c) {
+          const float m[2] = {mi[c], mt[c]};
+          const float lv[2] = {li[c], lt[c]};
+          const Poe r = poe_eval<true>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
+          mm[c] = r.mu;
+          ll[c] = r.logvar;
+          // reparametrize (mnist/model.py:25-28): std = exp(0.5*logvar) = sqrt(pd_var); z = eps*std + mu
+          zz[c] = a.training ? ee[c] * sqrtf(r.pd_var) + r.mu : r.mu;
+          // KL integrand of mnist/train.py:79 (exp(logvar) = pd_var)
+          klacc += 1.f + r.logvar - r.mu * r.mu - r.pd_var;
+        }
       }
       store_pair(reinterpret_cast<ZT*>(a.z) + it * n + k, zz[0], zz[1]);
       if (a.mu != nullptr) {
@@ -273,19 +286,19 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
     const long long row = static_cast<long long>(g) * a.B + b;
     if (active) {
       const int label = present[1] ? static_cast<int>(a.labels[b]) : 0;
-      // text decoder: gradient at its first Linear's output (BatchNorm backward apply); every lane computes all ten
+      // text decoder: gradient at its first Linear's output (BatchNorm backward apply): lane j computes feature j,
+      // then the ten values are broadcast to every lane (full-warp shuffles, outside the latent loop)
+      float dt_mine = 0.f;
+      if (text_dec && lane < kTD) {
+        const float x = a.t1pre[row * kTD + lane];
+        const float xh = (x - s_co[(g * 4 + 0) * kTD + lane]) * s_co[(g * 4 + 1) * kTD + lane];
+        const float dy = a.t1_dyhat[row * kTD + lane];
+        dt_mine = a.t1_gamma[lane] * s_co[(g * 4 + 1) * kTD + lane] *
+                  (dy - s_co[(g * 4 + 2) * kTD + lane] - xh * s_co[(g * 4 + 3) * kTD + lane]);
+      }
       float dtb[kTD];
 #pragma unroll
-      for (int j = 0; j < kTD; ++j) {
-        dtb[j] = 0.f;
-        if (text_dec) {
-          const float x = a.t1pre[row * kTD + j];
-          const float xh = (x - s_co[(g * 4 + 0) * kTD + j]) * s_co[(g * 4 + 1) * kTD + j];
-          const float dy = a.t1_dyhat[row * kTD + j];
-          dtb[j] = a.t1_gamma[j] * s_co[(g * 4 + 1) * kTD + j] *
-                   (dy - s_co[(g * 4 + 2) * kTD + j] - xh * s_co[(g * 4 + 3) * kTD + j]);
-        }
-      }
+      for (int j = 0; j < kTD; ++j) dtb[j] = __shfl_sync(0xffffffffu, dt_mine, j);
       for (int k = lane * 2; k < n; k += 64) {
         const bool first_pass = k < 64;
         float mi[2] = {0.f, 0.f}, li[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f}, lt[2] = {0.f, 0.f};
@@ -532,11 +545,14 @@ __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
           if (o == label) ce = -sc * lp[o];  // F.nll_loss mean (mnist/train.py:73)
         }
       } else {
-        float su = 0.f;
+        float su = 0.f, up[kTD];
 #pragma unroll
-        for (int o = 0; o < kTD; ++o) su += a.dlogp_up[row * kTD + o];
+        for (int o = 0; o < kTD; ++o) {
+          up[o] = a.dlogp_up != nullptr ? a.dlogp_up[row * kTD + o] : 0.f;
+          su += up[o];
+        }
 #pragma unroll
-        for (int o = 0; o < kTD; ++o) dl[o] = a.dlogp_up[row * kTD + o] - expf(lp[o]) * su;
+        for (int o = 0; o < kTD; ++o) dl[o] = up[o] - expf(lp[o]) * su;  // log_softmax backward
       }
 #pragma unroll
       for (int j = 0; j < kTD; ++j) {
@@ -802,6 +818,7 @@ int check_tail(const TailArgs& a) {
   for (int g = 0; g < a.G; ++g) {
     const int t = a.group_type[g];
     MVAE_REQUIRE(t >= 0 && t <= 2, "tail: bad term type %d", t);
+    if (a.z_in != nullptr) continue;
     MVAE_REQUIRE(t == TERM_TEXT || a.enc_img != nullptr, "tail: term %d needs the image expert", g);
     MVAE_REQUIRE(t == TERM_IMAGE || (a.txt_table != nullptr && a.labels != nullptr), "tail: term %d needs the text expert", g);
   }
@@ -849,7 +866,7 @@ int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.training || (a.running_mean && a.running_var), "textdec: running statistics missing");
   if (a.backward) {
     MVAE_REQUIRE(a.dyhat && a.s0 && a.s1, "textdec: backward outputs missing");
-    MVAE_REQUIRE(a.fused_loss ? a.labels != nullptr : a.dlogp_up != nullptr, "textdec: labels / upstream gradient missing");
+    MVAE_REQUIRE(!a.fused_loss || a.labels != nullptr, "textdec: labels missing");
   }
   const long long rows = static_cast<long long>(a.G) * a.B;
   const int blocks = static_cast<int>((rows + 255) / 256);

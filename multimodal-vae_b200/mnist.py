@@ -93,6 +93,8 @@ class MVAE(nn.Module):
         self._table = tensor_table(self.n_latents)
         self.image_encoder, self.image_decoder = _Block(), _Block()
         self.text_encoder, self.text_decoder = _Block(), _Block()
+        from .functional import ProductOfExperts
+        self.experts = ProductOfExperts("ref" if self.poe_mode == _lib.POE_REF else "precision", self.prior_expert)
         for name, kind, shape, off in self._table:
             block, _, idx, leaf = name.split(".")
             net = getattr(self, block).net
@@ -112,6 +114,7 @@ class MVAE(nn.Module):
                 holder.register_buffer(leaf, self.flat_nbt[off])
         self.reset_parameters()
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._injected_noise = []
         self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
 
     # ------------------------------------------------------------------ parameters
@@ -200,7 +203,8 @@ class MVAE(nn.Module):
 
     # ------------------------------------------------------------------ the C call
     def _build_args(self, image, text, terms: Sequence[int], lambdas, kl_weights, eps=None, backward=False,
-                    zero_grad=True, adam=None, outputs=False, grad_scale=1.0, losses=None):
+                    zero_grad=True, adam=None, outputs=False, grad_scale=1.0, losses=None, workspace=None,
+                    grads=None, extra=None):
         B = image.shape[0]
         G = len(terms)
         if image.dtype != self.act_dtype() or not image.is_contiguous() or image.shape[1] != 784:
@@ -221,7 +225,7 @@ class MVAE(nn.Module):
         a.params_bf16 = None if self.flat_params_bf16 is None else self.flat_params_bf16.data_ptr()
         a.buffers = self.flat_buffers.data_ptr()
         a.num_batches_tracked = self.flat_nbt.data_ptr()
-        a.grads = self.flat_grads.data_ptr()
+        a.grads = (self.flat_grads if grads is None else grads).data_ptr()
         a.do_backward, a.zero_grad = int(backward), int(zero_grad)
         a.adam_step = self._step_counter.data_ptr()
         a.grad_scale = float(grad_scale)
@@ -229,7 +233,7 @@ class MVAE(nn.Module):
             a.do_adam = 1
             a.adam_m, a.adam_v = adam["m"].data_ptr(), adam["v"].data_ptr()
             a.lr, a.beta1, a.beta2, a.adam_eps = adam["lr"], adam["betas"][0], adam["betas"][1], adam["eps"]
-        ws = self.workspace(B)
+        ws = self.workspace(B) if workspace is None else workspace
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         if losses is None:
             losses = torch.empty(G, 4, device=self.device_, dtype=torch.float32)
@@ -243,6 +247,8 @@ class MVAE(nn.Module):
             a.out_recon_image, a.out_recon_text = ri.data_ptr(), rt.data_ptr()
             a.out_mu, a.out_logvar = mu.data_ptr(), lv.data_ptr()
             outs = (ri, rt, mu, lv)
+        for k, v in (extra or {}).items():
+            setattr(a, k, v)
         return a, losses, outs
 
     def _run(self, image, text, terms, lambdas, kl_weights, **kw):
@@ -263,23 +269,137 @@ class MVAE(nn.Module):
         return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), float(ms[i])) for i in range(n.value)]
 
     # ------------------------------------------------------------------ reference surface
-    def forward(self, image=None, text=None):
-        """MultimodalVAE.forward (mnist/model.py:53-84): (recon_image probs, recon_text log-probs, mu, logvar).
+    def new_workspace(self, batch: int) -> torch.Tensor:
+        si = sizes(self.n_latents, batch, self.dtype_code)
+        ws = torch.empty(si.workspace_bytes + 256, device=self.device_, dtype=torch.uint8)
+        return ws[(-ws.data_ptr()) % 256:]
 
-        Train mode uses batch statistics (and advances the running statistics) and samples z; this entry does
-        not build an autograd graph - training goes through MVAETrainer.step, which fuses the three terms."""
+    def _prep_inputs(self, image, text):
         assert image is not None or text is not None
-        if not self.training:
-            raise NotImplementedError("eval-mode forward (running statistics) is the next row of SURVEY 8f")
         term = TERMS["joint"] if (image is not None and text is not None) else (
             TERMS["image"] if image is not None else TERMS["text"])
         B = image.shape[0] if image is not None else text.shape[0]
         x = self.to_act(image) if image is not None else torch.zeros(B, 784, device=self.device_, dtype=self.act_dtype())
         y = (text.to(self.device_).long().contiguous() if text is not None
              else torch.zeros(B, device=self.device_, dtype=torch.int64))
-        _, outs = self._run(x, y, [term], [(0.0, 0.0)], [0.0], outputs=True)
+        return term, B, x, y
+
+    def forward(self, image=None, text=None):
+        """MultimodalVAE.forward (mnist/model.py:53-84): (recon_image probs, recon_text log-probs, mu, logvar).
+
+        train(): batch statistics (running statistics advance), z sampled; the outputs carry an autograd graph
+        whose backward runs the library's backward kernels, so the reference loop (three forwards,
+        `loss_function`, `.backward()`, any torch optimizer) works unchanged.  eval(): running statistics, z = mu.
+        The fast path for training is MVAETrainer.step, which fuses the three terms."""
+        term, B, x, y = self._prep_inputs(image, text)
+        if not self.training:
+            with torch.no_grad():
+                _, outs = self._run(x, y, [term], [(0.0, 0.0)], [0.0], outputs=True, extra={"eval_mode": 1})
+            ri, rt, mu, lv = outs
+            return ri, rt, mu[0], lv[0]
+        if self._injected_noise:   # tests: the N(0,1) draw of reparametrize (mnist/model.py:27) can be injected
+            eps = self._injected_noise.pop(0).to(self.device_, torch.float32).reshape(1, B, self.n_latents).contiguous()
+        else:
+            eps = torch.randn(1, B, self.n_latents, device=self.device_, dtype=torch.float32)
+        if torch.is_grad_enabled():
+            return _MVAEForwardFn.apply(self, x, y, term, eps, *self.parameters())
+        _, outs = self._run(x, y, [term], [(0.0, 0.0)], [0.0], eps=eps, outputs=True)
         ri, rt, mu, lv = outs
-        return ri.float(), rt, mu[0], lv[0]
+        return ri, rt, mu[0], lv[0]
+
+    # sub-calls used by the reference's sampling / visualisation scripts (mnist/sample.py:78-116, manifold.py:49)
+    @torch.no_grad()
+    def encode_image(self, x):
+        """ImageEncoder (mnist/model.py:99-117): (mu, logvar) of the image expert."""
+        _, B, xa, y = self._prep_inputs(x, None)
+        self._run(xa, y, [TERMS["image"]], [(0.0, 0.0)], [0.0], extra={"eval_mode": int(not self.training)})
+        enc = self.debug_buffer("enc", B, (B, 2 * self.n_latents), torch.float32).clone()
+        return enc[:, :self.n_latents], enc[:, self.n_latents:]
+
+    @torch.no_grad()
+    def encode_text(self, x):
+        """TextEncoder (mnist/model.py:138-153): (mu, logvar) of the text expert."""
+        _, B, xa, y = self._prep_inputs(None, x)
+        self._run(xa, y, [TERMS["text"]], [(0.0, 0.0)], [0.0], extra={"eval_mode": int(not self.training)})
+        table = self.debug_buffer("txt_table", B, (10, 2 * self.n_latents), torch.float32).clone()
+        out = table[y]
+        return out[:, :self.n_latents], out[:, self.n_latents:]
+
+    @torch.no_grad()
+    def _decode(self, z):
+        z = z.to(self.device_, torch.float32).contiguous()
+        B = z.shape[0]
+        x = torch.zeros(B, 784, device=self.device_, dtype=self.act_dtype())
+        y = torch.zeros(B, device=self.device_, dtype=torch.int64)
+        _, outs = self._run(x, y, [TERMS["joint"]], [(0.0, 0.0)], [0.0], outputs=True,
+                            extra={"eval_mode": int(not self.training), "z_in": z.data_ptr()})
+        return outs[0], outs[1]
+
+    def decode_image(self, x):
+        """ImageDecoder (mnist/model.py:120-135): pixel probabilities for latents x."""
+        return self._decode(x)[0]
+
+    def decode_text(self, x):
+        """TextDecoder (mnist/model.py:156-170): label log-probabilities for latents x."""
+        return self._decode(x)[1]
+
+    def reparametrize(self, mu, logvar):
+        """mnist/model.py:24-30 (host-side convenience, not on the hot path)."""
+        if self.training:
+            return torch.randn_like(mu) * torch.exp(0.5 * logvar) + mu
+        return mu
+
+    def prior(self, size, use_cuda=True):
+        """mnist/model.py:44-51."""
+        return torch.zeros(size, device=self.device_), torch.zeros(size, device=self.device_)
+
+    def gen_latents(self, image, text):
+        """mnist/model.py:86-96: a sample from the joint posterior q(z | image, text)."""
+        with torch.no_grad():
+            mu_i, lv_i = self.encode_image(image)
+            mu_t, lv_t = self.encode_text(text)
+            mu, lv = self.experts(torch.stack((mu_i, mu_t)), torch.stack((lv_i, lv_t)))
+            return self.reparametrize(mu, lv)
+
+
+class _MVAEForwardFn(torch.autograd.Function):
+    """Autograd bridge of MVAE.forward: forward = one forward-only C call on a private workspace; backward = one
+    backward-only C call (phase 2) fed with the upstream gradients of (recon_image, recon_text, mu, logvar)."""
+
+    @staticmethod
+    def forward(ctx, model, x, y, term, eps, *params):
+        B = x.shape[0]
+        ws = model.new_workspace(B)
+        _, outs = model._run(x, y, [term], [(0.0, 0.0)], [0.0], eps=eps, outputs=True, workspace=ws)
+        ri, rt, mu, lv = outs
+        ctx.model, ctx.ws, ctx.x, ctx.y, ctx.term, ctx.eps = model, ws, x, y, term, eps
+        ctx.save_for_backward(ri)
+        return ri, rt, mu[0].clone(), lv[0].clone()
+
+    @staticmethod
+    def backward(ctx, g_ri, g_rt, g_mu, g_lv):
+        m = ctx.model
+        (ri,) = ctx.saved_tensors
+
+        def c(t, dtype):
+            return None if t is None else t.to(dtype).contiguous()
+
+        g_ri, g_rt = c(g_ri, m.act_dtype()), c(g_rt, torch.float32)
+        g_mu, g_lv = c(g_mu, torch.float32), c(g_lv, torch.float32)
+        grads = torch.zeros_like(m.flat_params)
+        extra = {"phase": 2, "d_recon_image": _lib.ptr(g_ri), "d_recon_text": _lib.ptr(g_rt),
+                 "d_mu": _lib.ptr(g_mu), "d_logvar": _lib.ptr(g_lv), "out_recon_image": ri.data_ptr()}
+        a, _, _ = m._build_args(ctx.x, ctx.y, [ctx.term], [(0.0, 0.0)], [0.0], eps=ctx.eps, backward=True,
+                                zero_grad=False, workspace=ctx.ws, grads=grads, extra=extra)
+        _lib.check(_lib.load().mvae_mnist_step(C.byref(a), _stream_ptr()), "mvae_mnist_step(backward)")
+        out = []
+        for name, kind, shape, off in m._table:
+            if kind == 0:
+                numel = 1
+                for s_ in shape:
+                    numel *= s_
+                out.append(grads[off:off + numel].view(shape))
+        return (None, None, None, None, None, *out)
 
 
 MultimodalVAE = MVAE  # the reference's class name (mnist/model.py:14)
@@ -359,3 +479,80 @@ class MVAETrainer:
         ent["graph"].replay()
         self.last_graph_launches = ent["launches"]
         return ent["losses"]
+
+
+class HostPipeline:
+    """Feeds host batches to a trainer with the copies overlapped with compute (the public end-to-end path).
+
+    Batches are (image uint8/float32 [B,784] or [B,1,28,28], labels int64 [B]) in PINNED host memory.  Batch i+1
+    is uploaded on a copy stream while step i runs; each step's [n_terms, 4] loss tensor is copied back to a pinned
+    host buffer asynchronously and handed out one step later (so the host never stalls the GPU).  Every step's
+    inputs cross host->device and every step's result crosses device->host.
+    """
+
+    def __init__(self, trainer: "MVAETrainer", depth: int = 2):
+        self.trainer = trainer
+        self.dev = trainer.model.device_
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.depth = depth
+        self._slots = []
+
+    def _slot(self, i, image, labels):
+        while len(self._slots) <= i:
+            self._slots.append(None)
+        sl = self._slots[i]
+        if sl is None or sl["x"].shape != image.shape or sl["x"].dtype != image.dtype:
+            sl = {"x": torch.empty(image.shape, dtype=image.dtype, device=self.dev),
+                  "y": torch.empty(labels.shape, dtype=labels.dtype, device=self.dev),
+                  "ready": torch.cuda.Event(), "free": torch.cuda.Event(),
+                  "loss_host": None, "loss_evt": torch.cuda.Event()}
+            self._slots[i] = sl
+        return sl
+
+    def run(self, batches, **step_kwargs):
+        """Generator over the per-step host loss arrays ([n_terms, 4] pinned float32 tensors)."""
+        main = torch.cuda.current_stream(self.dev)
+        it = iter(batches)
+        pending = []           # (slot index) uploaded, waiting to be stepped
+        inflight = []          # slots whose loss copy has been enqueued
+        idx = 0
+
+        def upload(k, batch):
+            image, labels = batch
+            sl = self._slot(k, image, labels)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(sl["free"])            # previous use of this slot has been consumed
+                sl["x"].copy_(image, non_blocking=True)
+                sl["y"].copy_(labels, non_blocking=True)
+                sl["ready"].record(self.copy_stream)
+            return sl
+
+        nslots = self.depth + 1
+        for _ in range(self.depth):
+            b = next(it, None)
+            if b is None:
+                break
+            pending.append(upload(idx % nslots, b))
+            idx += 1
+        while pending:
+            sl = pending.pop(0)
+            main.wait_event(sl["ready"])
+            losses, _ = self.trainer.step(sl["x"], sl["y"], **step_kwargs)
+            sl["free"].record(main)
+            if sl["loss_host"] is None or sl["loss_host"].shape != losses.shape:
+                sl["loss_host"] = torch.empty(losses.shape, dtype=losses.dtype).pin_memory()
+            sl["loss_host"].copy_(losses, non_blocking=True)
+            sl["loss_evt"].record(main)
+            inflight.append(sl)
+            b = next(it, None)
+            if b is not None:
+                pending.append(upload(idx % nslots, b))
+                idx += 1
+            if len(inflight) > 1:
+                done = inflight.pop(0)
+                done["loss_evt"].synchronize()
+                yield done["loss_host"]
+        for done in inflight:
+            done["loss_evt"].synchronize()
+            yield done["loss_host"]
+

@@ -1,0 +1,162 @@
+"""GPU tests of the reference-facing module surface: ProductOfExperts (+mask), loss_function / elbo_loss,
+MVAE.forward with autograd (the reference's own three-forward training loop), eval mode, sub-calls."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import mnist_oracle as O
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_poe_kat1_ref_vs_precision():
+    import mvae_b200
+    mu = torch.tensor([[0.0], [2.0]]).view(2, 1, 1).cuda()
+    lv = torch.tensor([[0.0], [math.log(3.0)]]).view(2, 1, 1).cuda()
+    pm, pl = mvae_b200.ProductOfExperts()(mu, lv)
+    assert float(pm) == pytest.approx(1.5, abs=1e-6)           # the reference's variance-weighted mean (KAT-1)
+    assert float(pl) == pytest.approx(math.log(0.75), abs=1e-6)
+    pm2, pl2 = mvae_b200.ProductOfExperts("precision")(mu, lv)
+    assert float(pm2) == pytest.approx(0.5, abs=1e-6)          # the paper's precision-weighted mean
+    assert float(pl2) == pytest.approx(math.log(0.75), abs=1e-6)
+
+
+@pytest.mark.parametrize("mode,prior,masked", [("ref", False, False), ("precision", False, False),
+                                               ("precision", True, True), ("ref", False, True)])
+def test_poe_matches_oracle_forward_backward(mode, prior, masked):
+    import mvae_b200
+    g = torch.Generator().manual_seed(3)
+    M, B, D = 3, 37, 20
+    mu = torch.randn(M, B, D, generator=g)
+    lv = torch.randn(M, B, D, generator=g)
+    mask = None
+    if masked:
+        mask = (torch.rand(M, B, generator=g) > 0.4).float()
+        mask[0] = 1.0  # at least one expert per sample
+    mu_r, lv_r = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    if mode == "ref" and not masked:
+        pm, pl = O.product_of_experts(mu_r, lv_r)
+    elif mode == "ref":
+        var = torch.exp(lv_r) + 1e-8
+        w = mask.unsqueeze(-1)
+        pm = (mu_r * var * w).sum(0) / (var * w).sum(0)
+        pl = torch.log(1.0 / (w / var).sum(0))
+    else:
+        pm, pl = O.product_of_experts_precision(mu_r, lv_r, mask, prior)
+    gm, gl = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+    (pm * gm + pl * gl).sum().backward()
+    mu_d, lv_d = mu.cuda().requires_grad_(True), lv.cuda().requires_grad_(True)
+    dm, dl = mvae_b200.ProductOfExperts(mode, prior)(mu_d, lv_d, None if mask is None else mask.cuda())
+    (dm * gm.cuda() + dl * gl.cuda()).sum().backward()
+    np.testing.assert_allclose(dm.detach().cpu().numpy(), pm.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(dl.detach().cpu().numpy(), pl.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(mu_d.grad.cpu().numpy(), mu_r.grad.numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(lv_d.grad.cpu().numpy(), lv_r.grad.numpy(), rtol=2e-4, atol=2e-6)
+
+
+def test_loss_function_matches_reference_semantics():
+    import mvae_b200
+    g = torch.Generator().manual_seed(5)
+    B, n = 33, 16
+    mu, lv = torch.randn(B, n, generator=g), torch.randn(B, n, generator=g) * 0.3
+    ri = torch.rand(B, 784, generator=g).clamp(1e-4, 1 - 1e-4)
+    img = torch.rand(B, 784, generator=g)
+    rt = torch.log_softmax(torch.randn(B, 10, generator=g), 1)
+    txt = torch.randint(0, 10, (B,), generator=g)
+    # KAT-2 / KAT-3 of SURVEY section 4
+    k2 = mvae_b200.loss_function(torch.zeros(4, 64).cuda(), torch.zeros(4, 64).cuda(), torch.full((4, 784), 0.5).cuda(),
+                                 torch.rand(4, 784).cuda(), torch.full((4, 10), math.log(0.1)).cuda(),
+                                 torch.randint(0, 10, (4,)).cuda())
+    assert float(k2) == pytest.approx(math.log(2) + math.log(10), abs=2e-6)
+    k3 = mvae_b200.loss_function(torch.ones(5, 64).cuda(), torch.zeros(5, 64).cuda())
+    assert float(k3) == pytest.approx(0.5 * 64 * 3 / 784, abs=1e-7)
+    for lam in ((1.0, 1.0), (1.0, 0.5), (0.0, 1.0)):
+        leaves = [t.clone().requires_grad_(True) for t in (mu, lv, ri, rt)]
+        ref = O.loss_function(leaves[0], leaves[1], leaves[2], img, leaves[3], txt, lam[0], lam[1])
+        ref.backward()
+        dleaves = [t.cuda().requires_grad_(True) for t in (mu, lv, ri, rt)]
+        got = mvae_b200.loss_function(dleaves[0], dleaves[1], dleaves[2], img.cuda(), dleaves[3], txt.cuda(), lam[0], lam[1])
+        got.backward()
+        assert float(got) == pytest.approx(float(ref), rel=2e-6)
+        for a, b in zip(dleaves, leaves):
+            np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-8)
+    e = mvae_b200.elbo_loss(ri.cuda(), img.cuda(), rt.cuda(), txt.cuda(), mu.cuda(), lv.cuda(), 1.0, 1.0, 0.25)
+    r = O.loss_function(mu, lv, ri, img, rt, txt) - 0.75 * O.loss_function(mu, lv)
+    assert float(e) == pytest.approx(float(r), rel=2e-6)
+
+
+def test_reference_training_loop_with_autograd():
+    """mnist/train.py:132-148 verbatim on the drop-in module: three forwards, three loss_function calls, backward."""
+    import mvae_b200
+    B, n, seed = 96, 16, 2
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    losses, grads, bufs, _ = O.train_step(state, image, text, noises)
+    vae = mvae_b200.MultimodalVAE(n_latents=n, precision="tf32")
+    vae.load_state_dict(state)
+    vae.train()
+    vae._injected_noise = [x.clone() for x in noises]
+    optimizer = torch.optim.Adam(vae.parameters(), lr=1e-3)
+    optimizer.zero_grad()
+    img_d, txt_d = image.cuda(), text.cuda()
+    r1 = vae(img_d, txt_d)
+    r2 = vae(image=img_d)
+    r3 = vae(text=txt_d)
+    l1 = mvae_b200.loss_function(r1[2], r1[3], recon_image=r1[0], image=img_d, recon_text=r1[1], text=txt_d)
+    l2 = mvae_b200.loss_function(r2[2], r2[3], recon_image=r2[0], image=img_d, recon_text=r2[1], text=txt_d)
+    l3 = mvae_b200.loss_function(r3[2], r3[3], recon_image=r3[0], image=img_d, recon_text=r3[1], text=txt_d)
+    (l1 + l2 + l3).backward()
+    np.testing.assert_allclose([float(l1), float(l2), float(l3)], losses, rtol=3e-5)
+    sd = vae.state_dict()
+    for k, v in bufs.items():                      # KAT-4 bookkeeping: 2 / 2 / 3 / 3
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+    for name, p in vae.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            continue
+        assert rel_l2(p.grad, grads[name]) < 6e-2, (name, rel_l2(p.grad, grads[name]))
+    optimizer.step()
+
+
+def test_eval_mode_forward_and_subcalls():
+    import mvae_b200
+    B, n, seed = 40, 16, 7
+    state = O.perturbed_state(n, seed)
+    g = torch.Generator().manual_seed(1)
+    for k in state:   # non-trivial running statistics
+        if k.endswith("running_mean"):
+            state[k] = 0.1 * torch.randn(state[k].shape, generator=g)
+        if k.endswith("running_var"):
+            state[k] = 0.5 + torch.rand(state[k].shape, generator=g)
+    image, text, _ = O.synthetic_batch(B, n, seed)
+    vae = mvae_b200.MVAE(n, precision="tf32")
+    vae.load_state_dict(state)
+    vae.eval()
+    for args in ((image, text), (image, None), (None, text)):
+        ri, rt, mu, lv = vae(None if args[0] is None else args[0].cuda(), None if args[1] is None else args[1].cuda())
+        o = O.forward(state, args[0], args[1], None, None, training=False)
+        assert rel_l2(ri.float(), o[0]) < 1e-3 and rel_l2(rt, o[1]) < 1e-3
+        assert rel_l2(mu, o[2]) < 2e-3 and rel_l2(lv, o[3]) < 2e-3
+    sd = vae.state_dict()
+    for k, v in state.items():                      # eval mode updates nothing
+        if O.is_buffer(k):
+            assert torch.equal(sd[k].cpu(), v), k
+    # sub-calls of mnist/sample.py / manifold.py
+    mi, li = vae.encode_image(image.cuda())
+    om, ol = O.image_encoder(state, image, None, training=False)
+    assert rel_l2(mi, om) < 2e-3 and rel_l2(li, ol) < 2e-3
+    mt, lt = vae.encode_text(text.cuda())
+    tm, tl = O.text_encoder(state, text, None, training=False)
+    assert rel_l2(mt, tm) < 1e-4 and rel_l2(lt, tl) < 1e-4
+    z = torch.randn(B, n, generator=g)
+    di, dt_ = vae.decode_image(z.cuda()), vae.decode_text(z.cuda())
+    assert rel_l2(di.float(), torch.sigmoid(O.image_decoder_logits(state, z, None, training=False))) < 1e-3
+    assert rel_l2(dt_, torch.log_softmax(O.text_decoder_logits(state, z, None, training=False), 1)) < 1e-4
+    pm, pl = vae.experts(torch.stack((mi, mt)), torch.stack((li, lt)))
+    rm, rl = O.product_of_experts(torch.stack((mi.cpu(), mt.cpu())), torch.stack((li.cpu(), lt.cpu())))
+    assert rel_l2(pm, rm) < 1e-5 and rel_l2(pl, rl) < 1e-5
+    assert vae.gen_latents(image.cuda(), text.cuda()).shape == (B, n)
+    assert vae.n_latents == n
