@@ -90,4 +90,38 @@ void set_gemm_debug_times(void* ptr, int epi_kind);
 // Tuning knobs readable from the environment (debug / bench sweeps only).
 int env_int(const char* name, int dflt);
 
+// Programmatic dependent launch (PDL).  Every kernel of the step starts with pdl_enter(): it lets the NEXT kernel
+// in the stream be scheduled as soon as all CTAs of this one are resident (its prologue - barrier init, TMEM
+// allocation, tensor-map prefetch - then overlaps this kernel's execution) and blocks until the PREVIOUS
+// kernel has completed and flushed its memory.  Because every kernel waits on its predecessor, completion is
+// transitive along the stream.  Launches go through launch_pdl(), which sets the stream-serialization attribute
+// (also honoured under CUDA-graph capture).  Measured on B200 (bench.py, graph replay): no gain (355 vs 349 us
+// per step), so plain launches are the default; MVAE_PDL=1 switches it on.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const int use_pdl = env_int("MVAE_PDL", 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx", __FILE__, __LINE__);
+  return 0;
+}
+#endif
+
 }  // namespace mvae

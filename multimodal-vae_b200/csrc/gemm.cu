@@ -343,6 +343,9 @@ __global__ void __launch_bounds__(kGemmThreads)
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) stamp(1);
+  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel;
+  // from here on global memory written by it is touched.
+  pdl_enter();
 
   // Auxiliary epilogue operand (BCE: the target image tile; dgrad: the pre-BatchNorm activations): every thread
   // copies exactly the elements its own row pass will consume into shared memory with cp.async NOW, so the
@@ -583,9 +586,7 @@ int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams&
     MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
     smem_set = dyn_smem;
   }
-  gemm_kernel<kKind, kEpi><<<grid, kGemmThreads, dyn_smem, stream>>>(ta, tb, kp);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(gemm_kernel<kKind, kEpi>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
 }
 
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
@@ -692,7 +693,10 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (block_n <= 0) {
     double best = 1e30;
     const int n_cap = 16 * ceil_div(g.N, 16);
-    for (int bn = 32; bn <= 256; bn += 16) {
+    // heavy epilogues (BCE, dgrad+BatchNorm statistics) carry an auxiliary tile in shared memory and are bound by
+    // SFU / issue rate per row, not per column: measured best at <= 128 columns (2 CTAs per SM, full lanes)
+    const int bn_max = (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) ? 128 : 256;
+    for (int bn = 32; bn <= bn_max; bn += 16) {
       if (bn > n_cap && bn != 32) break;
       int sp, st, dy, bs, bt;
       const double t = plan_for(bn, sp, st, dy, bs, bt);

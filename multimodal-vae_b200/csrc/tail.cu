@@ -135,6 +135,7 @@ __device__ __forceinline__ void store_pair(T* p, float a, float b) {
 // One warp per (term, sample): lanes own latent pairs.
 template <typename ZT>
 __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a) {
+  pdl_enter();
   __shared__ float s_stat[kMaxGroups][2][kTD];
   __shared__ float s_kl[kMaxGroups];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,6 +242,7 @@ __global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a
 constexpr int kBwdRows = 4;
 template <typename ZT>
 __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel(const TailArgs a, int smem_floats) {
+  pdl_enter();
   extern __shared__ float sm[];
   // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] |
   //         image-expert combine [rows][G][2n] | text-expert combine [rows][G][2n] | labels [rows]
@@ -455,6 +457,7 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
 // One thread per decoder row.  Forward + (optionally) the fused NLL loss and the backward down to the
 // BatchNorm output: dyhat, its two per-group column sums, and the gradients of the second Linear.
 __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
+  pdl_enter();
   __shared__ float s_mean[kMaxGroups][kTD], s_rstd[kMaxGroups][kTD];
   __shared__ float s_w2[kTD][kTD], s_b2[kTD], s_gamma[kTD], s_beta[kTD];
   __shared__ float s_dw2[kTD][kTD], s_db2[kTD], s_s0[kMaxGroups][kTD], s_s1[kMaxGroups][kTD], s_ce[kMaxGroups];
@@ -610,6 +613,7 @@ __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
 // kernel gathers from.  Single block.
 constexpr int kEmb = 50;
 __global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
+  pdl_enter();
   __shared__ float s_cnt[kTD];
   __shared__ float s_h[kTD][kEmb];
   float* sv_cnt = a.save;
@@ -686,6 +690,7 @@ __global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
 }
 
 __global__ void __launch_bounds__(256) textenc_bwd_kernel(const TextEncArgs a) {
+  pdl_enter();
   __shared__ float s_dh[kTD][kEmb];
   const float* sv_cnt = a.save;
   const float* sv_xh = a.save + kTD;
@@ -834,12 +839,8 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
   const long long items = static_cast<long long>(a.G) * a.B;
   int blocks = static_cast<int>(std::min<long long>((items + kTailWarps - 1) / kTailWarps, 148 * 8));
   if (blocks < 1) blocks = 1;
-  if (a.z_dtype == MVAE_F32)
-    tail_fwd_kernel<float><<<blocks, kTailThreads, 0, st>>>(a);
-  else
-    tail_fwd_kernel<__nv_bfloat16><<<blocks, kTailThreads, 0, st>>>(a);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+  if (a.z_dtype == MVAE_F32) return launch_pdl(tail_fwd_kernel<float>, dim3(blocks), dim3(kTailThreads), 0, st, a);
+  return launch_pdl(tail_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(kTailThreads), 0, st, a);
 }
 
 int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
@@ -852,11 +853,8 @@ int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
   int blocks = std::min(row_blocks, 148 * 2);
   const int threads = 32 * a.G * kBwdRows;
   if (a.z_dtype == MVAE_F32)
-    tail_bwd_kernel<float><<<blocks, threads, smem, st>>>(a, smem_floats);
-  else
-    tail_bwd_kernel<__nv_bfloat16><<<blocks, threads, smem, st>>>(a, smem_floats);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+    return launch_pdl(tail_bwd_kernel<float>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
+  return launch_pdl(tail_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
 }
 
 int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
@@ -870,25 +868,19 @@ int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
   }
   const long long rows = static_cast<long long>(a.G) * a.B;
   const int blocks = static_cast<int>((rows + 255) / 256);
-  textdec_kernel<<<blocks, 256, 0, st>>>(a);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(textdec_kernel, dim3(blocks), dim3(256), 0, st, a);
 }
 
 int launch_textenc_forward(const TextEncArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.B > 0 && a.n > 0 && a.labels && a.emb && a.gamma && a.beta && a.w && a.b && a.table && a.save,
                "textenc_forward: missing arguments");
-  textenc_fwd_kernel<<<1, 256, 0, st>>>(a);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(textenc_fwd_kernel, dim3(1), dim3(256), 0, st, a);
 }
 
 int launch_textenc_backward(const TextEncArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.d_table && a.d_emb && a.d_gamma && a.d_beta && a.d_w && a.d_b && a.save && a.w && a.gamma,
                "textenc_backward: missing arguments");
-  textenc_bwd_kernel<<<1, 256, 0, st>>>(a);
-  MVAE_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(textenc_bwd_kernel, dim3(1), dim3(256), 0, st, a);
 }
 
 int launch_poe_forward(int mode, int prior, float eps, int M, long long B, int D, const float* mu, const float* logvar,
