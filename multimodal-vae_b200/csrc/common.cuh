@@ -65,6 +65,26 @@ struct GemmEpilogue {
   const float* bn_beta = nullptr;  // [N]
 };
 
+// Optional transform of the A operand on its way to the tensor core: A' = relu(BatchNorm(A)) with train-mode
+// batch statistics - the BatchNorm1d + ReLU between two Linear layers (mnist/model.py:105-106 etc.) folded into
+// the consuming GEMM instead of a separate elementwise pass.  A is the pre-BatchNorm activation [M, K]
+// (K-major); statistics are per (group, feature k) column sums produced by the previous GEMM's epilogue.
+struct GemmATransform {
+  int enabled = 0;
+  const float* sum = nullptr;      // [groups][K]
+  const float* sumsq = nullptr;    // [groups][K]
+  const float* gamma = nullptr;    // [K]
+  const float* beta = nullptr;     // [K]
+  int rows_per_group = 1 << 30;    // every 128-row tile must lie inside one group
+  float eps = 1e-5f, momentum = 0.1f;
+  int updates_per_group = 1;       // running-statistics updates this pass stands for
+  float* save_mean = nullptr;      // [groups][K] out (block (0,0))
+  float* save_rstd = nullptr;      // [groups][K] out
+  float* running_mean = nullptr;   // [K] in/out (block (0,0)), may be null
+  float* running_var = nullptr;
+  void* out = nullptr;             // [M, K] materialised A' (storage dtype), written by the blockIdx.x == 0 tiles
+};
+
 struct GemmDesc {
   int kind = MVAE_F32;  // operand storage: fp32 (kind::tf32) or bf16 (kind::f16)
   int M = 0, N = 0, K = 0;
@@ -81,6 +101,7 @@ struct GemmDesc {
   int split_k = 0;  // 0 = auto (only EPI_ATOMIC may split)
   int stages = 0;   // 0 = auto
   long long* dbg = nullptr;  // device buffer [ctas][8] of %globaltimer stamps (bring-up only)
+  GemmATransform atf;
   GemmEpilogue epi;
 };
 

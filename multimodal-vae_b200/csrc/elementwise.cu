@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(kEwThreads)
           float o[N];
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            const float xh = (v[u][i] - mean[i]) * rstd[i];
-            const float t = fmaf(ga[i], xh, be[i]);
+            // folded form a*x + b, a = gamma*rstd, b = beta - mean*a: the SAME expression as the GEMM A-transform
+            // and the dgrad epilogue's mask recomputation, so all three agree bit for bit
+            const float a_ = ga[i] * rstd[i];
+            const float t = fmaf(a_, v[u][i], fmaf(-mean[i], a_, be[i]));
             o[i] = relu ? fmaxf(t, 0.f) : t;
           }
           stv(y + static_cast<long long>(rr) * F + f, o);

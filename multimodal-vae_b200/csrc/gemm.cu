@@ -48,7 +48,9 @@ struct GemmKParams {
   int aux_off;        // byte offset (dynamic smem) of the prefetched auxiliary tile, or -1
   int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
+  int coef_off;       // byte offset (dynamic smem) of the A-transform coefficient table [2][kb_total*BK], or -1
   long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
+  GemmATransform atf;
   GemmEpilogue epi;
 };
 
@@ -117,7 +119,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
   using act_t = typename ActT<kKind>::type;
   const GemmEpilogue& e = p.epi;
   float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-  float bias[4], g_mean[4], g_rstd[4], g_gamma[4], g_beta[4];
+  float bias[4], g_mean[4], g_rstd[4], g_gamma[4], g_beta[4], g_a[4] = {0.f, 0.f, 0.f, 0.f}, g_b[4] = {0.f, 0.f, 0.f, 0.f};
   float lsum = 0.f, g_scale = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -146,6 +148,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
         if (i < nv) {
           g_mean[i] = e.bn_mean[static_cast<long long>(g) * p.N + cn + i];
           g_rstd[i] = e.bn_rstd[static_cast<long long>(g) * p.N + cn + i];
+          g_a[i] = g_gamma[i] * g_rstd[i];
+          g_b[i] = fmaf(-g_mean[i], g_a[i], g_beta[i]);
         }
     }
     // Rows in batches of kRB: issue every load of the batch (staging tile + auxiliary tensor) first, then the
@@ -224,7 +228,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float xh = (aux[u][i] - g_mean[i]) * g_rstd[i];
-            const float y = fmaf(g_gamma[i], xh, g_beta[i]);
+            const float y = fmaf(g_a[i], aux[u][i], g_b[i]);  // same folded form as the forward (bitwise same mask)
             d[i] = y > 0.f ? v[u][i] : 0.f;
             acc0[i] += d[i];
             acc1[i] = fmaf(d[i], xh, acc1[i]);
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t ready_bar[kMaxStages];  // A-transform: stage transformed, MMA may read it
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_loss[4];
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&ready_bar[s], 128);
     }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_mbar_init();
@@ -346,6 +352,53 @@ __global__ void __launch_bounds__(kGemmThreads)
   // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel;
   // from here on global memory written by it is touched.
   pdl_enter();
+
+  // A-transform coefficients for this tile's statistics group: a = gamma*rstd, b = beta - mean*a (0 beyond K so
+  // that TMA's zero fill stays zero).  Block (0,0) also finalises the BatchNorm layer: saved mean/rstd for the
+  // backward and the running statistics, group by group in order (one reference forward pass per group).
+  if (p.coef_off >= 0) {
+    const GemmATransform& t = p.atf;
+    float* coef_a = reinterpret_cast<float*>(smem + p.coef_off);
+    float* coef_b = coef_a + p.kb_total * BK;
+    const int g = m0 / t.rows_per_group;
+    const int cnt = min(p.M - g * t.rows_per_group, t.rows_per_group);
+    const float inv_cnt = 1.f / cnt;
+    for (int k = threadIdx.x; k < p.kb_total * BK; k += kGemmThreads) {
+      float a = 0.f, b = 0.f;
+      if (k < p.K) {
+        const float mean = t.sum[static_cast<long long>(g) * p.K + k] * inv_cnt;
+        const float var = fmaxf(t.sumsq[static_cast<long long>(g) * p.K + k] * inv_cnt - mean * mean, 0.f);
+        a = t.gamma[k] * rsqrtf(var + t.eps);
+        b = fmaf(-mean, a, t.beta[k]);
+      }
+      coef_a[k] = a;
+      coef_b[k] = b;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t.save_mean != nullptr) {
+      const int groups = (p.M + t.rows_per_group - 1) / t.rows_per_group;
+      for (int k = threadIdx.x; k < p.K; k += kGemmThreads) {
+        float rm = t.running_mean != nullptr ? t.running_mean[k] : 0.f;
+        float rv = t.running_var != nullptr ? t.running_var[k] : 0.f;
+        for (int gg = 0; gg < groups; ++gg) {
+          const int c2 = min(p.M - gg * t.rows_per_group, t.rows_per_group);
+          const float mean = t.sum[static_cast<long long>(gg) * p.K + k] / c2;
+          const float var = fmaxf(t.sumsq[static_cast<long long>(gg) * p.K + k] / c2 - mean * mean, 0.f);
+          t.save_mean[static_cast<long long>(gg) * p.K + k] = mean;
+          t.save_rstd[static_cast<long long>(gg) * p.K + k] = rsqrtf(var + t.eps);
+          const float unb = c2 > 1 ? var * (static_cast<float>(c2) / (c2 - 1)) : var;
+          for (int u = 0; u < t.updates_per_group; ++u) {
+            rm = (1.f - t.momentum) * rm + t.momentum * mean;
+            rv = (1.f - t.momentum) * rv + t.momentum * unb;
+          }
+        }
+        if (t.running_mean != nullptr) {
+          t.running_mean[k] = rm;
+          t.running_var[k] = rv;
+        }
+      }
+    }
+    __syncthreads();
+  }
 
   // Auxiliary epilogue operand (BCE: the target image tile; dgrad: the pre-BatchNorm activations): every thread
   // copies exactly the elements its own row pass will consume into shared memory with cp.async NOW, so the
@@ -410,7 +463,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::mbar_wait(p.coef_off >= 0 ? &ready_bar[s] : &full_bar[s], ph);
         ptx::tc_fence_after();
         if (i == 0) stamp(2);
         const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
@@ -430,6 +483,69 @@ __global__ void __launch_bounds__(kGemmThreads)
       }
       ptx::umma_commit(&accum_bar);  // accumulator complete
       stamp(3);
+    }
+  } else if (warp >= 4 && p.coef_off >= 0) {
+    // ------------------------------------------------------------ A-operand transform (warps 4..7)
+    // relu(a[k]*x + b[k]) applied in place to every landed A stage (BatchNorm + ReLU of the previous layer),
+    // then handed to the MMA warp through ready_bar.  A warp covers 4 rows x 8 16-byte chunks = 512 contiguous
+    // bytes per access (conflict-free); SWIZZLE_128B puts logical chunk (c ^ (row & 7)) at physical chunk c.
+    constexpr int CE = 16 / ESZ;  // elements per 16-byte chunk
+    const float* coef_a = reinterpret_cast<const float*>(smem + p.coef_off);
+    const float* coef_b = coef_a + p.kb_total * BK;
+    const int tt = threadIdx.x - 128;
+    const int c = tt & 7, rbase = tt >> 3;
+    act_t* out = reinterpret_cast<act_t*>(p.atf.out);
+    const bool write_out = out != nullptr && blockIdx.x == 0;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (i / S) & 1;
+      ptx::mbar_wait(&full_bar[s], ph);
+      const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
+      const int kblk = (kb0 + i) * BK;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = rbase + 16 * j;
+        const int lc = c ^ (r & 7);
+        const int k = kblk + lc * CE;
+        const uint32_t addr = a_base + r * 128 + c * 16;
+        uint32_t w[4];
+        ptx::lds128_u32(addr, w);
+        float ca[CE], cb[CE], x[CE];
+#pragma unroll
+        for (int e4 = 0; e4 < CE; e4 += 4) {
+          const float4 t0 = *reinterpret_cast<const float4*>(coef_a + k + e4);
+          const float4 t1 = *reinterpret_cast<const float4*>(coef_b + k + e4);
+          ca[e4] = t0.x; ca[e4 + 1] = t0.y; ca[e4 + 2] = t0.z; ca[e4 + 3] = t0.w;
+          cb[e4] = t1.x; cb[e4 + 1] = t1.y; cb[e4 + 2] = t1.z; cb[e4 + 3] = t1.w;
+        }
+        if constexpr (ESZ == 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) x[q] = __uint_as_float(w[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            x[2 * q] = __uint_as_float(w[q] << 16);
+            x[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < CE; ++q) x[q] = fmaxf(fmaf(ca[q], x[q], cb[q]), 0.f);
+        if constexpr (ESZ == 4) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = __float_as_uint(x[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        ptx::sts128(addr, w[0], w[1], w[2], w[3]);
+        if (write_out && m0 + r < p.M && k < p.K)
+          *reinterpret_cast<uint4*>(out + static_cast<long long>(m0 + r) * p.K + k) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+      ptx::mbar_arrive(&ready_bar[s]);
     }
   }
   __syncwarp();  // producer / MMA warps reconverge before joining the epilogue
@@ -623,6 +739,15 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   // ANOTHER CTA on the same SM - so shallow rings (2 stages) with 2-3 co-resident CTAs beat deep rings.
   const bool atomic = e.kind == EPI_ATOMIC;
   const int sms = 148;
+  const bool atf_on = g.atf.enabled != 0;
+  if (atf_on) {
+    MVAE_REQUIRE(!g.a_mn && e.kind != EPI_ATOMIC, "gemm: the A transform needs a K-major A and no split-K");
+    MVAE_REQUIRE(g.atf.sum && g.atf.sumsq && g.atf.gamma && g.atf.beta, "gemm: A-transform statistics missing");
+    MVAE_REQUIRE(g.atf.rows_per_group >= g.M || g.atf.rows_per_group % kBlockM == 0,
+                 "gemm: A-transform needs statistics groups aligned to %d rows", kBlockM);
+    MVAE_REQUIRE(g.lda == g.K && g.K % (16 / esz) == 0, "gemm: A-transform needs a dense A with K a multiple of %d", 16 / esz);
+  }
+  const int coef_bytes = atf_on ? 2 * kb_total * BK * 4 : 0;
   static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
   auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
@@ -655,7 +780,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
     int dyn = stages * stage_bytes;
     if (dyn < staging) dyn = staging;
-    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn);
+    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn) + coef_bytes;
     dyn += 1024;
     split_o = split; stages_o = stages; dyn_o = dyn; bstage_o = b_stage; btx_o = b_tx;
     if (dyn > max_dyn + 1024) return 1e30;
@@ -745,8 +870,10 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_BCE) vec = vec && (e.ldt % 4 == 0) && al(e.target, aa);
   if (e.kind == EPI_DGRAD_BN) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
   kp.vec_ok = vec ? 1 : 0;
-  kp.aux_off = (aux_ok && vec) ? (dyn - 1024 - aux_bytes(block_n) - red_bytes(block_n)) : -1;
-  kp.red_off = red_ok ? (dyn - 1024 - red_bytes(block_n)) : -1;
+  kp.aux_off = (aux_ok && vec) ? (dyn - 1024 - coef_bytes - aux_bytes(block_n) - red_bytes(block_n)) : -1;
+  kp.red_off = red_ok ? (dyn - 1024 - coef_bytes - red_bytes(block_n)) : -1;
+  kp.coef_off = atf_on ? (dyn - 1024 - coef_bytes) : -1;
+  kp.atf = g.atf;
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");
   if (e.kind == EPI_DGRAD_BN)
     MVAE_REQUIRE(e.hpre && e.bn_mean && e.bn_rstd && e.bn_gamma && e.bn_beta, "gemm: dgrad-BN epilogue needs BN state");

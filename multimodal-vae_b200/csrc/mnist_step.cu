@@ -176,8 +176,9 @@ struct Ptrs {
 };
 
 int gemm_fwd(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
-             float* st_sum, float* st_sumsq, int rows_per_group, cudaStream_t st) {
+             float* st_sum, float* st_sumsq, int rows_per_group, cudaStream_t st, const GemmATransform* atf = nullptr) {
   GemmDesc g;
+  if (atf != nullptr) g.atf = *atf;
   g.kind = dtype; g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = K; g.a_mn = 0;
   g.B = W; g.ldb = K; g.b_mn = 0;
@@ -410,22 +411,44 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (dep(st, s2)) return 1;  // fork: the per-label text encoder runs beside the image encoder
   if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s2), "launch_textenc_forward");
 
+  // BatchNorm+ReLU between two Linears is folded into the CONSUMING GEMM's A-operand path (gemm.cu, A transform)
+  // when the statistics groups are tile-aligned; the separate apply kernel remains for ragged batches and eval.
+  static const int fuse_env = env_int("MVAE_FUSE_BN", 0);  // measured slower: every N tile redoes the transform
+  const bool fuse_enc = fuse_env != 0 && training;
+  const bool fuse_dec = fuse_enc && (G == 1 || B % 128 == 0);
+  auto make_atf = [&](float* sums, int F, int groups, int rpg, int nupd, const char* bn, float* sv, void* out) {
+    GemmATransform t;
+    t.enabled = 1;
+    t.sum = sums; t.sumsq = sums + groups * F;
+    char nm[96];
+    snprintf(nm, sizeof(nm), "%s.weight", bn); t.gamma = pf(nm);
+    snprintf(nm, sizeof(nm), "%s.bias", bn); t.beta = pf(nm);
+    snprintf(nm, sizeof(nm), "%s.running_mean", bn); t.running_mean = bf(nm);
+    snprintf(nm, sizeof(nm), "%s.running_var", bn); t.running_var = bf(nm);
+    t.rows_per_group = rpg; t.eps = bn_eps; t.momentum = mom; t.updates_per_group = nupd;
+    t.save_mean = sv; t.save_rstd = sv + groups * F;
+    t.out = out;
+    return t;
+  };
   if (n_img > 0) {
     // ImageEncoder (mnist/model.py:99-117), once for all terms that use it
     if (fwd) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
                  pf("image_encoder.net.0.bias"), training ? st_e1 : nullptr, training ? st_e1 + 400 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.0.weight#3");
-    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
+    const GemmATransform atf_e1 = make_atf(st_e1, 400, 1, 1 << 30, n_img, "image_encoder.net.1", sv_e1, W.at<void>(P.h1));
+    if (fwd && !fuse_enc) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
                           pf("image_encoder.net.1.weight"), pf("image_encoder.net.1.bias"), sv_e1, sv_e1 + 400,
                           bf("image_encoder.net.1.running_mean"), bf("image_encoder.net.1.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.1.weight#4");
-    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
-                 pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.3.weight#5");
-    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 200, 400, fuse_enc ? W.at<void>(P.h1pre) : W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
+                 pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st,
+                 fuse_enc ? &atf_e1 : nullptr), "gemm_fwd:image_encoder.net.3.weight#5");
+    const GemmATransform atf_e2 = make_atf(st_e2, 200, 1, 1 << 30, n_img, "image_encoder.net.4", sv_e2, W.at<void>(P.h2));
+    if (fwd && !fuse_enc) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
                           pf("image_encoder.net.4.weight"), pf("image_encoder.net.4.bias"), sv_e2, sv_e2 + 200,
                           bf("image_encoder.net.4.running_mean"), bf("image_encoder.net.4.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.4.weight#6");
-    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
-                 pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.6.weight#7");
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, fuse_enc ? W.at<void>(P.h2pre) : W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
+                 pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st, fuse_enc ? &atf_e2 : nullptr), "gemm_fwd:image_encoder.net.6.weight#7");
   }
   if (dep(s2, st)) return 1;  // join: the tail needs both experts
   TailArgs ta;
@@ -467,13 +490,16 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
   if (fwd) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
                pf("image_decoder.net.0.bias"), training ? st_d1 : nullptr, training ? st_d1 + G * 200 : nullptr, B, st), "gemm_fwd:image_decoder.net.0.weight#9");
-  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
+  const GemmATransform atf_d1 = make_atf(st_d1, 200, G, B, 1, "image_decoder.net.1", sv_d1, W.at<void>(P.g1));
+  if (fwd && !fuse_dec) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
                         pf("image_decoder.net.1.weight"), pf("image_decoder.net.1.bias"), sv_d1, sv_d1 + G * 200,
                         bf("image_decoder.net.1.running_mean"), bf("image_decoder.net.1.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.1.weight#10");
-  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
-               pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st), "gemm_fwd:image_decoder.net.3.weight#11");
-  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
+  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 400, 200, fuse_dec ? W.at<void>(P.g1pre) : W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
+               pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st,
+               fuse_dec ? &atf_d1 : nullptr), "gemm_fwd:image_decoder.net.3.weight#11");
+  const GemmATransform atf_d2 = make_atf(st_d2, 400, G, B, 1, "image_decoder.net.4", sv_d2, W.at<void>(P.g2));
+  if (fwd && !fuse_dec) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
@@ -481,7 +507,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     // last Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70) in one kernel
     GemmDesc g;
     g.kind = dt; g.M = R; g.N = 784; g.K = 400;
-    g.A = W.at<void>(P.g2); g.lda = 400; g.a_mn = 0;
+    g.A = fuse_dec ? W.at<void>(P.g2pre) : W.at<void>(P.g2); g.lda = 400; g.a_mn = 0;
+    if (fuse_dec) g.atf = atf_d2;
     g.B = wop("image_decoder.net.6.weight"); g.ldb = 400; g.b_mn = 0;
     g.epi.kind = EPI_BCE;
     g.epi.C = W.at<void>(P.dlog); g.epi.ldc = 784; g.epi.c_dtype = dt;

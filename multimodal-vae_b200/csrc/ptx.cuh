@@ -138,6 +138,12 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void lds128_u32(uint32_t addr, uint32_t (&v)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(addr)
+               : "memory");
+}
 __device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
