@@ -316,8 +316,21 @@ def run_device(args):
     gemm_launches = sum(1 for label, _ in prof_runs[-1] if label.startswith("gemm"))
     serial_ms = sum(agg.values())
     flops = F_ALG_PER_SAMPLE * B
-    achieved_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    family_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
+    # dominant kernel = the single most expensive launch: the last decoder Linear with the fused sigmoid/BCE/dlogits
+    # epilogue (gemm_kernel<bf16, BCE>), [3B,400] x [784,400]^T
+    dom_ms = agg.get("gemm_fwd_bce", 0.0)
+    dom_flops = 2.0 * 3 * B * 784 * 400
+    achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_kernel_sample.json")) as f:
+            prof = json.load(f)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(prof[k][0]) * scale[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        pass
     t_roof_us = flops / (peaks["bf16_tflops"] * 1e12) * 1e6 + Q_TAIL_PER_SAMPLE * B / (peaks["hbm_gbs"] * 1e9) * 1e6
     ms_per_step = ms_total / args.steps
 
@@ -340,10 +353,16 @@ def run_device(args):
                 "d2h_bytes_per_step": 3 * 4 * 4, "steps": e2e_steps,
                 "path": "HostPipeline(MVAETrainer).run(pinned uint8 images, int64 labels) -> pinned host losses, "
                         "copies overlapped with compute"},
-        "roofline": {"bound": "tensor", "kernel": "mvae::gemm_kernel (tcgen05/TMA GEMM, %d launches per step)" % gemm_launches,
+        "roofline": {"bound": "tensor",
+                     "kernel": "mvae::gemm_kernel<bf16, BCE> (tcgen05/TMA GEMM [3B,400]x[784,400]^T + fused sigmoid/BCE/"
+                               "dlogits epilogue; the most expensive launch of the step)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": None, "peak_source": peaks["source"] + (" (sustained bf16; tf32 = half)"),
-                     "flops_per_step": flops, "kernel_ms_per_step": gemm_ms},
+                     "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_gemm_kernel_sample.json (ncu --set full)",
+                     "peak_source": peaks["source"] + " (sustained bf16 GEMM peak; tf32 = half)",
+                     "flops_per_launch": dom_flops, "launch_ms": dom_ms,
+                     "note": "duration = CUDA events around the launch on its stream (includes ~5 us launch latency)"},
+        "gemm_family": {"launches_per_step": gemm_launches, "flops_per_step": flops, "ms_per_step_serialised": gemm_ms,
+                        "achieved_tflops": family_tf, "frac_of_peak": family_tf / peak_tf},
         "step_roofline": {"t_roof_us": t_roof_us, "t_measured_us": ms_per_step * 1e3,
                           "frac": t_roof_us / (ms_per_step * 1e3),
                           "definition": "SURVEY 8d: F_alg/bf16 burst peak + Q_tail/HBM peak"},
