@@ -206,7 +206,7 @@ def run_device(args):
     B = args.batch
     model = MVAE(N_LATENTS, precision=args.precision, device=dev, seed=1234 + rank)
     if world > 1:
-        trainer = DataParallelTrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph)
+        trainer = DataParallelTrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph, overlap=not args.no_overlap)
     else:
         trainer = MVAETrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph)
 
@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the whole backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -392,7 +393,16 @@ def main():
     return run_device(args)
 
 
+def _protect_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.  Route
+    fd 1 to stderr for the whole run and keep a private handle on the real stdout for the final line."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w")
+
+
 if __name__ == "__main__":
+    _protect_stdout()
     rc = main()
     sys.stdout.flush()
     sys.stderr.flush()

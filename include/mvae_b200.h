@@ -91,6 +91,7 @@ int mvae_mnist_tensor_info(int n_latents, int index, mvae_tensor_info* out);
 
 typedef struct mvae_mnist_size_info {
   int64_t param_floats;     /* length of the flat params / grads / adam_m / adam_v (/ bf16 mirror) buffers */
+  int64_t encoder_param_floats; /* [0, this) = encoder parameters, [this, param_floats) = decoder parameters */
   int64_t buffer_floats;    /* length of the flat running-statistics buffer */
   int64_t num_bn;           /* length of the num_batches_tracked array */
   int64_t workspace_bytes;  /* activation workspace for (batch, n_latents, dtype), up to 3 terms */
@@ -137,7 +138,9 @@ typedef struct mvae_mnist_step_args {
   /* --- module-surface extensions (all zero / NULL for the fused training step) --- */
   int eval_mode;            /* 1: vae.eval() - BatchNorm running statistics, z = mu (mnist/model.py:29-30), no updates */
   int phase;                /* 0: forward (+ backward if do_backward); 2: backward only from the upstream gradients
-                               below, reusing the workspace of the preceding forward (autograd path of forward()) */
+                               below, reusing the workspace of the preceding forward (autograd path of forward());
+                               3: forward + decoder-side backward, 4: encoder-side backward (data-parallel overlap:
+                               the decoder gradient bucket is all-reduced between the two) */
   const float* z_in;        /* optional [n_terms*batch, n_latents]: decode these latents (decode_image / decode_text,
                                mnist/model.py:35-42), encoders and PoE are skipped */
   const void* d_recon_image;/* phase 2: gradient w.r.t. the recon_image probabilities, `dtype` storage, or NULL */

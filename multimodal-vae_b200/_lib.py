@@ -79,8 +79,8 @@ class TensorInfo(C.Structure):
 
 
 class MnistSizeInfo(C.Structure):
-    _fields_ = [("param_floats", c_int64), ("buffer_floats", c_int64), ("num_bn", c_int64),
-                ("workspace_bytes", c_int64)]
+    _fields_ = [("param_floats", c_int64), ("encoder_param_floats", c_int64), ("buffer_floats", c_int64),
+                ("num_bn", c_int64), ("workspace_bytes", c_int64)]
 
 
 class MnistStepArgs(C.Structure):

@@ -77,7 +77,7 @@ struct Layout {
   int count = 0;
   TensorInfo info[kMaxTensors];
   long long offset[kMaxTensors];  // into params (kind 0), buffers (kind 1) or nbt (kind 2)
-  long long param_floats = 0, buffer_floats = 0, nbt_count = 0;
+  long long param_floats = 0, buffer_floats = 0, nbt_count = 0, enc_floats = 0;
   long long find(const char* name) const {
     for (int i = 0; i < count; ++i)
       if (strcmp(info[i].name, name) == 0) return offset[i];
@@ -85,14 +85,28 @@ struct Layout {
   }
 };
 
+// Parameters are laid out in two contiguous buckets so that data-parallel training can all-reduce the decoder
+// gradients (complete after the decoder + tail backward) while the encoder backward is still running:
+//   bucket 0 = image_encoder.* + text_encoder.*   [0, enc_floats)
+//   bucket 1 = image_decoder.* + text_decoder.*   [enc_floats, param_floats)
+// The tensor TABLE keeps the reference's state_dict order; only the offsets follow the buckets.
+bool is_decoder_tensor(const char* name) { return strstr(name, "_decoder.") != nullptr; }
+
 Layout make_layout(int n) {
   Layout L;
   L.count = build_tensor_list(n, L.info);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int i = 0; i < L.count; ++i) {
+      if (L.info[i].kind != 0 || is_decoder_tensor(L.info[i].name) != (pass == 1)) continue;
+      L.offset[i] = L.param_floats;
+      L.param_floats += round_up(numel(L.info[i]), kAlignFloats);
+    }
+    if (pass == 0) L.enc_floats = L.param_floats;
+  }
   for (int i = 0; i < L.count; ++i) {
     const long long ne = numel(L.info[i]);
     if (L.info[i].kind == 0) {
-      L.offset[i] = L.param_floats;
-      L.param_floats += round_up(ne, kAlignFloats);
+      continue;
     } else if (L.info[i].kind == 1) {
       L.offset[i] = L.buffer_floats;
       L.buffer_floats += round_up(ne, kAlignFloats);
@@ -320,6 +334,7 @@ int mvae_mnist_sizes(int n_latents, int batch, int dtype, mvae_mnist_size_info* 
   const Layout L = make_layout(n_latents);
   const Plan p = make_plan(batch, n_latents, dtype);
   out->param_floats = L.param_floats;
+  out->encoder_param_floats = L.enc_floats;
   out->buffer_floats = L.buffer_floats;
   out->num_bn = L.nbt_count;
   out->workspace_bytes = p.bytes;
@@ -356,8 +371,12 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   MVAE_REQUIRE(!bwd || a->grads != nullptr, "mnist_step: backward needs the gradient buffer");
   // phase 0: forward (+ backward when do_backward); phase 2: backward only, driven by upstream gradients of the
   // module outputs (the forward of the same workspace must have run before - autograd path of MVAE.forward)
-  const bool fwd = a->phase != 2;
+  // phase 3: forward + the decoder-side backward (through the tail backward); phase 4: the encoder-side backward
+  // only (text + image encoder) - data-parallel training all-reduces the decoder bucket between the two
+  const bool fwd = a->phase != 2 && a->phase != 4;
   const bool module_bwd = a->phase == 2;
+  const bool bwd_dec = a->phase != 4;
+  const bool bwd_enc = a->phase != 3;
   const bool training = a->eval_mode == 0;
   MVAE_REQUIRE(fwd || bwd, "mnist_step: phase 2 needs do_backward");
   MVAE_REQUIRE(training || !bwd, "mnist_step: backward needs train mode");
@@ -523,7 +542,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   }
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist
   // ================================================================ backward
-  if (bwd) {
+  if (bwd && bwd_dec) {
     if (module_bwd) {
       // autograd path: dlogits = d(recon_image) * p * (1 - p) from the probabilities the forward returned
       // (+ the last Linear's bias gradient), and the text decoder's backward from d(log-probs)
@@ -571,7 +590,9 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     if (dep(s2, st)) return 1;  // join: text decoder results
     MVAE_STEP(launch_tail_backward(ta, st), "launch_tail_backward");
     if (dep(st, s2)) return 1;  // fork: text encoder backward + encoder weight gradients
-
+  }
+  if (bwd && bwd_enc) {
+    if (!bwd_dec && dep(st, s2)) return 1;
     // ---- text encoder
     if (n_txt > 0) {
       te.d_table = W.at<float>(P.d_txt_table);
@@ -604,10 +625,10 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
 
   if (dep(s2, st)) return 1;  // join everything before the loss read-out / optimizer
   // ---- losses out: [G][4] = total, bce, ce, kl
-  if (a->out_losses != nullptr)
+  if (a->out_losses != nullptr && fwd)
     MVAE_STEP(launch_loss_pack(losses, a->out_losses, G, st), "launch_loss_pack#32");
 
-  if (bwd && a->do_adam) {
+  if (bwd && bwd_enc && a->do_adam) {
     MVAE_REQUIRE(a->adam_m && a->adam_v && a->adam_step, "mnist_step: Adam state missing");
     MVAE_STEP(launch_adam(prm, a->grads, a->adam_m, a->adam_v, a->params_bf16, L.param_floats, a->lr, a->beta1, a->beta2,
                     a->adam_eps, a->adam_step, a->grad_scale, 0, st), "launch_adam#33");

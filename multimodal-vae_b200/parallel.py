@@ -58,19 +58,39 @@ class DataParallelTrainer(MVAETrainer):
     """MVAETrainer whose step is: local fused fwd+bwd -> all-reduce(flat grads) -> fused Adam(1/world)."""
 
     def __init__(self, model: MVAE, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 use_cuda_graph: bool = False, group=None):
+                 use_cuda_graph: bool = False, group=None, overlap: bool = True):
         super().__init__(model, lr=lr, betas=betas, eps=eps, use_cuda_graph=False)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.dp_graph = use_cuda_graph
         self._dp_graphs = {}
+        self.overlap = overlap
+        self.comm_stream = torch.cuda.Stream(device=model.device_)
+        from .mnist import sizes
+        self.enc_floats = int(sizes(model.n_latents, 2, model.dtype_code).encoder_param_floats)
         broadcast_model_(model, 0, group)
 
     def _local_then_reduce(self, x, y, eps, terms, lambdas, annealing_factor, losses=None):
+        """fwd + decoder backward -> [all-reduce(decoder bucket) on the comm stream || encoder backward]
+        -> all-reduce(encoder bucket) -> Adam(1/world).  The flat parameter buffer is laid out as
+        [encoders | decoders] exactly for this split (csrc/mnist_step.cu::make_layout)."""
         m = self.model
         tt, klw = self._norm(terms, x.shape[0], annealing_factor)
-        out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses)
-        allreduce_flat_(m.flat_grads, self.group)
+        split = self.enc_floats
+        main = torch.cuda.current_stream(m.device_)
+        if self.overlap and self.world > 1:
+            out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses,
+                            extra={"phase": 3})
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                allreduce_flat_(m.flat_grads[split:], self.group)
+            m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=False, adam=None, losses=losses,
+                   extra={"phase": 4})
+            allreduce_flat_(m.flat_grads[:split], self.group)
+            main.wait_stream(self.comm_stream)
+        else:
+            out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses)
+            allreduce_flat_(m.flat_grads, self.group)
         a = self.adam
         _lib.check(_lib.load().mvae_adam_step(
             C.c_void_p(m.flat_params.data_ptr()), C.c_void_p(m.flat_grads.data_ptr()), C.c_void_p(a["m"].data_ptr()),

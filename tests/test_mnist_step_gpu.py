@@ -202,3 +202,35 @@ def test_bf16_training_curve_within_one_percent():
             ref_curve.append(sum(losses))
     dev, ref = np.mean(dev_curve), np.mean(ref_curve)
     assert abs(dev - ref) / abs(ref) < 0.01, (dev, ref)
+
+
+def test_split_backward_phases_equal_single_call():
+    """phase 3 (forward + decoder-side backward) followed by phase 4 (encoder-side backward) - the split the
+    data-parallel trainer uses to overlap the decoder-bucket all-reduce - must give the gradients of one call."""
+    import mvae_b200
+    from mvae_b200 import mnist
+    B, n, seed = 256, 16, 8
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m1, _, l1, _ = run_device_step(state, image, text, noises, n, "bf16")
+    m2 = mvae_b200.MVAE(n, precision="bf16")
+    m2.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m2)
+    x, y = m2.to_act(image.cuda()), text.cuda()
+    eps = torch.stack(noises).cuda()
+    tt, klw = tr._norm(NAMES, B, 1.0)
+    l2, _ = m2._run(x, y, tt, ((1., 1.),) * 3, klw, eps=eps, backward=True, zero_grad=True, extra={"phase": 3})
+    si = mnist.sizes(n, B, m2.dtype_code)
+    enc = int(si.encoder_param_floats)
+    assert 0 < enc < int(si.param_floats)
+    torch.cuda.synchronize()
+    # decoder bucket is final after phase 3; most of the encoder bucket is still untouched (zero)
+    dec_after_3 = m2.flat_grads[enc:].clone()
+    m2._run(x, y, tt, ((1., 1.),) * 3, klw, eps=eps, backward=True, zero_grad=False, extra={"phase": 4})
+    torch.cuda.synchronize()
+    assert torch.equal(dec_after_3, m2.flat_grads[enc:])
+    np.testing.assert_allclose(l2.cpu().numpy(), l1.numpy(), rtol=1e-5)
+    for (name, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if name in O.PRE_BN_BIASES:
+            continue
+        assert rel_l2(p2.grad, p1.grad) < 2e-3, name   # atomics order only
