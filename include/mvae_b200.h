@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 2
+#define MVAE_ABI_VERSION 3
 
 #define MVAE_DT_F32 0
 #define MVAE_DT_BF16 1
@@ -194,6 +194,124 @@ int mvae_poe_forward(int mode, int prior_expert, float eps, int n_experts, int64
 int mvae_poe_backward(int mode, int prior_expert, float eps, int n_experts, int64_t batch, int dim, const float* mu,
                       const float* logvar, const float* mask, const float* d_out_mu, const float* d_out_logvar,
                       float* d_mu, float* d_logvar, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Operator-level entries for the convolutional MVAEs (CelebA celeba/model.py:91-200, MultiMNIST
+ * multimnist/model.py:150-266).  The host (multimodal-vae_b200/celeba.py) composes them with mvae_gemm into the
+ * reference's forward / loss / backward; every convolution is a tensor-core GEMM over an im2col matrix.
+ *
+ * Activations are NHWC matrices [batch*H*W, C] in fp32 or bf16.  The K axis of a patch matrix is ordered
+ * (kh, kw, c): Conv2d weights are therefore held as [Cout, kh, kw, Cin] and ConvTranspose2d weights as
+ * [Cin, kh, kw, Cout] inside the flat parameter buffer (the host permutes at the state_dict boundary).
+ */
+#define MVAE_ACT_NONE 0
+#define MVAE_ACT_RELU 1
+#define MVAE_ACT_SWISH 2 /* x * sigmoid(x), celeba/model.py:238-245 */
+
+typedef struct mvae_conv_geometry {
+  int batch, height, width, channels; /* the IMAGE side: conv input / conv-transpose output */
+  int kernel, stride, pad;
+  int64_t stride_n, stride_h, stride_w, stride_c; /* element strides of the image tensor (NHWC dense or e.g. NCHW) */
+} mvae_conv_geometry;
+int mvae_conv_out_size(int in, int kernel, int stride, int pad);
+/* col[m, (kh*k+kw)*C + c] = image[n, ho*s-p+kh, wo*s-p+kw, c] (0 outside), m = (n*Ho+ho)*Wo+wo.
+ * replaces: the patch gather inside nn.Conv2d forward / ConvTranspose2d backward (celeba/model.py:101-113, 142-152). */
+int mvae_im2col(const mvae_conv_geometry* g, int image_dtype, const void* image, int col_dtype, void* col, int64_t ldcol,
+                void* stream);
+/* adjoint of mvae_im2col (gather form, no atomics): image[n,h,w,c] = sum of the col entries that im2col read from it.
+ * replaces: the scatter inside nn.ConvTranspose2d forward / Conv2d input-gradient. */
+int mvae_col2im(const mvae_conv_geometry* g, int col_dtype, const void* col, int64_t ldcol, int image_dtype, void* image,
+                void* stream);
+/* sum[g, c] += sum_rows x, sumsq[g, c] += sum_rows x^2 (sumsq may be NULL), group = row / rows_per_group; only columns
+ * < valid_channels are accumulated.  BatchNorm batch statistics and bias gradients. */
+int mvae_col_stats(int dtype, const void* x, int64_t rows, int channels, int valid_channels, int64_t rows_per_group,
+                   float* sum, float* sumsq, void* stream);
+
+/* nn.BatchNorm1d / nn.BatchNorm2d (channel-last matrix) fused with the activation that follows it.
+ * Each statistics group (rows_per_group consecutive rows) stands for one forward pass of the reference (one ELBO
+ * term); running statistics are updated once per group, in order, `updates_per_group` times each. */
+typedef struct mvae_bn_act_args {
+  int dtype;
+  int64_t rows;
+  int channels;
+  int64_t rows_per_group; /* <= 0: one group */
+  int act;                /* MVAE_ACT_* */
+  int training;           /* 0: normalise with the running statistics, update nothing */
+  const void* x;          /* pre-BatchNorm activations [rows, channels] */
+  void* y;                /* forward output */
+  const float* gamma; const float* beta;
+  float* sum; float* sumsq; /* [groups, channels] batch sums */
+  int stats_ready;          /* 1: sum / sumsq already hold the batch sums (e.g. from a GEMM epilogue) */
+  float* save_mean; float* save_rstd; /* [groups, channels], written by forward, read by backward */
+  float* running_mean; float* running_var;
+  int updates_per_group;
+  float momentum, eps;
+  const void* dy; void* dx; /* backward: gradient at y -> gradient at x */
+  float* s0; float* s1;     /* [groups, channels] scratch of the backward */
+  float* dgamma; float* dbeta; /* += (may be NULL) */
+} mvae_bn_act_args;
+int mvae_bn_act_forward(const mvae_bn_act_args* args, void* stream);
+int mvae_bn_act_backward(const mvae_bn_act_args* args, void* stream);
+
+/* y[rep*rows + r] = dropout_rep(act(x[r])) for rep < repeat: activation after a Linear, optional nn.Dropout(p)
+ * (celeba/model.py:116-117) with an independent Philox keep-mask per replica (one replica per reference forward pass).
+ * backward: dx[r] = act'(x[r]) * sum_rep mask_rep * dy[rep*rows + r] / (1-p);  dbias[c] += sum_r dx[r, c] if not NULL. */
+int mvae_act_forward(int dtype, int act, const void* x, void* y, int64_t rows, int channels, int repeat, float dropout_p,
+                     uint64_t seed, const int* step_counter, void* stream);
+int mvae_act_backward(int dtype, int act, const void* x, const void* dy, void* dx, int64_t rows, int channels, int repeat,
+                      float dropout_p, uint64_t seed, const int* step_counter, float* dbias, void* stream);
+
+/* F.sigmoid + F.binary_cross_entropy(mean) (celeba/model.py:163,200; celeba/train.py:66-74), value and gradient:
+ *   loss[g] += sum_{rows of group g} BCE(sigmoid(logit), target)      (unscaled sum)
+ *   dlogits  = grad_scale[g] * (sigmoid(logit) - target)
+ * Row m compares with target row m % target_rows.  With target == NULL and dprobs != NULL it is the plain sigmoid
+ * backward dlogits = dprobs * p * (1 - p).  Columns [cols, ld_dlogits) of dlogits are zero-filled. */
+typedef struct mvae_sigmoid_bce_args {
+  int64_t rows; int cols; int64_t rows_per_group;
+  int logit_dtype; const void* logits; int64_t ld_logits;
+  int target_dtype; const void* target; int64_t ld_target; int64_t target_rows;
+  float grad_scale[3];
+  float* loss;
+  int prob_dtype; void* probs; int64_t ld_probs;
+  int grad_dtype; void* dlogits; int64_t ld_dlogits;
+  const float* dprobs; int64_t ld_dprobs;
+} mvae_sigmoid_bce_args;
+int mvae_sigmoid_bce(const mvae_sigmoid_bce_args* args, void* stream);
+
+/* The latent path for all ELBO terms in one launch per direction: ProductOfExperts over the experts present in each
+ * term (celeba/model.py:38-52, 224-235), reparametrize (:27-34) and the KL term of loss_function (celeba/train.py:79-80).
+ * Expert tensors are [rows, 2*n_latents] (mu | logvar).  Term g reads expert A rows [expert_a_row0[g], +batch) (two terms
+ * may share rows: their gradients are summed) and expert B rows [0, batch). */
+typedef struct mvae_latent_args {
+  int64_t batch; int n_latents; int n_terms;
+  int term_type[3];          /* MVAE_TERM_JOINT / _IMAGE (expert A only) / _TEXT (expert B only) */
+  int poe_mode, prior_expert; float poe_eps;
+  const float* expert_a; int64_t ld_a; int64_t expert_a_row0[3];
+  const float* expert_b; int64_t ld_b;
+  const float* eps;          /* [n_terms, batch, n_latents] injected N(0,1) draws, or NULL (Philox: seed, *step_counter) */
+  uint64_t seed; const int* step_counter;
+  int training;              /* 0: z = mu */
+  float kl_weight[3];
+  int z_dtype; void* z; int64_t ld_z;   /* [n_terms*batch, ld_z] */
+  float* mu; float* logvar;  /* optional [n_terms, batch, n_latents] */
+  float* kl;                 /* [n_terms] += kl_weight[g] * KL_g */
+  /* backward */
+  int dz_dtype; const void* dz; int64_t ld_dz;
+  const float* d_mu; const float* d_logvar; /* optional upstream gradients [n_terms, batch, n_latents] */
+  int d_dtype; void* d_expert_a; int64_t ld_da; void* d_expert_b; int64_t ld_db;
+} mvae_latent_args;
+int mvae_latent_forward(const mvae_latent_args* args, void* stream);
+int mvae_latent_backward(const mvae_latent_args* args, void* stream);
+
+/* dst[r, c] = src[r, c] for c < cols, 0 for cols <= c < ld_dst: GEMM-operand copies of weights whose row length does
+ * not meet the 16-byte TMA stride rule (e.g. Linear(18, 64), Linear(100, 6400) in bf16). */
+int mvae_cast_pad_2d(const float* src, int64_t rows, int64_t cols, int64_t ld_src, int dst_dtype, void* dst, int64_t ld_dst,
+                     void* stream);
+/* Start of a training step: ++*step_counter (Adam bias correction, Philox counter), zero `zero_floats` floats (loss and
+ * statistics accumulators), counters[i] += increments[i] (num_batches_tracked). */
+int mvae_step_begin(int* step_counter, float* zero_buf, int64_t zero_floats, int64_t* counters, const int64_t* increments,
+                    int n_counters, void* stream);
 
 #ifdef __cplusplus
 }

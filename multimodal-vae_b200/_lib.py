@@ -55,6 +55,7 @@ def load():
         lib.mvae_mnist_workspace_offset.argtypes = [C.c_char_p, c_int, c_int, c_int]
         lib.mvae_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                        c_float, c_float, c_void_p, c_float, c_int, c_void_p]
+        _conv_argtypes(lib)
         _lib = lib
         return lib
 
@@ -118,3 +119,68 @@ class ElboLossArgs(C.Structure):
 DT_F32, DT_BF16 = 0, 1
 POE_REF, POE_PRECISION = 0, 1
 TERM_JOINT, TERM_IMAGE, TERM_TEXT = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+
+
+# ---------------------------------------------------------------- operator-level ABI (conv models)
+class ConvGeometry(C.Structure):
+    _fields_ = [("batch", c_int), ("height", c_int), ("width", c_int), ("channels", c_int),
+                ("kernel", c_int), ("stride", c_int), ("pad", c_int),
+                ("stride_n", c_int64), ("stride_h", c_int64), ("stride_w", c_int64), ("stride_c", c_int64)]
+
+
+class BnActArgs(C.Structure):
+    _fields_ = [("dtype", c_int), ("rows", c_int64), ("channels", c_int), ("rows_per_group", c_int64),
+                ("act", c_int), ("training", c_int),
+                ("x", c_void_p), ("y", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("sum", c_void_p), ("sumsq", c_void_p), ("stats_ready", c_int),
+                ("save_mean", c_void_p), ("save_rstd", c_void_p),
+                ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("updates_per_group", c_int), ("momentum", c_float), ("eps", c_float),
+                ("dy", c_void_p), ("dx", c_void_p), ("s0", c_void_p), ("s1", c_void_p),
+                ("dgamma", c_void_p), ("dbeta", c_void_p)]
+
+
+class SigmoidBceArgs(C.Structure):
+    _fields_ = [("rows", c_int64), ("cols", c_int), ("rows_per_group", c_int64),
+                ("logit_dtype", c_int), ("logits", c_void_p), ("ld_logits", c_int64),
+                ("target_dtype", c_int), ("target", c_void_p), ("ld_target", c_int64), ("target_rows", c_int64),
+                ("grad_scale", c_float * 3), ("loss", c_void_p),
+                ("prob_dtype", c_int), ("probs", c_void_p), ("ld_probs", c_int64),
+                ("grad_dtype", c_int), ("dlogits", c_void_p), ("ld_dlogits", c_int64),
+                ("dprobs", c_void_p), ("ld_dprobs", c_int64)]
+
+
+class LatentArgs(C.Structure):
+    _fields_ = [("batch", c_int64), ("n_latents", c_int), ("n_terms", c_int), ("term_type", c_int * 3),
+                ("poe_mode", c_int), ("prior_expert", c_int), ("poe_eps", c_float),
+                ("expert_a", c_void_p), ("ld_a", c_int64), ("expert_a_row0", c_int64 * 3),
+                ("expert_b", c_void_p), ("ld_b", c_int64),
+                ("eps", c_void_p), ("seed", c_uint64), ("step_counter", c_void_p), ("training", c_int),
+                ("kl_weight", c_float * 3),
+                ("z_dtype", c_int), ("z", c_void_p), ("ld_z", c_int64),
+                ("mu", c_void_p), ("logvar", c_void_p), ("kl", c_void_p),
+                ("dz_dtype", c_int), ("dz", c_void_p), ("ld_dz", c_int64),
+                ("d_mu", c_void_p), ("d_logvar", c_void_p),
+                ("d_dtype", c_int), ("d_expert_a", c_void_p), ("ld_da", c_int64),
+                ("d_expert_b", c_void_p), ("ld_db", c_int64)]
+
+
+def _conv_argtypes(lib) -> None:
+    P = C.POINTER
+    lib.mvae_conv_out_size.argtypes = [c_int] * 4
+    lib.mvae_im2col.argtypes = [P(ConvGeometry), c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]
+    lib.mvae_col2im.argtypes = [P(ConvGeometry), c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]
+    lib.mvae_col_stats.argtypes = [c_int, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.mvae_bn_act_forward.argtypes = [P(BnActArgs), c_void_p]
+    lib.mvae_bn_act_backward.argtypes = [P(BnActArgs), c_void_p]
+    lib.mvae_act_forward.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_uint64,
+                                     c_void_p, c_void_p]
+    lib.mvae_act_backward.argtypes = [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_float,
+                                      c_uint64, c_void_p, c_void_p, c_void_p]
+    lib.mvae_sigmoid_bce.argtypes = [P(SigmoidBceArgs), c_void_p]
+    lib.mvae_latent_forward.argtypes = [P(LatentArgs), c_void_p]
+    lib.mvae_latent_backward.argtypes = [P(LatentArgs), c_void_p]
+    lib.mvae_cast_pad_2d.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]
+    lib.mvae_step_begin.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]
+    lib.mvae_gemm.argtypes = [P(GemmArgs), c_void_p]

@@ -1,0 +1,153 @@
+"""Thin Python wrappers over the operator-level C ABI (include/mvae_b200.h): one function per entry point, torch
+tensors in, nothing computed on the host.  Used by the conv-model hosts (celeba.py).  No fallback: every function
+ends in a call into libmvae_b200.so and raises MvaeError on failure.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+DT = {torch.float32: _lib.DT_F32, torch.bfloat16: _lib.DT_BF16}
+
+
+def stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, accumulate=False, col_sum=None,
+         col_sumsq=None, rows_per_group=0):
+    """Cout[M,N] (+)= A[M,K] * B[N,K]^T (+ bias).  A and B share one storage dtype (bf16 -> kind::f16, fp32 -> tf32)."""
+    if A.dtype != B.dtype:
+        raise TypeError("gemm operands differ in dtype: %s vs %s" % (A.dtype, B.dtype))
+    a = _lib.GemmArgs()
+    a.dtype = DT[A.dtype]
+    a.M, a.N, a.K = int(M), int(N), int(K)
+    a.A, a.lda, a.a_major = A.data_ptr(), int(lda), int(a_major)
+    a.B, a.ldb, a.b_major = B.data_ptr(), int(ldb), int(b_major)
+    a.C, a.ldc, a.c_dtype = Cout.data_ptr(), int(ldc), DT[Cout.dtype]
+    a.bias = _p(bias)
+    a.accumulate = 1 if accumulate else 0
+    a.col_sum, a.col_sumsq = _p(col_sum), _p(col_sumsq)
+    a.rows_per_group = int(rows_per_group)
+    _lib.check(_lib.load().mvae_gemm(C.byref(a), stream()), "mvae_gemm %dx%dx%d" % (M, N, K))
+
+
+def geometry(batch, height, width, channels, kernel, stride, pad, strides=None) -> _lib.ConvGeometry:
+    g = _lib.ConvGeometry()
+    g.batch, g.height, g.width, g.channels = int(batch), int(height), int(width), int(channels)
+    g.kernel, g.stride, g.pad = int(kernel), int(stride), int(pad)
+    if strides is None:  # dense NHWC
+        strides = (height * width * channels, width * channels, channels, 1)
+    g.stride_n, g.stride_h, g.stride_w, g.stride_c = (int(s) for s in strides)
+    return g
+
+
+def nchw_strides(channels, height, width):
+    return (channels * height * width, width, 1, height * width)
+
+
+def out_size(n, kernel, stride, pad) -> int:
+    return (n + 2 * pad - kernel) // stride + 1
+
+
+def im2col(g, image, col, ldcol):
+    _lib.check(_lib.load().mvae_im2col(C.byref(g), DT[image.dtype], image.data_ptr(), DT[col.dtype], col.data_ptr(),
+                                       int(ldcol), stream()), "mvae_im2col")
+
+
+def col2im(g, col, ldcol, image):
+    _lib.check(_lib.load().mvae_col2im(C.byref(g), DT[col.dtype], col.data_ptr(), int(ldcol), DT[image.dtype],
+                                       image.data_ptr(), stream()), "mvae_col2im")
+
+
+def col_stats(x, rows, channels, sum_, sumsq=None, valid_channels=0, rows_per_group=0):
+    _lib.check(_lib.load().mvae_col_stats(DT[x.dtype], x.data_ptr(), int(rows), int(channels), int(valid_channels),
+                                          int(rows_per_group), _p(sum_), _p(sumsq), stream()), "mvae_col_stats")
+
+
+def bn_args(x, rows, channels, rows_per_group, act, training, gamma, beta, sum_, sumsq, save_mean, save_rstd,
+            running_mean=None, running_var=None, updates=1, stats_ready=False) -> _lib.BnActArgs:
+    a = _lib.BnActArgs()
+    a.dtype = DT[x.dtype]
+    a.rows, a.channels, a.rows_per_group = int(rows), int(channels), int(rows_per_group)
+    a.act, a.training = int(act), 1 if training else 0
+    a.x = x.data_ptr()
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    a.sum, a.sumsq, a.stats_ready = _p(sum_), _p(sumsq), 1 if stats_ready else 0
+    a.save_mean, a.save_rstd = _p(save_mean), _p(save_rstd)
+    a.running_mean, a.running_var = _p(running_mean), _p(running_var)
+    a.updates_per_group, a.momentum, a.eps = int(updates), 0.1, 1e-5
+    return a
+
+
+def bn_act_forward(a: _lib.BnActArgs, y):
+    a.y = y.data_ptr()
+    _lib.check(_lib.load().mvae_bn_act_forward(C.byref(a), stream()), "mvae_bn_act_forward")
+
+
+def bn_act_backward(a: _lib.BnActArgs, dy, dx, s0, s1, dgamma=None, dbeta=None):
+    a.dy, a.dx, a.s0, a.s1 = dy.data_ptr(), dx.data_ptr(), s0.data_ptr(), s1.data_ptr()
+    a.dgamma, a.dbeta = _p(dgamma), _p(dbeta)
+    _lib.check(_lib.load().mvae_bn_act_backward(C.byref(a), stream()), "mvae_bn_act_backward")
+
+
+def act_forward(act, x, y, rows, channels, repeat=1, dropout_p=0.0, seed=0, step_counter=None):
+    _lib.check(_lib.load().mvae_act_forward(DT[x.dtype], int(act), x.data_ptr(), y.data_ptr(), int(rows), int(channels),
+                                            int(repeat), float(dropout_p), int(seed), _p(step_counter), stream()),
+               "mvae_act_forward")
+
+
+def act_backward(act, x, dy, dx, rows, channels, repeat=1, dropout_p=0.0, seed=0, step_counter=None, dbias=None):
+    _lib.check(_lib.load().mvae_act_backward(DT[x.dtype], int(act), x.data_ptr(), dy.data_ptr(), dx.data_ptr(), int(rows),
+                                             int(channels), int(repeat), float(dropout_p), int(seed), _p(step_counter),
+                                             _p(dbias), stream()), "mvae_act_backward")
+
+
+def sigmoid_bce(logits, ld_logits, rows, cols, rows_per_group=0, target=None, ld_target=0, target_rows=0,
+                grad_scale=(0.0, 0.0, 0.0), loss=None, probs=None, ld_probs=0, dlogits=None, ld_dlogits=0, dprobs=None,
+                ld_dprobs=0):
+    a = _lib.SigmoidBceArgs()
+    a.rows, a.cols, a.rows_per_group = int(rows), int(cols), int(rows_per_group)
+    a.logit_dtype, a.logits, a.ld_logits = DT[logits.dtype], logits.data_ptr(), int(ld_logits)
+    if target is not None:
+        a.target_dtype, a.target, a.ld_target, a.target_rows = DT[target.dtype], target.data_ptr(), int(ld_target), int(target_rows)
+    for i in range(3):
+        a.grad_scale[i] = float(grad_scale[i]) if i < len(grad_scale) else 0.0
+    a.loss = _p(loss)
+    if probs is not None:
+        a.prob_dtype, a.probs, a.ld_probs = DT[probs.dtype], probs.data_ptr(), int(ld_probs)
+    if dlogits is not None:
+        a.grad_dtype, a.dlogits, a.ld_dlogits = DT[dlogits.dtype], dlogits.data_ptr(), int(ld_dlogits)
+    if dprobs is not None:
+        a.dprobs, a.ld_dprobs = dprobs.data_ptr(), int(ld_dprobs)
+    _lib.check(_lib.load().mvae_sigmoid_bce(C.byref(a), stream()), "mvae_sigmoid_bce")
+
+
+def cast_pad_2d(src, rows, cols, ld_src, dst, ld_dst):
+    _lib.check(_lib.load().mvae_cast_pad_2d(src.data_ptr(), int(rows), int(cols), int(ld_src), DT[dst.dtype], dst.data_ptr(),
+                                            int(ld_dst), stream()), "mvae_cast_pad_2d")
+
+
+def step_begin(step_counter, zero_buf=None, counters=None, increments=None):
+    n = 0 if counters is None else counters.numel()
+    _lib.check(_lib.load().mvae_step_begin(_p(step_counter), _p(zero_buf), 0 if zero_buf is None else zero_buf.numel(),
+                                           _p(counters), _p(increments), n, stream()), "mvae_step_begin")
+
+
+def adam_step(params, grads, m, v, params_bf16, count, lr, beta1, beta2, eps, step_counter, grad_scale=1.0, zero_grad=True):
+    _lib.check(_lib.load().mvae_adam_step(params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), _p(params_bf16),
+                                          int(count), lr, beta1, beta2, eps, step_counter.data_ptr(), grad_scale,
+                                          1 if zero_grad else 0, stream()), "mvae_adam_step")
+
+
+def cast_f32_to_bf16(src, dst, count):
+    _lib.check(_lib.load().mvae_cast_f32_to_bf16(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(int(count)),
+                                                 stream()), "mvae_cast_f32_to_bf16")

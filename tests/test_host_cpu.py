@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in sorted(names):
         assert hasattr(lib, n), n
-    assert lib.mvae_abi_version() == 2
+    assert lib.mvae_abi_version() == 3
 
 
 def test_layout_matches_reference_state_dict():
