@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const BnArgs a) {
     s_scale[i] = sc;
     s_shift[i] = fmaf(-mean, sc, a.beta[c]);
     s_c0[i] = a.s0[i] * inv;
-    s_c1[i] = a.s1[i] * inv * rstd * rstd;
+    s_c1[i] = a.s1[i] * inv * rstd;   // multiplies (x - mean): xhat * S1/cnt
     s_mean[i] = mean;
     if (blockIdx.x == 0 && g == 0 && a.dgamma != nullptr) {
       float dg = 0.f, db = 0.f;
