@@ -387,7 +387,16 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the whole backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mnist", choices=["mnist", "celeba", "multimnist"],
+                    help="mnist = the headline config (BASELINE.json configs[1]); celeba / multimnist = configs[3] / [2]")
     args = ap.parse_args()
+    args.batch_set = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
+    if args.workload != "mnist":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is timed on the headline MNIST config only"}))
+            return 0
+        import bench_conv
+        return bench_conv.run(args, log, ClockSampler, load_peaks)
     if args.impl == "reference":
         return run_reference(args)
     return run_device(args)

@@ -1,0 +1,606 @@
+"""Shared host code of the convolutional MVAEs (CelebA celeba/model.py, MultiMNIST multimnist/model.py).
+
+ConvMVAEBase owns the flat parameter / gradient buffers (reference state_dict keys, internal GEMM-friendly layouts),
+the convolutional image encoder (`features`) and decoder (`hallucinate`) stacks composed from the operator-level C ABI
+(mvae_im2col / mvae_col2im / mvae_gemm / mvae_bn_act_* / mvae_act_*), the Linear helpers, and the latent path
+(mvae_latent_*).  ConvMVAETrainer owns the step: zero accumulators, forward of all ELBO terms, backward, the
+data-parallel gradient all-reduce (decoder bucket overlapped with the encoder backward) and fused Adam, optionally as
+one CUDA graph.  Subclasses provide the model spec and the second modality's networks.
+
+Every Conv2d / ConvTranspose2d / Linear is a tcgen05 GEMM over NHWC activation matrices [batch*H*W, C].  The image
+encoder runs ONCE per step (the reference runs it twice on identical inputs; only Dropout differs, so everything up
+to the first Dropout is shared and the masks are applied to replicated rows); the decoders run once on the stacked
+[terms*B] latents with per-term BatchNorm statistics.  There is no PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, _ops
+
+_DTYPES = {"tf32": torch.float32, "fp32": torch.float32, "bf16": torch.bfloat16}
+SWISH = _lib.ACT_SWISH
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Layout:
+    """How one reference parameter tensor is held inside the flat buffer.
+    kind: conv [Co,Ci,kh,kw]->[Co,kh,kw,Ci] | convT [Ci,Co,kh,kw]->[Ci,kh,kw,Co] | fc_in (columns (c,hw)->(hw,c)) |
+          fc_out (rows (c,hw)->(hw,c)) | fc_out_bias | plain"""
+
+    def __init__(self, key, ref_shape, kind, flat_c=256, flat_hw=1):
+        self.key, self.ref_shape, self.kind = key, tuple(ref_shape), kind
+        self.c, self.hw = flat_c, flat_hw
+        self.numel = 1
+        for s in ref_shape:
+            self.numel *= s
+        self.offset = -1
+
+    def to_internal(self, t: torch.Tensor) -> torch.Tensor:
+        k, c, hw = self.kind, self.c, self.hw
+        if k in ("conv", "convT"):
+            return t.permute(0, 2, 3, 1).contiguous()
+        if k == "fc_in":
+            o = t.shape[0]
+            return t.reshape(o, c, hw).permute(0, 2, 1).contiguous().reshape(o, c * hw)
+        if k == "fc_out":
+            n = t.shape[1]
+            return t.reshape(c, hw, n).permute(1, 0, 2).contiguous().reshape(c * hw, n)
+        if k == "fc_out_bias":
+            return t.reshape(c, hw).t().contiguous().reshape(c * hw)
+        return t.contiguous()
+
+    def to_reference(self, t: torch.Tensor) -> torch.Tensor:
+        k, c, hw = self.kind, self.c, self.hw
+        if k in ("conv", "convT"):
+            a, b, kh, kw = self.ref_shape
+            return t.reshape(a, kh, kw, b).permute(0, 3, 1, 2).contiguous()
+        if k == "fc_in":
+            o = self.ref_shape[0]
+            return t.reshape(o, hw, c).permute(0, 2, 1).contiguous().reshape(o, c * hw)
+        if k == "fc_out":
+            n = self.ref_shape[1]
+            return t.reshape(hw, c, n).permute(1, 0, 2).contiguous().reshape(c * hw, n)
+        if k == "fc_out_bias":
+            return t.reshape(hw, c).t().contiguous().reshape(c * hw)
+        return t.reshape(self.ref_shape).clone()
+
+
+class ConvMVAEBase:
+    """Parameter store + conv stacks.  Subclass attributes:
+        IMG_C, IMG_H           image channels / side
+        ENC_CONVS              [(key, Cin, Cout, k, stride, pad, H_in, bn_key | None)]
+        DEC_CONVS              [(key, Cin, Cout, k, stride, pad, H_out, bn_key | None)]   (last one produces the logits)
+        FLAT_C, FLAT_HW        channels / pixels of the bottleneck feature map
+        BN_LAYERS              {bn_key: channels} in a fixed order (num_batches_tracked index)
+    and reference_keys(n_latents) -> [(key, reference shape, kind)] in state_dict order."""
+
+    IMG_C = 3
+    IMG_H = 64
+    ENC_CONVS: Tuple = ()
+    DEC_CONVS: Tuple = ()
+    FLAT_C = 256
+    FLAT_HW = 25
+    BN_LAYERS: Dict[str, int] = {}
+
+    def __init__(self, n_latents: int, precision: str, dropout_p: float, device, seed: int):
+        if precision not in _DTYPES:
+            raise ValueError("precision must be one of %s" % sorted(_DTYPES))
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if dev.type != "cuda":
+            raise RuntimeError("mvae_b200 has no CPU path: a CUDA (sm_100) device is required")
+        _lib.check(_lib.load().mvae_device_check(dev.index or 0), "mvae_device_check")
+        self.device = dev
+        self.n_latents = int(n_latents)
+        self.precision = precision
+        self.act_dtype = _DTYPES[precision]
+        self.vec = 8 if self.act_dtype == torch.bfloat16 else 4
+        self.dropout_p = float(dropout_p)
+        self.noise_seed = int(seed)
+        self.training = True
+        self.poe_mode, self.prior_expert, self.poe_eps = _lib.POE_REF, 0, 1e-8
+        self.flat_feat = self.FLAT_C * self.FLAT_HW
+        self.n_pixels = self.IMG_C * self.IMG_H * self.IMG_H
+        # ---- flat parameter buffer, [encoders | decoders] (the two all-reduce buckets of data-parallel training)
+        self.layouts: Dict[str, Layout] = {}
+        self.state_keys = self.reference_keys(self.n_latents)
+        params = [Layout(k, s, kind, self.FLAT_C, self.FLAT_HW) for k, s, kind in self.state_keys
+                  if kind not in ("rm", "rv", "nbt")]
+        enc = [l for l in params if "encoder" in l.key]
+        dec = [l for l in params if "encoder" not in l.key]
+        off = 0
+        for l in enc + dec:
+            l.offset = off
+            off += round_up(l.numel, 64)
+            self.layouts[l.key] = l
+            if l is enc[-1]:
+                self.encoder_param_floats = off
+        self.param_floats = off
+        self.flat_params = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_grads = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_params_bf16 = torch.zeros(off, device=dev, dtype=torch.bfloat16) if self.act_dtype == torch.bfloat16 else None
+        # ---- BatchNorm buffers
+        self.bn_names = list(self.BN_LAYERS)
+        self.bn_index = {p: i for i, p in enumerate(self.bn_names)}
+        self.bn_off: Dict[str, int] = {}
+        boff = 0
+        for p in self.bn_names:
+            self.bn_off[p] = boff
+            boff += 2 * self.BN_LAYERS[p]
+        self.flat_buffers = torch.zeros(max(boff, 4), device=dev, dtype=torch.float32)
+        self.flat_nbt = torch.zeros(max(len(self.bn_names), 1), device=dev, dtype=torch.int64)
+        self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._ws: Dict[Tuple[int, int], object] = {}
+        self._pad: Dict[str, Tuple[torch.Tensor, int]] = {}
+        self.reset_parameters()
+
+    # ------------------------------------------------------------------ parameters
+    def reference_keys(self, n_latents: int):
+        raise NotImplementedError
+
+    def P(self, key: str) -> torch.Tensor:
+        l = self.layouts[key]
+        return self.flat_params[l.offset:l.offset + l.numel]
+
+    def G(self, key: str) -> torch.Tensor:
+        l = self.layouts[key]
+        return self.flat_grads[l.offset:l.offset + l.numel]
+
+    def W(self, key: str) -> torch.Tensor:
+        """GEMM-operand view of a weight in the activation dtype (bf16 mirror / fp32 master)."""
+        if self.act_dtype == torch.float32:
+            return self.P(key)
+        l = self.layouts[key]
+        return self.flat_params_bf16[l.offset:l.offset + l.numel]
+
+    def running(self, bn: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        o, c = self.bn_off[bn], self.BN_LAYERS[bn]
+        return self.flat_buffers[o:o + c], self.flat_buffers[o + c:o + 2 * c]
+
+    def _init_tensor(self, key, shape, kind, g, sd):
+        """PyTorch-default-like initialisation of one tensor (subclasses override for GRU / Embedding)."""
+        if kind == "nbt":
+            return torch.zeros((), dtype=torch.int64)
+        if kind == "rm":
+            return torch.zeros(shape)
+        if kind == "rv":
+            return torch.ones(shape)
+        if key.rsplit(".", 1)[0] in self.BN_LAYERS:
+            return torch.ones(shape) if key.endswith("weight") else torch.zeros(shape)
+        if len(shape) == 4:
+            fan_in = (shape[1] if kind == "conv" else shape[0]) * shape[2] * shape[3]
+            return (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+        if len(shape) == 2:
+            return (torch.rand(shape, generator=g) * 2 - 1) / shape[1] ** 0.5
+        fan_in = sd[key[:-4] + "weight"].shape[1]
+        return (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+
+    def reset_parameters(self, seed: int = 1234) -> None:
+        g = torch.Generator().manual_seed(seed)
+        sd: Dict[str, torch.Tensor] = {}
+        for k, shp, kind in self.state_keys:
+            sd[k] = self._init_tensor(k, shp, kind, g, sd)
+        self.load_state_dict(sd)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-shaped copies under the reference's keys."""
+        out: Dict[str, torch.Tensor] = {}
+        for k, shp, kind in self.state_keys:
+            bn = k.rsplit(".", 1)[0]
+            if kind == "rm":
+                out[k] = self.running(bn)[0].clone()
+            elif kind == "rv":
+                out[k] = self.running(bn)[1].clone()
+            elif kind == "nbt":
+                out[k] = self.flat_nbt[self.bn_index[bn]].clone()
+            else:
+                out[k] = self.layouts[k].to_reference(self.P(k))
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = True) -> None:
+        """Loads a reference checkpoint's state_dict (reference shapes; converted to the internal layouts)."""
+        missing = [k for k, _, _ in self.state_keys if k not in sd]
+        if strict and missing:
+            raise KeyError("missing keys in state_dict: %s" % missing[:4])
+        for k, shp, kind in self.state_keys:
+            if k not in sd:
+                continue
+            t = sd[k].detach()
+            if tuple(t.shape) != tuple(shp):
+                raise ValueError("%s: shape %s, expected %s" % (k, tuple(t.shape), shp))
+            bn = k.rsplit(".", 1)[0]
+            if kind == "rm":
+                self.running(bn)[0].copy_(t)
+            elif kind == "rv":
+                self.running(bn)[1].copy_(t)
+            elif kind == "nbt":
+                self.flat_nbt[self.bn_index[bn]] = int(t)
+            else:
+                self.P(k).copy_(self.layouts[k].to_internal(t.to(torch.float32)).reshape(-1))
+        self.sync_operands()
+
+    def grads_reference(self) -> Dict[str, torch.Tensor]:
+        """Gradients in the reference's layout (tests / interop)."""
+        return {k: l.to_reference(self.G(k)) for k, l in self.layouts.items()}
+
+    def sync_operands(self) -> None:
+        """Refresh the bf16 mirror after the fp32 master changed outside the fused Adam kernel."""
+        if self.flat_params_bf16 is not None:
+            _ops.cast_f32_to_bf16(self.flat_params, self.flat_params_bf16, self.param_floats)
+
+    def train(self, mode: bool = True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def cuda(self, *a, **k):
+        return self
+
+    def parameters(self):
+        return [self.flat_params]
+
+    # ------------------------------------------------------------------ Linear helpers
+    def operand(self, key: str, rows: int, cols: int) -> Tuple[torch.Tensor, int]:
+        """GEMM operand of weight `key` [rows, cols] with a TMA-legal row stride: the bf16 mirror / fp32 master itself,
+        or (row length not a 16-byte multiple) a zero-padded copy refreshed on every call."""
+        ld = round_up(cols, self.vec)
+        if ld == cols:
+            return self.W(key), cols
+        if key not in self._pad:
+            self._pad[key] = (torch.zeros(rows * ld, device=self.device, dtype=self.act_dtype), ld)
+        buf, _ = self._pad[key]
+        _ops.cast_pad_2d(self.P(key), rows, cols, cols, buf, ld)
+        return buf, ld
+
+    def linear_fwd(self, x, ldx, M, prefix, n_out, n_in, out, ldo, col_off: int = 0, refresh: bool = True):
+        """out[:, col_off:col_off+n_out] = x[M, n_in] W^T + b  (nn.Linear `prefix`)."""
+        w, ldw = self.operand(prefix + ".weight", n_out, n_in) if refresh else self._operand_cached(prefix + ".weight", n_in)
+        dst = out if col_off == 0 else out[col_off:]
+        _ops.gemm(x, w, dst, M, n_out, n_in, ldx, ldw, ldo, bias=self.P(prefix + ".bias"))
+
+    def _operand_cached(self, key: str, cols: int) -> Tuple[torch.Tensor, int]:
+        if key in self._pad:
+            return self._pad[key]
+        return self.W(key), cols
+
+    def linear_bwd(self, x, ldx, dy, lddy, M, prefix, n_out, n_in, dx=None, lddx=0, accumulate_dx=False, bias=True):
+        """dW += dy^T x, db += colsum(dy), dx (=|+=) dy W.  dy is [M, n_out] in the activation dtype with a row stride that
+        is a multiple of the vector width (columns >= n_out zero)."""
+        _ops.gemm(dy, x, self.G(prefix + ".weight"), n_out, n_in, M, lddy, ldx, n_in, a_major=1, b_major=1, accumulate=True)
+        if bias:
+            _ops.col_stats(dy, M, lddy, self.G(prefix + ".bias"), valid_channels=n_out)
+        if dx is not None:
+            w, ldw = self._operand_cached(prefix + ".weight", n_in)
+            _ops.gemm(dy, w, dx, M, n_in, n_out, lddy, ldw, lddx, b_major=1, accumulate=accumulate_dx)
+
+    # ------------------------------------------------------------------ conv stacks
+    def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
+        """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
+        NHWC bottleneck [B, FLAT_HW * FLAT_C]."""
+        src = image
+        for li, (pre, ci, co, k, s, p, hin, bn) in enumerate(self.ENC_CONVS):
+            ho = _ops.out_size(hin, k, s, p)
+            K = k * k * ci
+            ldk = ws.enc_ldk[li]
+            strides = _ops.nchw_strides(self.IMG_C, self.IMG_H, self.IMG_H) if li == 0 else None
+            g = _ops.geometry(B, hin, hin, ci, k, s, p, strides)
+            _ops.im2col(g, src, ws.enc_col[li], ldk)
+            rows = B * ho * ho
+            w, ldw = self.operand(pre + ".weight", co, K)
+            _ops.gemm(ws.enc_col[li], w, ws.enc_pre[li], rows, co, K, ldk, ldw, co)
+            if bn:
+                rm, rv = self.running(bn)
+                a = _ops.bn_args(ws.enc_pre[li], rows, co, rows, SWISH, training, self.P(bn + ".weight"), self.P(bn + ".bias"),
+                                 ws.enc_sum[li], ws.enc_sumsq[li], ws.enc_mean[li], ws.enc_rstd[li], rm, rv, updates=updates)
+                _ops.bn_act_forward(a, ws.enc_act[li])
+            else:
+                _ops.act_forward(SWISH, ws.enc_pre[li], ws.enc_act[li], rows, co)
+            src = ws.enc_act[li]
+
+    def features_bwd(self, ws, B) -> None:
+        """Backward of features_fwd from ws.enc_dact[-1] (gradient at the bottleneck)."""
+        for li in range(len(self.ENC_CONVS) - 1, -1, -1):
+            pre, ci, co, k, s, p, hin, bn = self.ENC_CONVS[li]
+            ho = _ops.out_size(hin, k, s, p)
+            K = k * k * ci
+            ldk = ws.enc_ldk[li]
+            rows = B * ho * ho
+            if bn:
+                a = _ops.bn_args(ws.enc_pre[li], rows, co, rows, SWISH, True, self.P(bn + ".weight"), self.P(bn + ".bias"),
+                                 None, None, ws.enc_mean[li], ws.enc_rstd[li])
+                _ops.bn_act_backward(a, ws.enc_dact[li], ws.enc_dpre[li], ws.enc_s0[li], ws.enc_s1[li], self.G(bn + ".weight"),
+                                     self.G(bn + ".bias"))
+            else:
+                _ops.act_backward(SWISH, ws.enc_pre[li], ws.enc_dact[li], ws.enc_dpre[li], rows, co)
+            # dW'[co, K] += dpre^T col
+            _ops.gemm(ws.enc_dpre[li], ws.enc_col[li], self.G(pre + ".weight"), co, K, rows, co, ldk, K, a_major=1, b_major=1,
+                      accumulate=True)
+            if li > 0:
+                w, ldw = self._operand_cached(pre + ".weight", K)
+                _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
+                g = _ops.geometry(B, hin, hin, ci, k, s, p)
+                _ops.col2im(g, ws.colbuf, ldk, ws.enc_dact[li - 1])
+
+    def hallucinate_fwd(self, ws, M3, rows_per_term, training: bool) -> None:
+        """The image decoder's transposed-conv stack on ws.u1 [M3, FLAT_HW*FLAT_C] -> ws.logits (NCHW fp32)."""
+        src = ws.u1
+        last = len(self.DEC_CONVS) - 1
+        for li, (pre, ci, co, k, s, p, hout, bn) in enumerate(self.DEC_CONVS):
+            hin = _ops.out_size(hout, k, s, p)
+            K = k * k * co
+            ldk = ws.dec_ldk[li]
+            rows_in = M3 * hin * hin
+            # col[M_in, (kh,kw,co)] = X[M_in, ci] * W'[ci, (kh,kw,co)]
+            w, ldw = self.operand(pre + ".weight", ci, K)
+            _ops.gemm(src, w, ws.colbuf, rows_in, K, ci, ci, ldw, ldk, b_major=1)
+            if li < last:
+                g = _ops.geometry(M3, hout, hout, co, k, s, p)
+                _ops.col2im(g, ws.colbuf, ldk, ws.dec_pre[li])
+                rows = M3 * hout * hout
+                rm, rv = self.running(bn)
+                a = _ops.bn_args(ws.dec_pre[li], rows, co, rows_per_term * hout * hout, SWISH, training, self.P(bn + ".weight"),
+                                 self.P(bn + ".bias"), ws.dec_sum[li], ws.dec_sumsq[li], ws.dec_mean[li], ws.dec_rstd[li],
+                                 rm, rv, updates=1)
+                ws.dec_bn[li] = a
+                _ops.bn_act_forward(a, ws.dec_act[li])
+                src = ws.dec_act[li]
+            else:
+                g = _ops.geometry(M3, hout, hout, co, k, s, p, _ops.nchw_strides(self.IMG_C, self.IMG_H, self.IMG_H))
+                _ops.col2im(g, ws.colbuf, ldk, ws.logits)
+
+    def hallucinate_bwd(self, ws, M3) -> None:
+        """Backward of hallucinate_fwd: the gradient at the logits sits in ws.logits (NCHW fp32); leaves ws.du1."""
+        dsrc = ws.logits
+        last = len(self.DEC_CONVS) - 1
+        for li in range(last, -1, -1):
+            pre, ci, co, k, s, p, hout, bn = self.DEC_CONVS[li]
+            hin = _ops.out_size(hout, k, s, p)
+            K = k * k * co
+            ldk = ws.dec_ldk[li]
+            rows_in = M3 * hin * hin
+            strides = _ops.nchw_strides(self.IMG_C, self.IMG_H, self.IMG_H) if li == last else None
+            g = _ops.geometry(M3, hout, hout, co, k, s, p, strides)
+            if li < last:
+                _ops.bn_act_backward(ws.dec_bn[li], dsrc, ws.dec_dpre[li], ws.dec_s0[li], ws.dec_s1[li], self.G(bn + ".weight"),
+                                     self.G(bn + ".bias"))
+                dsrc = ws.dec_dpre[li]
+            _ops.im2col(g, dsrc, ws.colbuf, ldk)                       # dcol [M_in, (kh,kw,co)]
+            x_in = ws.dec_act[li - 1] if li > 0 else ws.u1             # the layer's input [M_in, ci]
+            _ops.gemm(x_in, ws.colbuf, self.G(pre + ".weight"), ci, K, rows_in, ci, ldk, K, a_major=1, b_major=1, accumulate=True)
+            dx = ws.dec_dact[li - 1] if li > 0 else ws.du1
+            w, ldw = self._operand_cached(pre + ".weight", K)
+            _ops.gemm(ws.colbuf, w, dx, rows_in, ci, K, ldk, ldw, ci)
+            dsrc = dx
+
+    def alloc_conv_buffers(self, ws, B, G) -> None:
+        """Activation / gradient buffers of the two conv stacks for batch B and G stacked terms."""
+        dev, T = self.device, self.act_dtype
+        f32 = torch.float32
+        M3 = G * B
+
+        def buf(*shape, dtype=T):
+            return torch.zeros(*shape, device=dev, dtype=dtype)
+
+        ws.buf = buf
+        ws.enc_col, ws.enc_pre, ws.enc_act, ws.enc_dact, ws.enc_dpre, ws.enc_ldk = [], [], [], [], [], []
+        ws.enc_sum, ws.enc_sumsq, ws.enc_mean, ws.enc_rstd, ws.enc_s0, ws.enc_s1 = [], [], [], [], [], []
+        colmax = 0
+        for li, (pre, ci, co, k, s, p, hin, bn) in enumerate(self.ENC_CONVS):
+            ho = _ops.out_size(hin, k, s, p)
+            rows = B * ho * ho
+            ldk = round_up(k * k * ci, self.vec)
+            ws.enc_ldk.append(ldk)
+            ws.enc_col.append(buf(rows * ldk))
+            ws.enc_pre.append(buf(rows * co))
+            ws.enc_act.append(buf(rows * co))
+            ws.enc_dact.append(buf(rows * co))
+            ws.enc_dpre.append(buf(rows * co))
+            for lst in (ws.enc_sum, ws.enc_sumsq, ws.enc_mean, ws.enc_rstd, ws.enc_s0, ws.enc_s1):
+                lst.append(buf(co, dtype=f32))
+            if li > 0:
+                colmax = max(colmax, rows * ldk)
+        F = self.flat_feat
+        ws.u1pre, ws.u1, ws.du1, ws.du1pre = buf(M3 * F), buf(M3 * F), buf(M3 * F), buf(M3 * F)
+        ws.dec_pre, ws.dec_act, ws.dec_dact, ws.dec_dpre, ws.dec_ldk = [], [], [], [], []
+        ws.dec_sum, ws.dec_sumsq, ws.dec_mean, ws.dec_rstd, ws.dec_s0, ws.dec_s1 = [], [], [], [], [], []
+        ws.dec_bn = [None] * len(self.DEC_CONVS)
+        for li, (pre, ci, co, k, s, p, hout, bn) in enumerate(self.DEC_CONVS):
+            hin = _ops.out_size(hout, k, s, p)
+            ldk = round_up(k * k * co, self.vec)
+            ws.dec_ldk.append(ldk)
+            colmax = max(colmax, M3 * hin * hin * ldk)
+            rows = M3 * hout * hout
+            if li < len(self.DEC_CONVS) - 1:
+                ws.dec_pre.append(buf(rows * co))
+                ws.dec_act.append(buf(rows * co))
+                ws.dec_dact.append(buf(rows * co))
+                ws.dec_dpre.append(buf(rows * co))
+            for lst in (ws.dec_sum, ws.dec_sumsq, ws.dec_mean, ws.dec_rstd, ws.dec_s0, ws.dec_s1):
+                lst.append(buf(G, co, dtype=f32))
+        ws.colbuf = buf(colmax)
+        ws.logits = buf(M3 * self.n_pixels, dtype=f32)
+        ws.probs_image = buf(M3 * self.n_pixels, dtype=f32)
+        # latent
+        n = self.n_latents
+        ws.ld_z = round_up(n, self.vec)
+        ws.ld_enc = round_up(2 * n, self.vec)
+        ws.z = buf(M3 * ws.ld_z)
+        ws.dz = buf(M3 * n, dtype=f32)
+        ws.mu, ws.logvar = buf(M3 * n, dtype=f32), buf(M3 * n, dtype=f32)
+        ws.acc = buf(3, 4, dtype=f32)   # rows: image BCE sums, second-modality loss sums, weighted KL; columns: term
+
+    # ------------------------------------------------------------------ latent path
+    def latent_forward(self, ws, term_types, kl_weights, eps, training, enc_a, enc_b, R) -> None:
+        B, n, G = ws.B, self.n_latents, len(term_types)
+        la = _lib.LatentArgs()
+        la.batch, la.n_latents, la.n_terms = B, n, G
+        img_seen = 0
+        for gi, t in enumerate(term_types):
+            la.term_type[gi] = t
+            la.kl_weight[gi] = float(kl_weights[gi])
+            la.expert_a_row0[gi] = 0
+            if t != _lib.TERM_TEXT:
+                la.expert_a_row0[gi] = (img_seen * B) if R > 1 else 0
+                img_seen += 1
+        la.poe_mode, la.prior_expert, la.poe_eps = self.poe_mode, self.prior_expert, self.poe_eps
+        if enc_a is not None:
+            la.expert_a, la.ld_a = enc_a.data_ptr(), 2 * n
+        if enc_b is not None:
+            la.expert_b, la.ld_b = enc_b.data_ptr(), 2 * n
+        la.eps = None if eps is None else eps.data_ptr()
+        la.seed, la.step_counter = self.noise_seed, self._step_counter.data_ptr()
+        la.training = 1 if training else 0
+        la.z_dtype, la.z, la.ld_z = _ops.DT[self.act_dtype], ws.z.data_ptr(), ws.ld_z
+        la.mu, la.logvar, la.kl = ws.mu.data_ptr(), ws.logvar.data_ptr(), ws.acc[2].data_ptr()
+        ws.latent = la
+        _lib.check(_lib.load().mvae_latent_forward(C.byref(la), _ops.stream()), "mvae_latent_forward")
+
+    def latent_backward(self, ws, denc_a, denc_b) -> None:
+        la = ws.latent
+        la.dz_dtype, la.dz, la.ld_dz = _lib.DT_F32, ws.dz.data_ptr(), self.n_latents
+        la.d_dtype = _ops.DT[self.act_dtype]
+        la.d_expert_a, la.ld_da = (None if denc_a is None else denc_a.data_ptr()), ws.ld_enc
+        la.d_expert_b, la.ld_db = (None if denc_b is None else denc_b.data_ptr()), ws.ld_enc
+        _lib.check(_lib.load().mvae_latent_backward(C.byref(la), _ops.stream()), "mvae_latent_backward")
+
+    def workspace(self, batch: int, n_terms: int):
+        key = (int(batch), int(n_terms))
+        if key not in self._ws:
+            self._ws[key] = self._make_workspace(int(batch), int(n_terms))
+        return self._ws[key]
+
+    # subclass hooks
+    def _make_workspace(self, B, G):
+        raise NotImplementedError
+
+    def run_forward(self, ws, image, other, term_types, eps, training, lambdas, kl_weights, want_probs, with_loss):
+        raise NotImplementedError
+
+    def backward_decoders(self, ws):
+        """Decoder-side backward + latent backward: fills every decoder gradient (the first all-reduce bucket)."""
+        raise NotImplementedError
+
+    def backward_encoders(self, ws):
+        raise NotImplementedError
+
+    def bn_increments(self, term_types) -> List[int]:
+        raise NotImplementedError
+
+
+class Workspace:
+    pass
+
+
+class ConvMVAETrainer:
+    """zero_grad, the three forwards, the three loss_function calls, backward, Adam (celeba/train.py:132-157,
+    multimnist/train.py:148-175) as one stream of kernels; data-parallel when torch.distributed is initialised:
+    the decoder gradient bucket is all-reduced on a side stream while the encoder backward runs."""
+
+    def __init__(self, model: ConvMVAEBase, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, kl_lambda: float = 1e-3,
+                 use_cuda_graph: bool = False, group=None, overlap: bool = True):
+        self.model = model
+        self.lr, self.betas, self.eps, self.kl_lambda = float(lr), betas, float(eps), float(kl_lambda)
+        self.adam_m = torch.zeros_like(model.flat_params)
+        self.adam_v = torch.zeros_like(model.flat_params)
+        self.use_cuda_graph = use_cuda_graph
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self._inc_cache: Dict[Tuple, torch.Tensor] = {}
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.overlap = overlap
+        self.comm_stream = torch.cuda.Stream(device=model.device) if self.world > 1 else None
+        if self.world > 1:
+            dist.broadcast(model.flat_params, 0, group=group)
+            dist.broadcast(model.flat_buffers, 0, group=group)
+            dist.broadcast(model.flat_nbt, 0, group=group)
+            model.sync_operands()
+
+    def _increments(self, term_types) -> torch.Tensor:
+        key = tuple(term_types)
+        if key not in self._inc_cache:
+            self._inc_cache[key] = torch.tensor(self.model.bn_increments(term_types), dtype=torch.int64, device=self.model.device)
+        return self._inc_cache[key]
+
+    def _enqueue(self, ws, image, other, term_types, lambdas, eps, adam: bool) -> None:
+        m = self.model
+        B = ws.B
+        _ops.step_begin(m._step_counter, ws.acc.view(-1), m.flat_nbt, self._increments(term_types))
+        klw = [self.kl_lambda / B] * len(term_types)
+        m.run_forward(ws, image, other, term_types, eps, True, lambdas, klw, False, True)
+        m.backward_decoders(ws)
+        split = m.encoder_param_floats
+        if self.world > 1 and self.overlap:
+            main = torch.cuda.current_stream(m.device)
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(m.flat_grads[split:], op=dist.ReduceOp.SUM, group=self.group)
+            m.backward_encoders(ws)
+            dist.all_reduce(m.flat_grads[:split], op=dist.ReduceOp.SUM, group=self.group)
+            main.wait_stream(self.comm_stream)
+        else:
+            m.backward_encoders(ws)
+            if self.world > 1:
+                dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        if adam:
+            _ops.adam_step(m.flat_params, m.flat_grads, self.adam_m, self.adam_v, m.flat_params_bf16, m.param_floats, self.lr,
+                           self.betas[0], self.betas[1], self.eps, m._step_counter, 1.0 / self.world, True)
+
+    def _prepare(self, image, other):
+        m = self.model
+        return image.to(m.device, torch.float32).contiguous(), other
+
+    def step(self, image: torch.Tensor, other: torch.Tensor, terms: Sequence[str], lambdas, eps: Optional[torch.Tensor] = None,
+             adam: bool = True):
+        m = self.model
+        tt = tuple(m.TERMS[t] for t in terms)
+        lambdas = tuple(tuple(float(v) for v in l) for l in lambdas)
+        B = image.shape[0]
+        ws = m.workspace(B, len(tt))
+        image, other = self._prepare(image, other)
+        if eps is not None:
+            eps = eps.to(m.device, torch.float32).contiguous()
+        self._last = (ws, tt, lambdas)
+        if not self.use_cuda_graph:
+            self._enqueue(ws, image, other, tt, lambdas, eps, adam)
+            return ws.acc
+        key = (B, tt, lambdas, eps is not None, adam)
+        if key not in self._graphs:
+            st_img, st_oth = image.clone(), other.clone()
+            st_eps = None if eps is None else eps.clone()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                # warm-up outside capture (allocates padded operand copies, sets up NCCL), state restored afterwards
+                state = (m.flat_params, m.flat_buffers, m.flat_nbt, m._step_counter, self.adam_m, self.adam_v, m.flat_grads)
+                snap = [t.clone() for t in state]
+                self._enqueue(ws, st_img, st_oth, tt, lambdas, st_eps, adam)
+                for dst, src in zip(state, snap):
+                    dst.copy_(src)
+                m.sync_operands()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            lib = _lib.load()
+            before = lib.mvae_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue(ws, st_img, st_oth, tt, lambdas, st_eps, adam)
+            self._graphs[key] = (g, st_img, st_oth, st_eps, int(lib.mvae_launch_count() - before))
+        g, st_img, st_oth, st_eps, self.last_graph_launches = self._graphs[key]
+        st_img.copy_(image, non_blocking=True)
+        st_oth.copy_(other, non_blocking=True)
+        if st_eps is not None:
+            st_eps.copy_(eps, non_blocking=True)
+        g.replay()
+        return ws.acc
+
+    def teardown(self) -> None:
+        self._graphs.clear()

@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "../../include/mvae_b200.h"
 #include "common.cuh"
 
@@ -21,6 +23,10 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d: %s", static_cast<int>(e), cudaGetErrorString(e), file, line, what);
   return 2;
 }
+
+static std::atomic<long long> g_noted_launches{0};
+void note_launch(int n) { g_noted_launches.fetch_add(n, std::memory_order_relaxed); }
+long long noted_launches() { return g_noted_launches.load(std::memory_order_relaxed); }
 
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
@@ -64,6 +70,7 @@ int mvae_gemm(const mvae_gemm_args* a, void* stream) {
   g.epi.stat0 = a->col_sum; g.epi.stat1 = a->col_sumsq;
   g.epi.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : (1 << 30);
   g.dbg = reinterpret_cast<long long*>(a->debug_times);
+  note_launch(1);
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 

@@ -111,6 +111,10 @@ void set_gemm_debug_times(void* ptr, int epi_kind);
 // Tuning knobs readable from the environment (debug / bench sweeps only).
 int env_int(const char* name, int dflt);
 
+// Kernel launches enqueued by the operator-level entries (added to mvae_launch_count()).
+void note_launch(int n = 1);
+long long noted_launches();
+
 // Programmatic dependent launch (PDL).  Every kernel of the step starts with pdl_enter(): it lets the NEXT kernel
 // in the stream be scheduled as soon as all CTAs of this one are resident (its prologue - barrier init, TMEM
 // allocation, tensor-map prefetch - then overlaps this kernel's execution) and blocks until the PREVIOUS

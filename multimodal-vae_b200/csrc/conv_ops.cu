@@ -413,6 +413,7 @@ int launch_col_reduce_t(RedArgs a, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(TY) * TX * 2 * N * sizeof(float);
   col_reduce_kernel<T, kMode><<<dim3(a.groups * a.chunks, gy), kThreads, smem, st>>>(a);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 template <int kMode>
@@ -878,6 +879,7 @@ int mvae_im2col(const mvae_conv_geometry* q, int image_dtype, const void* image,
 #undef MVAE_I2C
   }
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -911,6 +913,7 @@ int mvae_col2im(const mvae_conv_geometry* q, int col_dtype, const void* col, int
 #undef MVAE_C2I
   }
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -973,6 +976,7 @@ int mvae_bn_act_forward(const mvae_bn_act_args* p, void* stream) {
   if (p->dtype == MVAE_F32) bn_act_fwd_kernel<float><<<blocks, kThreads, smem, st>>>(b);
   else bn_act_fwd_kernel<__nv_bfloat16><<<blocks, kThreads, smem, st>>>(b);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1004,6 +1008,7 @@ int mvae_bn_act_backward(const mvae_bn_act_args* p, void* stream) {
   if (p->dtype == MVAE_F32) bn_act_bwd_kernel<float><<<blocks, kThreads, smem, st>>>(b);
   else bn_act_bwd_kernel<__nv_bfloat16><<<blocks, kThreads, smem, st>>>(b);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1037,6 +1042,7 @@ int mvae_act_forward(int dtype, int act, const void* x, void* y, int64_t rows, i
                                                                static_cast<__nv_bfloat16*>(y), rows, channels, act, repeat,
                                                                ks, th, seed, step_counter);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1071,6 +1077,7 @@ int mvae_sigmoid_bce(const mvae_sigmoid_bce_args* p, void* stream) {
   const long long items = a.rows * (a.ld_pad_zero ? a.ldd : a.cols);
   sigmoid_bce_kernel<<<grid_for(items, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1103,6 +1110,7 @@ int mvae_latent_forward(const mvae_latent_args* p, void* stream) {
   MVAE_REQUIRE(a.z != nullptr && a.ldz >= a.n, "latent_forward: z required with ld_z >= n_latents");
   latent_kernel<false><<<grid_for(a.B * a.n, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 int mvae_latent_backward(const mvae_latent_args* p, void* stream) {
@@ -1111,6 +1119,7 @@ int mvae_latent_backward(const mvae_latent_args* p, void* stream) {
   MVAE_REQUIRE(a.d_enc_a != nullptr || a.d_enc_b != nullptr, "latent_backward: no gradient output");
   latent_kernel<true><<<grid_for(a.B * a.n, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1123,6 +1132,7 @@ int mvae_cast_pad_2d(const float* src, int64_t rows, int64_t cols, int64_t ld_sr
   if (dst_dtype == MVAE_F32) cast_pad_kernel<float><<<blocks, kThreads, 0, st>>>(src, rows, cols, ld_src, static_cast<float*>(dst), ld_dst);
   else cast_pad_kernel<__nv_bfloat16><<<blocks, kThreads, 0, st>>>(src, rows, cols, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 
@@ -1135,6 +1145,7 @@ int mvae_step_begin(int* step_counter, float* zero_buf, int64_t zero_floats, int
       step_counter, reinterpret_cast<float4*>(zero_buf), zero_buf != nullptr ? n4 : 0,
       reinterpret_cast<long long*>(counters), reinterpret_cast<const long long*>(increments), n_counters);
   MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
   return 0;
 }
 

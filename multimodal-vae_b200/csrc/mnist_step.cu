@@ -636,7 +636,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   return 0;
 }
 
-long long mvae_launch_count(void) { return g_launches; }
+long long mvae_launch_count(void) { return g_launches + mvae::noted_launches(); }
 
 // Byte offset of a named workspace buffer (tests / bring-up: lets the host inspect intermediate tensors).
 long long mvae_mnist_workspace_offset(const char* name, int batch, int n_latents, int dtype) {
