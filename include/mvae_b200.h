@@ -313,6 +313,60 @@ int mvae_cast_pad_2d(const float* src, int64_t rows, int64_t cols, int64_t ld_sr
 int mvae_step_begin(int* step_counter, float* zero_buf, int64_t zero_floats, int64_t* counters, const int64_t* increments,
                     int n_counters, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * MultiMNIST text path (multimnist/model.py:220-307).  The projections of every GRU cell are mvae_gemm calls; these
+ * entries are what sits between them.  Matrices carry explicit leading dimensions so that the reference's torch.cat
+ * of (embedding, z) and (hidden, z) are column ranges of one buffer.
+ */
+/* out[m, j] = act(table[indices[m * index_stride], j]), j < width: nn.Embedding (+ Swish, multimnist/model.py:299). */
+int mvae_embed_forward(const int64_t* indices, int64_t index_stride, const float* table, int vocab, int width, int act,
+                       int out_dtype, void* out, int64_t ld_out, int64_t rows, void* stream);
+/* dtable[indices[m], j] += dout[m, j] * act'(table[indices[m], j]) */
+int mvae_embed_backward(const int64_t* indices, int64_t index_stride, const float* table, int vocab, int width, int act,
+                        int dout_dtype, const void* dout, int64_t ld_dout, int64_t rows, float* dtable, void* stream);
+
+/* One nn.GRU cell step given gi = x W_ih^T + b_ih and gh = h W_hh^T + b_hh (fp32, gate order r, z, n):
+ *   r = sigmoid(gi_r + gh_r), z = sigmoid(gi_z + gh_z), n = tanh(gi_n + r * gh_n), h' = (1 - z) * n + z * h.
+ * forward writes h' (+ addend) to h_out (and h_out2) and keeps (r, z, n, gh_n) in `saved` [rows, 4*hidden];
+ * backward turns the gradient at h' (dh_a + dh_b) into dgi / dgh (GEMM operands, activation dtype) and the direct part
+ * of the gradient at h (dh_prev = dh * z; the caller adds dgh W_hh with an accumulating GEMM). */
+typedef struct mvae_gru_cell_args {
+  int64_t rows; int hidden;
+  const float* gi; int64_t ld_gi;
+  const float* gh; int64_t ld_gh;
+  int h_dtype; const void* h_prev; int64_t ld_h_prev;   /* NULL: zeros */
+  const void* addend; int64_t ld_addend;                /* optional, h_dtype */
+  void* h_out; int64_t ld_h_out;
+  void* h_out2; int64_t ld_h_out2;                       /* optional second destination */
+  float* saved;
+  int dh_a_dtype; const void* dh_a; int64_t ld_dh_a;
+  int dh_b_dtype; const void* dh_b; int64_t ld_dh_b;
+  int dg_dtype; void* dgi; void* dgh; int64_t ld_dg;     /* columns [3*hidden, ld_dg) are zero-filled */
+  float* dh_prev; int64_t ld_dh_prev;
+} mvae_gru_cell_args;
+int mvae_gru_cell_forward(const mvae_gru_cell_args* args, void* stream);
+int mvae_gru_cell_backward(const mvae_gru_cell_args* args, void* stream);
+
+/* F.log_softmax + F.nll_loss + torch.max of one decoding step (multimnist/model.py:285-287, 303-306; train.py:78):
+ *   logp = log_softmax(logits); argmax[m] = first maximum; loss[g] += -logp[m, target]; dlogits = grad_scale[g]*(softmax - onehot).
+ * Row m compares with target[(m % target_rows) * target_stride]. */
+typedef struct mvae_logsoftmax_nll_args {
+  int64_t rows; int classes; int64_t rows_per_group;
+  const float* logits; int64_t ld_logits;
+  const int64_t* target; int64_t target_stride; int64_t target_rows;
+  float grad_scale[3];
+  float* loss;
+  float* logp; int64_t ld_logp;
+  int64_t* argmax;
+  int grad_dtype; void* dlogits; int64_t ld_dlogits;
+} mvae_logsoftmax_nll_args;
+int mvae_logsoftmax_nll(const mvae_logsoftmax_nll_args* args, void* stream);
+
+/* dst[r, c] (+)= src[r, c] (+ src2[r, c]) for c < cols, with independent dtypes and leading dimensions. */
+int mvae_copy_2d(int src_dtype, const void* src, int64_t ld_src, int dst_dtype, void* dst, int64_t ld_dst, int64_t rows,
+                 int64_t cols, int accumulate, int src2_dtype, const void* src2, int64_t ld_src2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,6 +166,28 @@ class LatentArgs(C.Structure):
                 ("d_expert_b", c_void_p), ("ld_db", c_int64)]
 
 
+class GruCellArgs(C.Structure):
+    _fields_ = [("rows", c_int64), ("hidden", c_int),
+                ("gi", c_void_p), ("ld_gi", c_int64), ("gh", c_void_p), ("ld_gh", c_int64),
+                ("h_dtype", c_int), ("h_prev", c_void_p), ("ld_h_prev", c_int64),
+                ("addend", c_void_p), ("ld_addend", c_int64),
+                ("h_out", c_void_p), ("ld_h_out", c_int64), ("h_out2", c_void_p), ("ld_h_out2", c_int64),
+                ("saved", c_void_p),
+                ("dh_a_dtype", c_int), ("dh_a", c_void_p), ("ld_dh_a", c_int64),
+                ("dh_b_dtype", c_int), ("dh_b", c_void_p), ("ld_dh_b", c_int64),
+                ("dg_dtype", c_int), ("dgi", c_void_p), ("dgh", c_void_p), ("ld_dg", c_int64),
+                ("dh_prev", c_void_p), ("ld_dh_prev", c_int64)]
+
+
+class LogSoftmaxNllArgs(C.Structure):
+    _fields_ = [("rows", c_int64), ("classes", c_int), ("rows_per_group", c_int64),
+                ("logits", c_void_p), ("ld_logits", c_int64),
+                ("target", c_void_p), ("target_stride", c_int64), ("target_rows", c_int64),
+                ("grad_scale", c_float * 3), ("loss", c_void_p),
+                ("logp", c_void_p), ("ld_logp", c_int64), ("argmax", c_void_p),
+                ("grad_dtype", c_int), ("dlogits", c_void_p), ("ld_dlogits", c_int64)]
+
+
 def _conv_argtypes(lib) -> None:
     P = C.POINTER
     lib.mvae_conv_out_size.argtypes = [c_int] * 4
@@ -184,3 +206,12 @@ def _conv_argtypes(lib) -> None:
     lib.mvae_cast_pad_2d.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]
     lib.mvae_step_begin.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]
     lib.mvae_gemm.argtypes = [P(GemmArgs), c_void_p]
+    lib.mvae_embed_forward.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64,
+                                       c_void_p]
+    lib.mvae_embed_backward.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64,
+                                        c_void_p, c_void_p]
+    lib.mvae_gru_cell_forward.argtypes = [P(GruCellArgs), c_void_p]
+    lib.mvae_gru_cell_backward.argtypes = [P(GruCellArgs), c_void_p]
+    lib.mvae_logsoftmax_nll.argtypes = [P(LogSoftmaxNllArgs), c_void_p]
+    lib.mvae_copy_2d.argtypes = [c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
+                                 c_int64, c_void_p]

@@ -151,3 +151,72 @@ def adam_step(params, grads, m, v, params_bf16, count, lr, beta1, beta2, eps, st
 def cast_f32_to_bf16(src, dst, count):
     _lib.check(_lib.load().mvae_cast_f32_to_bf16(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_int64(int(count)),
                                                  stream()), "mvae_cast_f32_to_bf16")
+
+
+# ---------------------------------------------------------------- MultiMNIST text path
+def view_ptr(t: torch.Tensor, elem_offset: int = 0) -> int:
+    """Device address of element `elem_offset` of a flat tensor."""
+    return t.data_ptr() + int(elem_offset) * t.element_size()
+
+
+def embed_forward(indices, index_offset, index_stride, table, vocab, width, act, out, col_off, ld_out, rows):
+    _lib.check(_lib.load().mvae_embed_forward(view_ptr(indices, index_offset), int(index_stride), table.data_ptr(), int(vocab),
+                                              int(width), int(act), DT[out.dtype], view_ptr(out, col_off), int(ld_out), int(rows),
+                                              stream()), "mvae_embed_forward")
+
+
+def embed_backward(indices, index_offset, index_stride, table, vocab, width, act, dout, col_off, ld_dout, rows, dtable):
+    _lib.check(_lib.load().mvae_embed_backward(view_ptr(indices, index_offset), int(index_stride), table.data_ptr(), int(vocab),
+                                               int(width), int(act), DT[dout.dtype], view_ptr(dout, col_off), int(ld_dout),
+                                               int(rows), dtable.data_ptr(), stream()), "mvae_embed_backward")
+
+
+def gru_cell_forward(rows, hidden, gi, gh, h_prev, ld_h_prev, h_out, ld_h_out, saved, h_out2=None, ld_h_out2=0, addend=None,
+                     ld_addend=0) -> _lib.GruCellArgs:
+    a = _lib.GruCellArgs()
+    a.rows, a.hidden = int(rows), int(hidden)
+    a.gi, a.ld_gi, a.gh, a.ld_gh = gi.data_ptr(), 3 * hidden, gh.data_ptr(), 3 * hidden
+    a.h_dtype = DT[h_out.dtype]
+    a.h_prev, a.ld_h_prev = _p(h_prev), int(ld_h_prev)
+    a.addend, a.ld_addend = _p(addend), int(ld_addend)
+    a.h_out, a.ld_h_out = h_out.data_ptr(), int(ld_h_out)
+    a.h_out2, a.ld_h_out2 = _p(h_out2), int(ld_h_out2)
+    a.saved = saved.data_ptr()
+    _lib.check(_lib.load().mvae_gru_cell_forward(C.byref(a), stream()), "mvae_gru_cell_forward")
+    return a
+
+
+def gru_cell_backward(a: _lib.GruCellArgs, dh_a, ld_dh_a, dh_b, ld_dh_b, dgi, dgh, ld_dg, dh_prev, ld_dh_prev):
+    """`a` is the struct returned by gru_cell_forward for the same cell (gi / gh / h_prev / saved are reused)."""
+    a.dh_a_dtype, a.dh_a, a.ld_dh_a = (DT[dh_a.dtype], dh_a.data_ptr(), int(ld_dh_a)) if dh_a is not None else (0, None, 0)
+    a.dh_b_dtype, a.dh_b, a.ld_dh_b = (DT[dh_b.dtype], dh_b.data_ptr(), int(ld_dh_b)) if dh_b is not None else (0, None, 0)
+    a.dg_dtype, a.dgi, a.dgh, a.ld_dg = DT[dgi.dtype], dgi.data_ptr(), dgh.data_ptr(), int(ld_dg)
+    a.dh_prev, a.ld_dh_prev = _p(dh_prev), int(ld_dh_prev)
+    _lib.check(_lib.load().mvae_gru_cell_backward(C.byref(a), stream()), "mvae_gru_cell_backward")
+
+
+def logsoftmax_nll(logits, ld_logits, rows, classes, rows_per_group=0, target=None, target_offset=0, target_stride=1,
+                   target_rows=0, grad_scale=(0.0, 0.0, 0.0), loss=None, logp=None, logp_offset=0, ld_logp=0, argmax=None,
+                   dlogits=None, ld_dlogits=0):
+    a = _lib.LogSoftmaxNllArgs()
+    a.rows, a.classes, a.rows_per_group = int(rows), int(classes), int(rows_per_group)
+    a.logits, a.ld_logits = logits.data_ptr(), int(ld_logits)
+    if target is not None:
+        a.target, a.target_stride, a.target_rows = view_ptr(target, target_offset), int(target_stride), int(target_rows)
+    for i in range(3):
+        a.grad_scale[i] = float(grad_scale[i]) if i < len(grad_scale) else 0.0
+    a.loss = _p(loss)
+    if logp is not None:
+        a.logp, a.ld_logp = view_ptr(logp, logp_offset), int(ld_logp)
+    a.argmax = _p(argmax)
+    if dlogits is not None:
+        a.grad_dtype, a.dlogits, a.ld_dlogits = DT[dlogits.dtype], dlogits.data_ptr(), int(ld_dlogits)
+    _lib.check(_lib.load().mvae_logsoftmax_nll(C.byref(a), stream()), "mvae_logsoftmax_nll")
+
+
+def copy_2d(src, src_off, ld_src, dst, dst_off, ld_dst, rows, cols, accumulate=False, src2=None, src2_off=0, ld_src2=0):
+    _lib.check(_lib.load().mvae_copy_2d(DT[src.dtype], view_ptr(src, src_off), int(ld_src), DT[dst.dtype], view_ptr(dst, dst_off),
+                                        int(ld_dst), int(rows), int(cols), 1 if accumulate else 0,
+                                        DT[src2.dtype] if src2 is not None else 0,
+                                        view_ptr(src2, src2_off) if src2 is not None else None, int(ld_src2), stream()),
+               "mvae_copy_2d")

@@ -125,6 +125,7 @@ class MultimodalVAE(ConvMVAEBase):
     def run_forward(self, ws, image, attrs, term_types: Sequence[int], eps, training: bool, lambdas, kl_weights,
                     want_probs: bool, with_loss: bool) -> None:
         B, n = ws.B, self.n_latents
+        self.begin_forward()
         use_img = any(t != _lib.TERM_TEXT for t in term_types)
         use_att = any(t != _lib.TERM_IMAGE for t in term_types)
         n_img = sum(1 for t in term_types if t != _lib.TERM_TEXT)
@@ -241,6 +242,7 @@ class MultimodalVAE(ConvMVAEBase):
         B = z.shape[0]
         ws = self.workspace(B, 1)
         ws.z.view(B, ws.ld_z)[:, :self.n_latents].copy_(z.to(self.device))
+        self.begin_forward()
         self.decode(ws, self.training, ((0.0, 0.0),), True, False)
         return ws.probs_image.view(B, 3, 64, 64).clone(), ws.probs_attrs.view(B, N_ATTRS).clone()
 

@@ -139,6 +139,7 @@ class ConvMVAEBase:
         self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
         self._ws: Dict[Tuple[int, int], object] = {}
         self._pad: Dict[str, Tuple[torch.Tensor, int]] = {}
+        self._fresh = set()
         self.reset_parameters()
 
     # ------------------------------------------------------------------ parameters
@@ -251,15 +252,21 @@ class ConvMVAEBase:
     # ------------------------------------------------------------------ Linear helpers
     def operand(self, key: str, rows: int, cols: int) -> Tuple[torch.Tensor, int]:
         """GEMM operand of weight `key` [rows, cols] with a TMA-legal row stride: the bf16 mirror / fp32 master itself,
-        or (row length not a 16-byte multiple) a zero-padded copy refreshed on every call."""
+        or (row length not a 16-byte multiple) a zero-padded copy refreshed once per forward (begin_forward())."""
         ld = round_up(cols, self.vec)
         if ld == cols:
             return self.W(key), cols
         if key not in self._pad:
             self._pad[key] = (torch.zeros(rows * ld, device=self.device, dtype=self.act_dtype), ld)
         buf, _ = self._pad[key]
-        _ops.cast_pad_2d(self.P(key), rows, cols, cols, buf, ld)
+        if key not in self._fresh:
+            _ops.cast_pad_2d(self.P(key), rows, cols, cols, buf, ld)
+            self._fresh.add(key)
         return buf, ld
+
+    def begin_forward(self) -> None:
+        """The parameters may have changed since the last forward: padded operand copies must be rebuilt."""
+        self._fresh.clear()
 
     def linear_fwd(self, x, ldx, M, prefix, n_out, n_in, out, ldo, col_off: int = 0, refresh: bool = True):
         """out[:, col_off:col_off+n_out] = x[M, n_in] W^T + b  (nn.Linear `prefix`)."""

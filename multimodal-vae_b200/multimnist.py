@@ -1,0 +1,392 @@
+"""MultiMNIST MVAE (50x50 conv image encoder / decoder + <= 4 character text through GRUs) on the B200-native library.
+
+Reference surface kept (multimnist/model.py:20-93, multimnist/train.py:69-87,148-175):
+    MultimodalVAE(n_latents=20, use_cuda=False).forward(image=None, text=None)
+        -> (image_recon [B,1,50,50] probs, text_recon [B,4,12] log-probs, mu, logvar)
+    state_dict()/load_state_dict() with the reference's keys and shapes
+    MultiMNISTTrainer.step(image, text): zero_grad + vae(image, text) + vae(image=image) + vae(text=text) + the three
+        loss_function calls (lambdas (1,1), (1,.5), (0,1)) + backward + Adam.
+
+The conv stacks, parameter store and trainer come from convnet.py.  The text side is composed from tcgen05 GEMMs (the
+two projections of every GRU cell, z2h, h2p, h2o) and the kernels of csrc/text_ops.cu (embedding, GRU gate math,
+log_softmax + NLL + greedy argmax).  The text encoder runs once per step on [B] rows (the reference runs it twice on
+identical inputs); the autoregressive text decoder runs its 4 steps once on the stacked [3B] latents.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, _ops
+from .convnet import ConvMVAEBase, ConvMVAETrainer, Workspace, SWISH, round_up
+
+N_CHARS, SOS, FILL, MAX_LEN, H = 12, 10, 11, 4, 100   # multimnist/utils.py:14-19, model.py:25-29
+NONE = _lib.ACT_NONE
+
+
+class MultimodalVAE(ConvMVAEBase):
+    """Drop-in for multimnist/model.py:20-93.  `precision`: "bf16" (default) or "tf32" (fp32 storage; the parity path)."""
+
+    TERMS = {"joint": _lib.TERM_JOINT, "image": _lib.TERM_IMAGE, "text": _lib.TERM_TEXT}
+    IMG_C, IMG_H = 1, 50
+    ENC_CONVS = (("image_encoder.features.0", 1, 32, 4, 2, 1, 50, None),
+                 ("image_encoder.features.2", 32, 64, 4, 2, 1, 25, "image_encoder.features.3"),
+                 ("image_encoder.features.5", 64, 128, 4, 2, 1, 12, "image_encoder.features.6"),
+                 ("image_encoder.features.8", 128, 256, 4, 2, 0, 6, "image_encoder.features.9"))
+    DEC_CONVS = (("image_decoder.hallucinate.0", 256, 128, 4, 2, 0, 6, "image_decoder.hallucinate.1"),
+                 ("image_decoder.hallucinate.3", 128, 64, 4, 2, 1, 12, "image_decoder.hallucinate.4"),
+                 ("image_decoder.hallucinate.6", 64, 32, 5, 2, 1, 25, "image_decoder.hallucinate.7"),
+                 ("image_decoder.hallucinate.9", 32, 1, 4, 2, 1, 50, None))
+    FLAT_C, FLAT_HW = 256, 4
+    BN_LAYERS = {"image_encoder.features.3": 64, "image_encoder.features.6": 128, "image_encoder.features.9": 256,
+                 "image_decoder.hallucinate.1": 128, "image_decoder.hallucinate.4": 64, "image_decoder.hallucinate.7": 32}
+
+    def __init__(self, n_latents: int = 20, use_cuda: bool = True, precision: str = "bf16", dropout_p: float = 0.1,
+                 device: Optional[torch.device] = None, seed: int = 0):
+        super().__init__(n_latents, precision, dropout_p, device, seed)
+
+    def reference_keys(self, n_latents: int) -> List[Tuple[str, Tuple[int, ...], str]]:
+        """(key, reference shape, kind) in the reference's state_dict order (multimnist/model.py:22-31)."""
+        n = n_latents
+        out: List[Tuple[str, Tuple[int, ...], str]] = []
+
+        def bn(p, c):
+            out.extend([(p + ".weight", (c,), "plain"), (p + ".bias", (c,), "plain"), (p + ".running_mean", (c,), "rm"),
+                        (p + ".running_var", (c,), "rv"), (p + ".num_batches_tracked", (), "nbt")])
+
+        def lin(p, o, i, wkind="plain", bkind="plain"):
+            out.extend([(p + ".weight", (o, i), wkind), (p + ".bias", (o,), bkind)])
+
+        def gru(p, layer, inp, suffix=""):
+            out.extend([("%s.weight_ih_l%d%s" % (p, layer, suffix), (3 * H, inp), "plain"),
+                        ("%s.weight_hh_l%d%s" % (p, layer, suffix), (3 * H, H), "plain"),
+                        ("%s.bias_ih_l%d%s" % (p, layer, suffix), (3 * H,), "plain"),
+                        ("%s.bias_hh_l%d%s" % (p, layer, suffix), (3 * H,), "plain")])
+
+        for pre, ci, co, k, _, _, _, b in self.ENC_CONVS:
+            out.append((pre + ".weight", (co, ci, k, k), "conv"))
+            if b:
+                bn(b, co)
+        lin("image_encoder.classifier.0", 400, 1024, "fc_in")
+        lin("image_encoder.classifier.3", 200, 400)
+        lin("image_encoder.classifier.6", 2 * n, 200)
+        lin("image_decoder.upsample.0", 1024, n, "fc_out", "fc_out_bias")
+        for pre, ci, co, k, _, _, _, b in self.DEC_CONVS:
+            out.append((pre + ".weight", (ci, co, k, k), "convT"))
+            if b:
+                bn(b, co)
+        out.append(("text_encoder.embed.weight", (N_CHARS, H), "plain"))
+        gru("text_encoder.gru", 0, H)
+        gru("text_encoder.gru", 0, H, "_reverse")
+        lin("text_encoder.h2p", 2 * n, H)
+        out.append(("text_decoder.embed.weight", (N_CHARS, H), "plain"))
+        lin("text_decoder.z2h", H, n)
+        gru("text_decoder.gru", 0, H + n)
+        gru("text_decoder.gru", 1, H)
+        lin("text_decoder.h2o", N_CHARS, H + n)
+        return out
+
+    def _init_tensor(self, key, shape, kind, g, sd):
+        if key.endswith("embed.weight"):
+            return torch.randn(shape, generator=g)
+        if ".gru." in key:
+            return (torch.rand(shape, generator=g) * 2 - 1) / H ** 0.5
+        return super()._init_tensor(key, shape, kind, g, sd)
+
+    def bn_increments(self, term_types) -> List[int]:
+        ni = sum(1 for t in term_types if t != _lib.TERM_TEXT)
+        g = len(term_types)
+        return [ni, ni, ni, g, g, g]
+
+    def linear_shapes(self, n_terms: int, n_img_terms: int):
+        n = self.n_latents
+        return [(400, 1024, 1), (200, 400, n_img_terms), (2 * n, 200, n_img_terms), (1024, n, n_terms),
+                (3 * H, H, 5), (3 * H, H, 4), (2 * n, H, 1),                                  # text encoder cells + h2p
+                (H, n, n_terms), (3 * H, H + n, 4 * n_terms), (3 * H, H, 12 * n_terms), (N_CHARS, H + n, 4 * n_terms)]
+
+    # ------------------------------------------------------------------ workspace
+    def _make_workspace(self, B: int, G: int) -> Workspace:
+        ws = Workspace()
+        ws.B, ws.G, ws.R = B, G, 1
+        self.alloc_conv_buffers(ws, B, G)
+        buf, n, f32, dev = ws.buf, self.n_latents, torch.float32, self.device
+        M3, Rmax = G * B, 2
+        ws.f1pre, ws.f1, ws.df1, ws.df1pre = buf(B * 400), buf(Rmax * B * 400), buf(Rmax * B * 400), buf(B * 400)
+        ws.f2pre, ws.f2, ws.df2, ws.df2pre = buf(Rmax * B * 200), buf(Rmax * B * 200), buf(Rmax * B * 200), buf(Rmax * B * 200)
+        ws.encA, ws.encB = buf(Rmax * B * 2 * n, dtype=f32), buf(B * 2 * n, dtype=f32)
+        ws.dencA, ws.dencB = buf(Rmax * B * ws.ld_enc), buf(B * ws.ld_enc)
+        ldH = ws.ldH = round_up(H, self.vec)
+        ldc = ws.ldc = round_up(H + n, self.vec)
+        ldg = ws.ldg = round_up(3 * H, self.vec)
+        rows = max(M3, B)
+        ws.gi, ws.gh = buf(rows * 3 * H, dtype=f32), buf(rows * 3 * H, dtype=f32)
+        ws.dgi, ws.dgh = buf(rows * ldg), buf(rows * ldg)
+        # text encoder
+        ws.ex = [buf(B * ldH) for _ in range(MAX_LEN)]
+        ws.zeros_h = buf(rows * ldH)
+        ws.hf = [buf(B * ldH) for _ in range(MAX_LEN)]
+        ws.hsum = buf(B * ldH)
+        ws.te_saved = [buf(B * 4 * H, dtype=f32) for _ in range(MAX_LEN + 1)]
+        ws.te_cells = [None] * (MAX_LEN + 1)
+        ws.dhsum, ws.te_carry = buf(B * H, dtype=f32), buf(B * H, dtype=f32)
+        ws.dex = [buf(B * H, dtype=f32) for _ in range(MAX_LEN)]
+        # text decoder
+        ws.h_init = buf(M3 * ldH)
+        ws.cat1 = [buf(M3 * ldc) for _ in range(MAX_LEN)]
+        ws.cat2 = [buf(M3 * ldc) for _ in range(MAX_LEN)]
+        ws.h0 = [buf(M3 * ldH) for _ in range(MAX_LEN)]
+        ws.h0d = [buf(M3 * ldH) for _ in range(MAX_LEN)]
+        ws.h1 = [buf(M3 * ldH) for _ in range(MAX_LEN)]
+        ws.td_saved = [[buf(M3 * 4 * H, dtype=f32) for _ in range(MAX_LEN)] for _ in range(2)]
+        ws.td_cells = [[None] * MAX_LEN for _ in range(2)]
+        ws.c_in = [torch.full((M3,), SOS, device=dev, dtype=torch.int64) for _ in range(MAX_LEN + 1)]
+        ws.tlogits = buf(M3 * N_CHARS, dtype=f32)
+        ws.words = buf(M3 * MAX_LEN * N_CHARS, dtype=f32)
+        ws.ld_dlog = round_up(N_CHARS, self.vec)
+        ws.dlog = [buf(M3 * ws.ld_dlog) for _ in range(MAX_LEN)]
+        ws.dcat = buf(M3 * (H + n), dtype=f32)
+        ws.carry = [buf(M3 * H, dtype=f32), buf(M3 * H, dtype=f32)]
+        ws.dx1, ws.dx1_t, ws.dx1d_t = buf(M3 * H, dtype=f32), buf(M3 * ldH), buf(M3 * ldH)
+        ws.dhinit = buf(M3 * ldH)
+        return ws
+
+    # ------------------------------------------------------------------ GRU helpers
+    def _cell_fwd(self, ws, rows, x, ldx, n_in, h_prev, prefix, suffix, saved, h_out, h_out2=None, ld_h_out2=0, addend=None):
+        """One GRU cell: gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (tcgen05 GEMMs), then the gate kernel."""
+        wi, ldwi = self.operand("%s.weight_ih_%s" % (prefix, suffix), 3 * H, n_in)
+        wh, ldwh = self.operand("%s.weight_hh_%s" % (prefix, suffix), 3 * H, H)
+        _ops.gemm(x, wi, ws.gi, rows, 3 * H, n_in, ldx, ldwi, 3 * H, bias=self.P("%s.bias_ih_%s" % (prefix, suffix)))
+        hp = h_prev if h_prev is not None else ws.zeros_h
+        _ops.gemm(hp, wh, ws.gh, rows, 3 * H, H, ws.ldH, ldwh, 3 * H, bias=self.P("%s.bias_hh_%s" % (prefix, suffix)))
+        return _ops.gru_cell_forward(rows, H, ws.gi, ws.gh, h_prev, ws.ldH, h_out, ws.ldH, saved, h_out2, ld_h_out2, addend, ws.ldH)
+
+    def _cell_bwd(self, ws, rows, cell, x, ldx, n_in, h_prev, prefix, suffix, dh_a, ld_dh_a, dh_b, carry, dx, lddx,
+                  accumulate_dx=False, propagate_h=True):
+        """Backward of _cell_fwd: parameter gradients, dx (=|+=) dgi W_ih, carry = dh*z + dgh W_hh (gradient at h_prev)."""
+        _ops.gru_cell_backward(cell, dh_a, ld_dh_a, dh_b, H, ws.dgi, ws.dgh, ws.ldg, carry, H)
+        G = self.G
+        ki, kh = "%s.weight_ih_%s" % (prefix, suffix), "%s.weight_hh_%s" % (prefix, suffix)
+        _ops.gemm(ws.dgi, x, G(ki), 3 * H, n_in, rows, ws.ldg, ldx, n_in, a_major=1, b_major=1, accumulate=True)
+        _ops.col_stats(ws.dgi, rows, ws.ldg, G("%s.bias_ih_%s" % (prefix, suffix)), valid_channels=3 * H)
+        _ops.col_stats(ws.dgh, rows, ws.ldg, G("%s.bias_hh_%s" % (prefix, suffix)), valid_channels=3 * H)
+        if h_prev is not None:
+            _ops.gemm(ws.dgh, h_prev, G(kh), 3 * H, H, rows, ws.ldg, ws.ldH, H, a_major=1, b_major=1, accumulate=True)
+            if propagate_h and carry is not None:
+                wh, ldwh = self._operand_cached(kh, H)
+                _ops.gemm(ws.dgh, wh, carry, rows, H, 3 * H, ws.ldg, ldwh, H, b_major=1, accumulate=True)
+        if dx is not None:
+            wi, ldwi = self._operand_cached(ki, n_in)
+            _ops.gemm(ws.dgi, wi, dx, rows, n_in, 3 * H, ws.ldg, ldwi, lddx, b_major=1, accumulate=accumulate_dx)
+
+    # ------------------------------------------------------------------ forward
+    def run_forward(self, ws, image, text, term_types: Sequence[int], eps, training: bool, lambdas, kl_weights,
+                    want_probs: bool, with_loss: bool) -> None:
+        B, n = ws.B, self.n_latents
+        self.begin_forward()
+        use_img = any(t != _lib.TERM_TEXT for t in term_types)
+        use_txt = any(t != _lib.TERM_IMAGE for t in term_types)
+        n_img = sum(1 for t in term_types if t != _lib.TERM_TEXT)
+        R = n_img if (training and self.dropout_p > 0 and n_img > 1) else 1
+        p = self.dropout_p if training else 0.0
+        ws.R, ws.training, ws.use_img, ws.use_txt = R, training, use_img, use_txt
+        ws.image, ws.text = image, text
+        if use_img:
+            self.features_fwd(ws, image, B, training, n_img)
+            # classifier: Linear(1024,400) Swish Dropout Linear(400,200) Swish Dropout Linear(200,2n)  multimnist/model.py:172-180
+            self.linear_fwd(ws.enc_act[3], 1024, B, "image_encoder.classifier.0", 400, 1024, ws.f1pre, 400)
+            _ops.act_forward(SWISH, ws.f1pre, ws.f1, B, 400, repeat=R, dropout_p=p, seed=self.noise_seed + 101,
+                             step_counter=self._step_counter)
+            self.linear_fwd(ws.f1, 400, R * B, "image_encoder.classifier.3", 200, 400, ws.f2pre, 200)
+            _ops.act_forward(SWISH, ws.f2pre, ws.f2, R * B, 200, dropout_p=p, seed=self.noise_seed + 202,
+                             step_counter=self._step_counter)
+            self.linear_fwd(ws.f2, 200, R * B, "image_encoder.classifier.6", 2 * n, 200, ws.encA, 2 * n)
+        if use_txt:
+            self._text_encoder_fwd(ws, text, B)
+        self.latent_forward(ws, term_types, kl_weights, eps, training, ws.encA if use_img else None,
+                            ws.encB if use_txt else None, R)
+        self.decode(ws, training, lambdas, want_probs, with_loss)
+
+    def _text_encoder_fwd(self, ws, text, B) -> None:
+        """multimnist/model.py:220-249."""
+        n = self.n_latents
+        emb = self.P("text_encoder.embed.weight")
+        g = "text_encoder.gru"
+        for t in range(MAX_LEN):
+            _ops.embed_forward(text, t, MAX_LEN, emb, N_CHARS, H, NONE, ws.ex[t], 0, ws.ldH, B)
+        for t in range(MAX_LEN):
+            ws.te_cells[t] = self._cell_fwd(ws, B, ws.ex[t], ws.ldH, H, ws.hf[t - 1] if t > 0 else None, g, "l0", ws.te_saved[t],
+                                            ws.hf[t])
+        # reverse direction at the last position: one cell from a zero state; its output is summed with the forward one
+        ws.te_cells[MAX_LEN] = self._cell_fwd(ws, B, ws.ex[MAX_LEN - 1], ws.ldH, H, None, g, "l0_reverse", ws.te_saved[MAX_LEN],
+                                              ws.hsum, addend=ws.hf[MAX_LEN - 1])
+        self.linear_fwd(ws.hsum, ws.ldH, B, "text_encoder.h2p", 2 * n, H, ws.encB, 2 * n)
+
+    def decode(self, ws, training: bool, lambdas, want_probs: bool, with_loss: bool) -> None:
+        """Image decoder (multimnist/model.py:192-217) and greedy text decoder (:252-307) on the stacked latents."""
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
+        npx = self.n_pixels
+        self.linear_fwd(ws.z, ws.ld_z, M3, "image_decoder.upsample.0", 1024, n, ws.u1pre, 1024)
+        _ops.act_forward(SWISH, ws.u1pre, ws.u1, M3, 1024)
+        self.hallucinate_fwd(ws, M3, B, training)
+        sx = [float(lambdas[g][0]) / (B * npx) for g in range(G)]
+        _ops.sigmoid_bce(ws.logits, npx, M3, npx, rows_per_group=B, target=ws.image if with_loss else None, ld_target=npx,
+                         target_rows=B, grad_scale=sx, loss=ws.acc[0] if with_loss else None,
+                         probs=ws.probs_image if want_probs else None, ld_probs=npx,
+                         dlogits=ws.logits if with_loss else None, ld_dlogits=npx)
+        # ---- text decoder
+        sy = [float(lambdas[g][1]) / (B * MAX_LEN) for g in range(G)]
+        p = self.dropout_p if training else 0.0
+        ws.td_dropout = p
+        g = "text_decoder.gru"
+        emb = self.P("text_decoder.embed.weight")
+        ldH, ldc = ws.ldH, ws.ldc
+        wz, ldwz = self.operand("text_decoder.z2h.weight", H, n)
+        _ops.gemm(ws.z, wz, ws.h_init, M3, H, n, ws.ld_z, ldwz, ldH, bias=self.P("text_decoder.z2h.bias"))
+        for t in range(MAX_LEN):
+            _ops.embed_forward(ws.c_in[t], 0, 1, emb, N_CHARS, H, SWISH, ws.cat1[t], 0, ldc, M3)
+            _ops.copy_2d(ws.z, 0, ws.ld_z, ws.cat1[t], H, ldc, M3, n)
+            ws.td_cells[0][t] = self._cell_fwd(ws, M3, ws.cat1[t], ldc, H + n, ws.h0[t - 1] if t > 0 else ws.h_init, g, "l0",
+                                               ws.td_saved[0][t], ws.h0[t])
+            x1 = ws.h0[t]
+            if p > 0:
+                _ops.act_forward(NONE, ws.h0[t], ws.h0d[t], M3, ldH, dropout_p=p, seed=self.noise_seed + 303 + t,
+                                 step_counter=self._step_counter)
+                x1 = ws.h0d[t]
+            ws.td_cells[1][t] = self._cell_fwd(ws, M3, x1, ldH, H, ws.h1[t - 1] if t > 0 else ws.h_init, g, "l1",
+                                               ws.td_saved[1][t], ws.h1[t], h_out2=ws.cat2[t], ld_h_out2=ldc)
+            _ops.copy_2d(ws.z, 0, ws.ld_z, ws.cat2[t], H, ldc, M3, n)
+            self.linear_fwd(ws.cat2[t], ldc, M3, "text_decoder.h2o", N_CHARS, H + n, ws.tlogits, N_CHARS)
+            _ops.logsoftmax_nll(ws.tlogits, N_CHARS, M3, N_CHARS, rows_per_group=B,
+                                target=ws.text if with_loss else None, target_offset=t, target_stride=MAX_LEN, target_rows=B,
+                                grad_scale=sy, loss=ws.acc[1] if with_loss else None, logp=ws.words, logp_offset=t * N_CHARS,
+                                ld_logp=MAX_LEN * N_CHARS, argmax=ws.c_in[t + 1],
+                                dlogits=ws.dlog[t] if with_loss else None, ld_dlogits=ws.ld_dlog)
+
+    # ------------------------------------------------------------------ backward (multimnist/train.py:167-168)
+    def backward_decoders(self, ws) -> None:
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
+        Gd = self.G
+        # image decoder first: its latent gradient is STORED into dz, the text decoder accumulates on top
+        self.hallucinate_bwd(ws, M3)
+        _ops.act_backward(SWISH, ws.u1pre, ws.du1, ws.du1pre, M3, 1024, dbias=Gd("image_decoder.upsample.0.bias"))
+        self.linear_bwd(ws.z, ws.ld_z, ws.du1pre, 1024, M3, "image_decoder.upsample.0", 1024, n, dx=ws.dz, lddx=n, bias=False)
+        # text decoder, backward through time
+        g = "text_decoder.gru"
+        emb = self.P("text_decoder.embed.weight")
+        ldH, ldc, p = ws.ldH, ws.ldc, ws.td_dropout
+        Kc = H + n
+        for t in range(MAX_LEN - 1, -1, -1):
+            last = t == MAX_LEN - 1
+            self.linear_bwd(ws.cat2[t], ldc, ws.dlog[t], ws.ld_dlog, M3, "text_decoder.h2o", N_CHARS, Kc, dx=ws.dcat, lddx=Kc)
+            _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
+            x1 = ws.h0d[t] if p > 0 else ws.h0[t]
+            dx1 = ws.dx1_t if p > 0 else ws.dx1
+            self._cell_bwd(ws, M3, ws.td_cells[1][t], x1, ldH, H, ws.h1[t - 1] if t > 0 else ws.h_init, g, "l1",
+                           ws.dcat, Kc, None if last else ws.carry[1], ws.carry[1], dx1, ldH if p > 0 else H)
+            if p > 0:
+                _ops.act_backward(NONE, ws.h0[t], ws.dx1_t, ws.dx1d_t, M3, ldH, dropout_p=p, seed=self.noise_seed + 303 + t,
+                                  step_counter=self._step_counter)
+                dh0, ld_dh0 = ws.dx1d_t, ldH
+            else:
+                dh0, ld_dh0 = ws.dx1, H
+            self._cell_bwd(ws, M3, ws.td_cells[0][t], ws.cat1[t], ldc, Kc, ws.h0[t - 1] if t > 0 else ws.h_init, g, "l0",
+                           dh0, ld_dh0, None if last else ws.carry[0], ws.carry[0], ws.dcat, Kc)
+            _ops.embed_backward(ws.c_in[t], 0, 1, emb, N_CHARS, H, SWISH, ws.dcat, 0, Kc, M3, Gd("text_decoder.embed.weight"))
+            _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
+        # both GRU layers start from h = z2h(z)
+        _ops.copy_2d(ws.carry[0], 0, H, ws.dhinit, 0, ldH, M3, H, src2=ws.carry[1], ld_src2=H)
+        self.linear_bwd(ws.z, ws.ld_z, ws.dhinit, ldH, M3, "text_decoder.z2h", H, n, dx=ws.dz, lddx=n, accumulate_dx=True)
+        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_txt else None)
+
+    def backward_encoders(self, ws) -> None:
+        B, n, R = ws.B, self.n_latents, ws.R
+        Gd = self.G
+        p = self.dropout_p if ws.training else 0.0
+        if ws.use_txt:
+            g = "text_encoder.gru"
+            ldH = ws.ldH
+            self.linear_bwd(ws.hsum, ldH, ws.dencB, ws.ld_enc, B, "text_encoder.h2p", 2 * n, H, dx=ws.dhsum, lddx=H)
+            # reverse-direction cell (zero initial state: no W_hh gradient, no carry)
+            self._cell_bwd(ws, B, ws.te_cells[MAX_LEN], ws.ex[MAX_LEN - 1], ldH, H, None, g, "l0_reverse", ws.dhsum, H, None, None,
+                           ws.dex[MAX_LEN - 1], H)
+            for t in range(MAX_LEN - 1, -1, -1):
+                last = t == MAX_LEN - 1
+                self._cell_bwd(ws, B, ws.te_cells[t], ws.ex[t], ldH, H, ws.hf[t - 1] if t > 0 else None, g, "l0",
+                               ws.dhsum if last else None, H, None if last else ws.te_carry, ws.te_carry, ws.dex[t], H,
+                               accumulate_dx=last)
+                _ops.embed_backward(ws.text, t, MAX_LEN, self.P("text_encoder.embed.weight"), N_CHARS, H, NONE, ws.dex[t], 0, H, B,
+                                    Gd("text_encoder.embed.weight"))
+        if ws.use_img:
+            RB = R * B
+            self.linear_bwd(ws.f2, 200, ws.dencA, ws.ld_enc, RB, "image_encoder.classifier.6", 2 * n, 200, dx=ws.df2, lddx=200)
+            _ops.act_backward(SWISH, ws.f2pre, ws.df2, ws.df2pre, RB, 200, dropout_p=p, seed=self.noise_seed + 202,
+                              step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.3.bias"))
+            self.linear_bwd(ws.f1, 400, ws.df2pre, 200, RB, "image_encoder.classifier.3", 200, 400, dx=ws.df1, lddx=400, bias=False)
+            _ops.act_backward(SWISH, ws.f1pre, ws.df1, ws.df1pre, B, 400, repeat=R, dropout_p=p, seed=self.noise_seed + 101,
+                              step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.0.bias"))
+            self.linear_bwd(ws.enc_act[3], 1024, ws.df1pre, 400, B, "image_encoder.classifier.0", 400, 1024, dx=ws.enc_dact[3],
+                            lddx=1024, bias=False)
+            self.features_bwd(ws, B)
+
+    # ------------------------------------------------------------------ module surface
+    def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
+        """multimnist/model.py:58-93: returns (image_recon, text_recon log-probs [B,4,12], mu, logvar); forward only."""
+        assert image is not None or text is not None
+        t = _lib.TERM_JOINT if (image is not None and text is not None) else (_lib.TERM_IMAGE if image is not None else _lib.TERM_TEXT)
+        B = (image if image is not None else text).shape[0]
+        ws = self.workspace(B, 1)
+        image = None if image is None else image.to(self.device, torch.float32).contiguous()
+        text = None if text is None else text.to(self.device, torch.int64).contiguous()
+        if eps is not None:
+            eps = eps.to(self.device, torch.float32).contiguous()
+        self.run_forward(ws, image, text, (t,), eps, self.training, ((0.0, 0.0),), (0.0,), True, False)
+        n = self.n_latents
+        return (ws.probs_image.view(B, 1, 50, 50).clone(), ws.words.view(B, MAX_LEN, N_CHARS).clone(),
+                ws.mu.view(1, B, n)[0].clone(), ws.logvar.view(1, B, n)[0].clone())
+
+    __call__ = forward
+
+    def _decode_only(self, z: torch.Tensor):
+        B = z.shape[0]
+        ws = self.workspace(B, 1)
+        ws.z.view(B, ws.ld_z)[:, :self.n_latents].copy_(z.to(self.device))
+        self.begin_forward()
+        self.decode(ws, self.training, ((0.0, 0.0),), True, False)
+        return ws.probs_image.view(B, 1, 50, 50).clone(), ws.words.view(B, MAX_LEN, N_CHARS).clone()
+
+    def decode_image(self, z):
+        return self._decode_only(z)[0]
+
+    image_decoder = decode_image
+
+    def decode_text(self, z):
+        return self._decode_only(z)[1]
+
+
+class MultiMNISTTrainer(ConvMVAETrainer):
+    """multimnist/train.py:148-175 with its lambdas (1,1), (1,.5), (0,1) and kl_lambda 1e-3 (:227)."""
+
+    def _prepare(self, image, text):
+        m = self.model
+        return image.to(m.device, torch.float32).contiguous(), text.to(m.device, torch.int64).contiguous()
+
+    def step(self, image, text, terms: Sequence[str] = ("joint", "image", "text"),
+             lambdas: Sequence[Tuple[float, float]] = ((1.0, 1.0), (1.0, 0.5), (0.0, 1.0)), eps: Optional[torch.Tensor] = None,
+             adam: bool = True):
+        return super().step(image, text, terms, lambdas, eps, adam)
+
+    def losses(self) -> List[Tuple[float, float, float, float]]:
+        """Per-term (total, image BCE term, text NLL term, KL term) of the last step; multimnist/train.py:69-87."""
+        ws, tt, lambdas = self._last
+        acc = ws.acc.cpu()
+        B = ws.B
+        out = []
+        for g in range(len(tt)):
+            x = float(acc[0, g]) * lambdas[g][0] / (B * 2500)
+            y = float(acc[1, g]) * lambdas[g][1] / (B * MAX_LEN)
+            k = float(acc[2, g])
+            out.append((x + y + k, x, y, k))
+        return out
