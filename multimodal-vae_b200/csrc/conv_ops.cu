@@ -151,14 +151,15 @@ __global__ void __launch_bounds__(kThreads) col2im_vec_kernel(const T* __restric
     float acc[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[j] = 0.f;
-    for (int kh = 0; kh < g.k; ++kh) {
+    // only taps with (h + pad - kh) divisible by the stride contribute: kh = (h + pad) % stride, + stride, ...
+    for (int kh = (h + g.pad) % g.stride; kh < g.k; kh += g.stride) {
       const int th = h + g.pad - kh;
-      if (th < 0 || th % g.stride != 0) continue;
+      if (th < 0) break;
       const int ho = th / g.stride;
       if (ho >= g.Ho) continue;
-      for (int kw = 0; kw < g.k; ++kw) {
+      for (int kw = (w + g.pad) % g.stride; kw < g.k; kw += g.stride) {
         const int tw = w + g.pad - kw;
-        if (tw < 0 || tw % g.stride != 0) continue;
+        if (tw < 0) break;
         const int wo = tw / g.stride;
         if (wo >= g.Wo) continue;
         float v[N];
@@ -176,66 +177,65 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads) im2col_any_kernel(const TI* __restrict__ x, long long sn, long long sh,
                                                               long long sw, long long sc, TO* __restrict__ col,
                                                               long long ldcol, Geom g) {
+  // one thread per (m, tap), all channels: neighbouring threads read neighbouring pixels of one channel plane
+  // (NCHW sources) and write neighbouring C-element groups of one col row
   const int kk = g.k * g.k;
-  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * kk * g.C;
+  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * kk;
   for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int c = static_cast<int>(i % g.C);
-    long long r = i / g.C;
-    const int tap = static_cast<int>(r % kk);
-    const long long m = r / kk;
+    const int tap = static_cast<int>(i % kk);
+    const long long m = i / kk;
     const int wo = static_cast<int>(m % g.Wo);
     const long long t = m / g.Wo;
     const int ho = static_cast<int>(t % g.Ho);
     const long long n = t / g.Ho;
     const int kh = tap / g.k, kw = tap - kh * g.k;
     const int hi = ho * g.stride - g.pad + kh, wi = wo * g.stride - g.pad + kw;
-    float v = 0.f;
-    if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) v = ld1(x + n * sn + hi * sh + wi * sw + c * sc);
-    st1(col + m * ldcol + static_cast<long long>(tap) * g.C + c, v);
+    const bool inside = hi >= 0 && hi < g.H && wi >= 0 && wi < g.W;
+    const TI* src = x + n * sn + hi * sh + wi * sw;
+    TO* dst = col + m * ldcol + static_cast<long long>(tap) * g.C;
+    for (int c = 0; c < g.C; ++c) st1(dst + c, inside ? ld1(src + c * sc) : 0.f);
   }
 }
-// thread order follows the OUTPUT's fastest axis: sw == 1 (NCHW) iterates w fastest, else c fastest
+// one thread per output pixel, all channels (w fastest): a warp walks 32 neighbouring pixels, whose taps sit in a
+// handful of contiguous col rows
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(kThreads) col2im_any_kernel(const TI* __restrict__ col, long long ldcol,
                                                               TO* __restrict__ y, long long sn, long long sh,
                                                               long long sw, long long sc, Geom g) {
-  const long long total = static_cast<long long>(g.B) * g.H * g.W * g.C;
-  const bool w_fast = sw == 1;
+  constexpr int kMaxC = 8;
+  const long long total = static_cast<long long>(g.B) * g.H * g.W;
   for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * kThreads) {
-    int c, h, w;
-    long long n;
-    if (w_fast) {
-      w = static_cast<int>(i % g.W);
-      long long r = i / g.W;
-      h = static_cast<int>(r % g.H);
-      r /= g.H;
-      c = static_cast<int>(r % g.C);
-      n = r / g.C;
-    } else {
-      c = static_cast<int>(i % g.C);
-      long long r = i / g.C;
-      w = static_cast<int>(r % g.W);
-      r /= g.W;
-      h = static_cast<int>(r % g.H);
-      n = r / g.H;
-    }
-    float acc = 0.f;
-    for (int kh = 0; kh < g.k; ++kh) {
-      const int th = h + g.pad - kh;
-      if (th < 0 || th % g.stride != 0) continue;
-      const int ho = th / g.stride;
-      if (ho >= g.Ho) continue;
-      for (int kw = 0; kw < g.k; ++kw) {
-        const int tw = w + g.pad - kw;
-        if (tw < 0 || tw % g.stride != 0) continue;
-        const int wo = tw / g.stride;
-        if (wo >= g.Wo) continue;
-        acc += ld1(col + ((n * g.Ho + ho) * g.Wo + wo) * ldcol + static_cast<long long>(kh * g.k + kw) * g.C + c);
+    const int w = static_cast<int>(i % g.W);
+    long long r = i / g.W;
+    const int h = static_cast<int>(r % g.H);
+    const long long n = r / g.H;
+    for (int c0 = 0; c0 < g.C; c0 += kMaxC) {
+      const int cn = min(kMaxC, g.C - c0);
+      float acc[kMaxC];
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c) acc[c] = 0.f;
+      for (int kh = (h + g.pad) % g.stride; kh < g.k; kh += g.stride) {
+        const int th = h + g.pad - kh;
+        if (th < 0) break;
+        const int ho = th / g.stride;
+        if (ho >= g.Ho) continue;
+        for (int kw = (w + g.pad) % g.stride; kw < g.k; kw += g.stride) {
+          const int tw = w + g.pad - kw;
+          if (tw < 0) break;
+          const int wo = tw / g.stride;
+          if (wo >= g.Wo) continue;
+          const TI* src = col + ((n * g.Ho + ho) * g.Wo + wo) * ldcol + static_cast<long long>(kh * g.k + kw) * g.C + c0;
+#pragma unroll
+          for (int c = 0; c < kMaxC; ++c)
+            if (c < cn) acc[c] += ld1(src + c);
+        }
       }
+#pragma unroll
+      for (int c = 0; c < kMaxC; ++c)
+        if (c < cn) st1(y + n * sn + h * sh + w * sw + (c0 + c) * sc, acc[c]);
     }
-    st1(y + n * sn + h * sh + w * sw + c * sc, acc);
   }
 }
 
@@ -868,7 +868,7 @@ int mvae_im2col(const mvae_conv_geometry* q, int image_dtype, const void* image,
       im2col_vec_kernel<__nv_bfloat16><<<grid_for(items / vec), kThreads, 0, st>>>(
           static_cast<const __nv_bfloat16*>(image), static_cast<__nv_bfloat16*>(col), ldcol, g);
   } else {
-    const int blocks = grid_for(items);
+    const int blocks = grid_for(items / g.C);
 #define MVAE_I2C(TI, TO)                                                                                              \
   im2col_any_kernel<TI, TO><<<blocks, kThreads, 0, st>>>(static_cast<const TI*>(image), q->stride_n, q->stride_h,     \
                                                          q->stride_w, q->stride_c, static_cast<TO*>(col), ldcol, g)
@@ -902,7 +902,7 @@ int mvae_col2im(const mvae_conv_geometry* q, int col_dtype, const void* col, int
       col2im_vec_kernel<__nv_bfloat16><<<grid_for(items / vec), kThreads, 0, st>>>(
           static_cast<const __nv_bfloat16*>(col), ldcol, static_cast<__nv_bfloat16*>(image), g);
   } else {
-    const int blocks = grid_for(items);
+    const int blocks = grid_for(items / g.C);
 #define MVAE_C2I(TI, TO)                                                                                          \
   col2im_any_kernel<TI, TO><<<blocks, kThreads, 0, st>>>(static_cast<const TI*>(col), ldcol, static_cast<TO*>(image), \
                                                          q->stride_n, q->stride_h, q->stride_w, q->stride_c, g)

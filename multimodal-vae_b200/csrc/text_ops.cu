@@ -71,22 +71,28 @@ __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const long long* __
                                                              const float* __restrict__ table, int vocab, int width, int act,
                                                              const void* dout, int dout_dtype, long long ldd, long long rows,
                                                              float* __restrict__ dtable) {
-  extern __shared__ float s_acc[];  // [vocab, width]
-  for (int i = threadIdx.x; i < vocab * width; i += kThreads) s_acc[i] = 0.f;
+  extern __shared__ float s_acc[];  // [lanes][vocab, width]
+  const int lanes = max(1, min(kThreads / width, 4));   // row lanes per column
+  const int vw = vocab * width;
+  for (int i = threadIdx.x; i < lanes * vw; i += kThreads) s_acc[i] = 0.f;
   __syncthreads();
   const long long slab = (rows + gridDim.x - 1) / gridDim.x;
   const long long r0 = blockIdx.x * slab, r1 = min(rows, r0 + slab);
-  // thread -> column j, rows strided by (kThreads / width) lanes would need atomics; instead each thread owns columns
-  for (int j = threadIdx.x; j < width; j += kThreads) {
-    for (long long m = r0; m < r1; ++m) {
+  const int lane = threadIdx.x / width, j = threadIdx.x - lane * width;
+  if (lane < lanes) {
+    float* mine = s_acc + lane * vw;     // (lane, column) pairs own disjoint addresses: no atomics needed
+    for (long long m = r0 + lane; m < r1; m += lanes) {
       long long c = idx[m * idx_stride];
       c = c < 0 ? 0 : (c >= vocab ? vocab - 1 : c);
-      s_acc[c * width + j] += ld_any(dout, dout_dtype, m * ldd + j) * act_g(act, table[c * width + j]);
+      mine[c * width + j] += ld_any(dout, dout_dtype, m * ldd + j) * act_g(act, table[c * width + j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < vocab * width; i += kThreads)
-    if (s_acc[i] != 0.f) atomicAdd(dtable + i, s_acc[i]);
+  for (int i = threadIdx.x; i < vw; i += kThreads) {
+    float v = 0.f;
+    for (int l = 0; l < lanes; ++l) v += s_acc[l * vw + i];
+    if (v != 0.f) atomicAdd(dtable + i, v);
+  }
 }
 
 // ---------------------------------------------------------------- GRU cell (gate order r, z, n like nn.GRU)
@@ -259,9 +265,11 @@ int mvae_embed_backward(const int64_t* indices, int64_t index_stride, const floa
                         int dout_dtype, const void* dout, int64_t ld_dout, int64_t rows, float* dtable, void* stream) {
   MVAE_REQUIRE(indices != nullptr && table != nullptr && dout != nullptr && dtable != nullptr, "embed_backward: null tensor");
   MVAE_REQUIRE(rows > 0 && width > 0 && vocab > 0 && vocab <= kMaxVocab, "embed_backward: vocabulary %d outside [1, %d]", vocab, kMaxVocab);
-  const size_t smem = static_cast<size_t>(vocab) * width * sizeof(float);
+  MVAE_REQUIRE(width <= kThreads, "embed_backward: width %d > %d", width, kThreads);
+  const int lanes = std::max(1, std::min(kThreads / width, 4));
+  const size_t smem = static_cast<size_t>(lanes) * vocab * width * sizeof(float);
   MVAE_REQUIRE(smem <= 48 * 1024, "embed_backward: table too large for shared memory");
-  const int blocks = static_cast<int>(std::min<long long>((rows + 63) / 64, 296));
+  const int blocks = static_cast<int>(std::min<long long>((rows + 15) / 16, 592));
   embed_bwd_kernel<<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(indices), index_stride, table, vocab, width, act, dout, dout_dtype, ld_dout, rows, dtable);
   MVAE_CUDA(cudaGetLastError());
