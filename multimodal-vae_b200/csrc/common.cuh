@@ -63,6 +63,20 @@ struct GemmEpilogue {
   const float* bn_rstd = nullptr;  // [groups][N]
   const float* bn_gamma = nullptr; // [N]
   const float* bn_beta = nullptr;  // [N]
+  // EPI_STORE + fuse_bn: BatchNorm(+ReLU) of the layer applied by the SAME kernel.  After its column sums are published
+  // every CTA arrives at a grid-wide barrier (all CTAs are co-resident - checked on the host), then normalises its own
+  // tile straight from the on-chip staging buffer: Y = relu(a * round(C) + b), a = gamma*rstd, b = beta - mean*a.
+  // Needs stat0/stat1, bn_gamma/bn_beta, statistics groups aligned to the 128-row tiles.
+  int fuse_bn = 0;
+  void* Y = nullptr;               // [M, N] BatchNorm output, dtype and leading dimension of C
+  float* save_mean = nullptr;      // [groups][N] out
+  float* save_rstd = nullptr;
+  float* running_mean = nullptr;   // [N] in/out (may be null)
+  float* running_var = nullptr;
+  int bn_updates = 1;              // running-statistics updates each group stands for
+  float bn_momentum = 0.1f, bn_eps = 1e-5f;
+  int bn_relu = 1;
+  unsigned int* grid_barrier = nullptr;  // [2] zeroed before the launch: arrivals, time-out flag
 };
 
 // Optional transform of the A operand on its way to the tensor core: A' = relu(BatchNorm(A)) with train-mode
@@ -106,6 +120,8 @@ struct GemmDesc {
 };
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
+// true if launch_gemm can honour g.epi.fuse_bn (every CTA of the grid co-resident); nothing is launched
+bool gemm_bn_fusable(const GemmDesc& g);
 void set_gemm_debug_times(void* ptr, int epi_kind);
 
 // Tuning knobs readable from the environment (debug / bench sweeps only).

@@ -49,6 +49,8 @@ struct GemmKParams {
   int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
   int coef_off;       // byte offset (dynamic smem) of the A-transform coefficient table [2][kb_total*BK], or -1
+  int bnco_off;       // byte offset (dynamic smem) of the fused-BatchNorm coefficient table [2][block_n], or -1
+  unsigned int grid_ctas;  // CTAs of the launch (fused-BatchNorm grid barrier)
   long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
   GemmATransform atf;
   GemmEpilogue epi;
@@ -643,6 +645,115 @@ __global__ void __launch_bounds__(kGemmThreads)
     if (threadIdx.x == 64) stamp(6);
   }
 
+  if constexpr (kEpi == EPI_STORE) {
+    if (e.fuse_bn) {
+      using CT = act_t;  // fused BatchNorm writes the activation dtype (C and Y share dtype and leading dimension)
+      // ---- (3) grid-wide barrier: every CTA has published its column sums (atomics above)
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(e.grid_barrier, 1u);
+        unsigned int seen = 0;
+        long long spins = 0;
+        while (true) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(e.grid_barrier) : "memory");
+          if (seen >= p.grid_ctas) break;
+          if (++spins > (1ll << 21)) {  // ~0.2 s: a co-residency bug must not hang the GPU; flag it instead
+            e.grid_barrier[1] = 0xdeadu;
+            break;
+          }
+          __nanosleep(64);
+        }
+        __threadfence();
+      }
+      __syncthreads();
+      // ---- (4) coefficients of this CTA's columns (the tile lies inside one statistics group)
+      float* s_co = reinterpret_cast<float*>(smem + p.bnco_off);
+      const int groups = (p.M + e.rows_per_group - 1) / e.rows_per_group;
+      const int g = m0 / e.rows_per_group;
+      for (int c = threadIdx.x; c < p.block_n; c += kGemmThreads) {
+        const int n = n0 + c;
+        float a_ = 0.f, b_ = 0.f;
+        if (n < p.N) {
+          const float ga = e.bn_gamma[n], be = e.bn_beta[n];
+          const int cnt = min(p.M, (g + 1) * e.rows_per_group) - g * e.rows_per_group;
+          const float inv = 1.f / static_cast<float>(cnt);
+          const float mean = __ldcg(e.stat0 + static_cast<long long>(g) * p.stat_group_stride + n) * inv;
+          const float var = fmaxf(__ldcg(e.stat1 + static_cast<long long>(g) * p.stat_group_stride + n) * inv - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + e.bn_eps);
+          a_ = ga * rstd;
+          b_ = fmaf(-mean, a_, be);
+          if (blockIdx.y == 0) {
+            // the first row of tiles also publishes the saved / running statistics of ALL groups, in group order
+            float rm = e.running_mean != nullptr ? e.running_mean[n] : 0.f;
+            float rv = e.running_var != nullptr ? e.running_var[n] : 0.f;
+            for (int gg = 0; gg < groups; ++gg) {
+              const int cn_ = min(p.M, (gg + 1) * e.rows_per_group) - gg * e.rows_per_group;
+              const float iv = 1.f / static_cast<float>(cn_);
+              const float m2 = __ldcg(e.stat0 + static_cast<long long>(gg) * p.stat_group_stride + n) * iv;
+              const float v2 = fmaxf(__ldcg(e.stat1 + static_cast<long long>(gg) * p.stat_group_stride + n) * iv - m2 * m2, 0.f);
+              if (e.save_mean != nullptr) {
+                e.save_mean[static_cast<long long>(gg) * p.N + n] = m2;
+                e.save_rstd[static_cast<long long>(gg) * p.N + n] = rsqrtf(v2 + e.bn_eps);
+              }
+              const float unb = cn_ > 1 ? v2 * (static_cast<float>(cn_) / static_cast<float>(cn_ - 1)) : v2;
+              for (int u = 0; u < e.bn_updates; ++u) {
+                rm = (1.f - e.bn_momentum) * rm + e.bn_momentum * m2;
+                rv = (1.f - e.bn_momentum) * rv + e.bn_momentum * unb;
+              }
+            }
+            if (e.running_mean != nullptr) {
+              e.running_mean[n] = rm;
+              e.running_var[n] = rv;
+            }
+          }
+        }
+        s_co[c] = a_;
+        s_co[p.block_n + c] = b_;
+      }
+      __syncthreads();
+      // ---- (5) second row pass over the staged tile: Y = relu(a * round(acc + bias) + b)
+      {
+        const int r_begin = warp * 16;
+        const int rows_here = min(16, p.M - m0 - r_begin);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const int col = ch * 128 + lane * 4;
+          const int cn = n0 + col;
+          int nv = 0;
+          if (col < p.block_n) nv = min(4, p.N - cn);
+          if (nv <= 0 || rows_here <= 0) continue;
+          const bool fast = (nv == 4) && (p.vec_ok != 0);
+          float ca[4], cb[4], bs[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ca[i] = s_co[col + i];
+            cb[i] = s_co[p.block_n + col + i];
+            bs[i] = (e.bias != nullptr && i < nv) ? e.bias[cn + i] : 0.f;
+          }
+          uint32_t saddr = stage_addr + static_cast<uint32_t>(r_begin * ldst + col) * 4u;
+          CT* yrow = reinterpret_cast<CT*>(e.Y) + static_cast<long long>(m0 + r_begin) * e.ldc + cn;
+#pragma unroll 4
+          for (int r = 0; r < rows_here; ++r) {
+            float v[4];
+            ptx::lds128(saddr, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float x = v[i] + bs[i];
+              if constexpr (sizeof(CT) == 2) x = __bfloat162float(__float2bfloat16_rn(x));  // what C holds
+              const float y = fmaf(ca[i], x, cb[i]);
+              v[i] = e.bn_relu ? fmaxf(y, 0.f) : y;
+            }
+            store4(yrow, fast, nv, v);
+            saddr += ldst * 4;
+            yrow += e.ldc;
+          }
+        }
+      }
+    }
+  }
+
   ptx::tc_fence_before();
   __syncthreads();
   if (kEpi == EPI_BCE && threadIdx.x < 4 && p.epi.loss != nullptr && s_loss[threadIdx.x] != 0.f)
@@ -695,13 +806,21 @@ int make_tmap(CUtensorMap* out, int kind, const void* base, long long rows, long
 }
 
 template <int kKind, int kEpi>
-int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, dim3 grid, int dyn_smem,
-                cudaStream_t stream) {
+int ensure_smem(int dyn_smem) {
   static int smem_set = 0;  // per instantiation; monotone, benign race
   if (dyn_smem > smem_set) {
+    if (smem_set == 0)  // always the largest shared-memory carve-out: several CTAs per SM is the operating point
+      MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
     MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
     smem_set = dyn_smem;
   }
+  return 0;
+}
+template <int kKind, int kEpi>
+int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, dim3 grid, int dyn_smem,
+                cudaStream_t stream) {
+  if (int rc = ensure_smem<kKind, kEpi>(dyn_smem)) return rc;
   return launch_pdl(gemm_kernel<kKind, kEpi>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
 }
 
@@ -717,7 +836,13 @@ void set_gemm_debug_times(void* ptr, int epi_kind) {
   g_dbg_epi = epi_kind;
 }
 
-int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
+static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run);
+int launch_gemm(const GemmDesc& g, cudaStream_t stream) { return launch_gemm_impl(g, stream, false); }
+bool gemm_bn_fusable(const GemmDesc& g) { return launch_gemm_impl(g, nullptr, true) == 0; }
+
+// rc 3: g.epi.fuse_bn was requested but the grid cannot be made co-resident (nothing launched; the caller falls back
+// to the separate BatchNorm kernel).
+static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run) {
   const int esz = g.kind == MVAE_F32 ? 4 : 2;
   const int BK = 128 / esz;
   MVAE_REQUIRE(g.kind == MVAE_F32 || g.kind == MVAE_BF16, "gemm: bad kind %d", g.kind);
@@ -748,6 +873,24 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     MVAE_REQUIRE(g.lda == g.K && g.K % (16 / esz) == 0, "gemm: A-transform needs a dense A with K a multiple of %d", 16 / esz);
   }
   const int coef_bytes = atf_on ? 2 * kb_total * BK * 4 : 0;
+  const bool fuse = e.kind == EPI_STORE && e.fuse_bn != 0;
+  if (fuse) {
+    MVAE_REQUIRE(e.stat0 && e.stat1 && e.bn_gamma && e.bn_beta && e.Y && e.grid_barrier, "gemm: fused BatchNorm needs statistics buffers, gamma/beta, Y and a barrier counter");
+    MVAE_REQUIRE(e.c_dtype == g.kind, "gemm: fused BatchNorm writes the activation dtype");
+    MVAE_REQUIRE(!atf_on, "gemm: fused BatchNorm and the A transform are exclusive");
+    if (!(e.rows_per_group >= g.M || e.rows_per_group % kBlockM == 0)) return 3;
+  }
+  auto bnco_bytes = [&](int bn) -> int { return fuse ? 2 * bn * 4 : 0; };
+  int sm_count = 148;
+  {
+    static int cached = 0;
+    if (cached == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached <= 0) cached = 148;
+    }
+    sm_count = cached;
+  }
   static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
   auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
@@ -780,7 +923,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
     int dyn = stages * stage_bytes;
     if (dyn < staging) dyn = staging;
-    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn) + coef_bytes;
+    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn) + coef_bytes + bnco_bytes(bn);
     dyn += 1024;
     split_o = split; stages_o = stages; dyn_o = dyn; bstage_o = b_stage; btx_o = b_tx;
     if (dyn > max_dyn + 1024) return 1e30;
@@ -790,6 +933,8 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
     if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
+    // the fused-BatchNorm grid barrier needs every CTA resident at once (256 threads x ~110 registers: at most 2 per SM)
+    if (fuse && ctas > static_cast<long long>(sm_count) * (occ > 2 ? 2 : occ)) return 1e30;
     const double slots = static_cast<double>(sms) * occ;
     const double waves = static_cast<double>((ctas + static_cast<long long>(slots) - 1) / static_cast<long long>(slots));
     // operand bytes streamed from L2 by all CTAs
@@ -831,6 +976,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
       }
     }
   }
+  if (fuse && (block_n <= 0 || plan_for(block_n, split, stages, dyn, b_stage, b_tx) >= 1e29)) return 3;
   MVAE_REQUIRE(block_n >= 16 && block_n <= 256 && block_n % 16 == 0, "gemm: block_n %d invalid", block_n);
   MVAE_REQUIRE(plan_for(block_n, split, stages, dyn, b_stage, b_tx) < 1e29, "gemm: tile %d does not fit in shared memory", block_n);
   const int tiles_n = ceil_div(g.N, block_n);
@@ -870,9 +1016,12 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   if (e.kind == EPI_BCE) vec = vec && (e.ldt % 4 == 0) && al(e.target, aa);
   if (e.kind == EPI_DGRAD_BN) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
   kp.vec_ok = vec ? 1 : 0;
-  kp.aux_off = (aux_ok && vec) ? (dyn - 1024 - coef_bytes - aux_bytes(block_n) - red_bytes(block_n)) : -1;
-  kp.red_off = red_ok ? (dyn - 1024 - coef_bytes - red_bytes(block_n)) : -1;
-  kp.coef_off = atf_on ? (dyn - 1024 - coef_bytes) : -1;
+  const int tail0 = dyn - 1024 - coef_bytes - bnco_bytes(block_n) - aux_bytes(block_n) - red_bytes(block_n);
+  kp.aux_off = (aux_ok && vec) ? tail0 : -1;
+  kp.red_off = red_ok ? tail0 + aux_bytes(block_n) : -1;
+  kp.coef_off = atf_on ? tail0 + aux_bytes(block_n) + red_bytes(block_n) : -1;
+  kp.bnco_off = fuse ? tail0 + aux_bytes(block_n) + red_bytes(block_n) + coef_bytes : -1;
+  kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");
   if (e.kind == EPI_DGRAD_BN)
@@ -880,6 +1029,25 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   MVAE_REQUIRE(e.rows_per_group > 0, "gemm: rows_per_group must be positive");
 
   dim3 grid(tiles_n, tiles_m, split);
+  if (fuse) {
+    // authoritative co-residency check with the real register / shared-memory footprint of the kernel
+    int occ = 0;
+    if (g.kind == MVAE_F32) {
+      if (int rc = ensure_smem<MVAE_F32, EPI_STORE>(dyn)) return rc;
+      MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_kernel<MVAE_F32, EPI_STORE>, kGemmThreads, dyn));
+    } else {
+      if (int rc = ensure_smem<MVAE_BF16, EPI_STORE>(dyn)) return rc;
+      MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_kernel<MVAE_BF16, EPI_STORE>, kGemmThreads, dyn));
+    }
+    int tmem_cols = 32;
+    while (tmem_cols < block_n) tmem_cols <<= 1;
+    if (env_int("MVAE_GEMM_VERBOSE", 0))
+      fprintf(stderr, "[mvae gemm] fused BatchNorm: occupancy %d (tmem limit %d), %u CTAs, %d SMs\n", occ, 512 / tmem_cols,
+              kp.grid_ctas, sm_count);
+    if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
+    if (static_cast<long long>(kp.grid_ctas) > static_cast<long long>(occ) * sm_count) return 3;
+  }
+  if (dry_run) return 0;
 #define MVAE_GEMM_CASE(KIND, EPI)                                   \
   if (g.kind == KIND && e.kind == EPI) return launch_inst<KIND, EPI>(ta, tb, kp, grid, dyn, stream);
   MVAE_GEMM_CASE(MVAE_F32, EPI_STORE)

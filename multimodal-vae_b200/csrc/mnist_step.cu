@@ -125,6 +125,7 @@ struct Plan {
   long long st_e1, st_e2, st_d1, st_d2, st_t1;          // forward BN sums: [2][groups][F]
   long long sb_e1, sb_e2, sb_d1, sb_d2, sb_t1;          // backward BN sums
   long long losses;                                      // [3][kMaxGroups]: bce, ce, kl
+  long long bars;                                        // grid-barrier counters of the fused-BatchNorm GEMMs [8][2] (uint)
   long long d_txt_table;                                 // [10][2n]
   // saved statistics
   long long sv_e1, sv_e2, sv_d1, sv_d2;                  // [2][groups][F]: mean, rstd
@@ -156,6 +157,7 @@ Plan make_plan(int B, int n, int dtype) {
   p.sb_e1 = acc(2 * 400); p.sb_e2 = acc(2 * 200);
   p.sb_d1 = acc(2 * G * 200); p.sb_d2 = acc(2 * G * 400); p.sb_t1 = acc(2 * G * 10);
   p.losses = acc(3 * G);
+  p.bars = acc(16);
   p.d_txt_table = acc(10 * 2 * n);
   p.acc_floats = f;
   off += f * 4;
@@ -188,6 +190,39 @@ struct Ptrs {
     return reinterpret_cast<T*>(ws + off);
   }
 };
+
+// BatchNorm(+ReLU) applied by the producing GEMM itself (gemm.cu, fuse_bn): what launch_bn_forward would be given.
+struct FusedBn {
+  void* Y = nullptr;
+  const float* gamma = nullptr; const float* beta = nullptr;
+  float* save_mean = nullptr; float* save_rstd = nullptr;
+  float* running_mean = nullptr; float* running_var = nullptr;
+  int updates = 1; float momentum = 0.1f, eps = 1e-5f;
+  unsigned int* barrier = nullptr;
+};
+
+GemmDesc fwd_desc(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
+                  float* st_sum, float* st_sumsq, int rows_per_group, const FusedBn* fb) {
+  GemmDesc g;
+  g.kind = dtype; g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = K; g.a_mn = 0;
+  g.B = W; g.ldb = K; g.b_mn = 0;
+  g.epi.kind = EPI_STORE;
+  g.epi.C = C; g.epi.ldc = N; g.epi.c_dtype = c_dtype;
+  g.epi.bias = bias;
+  g.epi.stat0 = st_sum; g.epi.stat1 = st_sumsq;
+  g.epi.rows_per_group = rows_per_group;
+  if (fb != nullptr) {
+    g.epi.fuse_bn = 1;
+    g.epi.Y = fb->Y;
+    g.epi.bn_gamma = fb->gamma; g.epi.bn_beta = fb->beta;
+    g.epi.save_mean = fb->save_mean; g.epi.save_rstd = fb->save_rstd;
+    g.epi.running_mean = fb->running_mean; g.epi.running_var = fb->running_var;
+    g.epi.bn_updates = fb->updates; g.epi.bn_momentum = fb->momentum; g.epi.bn_eps = fb->eps; g.epi.bn_relu = 1;
+    g.epi.grid_barrier = fb->barrier;
+  }
+  return g;
+}
 
 int gemm_fwd(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
              float* st_sum, float* st_sumsq, int rows_per_group, cudaStream_t st, const GemmATransform* atf = nullptr) {
@@ -434,6 +469,9 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   // when the statistics groups are tile-aligned; the separate apply kernel remains for ragged batches and eval.
   static const int fuse_env = env_int("MVAE_FUSE_BN", 0);  // measured slower: every N tile redoes the transform
   const bool fuse_enc = fuse_env != 0 && training;
+  static const int epi_fuse_env = env_int("MVAE_FUSE_BN_EPI", 0);  // producer-side fusion (grid barrier in the GEMM epilogue): measured +-0
+  const bool epi_fuse = epi_fuse_env != 0 && training && !fuse_enc;
+  unsigned int* bars = W.at<unsigned int>(P.bars);
   const bool fuse_dec = fuse_enc && (G == 1 || B % 128 == 0);
   auto make_atf = [&](float* sums, int F, int groups, int rpg, int nupd, const char* bn, float* sv, void* out) {
     GemmATransform t;
@@ -451,18 +489,38 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   };
   if (n_img > 0) {
     // ImageEncoder (mnist/model.py:99-117), once for all terms that use it
-    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
+    // BatchNorm+ReLU applied by the producing GEMM (grid barrier + second pass over the on-chip tile) when the whole
+    // grid is co-resident; otherwise the GEMM publishes the sums and launch_bn_forward applies them.
+    FusedBn fb_e1;
+    fb_e1.Y = W.at<void>(P.h1); fb_e1.gamma = pf("image_encoder.net.1.weight"); fb_e1.beta = pf("image_encoder.net.1.bias");
+    fb_e1.save_mean = sv_e1; fb_e1.save_rstd = sv_e1 + 400;
+    fb_e1.running_mean = bf("image_encoder.net.1.running_mean"); fb_e1.running_var = bf("image_encoder.net.1.running_var");
+    fb_e1.updates = n_img; fb_e1.momentum = mom; fb_e1.eps = bn_eps; fb_e1.barrier = bars + 0;
+    const GemmDesc gd_e1 = fwd_desc(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
+                                    pf("image_encoder.net.0.bias"), st_e1, st_e1 + 400, 1 << 30, &fb_e1);
+    const bool fz_e1 = epi_fuse && gemm_bn_fusable(gd_e1);
+    if (fwd && fz_e1) MVAE_STEP(launch_gemm(gd_e1, st), "gemm_fwd_bn:image_encoder.net.0.weight#3");
+    if (fwd && !fz_e1) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
                  pf("image_encoder.net.0.bias"), training ? st_e1 : nullptr, training ? st_e1 + 400 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.0.weight#3");
     const GemmATransform atf_e1 = make_atf(st_e1, 400, 1, 1 << 30, n_img, "image_encoder.net.1", sv_e1, W.at<void>(P.h1));
-    if (fwd && !fuse_enc) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
+    if (fwd && !fuse_enc && !fz_e1) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
                           pf("image_encoder.net.1.weight"), pf("image_encoder.net.1.bias"), sv_e1, sv_e1 + 400,
                           bf("image_encoder.net.1.running_mean"), bf("image_encoder.net.1.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.1.weight#4");
-    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 200, 400, fuse_enc ? W.at<void>(P.h1pre) : W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
+    FusedBn fb_e2;
+    fb_e2.Y = W.at<void>(P.h2); fb_e2.gamma = pf("image_encoder.net.4.weight"); fb_e2.beta = pf("image_encoder.net.4.bias");
+    fb_e2.save_mean = sv_e2; fb_e2.save_rstd = sv_e2 + 200;
+    fb_e2.running_mean = bf("image_encoder.net.4.running_mean"); fb_e2.running_var = bf("image_encoder.net.4.running_var");
+    fb_e2.updates = n_img; fb_e2.momentum = mom; fb_e2.eps = bn_eps; fb_e2.barrier = bars + 2;
+    const GemmDesc gd_e2 = fwd_desc(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
+                                    pf("image_encoder.net.3.bias"), st_e2, st_e2 + 200, 1 << 30, &fb_e2);
+    const bool fz_e2 = epi_fuse && gemm_bn_fusable(gd_e2);
+    if (fwd && fz_e2) MVAE_STEP(launch_gemm(gd_e2, st), "gemm_fwd_bn:image_encoder.net.3.weight#5");
+    if (fwd && !fz_e2) MVAE_STEP(gemm_fwd(dt, B, 200, 400, fuse_enc ? W.at<void>(P.h1pre) : W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
                  pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st,
                  fuse_enc ? &atf_e1 : nullptr), "gemm_fwd:image_encoder.net.3.weight#5");
     const GemmATransform atf_e2 = make_atf(st_e2, 200, 1, 1 << 30, n_img, "image_encoder.net.4", sv_e2, W.at<void>(P.h2));
-    if (fwd && !fuse_enc) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
+    if (fwd && !fuse_enc && !fz_e2) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
                           pf("image_encoder.net.4.weight"), pf("image_encoder.net.4.bias"), sv_e2, sv_e2 + 200,
                           bf("image_encoder.net.4.running_mean"), bf("image_encoder.net.4.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.4.weight#6");
@@ -507,18 +565,36 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (fwd) MVAE_STEP(launch_textdec(td, s2), "launch_textdec");
 
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
-  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
+  FusedBn fb_d1;
+  fb_d1.Y = W.at<void>(P.g1); fb_d1.gamma = pf("image_decoder.net.1.weight"); fb_d1.beta = pf("image_decoder.net.1.bias");
+  fb_d1.save_mean = sv_d1; fb_d1.save_rstd = sv_d1 + G * 200;
+  fb_d1.running_mean = bf("image_decoder.net.1.running_mean"); fb_d1.running_var = bf("image_decoder.net.1.running_var");
+  fb_d1.updates = 1; fb_d1.momentum = mom; fb_d1.eps = bn_eps; fb_d1.barrier = bars + 4;
+  const GemmDesc gd_d1 = fwd_desc(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
+                                  pf("image_decoder.net.0.bias"), st_d1, st_d1 + G * 200, B, &fb_d1);
+  const bool fz_d1 = epi_fuse && gemm_bn_fusable(gd_d1);
+  if (fwd && fz_d1) MVAE_STEP(launch_gemm(gd_d1, st), "gemm_fwd_bn:image_decoder.net.0.weight#9");
+  if (fwd && !fz_d1) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
                pf("image_decoder.net.0.bias"), training ? st_d1 : nullptr, training ? st_d1 + G * 200 : nullptr, B, st), "gemm_fwd:image_decoder.net.0.weight#9");
   const GemmATransform atf_d1 = make_atf(st_d1, 200, G, B, 1, "image_decoder.net.1", sv_d1, W.at<void>(P.g1));
-  if (fwd && !fuse_dec) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
+  if (fwd && !fuse_dec && !fz_d1) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
                         pf("image_decoder.net.1.weight"), pf("image_decoder.net.1.bias"), sv_d1, sv_d1 + G * 200,
                         bf("image_decoder.net.1.running_mean"), bf("image_decoder.net.1.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.1.weight#10");
-  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 400, 200, fuse_dec ? W.at<void>(P.g1pre) : W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
+  FusedBn fb_d2;
+  fb_d2.Y = W.at<void>(P.g2); fb_d2.gamma = pf("image_decoder.net.4.weight"); fb_d2.beta = pf("image_decoder.net.4.bias");
+  fb_d2.save_mean = sv_d2; fb_d2.save_rstd = sv_d2 + G * 400;
+  fb_d2.running_mean = bf("image_decoder.net.4.running_mean"); fb_d2.running_var = bf("image_decoder.net.4.running_var");
+  fb_d2.updates = 1; fb_d2.momentum = mom; fb_d2.eps = bn_eps; fb_d2.barrier = bars + 6;
+  const GemmDesc gd_d2 = fwd_desc(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
+                                  pf("image_decoder.net.3.bias"), st_d2, st_d2 + G * 400, B, &fb_d2);
+  const bool fz_d2 = epi_fuse && gemm_bn_fusable(gd_d2);
+  if (fwd && fz_d2) MVAE_STEP(launch_gemm(gd_d2, st), "gemm_fwd_bn:image_decoder.net.3.weight#11");
+  if (fwd && !fz_d2) MVAE_STEP(gemm_fwd(dt, R, 400, 200, fuse_dec ? W.at<void>(P.g1pre) : W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
                pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st,
                fuse_dec ? &atf_d1 : nullptr), "gemm_fwd:image_decoder.net.3.weight#11");
   const GemmATransform atf_d2 = make_atf(st_d2, 400, G, B, 1, "image_decoder.net.4", sv_d2, W.at<void>(P.g2));
-  if (fwd && !fuse_dec) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
+  if (fwd && !fuse_dec && !fz_d2) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
@@ -642,7 +718,7 @@ long long mvae_launch_count(void) { return g_launches + mvae::noted_launches(); 
 long long mvae_mnist_workspace_offset(const char* name, int batch, int n_latents, int dtype) {
   const Plan p = make_plan(batch, n_latents, dtype);
 #define MVAE_OFF(f) if (strcmp(name, #f) == 0) return p.f;
-  MVAE_OFF(st_e1) MVAE_OFF(st_e2) MVAE_OFF(st_d1) MVAE_OFF(st_d2) MVAE_OFF(st_t1)
+  MVAE_OFF(bars) MVAE_OFF(st_e1) MVAE_OFF(st_e2) MVAE_OFF(st_d1) MVAE_OFF(st_d2) MVAE_OFF(st_t1)
   MVAE_OFF(sb_e1) MVAE_OFF(sb_e2) MVAE_OFF(sb_d1) MVAE_OFF(sb_d2) MVAE_OFF(sb_t1)
   MVAE_OFF(losses) MVAE_OFF(d_txt_table) MVAE_OFF(sv_e1) MVAE_OFF(sv_e2) MVAE_OFF(sv_d1) MVAE_OFF(sv_d2)
   MVAE_OFF(txt_table) MVAE_OFF(h1pre) MVAE_OFF(h1) MVAE_OFF(h2pre) MVAE_OFF(h2) MVAE_OFF(enc) MVAE_OFF(z)
