@@ -392,10 +392,9 @@ def main():
     args = ap.parse_args()
     args.batch_set = any(a == "--batch" or a.startswith("--batch=") for a in sys.argv[1:])
     if args.workload != "mnist":
-        if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is timed on the headline MNIST config only"}))
-            return 0
         import bench_conv
+        if args.impl == "reference":
+            return bench_conv.run_reference(args)
         return bench_conv.run(args, log, ClockSampler, load_peaks)
     if args.impl == "reference":
         return run_reference(args)

@@ -34,6 +34,51 @@ def algorithmic_flops(model, n_terms=3, n_img_terms=2) -> float:
     return f
 
 
+def run_reference(args):
+    """CPU arm for the conv workloads: the oracle port (oracle/{celeba,multimnist}_oracle.py, pinned to the reference's
+    fixtures) on all host cores, a bounded sample of steps of the same batch size, Adam included."""
+    import time
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mnist_oracle as MN
+    O = __import__("celeba_oracle" if args.workload == "celeba" else "multimnist_oracle")
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, n = (args.batch if args.batch_set else 256), 100
+    state = O.init_state(n, seed=1234)
+    image, other, noises = O.synthetic_batch(B, n, 0)
+    mom = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    steps, warmup = min(args.steps, 10), min(args.warmup, 2)
+    p, step_no = state, 0
+
+    def one():
+        nonlocal p, step_no
+        step_no += 1
+        _, grads, bufs, _ = O.train_step(p, image, other, [torch.randn_like(x) for x in noises])
+        p = MN.adam_step(p, grads, mom, vel, step_no)
+        p.update(bufs)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    value = B * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "MVAE train samples/sec (fwd+bwd ELBO)", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s MVAE n_latents=100 batch=%d 3-term ELBO step (fwd+bwd+Adam), CPU oracle port (Dropout off)" % (args.workload, B)},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "%d steps of batch %d after %d warm-up" % (steps, B, warmup)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
+
+
 def run(args, log, ClockSampler, load_peaks):
     import torch
     import torch.distributed as dist

@@ -329,3 +329,39 @@ def test_graph_replay_and_adam_decrease_loss_bf16():
     assert hist[-1] < hist[0] - 0.05, hist
     assert int(m.state_dict()["image_decoder.hallucinate.1.num_batches_tracked"]) == 180
     assert int(m.state_dict()["image_encoder.features.3.num_batches_tracked"]) == 120
+
+
+def test_bf16_training_curve_tracks_fp32_oracle():
+    """north_star: the bf16 path's ELBO curve stays within 1% of the fp32 reference run on the same data, weights and
+    noise.  150 Adam steps (celeba/train.py:132-157 semantics) on one fixed batch; device bf16 vs CPU oracle fp32."""
+    import celeba_oracle as O
+    import mnist_oracle as MN
+    from mvae_b200.celeba import MultimodalVAE, CelebATrainer
+    n, B, steps = 16, 16, 150
+    state = O.init_state(n, seed=99)
+    image, attrs, _ = O.synthetic_batch(B, n, 5)
+    g = torch.Generator().manual_seed(123)
+    noise = [torch.randn(3, B, n, generator=g) for _ in range(steps)]
+    m = MultimodalVAE(n_latents=n, precision="bf16", dropout_p=0.0)
+    m.load_state_dict(state)
+    tr = CelebATrainer(m, lr=1e-3)
+    dev_curve = []
+    img_d, att_d = image.cuda(), attrs.cuda()
+    for it in range(steps):
+        tr.step(img_d, att_d, eps=noise[it].cuda())
+        if it % 10 == 9:
+            dev_curve.append(sum(l[0] for l in tr.losses()))
+    p = {k: v.clone() for k, v in state.items()}
+    mom = {k: torch.zeros_like(v) for k, v in p.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in p.items() if not O.is_buffer(k)}
+    ref_curve = []
+    for it in range(steps):
+        losses, grads, bufs, _ = O.train_step(p, image, attrs, list(noise[it]))
+        p = MN.adam_step(p, grads, mom, vel, it + 1)
+        p.update(bufs)
+        if it % 10 == 9:
+            ref_curve.append(sum(losses))
+    dev_curve, ref_curve = np.array(dev_curve), np.array(ref_curve)
+    assert ref_curve[-1] < ref_curve[0] - 0.05, ref_curve          # it does train
+    rel_err = np.abs(dev_curve - ref_curve) / np.abs(ref_curve)
+    assert rel_err.max() < 0.01, (rel_err, dev_curve, ref_curve)

@@ -232,3 +232,75 @@ def test_graph_replay_and_adam_decrease_loss_bf16():
     assert all(np.isfinite(hist)), hist
     assert hist[-1] < hist[0] - 0.3, hist
     assert int(m.state_dict()["image_decoder.hallucinate.1.num_batches_tracked"]) == 180
+
+
+def test_tf32_training_curve_tracks_fp32_oracle():
+    """60 Adam steps (multimnist/train.py:148-175 semantics) on one fixed batch: device tf32 vs CPU oracle fp32, ELBO within
+    1% at every checkpoint (the greedy text decode makes later steps sensitive to near-tie logits, hence tf32 and 60 steps)."""
+    import multimnist_oracle as O
+    import mnist_oracle as MN
+    from mvae_b200.multimnist import MultimodalVAE, MultiMNISTTrainer
+    n, B, steps = 16, 16, 60
+    state = O.init_state(n, seed=98)
+    image, text, _ = O.synthetic_batch(B, n, 6)
+    g = torch.Generator().manual_seed(321)
+    noise = [torch.randn(3, B, n, generator=g) for _ in range(steps)]
+    m = MultimodalVAE(n_latents=n, precision="tf32", dropout_p=0.0)
+    m.load_state_dict(state)
+    tr = MultiMNISTTrainer(m, lr=1e-3)
+    dev_curve = []
+    img_d, txt_d = image.cuda(), text.cuda()
+    for it in range(steps):
+        tr.step(img_d, txt_d, eps=noise[it].cuda())
+        if it % 10 == 9:
+            dev_curve.append(sum(l[0] for l in tr.losses()))
+    p = {k: v.clone() for k, v in state.items()}
+    mom = {k: torch.zeros_like(v) for k, v in p.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in p.items() if not O.is_buffer(k)}
+    ref_curve = []
+    for it in range(steps):
+        losses, grads, bufs, _ = O.train_step(p, image, text, list(noise[it]))
+        p = MN.adam_step(p, grads, mom, vel, it + 1)
+        p.update(bufs)
+        if it % 10 == 9:
+            ref_curve.append(sum(losses))
+    dev_curve, ref_curve = np.array(dev_curve), np.array(ref_curve)
+    assert ref_curve[-1] < ref_curve[0] - 0.3, ref_curve
+    rel_err = np.abs(dev_curve - ref_curve) / np.abs(ref_curve)
+    assert rel_err.max() < 0.01, (rel_err, dev_curve, ref_curve)
+
+
+def test_weak_supervision_term_subsets():
+    """Steps with a subset of the ELBO terms (image-only / text-only batches): losses and gradients against the oracle's
+    single-term forward + loss, and encoders that took no part get exactly zero gradients."""
+    import multimnist_oracle as O
+    from mvae_b200.multimnist import MultimodalVAE, MultiMNISTTrainer
+    n, B = 16, 8
+    state = O.init_state(n, seed=55)
+    image, text, noises = O.synthetic_batch(B, n, 7)
+    for terms, lam in ((("text",), ((0.0, 1.0),)), (("joint", "image"), ((1.0, 1.0), (1.0, 0.5)))):
+        m = MultimodalVAE(n_latents=n, precision="tf32", dropout_p=0.0)
+        m.load_state_dict(state)
+        tr = MultiMNISTTrainer(m)
+        eps = torch.stack([noises[("joint", "image", "text").index(t)] for t in terms])
+        tr.step(image.cuda(), text.cuda(), terms=terms, lambdas=lam, eps=eps.cuda(), adam=False)
+        torch.cuda.synchronize()
+        work = {k: (v.clone() if O.is_buffer(k) else v.clone().requires_grad_(True)) for k, v in state.items()}
+        total, ref_losses = 0, []
+        for t, l, e in zip(terms, lam, eps):
+            args = dict(joint=(image, text), image=(image, None), text=(None, text))[t]
+            ri, rt, mu, lv, _ = O.forward(work, args[0], args[1], e, work, True)
+            ls = O.loss_function(mu, lv, ri, image, rt, text, O.KL_LAMBDA, l[0], l[1])
+            ref_losses.append(float(ls.detach()))
+            total = total + ls
+        names = [k for k in work if not O.is_buffer(k)]
+        gs = torch.autograd.grad(total, [work[k] for k in names], allow_unused=True)
+        dev = tr.losses()
+        for a, b in zip(dev, ref_losses):
+            assert abs(a[0] - b) <= 2e-3 * abs(b), (terms, dev, ref_losses)
+        dg = m.grads_reference()
+        for k, gr in zip(names, gs):
+            if gr is None or float(gr.abs().max()) < 1e-7:
+                assert float(dg[k].abs().max()) < 1e-5, (terms, k)
+            else:
+                assert rel(dg[k], gr) < 6e-3, (terms, k, rel(dg[k], gr))
