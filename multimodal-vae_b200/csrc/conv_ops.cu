@@ -112,25 +112,28 @@ struct Geom {
 template <typename T>
 __global__ void __launch_bounds__(kThreads) im2col_vec_kernel(const T* __restrict__ x, T* __restrict__ col,
                                                               long long ldcol, Geom g) {
+  // blockIdx.y strides over output rows (n, ho); inside a row the thread index is (wo, tap, channel vector): a row of
+  // taps (kh fixed) is one contiguous run of k*C input elements and k*C col elements - a strided memcpy
   constexpr int N = V16<T>::N;
   const int CV = g.C / N, kk = g.k * g.k;
-  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * kk * CV;
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int cv = static_cast<int>(i % CV);
-    long long r = i / CV;
-    const int tap = static_cast<int>(r % kk);
-    const long long m = r / kk;
-    const int wo = static_cast<int>(m % g.Wo);
-    const long long t = m / g.Wo;
-    const int ho = static_cast<int>(t % g.Ho);
-    const long long n = t / g.Ho;
-    const int kh = tap / g.k, kw = tap - kh * g.k;
-    const int hi = ho * g.stride - g.pad + kh, wi = wo * g.stride - g.pad + kw;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W)
-      v = *reinterpret_cast<const uint4*>(x + ((n * g.H + hi) * g.W + wi) * g.C + cv * N);
-    *reinterpret_cast<uint4*>(col + m * ldcol + static_cast<long long>(tap) * g.C + cv * N) = v;
+  const int per_row = g.Wo * kk * CV;
+  const long long n_rows = static_cast<long long>(g.B) * g.Ho;
+  for (long long row = blockIdx.y; row < n_rows; row += gridDim.y) {
+    const int ho = static_cast<int>(row % g.Ho);
+    const long long n = row / g.Ho;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+      const int cv = i % CV;
+      const int r = i / CV;
+      const int tap = r % kk;
+      const int wo = r / kk;
+      const int kh = tap / g.k, kw = tap - kh * g.k;
+      const int hi = ho * g.stride - g.pad + kh, wi = wo * g.stride - g.pad + kw;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (hi >= 0 && hi < g.H && wi >= 0 && wi < g.W)
+        v = *reinterpret_cast<const uint4*>(x + ((n * g.H + hi) * g.W + wi) * g.C + cv * N);
+      const long long m = row * g.Wo + wo;
+      *reinterpret_cast<uint4*>(col + m * ldcol + static_cast<long long>(tap) * g.C + cv * N) = v;
+    }
   }
 }
 // y[n, h, w, c] = sum over taps with h = ho*stride - pad + kh (same for w) of col[(n,ho,wo), tap*C + c]
@@ -139,62 +142,91 @@ __global__ void __launch_bounds__(kThreads) col2im_vec_kernel(const T* __restric
                                                               T* __restrict__ y, Geom g) {
   constexpr int N = V16<T>::N;
   const int CV = g.C / N;
-  const long long total = static_cast<long long>(g.B) * g.H * g.W * CV;
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int cv = static_cast<int>(i % CV);
-    long long r = i / CV;
-    const int w = static_cast<int>(r % g.W);
-    r /= g.W;
-    const int h = static_cast<int>(r % g.H);
-    const long long n = r / g.H;
-    float acc[N];
+  const int per_row = g.W * CV;
+  const long long n_rows = static_cast<long long>(g.B) * g.H;
+  for (long long row = blockIdx.y; row < n_rows; row += gridDim.y) {
+    const int h = static_cast<int>(row % g.H);
+    const long long n = row / g.H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+      const int cv = i % CV;
+      const int w = i / CV;
+      float acc[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) acc[j] = 0.f;
-    // only taps with (h + pad - kh) divisible by the stride contribute: kh = (h + pad) % stride, + stride, ...
-    for (int kh = (h + g.pad) % g.stride; kh < g.k; kh += g.stride) {
-      const int th = h + g.pad - kh;
-      if (th < 0) break;
-      const int ho = th / g.stride;
-      if (ho >= g.Ho) continue;
-      for (int kw = (w + g.pad) % g.stride; kw < g.k; kw += g.stride) {
-        const int tw = w + g.pad - kw;
-        if (tw < 0) break;
-        const int wo = tw / g.stride;
-        if (wo >= g.Wo) continue;
-        float v[N];
-        ldv(col + ((n * g.Ho + ho) * g.Wo + wo) * ldcol + static_cast<long long>(kh * g.k + kw) * g.C + cv * N, v);
+      for (int j = 0; j < N; ++j) acc[j] = 0.f;
+      // only taps with (h + pad - kh) divisible by the stride contribute: kh = (h + pad) % stride, + stride, ...
+      for (int kh = (h + g.pad) % g.stride; kh < g.k; kh += g.stride) {
+        const int th = h + g.pad - kh;
+        if (th < 0) break;
+        const int ho = th / g.stride;
+        if (ho >= g.Ho) continue;
+        for (int kw = (w + g.pad) % g.stride; kw < g.k; kw += g.stride) {
+          const int tw = w + g.pad - kw;
+          if (tw < 0) break;
+          const int wo = tw / g.stride;
+          if (wo >= g.Wo) continue;
+          float v[N];
+          ldv(col + ((n * g.Ho + ho) * g.Wo + wo) * ldcol + static_cast<long long>(kh * g.k + kw) * g.C + cv * N, v);
 #pragma unroll
-        for (int j = 0; j < N; ++j) acc[j] += v[j];
+          for (int j = 0; j < N; ++j) acc[j] += v[j];
+        }
       }
+      stv(y + (row * g.W + w) * g.C + cv * N, acc);
     }
-    stv(y + i * N, acc);
   }
 }
 
 // ================================================================= scalar strided variants (NCHW user tensors, C = 3)
-template <typename TI, typename TO>
+template <typename TI, typename TO, int kK = 0, int kC = 0>   // kK, kC > 0: compile-time kernel size / channel count
 __global__ void __launch_bounds__(kThreads) im2col_any_kernel(const TI* __restrict__ x, long long sn, long long sh,
                                                               long long sw, long long sc, TO* __restrict__ col,
                                                               long long ldcol, Geom g) {
-  // one thread per (m, tap), all channels: neighbouring threads read neighbouring pixels of one channel plane
-  // (NCHW sources) and write neighbouring C-element groups of one col row
-  const int kk = g.k * g.k;
-  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * kk;
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
-    const int tap = static_cast<int>(i % kk);
-    const long long m = i / kk;
+  // one thread per (m, kh): the k taps of that kernel row x all channels are k*C consecutive col entries.  Neighbouring
+  // threads read neighbouring pixels of one channel plane (NCHW sources); the run is written with 8-byte packs when aligned.
+  constexpr int kMaxRun = kK > 0 ? kK * kC : 1;
+  const int K = kK > 0 ? kK : g.k, Cn = kC > 0 ? kC : g.C;
+  const int run = K * Cn;
+  const long long total = static_cast<long long>(g.B) * g.Ho * g.Wo * K;
+  const bool packed = kK > 0 && sizeof(TO) == 2 && run % 4 == 0 && ldcol % 4 == 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kh = static_cast<int>(i % K);
+    const long long m = i / K;
     const int wo = static_cast<int>(m % g.Wo);
     const long long t = m / g.Wo;
     const int ho = static_cast<int>(t % g.Ho);
     const long long n = t / g.Ho;
-    const int kh = tap / g.k, kw = tap - kh * g.k;
-    const int hi = ho * g.stride - g.pad + kh, wi = wo * g.stride - g.pad + kw;
-    const bool inside = hi >= 0 && hi < g.H && wi >= 0 && wi < g.W;
-    const TI* src = x + n * sn + hi * sh + wi * sw;
-    TO* dst = col + m * ldcol + static_cast<long long>(tap) * g.C;
-    for (int c = 0; c < g.C; ++c) st1(dst + c, inside ? ld1(src + c * sc) : 0.f);
+    const int hi = ho * g.stride - g.pad + kh;
+    const int wi0 = wo * g.stride - g.pad;
+    const bool row_in = hi >= 0 && hi < g.H;
+    const TI* src = x + n * sn + hi * sh;
+    TO* dst = col + m * ldcol + static_cast<long long>(kh) * run;
+    if (packed) {
+      float vals[kMaxRun];
+#pragma unroll
+      for (int kw = 0; kw < (kK > 0 ? kK : 1); ++kw) {
+        const int wi = wi0 + kw;
+        const bool in = row_in && wi >= 0 && wi < g.W;
+#pragma unroll
+        for (int c = 0; c < (kC > 0 ? kC : 1); ++c) vals[kw * (kC > 0 ? kC : 1) + c] = in ? ld1(src + wi * sw + c * sc) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j + 3 < kMaxRun; j += 4) {
+        {
+          const __nv_bfloat162 a = __floats2bfloat162_rn(vals[j], vals[j + 1]);
+          const __nv_bfloat162 b = __floats2bfloat162_rn(vals[j + 2], vals[j + 3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&a);
+          pk.y = *reinterpret_cast<const uint32_t*>(&b);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + j) = pk;
+        }
+      }
+    } else {
+      for (int kw = 0; kw < K; ++kw) {
+        const int wi = wi0 + kw;
+        const bool in = row_in && wi >= 0 && wi < g.W;
+        for (int c = 0; c < Cn; ++c) st1(dst + kw * Cn + c, in ? ld1(src + wi * sw + c * sc) : 0.f);
+      }
+    }
   }
 }
 // one thread per output pixel, all channels (w fastest): a warp walks 32 neighbouring pixels, whose taps sit in a
@@ -621,6 +653,59 @@ __device__ __forceinline__ float ld_any(const void* p, int dtype, long long i) {
 __device__ __forceinline__ void st_any(void* p, int dtype, long long i, float v) {
   if (dtype == MVAE_F32) static_cast<float*>(p)[i] = v; else static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
 }
+// fp32, 4 elements per thread, the training configuration of the image decoders: logits, targets and gradients fp32 and
+// vector-aligned, loss + dlogits (+ probs).  Same arithmetic as the generic kernel below.
+__global__ void __launch_bounds__(kThreads) sigmoid_bce_f32x4_kernel(const BceArgs a) {
+  __shared__ float s_loss[kMaxGroups];
+  if (threadIdx.x < kMaxGroups) s_loss[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int c4 = a.cols / 4;
+  const long long total = a.rows * c4;
+  const float* logits = static_cast<const float*>(a.logits);
+  const float* target = static_cast<const float*>(a.target);
+  float* dl = static_cast<float*>(a.dlogits);
+  float* pr = static_cast<float*>(a.probs);
+  float acc[kMaxGroups] = {0.f, 0.f, 0.f};
+  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreads) {
+    const int c = static_cast<int>(i % c4) * 4;
+    const long long m = i / c4;
+    const int g = static_cast<int>(m / a.rows_per_group);
+    const float4 x4 = *reinterpret_cast<const float4*>(logits + m * a.ldl + c);
+    const float4 t4 = __ldg(reinterpret_cast<const float4*>(target + (m % a.target_rows) * a.ldt + c));
+    const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, ts[4] = {t4.x, t4.y, t4.z, t4.w};
+    float ps[4], ds[4], l = 0.f;
+    const float sc = a.scale[g];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = xs[k], t = ts[k];
+      const float e = __expf(-fabsf(x));
+      const float r = __fdividef(1.f, 1.f + e);
+      const float p = x >= 0.f ? r : e * r;
+      const float sp = __logf(1.f + e);
+      const float log_p = fmaxf(-(fmaxf(-x, 0.f) + sp), -100.f);
+      const float log_q = fmaxf(-(fmaxf(x, 0.f) + sp), -100.f);
+      l -= t * log_p + (1.f - t) * log_q;
+      ps[k] = p;
+      ds[k] = sc * (p - t);
+    }
+    if (g == 0) acc[0] += l; else if (g == 1) acc[1] += l; else acc[2] += l;
+    if (pr != nullptr) *reinterpret_cast<float4*>(pr + m * a.ldp + c) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+    if (dl != nullptr) *reinterpret_cast<float4*>(dl + m * a.ldd + c) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+  }
+  if (a.loss != nullptr) {
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      float v = acc[g];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && v != 0.f) atomicAdd(&s_loss[g], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxGroups && s_loss[threadIdx.x] != 0.f) atomicAdd(a.loss + threadIdx.x, s_loss[threadIdx.x]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) sigmoid_bce_kernel(const BceArgs a) {
   __shared__ float s_loss[kMaxGroups];
   if (threadIdx.x < kMaxGroups) s_loss[threadIdx.x] = 0.f;
@@ -861,18 +946,27 @@ int mvae_im2col(const mvae_conv_geometry* q, int image_dtype, const void* image,
   const long long items = static_cast<long long>(g.B) * g.Ho * g.Wo * K;
   if (image_dtype == col_dtype && dense_nhwc(q) && g.C % vec == 0 && ldcol % vec == 0 &&
       reinterpret_cast<uintptr_t>(image) % 16 == 0 && reinterpret_cast<uintptr_t>(col) % 16 == 0) {
+    const int per_row = g.Wo * g.k * g.k * (g.C / vec);
+    const int threads = std::max(64, std::min(kThreads, (per_row + 31) / 32 * 32));
+    const dim3 grid(std::max(1, std::min((per_row + threads - 1) / threads, 8)),
+                    static_cast<unsigned>(std::min<long long>(static_cast<long long>(g.B) * g.Ho, 16 * sm_count_())));
     if (col_dtype == MVAE_F32)
-      im2col_vec_kernel<float><<<grid_for(items / vec), kThreads, 0, st>>>(static_cast<const float*>(image),
-                                                                            static_cast<float*>(col), ldcol, g);
+      im2col_vec_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(image), static_cast<float*>(col), ldcol, g);
     else
-      im2col_vec_kernel<__nv_bfloat16><<<grid_for(items / vec), kThreads, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(image), static_cast<__nv_bfloat16*>(col), ldcol, g);
+      im2col_vec_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(image),
+                                                                   static_cast<__nv_bfloat16*>(col), ldcol, g);
   } else {
-    const int blocks = grid_for(items / g.C);
+    const int blocks = grid_for(items / (static_cast<long long>(g.C) * g.k));
 #define MVAE_I2C(TI, TO)                                                                                              \
   im2col_any_kernel<TI, TO><<<blocks, kThreads, 0, st>>>(static_cast<const TI*>(image), q->stride_n, q->stride_h,     \
                                                          q->stride_w, q->stride_c, static_cast<TO*>(col), ldcol, g)
     if (image_dtype == MVAE_F32 && col_dtype == MVAE_F32) MVAE_I2C(float, float);
+    else if (image_dtype == MVAE_F32 && g.k == 4 && g.C == 3)
+      im2col_any_kernel<float, __nv_bfloat16, 4, 3><<<blocks, kThreads, 0, st>>>(
+          static_cast<const float*>(image), q->stride_n, q->stride_h, q->stride_w, q->stride_c, static_cast<__nv_bfloat16*>(col), ldcol, g);
+    else if (image_dtype == MVAE_F32 && g.k == 4 && g.C == 1)
+      im2col_any_kernel<float, __nv_bfloat16, 4, 1><<<blocks, kThreads, 0, st>>>(
+          static_cast<const float*>(image), q->stride_n, q->stride_h, q->stride_w, q->stride_c, static_cast<__nv_bfloat16*>(col), ldcol, g);
     else if (image_dtype == MVAE_F32) MVAE_I2C(float, __nv_bfloat16);
     else if (col_dtype == MVAE_F32) MVAE_I2C(__nv_bfloat16, float);
     else MVAE_I2C(__nv_bfloat16, __nv_bfloat16);
@@ -895,12 +989,15 @@ int mvae_col2im(const mvae_conv_geometry* q, int col_dtype, const void* col, int
   const long long items = static_cast<long long>(g.B) * g.H * g.W * g.C;
   if (image_dtype == col_dtype && dense_nhwc(q) && g.C % vec == 0 && ldcol % vec == 0 &&
       reinterpret_cast<uintptr_t>(image) % 16 == 0 && reinterpret_cast<uintptr_t>(col) % 16 == 0) {
+    const int per_row = g.W * (g.C / vec);
+    const int threads = std::max(64, std::min(kThreads, (per_row + 31) / 32 * 32));
+    const dim3 grid(std::max(1, std::min((per_row + threads - 1) / threads, 8)),
+                    static_cast<unsigned>(std::min<long long>(static_cast<long long>(g.B) * g.H, 16 * sm_count_())));
     if (col_dtype == MVAE_F32)
-      col2im_vec_kernel<float><<<grid_for(items / vec), kThreads, 0, st>>>(static_cast<const float*>(col), ldcol,
-                                                                            static_cast<float*>(image), g);
+      col2im_vec_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(col), ldcol, static_cast<float*>(image), g);
     else
-      col2im_vec_kernel<__nv_bfloat16><<<grid_for(items / vec), kThreads, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(col), ldcol, static_cast<__nv_bfloat16*>(image), g);
+      col2im_vec_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(col), ldcol,
+                                                                   static_cast<__nv_bfloat16*>(image), g);
   } else {
     const int blocks = grid_for(items / g.C);
 #define MVAE_C2I(TI, TO)                                                                                          \
@@ -1075,7 +1172,15 @@ int mvae_sigmoid_bce(const mvae_sigmoid_bce_args* p, void* stream) {
   a.dprobs = p->dprobs; a.lddp = p->ld_dprobs;
   MVAE_REQUIRE(a.ldl >= a.cols, "sigmoid_bce: ld_logits < cols");
   const long long items = a.rows * (a.ld_pad_zero ? a.ldd : a.cols);
-  sigmoid_bce_kernel<<<grid_for(items, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  auto al16 = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  const bool f32x4 = a.target != nullptr && a.logit_dtype == MVAE_F32 && a.target_dtype == MVAE_F32 && a.cols % 4 == 0 &&
+                     a.ldl % 4 == 0 && a.ldt % 4 == 0 && !a.ld_pad_zero && al16(a.logits) && al16(a.target) &&
+                     (a.dlogits == nullptr || (a.grad_dtype == MVAE_F32 && a.ldd % 4 == 0 && al16(a.dlogits))) &&
+                     (a.probs == nullptr || (a.prob_dtype == MVAE_F32 && a.ldp % 4 == 0 && al16(a.probs)));
+  if (f32x4)
+    sigmoid_bce_f32x4_kernel<<<grid_for(items / 4, 8), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else
+    sigmoid_bce_kernel<<<grid_for(items, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
   return 0;
