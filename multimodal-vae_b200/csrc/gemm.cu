@@ -45,6 +45,7 @@ struct GemmKParams {
   int b_stage_bytes;  // smem bytes reserved per stage for B (multiple of 1024)
   int b_tx_bytes;     // bytes TMA actually writes per stage for B
   int vec_ok;         // all epilogue tensors allow 4-element vector access
+  int direct_store;   // plain STORE epilogue without statistics: TMEM -> registers -> global, no staging pass
   int aux_off;        // byte offset (dynamic smem) of the prefetched auxiliary tile, or -1
   int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
@@ -561,6 +562,61 @@ __global__ void __launch_bounds__(kGemmThreads)
   ptx::mbar_wait(&accum_bar, 0);
   ptx::tc_fence_after();
   if (threadIdx.x == 64) stamp(4);
+  bool stored_directly = false;
+  if constexpr (kEpi == EPI_STORE) {
+    if (p.direct_store) {
+      // Plain store (no column statistics): every thread owns one accumulator row (TMEM lane) and writes 16 consecutive
+      // columns per tcgen05.ld - 32-byte (bf16) / 64-byte (fp32) sector-aligned runs, no shared-memory staging pass.
+      stored_directly = true;
+      const int q = warp & 3;
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      for (int c = (warp >> 2) * 16; c < p.block_n; c += 32) {
+        uint32_t v[16];
+        ptx::tmem_ld16(t_base + c, v);
+        ptx::tmem_ld_wait();
+        const int cn = n0 + c;
+        if (row < p.M && cn < p.N) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (e.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cn + j < p.N) f[j] += __ldg(e.bias + cn + j);
+          }
+          if (e.c_dtype == MVAE_F32) {
+            float* dst = reinterpret_cast<float*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
+            if (cn + 16 <= p.N) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cn + j < p.N) dst[j] = f[j];
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
+            if (cn + 16 <= p.N) {
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cn + j < p.N) dst[j] = __float2bfloat16_rn(f[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!stored_directly) {
   {
     const int q = warp & 3;
     const uint32_t row_addr = stage_addr + static_cast<uint32_t>((q * 32 + lane) * ldst) * 4u;
@@ -644,6 +700,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     }
     if (threadIdx.x == 64) stamp(6);
   }
+  }  // !stored_directly
 
   if constexpr (kEpi == EPI_STORE) {
     if (e.fuse_bn) {
@@ -1016,6 +1073,12 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   if (e.kind == EPI_BCE) vec = vec && (e.ldt % 4 == 0) && al(e.target, aa);
   if (e.kind == EPI_DGRAD_BN) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
   kp.vec_ok = vec ? 1 : 0;
+  {
+    static const int use_direct = env_int("MVAE_GEMM_DIRECT_STORE", 1);
+    const int cvec = e.c_dtype == MVAE_F32 ? 4 : 8;   // elements per 16-byte store
+    kp.direct_store = (use_direct != 0 && e.kind == EPI_STORE && e.stat0 == nullptr && !fuse && !atf_on &&
+                       e.ldc % cvec == 0 && al(e.C, 16)) ? 1 : 0;
+  }
   const int tail0 = dyn - 1024 - coef_bytes - bnco_bytes(block_n) - aux_bytes(block_n) - red_bytes(block_n);
   kp.aux_off = (aux_ok && vec) ? tail0 : -1;
   kp.red_off = red_ok ? tail0 + aux_bytes(block_n) : -1;
