@@ -120,31 +120,45 @@ class MultimodalVAE(ConvMVAEBase):
         ldc = ws.ldc = round_up(H + n, self.vec)
         ldg = ws.ldg = round_up(3 * H, self.vec)
         rows = max(M3, B)
-        ws.gi, ws.gh = buf(rows * 3 * H, dtype=f32), buf(rows * 3 * H, dtype=f32)
-        ws.dgi, ws.dgh = buf(rows * ldg), buf(rows * ldg)
-        # text encoder
-        ws.ex = [buf(B * ldH) for _ in range(MAX_LEN)]
+        T = MAX_LEN
+
+        def slices(flat, per, count):
+            return [flat[i * per:(i + 1) * per] for i in range(count)]
+
+        ws.gi, ws.gh = buf(T * rows * 3 * H, dtype=f32), buf(rows * 3 * H, dtype=f32)
+        # gate gradients of every time step, stacked time-major: ONE weight-gradient GEMM / bias reduction per weight
+        ws.dgi_all = [buf(T * rows * ldg), buf(T * rows * ldg)]
+        ws.dgh_all = [buf(T * rows * ldg), buf(T * rows * ldg)]
+        ws.dgi_r, ws.dgh_r = buf(B * ldg), buf(B * ldg)
+        ws.gi_r = buf(B * 3 * H, dtype=f32)
+        # text encoder (rows B): ex_all slot t = embedded character t; hf_all slot 0 = zeros, slot t+1 = h_t
+        ws.ex_all = buf(T * B * ldH)
+        ws.ex = slices(ws.ex_all, B * ldH, T)
         ws.zeros_h = buf(rows * ldH)
-        ws.hf = [buf(B * ldH) for _ in range(MAX_LEN)]
+        ws.hf_all = buf((T + 1) * B * ldH)
+        ws.hf = slices(ws.hf_all, B * ldH, T + 1)[1:]
         ws.hsum = buf(B * ldH)
-        ws.te_saved = [buf(B * 4 * H, dtype=f32) for _ in range(MAX_LEN + 1)]
-        ws.te_cells = [None] * (MAX_LEN + 1)
+        ws.te_saved = [buf(B * 4 * H, dtype=f32) for _ in range(T + 1)]
+        ws.te_cells = [None] * (T + 1)
         ws.dhsum, ws.te_carry = buf(B * H, dtype=f32), buf(B * H, dtype=f32)
-        ws.dex = [buf(B * H, dtype=f32) for _ in range(MAX_LEN)]
-        # text decoder
-        ws.h_init = buf(M3 * ldH)
-        ws.cat1 = [buf(M3 * ldc) for _ in range(MAX_LEN)]
-        ws.cat2 = [buf(M3 * ldc) for _ in range(MAX_LEN)]
-        ws.h0 = [buf(M3 * ldH) for _ in range(MAX_LEN)]
-        ws.h0d = [buf(M3 * ldH) for _ in range(MAX_LEN)]
-        ws.h1 = [buf(M3 * ldH) for _ in range(MAX_LEN)]
-        ws.td_saved = [[buf(M3 * 4 * H, dtype=f32) for _ in range(MAX_LEN)] for _ in range(2)]
-        ws.td_cells = [[None] * MAX_LEN for _ in range(2)]
-        ws.c_in = [torch.full((M3,), SOS, device=dev, dtype=torch.int64) for _ in range(MAX_LEN + 1)]
+        ws.dex_all = buf(T * B * H, dtype=f32)
+        ws.dex = slices(ws.dex_all, B * H, T)
+        # text decoder (rows M3): h*_all slot 0 = z2h(z), slot t+1 = h_t of the layer
+        ws.cat1_all, ws.cat2_all = buf(T * M3 * ldc), buf(T * M3 * ldc)
+        ws.cat1, ws.cat2 = slices(ws.cat1_all, M3 * ldc, T), slices(ws.cat2_all, M3 * ldc, T)
+        ws.h0_all, ws.h1_all = buf((T + 1) * M3 * ldH), buf((T + 1) * M3 * ldH)
+        ws.h_init = ws.h0_all[:M3 * ldH]
+        ws.h0, ws.h1 = slices(ws.h0_all, M3 * ldH, T + 1)[1:], slices(ws.h1_all, M3 * ldH, T + 1)[1:]
+        ws.h0d_all = buf(T * M3 * ldH)
+        ws.h0d = slices(ws.h0d_all, M3 * ldH, T)
+        ws.td_saved = [[buf(M3 * 4 * H, dtype=f32) for _ in range(T)] for _ in range(2)]
+        ws.td_cells = [[None] * T for _ in range(2)]
+        ws.c_in = [torch.full((M3,), SOS, device=dev, dtype=torch.int64) for _ in range(T + 1)]
         ws.tlogits = buf(M3 * N_CHARS, dtype=f32)
-        ws.words = buf(M3 * MAX_LEN * N_CHARS, dtype=f32)
+        ws.words = buf(M3 * T * N_CHARS, dtype=f32)
         ws.ld_dlog = round_up(N_CHARS, self.vec)
-        ws.dlog = [buf(M3 * ws.ld_dlog) for _ in range(MAX_LEN)]
+        ws.dlog_all = buf(T * M3 * ws.ld_dlog)
+        ws.dlog = slices(ws.dlog_all, M3 * ws.ld_dlog, T)
         ws.dcat = buf(M3 * (H + n), dtype=f32)
         ws.carry = [buf(M3 * H, dtype=f32), buf(M3 * H, dtype=f32)]
         ws.dx1, ws.dx1_t, ws.dx1d_t = buf(M3 * H, dtype=f32), buf(M3 * ldH), buf(M3 * ldH)
@@ -152,32 +166,42 @@ class MultimodalVAE(ConvMVAEBase):
         return ws
 
     # ------------------------------------------------------------------ GRU helpers
-    def _cell_fwd(self, ws, rows, x, ldx, n_in, h_prev, prefix, suffix, saved, h_out, h_out2=None, ld_h_out2=0, addend=None):
-        """One GRU cell: gi = x W_ih^T + b_ih, gh = h W_hh^T + b_hh (tcgen05 GEMMs), then the gate kernel."""
-        wi, ldwi = self.operand("%s.weight_ih_%s" % (prefix, suffix), 3 * H, n_in)
+    def _cell_fwd(self, ws, rows, x, ldx, n_in, h_prev, prefix, suffix, saved, h_out, h_out2=None, ld_h_out2=0, addend=None,
+                  gi=None):
+        """One GRU cell: gi = x W_ih^T + b_ih (or precomputed for all steps), gh = h W_hh^T + b_hh (tcgen05 GEMMs), gates."""
         wh, ldwh = self.operand("%s.weight_hh_%s" % (prefix, suffix), 3 * H, H)
-        _ops.gemm(x, wi, ws.gi, rows, 3 * H, n_in, ldx, ldwi, 3 * H, bias=self.P("%s.bias_ih_%s" % (prefix, suffix)))
+        if gi is None:
+            wi, ldwi = self.operand("%s.weight_ih_%s" % (prefix, suffix), 3 * H, n_in)
+            gi = ws.gi
+            _ops.gemm(x, wi, gi, rows, 3 * H, n_in, ldx, ldwi, 3 * H, bias=self.P("%s.bias_ih_%s" % (prefix, suffix)))
         hp = h_prev if h_prev is not None else ws.zeros_h
         _ops.gemm(hp, wh, ws.gh, rows, 3 * H, H, ws.ldH, ldwh, 3 * H, bias=self.P("%s.bias_hh_%s" % (prefix, suffix)))
-        return _ops.gru_cell_forward(rows, H, ws.gi, ws.gh, h_prev, ws.ldH, h_out, ws.ldH, saved, h_out2, ld_h_out2, addend, ws.ldH)
+        return _ops.gru_cell_forward(rows, H, gi, ws.gh, h_prev, ws.ldH, h_out, ws.ldH, saved, h_out2, ld_h_out2, addend, ws.ldH)
 
-    def _cell_bwd(self, ws, rows, cell, x, ldx, n_in, h_prev, prefix, suffix, dh_a, ld_dh_a, dh_b, carry, dx, lddx,
-                  accumulate_dx=False, propagate_h=True):
-        """Backward of _cell_fwd: parameter gradients, dx (=|+=) dgi W_ih, carry = dh*z + dgh W_hh (gradient at h_prev)."""
-        _ops.gru_cell_backward(cell, dh_a, ld_dh_a, dh_b, H, ws.dgi, ws.dgh, ws.ldg, carry, H)
-        G = self.G
+    def _cell_bwd(self, ws, rows, cell, h_prev, prefix, suffix, dh_a, ld_dh_a, dh_b, carry, dgi, dgh, n_in=0, dx=None, lddx=0,
+                  accumulate_dx=False):
+        """Backward of one cell's gate math and its data gradients: dgi / dgh land in the caller's (time-stacked) buffers,
+        carry = dh*z + dgh W_hh (gradient at h_prev), dx (=|+=) dgi W_ih.  Parameter gradients: _cells_param_grads."""
+        _ops.gru_cell_backward(cell, dh_a, ld_dh_a, dh_b, H, dgi, dgh, ws.ldg, carry, H)
         ki, kh = "%s.weight_ih_%s" % (prefix, suffix), "%s.weight_hh_%s" % (prefix, suffix)
-        _ops.gemm(ws.dgi, x, G(ki), 3 * H, n_in, rows, ws.ldg, ldx, n_in, a_major=1, b_major=1, accumulate=True)
-        _ops.col_stats(ws.dgi, rows, ws.ldg, G("%s.bias_ih_%s" % (prefix, suffix)), valid_channels=3 * H)
-        _ops.col_stats(ws.dgh, rows, ws.ldg, G("%s.bias_hh_%s" % (prefix, suffix)), valid_channels=3 * H)
-        if h_prev is not None:
-            _ops.gemm(ws.dgh, h_prev, G(kh), 3 * H, H, rows, ws.ldg, ws.ldH, H, a_major=1, b_major=1, accumulate=True)
-            if propagate_h and carry is not None:
-                wh, ldwh = self._operand_cached(kh, H)
-                _ops.gemm(ws.dgh, wh, carry, rows, H, 3 * H, ws.ldg, ldwh, H, b_major=1, accumulate=True)
+        if h_prev is not None and carry is not None:
+            wh, ldwh = self._operand_cached(kh, H)
+            _ops.gemm(dgh, wh, carry, rows, H, 3 * H, ws.ldg, ldwh, H, b_major=1, accumulate=True)
         if dx is not None:
             wi, ldwi = self._operand_cached(ki, n_in)
-            _ops.gemm(ws.dgi, wi, dx, rows, n_in, 3 * H, ws.ldg, ldwi, lddx, b_major=1, accumulate=accumulate_dx)
+            _ops.gemm(dgi, wi, dx, rows, n_in, 3 * H, ws.ldg, ldwi, lddx, b_major=1, accumulate=accumulate_dx)
+
+    def _cells_param_grads(self, ws, rows, dgi, dgh, x, ldx, n_in, h_prev, prefix, suffix) -> None:
+        """dW_ih += dgi^T x, dW_hh += dgh^T h_prev, db_ih += colsum(dgi), db_hh += colsum(dgh) over `rows` stacked rows
+        (all time steps of a layer at once)."""
+        G = self.G
+        _ops.gemm(dgi, x, G("%s.weight_ih_%s" % (prefix, suffix)), 3 * H, n_in, rows, ws.ldg, ldx, n_in, a_major=1, b_major=1,
+                  accumulate=True)
+        _ops.col_stats(dgi, rows, ws.ldg, G("%s.bias_ih_%s" % (prefix, suffix)), valid_channels=3 * H)
+        _ops.col_stats(dgh, rows, ws.ldg, G("%s.bias_hh_%s" % (prefix, suffix)), valid_channels=3 * H)
+        if h_prev is not None:
+            _ops.gemm(dgh, h_prev, G("%s.weight_hh_%s" % (prefix, suffix)), 3 * H, H, rows, ws.ldg, ws.ldH, H, a_major=1, b_major=1,
+                      accumulate=True)
 
     # ------------------------------------------------------------------ forward
     def run_forward(self, ws, image, text, term_types: Sequence[int], eps, training: bool, lambdas, kl_weights,
@@ -214,12 +238,16 @@ class MultimodalVAE(ConvMVAEBase):
         g = "text_encoder.gru"
         for t in range(MAX_LEN):
             _ops.embed_forward(text, t, MAX_LEN, emb, N_CHARS, H, NONE, ws.ex[t], 0, ws.ldH, B)
+        wi, ldwi = self.operand(g + ".weight_ih_l0", 3 * H, H)
+        _ops.gemm(ws.ex_all, wi, ws.gi, MAX_LEN * B, 3 * H, H, ws.ldH, ldwi, 3 * H, bias=self.P(g + ".bias_ih_l0"))
         for t in range(MAX_LEN):
             ws.te_cells[t] = self._cell_fwd(ws, B, ws.ex[t], ws.ldH, H, ws.hf[t - 1] if t > 0 else None, g, "l0", ws.te_saved[t],
-                                            ws.hf[t])
+                                            ws.hf[t], gi=ws.gi[t * B * 3 * H:(t + 1) * B * 3 * H])
         # reverse direction at the last position: one cell from a zero state; its output is summed with the forward one
+        wr, ldwr = self.operand(g + ".weight_ih_l0_reverse", 3 * H, H)
+        _ops.gemm(ws.ex[MAX_LEN - 1], wr, ws.gi_r, B, 3 * H, H, ws.ldH, ldwr, 3 * H, bias=self.P(g + ".bias_ih_l0_reverse"))
         ws.te_cells[MAX_LEN] = self._cell_fwd(ws, B, ws.ex[MAX_LEN - 1], ws.ldH, H, None, g, "l0_reverse", ws.te_saved[MAX_LEN],
-                                              ws.hsum, addend=ws.hf[MAX_LEN - 1])
+                                              ws.hsum, addend=ws.hf[MAX_LEN - 1], gi=ws.gi_r)
         self.linear_fwd(ws.hsum, ws.ldH, B, "text_encoder.h2p", 2 * n, H, ws.encB, 2 * n)
 
     def decode(self, ws, training: bool, lambdas, want_probs: bool, with_loss: bool) -> None:
@@ -244,6 +272,7 @@ class MultimodalVAE(ConvMVAEBase):
         ldH, ldc = ws.ldH, ws.ldc
         wz, ldwz = self.operand("text_decoder.z2h.weight", H, n)
         _ops.gemm(ws.z, wz, ws.h_init, M3, H, n, ws.ld_z, ldwz, ldH, bias=self.P("text_decoder.z2h.bias"))
+        _ops.copy_2d(ws.h_init, 0, ldH, ws.h1_all, 0, ldH, M3, H)          # slot 0 of layer 1 = the same initial state
         for t in range(MAX_LEN):
             _ops.embed_forward(ws.c_in[t], 0, 1, emb, N_CHARS, H, SWISH, ws.cat1[t], 0, ldc, M3)
             _ops.copy_2d(ws.z, 0, ws.ld_z, ws.cat1[t], H, ldc, M3, n)
@@ -254,7 +283,7 @@ class MultimodalVAE(ConvMVAEBase):
                 _ops.act_forward(NONE, ws.h0[t], ws.h0d[t], M3, ldH, dropout_p=p, seed=self.noise_seed + 303 + t,
                                  step_counter=self._step_counter)
                 x1 = ws.h0d[t]
-            ws.td_cells[1][t] = self._cell_fwd(ws, M3, x1, ldH, H, ws.h1[t - 1] if t > 0 else ws.h_init, g, "l1",
+            ws.td_cells[1][t] = self._cell_fwd(ws, M3, x1, ldH, H, ws.h1[t - 1] if t > 0 else ws.h1_all[:M3 * ldH], g, "l1",
                                                ws.td_saved[1][t], ws.h1[t], h_out2=ws.cat2[t], ld_h_out2=ldc)
             _ops.copy_2d(ws.z, 0, ws.ld_z, ws.cat2[t], H, ldc, M3, n)
             self.linear_fwd(ws.cat2[t], ldc, M3, "text_decoder.h2o", N_CHARS, H + n, ws.tlogits, N_CHARS)
@@ -278,24 +307,36 @@ class MultimodalVAE(ConvMVAEBase):
         emb = self.P("text_decoder.embed.weight")
         ldH, ldc, p = ws.ldH, ws.ldc, ws.td_dropout
         Kc = H + n
-        for t in range(MAX_LEN - 1, -1, -1):
-            last = t == MAX_LEN - 1
-            self.linear_bwd(ws.cat2[t], ldc, ws.dlog[t], ws.ld_dlog, M3, "text_decoder.h2o", N_CHARS, Kc, dx=ws.dcat, lddx=Kc)
+        T = MAX_LEN
+        wo, ldwo = self._operand_cached("text_decoder.h2o.weight", Kc)
+        sl = lambda flat, t: flat[t * M3 * ws.ldg:(t + 1) * M3 * ws.ldg]
+        for t in range(T - 1, -1, -1):
+            last = t == T - 1
+            _ops.gemm(ws.dlog[t], wo, ws.dcat, M3, Kc, N_CHARS, ws.ld_dlog, ldwo, Kc, b_major=1)       # d[h1 | z] of step t
             _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
-            x1 = ws.h0d[t] if p > 0 else ws.h0[t]
             dx1 = ws.dx1_t if p > 0 else ws.dx1
-            self._cell_bwd(ws, M3, ws.td_cells[1][t], x1, ldH, H, ws.h1[t - 1] if t > 0 else ws.h_init, g, "l1",
-                           ws.dcat, Kc, None if last else ws.carry[1], ws.carry[1], dx1, ldH if p > 0 else H)
+            self._cell_bwd(ws, M3, ws.td_cells[1][t], ws.h1[t - 1] if t > 0 else ws.h1_all[:M3 * ldH], g, "l1", ws.dcat, Kc,
+                           None if last else ws.carry[1], ws.carry[1], sl(ws.dgi_all[1], t), sl(ws.dgh_all[1], t), n_in=H,
+                           dx=dx1, lddx=ldH if p > 0 else H)
             if p > 0:
                 _ops.act_backward(NONE, ws.h0[t], ws.dx1_t, ws.dx1d_t, M3, ldH, dropout_p=p, seed=self.noise_seed + 303 + t,
                                   step_counter=self._step_counter)
                 dh0, ld_dh0 = ws.dx1d_t, ldH
             else:
                 dh0, ld_dh0 = ws.dx1, H
-            self._cell_bwd(ws, M3, ws.td_cells[0][t], ws.cat1[t], ldc, Kc, ws.h0[t - 1] if t > 0 else ws.h_init, g, "l0",
-                           dh0, ld_dh0, None if last else ws.carry[0], ws.carry[0], ws.dcat, Kc)
+            self._cell_bwd(ws, M3, ws.td_cells[0][t], ws.h0[t - 1] if t > 0 else ws.h_init, g, "l0", dh0, ld_dh0,
+                           None if last else ws.carry[0], ws.carry[0], sl(ws.dgi_all[0], t), sl(ws.dgh_all[0], t), n_in=Kc,
+                           dx=ws.dcat, lddx=Kc)
             _ops.embed_backward(ws.c_in[t], 0, 1, emb, N_CHARS, H, SWISH, ws.dcat, 0, Kc, M3, Gd("text_decoder.embed.weight"))
             _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
+        # parameter gradients of the 4 steps at once (time-stacked operands)
+        TM = T * M3
+        _ops.gemm(ws.dlog_all, ws.cat2_all, Gd("text_decoder.h2o.weight"), N_CHARS, Kc, TM, ws.ld_dlog, ldc, Kc, a_major=1, b_major=1,
+                  accumulate=True)
+        _ops.col_stats(ws.dlog_all, TM, ws.ld_dlog, Gd("text_decoder.h2o.bias"), valid_channels=N_CHARS)
+        x1_all = ws.h0d_all if p > 0 else ws.h0_all[M3 * ldH:]
+        self._cells_param_grads(ws, TM, ws.dgi_all[1][:TM * ws.ldg], ws.dgh_all[1][:TM * ws.ldg], x1_all, ldH, H, ws.h1_all, g, "l1")
+        self._cells_param_grads(ws, TM, ws.dgi_all[0][:TM * ws.ldg], ws.dgh_all[0][:TM * ws.ldg], ws.cat1_all, ldc, Kc, ws.h0_all, g, "l0")
         # both GRU layers start from h = z2h(z)
         _ops.copy_2d(ws.carry[0], 0, H, ws.dhinit, 0, ldH, M3, H, src2=ws.carry[1], ld_src2=H)
         self.linear_bwd(ws.z, ws.ld_z, ws.dhinit, ldH, M3, "text_decoder.z2h", H, n, dx=ws.dz, lddx=n, accumulate_dx=True)
@@ -309,14 +350,22 @@ class MultimodalVAE(ConvMVAEBase):
             g = "text_encoder.gru"
             ldH = ws.ldH
             self.linear_bwd(ws.hsum, ldH, ws.dencB, ws.ld_enc, B, "text_encoder.h2p", 2 * n, H, dx=ws.dhsum, lddx=H)
-            # reverse-direction cell (zero initial state: no W_hh gradient, no carry)
-            self._cell_bwd(ws, B, ws.te_cells[MAX_LEN], ws.ex[MAX_LEN - 1], ldH, H, None, g, "l0_reverse", ws.dhsum, H, None, None,
-                           ws.dex[MAX_LEN - 1], H)
-            for t in range(MAX_LEN - 1, -1, -1):
-                last = t == MAX_LEN - 1
-                self._cell_bwd(ws, B, ws.te_cells[t], ws.ex[t], ldH, H, ws.hf[t - 1] if t > 0 else None, g, "l0",
-                               ws.dhsum if last else None, H, None if last else ws.te_carry, ws.te_carry, ws.dex[t], H,
-                               accumulate_dx=last)
+            T = MAX_LEN
+            sl = lambda flat, t: flat[t * B * ws.ldg:(t + 1) * B * ws.ldg]
+            for t in range(T - 1, -1, -1):
+                last = t == T - 1
+                self._cell_bwd(ws, B, ws.te_cells[t], ws.hf[t - 1] if t > 0 else None, g, "l0", ws.dhsum if last else None, H,
+                               None if last else ws.te_carry, ws.te_carry, sl(ws.dgi_all[0], t), sl(ws.dgh_all[0], t))
+            TB = T * B
+            dgi_all, dgh_all = ws.dgi_all[0][:TB * ws.ldg], ws.dgh_all[0][:TB * ws.ldg]
+            self._cells_param_grads(ws, TB, dgi_all, dgh_all, ws.ex_all, ldH, H, ws.hf_all, g, "l0")
+            wi, ldwi = self._operand_cached(g + ".weight_ih_l0", H)
+            _ops.gemm(dgi_all, wi, ws.dex_all, TB, H, 3 * H, ws.ldg, ldwi, H, b_major=1)              # gradient at every embedding
+            # reverse-direction cell (zero initial state: no W_hh gradient, no carry); its input is the last character too
+            self._cell_bwd(ws, B, ws.te_cells[T], None, g, "l0_reverse", ws.dhsum, H, None, None, ws.dgi_r, ws.dgh_r, n_in=H,
+                           dx=ws.dex[T - 1], lddx=H, accumulate_dx=True)
+            self._cells_param_grads(ws, B, ws.dgi_r, ws.dgh_r, ws.ex[T - 1], ldH, H, None, g, "l0_reverse")
+            for t in range(T):
                 _ops.embed_backward(ws.text, t, MAX_LEN, self.P("text_encoder.embed.weight"), N_CHARS, H, NONE, ws.dex[t], 0, H, B,
                                     Gd("text_encoder.embed.weight"))
         if ws.use_img:
