@@ -233,9 +233,29 @@ def run_device(args):
         return float(t.item())
 
     lib = mvae_b200._lib.load()
+    # Weak supervision (BASELINE.json configs[4], mnist/modal_weak.py:60-97): the joint term always, the image-only term with
+    # probability P1 and the text-only term (lambdas (0,1)) with probability P2 per batch, flips from np.random.seed(42) -
+    # identical on every rank, so the data-parallel graphs (one per term set) stay in lock step.
+    import numpy as np
+    flips = np.random.RandomState(42)
+
+    def step_kwargs():
+        if args.weak is None:
+            return {}
+        terms, lams = ["joint"], [(1.0, 1.0)]
+        if flips.random_sample() < args.weak[0]:
+            terms.append("image"); lams.append((1.0, 1.0))
+        if flips.random_sample() < args.weak[1]:
+            terms.append("text"); lams.append((0.0, 1.0))
+        return {"terms": tuple(terms), "lambdas": tuple(lams)}
+
+    if args.weak is not None:   # capture the (up to four) term-set graphs before timing
+        for terms, lams in ((("joint",), ((1.0, 1.0),)), (("joint", "image"), ((1.0, 1.0),) * 2),
+                            (("joint", "text"), ((1.0, 1.0), (0.0, 1.0))), (("joint", "image", "text"), ((1.0, 1.0), (1.0, 1.0), (0.0, 1.0)))):
+            trainer.step(pool_x[0], pool_y[0], terms=terms, lambdas=lams)
     # ---- device-resident throughput ("value")
     for i in range(max(args.warmup, 3)):
-        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], **step_kwargs())
     log("warmup done")
     barrier()
     log("barrier done")
@@ -245,7 +265,7 @@ def run_device(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots])
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], **step_kwargs())
     e1.record()
     log("timed loop enqueued")
     barrier()
@@ -344,7 +364,10 @@ def run_device(args):
                    "batch_per_gpu": B, "global_batch": B * world, "n_latents": N_LATENTS, "parallelism": "dp%d" % world,
                    "l2_policy": "inputs rotate through a pool of %d distinct batches (%.0f MB > 2x L2)" % (
                        n_slots, n_slots * B * 784 * es / 1e6),
-                   "cuda_graph": not args.no_graph, "precision": args.precision},
+                   "cuda_graph": not args.no_graph, "precision": args.precision,
+                   **({"weak_supervision": {"p_image_only": args.weak[0], "p_text_only": args.weak[1],
+                                            "rule": "mnist/modal_weak.py:60-97, np.random.seed(42) flips per batch"}}
+                      if args.weak is not None else {})},
         "final_loss_terms": final_loss,
         "gpu_launches": per_step_launches * args.steps,
         "gpu_launches_per_step": per_step_launches,
@@ -387,6 +410,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the whole backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weak", type=float, nargs=2, default=None, metavar=("P_IMAGE", "P_TEXT"),
+                    help="MNIST weak supervision (mnist/modal_weak.py): per-batch probabilities of the image-only / text-only terms")
     ap.add_argument("--workload", default="mnist", choices=["mnist", "celeba", "multimnist"],
                     help="mnist = the headline config (BASELINE.json configs[1]); celeba / multimnist = configs[3] / [2]")
     args = ap.parse_args()
