@@ -363,6 +363,11 @@ typedef struct mvae_logsoftmax_nll_args {
 } mvae_logsoftmax_nll_args;
 int mvae_logsoftmax_nll(const mvae_logsoftmax_nll_args* args, void* stream);
 
+/* Backward of F.log_softmax for callers that differentiate the returned log-probabilities themselves (module path):
+ * dlogits = dlogp - exp(logp) * sum_c dlogp; columns [classes, ld_dlogits) zero-filled. */
+int mvae_logsoftmax_backward(const float* logp, int64_t ld_logp, const float* dlogp, int64_t ld_dlogp, int64_t rows, int classes,
+                             int grad_dtype, void* dlogits, int64_t ld_dlogits, void* stream);
+
 /* dst[r, c] (+)= src[r, c] (+ src2[r, c]) for c < cols, with independent dtypes and leading dimensions. */
 int mvae_copy_2d(int src_dtype, const void* src, int64_t ld_src, int dst_dtype, void* dst, int64_t ld_dst, int64_t rows,
                  int64_t cols, int accumulate, int src2_dtype, const void* src2, int64_t ld_src2, void* stream);

@@ -213,5 +213,6 @@ def _conv_argtypes(lib) -> None:
     lib.mvae_gru_cell_forward.argtypes = [P(GruCellArgs), c_void_p]
     lib.mvae_gru_cell_backward.argtypes = [P(GruCellArgs), c_void_p]
     lib.mvae_logsoftmax_nll.argtypes = [P(LogSoftmaxNllArgs), c_void_p]
+    lib.mvae_logsoftmax_backward.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int64, c_void_p]
     lib.mvae_copy_2d.argtypes = [c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p,
                                  c_int64, c_void_p]

@@ -214,6 +214,12 @@ def logsoftmax_nll(logits, ld_logits, rows, classes, rows_per_group=0, target=No
     _lib.check(_lib.load().mvae_logsoftmax_nll(C.byref(a), stream()), "mvae_logsoftmax_nll")
 
 
+def logsoftmax_backward(logp, logp_off, ld_logp, dlogp, dlogp_off, ld_dlogp, rows, classes, dlogits, ld_dlogits):
+    _lib.check(_lib.load().mvae_logsoftmax_backward(view_ptr(logp, logp_off), int(ld_logp), view_ptr(dlogp, dlogp_off), int(ld_dlogp),
+                                                    int(rows), int(classes), DT[dlogits.dtype], dlogits.data_ptr(), int(ld_dlogits),
+                                                    stream()), "mvae_logsoftmax_backward")
+
+
 def copy_2d(src, src_off, ld_src, dst, dst_off, ld_dst, rows, cols, accumulate=False, src2=None, src2_off=0, ld_src2=0):
     _lib.check(_lib.load().mvae_copy_2d(DT[src.dtype], view_ptr(src, src_off), int(ld_src), DT[dst.dtype], view_ptr(dst, dst_off),
                                         int(ld_dst), int(rows), int(cols), 1 if accumulate else 0,

@@ -193,7 +193,34 @@ class MultimodalVAE(ConvMVAEBase):
         _ops.act_backward(SWISH, ws.u1pre, ws.du1, ws.du1pre, M3, 6400, dbias=Gd("image_decoder.upsample.0.bias"))
         self.linear_bwd(ws.z, ws.ld_z, ws.du1pre, 6400, M3, "image_decoder.upsample.0", 6400, n, dx=ws.dz, lddx=n,
                         accumulate_dx=True, bias=False)
-        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_att else None)
+        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_att else None, *getattr(ws, "upstream", (None, None)))
+
+    def module_outputs(self, ws):
+        B, n = ws.B, self.n_latents
+        return (ws.probs_image.view(B, 3, 64, 64).clone(), ws.probs_attrs.view(B, N_ATTRS).clone(),
+                ws.mu.view(1, B, n)[0].clone(), ws.logvar.view(1, B, n)[0].clone())
+
+    def module_backward(self, ws, g_image, g_attrs, g_mu, g_logvar) -> None:
+        """Backward from the gradients of (image_recon probs, attrs_recon probs, mu, logvar) - the reference's
+        loss.backward() (celeba/train.py:151) when the loss was built by the caller from forward()'s outputs."""
+        B = ws.B
+        if g_image is None:
+            ws.logits.zero_()
+        else:   # d logits = d probs * p * (1 - p), in place over the logits
+            _ops.sigmoid_bce(ws.logits, 12288, B, 12288, dprobs=g_image.reshape(B, 12288), ld_dprobs=12288, dlogits=ws.logits,
+                             ld_dlogits=12288)
+        if g_attrs is None:
+            ws.dalog.zero_()
+        else:
+            _ops.sigmoid_bce(ws.alogits, N_ATTRS, B, N_ATTRS, dprobs=g_attrs.reshape(B, N_ATTRS), ld_dprobs=N_ATTRS, dlogits=ws.dalog,
+                             ld_dlogits=ws.ld_dalog)
+        if g_mu is not None and g_logvar is None:
+            g_logvar = torch.zeros_like(g_mu)
+        if g_logvar is not None and g_mu is None:
+            g_mu = torch.zeros_like(g_logvar)
+        ws.upstream = (g_mu, g_logvar)
+        self.backward_decoders(ws)
+        self.backward_encoders(ws)
 
     def backward_encoders(self, ws) -> None:
         B, n, R = ws.B, self.n_latents, ws.R
@@ -215,16 +242,19 @@ class MultimodalVAE(ConvMVAEBase):
 
     # ------------------------------------------------------------------ module surface
     def forward(self, image: Optional[torch.Tensor] = None, attrs: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
-        """celeba/model.py:36-58: returns (image_recon, attrs_recon, mu, logvar).  Forward only (use CelebATrainer.step
-        for training); train mode draws the reparametrize noise in-kernel unless `eps` [B, n] is given."""
+        """celeba/model.py:36-58: returns (image_recon, attrs_recon, mu, logvar).  In train mode with autograd enabled the
+        outputs are differentiable (the reference's loop `loss_function(...).backward(); optimizer.step()` works unchanged;
+        CelebATrainer.step is the fused fast path); the reparametrize noise is drawn in-kernel unless `eps` [B, n] is given."""
         assert image is not None or attrs is not None
         t = _lib.TERM_JOINT if (image is not None and attrs is not None) else (_lib.TERM_IMAGE if image is not None else _lib.TERM_TEXT)
         B = (image if image is not None else attrs).shape[0]
-        ws = self.workspace(B, 1)
-        image = None if image is None else image.to(self.device, torch.float32).contiguous()
-        attrs = None if attrs is None else attrs.to(self.device, torch.float32).contiguous()
+        image = None if image is None else image.detach().to(self.device, torch.float32).contiguous()
+        attrs = None if attrs is None else attrs.detach().to(self.device, torch.float32).contiguous()
         if eps is not None:
             eps = eps.to(self.device, torch.float32).contiguous()
+        if self.training and torch.is_grad_enabled():
+            return self._autograd_forward(image, attrs, t, eps)
+        ws = self.workspace(B, 1)
         self.run_forward(ws, image, attrs, (t,), eps, self.training, ((0.0, 0.0),), (0.0,), True, False)
         n = self.n_latents
         return (ws.probs_image.view(B, 3, 64, 64).clone(), ws.probs_attrs.view(B, N_ATTRS).clone(),
@@ -272,3 +302,15 @@ class CelebATrainer(ConvMVAETrainer):
             k = float(acc[2, g])
             out.append((x + y + k, x, y, k))
         return out
+
+
+def loss_function(mu, logvar, recon_x=None, x=None, recon_y=None, y=None, kl_lambda=1e-3, lambda_x=1.0, lambda_y=1.0):
+    """celeba/train.py:60-81 on the module outputs (probabilities), differentiable; the arithmetic is the library's loss
+    kernels (mvae_elbo_loss_forward / _backward), not torch ops."""
+    from .functional import _ElboFn
+    B = mu.shape[0]
+    total = _ElboFn.apply(mu, logvar, recon_x, x, None, None, float(lambda_x), 0.0, float(kl_lambda) / B)
+    if recon_y is not None and y is not None:
+        z = torch.zeros(B, 1, device=mu.device)
+        total = total + _ElboFn.apply(z, z, recon_y, y, None, None, float(lambda_y), 0.0, 0.0)
+    return total

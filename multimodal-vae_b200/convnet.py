@@ -126,6 +126,9 @@ class ConvMVAEBase:
         self.flat_params = torch.zeros(off, device=dev, dtype=torch.float32)
         self.flat_grads = torch.zeros(off, device=dev, dtype=torch.float32)
         self.flat_params_bf16 = torch.zeros(off, device=dev, dtype=torch.bfloat16) if self.act_dtype == torch.bfloat16 else None
+        # the autograd / torch.optim view of the parameters: ONE leaf sharing the flat buffer's storage
+        self.param = torch.nn.Parameter(self.flat_params)
+        self.param.grad = self.flat_grads
         # ---- BatchNorm buffers
         self.bn_names = list(self.BN_LAYERS)
         self.bn_index = {p: i for i, p in enumerate(self.bn_names)}
@@ -247,7 +250,24 @@ class ConvMVAEBase:
         return self
 
     def parameters(self):
-        return [self.flat_params]
+        """One flat leaf (elementwise optimisers such as torch.optim.Adam do not care about the layout)."""
+        return [self.param]
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat_grads.zero_()
+        self.param.grad = self.flat_grads
+
+    # ------------------------------------------------------------------ module surface with autograd (train mode)
+    def _autograd_forward(self, image, other, term, eps):
+        """vae(image, other) usable in the reference's own training loop: outputs carry a grad_fn whose backward runs the
+        C-ABI backward kernels and delivers ONE gradient for the flat parameter leaf."""
+        return _ConvForwardFn.apply(self, image, other, term, eps, self.param)
+
+    def module_outputs(self, ws):
+        raise NotImplementedError
+
+    def module_backward(self, ws, g_image, g_other, g_mu, g_logvar):
+        raise NotImplementedError
 
     # ------------------------------------------------------------------ Linear helpers
     def operand(self, key: str, rows: int, cols: int) -> Tuple[torch.Tensor, int]:
@@ -471,8 +491,11 @@ class ConvMVAEBase:
         ws.latent = la
         _lib.check(_lib.load().mvae_latent_forward(C.byref(la), _ops.stream()), "mvae_latent_forward")
 
-    def latent_backward(self, ws, denc_a, denc_b) -> None:
+    def latent_backward(self, ws, denc_a, denc_b, d_mu=None, d_logvar=None) -> None:
         la = ws.latent
+        ws.keep_up = (d_mu, d_logvar)            # raw pointers below: keep the tensors alive
+        la.d_mu = None if d_mu is None else d_mu.data_ptr()
+        la.d_logvar = None if d_logvar is None else d_logvar.data_ptr()
         la.dz_dtype, la.dz, la.ld_dz = _lib.DT_F32, ws.dz.data_ptr(), self.n_latents
         la.d_dtype = _ops.DT[self.act_dtype]
         la.d_expert_a, la.ld_da = (None if denc_a is None else denc_a.data_ptr()), ws.ld_enc
@@ -505,6 +528,40 @@ class ConvMVAEBase:
 
 class Workspace:
     pass
+
+
+class _ConvForwardFn(torch.autograd.Function):
+    """Autograd bridge of MultimodalVAE.forward for the conv models: forward = the forward kernels on a PRIVATE workspace
+    (the reference's loop keeps three forwards alive before one backward), backward = the backward kernels fed with the
+    upstream gradients of (image_recon, second recon, mu, logvar); the gradient of the flat parameter leaf is returned."""
+
+    @staticmethod
+    def forward(ctx, model, image, other, term, eps, param):
+        B = (image if image is not None else other).shape[0]
+        model.sync_operands()                      # the parameters may have been stepped by a torch optimiser
+        inc = torch.tensor(model.bn_increments((term,)), dtype=torch.int64, device=model.device)
+        _ops.step_begin(model._step_counter, None, model.flat_nbt, inc)   # noise / dropout counter, num_batches_tracked
+        ws = model._make_workspace(B, 1)
+        ws.keep_inc = inc
+        model.run_forward(ws, image, other, (term,), eps, True, ((0.0, 0.0),), (0.0,), True, False)
+        ctx.model, ctx.ws = model, ws
+        return model.module_outputs(ws)
+
+    @staticmethod
+    def backward(ctx, g_image, g_other, g_mu, g_logvar):
+        m, ws = ctx.model, ctx.ws
+
+        def c(t):
+            return None if t is None else t.to(torch.float32).contiguous()
+
+        grads = torch.zeros_like(m.flat_params)
+        saved = m.flat_grads
+        m.flat_grads = grads
+        try:
+            m.module_backward(ws, c(g_image), c(g_other), c(g_mu), c(g_logvar))
+        finally:
+            m.flat_grads = saved
+        return None, None, None, None, None, grads
 
 
 class ConvMVAETrainer:

@@ -227,6 +227,19 @@ __global__ void __launch_bounds__(kThreads) logsoftmax_nll_kernel(const LsmArgs 
   }
 }
 
+// dlogits = dlogp - softmax * sum(dlogp): backward of F.log_softmax given an upstream gradient of the log-probabilities
+__global__ void __launch_bounds__(kThreads) logsoftmax_bwd_kernel(const float* __restrict__ logp, long long ldp,
+                                                                  const float* __restrict__ dlogp, long long ldg, long long rows,
+                                                                  int classes, void* dlogits, int g_dtype, long long ldd) {
+  for (long long m = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; m < rows;
+       m += static_cast<long long>(gridDim.x) * kThreads) {
+    float s = 0.f;
+    for (int c = 0; c < classes; ++c) s += dlogp[m * ldg + c];
+    for (int c = 0; c < classes; ++c) st_any(dlogits, g_dtype, m * ldd + c, dlogp[m * ldg + c] - expf(logp[m * ldp + c]) * s);
+    for (long long c = classes; c < ldd; ++c) st_any(dlogits, g_dtype, m * ldd + c, 0.f);
+  }
+}
+
 // ---------------------------------------------------------------- 2-D copy / add with leading dimensions
 __global__ void __launch_bounds__(kThreads) copy2d_kernel(const void* src, int src_dtype, long long ld_src, void* dst,
                                                           int dst_dtype, long long ld_dst, long long rows, long long cols,
@@ -333,6 +346,18 @@ int mvae_logsoftmax_nll(const mvae_logsoftmax_nll_args* p, void* stream) {
   a.dlogits = p->dlogits; a.g_dtype = p->grad_dtype; a.ldd = p->ld_dlogits;
   MVAE_REQUIRE(a.dlogits == nullptr || a.ldd >= a.classes, "logsoftmax_nll: ld_dlogits < classes");
   logsoftmax_nll_kernel<<<grid_for(a.rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return 0;
+}
+
+int mvae_logsoftmax_backward(const float* logp, int64_t ld_logp, const float* dlogp, int64_t ld_dlogp, int64_t rows, int classes,
+                            int grad_dtype, void* dlogits, int64_t ld_dlogits, void* stream) {
+  MVAE_REQUIRE(logp != nullptr && dlogp != nullptr && dlogits != nullptr, "logsoftmax_backward: null tensor");
+  MVAE_REQUIRE(rows > 0 && classes > 0 && ld_logp >= classes && ld_dlogp >= classes && ld_dlogits >= classes,
+               "logsoftmax_backward: bad shape");
+  logsoftmax_bwd_kernel<<<grid_for(rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(logp, ld_logp, dlogp, ld_dlogp, rows,
+                                                                                          classes, dlogits, grad_dtype, ld_dlogits);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
   return 0;

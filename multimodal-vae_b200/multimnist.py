@@ -340,7 +340,36 @@ class MultimodalVAE(ConvMVAEBase):
         # both GRU layers start from h = z2h(z)
         _ops.copy_2d(ws.carry[0], 0, H, ws.dhinit, 0, ldH, M3, H, src2=ws.carry[1], ld_src2=H)
         self.linear_bwd(ws.z, ws.ld_z, ws.dhinit, ldH, M3, "text_decoder.z2h", H, n, dx=ws.dz, lddx=n, accumulate_dx=True)
-        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_txt else None)
+        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_txt else None, *getattr(ws, "upstream", (None, None)))
+
+    def module_outputs(self, ws):
+        B, n = ws.B, self.n_latents
+        return (ws.probs_image.view(B, 1, 50, 50).clone(), ws.words.view(B, MAX_LEN, N_CHARS).clone(),
+                ws.mu.view(1, B, n)[0].clone(), ws.logvar.view(1, B, n)[0].clone())
+
+    def module_backward(self, ws, g_image, g_text, g_mu, g_logvar) -> None:
+        """Backward from the gradients of (image_recon probs, text_recon log-probs, mu, logvar): the reference's
+        loss.backward() (multimnist/train.py:168) when the loss was built by the caller from forward()'s outputs."""
+        B = ws.B
+        npx = self.n_pixels
+        if g_image is None:
+            ws.logits.zero_()
+        else:
+            _ops.sigmoid_bce(ws.logits, npx, B, npx, dprobs=g_image.reshape(B, npx), ld_dprobs=npx, dlogits=ws.logits, ld_dlogits=npx)
+        if g_text is None:
+            ws.dlog_all.zero_()
+        else:
+            g_text = g_text.reshape(B, MAX_LEN * N_CHARS)
+            for t in range(MAX_LEN):
+                _ops.logsoftmax_backward(ws.words, t * N_CHARS, MAX_LEN * N_CHARS, g_text, t * N_CHARS, MAX_LEN * N_CHARS, B, N_CHARS,
+                                         ws.dlog[t], ws.ld_dlog)
+        if g_mu is not None and g_logvar is None:
+            g_logvar = torch.zeros_like(g_mu)
+        if g_logvar is not None and g_mu is None:
+            g_mu = torch.zeros_like(g_logvar)
+        ws.upstream = (g_mu, g_logvar)
+        self.backward_decoders(ws)
+        self.backward_encoders(ws)
 
     def backward_encoders(self, ws) -> None:
         B, n, R = ws.B, self.n_latents, ws.R
@@ -386,11 +415,13 @@ class MultimodalVAE(ConvMVAEBase):
         assert image is not None or text is not None
         t = _lib.TERM_JOINT if (image is not None and text is not None) else (_lib.TERM_IMAGE if image is not None else _lib.TERM_TEXT)
         B = (image if image is not None else text).shape[0]
-        ws = self.workspace(B, 1)
-        image = None if image is None else image.to(self.device, torch.float32).contiguous()
+        image = None if image is None else image.detach().to(self.device, torch.float32).contiguous()
         text = None if text is None else text.to(self.device, torch.int64).contiguous()
         if eps is not None:
             eps = eps.to(self.device, torch.float32).contiguous()
+        if self.training and torch.is_grad_enabled():
+            return self._autograd_forward(image, text, t, eps)
+        ws = self.workspace(B, 1)
         self.run_forward(ws, image, text, (t,), eps, self.training, ((0.0, 0.0),), (0.0,), True, False)
         n = self.n_latents
         return (ws.probs_image.view(B, 1, 50, 50).clone(), ws.words.view(B, MAX_LEN, N_CHARS).clone(),
@@ -439,3 +470,16 @@ class MultiMNISTTrainer(ConvMVAETrainer):
             k = float(acc[2, g])
             out.append((x + y + k, x, y, k))
         return out
+
+
+def loss_function(mu, logvar, recon_image=None, image=None, recon_text=None, text=None, kl_lambda=1e-3, lambda_xy=1.0,
+                  lambda_yx=1.0):
+    """multimnist/train.py:69-87 on the module outputs, differentiable, through the library's loss kernels."""
+    from .functional import _ElboFn
+    B = mu.shape[0]
+    total = _ElboFn.apply(mu, logvar, recon_image, image, None, None, float(lambda_xy), 0.0, float(kl_lambda) / B)
+    if recon_text is not None and text is not None:
+        rt = recon_text.reshape(-1, recon_text.shape[-1])
+        z = torch.zeros(rt.shape[0], 1, device=mu.device)
+        total = total + _ElboFn.apply(z, z, None, None, rt, text.reshape(-1), 0.0, float(lambda_yx), 0.0)
+    return total

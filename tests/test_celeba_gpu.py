@@ -365,3 +365,40 @@ def test_bf16_training_curve_tracks_fp32_oracle():
     assert ref_curve[-1] < ref_curve[0] - 0.05, ref_curve          # it does train
     rel_err = np.abs(dev_curve - ref_curve) / np.abs(ref_curve)
     assert rel_err.max() < 0.01, (rel_err, dev_curve, ref_curve)
+
+
+def test_reference_training_loop_with_autograd():
+    """The reference's own loop (celeba/train.py:138-152): three vae(...) calls, three loss_function calls, loss.backward(),
+    through the module surface with autograd; gradients against the oracle, then one torch.optim.Adam step."""
+    import celeba_oracle as O
+    from mvae_b200.celeba import MultimodalVAE, loss_function
+    n, B, seed = 16, 8, 2
+    state = O.init_state(n, seed=1234 + seed)
+    image, attrs, noises = O.synthetic_batch(B, n, seed)
+    ref_losses, ref_grads, ref_bufs, _ = O.train_step(state, image, attrs, noises)
+    vae = MultimodalVAE(n_latents=n, precision="tf32", dropout_p=0.0)
+    vae.load_state_dict(state)
+    vae.train()
+    opt = torch.optim.Adam(vae.parameters(), lr=1e-3)
+    vae.zero_grad()
+    img, att = image.cuda(), attrs.cuda()
+    r1 = vae(image=img, attrs=att, eps=noises[0])
+    r2 = vae(image=img, eps=noises[1])
+    r3 = vae(attrs=att, eps=noises[2])
+    losses = [loss_function(r[2], r[3], recon_x=r[0], x=img, recon_y=r[1], y=att) for r in (r1, r2, r3)]
+    for a, b in zip(losses, ref_losses):
+        assert abs(float(a.detach()) - b) <= 1e-3 * abs(b)
+    (losses[0] + losses[1] + losses[2]).backward()
+    dg = vae.grads_reference()
+    for k, v in ref_grads.items():
+        if float(v.abs().max()) < 1e-7:
+            continue
+        assert rel(dg[k], v) < 4e-3, (k, rel(dg[k], v))
+    sd = vae.state_dict()
+    assert int(sd["image_encoder.features.3.num_batches_tracked"]) == 2 and int(sd["attrs_decoder.net.1.num_batches_tracked"]) == 3
+    for k, v in ref_bufs.items():
+        if not k.endswith("num_batches_tracked"):
+            assert rel(sd[k], v) < 5e-3, k
+    before = vae.flat_params.clone()
+    opt.step()
+    assert float((vae.flat_params - before).abs().max()) > 1e-4       # torch.optim updates the flat leaf in place

@@ -304,3 +304,30 @@ def test_weak_supervision_term_subsets():
                 assert float(dg[k].abs().max()) < 1e-5, (terms, k)
             else:
                 assert rel(dg[k], gr) < 6e-3, (terms, k, rel(dg[k], gr))
+
+
+def test_reference_training_loop_with_autograd():
+    """multimnist/train.py:148-168 through the module surface with autograd: three vae(...) calls, three loss_function
+    calls with the reference's lambdas, loss.backward(); gradients against the oracle."""
+    import multimnist_oracle as O
+    from mvae_b200.multimnist import MultimodalVAE, loss_function
+    n, B, seed = 16, 8, 2
+    state = O.init_state(n, seed=1234 + seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    ref_losses, ref_grads, _, _ = O.train_step(state, image, text, noises)
+    vae = MultimodalVAE(n_latents=n, precision="tf32", dropout_p=0.0)
+    vae.load_state_dict(state)
+    vae.train()
+    vae.zero_grad()
+    img, txt = image.cuda(), text.cuda()
+    outs = (vae(image=img, text=txt, eps=noises[0]), vae(image=img, eps=noises[1]), vae(text=txt, eps=noises[2]))
+    losses = [loss_function(r[2], r[3], recon_image=r[0], image=img, recon_text=r[1], text=txt, kl_lambda=O.KL_LAMBDA,
+                            lambda_xy=l[0], lambda_yx=l[1]) for r, l in zip(outs, O.LAMBDAS)]
+    for a, b in zip(losses, ref_losses):
+        assert abs(float(a.detach()) - b) <= 1e-3 * abs(b)
+    (losses[0] + losses[1] + losses[2]).backward()
+    dg = vae.grads_reference()
+    for k, v in ref_grads.items():
+        if float(v.abs().max()) < 1e-7:
+            continue
+        assert rel(dg[k], v) < 6e-3, (k, rel(dg[k], v))
