@@ -554,7 +554,13 @@ class _ConvForwardFn(torch.autograd.Function):
         def c(t):
             return None if t is None else t.to(torch.float32).contiguous()
 
-        grads = torch.zeros_like(m.flat_params)
+        g = m.param.grad
+        if g is not None and g.data_ptr() == m.flat_grads.data_ptr():
+            # param.grad IS the library's flat gradient buffer (model.zero_grad()): every kernel accumulates (+=) into it
+            # directly - autograd's AccumulateGrad would otherwise replace the aliased tensor by an out-of-place sum
+            m.module_backward(ws, c(g_image), c(g_other), c(g_mu), c(g_logvar))
+            return None, None, None, None, None, None
+        grads = torch.zeros_like(m.flat_params)     # e.g. after optimizer.zero_grad(set_to_none=True)
         saved = m.flat_grads
         m.flat_grads = grads
         try:

@@ -402,3 +402,26 @@ def test_reference_training_loop_with_autograd():
     before = vae.flat_params.clone()
     opt.step()
     assert float((vae.flat_params - before).abs().max()) > 1e-4       # torch.optim updates the flat leaf in place
+
+
+def test_autograd_with_optimizer_zero_grad_set_to_none():
+    """optimizer.zero_grad() (set_to_none) detaches param.grad from the library's buffer: autograd then delivers the gradient."""
+    import celeba_oracle as O
+    from mvae_b200.celeba import MultimodalVAE, loss_function
+    n, B = 16, 4
+    state = O.init_state(n, seed=7)
+    image, attrs, noises = O.synthetic_batch(B, n, 3)
+    vae = MultimodalVAE(n_latents=n, precision="tf32", dropout_p=0.0)
+    vae.load_state_dict(state)
+    opt = torch.optim.SGD(vae.parameters(), lr=0.1)
+    opt.zero_grad()
+    ri, ra, mu, lv = vae(image=image.cuda(), attrs=attrs.cuda(), eps=noises[0])
+    loss_function(mu, lv, recon_x=ri, x=image.cuda(), recon_y=ra, y=attrs.cuda()).backward()
+    g = vae.param.grad
+    assert g is not None and g.data_ptr() != vae.flat_grads.data_ptr() and float(g.abs().sum()) > 0
+    work = {k: (v.clone() if O.is_buffer(k) else v.clone().requires_grad_(True)) for k, v in state.items()}
+    r = O.forward(work, image, attrs, noises[0], work, True)
+    O.loss_function(r[2], r[3], r[0], image, r[1], attrs).backward()
+    key = "image_decoder.hallucinate.0.weight"
+    l = vae.layouts[key]
+    assert rel(l.to_reference(g[l.offset:l.offset + l.numel]), work[key].grad) < 4e-3
