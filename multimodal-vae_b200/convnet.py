@@ -483,6 +483,7 @@ class ConvMVAEBase:
             la.expert_a, la.ld_a = enc_a.data_ptr(), 2 * n
         if enc_b is not None:
             la.expert_b, la.ld_b = enc_b.data_ptr(), 2 * n
+        ws.keep_eps = eps                          # the backward re-reads the noise through this raw pointer
         la.eps = None if eps is None else eps.data_ptr()
         la.seed, la.step_counter = self.noise_seed, self._step_counter.data_ptr()
         la.training = 1 if training else 0
