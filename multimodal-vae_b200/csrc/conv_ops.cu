@@ -351,7 +351,35 @@ __global__ void __launch_bounds__(kThreads) col_reduce_kernel(const RedArgs a) {
       }
     }
     const uint32_t step = (kMode == RED_ACT_BWD && a.step_ptr != nullptr) ? static_cast<uint32_t>(*a.step_ptr) : 0u;
-    for (long long r = r0 + ty; r < r1; r += TY) {
+    long long r = r0 + ty;
+    if (kMode != RED_ACT_BWD) {
+      // four rows in flight per thread (the loads of a batch are issued before any of its math)
+      constexpr int U = 4;
+      for (; r + static_cast<long long>(U - 1) * TY < r1; r += static_cast<long long>(U) * TY) {
+        float v[U][N], d[U][N];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ldv(x + (r + static_cast<long long>(u) * TY) * a.C + c, v[u]);
+          if (kMode == RED_BN_BWD) ldv(dy + (r + static_cast<long long>(u) * TY) * a.C + c, d[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            if (kMode == RED_STATS) {
+              acc0[j] += v[u][j];
+              acc1[j] += v[u][j] * v[u][j];
+            } else {
+              const float uu = fmaf(sc[j], v[u][j], sh[j]);
+              const float dh = d[u][j] * act_grad(a.act, uu);
+              acc0[j] += dh;
+              acc1[j] += dh * (v[u][j] - mu[j]) * rs[j];
+            }
+          }
+        }
+      }
+    }
+    for (; r < r1; r += TY) {
       float v[N];
       ldv(x + r * a.C + c, v);
       if (kMode == RED_STATS) {
@@ -530,8 +558,25 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const BnArgs a) {
   const long long total = a.rows * CV;
   const T* x = static_cast<const T*>(a.x);
   T* y = static_cast<T*>(a.y);
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  constexpr int U = 4;   // vectors in flight per thread
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    float v[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) ldv(x + (i + u * stride) * N, v[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      const int cv = static_cast<int>(ii % CV);
+      const int g = static_cast<int>((ii / CV) / a.rows_per_group);
+      const int t = g * a.C + cv * N;
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[u][j] = act_fwd(a.act, fmaf(s_scale[t + j], v[u][j], s_shift[t + j]));
+      stv(y + ii * N, v[u]);
+    }
+  }
+  for (; i < total; i += stride) {
     const int cv = static_cast<int>(i % CV);
     const long long r = i / CV;
     const int g = static_cast<int>(r / a.rows_per_group);
@@ -583,8 +628,32 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const BnArgs a) {
   const T* x = static_cast<const T*>(a.x);
   const T* dy = static_cast<const T*>(a.dy);
   T* dx = static_cast<T*>(a.dx);
-  for (long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreads) {
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  constexpr int U = 2;   // (x, dy) vector pairs in flight per thread
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    float v[U][N], d[U][N];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ldv(x + (i + u * stride) * N, v[u]);
+      ldv(dy + (i + u * stride) * N, d[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      const int cv = static_cast<int>(ii % CV);
+      const int g = static_cast<int>((ii / CV) / a.rows_per_group);
+      const int t = g * a.C + cv * N;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float uu = fmaf(s_scale[t + j], v[u][j], s_shift[t + j]);
+        const float dh = d[u][j] * act_grad(a.act, uu);
+        d[u][j] = s_scale[t + j] * (dh - s_c0[t + j] - (v[u][j] - s_mean[t + j]) * s_c1[t + j]);
+      }
+      stv(dx + ii * N, d[u]);
+    }
+  }
+  for (; i < total; i += stride) {
     const int cv = static_cast<int>(i % CV);
     const long long r = i / CV;
     const int g = static_cast<int>(r / a.rows_per_group);
