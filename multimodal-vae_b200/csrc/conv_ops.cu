@@ -44,17 +44,6 @@ inline int grid_for(long long items, int per_sm = 8) {
   return static_cast<int>(b);
 }
 
-// grid of the BatchNorm apply kernels: y = column-vector tiles, x = row slabs (about 8 blocks per SM, >= 8 rows per thread)
-inline dim3 bn_grid(long long rows, int CV) {
-  const int TX = std::min(CV, kThreads), TY = kThreads / TX;
-  const int gy = (CV + TX - 1) / TX;
-  long long gx = (8ll * sm_count_()) / gy;
-  const long long max_gx = (rows + static_cast<long long>(TY) * 8 - 1) / (static_cast<long long>(TY) * 8);
-  if (gx > max_gx) gx = max_gx;
-  if (gx < 1) gx = 1;
-  return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy), 1);
-}
-
 template <typename T>
 struct V16 {
   static constexpr int N = 16 / sizeof(T);
@@ -509,175 +498,176 @@ struct BnArgs {
   float* dgamma; float* dbeta;
 };
 
-// Thread (tx, ty) owns column vector blockIdx.y*TX + tx for the rows r0 + ty, + TY, ... of its block's slab: the
-// per-(group, channel) coefficients live in registers, no index arithmetic per element, four rows in flight.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const BnArgs a) {
   constexpr int N = V16<T>::N;
-  const int CV = a.C / N;
-  const int TX = min(CV, kThreads), TY = kThreads / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int cv = blockIdx.y * TX + tx;
-  if (ty >= TY || cv >= CV) return;
-  const int c = cv * N;
-  const long long slab = (a.rows + gridDim.x - 1) / gridDim.x;
-  const long long r0 = blockIdx.x * slab, r1 = min(a.rows, r0 + slab);
-  const bool finalise = blockIdx.x == 0 && ty == 0;
-  const T* x = static_cast<const T*>(a.x);
-  T* y = static_cast<T*>(a.y);
-  float ga[N], be[N], rm[N], rv[N];
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    ga[j] = a.gamma[c + j];
-    be[j] = a.beta[c + j];
-    rm[j] = a.running_mean != nullptr ? a.running_mean[c + j] : 0.f;
-    rv[j] = a.running_var != nullptr ? a.running_var[c + j] : 1.f;
-  }
-  for (int g = 0; g < a.groups; ++g) {
-    const long long g0 = g * a.rows_per_group, g1 = min(a.rows, g0 + a.rows_per_group);
-    const long long lo = max(r0, g0), hi = min(r1, g1);
-    if (lo >= hi && !finalise) continue;
-    float sc[N], sh[N];
+  extern __shared__ float s_tab[];  // [groups*C] scale | [groups*C] shift
+  const int GC = a.groups * a.C;
+  float* s_scale = s_tab;
+  float* s_shift = s_tab + GC;
+  for (int i = threadIdx.x; i < GC; i += kThreads) {
+    const int g = i / a.C, c = i - g * a.C;
+    float mean, rstd;
     if (a.training) {
-      const float cnt = static_cast<float>(g1 - g0);
-      const float inv = 1.f / cnt;
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        const float mean = a.sum[g * a.C + c + j] * inv;
-        const float var = fmaxf(a.sumsq[g * a.C + c + j] * inv - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + a.eps);
-        sc[j] = ga[j] * rstd;
-        sh[j] = fmaf(-mean, sc[j], be[j]);
-        if (finalise) {
-          if (a.save_mean != nullptr) {
-            a.save_mean[g * a.C + c + j] = mean;
-            a.save_rstd[g * a.C + c + j] = rstd;
-          }
+      const long long g0 = g * a.rows_per_group;
+      const long long cnt = min(a.rows, g0 + a.rows_per_group) - g0;
+      const float inv = 1.f / static_cast<float>(cnt);
+      mean = a.sum[i] * inv;
+      const float var = fmaxf(a.sumsq[i] * inv - mean * mean, 0.f);
+      rstd = rsqrtf(var + a.eps);
+      if (blockIdx.x == 0) {
+        if (a.save_mean != nullptr) {
+          a.save_mean[i] = mean;
+          a.save_rstd[i] = rstd;
+        }
+        if (a.running_mean != nullptr) {
           // groups are separate forward passes of the reference (one per ELBO term), applied in order
-          const float unb = cnt > 1.f ? var * (cnt / (cnt - 1.f)) : var;
-          for (int u = 0; u < a.updates; ++u) {
-            rm[j] = (1.f - a.momentum) * rm[j] + a.momentum * mean;
-            rv[j] = (1.f - a.momentum) * rv[j] + a.momentum * unb;
+          const float unb = cnt > 1 ? var * (static_cast<float>(cnt) / static_cast<float>(cnt - 1)) : var;
+          if (g == 0) {
+            float rm = a.running_mean[c], rv = a.running_var[c];
+            for (int gg = 0; gg < a.groups; ++gg) {
+              float m2 = mean, u2 = unb;
+              if (gg > 0) {
+                const long long h0 = gg * a.rows_per_group;
+                const long long cn = min(a.rows, h0 + a.rows_per_group) - h0;
+                const float iv = 1.f / static_cast<float>(cn);
+                m2 = a.sum[gg * a.C + c] * iv;
+                const float v2 = fmaxf(a.sumsq[gg * a.C + c] * iv - m2 * m2, 0.f);
+                u2 = cn > 1 ? v2 * (static_cast<float>(cn) / static_cast<float>(cn - 1)) : v2;
+              }
+              for (int u = 0; u < a.updates; ++u) {
+                rm = (1.f - a.momentum) * rm + a.momentum * m2;
+                rv = (1.f - a.momentum) * rv + a.momentum * u2;
+              }
+            }
+            a.running_mean[c] = rm;
+            a.running_var[c] = rv;
           }
         }
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        sc[j] = ga[j] * rsqrtf(rv[j] + a.eps);
-        sh[j] = fmaf(-rm[j], sc[j], be[j]);
-      }
+      mean = a.running_mean[c];
+      rstd = rsqrtf(a.running_var[c] + a.eps);
     }
-    constexpr int U = 4;
-    long long r = lo + ty;
-    for (; r + static_cast<long long>(U - 1) * TY < hi; r += static_cast<long long>(U) * TY) {
-      float v[U][N];
+    const float sc = a.gamma[c] * rstd;
+    s_scale[i] = sc;
+    s_shift[i] = fmaf(-mean, sc, a.beta[c]);
+  }
+  __syncthreads();
+  const int CV = a.C / N;
+  const long long total = a.rows * CV;
+  const T* x = static_cast<const T*>(a.x);
+  T* y = static_cast<T*>(a.y);
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  constexpr int U = 4;   // vectors in flight per thread
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    float v[U][N];
 #pragma unroll
-      for (int u = 0; u < U; ++u) ldv(x + (r + static_cast<long long>(u) * TY) * a.C + c, v[u]);
+    for (int u = 0; u < U; ++u) ldv(x + (i + u * stride) * N, v[u]);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      const int cv = static_cast<int>(ii % CV);
+      const int g = static_cast<int>((ii / CV) / a.rows_per_group);
+      const int t = g * a.C + cv * N;
 #pragma unroll
-        for (int j = 0; j < N; ++j) v[u][j] = act_fwd(a.act, fmaf(sc[j], v[u][j], sh[j]));
-        stv(y + (r + static_cast<long long>(u) * TY) * a.C + c, v[u]);
-      }
-    }
-    for (; r < hi; r += TY) {
-      float v[N];
-      ldv(x + r * a.C + c, v);
-#pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = act_fwd(a.act, fmaf(sc[j], v[j], sh[j]));
-      stv(y + r * a.C + c, v);
+      for (int j = 0; j < N; ++j) v[u][j] = act_fwd(a.act, fmaf(s_scale[t + j], v[u][j], s_shift[t + j]));
+      stv(y + ii * N, v[u]);
     }
   }
-  if (finalise && a.training && a.running_mean != nullptr) {
+  for (; i < total; i += stride) {
+    const int cv = static_cast<int>(i % CV);
+    const long long r = i / CV;
+    const int g = static_cast<int>(r / a.rows_per_group);
+    const int t = g * a.C + cv * N;
+    float v[N];
+    ldv(x + i * N, v);
 #pragma unroll
-    for (int j = 0; j < N; ++j) {
-      a.running_mean[c + j] = rm[j];
-      a.running_var[c + j] = rv[j];
-    }
+    for (int j = 0; j < N; ++j) v[j] = act_fwd(a.act, fmaf(s_scale[t + j], v[j], s_shift[t + j]));
+    stv(y + i * N, v);
   }
 }
 
-// dx = gamma*rstd * (dyhat - S0/cnt - xhat*S1/cnt), dyhat = dy * act'(gamma*xhat + beta); same thread layout as the forward
+// dx = gamma*rstd * (dyhat - S0/cnt - xhat*S1/cnt), dyhat = dy * act'(gamma*xhat + beta)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const BnArgs a) {
   constexpr int N = V16<T>::N;
+  extern __shared__ float s_tab[];  // scale | shift | c0 | c1 (multiplies x - mean) | mean
+  const int GC = a.groups * a.C;
+  float* s_scale = s_tab;
+  float* s_shift = s_tab + GC;
+  float* s_c0 = s_tab + 2 * GC;
+  float* s_c1 = s_tab + 3 * GC;
+  float* s_mean = s_tab + 4 * GC;
+  for (int i = threadIdx.x; i < GC; i += kThreads) {
+    const int g = i / a.C, c = i - g * a.C;
+    const long long g0 = g * a.rows_per_group;
+    const long long cnt = min(a.rows, g0 + a.rows_per_group) - g0;
+    const float inv = 1.f / static_cast<float>(cnt);
+    const float mean = a.save_mean[i], rstd = a.save_rstd[i];
+    const float sc = a.gamma[c] * rstd;
+    s_scale[i] = sc;
+    s_shift[i] = fmaf(-mean, sc, a.beta[c]);
+    s_c0[i] = a.s0[i] * inv;
+    s_c1[i] = a.s1[i] * inv * rstd;   // multiplies (x - mean): xhat * S1/cnt
+    s_mean[i] = mean;
+    if (blockIdx.x == 0 && g == 0 && a.dgamma != nullptr) {
+      float dg = 0.f, db = 0.f;
+      for (int gg = 0; gg < a.groups; ++gg) {
+        dg += a.s1[gg * a.C + c];
+        db += a.s0[gg * a.C + c];
+      }
+      a.dgamma[c] += dg;
+      a.dbeta[c] += db;
+    }
+  }
+  __syncthreads();
   const int CV = a.C / N;
-  const int TX = min(CV, kThreads), TY = kThreads / TX;
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const int cv = blockIdx.y * TX + tx;
-  if (ty >= TY || cv >= CV) return;
-  const int c = cv * N;
-  const long long slab = (a.rows + gridDim.x - 1) / gridDim.x;
-  const long long r0 = blockIdx.x * slab, r1 = min(a.rows, r0 + slab);
-  const bool finalise = blockIdx.x == 0 && ty == 0 && a.dgamma != nullptr;
+  const long long total = a.rows * CV;
   const T* x = static_cast<const T*>(a.x);
   const T* dy = static_cast<const T*>(a.dy);
   T* dx = static_cast<T*>(a.dx);
-  float ga[N], be[N], dg[N], db[N];
+  const long long stride = static_cast<long long>(gridDim.x) * kThreads;
+  long long i = blockIdx.x * static_cast<long long>(kThreads) + threadIdx.x;
+  constexpr int U = 2;   // (x, dy) vector pairs in flight per thread
+  for (; i + (U - 1) * stride < total; i += U * stride) {
+    float v[U][N], d[U][N];
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    ga[j] = a.gamma[c + j];
-    be[j] = a.beta[c + j];
-    dg[j] = db[j] = 0.f;
-  }
-  for (int g = 0; g < a.groups; ++g) {
-    const long long g0 = g * a.rows_per_group, g1 = min(a.rows, g0 + a.rows_per_group);
-    const long long lo = max(r0, g0), hi = min(r1, g1);
-    if (lo >= hi && !finalise) continue;
-    const float inv = 1.f / static_cast<float>(g1 - g0);
-    float sc[N], sh[N], c0[N], c1[N], mu[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      const float mean = a.save_mean[g * a.C + c + j], rstd = a.save_rstd[g * a.C + c + j];
-      const float s0 = a.s0[g * a.C + c + j], s1 = a.s1[g * a.C + c + j];
-      sc[j] = ga[j] * rstd;
-      sh[j] = fmaf(-mean, sc[j], be[j]);
-      c0[j] = s0 * inv;
-      c1[j] = s1 * inv * rstd;   // multiplies (x - mean): xhat * S1/cnt = (x - mean) * rstd * S1/cnt
-      mu[j] = mean;
-      dg[j] += s1;
-      db[j] += s0;
+    for (int u = 0; u < U; ++u) {
+      ldv(x + (i + u * stride) * N, v[u]);
+      ldv(dy + (i + u * stride) * N, d[u]);
     }
-    constexpr int U = 2;
-    long long r = lo + ty;
-    for (; r + static_cast<long long>(U - 1) * TY < hi; r += static_cast<long long>(U) * TY) {
-      float v[U][N], d[U][N];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        ldv(x + (r + static_cast<long long>(u) * TY) * a.C + c, v[u]);
-        ldv(dy + (r + static_cast<long long>(u) * TY) * a.C + c, d[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-          const float uu = fmaf(sc[j], v[u][j], sh[j]);
-          const float dh = d[u][j] * act_grad(a.act, uu);
-          d[u][j] = sc[j] * (dh - c0[j] - (v[u][j] - mu[j]) * c1[j]);
-        }
-        stv(dx + (r + static_cast<long long>(u) * TY) * a.C + c, d[u]);
-      }
-    }
-    for (; r < hi; r += TY) {
-      float v[N], d[N];
-      ldv(x + r * a.C + c, v);
-      ldv(dy + r * a.C + c, d);
+    for (int u = 0; u < U; ++u) {
+      const long long ii = i + u * stride;
+      const int cv = static_cast<int>(ii % CV);
+      const int g = static_cast<int>((ii / CV) / a.rows_per_group);
+      const int t = g * a.C + cv * N;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        const float uu = fmaf(sc[j], v[j], sh[j]);
-        const float dh = d[j] * act_grad(a.act, uu);
-        d[j] = sc[j] * (dh - c0[j] - (v[j] - mu[j]) * c1[j]);
+        const float uu = fmaf(s_scale[t + j], v[u][j], s_shift[t + j]);
+        const float dh = d[u][j] * act_grad(a.act, uu);
+        d[u][j] = s_scale[t + j] * (dh - s_c0[t + j] - (v[u][j] - s_mean[t + j]) * s_c1[t + j]);
       }
-      stv(dx + r * a.C + c, d);
+      stv(dx + ii * N, d[u]);
     }
   }
-  if (finalise) {
+  for (; i < total; i += stride) {
+    const int cv = static_cast<int>(i % CV);
+    const long long r = i / CV;
+    const int g = static_cast<int>(r / a.rows_per_group);
+    const int t = g * a.C + cv * N;
+    float v[N], d[N];
+    ldv(x + i * N, v);
+    ldv(dy + i * N, d);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-      a.dgamma[c + j] += dg[j];
-      a.dbeta[c + j] += db[j];
+      const float u = fmaf(s_scale[t + j], v[j], s_shift[t + j]);
+      const float dh = d[j] * act_grad(a.act, u);
+      d[j] = s_scale[t + j] * (dh - s_c0[t + j] - (v[j] - s_mean[t + j]) * s_c1[t + j]);
     }
+    stv(dx + i * N, d);
   }
 }
 
@@ -1142,9 +1132,15 @@ int mvae_bn_act_forward(const mvae_bn_act_args* p, void* stream) {
     MVAE_REQUIRE(p->running_mean != nullptr && p->running_var != nullptr, "bn_act_forward: eval mode needs running statistics");
   }
   const int vec = p->dtype == MVAE_F32 ? 4 : 8;
-  const dim3 grid = bn_grid(b.rows, b.C / vec);
-  if (p->dtype == MVAE_F32) bn_act_fwd_kernel<float><<<grid, kThreads, 0, st>>>(b);
-  else bn_act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(b);
+  const int blocks = grid_for(b.rows * (b.C / vec), 4);
+  const size_t smem = 2 * gc * sizeof(float);
+  MVAE_REQUIRE(smem <= 200 * 1024, "bn_act_forward: groups * channels = %zu too large for the coefficient table", gc);
+  if (smem > 48 * 1024) {
+    MVAE_CUDA(cudaFuncSetAttribute(bn_act_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(bn_act_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  if (p->dtype == MVAE_F32) bn_act_fwd_kernel<float><<<blocks, kThreads, smem, st>>>(b);
+  else bn_act_fwd_kernel<__nv_bfloat16><<<blocks, kThreads, smem, st>>>(b);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
   return 0;
@@ -1168,9 +1164,15 @@ int mvae_bn_act_backward(const mvae_bn_act_args* p, void* stream) {
   b.x = p->x; b.dy = p->dy; b.dx = p->dx; b.s0 = p->s0; b.s1 = p->s1;
   b.dgamma = p->dgamma; b.dbeta = p->dbeta;
   const int vec = p->dtype == MVAE_F32 ? 4 : 8;
-  const dim3 grid = bn_grid(b.rows, b.C / vec);
-  if (p->dtype == MVAE_F32) bn_act_bwd_kernel<float><<<grid, kThreads, 0, st>>>(b);
-  else bn_act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>(b);
+  const int blocks = grid_for(b.rows * (b.C / vec), 4);
+  const size_t smem = 5 * gc * sizeof(float);
+  MVAE_REQUIRE(smem <= 200 * 1024, "bn_act_backward: groups * channels = %zu too large for the coefficient table", gc);
+  if (smem > 48 * 1024) {
+    MVAE_CUDA(cudaFuncSetAttribute(bn_act_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MVAE_CUDA(cudaFuncSetAttribute(bn_act_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  if (p->dtype == MVAE_F32) bn_act_bwd_kernel<float><<<blocks, kThreads, smem, st>>>(b);
+  else bn_act_bwd_kernel<__nv_bfloat16><<<blocks, kThreads, smem, st>>>(b);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
   return 0;
