@@ -48,7 +48,7 @@ __device__ __forceinline__ void store_pair(T* p, float a, float b) {
 // ================================================================= tail forward
 // One warp per (term, sample): lanes own latent pairs.
 template <typename ZT>
-__global__ void __launch_bounds__(kTailThreads) tail_fwd_kernel(const TailArgs a) {
+__global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArgs a) {
   pdl_enter();
   __shared__ float s_stat[kMaxGroups][2][kTD];
   __shared__ float s_kl[kMaxGroups];
