@@ -56,6 +56,8 @@ struct GemmEpilogue {
   float bce_scale[4] = {0, 0, 0, 0};
   float* loss = nullptr;   // [groups]
   void* probs = nullptr;   // optional sigmoid(x) output, same layout/dtype as C
+  int bce_direct = 0;      // EPI_BCE without the bias-gradient column sums (stat0 must be null; the caller reduces dlogits
+                           // itself): every thread owns one accumulator row, no shared-memory staging pass
   // EPI_DGRAD_BN: C = acc * 1[gamma*xhat+beta > 0], xhat = (hpre - mean[g])*rstd[g]
   const void* hpre = nullptr;
   long long ldh = 0;

@@ -46,6 +46,7 @@ struct GemmKParams {
   int b_tx_bytes;     // bytes TMA actually writes per stage for B
   int vec_ok;         // all epilogue tensors allow 4-element vector access
   int direct_store;   // plain STORE epilogue without statistics: TMEM -> registers -> global, no staging pass
+  int direct_bce;     // BCE epilogue, one accumulator row per thread (no staging, no column sums)
   int aux_off;        // byte offset (dynamic smem) of the prefetched auxiliary tile, or -1
   int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
@@ -616,6 +617,121 @@ __global__ void __launch_bounds__(kGemmThreads)
       }
     }
   }
+  if constexpr (kEpi == EPI_BCE) {
+    if (p.direct_bce) {
+      // Row-per-thread BCE epilogue: logits = acc + bias straight from TMEM, 16 columns per tcgen05.ld; the thread reads
+      // its row's 16 targets (one 32/64-byte run), writes 16 dlogits, keeps the loss partial in a register.  No staging
+      // tile, no auxiliary tile, no column sums (the bias gradient is a separate reduction over dlogits).
+      stored_directly = true;
+      float* s_bias = reinterpret_cast<float*>(smem + p.bnco_off);
+      for (int c = threadIdx.x; c < p.block_n; c += kGemmThreads)
+        s_bias[c] = (e.bias != nullptr && n0 + c < p.N) ? e.bias[n0 + c] : 0.f;
+      __syncthreads();
+      const int q = warp & 3;
+      const int row = m0 + q * 32 + lane;
+      const bool valid = row < p.M;
+      const int g = valid ? row / e.rows_per_group : 0;
+      const float g_scale = e.bce_scale[g & 3];
+      const int trow = valid ? row % e.target_rows : 0;
+      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+      const act_t* tptr = reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(trow) * e.ldt;
+      float lsum = 0.f;
+      for (int c = (warp >> 2) * 16; c < p.block_n; c += 32) {
+        uint32_t v[16];
+        ptx::tmem_ld16(t_base + c, v);
+        ptx::tmem_ld_wait();
+        const int cn = n0 + c;
+        if (!valid || cn >= p.N) continue;
+        const bool full = cn + 16 <= p.N;
+        float tg[16], d[16], pr[16];
+        if (full && p.vec_ok) {
+          if constexpr (ESZ == 4) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(tptr + cn + j));
+              tg[j] = t4.x; tg[j + 1] = t4.y; tg[j + 2] = t4.z; tg[j + 3] = t4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(tptr + cn + j));
+              const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                tg[j + 2 * k] = __uint_as_float(w4[k] << 16);
+                tg[j + 2 * k + 1] = __uint_as_float(w4[k] & 0xffff0000u);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) tg[j] = (cn + j < p.N) ? to_f(tptr[cn + j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = __uint_as_float(v[j]) + s_bias[c + j];
+          const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));  // exp(-|x|) in (0, 1]
+          const float dd = 1.f + ex;
+          float inv = fmaf(-0.47058823529f, dd, 1.41176470588f);             // 1/dd: linear seed + 3 Newton steps (FMA pipe)
+          inv = inv * fmaf(-dd, inv, 2.f);
+          inv = inv * fmaf(-dd, inv, 2.f);
+          inv = inv * fmaf(-dd, inv, 2.f);
+          const float pz = x >= 0.f ? inv : ex * inv;
+          pr[j] = pz;
+          d[j] = g_scale * (pz - tg[j]);
+          if (full || cn + j < p.N)
+            lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[j], x, fmaxf(x, 0.f)));
+        }
+        act_t* dst = reinterpret_cast<act_t*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
+        act_t* pdst = e.probs != nullptr ? reinterpret_cast<act_t*>(e.probs) + static_cast<long long>(row) * e.ldc + cn : nullptr;
+        if (full && p.vec_ok) {
+          if constexpr (ESZ == 4) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
+              if (pdst != nullptr)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(pdst) + j) = make_float4(pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
+            }
+          } else {
+            uint32_t w[8], wp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+              const __nv_bfloat162 hp = __floats2bfloat162_rn(pr[2 * j], pr[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&h);
+              wp[j] = *reinterpret_cast<const uint32_t*>(&hp);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+            if (pdst != nullptr) {
+              *reinterpret_cast<uint4*>(pdst) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pdst) + 8) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (cn + j < p.N) {
+              if constexpr (ESZ == 4) reinterpret_cast<float*>(dst)[j] = d[j];
+              else reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(d[j]);
+              if (pdst != nullptr) {
+                if constexpr (ESZ == 4) reinterpret_cast<float*>(pdst)[j] = pr[j];
+                else reinterpret_cast<__nv_bfloat16*>(pdst)[j] = __float2bfloat16_rn(pr[j]);
+              }
+            }
+        }
+      }
+      // per-term loss: every thread belongs to one term; warp-reduce per term, one shared atomic per warp per term
+      lsum *= g_scale;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float vv = (valid && (g & 3) == t) ? lsum : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
+        if (lane == 0 && vv != 0.f) atomicAdd(&s_loss[t], vv);
+      }
+    }
+  }
   if (!stored_directly) {
   {
     const int q = warp & 3;
@@ -937,7 +1053,9 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(!atf_on, "gemm: fused BatchNorm and the A transform are exclusive");
     if (!(e.rows_per_group >= g.M || e.rows_per_group % kBlockM == 0)) return 3;
   }
-  auto bnco_bytes = [&](int bn) -> int { return fuse ? 2 * bn * 4 : 0; };
+  const bool want_direct_bce = e.kind == EPI_BCE && e.bce_direct != 0;
+  if (want_direct_bce) MVAE_REQUIRE(e.stat0 == nullptr, "gemm: the direct BCE epilogue produces no column sums (stat0 must be null)");
+  auto bnco_bytes = [&](int bn) -> int { return fuse ? 2 * bn * 4 : (want_direct_bce ? bn * 4 : 0); };
   int sm_count = 148;
   {
     static int cached = 0;
@@ -951,7 +1069,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
   auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
-  if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz);
+  if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz) && !(e.bce_direct != 0);
   if (e.kind == EPI_DGRAD_BN) aux_ok = aux_ok && (e.ldh % 4 == 0) && al0(e.hpre, 4 * esz);
   auto aux_bytes = [&](int bn) -> int { return aux_ok ? kBlockM * bn * esz : 0; };
   static const int use_red = env_int("MVAE_GEMM_CTA_REDUCE", 1);
@@ -1083,7 +1201,11 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   kp.aux_off = (aux_ok && vec) ? tail0 : -1;
   kp.red_off = red_ok ? tail0 + aux_bytes(block_n) : -1;
   kp.coef_off = atf_on ? tail0 + aux_bytes(block_n) + red_bytes(block_n) : -1;
-  kp.bnco_off = fuse ? tail0 + aux_bytes(block_n) + red_bytes(block_n) + coef_bytes : -1;
+  kp.bnco_off = (fuse || want_direct_bce) ? tail0 + aux_bytes(block_n) + red_bytes(block_n) + coef_bytes : -1;
+  // 16-byte row runs: leading dimensions and bases must be 16-byte multiples, else the staged path runs (still without sums)
+  const bool bce_aligned = (e.ldc * esz) % 16 == 0 && (e.ldt * esz) % 16 == 0 && al(e.C, 16) && al(e.target, 16) && al(e.probs, 16);
+  kp.direct_bce = (want_direct_bce && bce_aligned) ? 1 : 0;
+  if (kp.direct_bce) kp.aux_off = -1;   // targets are read straight from global memory, one row run per thread
   kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");

@@ -598,6 +598,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
+  bool bce_direct = false;
   {
     // last Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70) in one kernel
     GemmDesc g;
@@ -608,7 +609,12 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     g.epi.kind = EPI_BCE;
     g.epi.C = W.at<void>(P.dlog); g.epi.ldc = 784; g.epi.c_dtype = dt;
     g.epi.bias = pf("image_decoder.net.6.bias");
-    g.epi.stat0 = bwd ? gf("image_decoder.net.6.bias") : nullptr;
+    // row-per-thread BCE epilogue (no column sums): the last Linear's bias gradient is then one column reduction over
+    // dlogits on the side stream, off the critical path
+    static const int bce_direct_env = env_int("MVAE_GEMM_DIRECT_BCE", 1);
+    bce_direct = bce_direct_env != 0 && !fuse_dec;
+    g.epi.bce_direct = bce_direct ? 1 : 0;
+    g.epi.stat0 = (bwd && !bce_direct) ? gf("image_decoder.net.6.bias") : nullptr;
     g.epi.rows_per_group = B;
     g.epi.target = a->image; g.epi.ldt = 784; g.epi.target_rows = B;
     for (int t = 0; t < G; ++t) g.epi.bce_scale[t] = a->lambda_image[t] / (static_cast<float>(B) * 784.f);
@@ -617,6 +623,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     if (fwd) MVAE_STEP(launch_gemm(g, st), "gemm_fwd_bce:image_decoder.net.6.weight");
   }
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist
+  if (fwd && bwd && bwd_dec && !module_bwd && bce_direct)
+    if (mvae_col_stats(dt, W.at<void>(P.dlog), R, 784, 784, 0, gf("image_decoder.net.6.bias"), nullptr, s2)) return 1;
   // ================================================================ backward
   if (bwd && bwd_dec) {
     if (module_bwd) {
