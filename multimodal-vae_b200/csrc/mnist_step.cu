@@ -611,7 +611,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     g.epi.bias = pf("image_decoder.net.6.bias");
     // row-per-thread BCE epilogue (no column sums): the last Linear's bias gradient is then one column reduction over
     // dlogits on the side stream, off the critical path
-    static const int bce_direct_env = env_int("MVAE_GEMM_DIRECT_BCE", 1);
+    static const int bce_direct_env = env_int("MVAE_GEMM_DIRECT_BCE", 0);  // measured: kernel 51.1 -> 48.0 us, step 358 -> 396 us
     bce_direct = bce_direct_env != 0 && !fuse_dec;
     g.epi.bce_direct = bce_direct ? 1 : 0;
     g.epi.stat0 = (bwd && !bce_direct) ? gf("image_decoder.net.6.bias") : nullptr;
