@@ -110,3 +110,22 @@ def test_dp_gradient_averaging_gloo_world2():
     out = mgr.dict()
     mp.spawn(_dp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on CPU only (the oracle port) and prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["value"] > 0 and d["vs_baseline"] is None
