@@ -129,3 +129,31 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["value"] > 0 and d["vs_baseline"] is None
+
+
+def test_conv_models_layout_and_no_cpu_fallback():
+    """Host logic of the conv models without a GPU: the reference state_dict layout (keys, shapes, order) matches the
+    oracles', the internal <-> reference layout conversions are exact inverses, and construction fails loudly on CPU."""
+    import pytest
+    import torch
+    import mvae_b200  # noqa: F401
+    from mvae_b200 import celeba, multimnist
+    from mvae_b200.convnet import Layout
+    import celeba_oracle as CO
+    import multimnist_oracle as MO
+    for mod, O in ((celeba, CO), (multimnist, MO)):
+        cls = mod.MultimodalVAE
+        keys = cls.reference_keys(cls.__new__(cls), 100)
+        shapes = O.param_shapes(100)
+        assert [k for k, _, _ in keys] == list(shapes.keys())
+        assert all(tuple(s) == tuple(shapes[k]) for k, s, _ in keys)
+        g = torch.Generator().manual_seed(0)
+        for k, s, kind in keys:
+            if kind in ("rm", "rv", "nbt"):
+                continue
+            l = Layout(k, s, kind, cls.FLAT_C, cls.FLAT_HW)
+            t = torch.randn(s, generator=g)
+            assert torch.equal(l.to_reference(l.to_internal(t).reshape(-1)), t), k
+        if not torch.cuda.is_available():
+            with pytest.raises(Exception):
+                cls(n_latents=16)
