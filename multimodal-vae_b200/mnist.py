@@ -335,6 +335,19 @@ class MVAE(nn.Module):
                             extra={"eval_mode": int(not self.training), "z_in": z.data_ptr()})
         return outs[0], outs[1]
 
+    @torch.no_grad()
+    def decode_losses(self, z, image, text):
+        """Reconstruction losses of latents z against (image, text) in ONE fused launch sequence (decoders + the BCE
+        epilogue + the NLL kernel, no probabilities materialised): returns the device tensor [bce_mean, nll_mean] with
+        the means of F.binary_cross_entropy over B*784 pixels and F.nll_loss over B labels - the inner loop of
+        mnist/loglikelihood.py:46-52."""
+        _, B, x, y = self._prep_inputs(image, text)
+        z = z.to(self.device_, torch.float32).contiguous()
+        self._keep_z = z
+        losses, _ = self._run(x, y, [TERMS["joint"]], [(1.0, 1.0)], [0.0],
+                              extra={"eval_mode": int(not self.training), "z_in": z.data_ptr()})
+        return losses[0, 1:3]
+
     def decode_image(self, x):
         """ImageDecoder (mnist/model.py:120-135): pixel probabilities for latents x."""
         return self._decode(x)[0]
