@@ -452,6 +452,13 @@ __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
 #pragma unroll
       for (int o = 0; o < kTD; ++o) a.logp[row * kTD + o] = lp[o];
     }
+    if (!a.backward && a.fused_loss && a.labels != nullptr && a.ce != nullptr) {
+      // forward-only evaluation (mnist/loglikelihood.py:49-52): the NLL term without any gradient work
+      const int label = static_cast<int>(a.labels[row % a.B]);
+#pragma unroll
+      for (int o = 0; o < kTD; ++o)
+        if (o == label) ce = -a.ce_scale[g] * lp[o];
+    }
     if (a.backward) {
       if (a.fused_loss) {
         const int label = static_cast<int>(a.labels[row % a.B]);
@@ -518,6 +525,16 @@ __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
       atomicAdd(a.s1 + tid, (&s_s1[0][0])[tid]);
     }
     if (tid < a.G && a.ce != nullptr && a.fused_loss) atomicAdd(a.ce + tid, s_ce[tid]);
+  } else if (a.fused_loss && a.labels != nullptr && a.ce != nullptr) {
+    for (int gg = 0; gg < a.G; ++gg) {
+      const bool mine = valid && g == gg;
+      if (__any_sync(0xffffffffu, mine)) {
+        const float c = warp_sum(mine ? ce : 0.f);
+        if (lane == 0) atomicAdd(&s_ce[gg], c);
+      }
+    }
+    __syncthreads();
+    if (tid < a.G) atomicAdd(a.ce + tid, s_ce[tid]);
   }
 }
 
