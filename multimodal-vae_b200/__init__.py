@@ -9,6 +9,6 @@ from .mnist import MVAE, MultimodalVAE, MVAETrainer, HostPipeline, TERMS  # noqa
 
 from .parallel import DataParallelTrainer  # noqa: F401
 from .functional import ProductOfExperts, elbo_loss, loss_function  # noqa: F401
-from . import celeba, multimnist, evaluation  # noqa: F401
+from . import celeba, multimnist, evaluation, checkpoint  # noqa: F401
 
 __all__ = ["MVAE", "MultimodalVAE", "MVAETrainer", "HostPipeline", "DataParallelTrainer", "ProductOfExperts", "elbo_loss", "loss_function", "TERMS", "_lib"]

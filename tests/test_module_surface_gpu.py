@@ -203,3 +203,50 @@ def test_evaluation_entry_points_match_oracle():
             ref_t += float(torch.nn.functional.nll_loss(rt, text, reduction="sum")) / S
     ref_i, ref_t = ref_i / (2 * B), ref_t / (2 * B)
     assert abs(got[0] - ref_i) <= 2e-3 * ref_i and abs(got[1] - ref_t) <= 5e-3 * ref_t, (got, ref_i, ref_t)
+
+
+@pytest.mark.parametrize("family", ["mnist", "celeba", "multimnist"])
+def test_checkpoint_roundtrip_and_resume(family, tmp_path):
+    """mnist/train.py:37-61,212-220: save_checkpoint / load_checkpoint with the reference's dict layout; resuming with the
+    saved optimiser state continues exactly like the uninterrupted run (up to the atomics-order noise of a step)."""
+    import importlib
+    import mvae_b200
+    from mvae_b200 import checkpoint as ck
+    n, B = 16, 16
+    if family == "mnist":
+        import mnist_oracle as O
+        Model, Trainer = mvae_b200.MVAE, mvae_b200.MVAETrainer
+        mk = lambda: Model(n, precision="tf32")
+    else:
+        O = importlib.import_module(family + "_oracle")
+        mod = importlib.import_module("mvae_b200." + family)
+        Model = mod.MultimodalVAE
+        Trainer = mod.CelebATrainer if family == "celeba" else mod.MultiMNISTTrainer
+        mk = lambda: Model(n_latents=n, precision="tf32", dropout_p=0.0)
+    image, other, noises = O.synthetic_batch(B, n, 3)
+    eps = torch.stack(noises).cuda()
+    image, other = image.cuda(), other.cuda()
+
+    def total(tr):
+        if family == "mnist":
+            return float(tr.step(image, other, eps=eps)[0][:, 0].sum())
+        tr.step(image, other, eps=eps)
+        return sum(l[0] for l in tr.losses())
+
+    m1 = mk(); t1 = Trainer(m1)
+    for _ in range(3):
+        total(t1)
+    ck.save_checkpoint({"state_dict": m1.state_dict(), "n_latents": n, "optimizer": ck.trainer_state(t1)}, True, str(tmp_path))
+    assert os.path.exists(os.path.join(str(tmp_path), "model_best.pth.tar"))
+    cont = [total(t1) for _ in range(2)]
+    m2 = ck.load_checkpoint(os.path.join(str(tmp_path), "checkpoint.pth.tar"), family=family, precision="tf32",
+                            **({} if family == "mnist" else {"dropout_p": 0.0}))
+    sd1 = torch.load(os.path.join(str(tmp_path), "checkpoint.pth.tar"), weights_only=False)["state_dict"]
+    sd2 = m2.state_dict()
+    for k in sd1:
+        assert torch.equal(sd1[k].cpu(), sd2[k].cpu()), k
+    t2 = Trainer(m2)
+    ck.load_trainer_state(t2, torch.load(os.path.join(str(tmp_path), "checkpoint.pth.tar"), weights_only=False)["optimizer"])
+    resumed = [total(t2) for _ in range(2)]
+    for a, b in zip(cont, resumed):
+        assert abs(a - b) <= 2e-3 * abs(a), (cont, resumed)
