@@ -1,6 +1,7 @@
 """GPU tests of the reference-facing module surface: ProductOfExperts (+mask), loss_function / elbo_loss,
 MVAE.forward with autograd (the reference's own three-forward training loop), eval mode, sub-calls."""
 import math
+import os
 
 import numpy as np
 import pytest
