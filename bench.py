@@ -332,6 +332,45 @@ def run_device(args):
         for label, ms in run:
             kind = label.split(":")[0].split("#")[0]
             agg[kind] = agg.get(kind, 0.0) + ms / (len(prof_runs) - 1)
+    # per-launch table: algorithmic work of every launch against the roofline that bounds it (tensor peak for the GEMMs,
+    # HBM peak for the streaming kernels), durations = CUDA events around the launch (they include ~4 us launch latency)
+    n_lat, es_ = N_LATENTS, (2 if args.precision == "bf16" else 4)
+    R3 = 3 * B
+    gemm_shapes = {  # (rows, out, in) of the Linear behind each label; fwd / dgrad / wgrad are all 2*rows*out*in FLOP
+        "image_encoder.net.0.weight": (B, 400, 784), "image_encoder.net.3.weight": (B, 200, 400),
+        "image_encoder.net.6.weight": (B, 2 * n_lat, 200), "image_decoder.net.0.weight": (R3, 200, n_lat),
+        "image_decoder.net.3.weight": (R3, 400, 200), "image_decoder.net.6.weight": (R3, 784, 400)}
+    bn_feats = {"image_encoder.net.1.weight": (B, 400), "image_encoder.net.4.weight": (B, 200),
+                "image_decoder.net.1.weight": (R3, 200), "image_decoder.net.4.weight": (R3, 400)}
+    hbm_peak = peaks["hbm_gbs"]
+    tc_peak = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
+    per_launch = []
+    n_runs = len(prof_runs) - 1
+    for j, (label, _) in enumerate(prof_runs[-1]):
+        us = sum(run[j][1] for run in prof_runs[1:]) / n_runs * 1e3
+        kind, _, rest = label.partition(":")
+        name = rest.split("#")[0]
+        row = {"launch": label, "us": round(us, 2)}
+        if kind.startswith("gemm") and name in gemm_shapes:
+            r_, o_, i_ = gemm_shapes[name]
+            fl = 2.0 * r_ * o_ * i_
+            row.update(bound="tensor", gflop=round(fl / 1e9, 3), tflops=round(fl / (us * 1e-6) / 1e12, 1),
+                       frac=round(fl / (us * 1e-6) / 1e12 / tc_peak, 4))
+        elif kind in ("launch_bn_forward", "launch_bn_backward") and name in bn_feats:
+            r_, f_ = bn_feats[name]
+            by = r_ * f_ * es_ * (2 if kind == "launch_bn_forward" else 3)
+            row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1),
+                       frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
+        elif kind == "launch_tail_forward":
+            by = 4096.0 * B
+            row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1), frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
+        elif kind == "launch_tail_backward":
+            by = 3584.0 * B
+            row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1), frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
+        elif kind == "launch_adam":
+            by = 4.0 * 7 * model.flat_params.numel() + (2 * model.flat_params.numel() if args.precision == "bf16" else 0)
+            row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1), frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
+        per_launch.append(row)
     gemm_ms = sum(v for k, v in agg.items() if k.startswith("gemm"))
     gemm_launches = sum(1 for label, _ in prof_runs[-1] if label.startswith("gemm"))
     serial_ms = sum(agg.values())
@@ -389,6 +428,7 @@ def run_device(args):
         "step_roofline": {"t_roof_us": t_roof_us, "t_measured_us": ms_per_step * 1e3,
                           "frac": t_roof_us / (ms_per_step * 1e3),
                           "definition": "SURVEY 8d: F_alg/bf16 burst peak + Q_tail/HBM peak"},
+        "per_launch": per_launch,
         "kernel_ms_per_step_serialised": {k: round(v, 5) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])},
         "serialised_ms_per_step": serial_ms,
     }
