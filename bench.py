@@ -349,6 +349,7 @@ def run_device(args):
     for j, (label, _) in enumerate(prof_runs[-1]):
         us = sum(run[j][1] for run in prof_runs[1:]) / n_runs * 1e3
         kind, _, rest = label.partition(":")
+        kind = kind.split("#")[0]
         name = rest.split("#")[0]
         row = {"launch": label, "us": round(us, 2)}
         if kind.startswith("gemm") and name in gemm_shapes:
