@@ -425,3 +425,16 @@ def test_autograd_with_optimizer_zero_grad_set_to_none():
     key = "image_decoder.hallucinate.0.weight"
     l = vae.layouts[key]
     assert rel(l.to_reference(g[l.offset:l.offset + l.numel]), work[key].grad) < 4e-3
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", 4e-3), ("bf16", 8e-2)])
+def test_ragged_sizes_match_oracle(precision, tol):
+    """Batch and latent sizes that are not multiples of any tile / vector width (B = 5, n = 10: padded leading dimensions,
+    partial 128-row tiles everywhere)."""
+    O, m, tr, state, image, attrs, noises = _device_step(precision, 5, 10, 4)
+    losses, grads, _, _ = O.train_step(state, image, attrs, noises)
+    for a, b in zip(tr.losses(), losses):
+        assert abs(a[0] - b) <= (2e-3 if precision == "tf32" else 3e-2) * abs(b)
+    dg = m.grads_reference()
+    bad = {k: rel(dg[k], v) for k, v in grads.items() if float(v.abs().max()) > 1e-7 and rel(dg[k], v) > tol}
+    assert not bad, bad

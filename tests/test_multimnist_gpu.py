@@ -331,3 +331,17 @@ def test_reference_training_loop_with_autograd():
         if float(v.abs().max()) < 1e-7:
             continue
         assert rel(dg[k], v) < 6e-3, (k, rel(dg[k], v))
+
+
+def test_ragged_sizes_match_oracle():
+    """B = 5, n = 10 (tf32): padded leading dimensions in the GRU / concatenation buffers, partial tiles."""
+    O, m, tr, state, image, text, noises = _device_step("tf32", 5, 10, 4)
+    losses, grads, _, outs = O.train_step(state, image, text, noises)
+    words = m.workspace(5, 3).words.view(3, 5, 4, 12).cpu()
+    for g in range(3):
+        assert torch.equal(words[g].argmax(-1), outs[g][1].argmax(-1))
+    for a, b in zip(tr.losses(), losses):
+        assert abs(a[0] - b) <= 2e-3 * abs(b)
+    dg = m.grads_reference()
+    bad = {k: rel(dg[k], v) for k, v in grads.items() if float(v.abs().max()) > 1e-7 and rel(dg[k], v) > 6e-3}
+    assert not bad, bad
