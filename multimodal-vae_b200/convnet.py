@@ -143,6 +143,10 @@ class ConvMVAEBase:
         self._ws: Dict[Tuple[int, int], object] = {}
         self._pad: Dict[str, Tuple[torch.Tensor, int]] = {}
         self._fresh = set()
+        # weight-gradient GEMMs (small split-K grids) run on a side stream under the bandwidth-bound dgrad / col2im / BatchNorm
+        # kernels of the main stream; fork / join are stream-ordered events (valid under CUDA-graph capture)
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self.use_side_stream = True
         self.reset_parameters()
 
     # ------------------------------------------------------------------ parameters
@@ -309,6 +313,19 @@ class ConvMVAEBase:
             w, ldw = self._operand_cached(prefix + ".weight", n_in)
             _ops.gemm(dy, w, dx, M, n_in, n_out, lddy, ldw, lddx, b_major=1, accumulate=accumulate_dx)
 
+    def _wgrad_aside(self, fn) -> None:
+        """Run `fn` (weight-gradient launches) on the side stream after everything enqueued so far on the current stream."""
+        if not self.use_side_stream:
+            fn()
+            return
+        self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side_stream):
+            fn()
+
+    def _join_side(self) -> None:
+        if self.use_side_stream:
+            torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
+
     # ------------------------------------------------------------------ conv stacks
     def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
         """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
@@ -348,14 +365,15 @@ class ConvMVAEBase:
                                      self.G(bn + ".bias"))
             else:
                 _ops.act_backward(SWISH, ws.enc_pre[li], ws.enc_dact[li], ws.enc_dpre[li], rows, co)
-            # dW'[co, K] += dpre^T col
-            _ops.gemm(ws.enc_dpre[li], ws.enc_col[li], self.G(pre + ".weight"), co, K, rows, co, ldk, K, a_major=1, b_major=1,
-                      accumulate=True)
+            # dW'[co, K] += dpre^T col   (side stream: overlaps the dgrad GEMM / col2im / BatchNorm backward of the next layer)
+            self._wgrad_aside(lambda li=li, pre=pre, co=co, K=K, rows=rows, ldk=ldk: _ops.gemm(
+                ws.enc_dpre[li], ws.enc_col[li], self.G(pre + ".weight"), co, K, rows, co, ldk, K, a_major=1, b_major=1, accumulate=True))
             if li > 0:
                 w, ldw = self._operand_cached(pre + ".weight", K)
                 _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
                 g = _ops.geometry(B, hin, hin, ci, k, s, p)
                 _ops.col2im(g, ws.colbuf, ldk, ws.enc_dact[li - 1])
+        self._join_side()
 
     def hallucinate_fwd(self, ws, M3, rows_per_term, training: bool) -> None:
         """The image decoder's transposed-conv stack on ws.u1 [M3, FLAT_HW*FLAT_C] -> ws.logits (NCHW fp32)."""
@@ -400,13 +418,16 @@ class ConvMVAEBase:
                 _ops.bn_act_backward(ws.dec_bn[li], dsrc, ws.dec_dpre[li], ws.dec_s0[li], ws.dec_s1[li], self.G(bn + ".weight"),
                                      self.G(bn + ".bias"))
                 dsrc = ws.dec_dpre[li]
+            self._join_side()                                          # the previous layer's weight gradient still reads colbuf
             _ops.im2col(g, dsrc, ws.colbuf, ldk)                       # dcol [M_in, (kh,kw,co)]
             x_in = ws.dec_act[li - 1] if li > 0 else ws.u1             # the layer's input [M_in, ci]
-            _ops.gemm(x_in, ws.colbuf, self.G(pre + ".weight"), ci, K, rows_in, ci, ldk, K, a_major=1, b_major=1, accumulate=True)
+            self._wgrad_aside(lambda x_in=x_in, pre=pre, ci=ci, K=K, rows_in=rows_in, ldk=ldk: _ops.gemm(
+                x_in, ws.colbuf, self.G(pre + ".weight"), ci, K, rows_in, ci, ldk, K, a_major=1, b_major=1, accumulate=True))
             dx = ws.dec_dact[li - 1] if li > 0 else ws.du1
             w, ldw = self._operand_cached(pre + ".weight", K)
             _ops.gemm(ws.colbuf, w, dx, rows_in, ci, K, ldk, ldw, ci)
             dsrc = dx
+        self._join_side()
 
     def alloc_conv_buffers(self, ws, B, G) -> None:
         """Activation / gradient buffers of the two conv stacks for batch B and G stacked terms."""
