@@ -321,10 +321,14 @@ class ConvMVAEBase:
         self.side_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.side_stream):
             fn()
+        self._side_forked = True
 
     def _join_side(self) -> None:
-        if self.use_side_stream:
+        # only after a fork: waiting on a side stream that holds no work of this step would, under CUDA-graph capture,
+        # create a dependency on uncaptured work
+        if self.use_side_stream and getattr(self, "_side_forked", False):
             torch.cuda.current_stream(self.device).wait_stream(self.side_stream)
+            self._side_forked = False
 
     # ------------------------------------------------------------------ conv stacks
     def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
