@@ -147,6 +147,9 @@ class ConvMVAEBase:
         # kernels of the main stream; fork / join are stream-ordered events (valid under CUDA-graph capture)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.use_side_stream = True
+        # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
+        # own stream beside the image networks
+        self.mod_stream = torch.cuda.Stream(device=dev)
         self.reset_parameters()
 
     # ------------------------------------------------------------------ parameters
@@ -312,6 +315,21 @@ class ConvMVAEBase:
         if dx is not None:
             w, ldw = self._operand_cached(prefix + ".weight", n_in)
             _ops.gemm(dy, w, dx, M, n_in, n_out, lddy, ldw, lddx, b_major=1, accumulate=accumulate_dx)
+
+    def on_mod_stream(self, fn) -> None:
+        """Fork: run `fn` on the second-modality stream after everything enqueued so far on the current stream."""
+        if not self.use_side_stream:
+            fn()
+            return
+        self.mod_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.mod_stream):
+            fn()
+        self._mod_forked = True
+
+    def join_mod_stream(self) -> None:
+        if self.use_side_stream and getattr(self, "_mod_forked", False):
+            torch.cuda.current_stream(self.device).wait_stream(self.mod_stream)
+            self._mod_forked = False
 
     def _wgrad_aside(self, fn) -> None:
         """Run `fn` (weight-gradient launches) on the side stream after everything enqueued so far on the current stream."""

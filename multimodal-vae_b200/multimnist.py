@@ -160,6 +160,7 @@ class MultimodalVAE(ConvMVAEBase):
         ws.dlog_all = buf(T * M3 * ws.ld_dlog)
         ws.dlog = slices(ws.dlog_all, M3 * ws.ld_dlog, T)
         ws.dcat = buf(M3 * (H + n), dtype=f32)
+        ws.dz_text = buf(M3 * n, dtype=f32)
         ws.carry = [buf(M3 * H, dtype=f32), buf(M3 * H, dtype=f32)]
         ws.dx1, ws.dx1_t, ws.dx1d_t = buf(M3 * H, dtype=f32), buf(M3 * ldH), buf(M3 * ldH)
         ws.dhinit = buf(M3 * ldH)
@@ -215,6 +216,8 @@ class MultimodalVAE(ConvMVAEBase):
         p = self.dropout_p if training else 0.0
         ws.R, ws.training, ws.use_img, ws.use_txt = R, training, use_img, use_txt
         ws.image, ws.text = image, text
+        if use_txt:
+            self.on_mod_stream(lambda: self._text_encoder_fwd(ws, text, B))     # beside the image encoder
         if use_img:
             self.features_fwd(ws, image, B, training, n_img)
             # classifier: Linear(1024,400) Swish Dropout Linear(400,200) Swish Dropout Linear(200,2n)  multimnist/model.py:172-180
@@ -225,8 +228,7 @@ class MultimodalVAE(ConvMVAEBase):
             _ops.act_forward(SWISH, ws.f2pre, ws.f2, R * B, 200, dropout_p=p, seed=self.noise_seed + 202,
                              step_counter=self._step_counter)
             self.linear_fwd(ws.f2, 200, R * B, "image_encoder.classifier.6", 2 * n, 200, ws.encA, 2 * n)
-        if use_txt:
-            self._text_encoder_fwd(ws, text, B)
+        self.join_mod_stream()
         self.latent_forward(ws, term_types, kl_weights, eps, training, ws.encA if use_img else None,
                             ws.encB if use_txt else None, R)
         self.decode(ws, training, lambdas, want_probs, with_loss)
@@ -252,6 +254,7 @@ class MultimodalVAE(ConvMVAEBase):
 
     def decode(self, ws, training: bool, lambdas, want_probs: bool, with_loss: bool) -> None:
         """Image decoder (multimnist/model.py:192-217) and greedy text decoder (:252-307) on the stacked latents."""
+        self.on_mod_stream(lambda: self._decode_text(ws, training, lambdas, with_loss))   # beside the image decoder
         B, G, n = ws.B, ws.G, self.n_latents
         M3 = G * B
         npx = self.n_pixels
@@ -263,7 +266,12 @@ class MultimodalVAE(ConvMVAEBase):
                          target_rows=B, grad_scale=sx, loss=ws.acc[0] if with_loss else None,
                          probs=ws.probs_image if want_probs else None, ld_probs=npx,
                          dlogits=ws.logits if with_loss else None, ld_dlogits=npx)
-        # ---- text decoder
+        self.join_mod_stream()
+
+    def _decode_text(self, ws, training: bool, lambdas, with_loss: bool) -> None:
+        """Greedy 4-step text decoder (multimnist/model.py:252-307) on the stacked latents."""
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
         sy = [float(lambdas[g][1]) / (B * MAX_LEN) for g in range(G)]
         p = self.dropout_p if training else 0.0
         ws.td_dropout = p
@@ -298,11 +306,20 @@ class MultimodalVAE(ConvMVAEBase):
         B, G, n = ws.B, ws.G, self.n_latents
         M3 = G * B
         Gd = self.G
-        # image decoder first: its latent gradient is STORED into dz, the text decoder accumulates on top
+        # the text decoder's backward runs beside the image decoder's and collects its latent gradient in dz_text
+        self.on_mod_stream(lambda: self._text_decoder_bwd(ws))
         self.hallucinate_bwd(ws, M3)
         _ops.act_backward(SWISH, ws.u1pre, ws.du1, ws.du1pre, M3, 1024, dbias=Gd("image_decoder.upsample.0.bias"))
         self.linear_bwd(ws.z, ws.ld_z, ws.du1pre, 1024, M3, "image_decoder.upsample.0", 1024, n, dx=ws.dz, lddx=n, bias=False)
-        # text decoder, backward through time
+        self.join_mod_stream()
+        _ops.copy_2d(ws.dz_text, 0, n, ws.dz, 0, n, M3, n, accumulate=True)
+        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_txt else None, *getattr(ws, "upstream", (None, None)))
+
+    def _text_decoder_bwd(self, ws) -> None:
+        """Backward through time of the text decoder; the gradient at z is STORED into ws.dz_text by the first contribution."""
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
+        Gd = self.G
         g = "text_decoder.gru"
         emb = self.P("text_decoder.embed.weight")
         ldH, ldc, p = ws.ldH, ws.ldc, ws.td_dropout
@@ -313,7 +330,7 @@ class MultimodalVAE(ConvMVAEBase):
         for t in range(T - 1, -1, -1):
             last = t == T - 1
             _ops.gemm(ws.dlog[t], wo, ws.dcat, M3, Kc, N_CHARS, ws.ld_dlog, ldwo, Kc, b_major=1)       # d[h1 | z] of step t
-            _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
+            _ops.copy_2d(ws.dcat, H, Kc, ws.dz_text, 0, n, M3, n, accumulate=not last)
             dx1 = ws.dx1_t if p > 0 else ws.dx1
             self._cell_bwd(ws, M3, ws.td_cells[1][t], ws.h1[t - 1] if t > 0 else ws.h1_all[:M3 * ldH], g, "l1", ws.dcat, Kc,
                            None if last else ws.carry[1], ws.carry[1], sl(ws.dgi_all[1], t), sl(ws.dgh_all[1], t), n_in=H,
@@ -328,7 +345,7 @@ class MultimodalVAE(ConvMVAEBase):
                            None if last else ws.carry[0], ws.carry[0], sl(ws.dgi_all[0], t), sl(ws.dgh_all[0], t), n_in=Kc,
                            dx=ws.dcat, lddx=Kc)
             _ops.embed_backward(ws.c_in[t], 0, 1, emb, N_CHARS, H, SWISH, ws.dcat, 0, Kc, M3, Gd("text_decoder.embed.weight"))
-            _ops.copy_2d(ws.dcat, H, Kc, ws.dz, 0, n, M3, n, accumulate=True)
+            _ops.copy_2d(ws.dcat, H, Kc, ws.dz_text, 0, n, M3, n, accumulate=True)
         # parameter gradients of the 4 steps at once (time-stacked operands)
         TM = T * M3
         _ops.gemm(ws.dlog_all, ws.cat2_all, Gd("text_decoder.h2o.weight"), N_CHARS, Kc, TM, ws.ld_dlog, ldc, Kc, a_major=1, b_major=1,
@@ -339,8 +356,7 @@ class MultimodalVAE(ConvMVAEBase):
         self._cells_param_grads(ws, TM, ws.dgi_all[0][:TM * ws.ldg], ws.dgh_all[0][:TM * ws.ldg], ws.cat1_all, ldc, Kc, ws.h0_all, g, "l0")
         # both GRU layers start from h = z2h(z)
         _ops.copy_2d(ws.carry[0], 0, H, ws.dhinit, 0, ldH, M3, H, src2=ws.carry[1], ld_src2=H)
-        self.linear_bwd(ws.z, ws.ld_z, ws.dhinit, ldH, M3, "text_decoder.z2h", H, n, dx=ws.dz, lddx=n, accumulate_dx=True)
-        self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_txt else None, *getattr(ws, "upstream", (None, None)))
+        self.linear_bwd(ws.z, ws.ld_z, ws.dhinit, ldH, M3, "text_decoder.z2h", H, n, dx=ws.dz_text, lddx=n, accumulate_dx=True)
 
     def module_outputs(self, ws):
         B, n = ws.B, self.n_latents
@@ -376,38 +392,49 @@ class MultimodalVAE(ConvMVAEBase):
         Gd = self.G
         p = self.dropout_p if ws.training else 0.0
         if ws.use_txt:
-            g = "text_encoder.gru"
-            ldH = ws.ldH
-            self.linear_bwd(ws.hsum, ldH, ws.dencB, ws.ld_enc, B, "text_encoder.h2p", 2 * n, H, dx=ws.dhsum, lddx=H)
-            T = MAX_LEN
-            sl = lambda flat, t: flat[t * B * ws.ldg:(t + 1) * B * ws.ldg]
-            for t in range(T - 1, -1, -1):
-                last = t == T - 1
-                self._cell_bwd(ws, B, ws.te_cells[t], ws.hf[t - 1] if t > 0 else None, g, "l0", ws.dhsum if last else None, H,
-                               None if last else ws.te_carry, ws.te_carry, sl(ws.dgi_all[0], t), sl(ws.dgh_all[0], t))
-            TB = T * B
-            dgi_all, dgh_all = ws.dgi_all[0][:TB * ws.ldg], ws.dgh_all[0][:TB * ws.ldg]
-            self._cells_param_grads(ws, TB, dgi_all, dgh_all, ws.ex_all, ldH, H, ws.hf_all, g, "l0")
-            wi, ldwi = self._operand_cached(g + ".weight_ih_l0", H)
-            _ops.gemm(dgi_all, wi, ws.dex_all, TB, H, 3 * H, ws.ldg, ldwi, H, b_major=1)              # gradient at every embedding
-            # reverse-direction cell (zero initial state: no W_hh gradient, no carry); its input is the last character too
-            self._cell_bwd(ws, B, ws.te_cells[T], None, g, "l0_reverse", ws.dhsum, H, None, None, ws.dgi_r, ws.dgh_r, n_in=H,
-                           dx=ws.dex[T - 1], lddx=H, accumulate_dx=True)
-            self._cells_param_grads(ws, B, ws.dgi_r, ws.dgh_r, ws.ex[T - 1], ldH, H, None, g, "l0_reverse")
-            for t in range(T):
-                _ops.embed_backward(ws.text, t, MAX_LEN, self.P("text_encoder.embed.weight"), N_CHARS, H, NONE, ws.dex[t], 0, H, B,
-                                    Gd("text_encoder.embed.weight"))
+            self.on_mod_stream(lambda: self._text_encoder_bwd(ws))            # beside the image encoder's backward
         if ws.use_img:
-            RB = R * B
-            self.linear_bwd(ws.f2, 200, ws.dencA, ws.ld_enc, RB, "image_encoder.classifier.6", 2 * n, 200, dx=ws.df2, lddx=200)
-            _ops.act_backward(SWISH, ws.f2pre, ws.df2, ws.df2pre, RB, 200, dropout_p=p, seed=self.noise_seed + 202,
-                              step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.3.bias"))
-            self.linear_bwd(ws.f1, 400, ws.df2pre, 200, RB, "image_encoder.classifier.3", 200, 400, dx=ws.df1, lddx=400, bias=False)
-            _ops.act_backward(SWISH, ws.f1pre, ws.df1, ws.df1pre, B, 400, repeat=R, dropout_p=p, seed=self.noise_seed + 101,
-                              step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.0.bias"))
-            self.linear_bwd(ws.enc_act[3], 1024, ws.df1pre, 400, B, "image_encoder.classifier.0", 400, 1024, dx=ws.enc_dact[3],
-                            lddx=1024, bias=False)
-            self.features_bwd(ws, B)
+            self._image_encoder_bwd(ws, p)
+        self.join_mod_stream()
+
+    def _text_encoder_bwd(self, ws) -> None:
+        B, n = ws.B, self.n_latents
+        Gd = self.G
+        g = "text_encoder.gru"
+        ldH = ws.ldH
+        self.linear_bwd(ws.hsum, ldH, ws.dencB, ws.ld_enc, B, "text_encoder.h2p", 2 * n, H, dx=ws.dhsum, lddx=H)
+        T = MAX_LEN
+        sl = lambda flat, t: flat[t * B * ws.ldg:(t + 1) * B * ws.ldg]
+        for t in range(T - 1, -1, -1):
+            last = t == T - 1
+            self._cell_bwd(ws, B, ws.te_cells[t], ws.hf[t - 1] if t > 0 else None, g, "l0", ws.dhsum if last else None, H,
+                           None if last else ws.te_carry, ws.te_carry, sl(ws.dgi_all[0], t), sl(ws.dgh_all[0], t))
+        TB = T * B
+        dgi_all, dgh_all = ws.dgi_all[0][:TB * ws.ldg], ws.dgh_all[0][:TB * ws.ldg]
+        self._cells_param_grads(ws, TB, dgi_all, dgh_all, ws.ex_all, ldH, H, ws.hf_all, g, "l0")
+        wi, ldwi = self._operand_cached(g + ".weight_ih_l0", H)
+        _ops.gemm(dgi_all, wi, ws.dex_all, TB, H, 3 * H, ws.ldg, ldwi, H, b_major=1)              # gradient at every embedding
+        # reverse-direction cell (zero initial state: no W_hh gradient, no carry); its input is the last character too
+        self._cell_bwd(ws, B, ws.te_cells[T], None, g, "l0_reverse", ws.dhsum, H, None, None, ws.dgi_r, ws.dgh_r, n_in=H,
+                       dx=ws.dex[T - 1], lddx=H, accumulate_dx=True)
+        self._cells_param_grads(ws, B, ws.dgi_r, ws.dgh_r, ws.ex[T - 1], ldH, H, None, g, "l0_reverse")
+        for t in range(T):
+            _ops.embed_backward(ws.text, t, MAX_LEN, self.P("text_encoder.embed.weight"), N_CHARS, H, NONE, ws.dex[t], 0, H, B,
+                                Gd("text_encoder.embed.weight"))
+
+    def _image_encoder_bwd(self, ws, p) -> None:
+        B, n, R = ws.B, self.n_latents, ws.R
+        Gd = self.G
+        RB = R * B
+        self.linear_bwd(ws.f2, 200, ws.dencA, ws.ld_enc, RB, "image_encoder.classifier.6", 2 * n, 200, dx=ws.df2, lddx=200)
+        _ops.act_backward(SWISH, ws.f2pre, ws.df2, ws.df2pre, RB, 200, dropout_p=p, seed=self.noise_seed + 202,
+                          step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.3.bias"))
+        self.linear_bwd(ws.f1, 400, ws.df2pre, 200, RB, "image_encoder.classifier.3", 200, 400, dx=ws.df1, lddx=400, bias=False)
+        _ops.act_backward(SWISH, ws.f1pre, ws.df1, ws.df1pre, B, 400, repeat=R, dropout_p=p, seed=self.noise_seed + 101,
+                          step_counter=self._step_counter, dbias=Gd("image_encoder.classifier.0.bias"))
+        self.linear_bwd(ws.enc_act[3], 1024, ws.df1pre, 400, B, "image_encoder.classifier.0", 400, 1024, dx=ws.enc_dact[3],
+                        lddx=1024, bias=False)
+        self.features_bwd(ws, B)
 
     # ------------------------------------------------------------------ module surface
     def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
