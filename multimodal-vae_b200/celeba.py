@@ -119,6 +119,7 @@ class MultimodalVAE(ConvMVAEBase):
         ws.alogits, ws.probs_attrs = buf(M3 * N_ATTRS, dtype=f32), buf(M3 * N_ATTRS, dtype=f32)
         ws.ld_dalog = round_up(N_ATTRS, self.vec)
         ws.dalog = buf(M3 * ws.ld_dalog)
+        ws.dz_attr = buf(M3 * n, dtype=f32)
         return ws
 
     # ------------------------------------------------------------------ forward
@@ -133,6 +134,8 @@ class MultimodalVAE(ConvMVAEBase):
         R = n_img if (training and self.dropout_p > 0 and n_img > 1) else 1
         ws.R, ws.training, ws.use_img, ws.use_att = R, training, use_img, use_att
         ws.image, ws.attrs = image, attrs
+        if use_att:
+            self.on_mod_stream(lambda: self._attrs_encoder_fwd(ws, attrs, training, n_att))    # beside the image encoder
         if use_img:
             self.features_fwd(ws, image, B, training, n_img)
             # classifier: Linear(6400, 1024) + Swish + Dropout + Linear(1024, 2n)   celeba/model.py:114-119
@@ -140,32 +143,43 @@ class MultimodalVAE(ConvMVAEBase):
             _ops.act_forward(SWISH, ws.f1pre, ws.f1, B, 1024, repeat=R, dropout_p=self.dropout_p if training else 0.0,
                              seed=self.noise_seed, step_counter=self._step_counter)
             self.linear_fwd(ws.f1, 1024, R * B, "image_encoder.classifier.3", 2 * n, 1024, ws.encA, 2 * n)
-        if use_att:                                                  # celeba/model.py:170-176
-            _ops.cast_pad_2d(attrs, B, N_ATTRS, N_ATTRS, ws.attrs_pad, ws.ld_attr)
-            bn = "attrs_encoder.net.1"
-            self.linear_fwd(ws.attrs_pad, ws.ld_attr, B, "attrs_encoder.net.0", 64, N_ATTRS, ws.t1pre, 64)
-            rm, rv = self.running(bn)
-            ws.ae_bn = _ops.bn_args(ws.t1pre, B, 64, B, SWISH, training, self.P(bn + ".weight"), self.P(bn + ".bias"),
-                                    ws.ae_sum[0], ws.ae_sum[1], ws.ae_mean, ws.ae_rstd, rm, rv, updates=n_att)
-            _ops.bn_act_forward(ws.ae_bn, ws.t1)
-            self.linear_fwd(ws.t1, 64, B, "attrs_encoder.net.3", 2 * n, 64, ws.encB, 2 * n)
+        self.join_mod_stream()
         self.latent_forward(ws, term_types, kl_weights, eps, training, ws.encA if use_img else None,
                             ws.encB if use_att else None, R)
         self.decode(ws, training, lambdas, want_probs, with_loss)
+
+    def _attrs_encoder_fwd(self, ws, attrs, training: bool, n_att: int) -> None:
+        """celeba/model.py:170-176."""
+        B, n = ws.B, self.n_latents
+        _ops.cast_pad_2d(attrs, B, N_ATTRS, N_ATTRS, ws.attrs_pad, ws.ld_attr)
+        bn = "attrs_encoder.net.1"
+        self.linear_fwd(ws.attrs_pad, ws.ld_attr, B, "attrs_encoder.net.0", 64, N_ATTRS, ws.t1pre, 64)
+        rm, rv = self.running(bn)
+        ws.ae_bn = _ops.bn_args(ws.t1pre, B, 64, B, SWISH, training, self.P(bn + ".weight"), self.P(bn + ".bias"),
+                                ws.ae_sum[0], ws.ae_sum[1], ws.ae_mean, ws.ae_rstd, rm, rv, updates=n_att)
+        _ops.bn_act_forward(ws.ae_bn, ws.t1)
+        self.linear_fwd(ws.t1, 64, B, "attrs_encoder.net.3", 2 * n, 64, ws.encB, 2 * n)
 
     def decode(self, ws, training: bool, lambdas, want_probs: bool, with_loss: bool) -> None:
         """Image and attribute decoders on the stacked [G*B] latents (celeba/model.py:134-163, 185-200) + BCE terms."""
         B, G, n = ws.B, ws.G, self.n_latents
         M3 = G * B
+        self.on_mod_stream(lambda: self._attrs_decoder_fwd(ws, training, lambdas, want_probs, with_loss))   # beside the image decoder
         self.linear_fwd(ws.z, ws.ld_z, M3, "image_decoder.upsample.0", 6400, n, ws.u1pre, 6400)
         _ops.act_forward(SWISH, ws.u1pre, ws.u1, M3, 6400)
         self.hallucinate_fwd(ws, M3, B, training)
         sx = [float(lambdas[g][0]) / (B * 12288) for g in range(G)]
-        sy = [float(lambdas[g][1]) / (B * N_ATTRS) for g in range(G)]
         _ops.sigmoid_bce(ws.logits, 12288, M3, 12288, rows_per_group=B,
                          target=ws.image if with_loss else None, ld_target=12288, target_rows=B, grad_scale=sx,
                          loss=ws.acc[0] if with_loss else None, probs=ws.probs_image if want_probs else None, ld_probs=12288,
                          dlogits=ws.logits if with_loss else None, ld_dlogits=12288)
+        self.join_mod_stream()
+
+    def _attrs_decoder_fwd(self, ws, training: bool, lambdas, want_probs: bool, with_loss: bool) -> None:
+        """celeba/model.py:185-200 + the attribute BCE of celeba/train.py:69-74."""
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
+        sy = [float(lambdas[g][1]) / (B * N_ATTRS) for g in range(G)]
         bn = "attrs_decoder.net.1"
         self.linear_fwd(ws.z, ws.ld_z, M3, "attrs_decoder.net.0", 64, n, ws.s1pre, 64)
         rm, rv = self.running(bn)
@@ -183,17 +197,24 @@ class MultimodalVAE(ConvMVAEBase):
         B, G, n = ws.B, ws.G, self.n_latents
         M3 = G * B
         Gd = self.G
-        # attribute decoder
-        self.linear_bwd(ws.s1, 64, ws.dalog, ws.ld_dalog, M3, "attrs_decoder.net.3", N_ATTRS, 64, dx=ws.ds1, lddx=64)
-        bn = "attrs_decoder.net.1"
-        _ops.bn_act_backward(ws.ad_bn, ws.ds1, ws.ds1pre, ws.ad_s[0], ws.ad_s[1], Gd(bn + ".weight"), Gd(bn + ".bias"))
-        self.linear_bwd(ws.z, ws.ld_z, ws.ds1pre, 64, M3, "attrs_decoder.net.0", 64, n, dx=ws.dz, lddx=n, bias=False)
+        # attribute decoder beside the image decoder; its latent gradient goes to dz_attr and is added after the join
+        self.on_mod_stream(lambda: self._attrs_decoder_bwd(ws))
         # image decoder (the gradient of the BCE sits in ws.logits)
         self.hallucinate_bwd(ws, M3)
         _ops.act_backward(SWISH, ws.u1pre, ws.du1, ws.du1pre, M3, 6400, dbias=Gd("image_decoder.upsample.0.bias"))
-        self.linear_bwd(ws.z, ws.ld_z, ws.du1pre, 6400, M3, "image_decoder.upsample.0", 6400, n, dx=ws.dz, lddx=n,
-                        accumulate_dx=True, bias=False)
+        self.linear_bwd(ws.z, ws.ld_z, ws.du1pre, 6400, M3, "image_decoder.upsample.0", 6400, n, dx=ws.dz, lddx=n, bias=False)
+        self.join_mod_stream()
+        _ops.copy_2d(ws.dz_attr, 0, n, ws.dz, 0, n, M3, n, accumulate=True)
         self.latent_backward(ws, ws.dencA if ws.use_img else None, ws.dencB if ws.use_att else None, *getattr(ws, "upstream", (None, None)))
+
+    def _attrs_decoder_bwd(self, ws) -> None:
+        B, G, n = ws.B, ws.G, self.n_latents
+        M3 = G * B
+        Gd = self.G
+        self.linear_bwd(ws.s1, 64, ws.dalog, ws.ld_dalog, M3, "attrs_decoder.net.3", N_ATTRS, 64, dx=ws.ds1, lddx=64)
+        bn = "attrs_decoder.net.1"
+        _ops.bn_act_backward(ws.ad_bn, ws.ds1, ws.ds1pre, ws.ad_s[0], ws.ad_s[1], Gd(bn + ".weight"), Gd(bn + ".bias"))
+        self.linear_bwd(ws.z, ws.ld_z, ws.ds1pre, 64, M3, "attrs_decoder.net.0", 64, n, dx=ws.dz_attr, lddx=n, bias=False)
 
     def module_outputs(self, ws):
         B, n = ws.B, self.n_latents
@@ -225,11 +246,14 @@ class MultimodalVAE(ConvMVAEBase):
     def backward_encoders(self, ws) -> None:
         B, n, R = ws.B, self.n_latents, ws.R
         Gd = self.G
-        if ws.use_att:
+        def attrs_encoder_bwd():
             self.linear_bwd(ws.t1, 64, ws.dencB, ws.ld_enc, B, "attrs_encoder.net.3", 2 * n, 64, dx=ws.dt1, lddx=64)
             bn = "attrs_encoder.net.1"
             _ops.bn_act_backward(ws.ae_bn, ws.dt1, ws.dt1pre, ws.ae_s[0], ws.ae_s[1], Gd(bn + ".weight"), Gd(bn + ".bias"))
             self.linear_bwd(ws.attrs_pad, ws.ld_attr, ws.dt1pre, 64, B, "attrs_encoder.net.0", 64, N_ATTRS, bias=False)
+
+        if ws.use_att:
+            self.on_mod_stream(attrs_encoder_bwd)              # beside the image encoder's backward
         if ws.use_img:
             RB = R * B
             self.linear_bwd(ws.f1, 1024, ws.dencA, ws.ld_enc, RB, "image_encoder.classifier.3", 2 * n, 1024, dx=ws.df1, lddx=1024)
@@ -239,6 +263,7 @@ class MultimodalVAE(ConvMVAEBase):
             self.linear_bwd(ws.enc_act[3], 6400, ws.df1pre, 1024, B, "image_encoder.classifier.0", 1024, 6400,
                             dx=ws.enc_dact[3], lddx=6400, bias=False)
             self.features_bwd(ws, B)
+        self.join_mod_stream()
 
     # ------------------------------------------------------------------ module surface
     def forward(self, image: Optional[torch.Tensor] = None, attrs: Optional[torch.Tensor] = None, eps: Optional[torch.Tensor] = None):
