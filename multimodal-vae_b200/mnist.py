@@ -457,6 +457,60 @@ class MVAETrainer:
         return m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=zero_grad,
                       adam=self.adam if update else None, outputs=outputs, grad_scale=self.grad_scale)
 
+    #: (row selector, terms, lambdas) of the three presence classes of step_masked
+    _MASK_CLASSES = (("paired", ("joint", "image", "text"), ((1.0, 1.0), (1.0, 1.0), (0.0, 1.0))),
+                     ("image_only", ("image",), ((1.0, 0.0),)),
+                     ("text_only", ("text",), ((0.0, 1.0),)))
+
+    def step_masked(self, image, text, has_image, has_text, eps=None, annealing_factor: float = 1.0,
+                    update: bool = True):
+        """One optimizer step over a batch that MIXES paired and unpaired samples (the per-sample
+        missing-modality mask end to end; the reference only flips a coin per batch, mnist/paired_weak.py:82-104).
+
+        `has_image`, `has_text`: [B] bool.  Rows are compacted by presence class on the device and each class runs
+        the fused step on its own rows: paired rows -> joint + image + text terms with the lambdas of
+        mnist/paired_weak.py:85-93, image-only rows -> the image term (:97-99), text-only rows -> the text term
+        (:100-102); rows with neither modality are skipped.  Every loss term is a mean over its own rows and
+        BatchNorm only ever sees present rows - exactly what the reference computes when it is fed the three
+        subsets as three batches - but the gradients accumulate and ONE Adam update follows.
+        `eps`: optional [3, B, n] noise per (term, row).  Returns {class: losses [n_terms, 4]} (device tensors)."""
+        m = self.model
+        hi = torch.as_tensor(has_image).to(m.device_).bool().reshape(-1)
+        ht = torch.as_tensor(has_text).to(m.device_).bool().reshape(-1)
+        x = m.to_act(image)
+        y = text.to(m.device_, non_blocking=True).long().contiguous()
+        if hi.numel() != x.shape[0] or ht.numel() != x.shape[0]:
+            raise ValueError("has_image / has_text must have one entry per sample")
+        if eps is not None:
+            eps = eps.to(m.device_, torch.float32)
+        rows = {"paired": hi & ht, "image_only": hi & ~ht, "text_only": ~hi & ht}
+        term_index = {"joint": 0, "image": 1, "text": 2}
+        out, first, ran = {}, True, 0
+        ws = m.workspace(x.shape[0])  # the full batch's workspace is large enough for every subset
+        for j, (name, terms, lambdas) in enumerate(self._MASK_CLASSES):
+            idx = torch.nonzero(rows[name]).reshape(-1)  # data-dependent size: one host sync per class
+            if idx.numel() == 0:
+                continue
+            e = None
+            if eps is not None:
+                e = torch.stack([eps[term_index[t]].index_select(0, idx) for t in terms]).contiguous()
+            tt, klw = self._norm(terms, int(idx.numel()), annealing_factor)
+            # a distinct Philox stream per class: the device step counter is rewound below
+            losses, _ = m._run(x.index_select(0, idx), y.index_select(0, idx), tt, lambdas, klw, eps=e, backward=True,
+                               zero_grad=first, adam=None, grad_scale=self.grad_scale, workspace=ws,
+                               extra={"seed": (m.noise_seed + 0x9E3779B1 * (j + 1)) & 0x7FFFFFFFFFFFFFFF})
+            out[name] = losses
+            first = False
+            ran += 1
+        if ran > 1:
+            m._step_counter.sub_(ran - 1)  # one optimizer step = one tick of Adam's bias-correction clock
+        if update and ran > 0:
+            from . import _ops
+            a = self.adam
+            _ops.adam_step(m.flat_params, m.flat_grads, a["m"], a["v"], m.flat_params_bf16, m.flat_params.numel(), a["lr"],
+                           a["betas"][0], a["betas"][1], a["eps"], m._step_counter, self.grad_scale, zero_grad=False)
+        return out
+
     def _graph_step(self, x, y, eps, terms, lambdas, annealing_factor, update, zero_grad):
         """Replay of the step as one CUDA graph (static input buffers; one graph per configuration)."""
         m = self.model

@@ -234,3 +234,88 @@ def test_split_backward_phases_equal_single_call():
         if name in O.PRE_BN_BIASES:
             continue
         assert rel_l2(p2.grad, p1.grad) < 2e-3, name   # atomics order only
+
+
+def test_masked_step_mixes_paired_and_unpaired_rows():
+    """per-sample missing-modality masks end to end.  MVAETrainer.step_masked must equal the oracle fed
+    the paired / image-only / text-only subsets as three batches (mnist/paired_weak.py:82-104 per subset) with the
+    gradients summed and one Adam update; BatchNorm running statistics thread through the subsets in that order."""
+    import mvae_b200
+    B, n, seed = 96, 16, 9
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    g = torch.Generator().manual_seed(5)
+    has_image = torch.rand(B, generator=g) < 0.7
+    has_text = torch.rand(B, generator=g) < 0.6
+    has_image[:4], has_text[:4] = False, False   # rows with neither modality are skipped
+    classes = [(has_image & has_text, ("joint", "image", "text"), ((1., 1.), (1., 1.), (0., 1.))),
+               (has_image & ~has_text, ("image",), ((1., 0.),)),
+               (~has_image & has_text, ("text",), ((0., 1.),))]
+    assert all(int(c[0].sum()) >= 8 for c in classes)
+
+    p = {k: v.clone() for k, v in state.items()}
+    total, ref_losses = None, []
+    for rows, terms, lambdas in classes:
+        idx = torch.nonzero(rows).reshape(-1)
+        losses, grads, bufs, _ = oracle_step(p, image[idx], text[idx], [e[idx] for e in noises], terms, lambdas)
+        ref_losses.append([losses[NAMES.index(t)] for t in terms])
+        total = grads if total is None else {k: total[k] + grads[k] for k in grads}
+        p.update(bufs)
+    mom = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
+    new = O.adam_step({k: v.clone() for k, v in p.items()}, total, mom, vel, 1)
+
+    for update in (False, True):
+        m = mvae_b200.MVAE(n, precision="tf32")
+        m.load_state_dict(state)
+        tr = mvae_b200.MVAETrainer(m)
+        out = tr.step_masked(image.cuda(), text.cuda(), has_image, has_text, eps=torch.stack(noises).cuda(), update=update)
+        torch.cuda.synchronize()
+        assert int(m._step_counter) == 1
+        for name, ref in zip(("paired", "image_only", "text_only"), ref_losses):
+            np.testing.assert_allclose(out[name][:, 0].cpu().numpy(), ref, rtol=3e-5)
+        sd = m.state_dict()
+        for k, v in p.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(sd[k]) == int(v), k
+            elif O.is_buffer(k):
+                np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+        if not update:
+            for name, prm in m.named_parameters():
+                if name in O.PRE_BN_BIASES:
+                    continue
+                assert rel_l2(prm.grad, total[name]) < 6e-2, (name, rel_l2(prm.grad, total[name]))
+        else:
+            # first Adam step moves every weight by ~lr * sign(grad): compare the update direction where it is defined
+            for k, v in new.items():
+                if O.is_buffer(k) or k in O.PRE_BN_BIASES:
+                    continue
+                big = total[k].abs() > 0.25 * total[k].abs().max()   # tf32 noise can flip the sign of the small entries
+                d_dev = (sd[k].cpu() - state[k])[big]
+                d_ref = (v - state[k])[big]
+                assert float((d_dev - d_ref).abs().max()) < 2.5e-4, k   # lr = 1e-3
+
+    # all rows paired == the ordinary three-term step with the paired lambdas
+    m1 = mvae_b200.MVAE(n, precision="tf32"); m1.load_state_dict(state)
+    m2 = mvae_b200.MVAE(n, precision="tf32"); m2.load_state_dict(state)
+    eps = torch.stack(noises).cuda()
+    ones = torch.ones(B, dtype=torch.bool)
+    o1 = mvae_b200.MVAETrainer(m1).step_masked(image.cuda(), text.cuda(), ones, ones, eps=eps, update=False)
+    l2, _ = mvae_b200.MVAETrainer(m2).step(image.cuda(), text.cuda(), eps=eps, lambdas=((1., 1.), (1., 1.), (0., 1.)), update=False)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(o1["paired"].cpu().numpy(), l2.cpu().numpy(), rtol=1e-6)
+    for (name, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if name not in O.PRE_BN_BIASES:
+            assert rel_l2(p1.grad, p2.grad) < 2e-3, name
+    # device-generated noise (Philox), bf16 storage, uint8 images: runs and trains
+    m3 = mvae_b200.MVAE(n, precision="bf16"); m3.load_state_dict(state)
+    tr3 = mvae_b200.MVAETrainer(m3)
+    u8 = (image * 255).to(torch.uint8)
+    first = last = None
+    for s in range(30):
+        out = tr3.step_masked(u8, text, has_image, has_text)
+        tot = float(sum(v[:, 0].sum() for v in out.values()))
+        assert np.isfinite(tot)
+        first = tot if first is None else first
+        last = tot
+    assert int(m3._step_counter) == 30 and last < first
