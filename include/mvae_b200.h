@@ -215,6 +215,12 @@ typedef struct mvae_conv_geometry {
   int64_t stride_n, stride_h, stride_w, stride_c; /* element strides of the image tensor (NHWC dense or e.g. NCHW) */
 } mvae_conv_geometry;
 int mvae_conv_out_size(int in, int kernel, int stride, int pad);
+/* Implicit GEMM: mvae_gemm where ONE operand is the patch matrix of `geometry` read straight from the channels-last bf16
+ * image (never materialised): patch_operand 1 -> A = im2col(image) [M = batch*Ho*Wo, K = k*k*C] (args->A = image, lda
+ * ignored; Conv2d forward celeba/model.py:101-113, ConvTranspose2d input gradient); patch_operand 2 -> B = im2col(image)
+ * with the pixel index as the contraction (args->B = image, b_major = 1, N = k*k*C, K = batch*Ho*Wo; weight gradients).
+ * Needs C % 8 == 0 and bf16 storage; bit-identical to mvae_im2col followed by mvae_gemm. */
+int mvae_conv_gemm(const mvae_gemm_args* args, const mvae_conv_geometry* geometry, int patch_operand, void* stream);
 /* col[m, (kh*k+kw)*C + c] = image[n, ho*s-p+kh, wo*s-p+kw, c] (0 outside), m = (n*Ho+ho)*Wo+wo.
  * replaces: the patch gather inside nn.Conv2d forward / ConvTranspose2d backward (celeba/model.py:101-113, 142-152). */
 int mvae_im2col(const mvae_conv_geometry* g, int image_dtype, const void* image, int col_dtype, void* col, int64_t ldcol,

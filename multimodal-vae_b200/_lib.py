@@ -206,6 +206,7 @@ def _conv_argtypes(lib) -> None:
     lib.mvae_cast_pad_2d.argtypes = [c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]
     lib.mvae_step_begin.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p]
     lib.mvae_gemm.argtypes = [P(GemmArgs), c_void_p]
+    lib.mvae_conv_gemm.argtypes = [P(GemmArgs), P(ConvGeometry), c_int, c_void_p]
     lib.mvae_embed_forward.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64,
                                        c_void_p]
     lib.mvae_embed_backward.argtypes = [c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_int64,

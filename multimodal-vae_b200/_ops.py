@@ -23,8 +23,10 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, accumulate=False, col_sum=None,
-         col_sumsq=None, rows_per_group=0):
-    """Cout[M,N] (+)= A[M,K] * B[N,K]^T (+ bias).  A and B share one storage dtype (bf16 -> kind::f16, fp32 -> tf32)."""
+         col_sumsq=None, rows_per_group=0, patch=None, split_k=0, block_n=0, stages=0):
+    """Cout[M,N] (+)= A[M,K] * B[N,K]^T (+ bias).  A and B share one storage dtype (bf16 -> kind::f16, fp32 -> tf32).
+    `patch=(geometry, operand)`: implicit GEMM - operand 1: A is the channels-last image whose patch matrix is the real A
+    (lda ignored); operand 2: likewise for B (b_major must be 1).  See mvae_conv_gemm."""
     if A.dtype != B.dtype:
         raise TypeError("gemm operands differ in dtype: %s vs %s" % (A.dtype, B.dtype))
     a = _lib.GemmArgs()
@@ -37,6 +39,12 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, ac
     a.accumulate = 1 if accumulate else 0
     a.col_sum, a.col_sumsq = _p(col_sum), _p(col_sumsq)
     a.rows_per_group = int(rows_per_group)
+    a.split_k, a.block_n, a.stages = int(split_k), int(block_n), int(stages)
+    if patch is not None:
+        geom, operand = patch
+        _lib.check(_lib.load().mvae_conv_gemm(C.byref(a), C.byref(geom), int(operand), stream()),
+                   "mvae_conv_gemm %dx%dx%d" % (M, N, K))
+        return
     _lib.check(_lib.load().mvae_gemm(C.byref(a), stream()), "mvae_gemm %dx%dx%d" % (M, N, K))
 
 

@@ -56,9 +56,31 @@ void mvae_debug_gemm_times(void* device_int64_buffer, int epilogue_kind) {
   set_gemm_debug_times(device_int64_buffer, epilogue_kind);
 }
 
-int mvae_gemm(const mvae_gemm_args* a, void* stream) {
+static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int patch_operand, void* stream);
+
+int mvae_gemm(const mvae_gemm_args* a, void* stream) { return gemm_entry(a, nullptr, 0, stream); }
+
+int mvae_conv_gemm(const mvae_gemm_args* a, const mvae_conv_geometry* geometry, int patch_operand, void* stream) {
+  MVAE_REQUIRE(geometry != nullptr && (patch_operand == 1 || patch_operand == 2), "mvae_conv_gemm: geometry / operand");
+  return gemm_entry(a, geometry, patch_operand, stream);
+}
+
+static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int patch_operand, void* stream) {
   MVAE_REQUIRE(a != nullptr, "mvae_gemm: null args");
   GemmDesc g;
+  if (cg != nullptr) {
+    MVAE_REQUIRE(cg->stride_c == 1, "mvae_conv_gemm: the image must be channels-last (stride_c == 1)");
+    g.gather.mode = patch_operand;
+    g.gather.X = patch_operand == 1 ? a->A : a->B;
+    g.gather.H = cg->height; g.gather.W = cg->width; g.gather.C = cg->channels;
+    g.gather.ksize = cg->kernel; g.gather.stride = cg->stride; g.gather.pad = cg->pad;
+    g.gather.Ho = (cg->height + 2 * cg->pad - cg->kernel) / cg->stride + 1;
+    g.gather.Wo = (cg->width + 2 * cg->pad - cg->kernel) / cg->stride + 1;
+    g.gather.sn = cg->stride_n; g.gather.sh = cg->stride_h; g.gather.sw = cg->stride_w;
+    const long long pixels = static_cast<long long>(cg->batch) * g.gather.Ho * g.gather.Wo;
+    MVAE_REQUIRE(pixels == (patch_operand == 1 ? a->M : a->K), "mvae_conv_gemm: %lld output pixels do not match the GEMM shape",
+                 pixels);
+  }
   g.kind = a->dtype;
   g.M = a->M; g.N = a->N; g.K = a->K;
   g.A = a->A; g.lda = a->lda; g.a_mn = a->a_major;

@@ -101,6 +101,18 @@ struct GemmATransform {
   void* out = nullptr;             // [M, K] materialised A' (storage dtype), written by the blockIdx.x == 0 tiles
 };
 
+// Implicit patch-matrix operand (implicit GEMM for the convolutions): instead of reading a materialised im2col
+// matrix col[m, (kh*k+kw)*C + c] = X[n, ho*s-p+kh, wo*s-p+kw, c] through TMA, warps 4..7 of the GEMM gather its
+// 16-byte chunks (8 bf16 channels of one tap) straight from the NHWC activation into the swizzled operand stage.
+//   mode 1: the patch matrix is A [M = n*Ho*Wo, K = k*k*C], K-major  (conv forward, transposed-conv dgrad)
+//   mode 2: the patch matrix is B, MN-major: reduction index = pixel, N = k*k*C  (weight gradients)
+struct ConvGather {
+  int mode = 0;
+  const void* X = nullptr;
+  int H = 0, W = 0, C = 0, ksize = 0, stride = 1, pad = 0, Ho = 0, Wo = 0;
+  long long sn = 0, sh = 0, sw = 0;  // element strides of X (channel stride 1)
+};
+
 struct GemmDesc {
   int kind = MVAE_F32;  // operand storage: fp32 (kind::tf32) or bf16 (kind::f16)
   int M = 0, N = 0, K = 0;
@@ -119,6 +131,7 @@ struct GemmDesc {
   long long* dbg = nullptr;  // device buffer [ctas][8] of %globaltimer stamps (bring-up only)
   GemmATransform atf;
   GemmEpilogue epi;
+  ConvGather gather;
 };
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);

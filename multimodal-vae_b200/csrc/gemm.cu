@@ -56,6 +56,7 @@ struct GemmKParams {
   long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
   GemmATransform atf;
   GemmEpilogue epi;
+  ConvGather gather;  // implicit patch-matrix operand (mode 0: none)
 };
 
 template <int kKind>
@@ -444,16 +445,19 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        ptx::mbar_expect_tx(&full_bar[s], kAStageBytes + p.b_tx_bytes);
+        const bool tma_a = p.gather.mode != 1, tma_b = p.gather.mode != 2;  // the gathered operand comes from warps 4..7
+        ptx::mbar_expect_tx(&full_bar[s], (tma_a ? kAStageBytes : 0) + (tma_b ? p.b_tx_bytes : 0));
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + kAStageBytes;
         const int kc = (kb0 + i) * BK;
-        if (!p.a_mn) {
+        if (!tma_a) {
+        } else if (!p.a_mn) {
           ptx::tma_load_2d(sa, &tmA, &full_bar[s], kc, m0);
         } else {
           for (int j = 0; j < a_boxes; ++j) ptx::tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + j * ATOM, kc);
         }
-        if (!p.b_mn) {
+        if (!tma_b) {
+        } else if (!p.b_mn) {
           ptx::tma_load_2d(sb, &tmB, &full_bar[s], kc, n0);
         } else {
           for (int j = 0; j < b_boxes; ++j) ptx::tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + j * ATOM, kc);
@@ -467,7 +471,12 @@ __global__ void __launch_bounds__(kGemmThreads)
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
-        ptx::mbar_wait(p.coef_off >= 0 ? &ready_bar[s] : &full_bar[s], ph);
+        if (p.gather.mode != 0) {  // TMA half landed AND the gathered half is in place
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::mbar_wait(&ready_bar[s], ph);
+        } else {
+          ptx::mbar_wait(p.coef_off >= 0 ? &ready_bar[s] : &full_bar[s], ph);
+        }
         ptx::tc_fence_after();
         if (i == 0) stamp(2);
         const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
@@ -550,6 +559,122 @@ __global__ void __launch_bounds__(kGemmThreads)
       }
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       ptx::mbar_arrive(&ready_bar[s]);
+    }
+  } else if (warp >= 4 && p.gather.mode != 0) {
+    // ------------------------------------------------------------ implicit patch-matrix operand (warps 4..7)
+    // The convolution's im2col matrix is never materialised: these 128 threads copy 16-byte chunks (8 bf16 channels of
+    // one filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of
+    // row r lives at physical chunk c ^ (r & 7)); padding and out-of-range rows are zero-filled by cp.async.  Up to
+    // `depth` stages are in flight per thread; a finished stage is published through ready_bar after a proxy fence.
+    if constexpr (kKind == MVAE_BF16) {
+      const ConvGather& cg = p.gather;
+      const int tt = threadIdx.x - 128;
+      const int c = tt & 7, rbase = tt >> 3;
+      const uint32_t chunk_off = static_cast<uint32_t>((c ^ (rbase & 7)) << 4);
+      const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(cg.X);
+      const int depth = S < 4 ? S : 4;
+      const int hw = cg.Ho * cg.Wo;
+      int published = 0;
+      if (cg.mode == 1) {
+        // A[m, k]: this thread owns chunk column c of rows rbase + 16 j (fixed pixels), k advances with the stage
+        long long off[8];
+        int hi0[8], wi0[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int m = m0 + rbase + 16 * j;
+          hi0[j] = -(1 << 28);
+          wi0[j] = 0;
+          off[j] = 0;
+          if (m < p.M) {
+            const int n = m / hw, rem = m - n * hw;
+            const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
+            hi0[j] = ho * cg.stride - cg.pad;
+            wi0[j] = wo * cg.stride - cg.pad;
+            off[j] = n * cg.sn + hi0[j] * cg.sh + wi0[j] * cg.sw;
+          }
+        }
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % S;
+          const uint32_t ph = (i / S) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
+          const int k0 = (kb0 + i) * BK + c * 8;
+          const int tap = k0 / cg.C, ch = k0 - tap * cg.C;
+          const int kh = tap / cg.ksize, kw = tap - kh * cg.ksize;
+          const long long koff = kh * cg.sh + kw * cg.sw + ch;
+          const bool kvalid = k0 < p.K;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = rbase + 16 * j;
+            const int hi = hi0[j] + kh, wi = wi0[j] + kw;
+            const bool ok = kvalid && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
+                            static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
+            ptx::cp_async16_zfill(a_base + r * 128 + chunk_off, ok ? X + off[j] + koff : X, ok ? 16u : 0u);
+          }
+          ptx::cp_async_commit();
+          if (i >= depth - 1) {
+            ptx::cp_async_wait_pending(depth - 1);
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&ready_bar[published % S]);
+            ++published;
+          }
+        }
+      } else {
+        // B, MN-major: stage row kr = reduction index (pixel (kb0+i)*BK + kr), 128-byte column boxes of 64 patch
+        // entries; this thread owns chunk c of every box (fixed taps / channels) for rows rbase + 16 jr
+        const uint32_t b_boxes = static_cast<uint32_t>((p.block_n + ATOM - 1) / ATOM);
+        long long koff[4];
+        int kh[4], kw[4];
+        bool kvalid[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k0 = n0 + j * ATOM + c * 8;
+          const int tap = k0 / cg.C, ch = k0 - tap * cg.C;
+          kh[j] = tap / cg.ksize;
+          kw[j] = tap - kh[j] * cg.ksize;
+          koff[j] = kh[j] * cg.sh + kw[j] * cg.sw + ch;
+          kvalid[j] = static_cast<uint32_t>(j) < b_boxes && k0 < p.N;
+        }
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % S;
+          const uint32_t ph = (i / S) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t b_base = ptx::smem_u32(smem + s * stage_bytes) + kAStageBytes;
+#pragma unroll
+          for (int jr = 0; jr < BK / 16; ++jr) {
+            const int kr = rbase + 16 * jr;
+            const int m = (kb0 + i) * BK + kr;
+            int hi0 = -(1 << 28), wi0 = 0;
+            long long off = 0;
+            if (m < p.K) {
+              const int n = m / hw, rem = m - n * hw;
+              const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
+              hi0 = ho * cg.stride - cg.pad;
+              wi0 = wo * cg.stride - cg.pad;
+              off = n * cg.sn + hi0 * cg.sh + wi0 * cg.sw;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (static_cast<uint32_t>(j) < b_boxes) {
+                const int hi = hi0 + kh[j], wi = wi0 + kw[j];
+                const bool ok = kvalid[j] && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
+                                static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
+                ptx::cp_async16_zfill(b_base + j * (BK * 128) + kr * 128 + chunk_off, ok ? X + off + koff[j] : X, ok ? 16u : 0u);
+              }
+            }
+          }
+          ptx::cp_async_commit();
+          if (i >= depth - 1) {
+            ptx::cp_async_wait_pending(depth - 1);
+            ptx::fence_proxy_async_smem();
+            ptx::mbar_arrive(&ready_bar[published % S]);
+            ++published;
+          }
+        }
+      }
+      ptx::cp_async_wait_pending(0);
+      ptx::fence_proxy_async_smem();
+      for (; published < nkb; ++published) ptx::mbar_arrive(&ready_bar[published % S]);
     }
   }
   __syncwarp();  // producer / MMA warps reconverge before joining the epilogue
@@ -1020,11 +1145,25 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   const int BK = 128 / esz;
   MVAE_REQUIRE(g.kind == MVAE_F32 || g.kind == MVAE_BF16, "gemm: bad kind %d", g.kind);
   MVAE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-  MVAE_REQUIRE((g.lda * esz) % 16 == 0 && (g.ldb * esz) % 16 == 0, "gemm: lda/ldb (%lld,%lld) must be 16-byte multiples",
-               g.lda, g.ldb);
-  MVAE_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
+  MVAE_REQUIRE((g.gather.mode == 1 || (g.lda * esz) % 16 == 0) && (g.gather.mode == 2 || (g.ldb * esz) % 16 == 0),
+               "gemm: lda/ldb (%lld,%lld) must be 16-byte multiples", g.lda, g.ldb);
+  MVAE_REQUIRE((g.gather.mode == 1 || (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
+                   (g.gather.mode == 2 || (reinterpret_cast<uintptr_t>(g.B) & 15) == 0),
                "gemm: A/B must be 16-byte aligned");
   const GemmEpilogue& e = g.epi;
+  const ConvGather& cg = g.gather;
+  if (cg.mode != 0) {
+    MVAE_REQUIRE(cg.mode == 1 || cg.mode == 2, "gemm: bad gather mode %d", cg.mode);
+    MVAE_REQUIRE(g.kind == MVAE_BF16, "gemm: the implicit patch-matrix operand is implemented for bf16 storage only");
+    MVAE_REQUIRE(cg.X != nullptr && (reinterpret_cast<uintptr_t>(cg.X) & 15) == 0, "gemm: gather source must be 16-byte aligned");
+    MVAE_REQUIRE(cg.C > 0 && cg.C % 8 == 0 && cg.sn % 8 == 0 && cg.sh % 8 == 0 && cg.sw % 8 == 0,
+                 "gemm: gather needs channels and strides that are multiples of 8 (16-byte chunks never straddle a tap)");
+    MVAE_REQUIRE(cg.ksize > 0 && cg.stride > 0 && cg.Ho > 0 && cg.Wo > 0, "gemm: bad gather geometry");
+    MVAE_REQUIRE(!g.atf.enabled && !(e.kind == EPI_STORE && e.fuse_bn), "gemm: gather excludes the A transform / fused BatchNorm");
+    MVAE_REQUIRE(e.kind == EPI_STORE || e.kind == EPI_ATOMIC, "gemm: gather supports the store / accumulate epilogues");
+    if (cg.mode == 1) MVAE_REQUIRE(!g.a_mn && g.K == cg.ksize * cg.ksize * cg.C, "gemm: gather A needs K = k*k*C, K-major");
+    if (cg.mode == 2) MVAE_REQUIRE(g.b_mn && g.N == cg.ksize * cg.ksize * cg.C, "gemm: gather B needs N = k*k*C, MN-major");
+  }
   MVAE_REQUIRE(e.C != nullptr, "gemm: null output");
   MVAE_REQUIRE(e.kind != EPI_ATOMIC || e.c_dtype == MVAE_F32, "gemm: atomic epilogue needs fp32 output");
 
@@ -1091,7 +1230,9 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     const int b_stage = (b_tx + 1023) / 1024 * 1024;
     const int stage_bytes = kAStageBytes + b_stage;
     const int staging = kBlockM * (bn + kStagePad) * 4;
-    int stages = g.stages > 0 ? g.stages : env_int("MVAE_GEMM_STAGES", ctas > sms ? 2 : 4);
+    int stages = g.stages > 0 ? g.stages
+                 : g.gather.mode != 0 ? env_int("MVAE_GATHER_STAGES", 3)   // gathered stages need more lead time than TMA
+                                      : env_int("MVAE_GEMM_STAGES", ctas > sms ? 2 : 4);
     if (stages > kbps) stages = kbps;
     if (stages > kMaxStages) stages = kMaxStages;
     const int max_dyn = 227 * 1024 - 2048;
@@ -1161,16 +1302,20 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
             g.M, g.N, g.K, g.kind, e.kind, g.a_mn, g.b_mn, block_n, split, stages, dyn, tiles_n, tiles_m, split);
 
   CUtensorMap ta, tb;
-  if (!g.a_mn) {
+  if (cg.mode == 1) {
+  } else if (!g.a_mn) {
     if (make_tmap(&ta, g.kind, g.A, g.M, g.K, g.lda, BK, kBlockM, false)) return 1;
   } else {
     if (make_tmap(&ta, g.kind, g.A, g.K, g.M, g.lda, BK, BK, true)) return 1;
   }
-  if (!g.b_mn) {
+  if (cg.mode == 2) {
+  } else if (!g.b_mn) {
     if (make_tmap(&tb, g.kind, g.B, g.N, g.K, g.ldb, BK, block_n, false)) return 1;
   } else {
     if (make_tmap(&tb, g.kind, g.B, g.K, g.N, g.ldb, BK, BK, true)) return 1;
   }
+  if (cg.mode == 1) ta = tb;  // the gathered operand has no tensor map; the kernel never touches this copy
+  if (cg.mode == 2) tb = ta;
 
   GemmKParams kp;
   kp.M = g.M; kp.N = g.N; kp.K = g.K;
@@ -1208,6 +1353,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   if (kp.direct_bce) kp.aux_off = -1;   // targets are read straight from global memory, one row run per thread
   kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
+  kp.gather = cg;
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");
   if (e.kind == EPI_DGRAD_BN)
     MVAE_REQUIRE(e.hpre && e.bn_mean && e.bn_rstd && e.bn_gamma && e.bn_beta, "gemm: dgrad-BN epilogue needs BN state");

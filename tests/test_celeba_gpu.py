@@ -72,6 +72,46 @@ def test_im2col_col2im_nchw_strided():
     assert rel(y, back) < 1e-6
 
 
+@pytest.mark.parametrize("cfg", [(8, 32, 32, 64, 4, 2, 1), (5, 8, 128, 256, 4, 1, 0), (3, 25, 32, 64, 4, 2, 1),
+                                 (6, 12, 64, 40, 4, 2, 1), (2, 23, 32, 8, 5, 2, 1), (4, 16, 8, 300, 4, 2, 1)])
+def test_implicit_gemm_equals_im2col_then_gemm(cfg):
+    """mvae_conv_gemm (the patch matrix gathered inside the GEMM) is bit-identical to mvae_im2col + mvae_gemm: forward /
+    transposed-conv dgrad form (patch matrix = A) and weight-gradient form (patch matrix = B, pixels contracted)."""
+    ops, _ = _ops()
+    B, H, Cc, Co, k, s, p = cfg
+    g = torch.Generator().manual_seed(11)
+    bf = torch.bfloat16
+    x = torch.randn(B, H, H, Cc, generator=g).to(bf).cuda()
+    Ho = ops.out_size(H, k, s, p)
+    rows, K = B * Ho * Ho, k * k * Cc
+    geo = ops.geometry(B, H, H, Cc, k, s, p)
+    col = torch.empty(rows, K, device="cuda", dtype=bf)
+    ops.im2col(geo, x, col, K)
+    w = (torch.randn(Co, K, generator=g) / K ** 0.5).to(bf).cuda()
+    ldo = (Co + 7) // 8 * 8
+    for block_n, stages in ((0, 0), (64, 2), (128, 4), (32, 1)):
+        y_ref = torch.zeros(rows, ldo, device="cuda", dtype=bf)
+        y_imp = torch.zeros(rows, ldo, device="cuda", dtype=bf)
+        ops.gemm(col, w, y_ref, rows, Co, K, K, K, ldo, block_n=block_n, stages=stages)
+        ops.gemm(x, w, y_imp, rows, Co, K, 0, K, ldo, patch=(geo, 1), block_n=block_n, stages=stages)
+        assert torch.equal(y_ref, y_imp), (cfg, block_n, stages, float((y_ref.float() - y_imp.float()).abs().max()))
+    # weight gradient: dW[Co, K] = dy^T col, both operands with the pixel index as the contraction
+    dy = torch.randn(rows, ldo, generator=g).to(bf).cuda()
+    for block_n, stages, split in ((0, 0, 1), (256, 3, 1), (64, 2, 1), (0, 0, 0)):
+        dw_ref = torch.zeros(Co, K, device="cuda")
+        dw_imp = torch.zeros(Co, K, device="cuda")
+        ops.gemm(dy, col, dw_ref, Co, K, rows, ldo, K, K, a_major=1, b_major=1, accumulate=True, split_k=split,
+                 block_n=block_n, stages=stages)
+        ops.gemm(dy, x, dw_imp, Co, K, rows, ldo, 0, K, a_major=1, b_major=1, accumulate=True, split_k=split,
+                 block_n=block_n, stages=stages, patch=(geo, 2))
+        if split == 1:
+            assert torch.equal(dw_ref, dw_imp), (cfg, block_n, stages, float((dw_ref - dw_imp).abs().max()))
+        else:   # split-K accumulates with atomics: order differs run to run
+            assert rel(dw_imp, dw_ref) < 1e-5
+    ref = dy[:, :Co].float().t() @ col.float()
+    assert rel(dw_imp, ref) < 2e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(3 * 40, 64, 40), (1000, 32, 1000), (257, 256, 257), (96, 1024, 32)])
 def test_bn_swish_forward_backward(dtype, shape):
