@@ -14,6 +14,8 @@ to the first Dropout is shared and the masks are applied to replicated rows); th
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -147,6 +149,9 @@ class ConvMVAEBase:
         # kernels of the main stream; fork / join are stream-ordered events (valid under CUDA-graph capture)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.use_side_stream = True
+        # implicit GEMM (mvae_conv_gemm): patch matrices of layers with >= 8 bf16 channels are gathered inside the GEMM
+        # instead of being written by mvae_im2col and read back (MVAE_IMPLICIT_CONV=0 restores the explicit path)
+        self.implicit_conv = self.act_dtype == torch.bfloat16 and os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
         # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
         # own stream beside the image networks
         self.mod_stream = torch.cuda.Stream(device=dev)
@@ -349,6 +354,11 @@ class ConvMVAEBase:
             self._side_forked = False
 
     # ------------------------------------------------------------------ conv stacks
+    def _implicit(self, channels: int, channels_last: bool = True) -> bool:
+        """Gather the patch matrix inside the GEMM?  (bf16 storage, channels-last source whose channel count is a multiple
+        of 8; the encoder's first layer reads the caller's NCHW fp32 image and keeps the explicit im2col.)"""
+        return self.implicit_conv and channels_last and channels % 8 == 0
+
     def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
         """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
         NHWC bottleneck [B, FLAT_HW * FLAT_C]."""
@@ -359,10 +369,13 @@ class ConvMVAEBase:
             ldk = ws.enc_ldk[li]
             strides = _ops.nchw_strides(self.IMG_C, self.IMG_H, self.IMG_H) if li == 0 else None
             g = _ops.geometry(B, hin, hin, ci, k, s, p, strides)
-            _ops.im2col(g, src, ws.enc_col[li], ldk)
             rows = B * ho * ho
             w, ldw = self.operand(pre + ".weight", co, K)
-            _ops.gemm(ws.enc_col[li], w, ws.enc_pre[li], rows, co, K, ldk, ldw, co)
+            if self._implicit(ci, li > 0):
+                _ops.gemm(src, w, ws.enc_pre[li], rows, co, K, 0, ldw, co, patch=(g, 1))
+            else:
+                _ops.im2col(g, src, ws.enc_col[li], ldk)
+                _ops.gemm(ws.enc_col[li], w, ws.enc_pre[li], rows, co, K, ldk, ldw, co)
             if bn:
                 rm, rv = self.running(bn)
                 a = _ops.bn_args(ws.enc_pre[li], rows, co, rows, SWISH, training, self.P(bn + ".weight"), self.P(bn + ".bias"),
@@ -388,8 +401,15 @@ class ConvMVAEBase:
             else:
                 _ops.act_backward(SWISH, ws.enc_pre[li], ws.enc_dact[li], ws.enc_dpre[li], rows, co)
             # dW'[co, K] += dpre^T col   (side stream: overlaps the dgrad GEMM / col2im / BatchNorm backward of the next layer)
-            self._wgrad_aside(lambda li=li, pre=pre, co=co, K=K, rows=rows, ldk=ldk: _ops.gemm(
-                ws.enc_dpre[li], ws.enc_col[li], self.G(pre + ".weight"), co, K, rows, co, ldk, K, a_major=1, b_major=1, accumulate=True))
+            if self._implicit(ci, li > 0):
+                gi = _ops.geometry(B, hin, hin, ci, k, s, p)
+                self._wgrad_aside(lambda li=li, pre=pre, co=co, K=K, rows=rows, gi=gi: _ops.gemm(
+                    ws.enc_dpre[li], ws.enc_act[li - 1], self.G(pre + ".weight"), co, K, rows, co, 0, K, a_major=1, b_major=1,
+                    accumulate=True, patch=(gi, 2)))
+            else:
+                self._wgrad_aside(lambda li=li, pre=pre, co=co, K=K, rows=rows, ldk=ldk: _ops.gemm(
+                    ws.enc_dpre[li], ws.enc_col[li], self.G(pre + ".weight"), co, K, rows, co, ldk, K, a_major=1, b_major=1,
+                    accumulate=True))
             if li > 0:
                 w, ldw = self._operand_cached(pre + ".weight", K)
                 _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
@@ -440,14 +460,22 @@ class ConvMVAEBase:
                 _ops.bn_act_backward(ws.dec_bn[li], dsrc, ws.dec_dpre[li], ws.dec_s0[li], ws.dec_s1[li], self.G(bn + ".weight"),
                                      self.G(bn + ".bias"))
                 dsrc = ws.dec_dpre[li]
-            self._join_side()                                          # the previous layer's weight gradient still reads colbuf
-            _ops.im2col(g, dsrc, ws.colbuf, ldk)                       # dcol [M_in, (kh,kw,co)]
             x_in = ws.dec_act[li - 1] if li > 0 else ws.u1             # the layer's input [M_in, ci]
-            self._wgrad_aside(lambda x_in=x_in, pre=pre, ci=ci, K=K, rows_in=rows_in, ldk=ldk: _ops.gemm(
-                x_in, ws.colbuf, self.G(pre + ".weight"), ci, K, rows_in, ci, ldk, K, a_major=1, b_major=1, accumulate=True))
             dx = ws.dec_dact[li - 1] if li > 0 else ws.du1
             w, ldw = self._operand_cached(pre + ".weight", K)
-            _ops.gemm(ws.colbuf, w, dx, rows_in, ci, K, ldk, ldw, ci)
+            if self._implicit(co, li < last):
+                # dcol = im2col(dOut) is never written: gathered as the B operand of the weight gradient and as the A
+                # operand of the input gradient
+                self._wgrad_aside(lambda x_in=x_in, pre=pre, ci=ci, K=K, rows_in=rows_in, g=g, dsrc=dsrc: _ops.gemm(
+                    x_in, dsrc, self.G(pre + ".weight"), ci, K, rows_in, ci, 0, K, a_major=1, b_major=1, accumulate=True,
+                    patch=(g, 2)))
+                _ops.gemm(dsrc, w, dx, rows_in, ci, K, 0, ldw, ci, patch=(g, 1))
+            else:
+                self._join_side()                                      # the previous layer's weight gradient still reads colbuf
+                _ops.im2col(g, dsrc, ws.colbuf, ldk)                   # dcol [M_in, (kh,kw,co)]
+                self._wgrad_aside(lambda x_in=x_in, pre=pre, ci=ci, K=K, rows_in=rows_in, ldk=ldk: _ops.gemm(
+                    x_in, ws.colbuf, self.G(pre + ".weight"), ci, K, rows_in, ci, ldk, K, a_major=1, b_major=1, accumulate=True))
+                _ops.gemm(ws.colbuf, w, dx, rows_in, ci, K, ldk, ldw, ci)
             dsrc = dx
         self._join_side()
 
@@ -469,7 +497,7 @@ class ConvMVAEBase:
             rows = B * ho * ho
             ldk = round_up(k * k * ci, self.vec)
             ws.enc_ldk.append(ldk)
-            ws.enc_col.append(buf(rows * ldk))
+            ws.enc_col.append(None if self._implicit(ci, li > 0) else buf(rows * ldk))
             ws.enc_pre.append(buf(rows * co))
             ws.enc_act.append(buf(rows * co))
             ws.enc_dact.append(buf(rows * co))

@@ -77,6 +77,7 @@ static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int
     g.gather.Ho = (cg->height + 2 * cg->pad - cg->kernel) / cg->stride + 1;
     g.gather.Wo = (cg->width + 2 * cg->pad - cg->kernel) / cg->stride + 1;
     g.gather.sn = cg->stride_n; g.gather.sh = cg->stride_h; g.gather.sw = cg->stride_w;
+    g.gather.extent = (cg->batch - 1) * cg->stride_n + (cg->height - 1) * cg->stride_h + (cg->width - 1) * cg->stride_w + cg->channels;
     const long long pixels = static_cast<long long>(cg->batch) * g.gather.Ho * g.gather.Wo;
     MVAE_REQUIRE(pixels == (patch_operand == 1 ? a->M : a->K), "mvae_conv_gemm: %lld output pixels do not match the GEMM shape",
                  pixels);

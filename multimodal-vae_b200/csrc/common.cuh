@@ -111,6 +111,8 @@ struct ConvGather {
   const void* X = nullptr;
   int H = 0, W = 0, C = 0, ksize = 0, stride = 1, pad = 0, Ho = 0, Wo = 0;
   long long sn = 0, sh = 0, sw = 0;  // element strides of X (channel stride 1)
+  long long extent = 0;              // elements spanned by X (32-bit offsets inside the kernel)
+  unsigned long long magic_hw = 0, magic_w = 0;  // filled by launch_gemm: multiply-shift division by Ho*Wo and Wo
 };
 
 struct GemmDesc {

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-      ptx::mbar_init(&ready_bar[s], 128);
+      ptx::mbar_init(&ready_bar[s], p.gather.mode != 0 ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
     }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_mbar_init();
@@ -562,119 +562,118 @@ __global__ void __launch_bounds__(kGemmThreads)
     }
   } else if (warp >= 4 && p.gather.mode != 0) {
     // ------------------------------------------------------------ implicit patch-matrix operand (warps 4..7)
-    // The convolution's im2col matrix is never materialised: these 128 threads copy 16-byte chunks (8 bf16 channels of
-    // one filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of
-    // row r lives at physical chunk c ^ (r & 7)); padding and out-of-range rows are zero-filled by cp.async.  Up to
-    // `depth` stages are in flight per thread; a finished stage is published through ready_bar after a proxy fence.
-    if constexpr (kKind == MVAE_BF16) {
+    // The convolution's im2col matrix is never materialised: these threads copy 16-byte chunks (8 bf16 channels of one
+    // filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of row r
+    // lives at physical chunk c ^ (r & 7)); padding and out-of-range rows are zero-filled by cp.async.  Two groups of
+    // 64 threads own the even / odd ring SLOTS (warps 4,5 / 6,7), so two stages are in flight and each is published
+    // through ready_bar (proxy fence first) the moment it lands - the same decoupling TMA gives the other operand.
+    // (Ownership is by slot, not by stage index: a group then sees every phase of its slots' barriers in order.)
+    if constexpr (kKind == MVAE_BF16 && (kEpi == EPI_STORE || kEpi == EPI_ATOMIC)) {
       const ConvGather& cg = p.gather;
-      const int tt = threadIdx.x - 128;
-      const int c = tt & 7, rbase = tt >> 3;
-      const uint32_t chunk_off = static_cast<uint32_t>((c ^ (rbase & 7)) << 4);
+      const int grp = (warp - 4) >> 1;
+      const int t64 = threadIdx.x & 63;
+      const int c = t64 & 7, rbase = t64 >> 3;   // chunk column; rows rbase + 8 j  ((row & 7) == rbase)
+      const uint32_t chunk_off = static_cast<uint32_t>((c ^ rbase) << 4);
       const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(cg.X);
-      const int depth = S < 4 ? S : 4;
-      const int hw = cg.Ho * cg.Wo;
-      int published = 0;
+      const uint32_t hw = static_cast<uint32_t>(cg.Ho * cg.Wo);
+      // pixel index -> element offset of the patch origin and (hi0 << 16 | wi0 & 0xffff); exact magic-number division
+      auto locate = [&](uint32_t m, bool valid, int& off, int& hw0) {
+        const uint32_t n = static_cast<uint32_t>((static_cast<unsigned long long>(m) * cg.magic_hw) >> 40);
+        const uint32_t rem = m - n * hw;
+        const uint32_t ho = static_cast<uint32_t>((static_cast<unsigned long long>(rem) * cg.magic_w) >> 40);
+        const uint32_t wo = rem - ho * static_cast<uint32_t>(cg.Wo);
+        const int hi0 = valid ? static_cast<int>(ho) * cg.stride - cg.pad : -20000;
+        const int wi0 = static_cast<int>(wo) * cg.stride - cg.pad;
+        off = valid ? static_cast<int>(n) * static_cast<int>(cg.sn) + hi0 * static_cast<int>(cg.sh) + wi0 * static_cast<int>(cg.sw) : 0;
+        hw0 = (hi0 << 16) | (wi0 & 0xffff);
+      };
       if (cg.mode == 1) {
-        // A[m, k]: this thread owns chunk column c of rows rbase + 16 j (fixed pixels), k advances with the stage
-        long long off[8];
-        int hi0[8], wi0[8];
+        // A[m, k]: fixed pixels (16 rows per thread), k advances with the stage
+        int off[16], hw0[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int m = m0 + rbase + 16 * j;
-          hi0[j] = -(1 << 28);
-          wi0[j] = 0;
-          off[j] = 0;
-          if (m < p.M) {
-            const int n = m / hw, rem = m - n * hw;
-            const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
-            hi0[j] = ho * cg.stride - cg.pad;
-            wi0[j] = wo * cg.stride - cg.pad;
-            off[j] = n * cg.sn + hi0[j] * cg.sh + wi0[j] * cg.sw;
-          }
+        for (int j = 0; j < 16; ++j) {
+          const int m = m0 + rbase + 8 * j;
+          locate(static_cast<uint32_t>(m), m < p.M, off[j], hw0[j]);
         }
+        int k0 = kb0 * BK + c * 8;
+        int tap = k0 / cg.C, ch = k0 - tap * cg.C;
+        int kh = tap / cg.ksize, kw = tap - kh * cg.ksize;
         for (int i = 0; i < nkb; ++i) {
           const int s = i % S;
-          const uint32_t ph = (i / S) & 1;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
-          const int k0 = (kb0 + i) * BK + c * 8;
-          const int tap = k0 / cg.C, ch = k0 - tap * cg.C;
-          const int kh = tap / cg.ksize, kw = tap - kh * cg.ksize;
-          const long long koff = kh * cg.sh + kw * cg.sw + ch;
-          const bool kvalid = k0 < p.K;
+          if ((s & 1) == grp) {
+            const uint32_t ph = (i / S) & 1;
+            const int koff = kh * static_cast<int>(cg.sh) + kw * static_cast<int>(cg.sw) + ch;
+            const bool kvalid = k0 < p.K;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+            const uint32_t dst = ptx::smem_u32(smem + s * stage_bytes) + rbase * 128 + chunk_off;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = rbase + 16 * j;
-            const int hi = hi0[j] + kh, wi = wi0[j] + kw;
-            const bool ok = kvalid && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
-                            static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
-            ptx::cp_async16_zfill(a_base + r * 128 + chunk_off, ok ? X + off[j] + koff : X, ok ? 16u : 0u);
-          }
-          ptx::cp_async_commit();
-          if (i >= depth - 1) {
-            ptx::cp_async_wait_pending(depth - 1);
+            for (int j = 0; j < 16; ++j) {
+              const int hi = (hw0[j] >> 16) + kh, wi = ((hw0[j] << 16) >> 16) + kw;
+              const bool ok = kvalid && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
+                              static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
+              ptx::cp_async16_zfill(dst + j * (8 * 128), ok ? X + (off[j] + koff) : X, ok ? 16u : 0u);
+            }
+            ptx::cp_async_commit();
+            ptx::cp_async_wait_pending(0);
             ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(&ready_bar[published % S]);
-            ++published;
+            ptx::mbar_arrive(&ready_bar[s]);
+          }
+          // the next stage: BK further along (kh, kw, c)
+          k0 += BK;
+          ch += BK;
+          while (ch >= cg.C) {
+            ch -= cg.C;
+            if (++kw == cg.ksize) {
+              kw = 0;
+              ++kh;
+            }
           }
         }
       } else {
         // B, MN-major: stage row kr = reduction index (pixel (kb0+i)*BK + kr), 128-byte column boxes of 64 patch
-        // entries; this thread owns chunk c of every box (fixed taps / channels) for rows rbase + 16 jr
+        // entries; this thread owns chunk c of every box (fixed taps / channels) for rows rbase + 8 jr
         const uint32_t b_boxes = static_cast<uint32_t>((p.block_n + ATOM - 1) / ATOM);
-        long long koff[4];
-        int kh[4], kw[4];
+        int koff[4], khw[4];
         bool kvalid[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k0 = n0 + j * ATOM + c * 8;
           const int tap = k0 / cg.C, ch = k0 - tap * cg.C;
-          kh[j] = tap / cg.ksize;
-          kw[j] = tap - kh[j] * cg.ksize;
-          koff[j] = kh[j] * cg.sh + kw[j] * cg.sw + ch;
+          const int kh = tap / cg.ksize, kw = tap - kh * cg.ksize;
+          khw[j] = (kh << 16) | kw;
+          koff[j] = kh * static_cast<int>(cg.sh) + kw * static_cast<int>(cg.sw) + ch;
           kvalid[j] = static_cast<uint32_t>(j) < b_boxes && k0 < p.N;
         }
         for (int i = 0; i < nkb; ++i) {
           const int s = i % S;
+          if ((s & 1) != grp) continue;
           const uint32_t ph = (i / S) & 1;
+          int off[8], hw0[8];
+#pragma unroll
+          for (int jr = 0; jr < 8; ++jr) {
+            const int m = (kb0 + i) * BK + rbase + 8 * jr;
+            locate(static_cast<uint32_t>(m), m < p.K, off[jr], hw0[jr]);
+          }
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          const uint32_t b_base = ptx::smem_u32(smem + s * stage_bytes) + kAStageBytes;
+          const uint32_t dst = ptx::smem_u32(smem + s * stage_bytes) + kAStageBytes + rbase * 128 + chunk_off;
 #pragma unroll
-          for (int jr = 0; jr < BK / 16; ++jr) {
-            const int kr = rbase + 16 * jr;
-            const int m = (kb0 + i) * BK + kr;
-            int hi0 = -(1 << 28), wi0 = 0;
-            long long off = 0;
-            if (m < p.K) {
-              const int n = m / hw, rem = m - n * hw;
-              const int ho = rem / cg.Wo, wo = rem - ho * cg.Wo;
-              hi0 = ho * cg.stride - cg.pad;
-              wi0 = wo * cg.stride - cg.pad;
-              off = n * cg.sn + hi0 * cg.sh + wi0 * cg.sw;
-            }
+          for (int j = 0; j < 4; ++j) {
+            if (static_cast<uint32_t>(j) < b_boxes) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (static_cast<uint32_t>(j) < b_boxes) {
-                const int hi = hi0 + kh[j], wi = wi0 + kw[j];
+              for (int jr = 0; jr < 8; ++jr) {
+                const int hi = (hw0[jr] >> 16) + (khw[j] >> 16), wi = ((hw0[jr] << 16) >> 16) + (khw[j] & 0xffff);
                 const bool ok = kvalid[j] && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
                                 static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
-                ptx::cp_async16_zfill(b_base + j * (BK * 128) + kr * 128 + chunk_off, ok ? X + off + koff[j] : X, ok ? 16u : 0u);
+                ptx::cp_async16_zfill(dst + j * (BK * 128) + jr * (8 * 128), ok ? X + (off[jr] + koff[j]) : X, ok ? 16u : 0u);
               }
             }
           }
           ptx::cp_async_commit();
-          if (i >= depth - 1) {
-            ptx::cp_async_wait_pending(depth - 1);
-            ptx::fence_proxy_async_smem();
-            ptx::mbar_arrive(&ready_bar[published % S]);
-            ++published;
-          }
+          ptx::cp_async_wait_pending(0);
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ready_bar[s]);
         }
       }
-      ptx::cp_async_wait_pending(0);
-      ptx::fence_proxy_async_smem();
-      for (; published < nkb; ++published) ptx::mbar_arrive(&ready_bar[published % S]);
     }
   }
   __syncwarp();  // producer / MMA warps reconverge before joining the epilogue
@@ -1161,6 +1160,9 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(cg.ksize > 0 && cg.stride > 0 && cg.Ho > 0 && cg.Wo > 0, "gemm: bad gather geometry");
     MVAE_REQUIRE(!g.atf.enabled && !(e.kind == EPI_STORE && e.fuse_bn), "gemm: gather excludes the A transform / fused BatchNorm");
     MVAE_REQUIRE(e.kind == EPI_STORE || e.kind == EPI_ATOMIC, "gemm: gather supports the store / accumulate epilogues");
+    MVAE_REQUIRE(static_cast<long long>(cg.Ho) * cg.Wo < 65536 && cg.H < 16384 && cg.W < 16384 && cg.pad < 4096,
+                 "gemm: gather geometry too large for the packed coordinates");
+    MVAE_REQUIRE(cg.extent < (1ll << 31) && (cg.mode == 1 ? g.M : g.K) < (1 << 24), "gemm: gather source too large for 32-bit offsets");
     if (cg.mode == 1) MVAE_REQUIRE(!g.a_mn && g.K == cg.ksize * cg.ksize * cg.C, "gemm: gather A needs K = k*k*C, K-major");
     if (cg.mode == 2) MVAE_REQUIRE(g.b_mn && g.N == cg.ksize * cg.ksize * cg.C, "gemm: gather B needs N = k*k*C, MN-major");
   }
@@ -1231,7 +1233,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     const int stage_bytes = kAStageBytes + b_stage;
     const int staging = kBlockM * (bn + kStagePad) * 4;
     int stages = g.stages > 0 ? g.stages
-                 : g.gather.mode != 0 ? env_int("MVAE_GATHER_STAGES", 3)   // gathered stages need more lead time than TMA
+                 : g.gather.mode != 0 ? env_int("MVAE_GATHER_STAGES", 2)   // measured: 2 > 3 > 4 > 6 (co-residency beats depth)
                                       : env_int("MVAE_GEMM_STAGES", ctas > sms ? 2 : 4);
     if (stages > kbps) stages = kbps;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -1354,6 +1356,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
   kp.gather = cg;
+  if (cg.mode != 0) {  // exact division by multiply-shift: q = (m * magic) >> 40 for m * d < 2^40
+    kp.gather.magic_hw = (1ull << 40) / static_cast<unsigned long long>(cg.Ho * cg.Wo) + 1;
+    kp.gather.magic_w = (1ull << 40) / static_cast<unsigned long long>(cg.Wo) + 1;
+  }
   if (e.kind == EPI_BCE) MVAE_REQUIRE(e.target != nullptr && e.target_rows > 0, "gemm: BCE epilogue needs a target");
   if (e.kind == EPI_DGRAD_BN)
     MVAE_REQUIRE(e.hpre && e.bn_mean && e.bn_rstd && e.bn_gamma && e.bn_beta, "gemm: dgrad-BN epilogue needs BN state");
