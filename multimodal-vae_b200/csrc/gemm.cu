@@ -285,7 +285,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
   }
 }
 
-template <int kKind, int kEpi>
+template <int kKind, int kEpi, bool kGather = false>  // kGather: one operand is an implicit patch matrix (separate instantiation)
 __global__ void __launch_bounds__(kGemmThreads)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmKParams p) {
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-      ptx::mbar_init(&ready_bar[s], p.gather.mode != 0 ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
+      ptx::mbar_init(&ready_bar[s], kGather ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
     }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_mbar_init();
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        const bool tma_a = p.gather.mode != 1, tma_b = p.gather.mode != 2;  // the gathered operand comes from warps 4..7
+        const bool tma_a = !kGather || p.gather.mode != 1, tma_b = !kGather || p.gather.mode != 2;  // the gathered operand comes from warps 4..7
         ptx::mbar_expect_tx(&full_bar[s], (tma_a ? kAStageBytes : 0) + (tma_b ? p.b_tx_bytes : 0));
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + kAStageBytes;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
-        if (p.gather.mode != 0) {  // TMA half landed AND the gathered half is in place
+        if (kGather) {  // TMA half landed AND the gathered half is in place
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::mbar_wait(&ready_bar[s], ph);
         } else {
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       ptx::mbar_arrive(&ready_bar[s]);
     }
-  } else if (warp >= 4 && p.gather.mode != 0) {
+  } else if (kGather && warp >= 4) {
     // ------------------------------------------------------------ implicit patch-matrix operand (warps 4..7)
     // The convolution's im2col matrix is never materialised: these threads copy 16-byte chunks (8 bf16 channels of one
     // filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of row r
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     // 64 threads own the even / odd ring SLOTS (warps 4,5 / 6,7), so two stages are in flight and each is published
     // through ready_bar (proxy fence first) the moment it lands - the same decoupling TMA gives the other operand.
     // (Ownership is by slot, not by stage index: a group then sees every phase of its slots' barriers in order.)
-    if constexpr (kKind == MVAE_BF16 && (kEpi == EPI_STORE || kEpi == EPI_ATOMIC)) {
+    if constexpr (kGather) {
       const ConvGather& cg = p.gather;
       const int grp = (warp - 4) >> 1;
       const int t64 = threadIdx.x & 63;
@@ -1102,23 +1102,23 @@ int make_tmap(CUtensorMap* out, int kind, const void* base, long long rows, long
   return 0;
 }
 
-template <int kKind, int kEpi>
+template <int kKind, int kEpi, bool kGather = false>
 int ensure_smem(int dyn_smem) {
   static int smem_set = 0;  // per instantiation; monotone, benign race
   if (dyn_smem > smem_set) {
     if (smem_set == 0)  // always the largest shared-memory carve-out: several CTAs per SM is the operating point
-      MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi>, cudaFuncAttributePreferredSharedMemoryCarveout,
+      MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi, kGather>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-    MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
+    MVAE_CUDA(cudaFuncSetAttribute(gemm_kernel<kKind, kEpi, kGather>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_smem));
     smem_set = dyn_smem;
   }
   return 0;
 }
-template <int kKind, int kEpi>
+template <int kKind, int kEpi, bool kGather = false>
 int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, dim3 grid, int dyn_smem,
                 cudaStream_t stream) {
-  if (int rc = ensure_smem<kKind, kEpi>(dyn_smem)) return rc;
-  return launch_pdl(gemm_kernel<kKind, kEpi>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
+  if (int rc = ensure_smem<kKind, kEpi, kGather>(dyn_smem)) return rc;
+  return launch_pdl(gemm_kernel<kKind, kEpi, kGather>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
 }
 
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
@@ -1385,6 +1385,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     if (static_cast<long long>(kp.grid_ctas) > static_cast<long long>(occ) * sm_count) return 3;
   }
   if (dry_run) return 0;
+  if (cg.mode != 0) {  // bf16 store / accumulate only (validated above)
+    if (e.kind == EPI_STORE) return launch_inst<MVAE_BF16, EPI_STORE, true>(ta, tb, kp, grid, dyn, stream);
+    return launch_inst<MVAE_BF16, EPI_ATOMIC, true>(ta, tb, kp, grid, dyn, stream);
+  }
 #define MVAE_GEMM_CASE(KIND, EPI)                                   \
   if (g.kind == KIND && e.kind == EPI) return launch_inst<KIND, EPI>(ta, tb, kp, grid, dyn, stream);
   MVAE_GEMM_CASE(MVAE_F32, EPI_STORE)
