@@ -66,6 +66,25 @@ def out_size(n, kernel, stride, pad) -> int:
     return (n + 2 * pad - kernel) // stride + 1
 
 
+def transposed_conv_classes(kernel: int, stride: int, pad: int, size_in: int):
+    """Output-parity decomposition of ConvTranspose2d (celeba/model.py:142-152, multimnist/model.py:198-210) along one axis.
+
+    out[o] = sum over (i, kh) with o = i*stride - pad + kh of x[i] * w[kh].  Outputs with o % stride == a only ever see the
+    taps kh = r + stride*t (r = (a + pad) % stride), so each class is a STRIDE-1 convolution of x with a short kernel:
+        out[stride*u + a] = sum_{t' < taps} x[u - pad_lo + t'] * w[kh[t']],   u in [0, count)
+    Returns (size_out, [dict(a, count, pad_lo, kh=[...]) per class]).  This is the index map of the implicit (col2im-free)
+    transposed convolution: a gather GEMM per class (patch matrix = A, K = taps_h*taps_w*Cin) writing interleaved rows."""
+    size_out = (size_in - 1) * stride - 2 * pad + kernel
+    classes = []
+    for a in range(stride):
+        r = (a + pad) % stride
+        taps = (kernel - r + stride - 1) // stride if kernel > r else 0
+        q = (a + pad) // stride
+        count = (size_out - a + stride - 1) // stride if size_out > a else 0
+        classes.append({"a": a, "count": count, "pad_lo": taps - 1 - q, "kh": [r + stride * (taps - 1 - t) for t in range(taps)]})
+    return size_out, classes
+
+
 def im2col(g, image, col, ldcol):
     _lib.check(_lib.load().mvae_im2col(C.byref(g), DT[image.dtype], image.data_ptr(), DT[col.dtype], col.data_ptr(),
                                        int(ldcol), stream()), "mvae_im2col")

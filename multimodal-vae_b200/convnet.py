@@ -354,10 +354,12 @@ class ConvMVAEBase:
             self._side_forked = False
 
     # ------------------------------------------------------------------ conv stacks
-    def _implicit(self, channels: int, channels_last: bool = True) -> bool:
+    def _implicit(self, channels: int, channels_last: bool, pixels: int, elements: int) -> bool:
         """Gather the patch matrix inside the GEMM?  (bf16 storage, channels-last source whose channel count is a multiple
-        of 8; the encoder's first layer reads the caller's NCHW fp32 image and keeps the explicit im2col.)"""
-        return self.implicit_conv and channels_last and channels % 8 == 0
+        of 8; the encoder's first layer reads the caller's NCHW fp32 image and keeps the explicit im2col.)  `pixels` =
+        rows of the patch matrix, `elements` = size of the gathered tensor: the kernel's 32-bit offsets and multiply-shift
+        division cover pixels < 2^24 and elements < 2^31 (mvae_conv_gemm refuses more) - beyond that the explicit path runs."""
+        return (self.implicit_conv and channels_last and channels % 8 == 0 and pixels < (1 << 24) and elements < (1 << 31))
 
     def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
         """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
@@ -371,7 +373,7 @@ class ConvMVAEBase:
             g = _ops.geometry(B, hin, hin, ci, k, s, p, strides)
             rows = B * ho * ho
             w, ldw = self.operand(pre + ".weight", co, K)
-            if self._implicit(ci, li > 0):
+            if self._implicit(ci, li > 0, rows, B * hin * hin * ci):
                 _ops.gemm(src, w, ws.enc_pre[li], rows, co, K, 0, ldw, co, patch=(g, 1))
             else:
                 _ops.im2col(g, src, ws.enc_col[li], ldk)
@@ -401,7 +403,7 @@ class ConvMVAEBase:
             else:
                 _ops.act_backward(SWISH, ws.enc_pre[li], ws.enc_dact[li], ws.enc_dpre[li], rows, co)
             # dW'[co, K] += dpre^T col   (side stream: overlaps the dgrad GEMM / col2im / BatchNorm backward of the next layer)
-            if self._implicit(ci, li > 0):
+            if self._implicit(ci, li > 0, rows, B * hin * hin * ci):
                 gi = _ops.geometry(B, hin, hin, ci, k, s, p)
                 self._wgrad_aside(lambda li=li, pre=pre, co=co, K=K, rows=rows, gi=gi: _ops.gemm(
                     ws.enc_dpre[li], ws.enc_act[li - 1], self.G(pre + ".weight"), co, K, rows, co, 0, K, a_major=1, b_major=1,
@@ -463,7 +465,7 @@ class ConvMVAEBase:
             x_in = ws.dec_act[li - 1] if li > 0 else ws.u1             # the layer's input [M_in, ci]
             dx = ws.dec_dact[li - 1] if li > 0 else ws.du1
             w, ldw = self._operand_cached(pre + ".weight", K)
-            if self._implicit(co, li < last):
+            if self._implicit(co, li < last, rows_in, M3 * hout * hout * co):
                 # dcol = im2col(dOut) is never written: gathered as the B operand of the weight gradient and as the A
                 # operand of the input gradient
                 self._wgrad_aside(lambda x_in=x_in, pre=pre, ci=ci, K=K, rows_in=rows_in, g=g, dsrc=dsrc: _ops.gemm(
@@ -497,7 +499,7 @@ class ConvMVAEBase:
             rows = B * ho * ho
             ldk = round_up(k * k * ci, self.vec)
             ws.enc_ldk.append(ldk)
-            ws.enc_col.append(None if self._implicit(ci, li > 0) else buf(rows * ldk))
+            ws.enc_col.append(None if self._implicit(ci, li > 0, rows, B * hin * hin * ci) else buf(rows * ldk))
             ws.enc_pre.append(buf(rows * co))
             ws.enc_act.append(buf(rows * co))
             ws.enc_dact.append(buf(rows * co))

@@ -157,3 +157,45 @@ def test_conv_models_layout_and_no_cpu_fallback():
         if not torch.cuda.is_available():
             with pytest.raises(Exception):
                 cls(n_latents=16)
+
+
+@pytest.mark.parametrize("k,s,p,hin", [(4, 2, 1, 8), (4, 2, 0, 2), (5, 2, 1, 12), (4, 1, 0, 5), (3, 3, 1, 4), (4, 2, 1, 5)])
+def test_transposed_conv_parity_classes_match_torch(k, s, p, hin):
+    """The index map of the implicit transposed convolution (mvae_b200._ops.transposed_conv_classes): every output-parity
+    class is a stride-1 gather GEMM; assembled, the classes reproduce F.conv_transpose2d exactly (CPU, float64)."""
+    import torch
+    import torch.nn.functional as F
+    from mvae_b200 import _ops
+    g = torch.Generator().manual_seed(k * 100 + s * 10 + p)
+    N, Ci, Co = 2, 3, 4
+    x = torch.randn(N, Ci, hin, hin, generator=g, dtype=torch.float64)
+    w = torch.randn(Ci, Co, k, k, generator=g, dtype=torch.float64)      # nn.ConvTranspose2d weight layout
+    ref = F.conv_transpose2d(x, w, stride=s, padding=p)
+    hout, classes = _ops.transposed_conv_classes(k, s, p, hin)
+    assert hout == ref.shape[-1]
+    xl = x.permute(0, 2, 3, 1)                                            # NHWC
+    out = torch.zeros(N, hout, hout, Co, dtype=torch.float64)
+    covered = torch.zeros(hout, hout, dtype=torch.int64)
+    for ca in classes:
+        for cb in classes:
+            Ta, Tb = len(ca["kh"]), len(cb["kh"])
+            if ca["count"] == 0 or cb["count"] == 0:
+                continue
+            # patch matrix A[(n,u,v), (t'h, t'w, ci)] and weights B[(t'h, t'w, ci), co]
+            A = torch.zeros(N, ca["count"], cb["count"], Ta, Tb, Ci, dtype=torch.float64)
+            for th in range(Ta):
+                for tw in range(Tb):
+                    for u in range(ca["count"]):
+                        ih = u - ca["pad_lo"] + th
+                        if not 0 <= ih < hin:
+                            continue
+                        for v in range(cb["count"]):
+                            iw = v - cb["pad_lo"] + tw
+                            if 0 <= iw < hin:
+                                A[:, u, v, th, tw] = xl[:, ih, iw]
+            Bm = torch.stack([torch.stack([w[:, :, ca["kh"][th], cb["kh"][tw]] for tw in range(Tb)]) for th in range(Ta)])
+            y = A.reshape(N * ca["count"] * cb["count"], -1) @ Bm.reshape(Ta * Tb * Ci, Co)
+            out[:, ca["a"]::s, cb["a"]::s] = y.view(N, ca["count"], cb["count"], Co)
+            covered[ca["a"]::s, cb["a"]::s] += 1
+    assert int(covered.min()) == 1 and int(covered.max()) == 1
+    torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-12, atol=1e-12)
