@@ -221,6 +221,25 @@ int mvae_conv_out_size(int in, int kernel, int stride, int pad);
  * with the pixel index as the contraction (args->B = image, b_major = 1, N = k*k*C, K = batch*Ho*Wo; weight gradients).
  * Needs C % 8 == 0 and bf16 storage; bit-identical to mvae_im2col followed by mvae_gemm. */
 int mvae_conv_gemm(const mvae_gemm_args* args, const mvae_conv_geometry* geometry, int patch_operand, void* stream);
+
+/* DRAFT (not on any product path yet; its GPU parity test is gated behind MVAE_TEST_CONVT=1 until it has run on a B200):
+ * one output-parity class of a ConvTranspose2d forward / Conv2d input gradient as an implicit GEMM, i.e. without the
+ * [pixels, k*k*C_out] patch matrix and without mvae_col2im (celeba/model.py:142-152, multimnist/model.py:198-210):
+ *   out[n, s*u + a, s*v + b, :] = sum_{th, tw, ci} x[n, u - pad_h + th, v - pad_w + tw, ci] * W[ci, kh[th], kw[tw], :]
+ * x: channels-last bf16 [batch, in_h, in_w, channels] (channels % 64 == 0); weight: bf16 [channels, kernel*kernel, out_channels]
+ * (ld_tap elements between taps); out: channels-last image [batch, out_h, out_w, ldc] (bf16 / fp32, ldc % 8 == 0).
+ * The host loops over the stride*stride classes; mvae_b200._ops.transposed_conv_classes() derives the fields. */
+typedef struct mvae_convt_class {
+  int batch, in_h, in_w, channels;
+  int out_h, out_w, out_channels;
+  int kernel, stride;
+  int a, b;                         /* output parity (row, column) of this class */
+  int count_h, count_w;             /* class grid: output rows s*u + a for u < count_h */
+  int taps_h, taps_w, pad_h, pad_w; /* tap window of the class (stride-1 gather over x) */
+  int kh[8], kw[8];                 /* kernel row / column used by window position t */
+} mvae_convt_class;
+int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, const void* weight, int64_t ld_tap, void* out,
+                          int64_t ldc, int out_dtype, void* stream);
 /* col[m, (kh*k+kw)*C + c] = image[n, ho*s-p+kh, wo*s-p+kw, c] (0 outside), m = (n*Ho+ho)*Wo+wo.
  * replaces: the patch gather inside nn.Conv2d forward / ConvTranspose2d backward (celeba/model.py:101-113, 142-152). */
 int mvae_im2col(const mvae_conv_geometry* g, int image_dtype, const void* image, int col_dtype, void* col, int64_t ldcol,

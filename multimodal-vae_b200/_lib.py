@@ -188,8 +188,22 @@ class LogSoftmaxNllArgs(C.Structure):
                 ("grad_dtype", c_int), ("dlogits", c_void_p), ("ld_dlogits", c_int64)]
 
 
+class ConvTClass(C.Structure):
+    """mvae_convt_class: one output-parity class of a transposed convolution (include/mvae_b200.h)."""
+    _fields_ = [
+        ("batch", c_int), ("in_h", c_int), ("in_w", c_int), ("channels", c_int),
+        ("out_h", c_int), ("out_w", c_int), ("out_channels", c_int),
+        ("kernel", c_int), ("stride", c_int),
+        ("a", c_int), ("b", c_int),
+        ("count_h", c_int), ("count_w", c_int),
+        ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int),
+        ("kh", c_int * 8), ("kw", c_int * 8),
+    ]
+
+
 def _conv_argtypes(lib) -> None:
     P = C.POINTER
+    lib.mvae_convt_class_gemm.argtypes = [P(ConvTClass), c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]
     lib.mvae_conv_out_size.argtypes = [c_int] * 4
     lib.mvae_im2col.argtypes = [P(ConvGeometry), c_int, c_void_p, c_int, c_void_p, c_int64, c_void_p]
     lib.mvae_col2im.argtypes = [P(ConvGeometry), c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p]

@@ -85,6 +85,32 @@ def transposed_conv_classes(kernel: int, stride: int, pad: int, size_in: int):
     return size_out, classes
 
 
+def transposed_conv_implicit(x, weight, out, batch, size_in, channels, out_channels, kernel, stride, pad, ldc=None):
+    """DRAFT (see include/mvae_b200.h, mvae_convt_class_gemm): ConvTranspose2d forward / Conv2d input gradient without the
+    patch matrix - one gather GEMM per output-parity class writing the interleaved rows of `out` [batch, H_out, H_out, ldc].
+    x: [batch, size_in, size_in, channels] bf16 channels-last; weight: [channels, kernel, kernel, out_channels] bf16."""
+    size_out, classes = transposed_conv_classes(kernel, stride, pad, size_in)
+    lib = _lib.load()
+    for ca in classes:
+        for cb in classes:
+            if ca["count"] == 0 or cb["count"] == 0 or not ca["kh"] or not cb["kh"]:
+                continue   # (a class without taps would be all zeros: not produced by the geometries of the reference)
+            c = _lib.ConvTClass()
+            c.batch, c.in_h, c.in_w, c.channels = int(batch), int(size_in), int(size_in), int(channels)
+            c.out_h, c.out_w, c.out_channels = size_out, size_out, int(out_channels)
+            c.kernel, c.stride, c.a, c.b = int(kernel), int(stride), ca["a"], cb["a"]
+            c.count_h, c.count_w = ca["count"], cb["count"]
+            c.taps_h, c.taps_w, c.pad_h, c.pad_w = len(ca["kh"]), len(cb["kh"]), ca["pad_lo"], cb["pad_lo"]
+            for t, v in enumerate(ca["kh"]):
+                c.kh[t] = v
+            for t, v in enumerate(cb["kh"]):
+                c.kw[t] = v
+            _lib.check(lib.mvae_convt_class_gemm(C.byref(c), DT[x.dtype], x.data_ptr(), weight.data_ptr(), int(out_channels),
+                                                 out.data_ptr(), int(ldc or out_channels), DT[out.dtype], stream()),
+                       "mvae_convt_class_gemm")
+    return size_out
+
+
 def im2col(g, image, col, ldcol):
     _lib.check(_lib.load().mvae_im2col(C.byref(g), DT[image.dtype], image.data_ptr(), DT[col.dtype], col.data_ptr(),
                                        int(ldcol), stream()), "mvae_im2col")

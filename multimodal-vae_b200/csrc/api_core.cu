@@ -65,6 +65,41 @@ int mvae_conv_gemm(const mvae_gemm_args* a, const mvae_conv_geometry* geometry, 
   return gemm_entry(a, geometry, patch_operand, stream);
 }
 
+int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, const void* weight, int64_t ld_tap, void* out,
+                          int64_t ldc, int out_dtype, void* stream) {
+  MVAE_REQUIRE(c != nullptr && x != nullptr && weight != nullptr && out != nullptr, "mvae_convt_class_gemm: null argument");
+  MVAE_REQUIRE(c->taps_h >= 1 && c->taps_h <= 8 && c->taps_w >= 1 && c->taps_w <= 8, "mvae_convt_class_gemm: 1..8 taps per axis");
+  MVAE_REQUIRE(c->count_h > 0 && c->count_w > 0, "mvae_convt_class_gemm: empty class");
+  GemmDesc g;
+  g.kind = dtype;
+  g.M = c->batch * c->count_h * c->count_w;
+  g.N = c->out_channels;
+  g.K = c->taps_h * c->taps_w * c->channels;
+  g.A = x; g.lda = 0; g.a_mn = 0;
+  g.B = weight; g.ldb = ld_tap; g.b_mn = 1;
+  g.epi.kind = EPI_STORE;
+  g.epi.C = out; g.epi.ldc = ldc; g.epi.c_dtype = out_dtype;
+  g.epi.rows_per_group = 1 << 30;
+  ConvGather& cg = g.gather;
+  cg.mode = 3;
+  cg.X = x;
+  cg.H = c->in_h; cg.W = c->in_w; cg.C = c->channels;
+  cg.ksize = c->taps_h; cg.ksize_w = c->taps_w; cg.stride = 1; cg.pad = c->pad_h; cg.pad_w = c->pad_w;
+  cg.Ho = c->count_h; cg.Wo = c->count_w;
+  cg.sw = c->channels; cg.sh = static_cast<long long>(c->in_w) * c->channels; cg.sn = cg.sh * c->in_h;
+  cg.extent = cg.sn * c->batch;
+  cg.kk = c->kernel;
+  for (int t = 0; t < 8; ++t) {
+    cg.kh_tab[t] = static_cast<signed char>(t < c->taps_h ? c->kh[t] : 0);
+    cg.kw_tab[t] = static_cast<signed char>(t < c->taps_w ? c->kw[t] : 0);
+    MVAE_REQUIRE(cg.kh_tab[t] >= 0 && cg.kh_tab[t] < c->kernel && cg.kw_tab[t] >= 0 && cg.kw_tab[t] < c->kernel,
+                 "mvae_convt_class_gemm: tap table out of range");
+  }
+  cg.sc_hout = c->out_h; cg.sc_wout = c->out_w; cg.sc_stride = c->stride; cg.sc_a = c->a; cg.sc_b = c->b;
+  note_launch(1);
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
 static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int patch_operand, void* stream) {
   MVAE_REQUIRE(a != nullptr, "mvae_gemm: null args");
   GemmDesc g;

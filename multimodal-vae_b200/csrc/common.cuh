@@ -113,6 +113,13 @@ struct ConvGather {
   long long sn = 0, sh = 0, sw = 0;  // element strides of X (channel stride 1)
   long long extent = 0;              // elements spanned by X (32-bit offsets inside the kernel)
   unsigned long long magic_hw = 0, magic_w = 0;  // filled by launch_gemm: multiply-shift division by Ho*Wo and Wo
+  // mode 3 (one output-parity class of a transposed convolution, see _ops.transposed_conv_classes): the patch matrix is A
+  // with a ksize x ksize_w tap window, pads (pad, pad_w), stride 1 over the Ho x Wo class grid; B is the weight tensor
+  // [C, kk*kk, N] read tap by tap through a rank-3 tensor map (tap of window position (th, tw) = kh_tab[th]*kk + kw_tab[tw]);
+  // row (n, u, v) of the result goes to output pixel (n, sc_stride*u + sc_a, sc_stride*v + sc_b) of an sc_hout x sc_wout image.
+  int ksize_w = 0, pad_w = 0, kk = 0;
+  signed char kh_tab[8] = {0, 0, 0, 0, 0, 0, 0, 0}, kw_tab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int sc_hout = 0, sc_wout = 0, sc_stride = 1, sc_a = 0, sc_b = 0;
 };
 
 struct GemmDesc {

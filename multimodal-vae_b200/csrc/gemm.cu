@@ -285,7 +285,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
   }
 }
 
-template <int kKind, int kEpi, bool kGather = false>  // kGather: one operand is an implicit patch matrix (separate instantiation)
+// kGather (separate instantiations): 1 = one operand is an implicit im2col patch matrix; 2 = output-parity class of a
+// transposed convolution (A gathered through a tap window, B = weights tap by tap via a rank-3 map, rows scattered)
+template <int kKind, int kEpi, int kGather = 0>
 __global__ void __launch_bounds__(kGemmThreads)
     gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmKParams p) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-      ptx::mbar_init(&ready_bar[s], kGather ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
+      ptx::mbar_init(&ready_bar[s], kGather != 0 ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
     }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_mbar_init();
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(kGemmThreads)
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        const bool tma_a = !kGather || p.gather.mode != 1, tma_b = !kGather || p.gather.mode != 2;  // the gathered operand comes from warps 4..7
+        const bool tma_a = kGather == 0 || p.gather.mode != 1, tma_b = kGather == 0 || p.gather.mode != 2;  // the gathered operand comes from warps 4..7
         ptx::mbar_expect_tx(&full_bar[s], (tma_a ? kAStageBytes : 0) + (tma_b ? p.b_tx_bytes : 0));
         uint8_t* sa = smem + s * stage_bytes;
         uint8_t* sb = sa + kAStageBytes;
@@ -457,6 +459,13 @@ __global__ void __launch_bounds__(kGemmThreads)
           for (int j = 0; j < a_boxes; ++j) ptx::tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + j * ATOM, kc);
         }
         if (!tma_b) {
+        } else if constexpr (kGather == 2) {
+          // weights of the tap this K block belongs to: window position (th, tw) -> tap kh_tab[th]*kk + kw_tab[tw]
+          const ConvGather& cg = p.gather;
+          const int w_pos = kc / cg.C, ci0 = kc - w_pos * cg.C;
+          const int th = w_pos / cg.ksize_w, tw = w_pos - th * cg.ksize_w;
+          const int tap = cg.kh_tab[th] * cg.kk + cg.kw_tab[tw];
+          for (int j = 0; j < b_boxes; ++j) ptx::tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + j * ATOM, tap, ci0);
         } else if (!p.b_mn) {
           ptx::tma_load_2d(sb, &tmB, &full_bar[s], kc, n0);
         } else {
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       for (int i = 0; i < nkb; ++i) {
         const int s = i % S;
         const uint32_t ph = (i / S) & 1;
-        if (kGather) {  // TMA half landed AND the gathered half is in place
+        if (kGather != 0) {  // TMA half landed AND the gathered half is in place
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::mbar_wait(&ready_bar[s], ph);
         } else {
@@ -560,7 +569,7 @@ __global__ void __launch_bounds__(kGemmThreads)
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       ptx::mbar_arrive(&ready_bar[s]);
     }
-  } else if (kGather && warp >= 4) {
+  } else if (kGather != 0 && warp >= 4) {
     // ------------------------------------------------------------ implicit patch-matrix operand (warps 4..7)
     // The convolution's im2col matrix is never materialised: these threads copy 16-byte chunks (8 bf16 channels of one
     // filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of row r
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     // 64 threads own the even / odd ring SLOTS (warps 4,5 / 6,7), so two stages are in flight and each is published
     // through ready_bar (proxy fence first) the moment it lands - the same decoupling TMA gives the other operand.
     // (Ownership is by slot, not by stage index: a group then sees every phase of its slots' barriers in order.)
-    if constexpr (kGather) {
+    if constexpr (kGather != 0) {
       const ConvGather& cg = p.gather;
       const int grp = (warp - 4) >> 1;
       const int t64 = threadIdx.x & 63;
@@ -576,6 +585,8 @@ __global__ void __launch_bounds__(kGemmThreads)
       const uint32_t chunk_off = static_cast<uint32_t>((c ^ rbase) << 4);
       const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(cg.X);
       const uint32_t hw = static_cast<uint32_t>(cg.Ho * cg.Wo);
+      const int win_w = kGather == 2 ? cg.ksize_w : cg.ksize;   // taps per window row
+      const int pad_w = kGather == 2 ? cg.pad_w : cg.pad;
       // pixel index -> element offset of the patch origin and (hi0 << 16 | wi0 & 0xffff); exact magic-number division
       auto locate = [&](uint32_t m, bool valid, int& off, int& hw0) {
         const uint32_t n = static_cast<uint32_t>((static_cast<unsigned long long>(m) * cg.magic_hw) >> 40);
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(kGemmThreads)
         const uint32_t ho = static_cast<uint32_t>((static_cast<unsigned long long>(rem) * cg.magic_w) >> 40);
         const uint32_t wo = rem - ho * static_cast<uint32_t>(cg.Wo);
         const int hi0 = valid ? static_cast<int>(ho) * cg.stride - cg.pad : -20000;
-        const int wi0 = static_cast<int>(wo) * cg.stride - cg.pad;
+        const int wi0 = static_cast<int>(wo) * cg.stride - pad_w;
         off = valid ? static_cast<int>(n) * static_cast<int>(cg.sn) + hi0 * static_cast<int>(cg.sh) + wi0 * static_cast<int>(cg.sw) : 0;
         hw0 = (hi0 << 16) | (wi0 & 0xffff);
       };
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(kGemmThreads)
         }
         int k0 = kb0 * BK + c * 8;
         int tap = k0 / cg.C, ch = k0 - tap * cg.C;
-        int kh = tap / cg.ksize, kw = tap - kh * cg.ksize;
+        int kh = tap / win_w, kw = tap - kh * win_w;
         for (int i = 0; i < nkb; ++i) {
           const int s = i % S;
           if ((s & 1) == grp) {
@@ -623,7 +634,7 @@ __global__ void __launch_bounds__(kGemmThreads)
           ch += BK;
           while (ch >= cg.C) {
             ch -= cg.C;
-            if (++kw == cg.ksize) {
+            if (++kw == win_w) {
               kw = 0;
               ++kh;
             }
@@ -695,6 +706,15 @@ __global__ void __launch_bounds__(kGemmThreads)
       stored_directly = true;
       const int q = warp & 3;
       const int row = m0 + q * 32 + lane;
+      long long row_off = static_cast<long long>(row) * e.ldc;
+      if constexpr (kGather == 2) {
+        // row (n, u, v) of this parity class -> pixel (n, stride*u + a, stride*v + b) of the interleaved output image
+        const ConvGather& cg = p.gather;
+        const int hw = cg.Ho * cg.Wo;
+        const int n = row / hw, rem = row - n * hw;
+        const int u = rem / cg.Wo, v2 = rem - u * cg.Wo;
+        row_off = ((static_cast<long long>(n) * cg.sc_hout + cg.sc_stride * u + cg.sc_a) * cg.sc_wout + cg.sc_stride * v2 + cg.sc_b) * e.ldc;
+      }
       const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
       for (int c = (warp >> 2) * 16; c < p.block_n; c += 32) {
         uint32_t v[16];
@@ -711,7 +731,7 @@ __global__ void __launch_bounds__(kGemmThreads)
               if (cn + j < p.N) f[j] += __ldg(e.bias + cn + j);
           }
           if (e.c_dtype == MVAE_F32) {
-            float* dst = reinterpret_cast<float*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
+            float* dst = reinterpret_cast<float*>(e.C) + row_off + cn;
             if (cn + 16 <= p.N) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -721,7 +741,7 @@ __global__ void __launch_bounds__(kGemmThreads)
                 if (cn + j < p.N) dst[j] = f[j];
             }
           } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.C) + row_off + cn;
             if (cn + 16 <= p.N) {
               uint32_t w[8];
 #pragma unroll
@@ -1102,7 +1122,24 @@ int make_tmap(CUtensorMap* out, int kind, const void* base, long long rows, long
   return 0;
 }
 
-template <int kKind, int kEpi, bool kGather = false>
+// weights [c rows, taps, n] (n contiguous, ld_tap elements between taps), bf16, box = box_n x 1 tap x box_c rows, SWIZZLE_128B
+int make_tmap_w3(CUtensorMap* out, const void* base, long long n, long long taps, long long c, long long ld_tap, int box_n,
+                 int box_c) {
+  EncodeTiledFn enc = get_encode_fn();
+  MVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(n), static_cast<cuuint64_t>(taps), static_cast<cuuint64_t>(c)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld_tap) * 2, static_cast<cuuint64_t>(taps) * static_cast<cuuint64_t>(ld_tap) * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_n), 1u, static_cast<cuuint32_t>(box_c)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (rank 3) failed (%d): n=%lld taps=%lld c=%lld ld=%lld", (int)r, n, taps, c,
+               ld_tap);
+  return 0;
+}
+
+template <int kKind, int kEpi, int kGather = 0>
 int ensure_smem(int dyn_smem) {
   static int smem_set = 0;  // per instantiation; monotone, benign race
   if (dyn_smem > smem_set) {
@@ -1114,7 +1151,7 @@ int ensure_smem(int dyn_smem) {
   }
   return 0;
 }
-template <int kKind, int kEpi, bool kGather = false>
+template <int kKind, int kEpi, int kGather = 0>
 int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, dim3 grid, int dyn_smem,
                 cudaStream_t stream) {
   if (int rc = ensure_smem<kKind, kEpi, kGather>(dyn_smem)) return rc;
@@ -1144,15 +1181,15 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   const int BK = 128 / esz;
   MVAE_REQUIRE(g.kind == MVAE_F32 || g.kind == MVAE_BF16, "gemm: bad kind %d", g.kind);
   MVAE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-  MVAE_REQUIRE((g.gather.mode == 1 || (g.lda * esz) % 16 == 0) && (g.gather.mode == 2 || (g.ldb * esz) % 16 == 0),
+  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode == 3 || (g.lda * esz) % 16 == 0) && (g.gather.mode == 2 || (g.ldb * esz) % 16 == 0),
                "gemm: lda/ldb (%lld,%lld) must be 16-byte multiples", g.lda, g.ldb);
-  MVAE_REQUIRE((g.gather.mode == 1 || (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
+  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode == 3 || (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
                    (g.gather.mode == 2 || (reinterpret_cast<uintptr_t>(g.B) & 15) == 0),
                "gemm: A/B must be 16-byte aligned");
   const GemmEpilogue& e = g.epi;
   const ConvGather& cg = g.gather;
   if (cg.mode != 0) {
-    MVAE_REQUIRE(cg.mode == 1 || cg.mode == 2, "gemm: bad gather mode %d", cg.mode);
+    MVAE_REQUIRE(cg.mode >= 1 && cg.mode <= 3, "gemm: bad gather mode %d", cg.mode);
     MVAE_REQUIRE(g.kind == MVAE_BF16, "gemm: the implicit patch-matrix operand is implemented for bf16 storage only");
     MVAE_REQUIRE(cg.X != nullptr && (reinterpret_cast<uintptr_t>(cg.X) & 15) == 0, "gemm: gather source must be 16-byte aligned");
     MVAE_REQUIRE(cg.C > 0 && cg.C % 8 == 0 && cg.sn % 8 == 0 && cg.sh % 8 == 0 && cg.sw % 8 == 0,
@@ -1162,9 +1199,18 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(e.kind == EPI_STORE || e.kind == EPI_ATOMIC, "gemm: gather supports the store / accumulate epilogues");
     MVAE_REQUIRE(static_cast<long long>(cg.Ho) * cg.Wo < 65536 && cg.H < 16384 && cg.W < 16384 && cg.pad < 4096,
                  "gemm: gather geometry too large for the packed coordinates");
-    MVAE_REQUIRE(cg.extent < (1ll << 31) && (cg.mode == 1 ? g.M : g.K) < (1 << 24), "gemm: gather source too large for 32-bit offsets");
+    MVAE_REQUIRE(cg.extent < (1ll << 31) && (cg.mode == 2 ? g.K : g.M) < (1 << 24), "gemm: gather source too large for 32-bit offsets");
     if (cg.mode == 1) MVAE_REQUIRE(!g.a_mn && g.K == cg.ksize * cg.ksize * cg.C, "gemm: gather A needs K = k*k*C, K-major");
     if (cg.mode == 2) MVAE_REQUIRE(g.b_mn && g.N == cg.ksize * cg.ksize * cg.C, "gemm: gather B needs N = k*k*C, MN-major");
+    if (cg.mode == 3) {
+      MVAE_REQUIRE(!g.a_mn && g.b_mn && e.kind == EPI_STORE, "gemm: transposed-conv class needs K-major A, MN-major weights, store epilogue");
+      MVAE_REQUIRE(cg.ksize_w > 0 && cg.ksize <= 8 && cg.ksize_w <= 8 && g.K == cg.ksize * cg.ksize_w * cg.C,
+                   "gemm: transposed-conv class needs K = taps_h*taps_w*C with at most 8 taps per axis");
+      MVAE_REQUIRE(cg.C % BK == 0, "gemm: transposed-conv class needs C %% %d == 0 (a K block never straddles a tap)", BK);
+      MVAE_REQUIRE(cg.kk > 0 && cg.sc_stride > 0 && cg.sc_a < cg.sc_stride && cg.sc_b < cg.sc_stride &&
+                       cg.sc_stride * (cg.Ho - 1) + cg.sc_a < cg.sc_hout && cg.sc_stride * (cg.Wo - 1) + cg.sc_b < cg.sc_wout,
+                   "gemm: transposed-conv class does not fit the output image");
+    }
   }
   MVAE_REQUIRE(e.C != nullptr, "gemm: null output");
   MVAE_REQUIRE(e.kind != EPI_ATOMIC || e.c_dtype == MVAE_F32, "gemm: atomic epilogue needs fp32 output");
@@ -1304,19 +1350,22 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
             g.M, g.N, g.K, g.kind, e.kind, g.a_mn, g.b_mn, block_n, split, stages, dyn, tiles_n, tiles_m, split);
 
   CUtensorMap ta, tb;
-  if (cg.mode == 1) {
+  if (cg.mode == 1 || cg.mode == 3) {
   } else if (!g.a_mn) {
     if (make_tmap(&ta, g.kind, g.A, g.M, g.K, g.lda, BK, kBlockM, false)) return 1;
   } else {
     if (make_tmap(&ta, g.kind, g.A, g.K, g.M, g.lda, BK, BK, true)) return 1;
   }
   if (cg.mode == 2) {
+  } else if (cg.mode == 3) {
+    // weights [C, kk*kk taps, N] (N contiguous, ldb elements between taps): one 64 x 1 x BK box per tap and column block
+    if (make_tmap_w3(&tb, g.B, g.N, static_cast<long long>(cg.kk) * cg.kk, cg.C, g.ldb, BK, BK)) return 1;
   } else if (!g.b_mn) {
     if (make_tmap(&tb, g.kind, g.B, g.N, g.K, g.ldb, BK, block_n, false)) return 1;
   } else {
     if (make_tmap(&tb, g.kind, g.B, g.K, g.N, g.ldb, BK, BK, true)) return 1;
   }
-  if (cg.mode == 1) ta = tb;  // the gathered operand has no tensor map; the kernel never touches this copy
+  if (cg.mode == 1 || cg.mode == 3) ta = tb;  // the gathered operand has no tensor map; the kernel never touches this copy
   if (cg.mode == 2) tb = ta;
 
   GemmKParams kp;
@@ -1356,6 +1405,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
   kp.gather = cg;
+  if (cg.mode == 3) {
+    kp.gather.mode = 1;  // inside the kernel: A is the gathered operand (instantiation kGather = 2)
+    MVAE_REQUIRE(kp.direct_store, "gemm: transposed-conv class needs the direct store epilogue (ldc %% 8 == 0, aligned C, no statistics)");
+  }
   if (cg.mode != 0) {  // exact division by multiply-shift: q = (m * magic) >> 40 for m * d < 2^40
     kp.gather.magic_hw = (1ull << 40) / static_cast<unsigned long long>(cg.Ho * cg.Wo) + 1;
     kp.gather.magic_w = (1ull << 40) / static_cast<unsigned long long>(cg.Wo) + 1;
@@ -1385,9 +1438,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     if (static_cast<long long>(kp.grid_ctas) > static_cast<long long>(occ) * sm_count) return 3;
   }
   if (dry_run) return 0;
+  if (cg.mode == 3) return launch_inst<MVAE_BF16, EPI_STORE, 2>(ta, tb, kp, grid, dyn, stream);
   if (cg.mode != 0) {  // bf16 store / accumulate only (validated above)
-    if (e.kind == EPI_STORE) return launch_inst<MVAE_BF16, EPI_STORE, true>(ta, tb, kp, grid, dyn, stream);
-    return launch_inst<MVAE_BF16, EPI_ATOMIC, true>(ta, tb, kp, grid, dyn, stream);
+    if (e.kind == EPI_STORE) return launch_inst<MVAE_BF16, EPI_STORE, 1>(ta, tb, kp, grid, dyn, stream);
+    return launch_inst<MVAE_BF16, EPI_ATOMIC, 1>(ta, tb, kp, grid, dyn, stream);
   }
 #define MVAE_GEMM_CASE(KIND, EPI)                                   \
   if (g.kind == KIND && e.kind == EPI) return launch_inst<KIND, EPI>(ta, tb, kp, grid, dyn, stream);

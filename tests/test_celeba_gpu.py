@@ -112,6 +112,26 @@ def test_implicit_gemm_equals_im2col_then_gemm(cfg):
     assert rel(dw_imp, ref) < 2e-3
 
 
+@pytest.mark.skipif(os.environ.get("MVAE_TEST_CONVT") != "1",
+                    reason="draft entry mvae_convt_class_gemm: not yet run on a B200 (enable with MVAE_TEST_CONVT=1)")
+@pytest.mark.parametrize("cfg", [(4, 8, 128, 64, 4, 2, 1), (3, 5, 256, 128, 4, 1, 0), (2, 2, 256, 128, 4, 2, 0),
+                                 (2, 12, 64, 32, 5, 2, 1), (5, 16, 64, 32, 4, 2, 1)])
+def test_transposed_conv_implicit_matches_torch(cfg):
+    """ConvTranspose2d forward as one gather GEMM per output-parity class (no patch matrix, no col2im) against torch."""
+    ops, _ = _ops()
+    B, hin, ci, co, k, s, p = cfg
+    g = torch.Generator().manual_seed(13)
+    bf = torch.bfloat16
+    x = torch.randn(B, hin, hin, ci, generator=g).to(bf).cuda()
+    w = (torch.randn(ci, k, k, co, generator=g) / (ci * k) ** 0.5).to(bf).cuda()
+    hout = (hin - 1) * s - 2 * p + k
+    out = torch.full((B, hout, hout, co), float("nan"), device="cuda", dtype=bf)
+    assert ops.transposed_conv_implicit(x, w, out, B, hin, ci, co, k, s, p) == hout
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), stride=s, padding=p).permute(0, 2, 3, 1)
+    assert not bool(torch.isnan(out.float()).any())
+    assert rel(out.float(), ref) < 4e-3
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(3 * 40, 64, 40), (1000, 32, 1000), (257, 256, 257), (96, 1024, 32)])
 def test_bn_swish_forward_backward(dtype, shape):
