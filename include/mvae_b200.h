@@ -222,13 +222,14 @@ int mvae_conv_out_size(int in, int kernel, int stride, int pad);
  * Needs C % 8 == 0 and bf16 storage; bit-identical to mvae_im2col followed by mvae_gemm. */
 int mvae_conv_gemm(const mvae_gemm_args* args, const mvae_conv_geometry* geometry, int patch_operand, void* stream);
 
-/* DRAFT (not on any product path yet; its GPU parity test is gated behind MVAE_TEST_CONVT=1 until it has run on a B200):
- * one output-parity class of a ConvTranspose2d forward / Conv2d input gradient as an implicit GEMM, i.e. without the
+/* One output-parity class of a ConvTranspose2d forward / Conv2d input gradient as an implicit GEMM, i.e. without the
  * [pixels, k*k*C_out] patch matrix and without mvae_col2im (celeba/model.py:142-152, multimnist/model.py:198-210):
  *   out[n, s*u + a, s*v + b, :] = sum_{th, tw, ci} x[n, u - pad_h + th, v - pad_w + tw, ci] * W[ci, kh[th], kw[tw], :]
  * x: channels-last bf16 [batch, in_h, in_w, channels] (channels % 64 == 0); weight: bf16 [channels, kernel*kernel, out_channels]
  * (ld_tap elements between taps); out: channels-last image [batch, out_h, out_w, ldc] (bf16 / fp32, ldc % 8 == 0).
- * The host loops over the stride*stride classes; mvae_b200._ops.transposed_conv_classes() derives the fields. */
+ * The host loops over the stride*stride classes; mvae_b200._ops.transposed_conv_classes() derives the fields.
+ * Parity: test_transposed_conv_implicit_matches_torch (5 geometries).  The shipped hosts still use mvae_gemm + mvae_col2im for
+ * this side (MVAE_IMPLICIT_COL2IM=1 switches them over; not yet measured). */
 typedef struct mvae_convt_class {
   int batch, in_h, in_w, channels;
   int out_h, out_w, out_channels;

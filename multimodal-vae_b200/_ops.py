@@ -86,7 +86,7 @@ def transposed_conv_classes(kernel: int, stride: int, pad: int, size_in: int):
 
 
 def transposed_conv_implicit(x, weight, out, batch, size_in, channels, out_channels, kernel, stride, pad, ldc=None):
-    """DRAFT (see include/mvae_b200.h, mvae_convt_class_gemm): ConvTranspose2d forward / Conv2d input gradient without the
+    """mvae_convt_class_gemm per class: ConvTranspose2d forward / Conv2d input gradient without the
     patch matrix - one gather GEMM per output-parity class writing the interleaved rows of `out` [batch, H_out, H_out, ldc].
     x: [batch, size_in, size_in, channels] bf16 channels-last; weight: [channels, kernel, kernel, out_channels] bf16."""
     size_out, classes = transposed_conv_classes(kernel, stride, pad, size_in)

@@ -112,8 +112,6 @@ def test_implicit_gemm_equals_im2col_then_gemm(cfg):
     assert rel(dw_imp, ref) < 2e-3
 
 
-@pytest.mark.skipif(os.environ.get("MVAE_TEST_CONVT") != "1",
-                    reason="draft entry mvae_convt_class_gemm: not yet run on a B200 (enable with MVAE_TEST_CONVT=1)")
 @pytest.mark.parametrize("cfg", [(4, 8, 128, 64, 4, 2, 1), (3, 5, 256, 128, 4, 1, 0), (2, 2, 256, 128, 4, 2, 0),
                                  (2, 12, 64, 32, 5, 2, 1), (5, 16, 64, 32, 4, 2, 1)])
 def test_transposed_conv_implicit_matches_torch(cfg):
