@@ -229,7 +229,7 @@ int mvae_conv_gemm(const mvae_gemm_args* args, const mvae_conv_geometry* geometr
  * (ld_tap elements between taps); out: channels-last image [batch, out_h, out_w, ldc] (bf16 / fp32, ldc % 8 == 0).
  * The host loops over the stride*stride classes; mvae_b200._ops.transposed_conv_classes() derives the fields.
  * Parity: test_transposed_conv_implicit_matches_torch (5 geometries).  The shipped hosts still use mvae_gemm + mvae_col2im for
- * this side (MVAE_IMPLICIT_COL2IM=1 switches them over; not yet measured). */
+ * this side (MVAE_IMPLICIT_COL2IM=1 switches them over; that wiring has not been run end to end or measured yet). */
 typedef struct mvae_convt_class {
   int batch, in_h, in_w, channels;
   int out_h, out_w, out_channels;

@@ -152,6 +152,9 @@ class ConvMVAEBase:
         # implicit GEMM (mvae_conv_gemm): patch matrices of layers with >= 8 bf16 channels are gathered inside the GEMM
         # instead of being written by mvae_im2col and read back (MVAE_IMPLICIT_CONV=0 restores the explicit path)
         self.implicit_conv = self.act_dtype == torch.bfloat16 and os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
+        # the col2im side through mvae_convt_class_gemm (one gather GEMM per output-parity class): the op is parity-tested,
+        # the hosts' use of it has not been run end to end yet - off unless MVAE_IMPLICIT_COL2IM=1
+        self.implicit_col2im = self.implicit_conv and os.environ.get("MVAE_IMPLICIT_COL2IM", "0") == "1"
         # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
         # own stream beside the image networks
         self.mod_stream = torch.cuda.Stream(device=dev)
@@ -361,6 +364,12 @@ class ConvMVAEBase:
         division cover pixels < 2^24 and elements < 2^31 (mvae_conv_gemm refuses more) - beyond that the explicit path runs."""
         return (self.implicit_conv and channels_last and channels % 8 == 0 and pixels < (1 << 24) and elements < (1 << 31))
 
+    def _implicit_t(self, channels: int, out_channels: int, exact: bool, pixels: int, elements: int) -> bool:
+        """Transposed convolution / Conv2d input gradient without the patch matrix?  (channels % 64: a K block of the class
+        GEMM never straddles a tap; `exact`: the transposed output covers the whole image.)"""
+        return (self.implicit_col2im and exact and channels % 64 == 0 and out_channels % 8 == 0 and pixels < (1 << 24)
+                and elements < (1 << 31))
+
     def features_fwd(self, ws, image, B, training: bool, updates: int) -> None:
         """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
         NHWC bottleneck [B, FLAT_HW * FLAT_C]."""
@@ -414,9 +423,13 @@ class ConvMVAEBase:
                     accumulate=True))
             if li > 0:
                 w, ldw = self._operand_cached(pre + ".weight", K)
-                _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
-                g = _ops.geometry(B, hin, hin, ci, k, s, p)
-                _ops.col2im(g, ws.colbuf, ldk, ws.enc_dact[li - 1])
+                if ldw == K and self._implicit_t(co, ci, (hin + 2 * p - k) % s == 0, rows, rows * co):
+                    # the input gradient IS a transposed convolution of dpre with the same weights [co, kh, kw, ci]
+                    _ops.transposed_conv_implicit(ws.enc_dpre[li], w, ws.enc_dact[li - 1], B, ho, co, ci, k, s, p)
+                else:
+                    _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
+                    g = _ops.geometry(B, hin, hin, ci, k, s, p)
+                    _ops.col2im(g, ws.colbuf, ldk, ws.enc_dact[li - 1])
         self._join_side()
 
     def hallucinate_fwd(self, ws, M3, rows_per_term, training: bool) -> None:
@@ -430,10 +443,15 @@ class ConvMVAEBase:
             rows_in = M3 * hin * hin
             # col[M_in, (kh,kw,co)] = X[M_in, ci] * W'[ci, (kh,kw,co)]
             w, ldw = self.operand(pre + ".weight", ci, K)
-            _ops.gemm(src, w, ws.colbuf, rows_in, K, ci, ci, ldw, ldk, b_major=1)
+            direct = li < last and ldw == K and self._implicit_t(ci, co, True, rows_in, rows_in * ci)
+            if direct:
+                _ops.transposed_conv_implicit(src, w, ws.dec_pre[li], M3, hin, ci, co, k, s, p)
+            else:
+                _ops.gemm(src, w, ws.colbuf, rows_in, K, ci, ci, ldw, ldk, b_major=1)
             if li < last:
-                g = _ops.geometry(M3, hout, hout, co, k, s, p)
-                _ops.col2im(g, ws.colbuf, ldk, ws.dec_pre[li])
+                if not direct:
+                    g = _ops.geometry(M3, hout, hout, co, k, s, p)
+                    _ops.col2im(g, ws.colbuf, ldk, ws.dec_pre[li])
                 rows = M3 * hout * hout
                 rm, rv = self.running(bn)
                 a = _ops.bn_args(ws.dec_pre[li], rows, co, rows_per_term * hout * hout, SWISH, training, self.P(bn + ".weight"),
