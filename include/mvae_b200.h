@@ -241,6 +241,14 @@ typedef struct mvae_convt_class {
 } mvae_convt_class;
 int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, const void* weight, int64_t ld_tap, void* out,
                           int64_t ldc, int out_dtype, void* stream);
+/* DRAFT (compiles; not yet run on a B200, on no product path; its parity test needs MVAE_TEST_CONVT_MERGED=1):
+ * the whole transposed convolution in ONE launch - grid.z enumerates the stride*stride parity classes of
+ * mvae_convt_class_gemm.  Only for geometries whose classes have equal shape (kernel % stride == 0 and an output size
+ * divisible by the stride, e.g. k4 s2 p1, or stride 1); returns 4 without launching otherwise (callers then loop over
+ * mvae_convt_class_gemm).  x [batch, in_h, in_w, channels] bf16, weight [channels, kernel*kernel, out_channels] bf16,
+ * out [batch, out_h, out_w, ldc] with out_h = (in_h-1)*stride - 2*pad + kernel. */
+int mvae_convt_gemm(int dtype, int batch, int in_h, int in_w, int channels, int out_channels, int kernel, int stride, int pad,
+                    const void* x, const void* weight, int64_t ld_tap, void* out, int64_t ldc, int out_dtype, void* stream);
 /* col[m, (kh*k+kw)*C + c] = image[n, ho*s-p+kh, wo*s-p+kw, c] (0 outside), m = (n*Ho+ho)*Wo+wo.
  * replaces: the patch gather inside nn.Conv2d forward / ConvTranspose2d backward (celeba/model.py:101-113, 142-152). */
 int mvae_im2col(const mvae_conv_geometry* g, int image_dtype, const void* image, int col_dtype, void* col, int64_t ldcol,

@@ -85,12 +85,22 @@ def transposed_conv_classes(kernel: int, stride: int, pad: int, size_in: int):
     return size_out, classes
 
 
-def transposed_conv_implicit(x, weight, out, batch, size_in, channels, out_channels, kernel, stride, pad, ldc=None):
+def transposed_conv_implicit(x, weight, out, batch, size_in, channels, out_channels, kernel, stride, pad, ldc=None,
+                             merged=False):
     """mvae_convt_class_gemm per class: ConvTranspose2d forward / Conv2d input gradient without the
     patch matrix - one gather GEMM per output-parity class writing the interleaved rows of `out` [batch, H_out, H_out, ldc].
-    x: [batch, size_in, size_in, channels] bf16 channels-last; weight: [channels, kernel, kernel, out_channels] bf16."""
+    x: [batch, size_in, size_in, channels] bf16 channels-last; weight: [channels, kernel, kernel, out_channels] bf16.
+    `merged` (draft): all classes in one launch (mvae_convt_gemm) when they have equal shape, else the per-class loop."""
     size_out, classes = transposed_conv_classes(kernel, stride, pad, size_in)
     lib = _lib.load()
+    if merged:
+        rc = lib.mvae_convt_gemm(DT[x.dtype], int(batch), int(size_in), int(size_in), int(channels), int(out_channels),
+                                 int(kernel), int(stride), int(pad), x.data_ptr(), weight.data_ptr(), int(out_channels),
+                                 out.data_ptr(), int(ldc or out_channels), DT[out.dtype], stream())
+        if rc == 0:
+            return size_out
+        if rc != 4:   # 4 = classes of unequal shape: fall through to the per-class launches
+            _lib.check(rc, "mvae_convt_gemm")
     for ca in classes:
         for cb in classes:
             if ca["count"] == 0 or cb["count"] == 0 or not ca["kh"] or not cb["kh"]:

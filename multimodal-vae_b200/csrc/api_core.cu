@@ -100,6 +100,54 @@ int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, c
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int mvae_convt_gemm(int dtype, int batch, int in_h, int in_w, int channels, int out_channels, int kernel, int stride, int pad,
+                    const void* x, const void* weight, int64_t ld_tap, void* out, int64_t ldc, int out_dtype, void* stream) {
+  MVAE_REQUIRE(x != nullptr && weight != nullptr && out != nullptr, "mvae_convt_gemm: null argument");
+  MVAE_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && kernel > 0 && stride > 0 && stride <= 4 && pad >= 0, "mvae_convt_gemm: bad geometry");
+  const int out_h = (in_h - 1) * stride - 2 * pad + kernel, out_w = (in_w - 1) * stride - 2 * pad + kernel;
+  // per-axis parity classes (mvae_b200._ops.transposed_conv_classes): all must have the same tap count and the same grid
+  int taps0 = -1, cnt_h0 = -1, cnt_w0 = -1;
+  GemmDesc g;
+  ConvGather& cg = g.gather;
+  for (int a = 0; a < stride; ++a) {
+    const int r = (a + pad) % stride;
+    const int taps = kernel > r ? (kernel - r + stride - 1) / stride : 0;
+    const int q = (a + pad) / stride;
+    const int cnt_h = out_h > a ? (out_h - a + stride - 1) / stride : 0;
+    const int cnt_w = out_w > a ? (out_w - a + stride - 1) / stride : 0;
+    if (a == 0) {
+      taps0 = taps; cnt_h0 = cnt_h; cnt_w0 = cnt_w;
+    }
+    if (taps != taps0 || cnt_h != cnt_h0 || cnt_w != cnt_w0 || taps < 1 || taps > 8 || cnt_h < 1 || cnt_w < 1) {
+      set_error("mvae_convt_gemm: parity classes of k=%d s=%d p=%d differ in shape; use mvae_convt_class_gemm per class", kernel,
+                stride, pad);
+      return 4;
+    }
+    cg.ax_pad[a] = static_cast<signed char>(taps - 1 - q);
+    for (int t = 0; t < taps; ++t) cg.ax_k[a][t] = static_cast<signed char>(r + stride * (taps - 1 - t));
+  }
+  g.kind = dtype;
+  g.M = batch * cnt_h0 * cnt_w0;
+  g.N = out_channels;
+  g.K = taps0 * taps0 * channels;
+  g.A = x; g.lda = 0; g.a_mn = 0;
+  g.B = weight; g.ldb = ld_tap; g.b_mn = 1;
+  g.epi.kind = EPI_STORE;
+  g.epi.C = out; g.epi.ldc = ldc; g.epi.c_dtype = out_dtype;
+  g.epi.rows_per_group = 1 << 30;
+  cg.mode = 4;
+  cg.X = x;
+  cg.H = in_h; cg.W = in_w; cg.C = channels;
+  cg.ksize = taps0; cg.ksize_w = taps0; cg.stride = 1; cg.pad = cg.ax_pad[0]; cg.pad_w = cg.ax_pad[0];
+  cg.Ho = cnt_h0; cg.Wo = cnt_w0;
+  cg.sw = channels; cg.sh = static_cast<long long>(in_w) * channels; cg.sn = cg.sh * in_h;
+  cg.extent = cg.sn * batch;
+  cg.kk = kernel;
+  cg.sc_hout = out_h; cg.sc_wout = out_w; cg.sc_stride = stride; cg.sc_a = 0; cg.sc_b = 0;
+  note_launch(1);
+  return launch_gemm(g, static_cast<cudaStream_t>(stream));
+}
+
 static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int patch_operand, void* stream) {
   MVAE_REQUIRE(a != nullptr, "mvae_gemm: null args");
   GemmDesc g;

@@ -120,6 +120,10 @@ struct ConvGather {
   int ksize_w = 0, pad_w = 0, kk = 0;
   signed char kh_tab[8] = {0, 0, 0, 0, 0, 0, 0, 0}, kw_tab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int sc_hout = 0, sc_wout = 0, sc_stride = 1, sc_a = 0, sc_b = 0;
+  // mode 4: ALL sc_stride^2 parity classes of mode 3 in one launch (blockIdx.z = class (a, b) = (z / stride, z % stride));
+  // needs classes of equal shape (same grid, same tap counts), so only the per-axis pad and tap tables vary with the class
+  signed char ax_pad[4] = {0, 0, 0, 0};
+  signed char ax_k[4][8] = {{0}};
 };
 
 struct GemmDesc {

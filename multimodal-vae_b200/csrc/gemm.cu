@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * p.block_n;
   const int m0 = blockIdx.y * kBlockM;
-  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb0 = (kGather == 3 ? 0 : static_cast<int>(blockIdx.z)) * p.kb_per_split;  // kGather 3: blockIdx.z is the parity class
   const int nkb = min(p.kb_per_split, p.kb_total - kb0);
   const int stage_bytes = kAStageBytes + p.b_stage_bytes;
   const int S = p.stages;
@@ -459,6 +459,14 @@ __global__ void __launch_bounds__(kGemmThreads)
           for (int j = 0; j < a_boxes; ++j) ptx::tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m0 + j * ATOM, kc);
         }
         if (!tma_b) {
+        } else if constexpr (kGather == 3) {
+          // as kGather 2, with the tap tables of this CTA's parity class (a, b) = (z / stride, z % stride)
+          const ConvGather& cg = p.gather;
+          const int za = static_cast<int>(blockIdx.z) / cg.sc_stride, zb = static_cast<int>(blockIdx.z) - za * cg.sc_stride;
+          const int w_pos = kc / cg.C, ci0 = kc - w_pos * cg.C;
+          const int th = w_pos / cg.ksize_w, tw = w_pos - th * cg.ksize_w;
+          const int tap = cg.ax_k[za][th] * cg.kk + cg.ax_k[zb][tw];
+          for (int j = 0; j < b_boxes; ++j) ptx::tma_load_3d(sb + j * (BK * 128), &tmB, &full_bar[s], n0 + j * ATOM, tap, ci0);
         } else if constexpr (kGather == 2) {
           // weights of the tap this K block belongs to: window position (th, tw) -> tap kh_tab[th]*kk + kw_tab[tw]
           const ConvGather& cg = p.gather;
@@ -569,7 +577,69 @@ __global__ void __launch_bounds__(kGemmThreads)
       ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
       ptx::mbar_arrive(&ready_bar[s]);
     }
-  } else if (kGather != 0 && warp >= 4) {
+  } else if (kGather == 3 && warp >= 4) {
+    // ------------------------------------------------------------ all parity classes in one launch (warps 4..7)
+    // Same producer as the kGather 1/2 patch-matrix-as-A path below (two 64-thread groups own the even / odd ring slots),
+    // with the tap window's pads taken from the tables of this CTA's class.
+    if constexpr (kGather == 3) {
+      const ConvGather& cg = p.gather;
+      const int za = static_cast<int>(blockIdx.z) / cg.sc_stride, zb = static_cast<int>(blockIdx.z) - za * cg.sc_stride;
+      const int pad_h = cg.ax_pad[za], pad_w = cg.ax_pad[zb];
+      const int grp = (warp - 4) >> 1;
+      const int t64 = threadIdx.x & 63;
+      const int c = t64 & 7, rbase = t64 >> 3;
+      const uint32_t chunk_off = static_cast<uint32_t>((c ^ rbase) << 4);
+      const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(cg.X);
+      const uint32_t hw = static_cast<uint32_t>(cg.Ho * cg.Wo);
+      int off[16], hw0[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int m = m0 + rbase + 8 * j;
+        const bool valid = m < p.M;
+        const uint32_t n = static_cast<uint32_t>((static_cast<unsigned long long>(m) * cg.magic_hw) >> 40);
+        const uint32_t rem = static_cast<uint32_t>(m) - n * hw;
+        const uint32_t u = static_cast<uint32_t>((static_cast<unsigned long long>(rem) * cg.magic_w) >> 40);
+        const uint32_t v = rem - u * static_cast<uint32_t>(cg.Wo);
+        const int hi0 = valid ? static_cast<int>(u) - pad_h : -20000;
+        const int wi0 = static_cast<int>(v) - pad_w;
+        off[j] = valid ? static_cast<int>(n) * static_cast<int>(cg.sn) + hi0 * static_cast<int>(cg.sh) + wi0 * static_cast<int>(cg.sw) : 0;
+        hw0[j] = (hi0 << 16) | (wi0 & 0xffff);
+      }
+      int k0 = c * 8;
+      int tap = k0 / cg.C, ch = k0 - tap * cg.C;
+      int kh = tap / cg.ksize_w, kw = tap - kh * cg.ksize_w;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S;
+        if ((s & 1) == grp) {
+          const uint32_t ph = (i / S) & 1;
+          const int koff = kh * static_cast<int>(cg.sh) + kw * static_cast<int>(cg.sw) + ch;
+          const bool kvalid = k0 < p.K;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t dst = ptx::smem_u32(smem + s * stage_bytes) + rbase * 128 + chunk_off;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int hi = (hw0[j] >> 16) + kh, wi = ((hw0[j] << 16) >> 16) + kw;
+            const bool ok = kvalid && static_cast<unsigned>(hi) < static_cast<unsigned>(cg.H) &&
+                            static_cast<unsigned>(wi) < static_cast<unsigned>(cg.W);
+            ptx::cp_async16_zfill(dst + j * (8 * 128), ok ? X + (off[j] + koff) : X, ok ? 16u : 0u);
+          }
+          ptx::cp_async_commit();
+          ptx::cp_async_wait_pending(0);
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ready_bar[s]);
+        }
+        k0 += BK;
+        ch += BK;
+        while (ch >= cg.C) {
+          ch -= cg.C;
+          if (++kw == cg.ksize_w) {
+            kw = 0;
+            ++kh;
+          }
+        }
+      }
+    }
+  } else if ((kGather == 1 || kGather == 2) && warp >= 4) {
     // ------------------------------------------------------------ implicit patch-matrix operand (warps 4..7)
     // The convolution's im2col matrix is never materialised: these threads copy 16-byte chunks (8 bf16 channels of one
     // filter tap) from the NHWC activation into the SWIZZLE_128B stage the tensor core reads (logical chunk c of row r
@@ -577,7 +647,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     // 64 threads own the even / odd ring SLOTS (warps 4,5 / 6,7), so two stages are in flight and each is published
     // through ready_bar (proxy fence first) the moment it lands - the same decoupling TMA gives the other operand.
     // (Ownership is by slot, not by stage index: a group then sees every phase of its slots' barriers in order.)
-    if constexpr (kGather != 0) {
+    if constexpr (kGather == 1 || kGather == 2) {
       const ConvGather& cg = p.gather;
       const int grp = (warp - 4) >> 1;
       const int t64 = threadIdx.x & 63;
@@ -707,6 +777,14 @@ __global__ void __launch_bounds__(kGemmThreads)
       const int q = warp & 3;
       const int row = m0 + q * 32 + lane;
       long long row_off = static_cast<long long>(row) * e.ldc;
+      if constexpr (kGather == 3) {
+        const ConvGather& cg = p.gather;
+        const int za = static_cast<int>(blockIdx.z) / cg.sc_stride, zb = static_cast<int>(blockIdx.z) - za * cg.sc_stride;
+        const int hw = cg.Ho * cg.Wo;
+        const int n = row / hw, rem = row - n * hw;
+        const int u = rem / cg.Wo, v2 = rem - u * cg.Wo;
+        row_off = ((static_cast<long long>(n) * cg.sc_hout + cg.sc_stride * u + za) * cg.sc_wout + cg.sc_stride * v2 + zb) * e.ldc;
+      }
       if constexpr (kGather == 2) {
         // row (n, u, v) of this parity class -> pixel (n, stride*u + a, stride*v + b) of the interleaved output image
         const ConvGather& cg = p.gather;
@@ -1181,15 +1259,15 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   const int BK = 128 / esz;
   MVAE_REQUIRE(g.kind == MVAE_F32 || g.kind == MVAE_BF16, "gemm: bad kind %d", g.kind);
   MVAE_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem %dx%dx%d", g.M, g.N, g.K);
-  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode == 3 || (g.lda * esz) % 16 == 0) && (g.gather.mode == 2 || (g.ldb * esz) % 16 == 0),
+  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode >= 3 || (g.lda * esz) % 16 == 0) && (g.gather.mode == 2 || (g.ldb * esz) % 16 == 0),
                "gemm: lda/ldb (%lld,%lld) must be 16-byte multiples", g.lda, g.ldb);
-  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode == 3 || (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
+  MVAE_REQUIRE((g.gather.mode == 1 || g.gather.mode >= 3 || (reinterpret_cast<uintptr_t>(g.A) & 15) == 0) &&
                    (g.gather.mode == 2 || (reinterpret_cast<uintptr_t>(g.B) & 15) == 0),
                "gemm: A/B must be 16-byte aligned");
   const GemmEpilogue& e = g.epi;
   const ConvGather& cg = g.gather;
   if (cg.mode != 0) {
-    MVAE_REQUIRE(cg.mode >= 1 && cg.mode <= 3, "gemm: bad gather mode %d", cg.mode);
+    MVAE_REQUIRE(cg.mode >= 1 && cg.mode <= 4, "gemm: bad gather mode %d", cg.mode);
     MVAE_REQUIRE(g.kind == MVAE_BF16, "gemm: the implicit patch-matrix operand is implemented for bf16 storage only");
     MVAE_REQUIRE(cg.X != nullptr && (reinterpret_cast<uintptr_t>(cg.X) & 15) == 0, "gemm: gather source must be 16-byte aligned");
     MVAE_REQUIRE(cg.C > 0 && cg.C % 8 == 0 && cg.sn % 8 == 0 && cg.sh % 8 == 0 && cg.sw % 8 == 0,
@@ -1202,7 +1280,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(cg.extent < (1ll << 31) && (cg.mode == 2 ? g.K : g.M) < (1 << 24), "gemm: gather source too large for 32-bit offsets");
     if (cg.mode == 1) MVAE_REQUIRE(!g.a_mn && g.K == cg.ksize * cg.ksize * cg.C, "gemm: gather A needs K = k*k*C, K-major");
     if (cg.mode == 2) MVAE_REQUIRE(g.b_mn && g.N == cg.ksize * cg.ksize * cg.C, "gemm: gather B needs N = k*k*C, MN-major");
-    if (cg.mode == 3) {
+    if (cg.mode == 3 || cg.mode == 4) {
       MVAE_REQUIRE(!g.a_mn && g.b_mn && e.kind == EPI_STORE, "gemm: transposed-conv class needs K-major A, MN-major weights, store epilogue");
       MVAE_REQUIRE(cg.ksize_w > 0 && cg.ksize <= 8 && cg.ksize_w <= 8 && g.K == cg.ksize * cg.ksize_w * cg.C,
                    "gemm: transposed-conv class needs K = taps_h*taps_w*C with at most 8 taps per axis");
@@ -1210,6 +1288,9 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
       MVAE_REQUIRE(cg.kk > 0 && cg.sc_stride > 0 && cg.sc_a < cg.sc_stride && cg.sc_b < cg.sc_stride &&
                        cg.sc_stride * (cg.Ho - 1) + cg.sc_a < cg.sc_hout && cg.sc_stride * (cg.Wo - 1) + cg.sc_b < cg.sc_wout,
                    "gemm: transposed-conv class does not fit the output image");
+      if (cg.mode == 4)  // every class (a, b) < stride must fit: the last one reaches furthest
+        MVAE_REQUIRE(cg.sc_stride <= 4 && cg.sc_stride * cg.Ho <= cg.sc_hout && cg.sc_stride * cg.Wo <= cg.sc_wout,
+                     "gemm: merged transposed-conv classes need stride <= 4 and equal class grids inside the output image");
     }
   }
   MVAE_REQUIRE(e.C != nullptr, "gemm: null output");
@@ -1350,14 +1431,14 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
             g.M, g.N, g.K, g.kind, e.kind, g.a_mn, g.b_mn, block_n, split, stages, dyn, tiles_n, tiles_m, split);
 
   CUtensorMap ta, tb;
-  if (cg.mode == 1 || cg.mode == 3) {
+  if (cg.mode == 1 || cg.mode >= 3) {
   } else if (!g.a_mn) {
     if (make_tmap(&ta, g.kind, g.A, g.M, g.K, g.lda, BK, kBlockM, false)) return 1;
   } else {
     if (make_tmap(&ta, g.kind, g.A, g.K, g.M, g.lda, BK, BK, true)) return 1;
   }
   if (cg.mode == 2) {
-  } else if (cg.mode == 3) {
+  } else if (cg.mode >= 3) {
     // weights [C, kk*kk taps, N] (N contiguous, ldb elements between taps): one 64 x 1 x BK box per tap and column block
     if (make_tmap_w3(&tb, g.B, g.N, static_cast<long long>(cg.kk) * cg.kk, cg.C, g.ldb, BK, BK)) return 1;
   } else if (!g.b_mn) {
@@ -1365,7 +1446,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   } else {
     if (make_tmap(&tb, g.kind, g.B, g.K, g.N, g.ldb, BK, BK, true)) return 1;
   }
-  if (cg.mode == 1 || cg.mode == 3) ta = tb;  // the gathered operand has no tensor map; the kernel never touches this copy
+  if (cg.mode == 1 || cg.mode >= 3) ta = tb;  // the gathered operand has no tensor map; the kernel never touches this copy
   if (cg.mode == 2) tb = ta;
 
   GemmKParams kp;
@@ -1405,8 +1486,8 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
   kp.atf = g.atf;
   kp.gather = cg;
-  if (cg.mode == 3) {
-    kp.gather.mode = 1;  // inside the kernel: A is the gathered operand (instantiation kGather = 2)
+  if (cg.mode >= 3) {
+    kp.gather.mode = 1;  // inside the kernel: A is the gathered operand (instantiation kGather = 2 / 3)
     MVAE_REQUIRE(kp.direct_store, "gemm: transposed-conv class needs the direct store epilogue (ldc %% 8 == 0, aligned C, no statistics)");
   }
   if (cg.mode != 0) {  // exact division by multiply-shift: q = (m * magic) >> 40 for m * d < 2^40
@@ -1418,7 +1499,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(e.hpre && e.bn_mean && e.bn_rstd && e.bn_gamma && e.bn_beta, "gemm: dgrad-BN epilogue needs BN state");
   MVAE_REQUIRE(e.rows_per_group > 0, "gemm: rows_per_group must be positive");
 
-  dim3 grid(tiles_n, tiles_m, split);
+  dim3 grid(tiles_n, tiles_m, cg.mode == 4 ? cg.sc_stride * cg.sc_stride : split);  // mode 4: z = parity class (split is 1)
   if (fuse) {
     // authoritative co-residency check with the real register / shared-memory footprint of the kernel
     int occ = 0;
@@ -1439,6 +1520,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   }
   if (dry_run) return 0;
   if (cg.mode == 3) return launch_inst<MVAE_BF16, EPI_STORE, 2>(ta, tb, kp, grid, dyn, stream);
+  if (cg.mode == 4) return launch_inst<MVAE_BF16, EPI_STORE, 3>(ta, tb, kp, grid, dyn, stream);
   if (cg.mode != 0) {  // bf16 store / accumulate only (validated above)
     if (e.kind == EPI_STORE) return launch_inst<MVAE_BF16, EPI_STORE, 1>(ta, tb, kp, grid, dyn, stream);
     return launch_inst<MVAE_BF16, EPI_ATOMIC, 1>(ta, tb, kp, grid, dyn, stream);

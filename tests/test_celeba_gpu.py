@@ -130,6 +130,29 @@ def test_transposed_conv_implicit_matches_torch(cfg):
     assert rel(out.float(), ref) < 4e-3
 
 
+@pytest.mark.skipif(os.environ.get("MVAE_TEST_CONVT_MERGED") != "1",
+                    reason="draft entry mvae_convt_gemm (all parity classes in one launch): not yet run on a B200")
+@pytest.mark.parametrize("cfg", [(4, 8, 128, 64, 4, 2, 1), (3, 5, 256, 128, 4, 1, 0), (2, 2, 256, 128, 4, 2, 0),
+                                 (2, 12, 64, 32, 5, 2, 1), (5, 16, 64, 32, 4, 2, 1)])
+def test_transposed_conv_merged_classes_matches_torch(cfg):
+    """As test_transposed_conv_implicit_matches_torch with merged=True (k5 s2 has unequal classes: exercises the fallback)."""
+    ops, _ = _ops()
+    B, hin, ci, co, k, s, p = cfg
+    g = torch.Generator().manual_seed(14)
+    bf = torch.bfloat16
+    x = torch.randn(B, hin, hin, ci, generator=g).to(bf).cuda()
+    w = (torch.randn(ci, k, k, co, generator=g) / (ci * k) ** 0.5).to(bf).cuda()
+    hout = (hin - 1) * s - 2 * p + k
+    out = torch.full((B, hout, hout, co), float("nan"), device="cuda", dtype=bf)
+    ops.transposed_conv_implicit(x, w, out, B, hin, ci, co, k, s, p, merged=True)
+    per_class = torch.empty_like(out)
+    ops.transposed_conv_implicit(x, w, per_class, B, hin, ci, co, k, s, p)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), stride=s, padding=p).permute(0, 2, 3, 1)
+    assert not bool(torch.isnan(out.float()).any())
+    assert rel(out.float(), ref) < 4e-3
+    assert torch.equal(out, per_class)      # same tiles, same accumulation order
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape", [(3 * 40, 64, 40), (1000, 32, 1000), (257, 256, 257), (96, 1024, 32)])
 def test_bn_swish_forward_backward(dtype, shape):
