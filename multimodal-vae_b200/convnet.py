@@ -155,6 +155,7 @@ class ConvMVAEBase:
         # the col2im side through mvae_convt_class_gemm (one gather GEMM per output-parity class): the op is parity-tested,
         # the hosts' use of it has not been run end to end yet - off unless MVAE_IMPLICIT_COL2IM=1
         self.implicit_col2im = self.implicit_conv and os.environ.get("MVAE_IMPLICIT_COL2IM", "0") == "1"
+        self.convt_merged = os.environ.get("MVAE_CONVT_MERGED", "0") == "1"   # all parity classes in one launch (draft)
         # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
         # own stream beside the image networks
         self.mod_stream = torch.cuda.Stream(device=dev)
@@ -425,7 +426,8 @@ class ConvMVAEBase:
                 w, ldw = self._operand_cached(pre + ".weight", K)
                 if ldw == K and self._implicit_t(co, ci, (hin + 2 * p - k) % s == 0, rows, rows * co):
                     # the input gradient IS a transposed convolution of dpre with the same weights [co, kh, kw, ci]
-                    _ops.transposed_conv_implicit(ws.enc_dpre[li], w, ws.enc_dact[li - 1], B, ho, co, ci, k, s, p)
+                    _ops.transposed_conv_implicit(ws.enc_dpre[li], w, ws.enc_dact[li - 1], B, ho, co, ci, k, s, p,
+                                                  merged=self.convt_merged)
                 else:
                     _ops.gemm(ws.enc_dpre[li], w, ws.colbuf, rows, K, co, co, ldw, ldk, b_major=1)   # dcol = dpre W'
                     g = _ops.geometry(B, hin, hin, ci, k, s, p)
@@ -445,7 +447,7 @@ class ConvMVAEBase:
             w, ldw = self.operand(pre + ".weight", ci, K)
             direct = li < last and ldw == K and self._implicit_t(ci, co, True, rows_in, rows_in * ci)
             if direct:
-                _ops.transposed_conv_implicit(src, w, ws.dec_pre[li], M3, hin, ci, co, k, s, p)
+                _ops.transposed_conv_implicit(src, w, ws.dec_pre[li], M3, hin, ci, co, k, s, p, merged=self.convt_merged)
             else:
                 _ops.gemm(src, w, ws.colbuf, rows_in, K, ci, ci, ldw, ldk, b_major=1)
             if li < last:

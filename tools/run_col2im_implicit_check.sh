@@ -7,8 +7,8 @@ MVAE_TEST_CONVT_MERGED=1 timeout 60 python -m pytest tests/test_celeba_gpu.py -x
 MVAE_IMPLICIT_COL2IM=1 timeout 280 python -m pytest tests/test_celeba_gpu.py tests/test_multimnist_gpu.py -x -q -m gpu \
   -k "step_matches_oracle or ragged or graph_replay or fixture or autograd" 2>&1 | tail -5
 for w in celeba multimnist; do
-  for imp in 1 0; do
-    MVAE_IMPLICIT_COL2IM=$imp timeout 200 python bench.py --workload $w --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/c2i_${w}_${imp}.json 2> gpurun_out/c2i_${w}_${imp}.err
+  for imp in 2 1 0; do
+    MVAE_CONVT_MERGED=$([ $imp = 2 ] && echo 1 || echo 0) MVAE_IMPLICIT_COL2IM=$([ $imp = 0 ] && echo 0 || echo 1) timeout 200 python bench.py --workload $w --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/c2i_${w}_${imp}.json 2> gpurun_out/c2i_${w}_${imp}.err
     python - <<P
 import json
 try:
