@@ -6,6 +6,7 @@ import re
 import socket
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -199,3 +200,15 @@ def test_transposed_conv_parity_classes_match_torch(k, s, p, hin):
             covered[ca["a"]::s, cb["a"]::s] += 1
     assert int(covered.min()) == 1 and int(covered.max()) == 1
     torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-12, atol=1e-12)
+
+
+def test_gather_multiply_shift_division_is_exact():
+    """The implicit-GEMM gather maps pixel index -> (n, ho, wo) with q = (m * magic) >> 40, magic = 2^40 // d + 1
+    (csrc/gemm.cu, launch_gemm): exact for m < 2^24 and d < 2^16, the limits the launcher enforces."""
+    rng = np.random.default_rng(0)
+    for d in [1, 2, 3, 5, 25, 64, 255, 256, 1023, 1024, 4096, 65535] + [int(x) for x in rng.integers(1, 65536, size=40)]:
+        magic = np.uint64((1 << 40) // d + 1)
+        mult = np.arange(0, (1 << 24) // d + 1, dtype=np.uint64) * np.uint64(d)
+        m = np.concatenate([rng.integers(0, 1 << 24, size=20000, dtype=np.uint64), mult[mult < (1 << 24)],
+                            mult[(mult > 0) & (mult <= (1 << 24))] - np.uint64(1), np.array([(1 << 24) - 1], dtype=np.uint64)])
+        assert ((m * magic) >> np.uint64(40) == m // np.uint64(d)).all(), d
