@@ -247,6 +247,10 @@ int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, c
  * divisible by the stride, e.g. k4 s2 p1, or stride 1); returns 4 without launching otherwise (callers then loop over
  * mvae_convt_class_gemm).  x [batch, in_h, in_w, channels] bf16, weight [channels, kernel*kernel, out_channels] bf16,
  * out [batch, out_h, out_w, ldc] with out_h = (in_h-1)*stride - 2*pad + kernel. */
+/* Host helper (no GPU work): the output-parity classes of a transposed convolution along one axis, stride <= 4.  For class
+ * a < stride: count[a] outputs stride*u + a, taps[a] window positions, pad_lo[a], kernel index kh[a*8 + t] of window position t
+ * (out[stride*u + a] = sum_t x[u - pad_lo[a] + t] * w[kh[a*8 + t]]).  Returns the output size, or -1 for a bad geometry. */
+int mvae_convt_axis_classes(int kernel, int stride, int pad, int size_in, int* count, int* taps, int* pad_lo, int* kh);
 int mvae_convt_gemm(int dtype, int batch, int in_h, int in_w, int channels, int out_channels, int kernel, int stride, int pad,
                     const void* x, const void* weight, int64_t ld_tap, void* out, int64_t ldc, int out_dtype, void* stream);
 /* col[m, (kh*k+kw)*C + c] = image[n, ho*s-p+kh, wo*s-p+kw, c] (0 outside), m = (n*Ho+ho)*Wo+wo.

@@ -203,6 +203,7 @@ class ConvTClass(C.Structure):
 
 def _conv_argtypes(lib) -> None:
     P = C.POINTER
+    lib.mvae_convt_axis_classes.argtypes = [c_int] * 4 + [P(c_int)] * 4
     lib.mvae_convt_gemm.argtypes = [c_int] * 9 + [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]
     lib.mvae_convt_class_gemm.argtypes = [P(ConvTClass), c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]
     lib.mvae_conv_out_size.argtypes = [c_int] * 4

@@ -100,31 +100,42 @@ int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, c
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }
 
+int mvae_convt_axis_classes(int kernel, int stride, int pad, int size_in, int* count, int* taps, int* pad_lo, int* kh) {
+  if (kernel <= 0 || stride <= 0 || stride > 4 || pad < 0 || size_in <= 0) return -1;
+  const int size_out = (size_in - 1) * stride - 2 * pad + kernel;
+  for (int a = 0; a < stride; ++a) {
+    const int r = (a + pad) % stride;
+    const int n = kernel > r ? (kernel - r + stride - 1) / stride : 0;
+    if (n > 8) return -1;
+    taps[a] = n;
+    count[a] = size_out > a ? (size_out - a + stride - 1) / stride : 0;
+    pad_lo[a] = n - 1 - (a + pad) / stride;
+    for (int t = 0; t < 8; ++t) kh[a * 8 + t] = t < n ? r + stride * (n - 1 - t) : 0;
+  }
+  return size_out;
+}
+
 int mvae_convt_gemm(int dtype, int batch, int in_h, int in_w, int channels, int out_channels, int kernel, int stride, int pad,
                     const void* x, const void* weight, int64_t ld_tap, void* out, int64_t ldc, int out_dtype, void* stream) {
   MVAE_REQUIRE(x != nullptr && weight != nullptr && out != nullptr, "mvae_convt_gemm: null argument");
   MVAE_REQUIRE(batch > 0 && in_h > 0 && in_w > 0 && kernel > 0 && stride > 0 && stride <= 4 && pad >= 0, "mvae_convt_gemm: bad geometry");
   const int out_h = (in_h - 1) * stride - 2 * pad + kernel, out_w = (in_w - 1) * stride - 2 * pad + kernel;
-  // per-axis parity classes (mvae_b200._ops.transposed_conv_classes): all must have the same tap count and the same grid
-  int taps0 = -1, cnt_h0 = -1, cnt_w0 = -1;
+  // per-axis parity classes: all must have the same tap count and the same grid
+  int cnt_h[4], cnt_w[4], taps[4], pad_lo[4], kh[32];
+  MVAE_REQUIRE(mvae_convt_axis_classes(kernel, stride, pad, in_h, cnt_h, taps, pad_lo, kh) == out_h &&
+                   mvae_convt_axis_classes(kernel, stride, pad, in_w, cnt_w, taps, pad_lo, kh) == out_w,
+               "mvae_convt_gemm: bad geometry");
+  const int taps0 = taps[0], cnt_h0 = cnt_h[0], cnt_w0 = cnt_w[0];
   GemmDesc g;
   ConvGather& cg = g.gather;
   for (int a = 0; a < stride; ++a) {
-    const int r = (a + pad) % stride;
-    const int taps = kernel > r ? (kernel - r + stride - 1) / stride : 0;
-    const int q = (a + pad) / stride;
-    const int cnt_h = out_h > a ? (out_h - a + stride - 1) / stride : 0;
-    const int cnt_w = out_w > a ? (out_w - a + stride - 1) / stride : 0;
-    if (a == 0) {
-      taps0 = taps; cnt_h0 = cnt_h; cnt_w0 = cnt_w;
-    }
-    if (taps != taps0 || cnt_h != cnt_h0 || cnt_w != cnt_w0 || taps < 1 || taps > 8 || cnt_h < 1 || cnt_w < 1) {
+    if (taps[a] != taps0 || cnt_h[a] != cnt_h0 || cnt_w[a] != cnt_w0 || taps0 < 1 || taps0 > 8 || cnt_h0 < 1 || cnt_w0 < 1) {
       set_error("mvae_convt_gemm: parity classes of k=%d s=%d p=%d differ in shape; use mvae_convt_class_gemm per class", kernel,
                 stride, pad);
       return 4;
     }
-    cg.ax_pad[a] = static_cast<signed char>(taps - 1 - q);
-    for (int t = 0; t < taps; ++t) cg.ax_k[a][t] = static_cast<signed char>(r + stride * (taps - 1 - t));
+    cg.ax_pad[a] = static_cast<signed char>(pad_lo[a]);
+    for (int t = 0; t < taps[a]; ++t) cg.ax_k[a][t] = static_cast<signed char>(kh[a * 8 + t]);
   }
   g.kind = dtype;
   g.M = batch * cnt_h0 * cnt_w0;

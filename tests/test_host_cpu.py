@@ -212,3 +212,30 @@ def test_gather_multiply_shift_division_is_exact():
         m = np.concatenate([rng.integers(0, 1 << 24, size=20000, dtype=np.uint64), mult[mult < (1 << 24)],
                             mult[(mult > 0) & (mult <= (1 << 24))] - np.uint64(1), np.array([(1 << 24) - 1], dtype=np.uint64)])
         assert ((m * magic) >> np.uint64(40) == m // np.uint64(d)).all(), d
+
+
+def test_c_parity_class_tables_equal_the_python_index_map():
+    """mvae_convt_axis_classes (the tables mvae_convt_gemm puts into the kernel parameters) == _ops.transposed_conv_classes,
+    which test_transposed_conv_parity_classes_match_torch pins to F.conv_transpose2d."""
+    import mvae_b200  # noqa: F401
+    from mvae_b200 import _lib, _ops
+    lib = _lib.load()
+    I4, I32 = C.c_int * 4, C.c_int * 32
+    for k in range(1, 9):
+        for s in range(1, 5):
+            for p in range(0, 4):
+                for n in (1, 2, 5, 8, 13):
+                    if (n - 1) * s - 2 * p + k <= 0:
+                        continue
+                    cnt, taps, pad_lo, kh = I4(), I4(), I4(), I32()
+                    out = lib.mvae_convt_axis_classes(k, s, p, n, cnt, taps, pad_lo, kh)
+                    size_out, classes = _ops.transposed_conv_classes(k, s, p, n)
+                    if max(len(c["kh"]) for c in classes) > 8:
+                        assert out == -1
+                        continue
+                    assert out == size_out, (k, s, p, n)
+                    for c in classes:
+                        a = c["a"]
+                        assert (cnt[a], taps[a], pad_lo[a]) == (c["count"], len(c["kh"]), c["pad_lo"]), (k, s, p, n, a)
+                        assert [kh[a * 8 + t] for t in range(taps[a])] == c["kh"], (k, s, p, n, a)
+    assert lib.mvae_convt_axis_classes(4, 5, 1, 8, I4(), I4(), I4(), I32()) == -1   # stride > 4
