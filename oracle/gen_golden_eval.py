@@ -1,0 +1,74 @@
+"""Generate tests/golden/*_eval.npz from the REAL reference in eval mode (run in the build container only).
+
+The reference's evaluation scripts (mnist/test.py:18-36, mnist/loglikelihood.py:24-38, */sample.py) call the models under
+`vae.eval()`: BatchNorm uses its running statistics, Dropout is off and `reparametrize` returns `mu`
+(mnist/model.py:24-30).  For each family this loads a deterministic state with NON-trivial running statistics into the
+reference's own `MultimodalVAE`, runs the three forward signatures and stores every output.  The fixtures pin the
+oracles' eval path (tests/test_oracle*.py), against which the device's eval path is tested on the GPU.
+
+    python oracle/gen_golden_eval.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+sys.path.insert(0, HERE)
+
+
+def run(vae, state, calls):
+    vae.load_state_dict({k: v.clone() for k, v in state.items()})
+    vae.eval()
+    outs = {}
+    with torch.no_grad():
+        for name, kw in calls.items():
+            ri, ro, mu, lv = vae(**kw)
+            outs[name + "/recon_image"] = ri.numpy().astype(np.float32)
+            outs[name + "/recon_other"] = ro.numpy().astype(np.float32)
+            outs[name + "/mu"] = mu.numpy().astype(np.float32)
+            outs[name + "/logvar"] = lv.numpy().astype(np.float32)
+    return outs
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    B, n, seed = 6, 16, 4
+
+    import gen_golden as GM
+    import mnist_oracle as MO
+    model_mod, _ = GM.import_reference_mnist()
+    state = MO.randomize_running_stats(MO.perturbed_state(n, seed), seed)
+    image, text, _ = MO.synthetic_batch(B, n, seed)
+    outs = run(model_mod.MultimodalVAE(n_latents=n), state, {"joint": dict(image=image, text=text), "image": dict(image=image),
+                                                             "text": dict(text=text)})
+    np.savez_compressed(os.path.join(GOLD, "mnist_eval.npz"), batch=B, n_latents=n, seed=seed, **outs)
+
+    import gen_golden_celeba as GC
+    import celeba_oracle as CO
+    model_mod, _ = GC.import_reference_celeba()
+    state = MO.randomize_running_stats(CO.init_state(n, seed=1234 + seed), seed)
+    Bc = 3   # 3x64x64 images: keep the fixture small
+    image, attrs, _ = CO.synthetic_batch(Bc, n, seed)
+    outs = run(model_mod.MultimodalVAE(n_latents=n), state, {"joint": dict(image=image, attrs=attrs), "image": dict(image=image),
+                                                             "attrs": dict(attrs=attrs)})
+    np.savez_compressed(os.path.join(GOLD, "celeba_eval.npz"), batch=Bc, n_latents=n, seed=seed, **outs)
+
+    import gen_golden_multimnist as GX
+    import multimnist_oracle as XO
+    model_mod, _ = GX.import_reference_multimnist()
+    state = MO.randomize_running_stats(XO.init_state(n, seed=1234 + seed), seed)
+    image, text, _ = XO.synthetic_batch(B, n, seed)
+    outs = run(model_mod.MultimodalVAE(n_latents=n), state, {"joint": dict(image=image, text=text), "image": dict(image=image),
+                                                             "text": dict(text=text)})
+    np.savez_compressed(os.path.join(GOLD, "multimnist_eval.npz"), batch=B, n_latents=n, seed=seed, **outs)
+    for f in ("mnist_eval", "celeba_eval", "multimnist_eval"):
+        print(f, os.path.getsize(os.path.join(GOLD, f + ".npz")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

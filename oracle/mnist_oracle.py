@@ -108,6 +108,21 @@ def perturbed_state(n_latents: int, seed: int) -> State:
     return st
 
 
+def randomize_running_stats(state: State, seed: int) -> State:
+    """Same weights, running_mean ~ 0.2 N(0,1), running_var ~ U(0.5, 1.5), deterministic in `seed` and the key order:
+    the state of the eval-mode fixtures (oracle/gen_golden_eval.py).  Works for any of the three families' states."""
+    g = torch.Generator().manual_seed(9000 + seed)
+    out = {}
+    for k, v in state.items():
+        if k.endswith("running_mean"):
+            out[k] = 0.2 * torch.randn(v.shape, generator=g)
+        elif k.endswith("running_var"):
+            out[k] = 0.5 + torch.rand(v.shape, generator=g)
+        else:
+            out[k] = v.clone()
+    return out
+
+
 def sample_flat(t: torch.Tensor, max_n: int = 512) -> torch.Tensor:
     """Deterministic strided sample of a tensor (fixtures store samples, not whole gradients)."""
     f = t.detach().reshape(-1)

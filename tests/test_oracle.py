@@ -117,3 +117,15 @@ def test_adam_matches_torch_optim():
         opt.step()
         p = O.adam_step(p, {"a.weight": g}, m, v, step)
         np.testing.assert_allclose(p["a.weight"].numpy(), ref.detach().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_eval_forward_matches_reference_fixture():
+    """vae.eval() forward of the real reference (running statistics, z = mu; mnist/test.py:18-36) vs the oracle."""
+    g = np.load(os.path.join(GOLD, "mnist_eval.npz"))
+    B, n, seed = int(g["batch"]), int(g["n_latents"]), int(g["seed"])
+    state = O.randomize_running_stats(O.perturbed_state(n, seed), seed)
+    image, text, _ = O.synthetic_batch(B, n, seed)
+    for name, (im, tx) in {"joint": (image, text), "image": (image, None), "text": (None, text)}.items():
+        ri, rt, mu, lv, _, _ = O.forward(state, im, tx, None, None, training=False)
+        for key, got in (("recon_image", ri), ("recon_other", rt), ("mu", mu), ("logvar", lv)):
+            np.testing.assert_allclose(got.detach().numpy(), g["%s/%s" % (name, key)], rtol=2e-5, atol=2e-6, err_msg=name + key)

@@ -55,3 +55,17 @@ def test_eval_forward_uses_running_stats():
     a = O.forward(state, image, attrs, None, None, training=False)
     b = O.forward(state, image[:2], attrs[:2], None, None, training=False)
     assert rel(b[0].detach(), a[0][:2].detach()) < 1e-6   # no batch coupling in eval mode
+
+
+def test_eval_forward_matches_reference_fixture():
+    """vae.eval() forward of the real reference (BatchNorm running statistics, Dropout off, z = mu; celeba/sample.py
+    usage) vs the oracle's eval path, all three call signatures (oracle/gen_golden_eval.py)."""
+    import mnist_oracle as MO
+    g = np.load(os.path.join(GOLD, "celeba_eval.npz"))
+    B, n, seed = int(g["batch"]), int(g["n_latents"]), int(g["seed"])
+    state = MO.randomize_running_stats(O.init_state(n, seed=1234 + seed), seed)
+    image, attrs, _ = O.synthetic_batch(B, n, seed)
+    for name, (im, at) in {"joint": (image, attrs), "image": (image, None), "attrs": (None, attrs)}.items():
+        ri, ra, mu, lv, _, _ = O.forward(state, im, at, None, None, training=False)
+        for key, got in (("recon_image", ri), ("recon_other", ra), ("mu", mu), ("logvar", lv)):
+            assert rel(got.detach(), g["%s/%s" % (name, key)]) < 2e-5, (name, key)

@@ -57,3 +57,17 @@ def test_text_decoder_shape_and_normalisation():
     lp = O.text_decoder(st, torch.randn(5, 16, generator=torch.Generator().manual_seed(0)))
     assert lp.shape == (5, O.MAX_LEN, O.N_CHARS)
     assert torch.allclose(lp.exp().sum(-1), torch.ones(5, O.MAX_LEN), atol=1e-5)
+
+
+def test_eval_forward_matches_reference_fixture():
+    """vae.eval() forward of the real reference (running statistics, Dropout off, z = mu, greedy text decode) vs the
+    oracle's eval path, all three call signatures (oracle/gen_golden_eval.py)."""
+    import mnist_oracle as MO
+    g = np.load(os.path.join(GOLD, "multimnist_eval.npz"))
+    B, n, seed = int(g["batch"]), int(g["n_latents"]), int(g["seed"])
+    state = MO.randomize_running_stats(O.init_state(n, seed=1234 + seed), seed)
+    image, text, _ = O.synthetic_batch(B, n, seed)
+    for name, (im, tx) in {"joint": (image, text), "image": (image, None), "text": (None, text)}.items():
+        ri, rt, mu, lv, _ = O.forward(state, im, tx, None, None, training=False)
+        for key, got in (("recon_image", ri), ("recon_other", rt), ("mu", mu), ("logvar", lv)):
+            assert rel(got.detach(), g["%s/%s" % (name, key)]) < 2e-5, (name, key)
