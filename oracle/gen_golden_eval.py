@@ -48,6 +48,36 @@ def main():
                                                              "text": dict(text=text)})
     np.savez_compressed(os.path.join(GOLD, "mnist_eval.npz"), batch=B, n_latents=n, seed=seed, **outs)
 
+    # the reference's evaluation entry points themselves (mnist/test.py:18-36, mnist/loglikelihood.py:15-63), compiled out of
+    # their files (the modules import torchvision / a py2-only train.py at top level) and run on two synthetic batches
+    import ast
+    from torch.autograd import Variable
+    REF = GM.REF
+    ns = {"torch": torch, "F": torch.nn.functional, "Variable": Variable, "xrange": range, "print": lambda *a, **k: None}
+    for rel_path, fn_name in (("mnist/test.py", "test_mnist"), ("mnist/loglikelihood.py", "compute_nll")):
+        tree = ast.parse(open(os.path.join(REF, rel_path)).read())
+        fn = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name == fn_name]
+        exec(compile(ast.Module(body=fn, type_ignores=[]), rel_path, "exec"), ns)
+
+    class Loader(list):
+        @property
+        def dataset(self):
+            return range(sum(len(b[1]) for b in self))
+
+    Be, S = 40, 3
+    batches = Loader([MO.synthetic_batch(Be, n, s)[:2] for s in (1, 2)])
+    vae = model_mod.MultimodalVAE(n_latents=n)
+    vae.load_state_dict({k: v.clone() for k, v in state.items()})
+    acc = float(ns["test_mnist"](vae, batches, verbose=False))
+    res = {}
+    for key, kw in (("joint", {}), ("image_only", {"image_only": True}), ("text_only", {"text_only": True})):
+        torch.manual_seed(11)
+        i_nll, t_nll = ns["compute_nll"](vae, batches, n_samples=S, **kw)
+        res[key] = (float(i_nll), float(t_nll))
+    np.savez_compressed(os.path.join(GOLD, "mnist_eval_scripts.npz"), batch=Be, n_latents=n, seed=seed, n_samples=S, noise_seed=11,
+                        batch_seeds=np.array([1, 2]), accuracy=acc, **{"nll_" + k: np.array(v) for k, v in res.items()})
+    print("mnist eval scripts: accuracy %.4f nll %s" % (acc, res))
+
     import gen_golden_celeba as GC
     import celeba_oracle as CO
     model_mod, _ = GC.import_reference_celeba()

@@ -404,3 +404,35 @@ def synthetic_batch(batch: int, n_latents: int, seed: int = 0, dtype=torch.float
     text = torch.randint(0, 10, (batch,), generator=g)
     noises = [torch.randn(batch, n_latents, generator=g, dtype=dtype) for _ in range(3)]
     return image, text, noises
+
+
+def test_mnist(p: State, batches) -> float:
+    """mnist/test.py:18-36: fraction of labels recovered from the image alone, eval mode (argmax of recon_text)."""
+    hits, total = 0, 0
+    for image, text in batches:
+        out = forward(p, image.reshape(image.shape[0], -1), None, None, None, training=False)
+        hits += int((out[1].argmax(1) == text).sum())
+        total += int(text.numel())
+    return hits / float(total)
+
+
+def compute_nll(p: State, batches, image_only=False, text_only=False, n_samples=1, generator=None):
+    """mnist/loglikelihood.py:15-63: per-example (image NLL, text NLL) with z ~ q(z | inputs); ONE [n_samples, n_latents]
+    normal tensor per batch, shared by its rows (:36-46), sums over pixels / classes (size_average=False, :51-52)."""
+    assert not (image_only and text_only)
+    tot_i = tot_t = 0.0
+    total = 0
+    for image, text in batches:
+        image = image.reshape(image.shape[0], -1)
+        out = forward(p, None if text_only else image, None if image_only else text, None, None, training=False)
+        mu, logvar = out[2], out[3]
+        sample = torch.randn(n_samples, mu.shape[1], generator=generator)
+        std = torch.exp(0.5 * logvar)
+        for i in range(n_samples):
+            z = sample[i].unsqueeze(0) * std + mu
+            ri = torch.sigmoid(image_decoder_logits(p, z, None, False))
+            rt = torch.log_softmax(text_decoder_logits(p, z, None, False), dim=1)
+            tot_i += float(torch.nn.functional.binary_cross_entropy(ri, image, reduction="sum")) / n_samples
+            tot_t += float(torch.nn.functional.nll_loss(rt, text, reduction="sum")) / n_samples
+        total += image.shape[0]
+    return tot_i / total, tot_t / total

@@ -179,30 +179,14 @@ def test_evaluation_entry_points_match_oracle():
     m = mvae_b200.MVAE(n, precision="tf32")
     m.load_state_dict(state)
     batches = [O.synthetic_batch(B, n, s)[:2] for s in (1, 2)]
-    # accuracy
+    # accuracy (O.test_mnist / O.compute_nll are pinned to the reference's own functions: tests/test_oracle.py)
     acc = evaluation.test_mnist(m, batches)
-    hits = 0
-    for image, text in batches:
-        out = O.forward(state, image, None, None, None, training=False)
-        hits += int((out[1].argmax(1) == text).sum())
-    assert abs(acc - hits / (2.0 * B)) <= 1.0 / (2 * B) + 1e-9          # tf32: at most one near-tie flip
+    assert abs(acc - O.test_mnist(state, batches)) <= 1.0 / (2 * B) + 1e-9          # tf32: at most one near-tie flip
     # sampled NLL with the same shared draws
     gen = torch.Generator().manual_seed(11)
     got = evaluation.compute_nll(m, batches, n_samples=S, generator=gen)
     gen = torch.Generator().manual_seed(11)
-    ref_i = ref_t = 0.0
-    for image, text in batches:
-        out = O.forward(state, image, text, None, None, training=False)
-        mu, logvar = out[2], out[3]
-        sample = torch.randn(S, n, generator=gen)
-        std = torch.exp(0.5 * logvar)
-        for i in range(S):
-            z = sample[i].unsqueeze(0) * std + mu
-            ri = torch.sigmoid(O.image_decoder_logits(state, z, None, False))
-            rt = torch.log_softmax(O.text_decoder_logits(state, z, None, False), dim=1)
-            ref_i += float(torch.nn.functional.binary_cross_entropy(ri, image, reduction="sum")) / S
-            ref_t += float(torch.nn.functional.nll_loss(rt, text, reduction="sum")) / S
-    ref_i, ref_t = ref_i / (2 * B), ref_t / (2 * B)
+    ref_i, ref_t = O.compute_nll(state, batches, n_samples=S, generator=gen)
     assert abs(got[0] - ref_i) <= 2e-3 * ref_i and abs(got[1] - ref_t) <= 5e-3 * ref_t, (got, ref_i, ref_t)
 
 

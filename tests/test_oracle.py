@@ -129,3 +129,17 @@ def test_eval_forward_matches_reference_fixture():
         ri, rt, mu, lv, _, _ = O.forward(state, im, tx, None, None, training=False)
         for key, got in (("recon_image", ri), ("recon_other", rt), ("mu", mu), ("logvar", lv)):
             np.testing.assert_allclose(got.detach().numpy(), g["%s/%s" % (name, key)], rtol=2e-5, atol=2e-6, err_msg=name + key)
+
+
+def test_evaluation_entry_points_match_reference_functions():
+    """mnist/test.py:18-36 (`test_mnist`) and mnist/loglikelihood.py:15-63 (`compute_nll`), the reference's OWN functions run
+    on its own model (oracle/gen_golden_eval.py), vs the oracle's restatements that the GPU evaluation test checks against."""
+    g = np.load(os.path.join(GOLD, "mnist_eval_scripts.npz"))
+    B, n, seed, S = int(g["batch"]), int(g["n_latents"]), int(g["seed"]), int(g["n_samples"])
+    state = O.randomize_running_stats(O.perturbed_state(n, seed), seed)
+    batches = [O.synthetic_batch(B, n, int(s))[:2] for s in g["batch_seeds"]]
+    assert O.test_mnist(state, batches) == pytest.approx(float(g["accuracy"]), abs=1e-7)   # the reference divides in fp32
+    for key, kw in (("joint", {}), ("image_only", {"image_only": True}), ("text_only", {"text_only": True})):
+        gen = torch.Generator().manual_seed(int(g["noise_seed"]))
+        got = O.compute_nll(state, batches, n_samples=S, generator=gen, **kw)
+        np.testing.assert_allclose(got, g["nll_" + key], rtol=2e-6, err_msg=key)
