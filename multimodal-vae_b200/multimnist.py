@@ -510,3 +510,23 @@ def loss_function(mu, logvar, recon_image=None, image=None, recon_text=None, tex
         z = torch.zeros(rt.shape[0], 1, device=mu.device)
         total = total + _ElboFn.apply(z, z, None, None, rt, text.reshape(-1), 0.0, float(lambda_yx), 0.0)
     return total
+
+
+# ---------------------------------------------------------------------------- label <-> character-index helpers
+def charlist_tensor(charlists, device=None) -> torch.Tensor:
+    """multimnist/utils.py:22-37 (`char_tensor` / `charlist_tensor`) for a whole batch at once: each entry is the list of
+    digits shown in one image (at most MAX_LEN = 4); returns int64 [batch, 4] with the digits left-aligned and FILL (11)
+    in the unused positions - the `text` input of MultimodalVAE.forward / MultiMNISTTrainer.step."""
+    out = torch.full((len(charlists), MAX_LEN), FILL, dtype=torch.int64)
+    for b, digits in enumerate(charlists):
+        digits = [int(d) for d in (digits.tolist() if torch.is_tensor(digits) else digits)]
+        if len(digits) > MAX_LEN or any(d < 0 or d > 9 for d in digits):
+            raise ValueError("entry %d: at most %d digits in 0..9, got %r" % (b, MAX_LEN, digits))
+        if digits:
+            out[b, :len(digits)] = torch.tensor(digits, dtype=torch.int64)
+    return out if device is None else out.to(device)
+
+
+def tensor_to_string(indices) -> str:
+    """multimnist/utils.py:40-56: digits as characters, SOS as '^', FILL as nothing."""
+    return "".join("^" if int(i) == SOS else "" if int(i) == FILL else "0123456789"[int(i)] for i in indices)

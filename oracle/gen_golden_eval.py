@@ -96,6 +96,22 @@ def main():
     outs = run(model_mod.MultimodalVAE(n_latents=n), state, {"joint": dict(image=image, text=text), "image": dict(image=image),
                                                              "text": dict(text=text)})
     np.savez_compressed(os.path.join(GOLD, "multimnist_eval.npz"), batch=B, n_latents=n, seed=seed, **outs)
+    # multimnist/utils.py:22-56: charlist_tensor / tensor_to_string of the reference on a few label lists
+    import builtins
+    builtins.xrange = range
+    for m in ("utils", "model", "train", "datasets"):
+        sys.modules.pop(m, None)
+    sys.path.insert(0, os.path.join(REF, "multimnist"))
+    import utils as U  # type: ignore
+    sys.path.pop(0)
+    cases = [[], [7], [1, 2], [0, 0, 9], [9, 8, 7, 6], [3, 3], [5, 0, 5, 0]]
+    exp = torch.stack([U.charlist_tensor(c) for c in cases]).numpy()
+    strs = [U.tensor_to_string(torch.tensor(r)) for r in exp] + [U.tensor_to_string(torch.tensor([10, 4, 11, 2]))]
+    flat = np.full((len(cases), 4), -1, dtype=np.int64)
+    for i, c in enumerate(cases):
+        flat[i, :len(c)] = c
+    np.savez_compressed(os.path.join(GOLD, "multimnist_charlist.npz"), digits=flat, expected=exp, strings=np.array(strs))
+
     for f in ("mnist_eval", "celeba_eval", "multimnist_eval"):
         print(f, os.path.getsize(os.path.join(GOLD, f + ".npz")), "bytes")
 

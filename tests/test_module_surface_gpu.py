@@ -235,3 +235,21 @@ def test_checkpoint_roundtrip_and_resume(family, tmp_path):
     resumed = [total(t2) for _ in range(2)]
     for a, b in zip(cont, resumed):
         assert abs(a - b) <= 2e-3 * abs(a), (cont, resumed)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_uint8_images_are_converted_on_the_device(precision):
+    """uint8 pixels -> activation dtype by mvae_u8_to_act (x / 255, transforms.ToTensor semantics of the
+    reference's loaders, mnist/train.py:100-108), host or device input, [B,1,28,28] or [B,784]."""
+    import mvae_b200
+    m = mvae_b200.MVAE(8, precision=precision)
+    g = torch.Generator().manual_seed(2)
+    u8 = torch.randint(0, 256, (37, 1, 28, 28), generator=g, dtype=torch.uint8)
+    ref = u8.reshape(37, 784).float() / 255.0
+    for src in (u8, u8.cuda(), u8.reshape(37, 784)):
+        x = m.to_act(src)
+        assert x.shape == (37, 784) and x.dtype == m.act_dtype() and x.is_cuda
+        err = float((x.float().cpu() - ref).abs().max())
+        assert err <= (1e-6 if precision == "tf32" else 8e-3), err
+    assert float(m.to_act(torch.zeros(4, 784, dtype=torch.uint8)).float().abs().max()) == 0.0
+    assert abs(float(m.to_act(torch.full((4, 784), 255, dtype=torch.uint8)).float().min()) - 1.0) <= 1e-6

@@ -71,3 +71,19 @@ def test_eval_forward_matches_reference_fixture():
         ri, rt, mu, lv, _ = O.forward(state, im, tx, None, None, training=False)
         for key, got in (("recon_image", ri), ("recon_other", rt), ("mu", mu), ("logvar", lv)):
             assert rel(got.detach(), g["%s/%s" % (name, key)]) < 2e-5, (name, key)
+
+
+def test_charlist_tensor_matches_reference_utils():
+    """multimnist/utils.py:22-56 (`charlist_tensor`, `tensor_to_string`) of the real reference vs the batched host helpers
+    (fixture written from the reference's functions by oracle/gen_golden_eval.py)."""
+    import mvae_b200  # noqa: F401
+    from mvae_b200 import multimnist as MM
+    g = np.load(os.path.join(GOLD, "multimnist_charlist.npz"))
+    cases = [[int(d) for d in row if d >= 0] for row in g["digits"]]
+    got = MM.charlist_tensor(cases)
+    assert got.dtype == torch.int64 and torch.equal(got, torch.from_numpy(g["expected"]))
+    strings = [str(s) for s in g["strings"]]
+    assert [MM.tensor_to_string(r) for r in got] == strings[:-1]
+    assert MM.tensor_to_string(torch.tensor([10, 4, 11, 2])) == strings[-1]
+    with pytest.raises(ValueError):
+        MM.charlist_tensor([[1, 2, 3, 4, 5]])
