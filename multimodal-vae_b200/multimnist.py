@@ -472,6 +472,30 @@ class MultimodalVAE(ConvMVAEBase):
     def decode_text(self, z):
         return self._decode_only(z)[1]
 
+    @property
+    def text_decoder(self):
+        """`vae.text_decoder(z)` / `vae.text_decoder.generate(z)` (multimnist/train.py:264, model.py:254-296)."""
+        return _TextDecoderSurface(self)
+
+
+class _TextDecoderSurface:
+    """The two calls the reference makes on `vae.text_decoder` from outside the model: the greedy decode and `generate`."""
+
+    def __init__(self, model: "MultimodalVAE"):
+        self._m = model
+
+    def __call__(self, z):
+        """log-probabilities [B, 4, 12] of the greedy decode (multimnist/model.py:254-288)."""
+        return self._m.decode_text(z)
+
+    def generate(self, z, generator: Optional[torch.Generator] = None):
+        """multimnist/model.py:290-296: one character index per position, drawn from the decoder's distribution; int64
+        [B, 4].  The reference passes the LOG-probabilities to torch.multinomial (which rejects negative weights, so the call
+        fails there); this samples from exp(log-probabilities), the evident intent."""
+        words = self._m.decode_text(z)
+        probs = words.reshape(-1, N_CHARS).float().exp()
+        return torch.multinomial(probs, 1, generator=generator).view(words.shape[0], MAX_LEN)
+
 
 class MultiMNISTTrainer(ConvMVAETrainer):
     """multimnist/train.py:148-175 with its lambdas (1,1), (1,.5), (0,1) and kl_lambda 1e-3 (:227)."""

@@ -4,6 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 MVAE_TEST_CONVT_MERGED=1 timeout 60 python -m pytest tests/test_celeba_gpu.py -x -q -m gpu -k "transposed_conv" 2>&1 | tail -5
+MVAE_TEST_UNVERIFIED=1 timeout 60 python -m pytest tests/test_multimnist_gpu.py tests/test_module_surface_gpu.py -x -q -m gpu -k "generate or uint8" 2>&1 | tail -5
 MVAE_IMPLICIT_COL2IM=1 timeout 280 python -m pytest tests/test_celeba_gpu.py tests/test_multimnist_gpu.py -x -q -m gpu \
   -k "step_matches_oracle or ragged or graph_replay or fixture or autograd" 2>&1 | tail -5
 for w in celeba multimnist; do
