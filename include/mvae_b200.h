@@ -23,10 +23,15 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 3
+#define MVAE_ABI_VERSION 4
 
 #define MVAE_DT_F32 0
 #define MVAE_DT_BF16 1
+/* fp32 storage, error-compensated 3xTF32 tensor-core GEMMs: every operand is split into hi = tf32(x) and
+ * lo = x - hi and the product is hi*hi + lo*hi + hi*lo in fp32 TMEM accumulators (fp32-grade results; the parity
+ * mode that meets "rtol 1e-3 on every gradient" against the fp32 reference).  Accepted by mvae_mnist_sizes /
+ * mvae_mnist_step (dtype) and by mvae_gemm (dtype, with x3_scratch). */
+#define MVAE_DT_F32X3 2
 
 /* PoE arithmetic:
  *   REF       - bit-for-bit the reference: var=exp(logvar)+eps, mu=sum(mu*var)/sum(var)
@@ -65,6 +70,8 @@ typedef struct mvae_gemm_args {
   int split_k;        /* 0 = auto */
   int stages;         /* 0 = auto */
   void* debug_times;  /* NULL, or device int64 [ctas][8] receiving %globaltimer stamps (bring-up only) */
+  void* x3_scratch;   /* MVAE_DT_F32X3 only: device scratch for the split operands, >= 12 * (M + N + 8) * (K + 4) bytes */
+  int64_t x3_scratch_bytes;
 } mvae_gemm_args;
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
 /* Bring-up: GEMM launches whose epilogue kind (0 store, 1 atomic, 2 BCE, 3 dgrad-BN) equals epilogue_kind write
@@ -127,7 +134,8 @@ typedef struct mvae_mnist_step_args {
   float* grads;             /* flat fp32 gradients (accumulated into) */
   int do_backward, zero_grad, do_adam;
   float* adam_m; float* adam_v;
-  int* adam_step;           /* device int: incremented at the start of every call (also the Philox step) */
+  int* adam_step;           /* device int, Adam's 1-based bias-correction clock: incremented at the start of a call that
+                               opens an optimizer step (do_adam or advance_adam_step), never by forward-only calls */
   float lr, beta1, beta2, adam_eps, grad_scale;
   void* workspace; int64_t workspace_bytes;
   float* out_losses;        /* device [n_terms][4]: total, image BCE, text NLL, KL (already weighted) or NULL */
@@ -147,6 +155,11 @@ typedef struct mvae_mnist_step_args {
   const float* d_recon_text;/* phase 2: gradient w.r.t. the recon_text log-probabilities, or NULL */
   const float* d_mu;        /* phase 2: gradient w.r.t. mu [n_terms, batch, n_latents], or NULL */
   const float* d_logvar;
+  /* --- ABI v4 --- */
+  int* noise_step;          /* device int: the Philox counter of the in-kernel N(0,1) draws; incremented at the start of
+                               every forward-type call (training or eval).  NULL: adam_step doubles as the counter */
+  int advance_adam_step;    /* 1: this call opens an optimizer step whose Adam update is issued separately (mvae_adam_step
+                               after a gradient all-reduce or after several accumulating calls): ++*adam_step */
 } mvae_mnist_step_args;
 int mvae_mnist_step(const mvae_mnist_step_args* args, void* stream);
 

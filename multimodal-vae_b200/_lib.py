@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("col_sum", c_void_p), ("col_sumsq", c_void_p), ("rows_per_group", c_int),
         ("block_n", c_int), ("split_k", c_int), ("stages", c_int),
         ("debug_times", c_void_p),
+        ("x3_scratch", c_void_p), ("x3_scratch_bytes", c_int64),
     ]
 
 
@@ -104,6 +105,7 @@ class MnistStepArgs(C.Structure):
         ("out_mu", c_void_p), ("out_logvar", c_void_p),
         ("eval_mode", c_int), ("phase", c_int), ("z_in", c_void_p),
         ("d_recon_image", c_void_p), ("d_recon_text", c_void_p), ("d_mu", c_void_p), ("d_logvar", c_void_p),
+        ("noise_step", c_void_p), ("advance_adam_step", c_int),
     ]
 
 
@@ -116,7 +118,7 @@ class ElboLossArgs(C.Structure):
     ]
 
 
-DT_F32, DT_BF16 = 0, 1
+DT_F32, DT_BF16, DT_F32X3 = 0, 1, 2
 POE_REF, POE_PRECISION = 0, 1
 TERM_JOINT, TERM_IMAGE, TERM_TEXT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2

@@ -37,11 +37,15 @@ def _model_class(family: str):
     raise ValueError("family must be mnist, celeba or multimnist")
 
 
-def load_checkpoint(file_path: str, family: str = "mnist", precision: str = "bf16", **model_kwargs):
+def load_checkpoint(file_path: str, family: str = "mnist", precision: str = "tf32", **model_kwargs):
     """mnist/train.py:44-61: a model of the checkpoint's n_latents (default 20) with its state_dict loaded.  Reference
-    checkpoints (CPU or CUDA tensors, reference shapes) load unchanged."""
+    checkpoints (CPU or CUDA tensors, reference shapes) load unchanged.  The default precision is "tf32" (any even
+    n_latents that is a multiple of 4, e.g. the reference's 20); MNIST in "bf16" needs n_latents % 8 == 0 and falls
+    back to "tf32" otherwise."""
     checkpoint = torch.load(file_path, map_location="cpu", weights_only=False)
     n_latents = int(checkpoint.get("n_latents", 20))
+    if family == "mnist" and precision == "bf16" and n_latents % 8:
+        precision = "tf32"
     vae = _model_class(family)(n_latents, precision=precision, **model_kwargs)
     vae.load_state_dict(checkpoint["state_dict"])
     return vae
@@ -83,7 +87,7 @@ def trainer_state(trainer) -> Dict:
         mom, vel, lr, betas, eps = trainer.adam["m"], trainer.adam["v"], trainer.adam["lr"], trainer.adam["betas"], trainer.adam["eps"]
     else:
         mom, vel, lr, betas, eps = trainer.adam_m, trainer.adam_v, trainer.lr, trainer.betas, trainer.eps
-    return {"step": int(m._step_counter.item()), "exp_avg": _param_views(m, mom), "exp_avg_sq": _param_views(m, vel),
+    return {"step": int(m._adam_counter.item()), "exp_avg": _param_views(m, mom), "exp_avg_sq": _param_views(m, vel),
             "lr": lr, "betas": tuple(betas), "eps": eps}
 
 
@@ -92,6 +96,7 @@ def load_trainer_state(trainer, state: Dict) -> None:
     mom, vel = (trainer.adam["m"], trainer.adam["v"]) if hasattr(trainer, "adam") else (trainer.adam_m, trainer.adam_v)
     _fill_flat(m, mom, state["exp_avg"])
     _fill_flat(m, vel, state["exp_avg_sq"])
-    m._step_counter.fill_(int(state["step"]))
+    m._adam_counter.fill_(int(state["step"]))
+    m._step_counter.fill_(int(state["step"]))   # the noise counter resumes from the same point (any value is valid)
     if hasattr(trainer, "_graphs"):
         trainer._graphs.clear()       # captured graphs stay valid (state lives in the same buffers) but drop them to be safe

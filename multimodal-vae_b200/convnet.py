@@ -141,7 +141,10 @@ class ConvMVAEBase:
             boff += 2 * self.BN_LAYERS[p]
         self.flat_buffers = torch.zeros(max(boff, 4), device=dev, dtype=torch.float32)
         self.flat_nbt = torch.zeros(max(len(self.bn_names), 1), device=dev, dtype=torch.int64)
-        self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        # [0] noise / dropout (Philox) counter, ticked by every forward; [1] Adam's bias-correction step
+        self._counters = torch.zeros(2, device=dev, dtype=torch.int32)
+        self._step_counter = self._counters[0:1]
+        self._adam_counter = self._counters[1:2]
         self._ws: Dict[Tuple[int, int], object] = {}
         self._pad: Dict[str, Tuple[torch.Tensor, int]] = {}
         self._fresh = set()
@@ -715,8 +718,9 @@ class ConvMVAETrainer:
             if self.world > 1:
                 dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
         if adam:
+            _ops.step_begin(m._adam_counter)     # one optimizer step = one tick of Adam's clock (forwards never tick it)
             _ops.adam_step(m.flat_params, m.flat_grads, self.adam_m, self.adam_v, m.flat_params_bf16, m.param_floats, self.lr,
-                           self.betas[0], self.betas[1], self.eps, m._step_counter, 1.0 / self.world, True)
+                           self.betas[0], self.betas[1], self.eps, m._adam_counter, 1.0 / self.world, True)
 
     def _prepare(self, image, other):
         m = self.model
@@ -736,15 +740,20 @@ class ConvMVAETrainer:
         if not self.use_cuda_graph:
             self._enqueue(ws, image, other, tt, lambdas, eps, adam)
             return ws.acc
-        key = (B, tt, lambdas, eps is not None, adam)
+        # every scalar baked into the captured kernel arguments is part of the key (anneal_kl / adjust_learning_rate of
+        # multimnist/train.py:227-241 mutate kl_lambda / lr between steps); the cache is bounded
+        key = (B, tt, lambdas, eps is not None, adam, float(self.kl_lambda), float(self.lr), tuple(map(float, self.betas)),
+               float(self.eps))
         if key not in self._graphs:
+            while len(self._graphs) >= 16:
+                self._graphs.pop(next(iter(self._graphs)))
             st_img, st_oth = image.clone(), other.clone()
             st_eps = None if eps is None else eps.clone()
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 # warm-up outside capture (allocates padded operand copies, sets up NCCL), state restored afterwards
-                state = (m.flat_params, m.flat_buffers, m.flat_nbt, m._step_counter, self.adam_m, self.adam_v, m.flat_grads)
+                state = (m.flat_params, m.flat_buffers, m.flat_nbt, m._counters, self.adam_m, self.adam_v, m.flat_grads)
                 snap = [t.clone() for t in state]
                 self._enqueue(ws, st_img, st_oth, tt, lambdas, st_eps, adam)
                 for dst, src in zip(state, snap):

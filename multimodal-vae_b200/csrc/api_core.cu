@@ -176,8 +176,17 @@ static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int
     MVAE_REQUIRE(pixels == (patch_operand == 1 ? a->M : a->K), "mvae_conv_gemm: %lld output pixels do not match the GEMM shape",
                  pixels);
   }
-  g.kind = a->dtype;
+  g.kind = a->dtype == MVAE_DT_F32X3 ? MVAE_F32 : a->dtype;
   g.M = a->M; g.N = a->N; g.K = a->K;
+  if (a->dtype == MVAE_DT_F32X3) {
+    const long long kp = (a->K + 3) / 4 * 4 + 4;
+    const long long need_a = 12ll * (a->M + 4) * kp, need_b = 12ll * (a->N + 4) * kp;
+    MVAE_REQUIRE(a->x3_scratch != nullptr && a->x3_scratch_bytes >= need_a + need_b + 512,
+                 "mvae_gemm: MVAE_DT_F32X3 needs x3_scratch of at least %lld bytes", need_a + need_b + 512);
+    g.x3 = 1;
+    g.x3_a = a->x3_scratch;
+    g.x3_b = static_cast<char*>(a->x3_scratch) + (need_a + 255) / 256 * 256;
+  }
   g.A = a->A; g.lda = a->lda; g.a_mn = a->a_major;
   g.B = a->B; g.ldb = a->ldb; g.b_mn = a->b_major;
   g.block_n = a->block_n; g.split_k = a->split_k; g.stages = a->stages;

@@ -142,6 +142,12 @@ struct GemmDesc {
   int split_k = 0;  // 0 = auto (only EPI_ATOMIC may split)
   int stages = 0;   // 0 = auto
   long long* dbg = nullptr;  // device buffer [ctas][8] of %globaltimer stamps (bring-up only)
+  // Error-compensated 3xTF32 (fp32 storage only): each operand is split into hi = tf32(x) and lo = x - hi and the
+  // product is evaluated as hi*hi + lo*hi + hi*lo by ONE GEMM over a 3x longer contraction ([hi|lo|hi] x [hi|hi|lo]).
+  // The split copies go to caller-provided scratch: x3_a >= 3*M*round_up(K,4) floats, x3_b >= 3*N*round_up(K,4).
+  int x3 = 0;
+  void* x3_a = nullptr;
+  void* x3_b = nullptr;
   GemmATransform atf;
   GemmEpilogue epi;
   ConvGather gather;

@@ -411,16 +411,17 @@ struct NbtInc {
   long long v[6];
 };
 __global__ void __launch_bounds__(kEwThreads)
-    step_prep_kernel(int* step_ptr, float4* zero_buf, long long n4, long long* nbt, NbtInc inc) {
+    step_prep_kernel(int* step_ptr, int* step_ptr2, float4* zero_buf, long long n4, long long* nbt, NbtInc inc) {
   pdl_enter();
   if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr != nullptr) *step_ptr += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr2 != nullptr && step_ptr2 != step_ptr) *step_ptr2 += 1;
   if (blockIdx.x == 0 && threadIdx.x < 6 && nbt != nullptr) nbt[threadIdx.x] += inc.v[threadIdx.x];
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     zero_buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
+int launch_step_prep(int* step_ptr, int* step_ptr2, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
                      cudaStream_t st) {
   MVAE_REQUIRE(zero_n % 4 == 0, "step_prep: zero_n=%lld must be a multiple of 4", zero_n);
   const long long n4 = zero_n / 4;
@@ -428,7 +429,7 @@ int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, long long
   if (blocks < 1) blocks = 1;
   NbtInc i;
   for (int k = 0; k < 6; ++k) i.v[k] = inc[k];
-  return launch_pdl(step_prep_kernel, dim3(blocks), dim3(kEwThreads), 0, st, step_ptr, reinterpret_cast<float4*>(zero_buf),
+  return launch_pdl(step_prep_kernel, dim3(blocks), dim3(kEwThreads), 0, st, step_ptr, step_ptr2, reinterpret_cast<float4*>(zero_buf),
                     n4, nbt, i);
 }
 

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -1249,7 +1250,67 @@ void set_gemm_debug_times(void* ptr, int epi_kind) {
 }
 
 static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run);
-int launch_gemm(const GemmDesc& g, cudaStream_t stream) { return launch_gemm_impl(g, stream, false); }
+
+// ---- 3xTF32: operand split.  dst holds three copies of the [R, Cc] source - parts (p0, p1, p2), each the tf32-rounded
+// value (hi, round to nearest even on the 10-bit mantissa) or the exact remainder x - hi (lo) - side by side along the
+// contraction axis: along the columns for a K-major operand (part p at column offset p*cpad) or along the rows for an
+// MN-major one (part p at row offset p*R).  Padding columns [Cc, cpad) are zero-filled.
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, long long ld_src, long long R, int Cc, int cpad,
+                                                     float* __restrict__ dst, long long ld_dst, long long part_stride, int lo_mask) {
+  const long long total = R * cpad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cpad;
+    const int c = static_cast<int>(i - r * cpad);
+    float hi = 0.f, lo = 0.f;
+    if (c < Cc) {
+      const float x = src[r * ld_src + c];
+      const uint32_t b = __float_as_uint(x);
+      hi = __uint_as_float((b + 0x0FFFu + ((b >> 13) & 1u)) & 0xFFFFE000u);
+      lo = x - hi;
+    }
+    float* d = dst + r * ld_dst + c;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) d[p * part_stride] = ((lo_mask >> p) & 1) ? lo : hi;
+  }
+}
+
+static int launch_split3(const void* src, long long ld, int major, long long rows, int K, void* dst, int lo_mask, long long* ld_out,
+                         cudaStream_t st) {
+  // major 0: src is [rows, K] -> dst [rows, 3*Kp]; major 1: src is [K, rows] -> dst [3*K, rows_p]
+  const int Kp = (K + 3) / 4 * 4;
+  const long long rows_p = (rows + 3) / 4 * 4;
+  long long R, ld_dst, part;
+  int Cc, cpad;
+  if (major == 0) { R = rows; Cc = K; cpad = Kp; ld_dst = 3ll * Kp; part = Kp; }
+  else { R = K; Cc = static_cast<int>(rows); cpad = static_cast<int>(rows_p); ld_dst = rows_p; part = static_cast<long long>(K) * rows_p; }
+  *ld_out = ld_dst;
+  const long long total = R * cpad;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  split3_kernel<<<blocks, 256, 0, st>>>(static_cast<const float*>(src), ld, R, Cc, cpad, static_cast<float*>(dst), ld_dst, part, lo_mask);
+  MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return 0;
+}
+
+int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
+  if (!g.x3) return launch_gemm_impl(g, stream, false);
+  MVAE_REQUIRE(g.kind == MVAE_F32 && g.gather.mode == 0 && !g.atf.enabled && !(g.epi.kind == EPI_STORE && g.epi.fuse_bn),
+               "gemm: 3xTF32 needs fp32 storage and a plain (non-gather, non-fused-BatchNorm) GEMM");
+  MVAE_REQUIRE(g.x3_a != nullptr && g.x3_b != nullptr, "gemm: 3xTF32 needs the two split-operand scratch buffers");
+  GemmDesc h = g;
+  h.x3 = 0;
+  long long lda3 = 0, ldb3 = 0;
+  if (launch_split3(g.A, g.lda, g.a_mn, g.M, g.K, g.x3_a, /*lo parts*/ 0b010, &lda3, stream)) return 1;   // [hi | lo | hi]
+  if (launch_split3(g.B, g.ldb, g.b_mn, g.N, g.K, g.x3_b, /*lo parts*/ 0b100, &ldb3, stream)) return 1;   // [hi | hi | lo]
+  h.A = g.x3_a; h.lda = lda3;
+  h.B = g.x3_b; h.ldb = ldb3;
+  // contraction length: K-major parts are padded to Kp columns, MN-major parts are exactly K rows; mixed majors must agree
+  const int Kp = (g.K + 3) / 4 * 4;
+  MVAE_REQUIRE((g.a_mn && g.b_mn) || (!g.a_mn && !g.b_mn) || Kp == g.K, "gemm: 3xTF32 with mixed operand majors needs K %% 4 == 0");
+  h.K = 3 * ((g.a_mn && g.b_mn) ? g.K : Kp);
+  return launch_gemm_impl(h, stream, false);
+}
 bool gemm_bn_fusable(const GemmDesc& g) { return launch_gemm_impl(g, nullptr, true) == 0; }
 
 // rc 3: g.epi.fuse_bn was requested but the grid cannot be made co-resident (nothing launched; the caller falls back

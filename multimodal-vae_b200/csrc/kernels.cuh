@@ -18,7 +18,7 @@ int launch_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t s
 int launch_u8_to_act(const uint8_t* in, float* o32, void* o16, long long n, float scale, cudaStream_t st);
 int launch_adam(float* p, float* g, float* m, float* v, void* p16, long long n, float lr, float b1, float b2, float eps,
                 const int* step_ptr, float grad_scale, int zero_grad, cudaStream_t st);
-int launch_step_prep(int* step_ptr, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
+int launch_step_prep(int* step_ptr, int* step_ptr2, float* zero_buf, long long zero_n, long long* nbt, const long long (&inc)[6],
                      cudaStream_t st);
 int launch_loss_pack(const float* acc, float* out, int G, cudaStream_t st);
 int launch_sigmoid_backward(int dtype, const void* dprob, const void* prob, void* dlogit, int rows, int F, float* dbias,

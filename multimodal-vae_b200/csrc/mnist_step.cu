@@ -132,9 +132,12 @@ struct Plan {
   long long txt_table, txt_save;
   // activations
   long long h1pre, h1, h2pre, h2, enc, z, t1pre, g1pre, g1, g2pre, g2, dlog, dyt, dy2, dy1, dz, denc, dye2, dye1;
+  long long x3_a = -1, x3_b = -1;                        // 3xTF32 split-operand scratch (MVAE_DT_F32X3 only)
 };
 
-Plan make_plan(int B, int n, int dtype) {
+Plan make_plan(int B, int n, int dtype_code) {
+  const bool x3 = dtype_code == MVAE_DT_F32X3;
+  const int dtype = x3 ? MVAE_F32 : dtype_code;
   Plan p;
   const long long G = kMaxGroups, R = G * B;
   const long long es = dtype == MVAE_F32 ? 4 : 2;
@@ -179,6 +182,12 @@ Plan make_plan(int B, int n, int dtype) {
   p.dz = take(R * n * 4);
   p.denc = take(B * 2 * n * es);
   p.dye2 = take(B * 200 * es); p.dye1 = take(B * 400 * es);
+  if (x3) {
+    // largest split A operand: dlogits [R, 784] (dgrad / wgrad of the last Linear); largest split B operand: g2 [R, 400]
+    const long long b_max = R * 400 > 784ll * B ? R * 400 : 784ll * B;
+    p.x3_a = take(3 * (R + 4) * 784 * 4);
+    p.x3_b = take(3 * ((b_max > 784 * 400 ? b_max : 784 * 400) + 4 * 784) * 4);
+  }
   p.bytes = off;
   return p;
 }
@@ -200,6 +209,20 @@ struct FusedBn {
   int updates = 1; float momentum = 0.1f, eps = 1e-5f;
   unsigned int* barrier = nullptr;
 };
+
+// 3xTF32 mode of the current mvae_mnist_step call (set at its start; the helpers below stamp it on every GEMM)
+struct X3Scratch {
+  void* a = nullptr;
+  void* b = nullptr;
+};
+thread_local X3Scratch g_x3;
+void stamp_x3(GemmDesc& g) {
+  if (g_x3.a != nullptr && g.kind == MVAE_F32) {
+    g.x3 = 1;
+    g.x3_a = g_x3.a;
+    g.x3_b = g_x3.b;
+  }
+}
 
 GemmDesc fwd_desc(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
                   float* st_sum, float* st_sumsq, int rows_per_group, const FusedBn* fb) {
@@ -236,6 +259,7 @@ int gemm_fwd(int dtype, int M, int N, int K, const void* A, const void* W, void*
   g.epi.bias = bias;
   g.epi.stat0 = st_sum; g.epi.stat1 = st_sumsq;
   g.epi.rows_per_group = rows_per_group;
+  stamp_x3(g);
   return launch_gemm(g, st);
 }
 
@@ -257,6 +281,7 @@ int gemm_dgrad(int dtype, int M, int Nin, int Kout, const void* dY, const void* 
   } else {
     g.epi.kind = EPI_STORE;
   }
+  stamp_x3(g);
   return launch_gemm(g, st);
 }
 
@@ -268,6 +293,7 @@ int gemm_wgrad(int dtype, int rows, int Nout, int Kin, const void* dY, const voi
   g.B = X; g.ldb = Kin; g.b_mn = 1;
   g.epi.kind = EPI_ATOMIC;
   g.epi.C = dW; g.epi.ldc = Kin; g.epi.c_dtype = MVAE_F32;
+  stamp_x3(g);
   return launch_gemm(g, st);
 }
 
@@ -365,7 +391,7 @@ int mvae_mnist_tensor_info(int n_latents, int index, mvae_tensor_info* out) {
 int mvae_mnist_sizes(int n_latents, int batch, int dtype, mvae_mnist_size_info* out) {
   MVAE_REQUIRE(n_latents > 0 && n_latents % 4 == 0, "n_latents=%d must be a positive multiple of 4", n_latents);
   MVAE_REQUIRE(batch > 1, "batch=%d must be > 1 (train-mode BatchNorm)", batch);
-  MVAE_REQUIRE(dtype == MVAE_DT_F32 || dtype == MVAE_DT_BF16, "bad dtype %d", dtype);
+  MVAE_REQUIRE(dtype == MVAE_DT_F32 || dtype == MVAE_DT_BF16 || dtype == MVAE_DT_F32X3, "bad dtype %d", dtype);
   const Layout L = make_layout(n_latents);
   const Plan p = make_plan(batch, n_latents, dtype);
   out->param_floats = L.param_floats;
@@ -381,18 +407,19 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   static const int debug_sync = env_int("MVAE_DEBUG_SYNC", 0);
   static const int use_side = env_int("MVAE_SIDE_STREAM", 1);
   MVAE_REQUIRE(a != nullptr, "mnist_step: null args");
-  SideStream* ss = (use_side && !debug_sync && !g_prof.on) ? side_stream_for_current_device() : nullptr;
+  const bool x3 = a->dtype == MVAE_DT_F32X3;  // fp32 storage, error-compensated 3xTF32 GEMMs (shared split scratch: one stream)
+  SideStream* ss = (use_side && !debug_sync && !g_prof.on && !x3) ? side_stream_for_current_device() : nullptr;
   cudaStream_t s2 = ss != nullptr ? ss->s : st;  // side stream (or the main one when disabled)
   auto dep = [&](cudaStream_t from, cudaStream_t to) -> int { return (ss != nullptr && from != to) ? stream_dep(ss, from, to) : 0; };
-  const int B = a->batch, n = a->n_latents, dt = a->dtype, G = a->n_terms;
+  const int B = a->batch, n = a->n_latents, dt = x3 ? MVAE_DT_F32 : a->dtype, G = a->n_terms;
   MVAE_REQUIRE(n > 0 && n % 4 == 0, "n_latents=%d must be a positive multiple of 4", n);
   MVAE_REQUIRE(B > 1, "batch=%d must be > 1", B);
-  MVAE_REQUIRE(dt == MVAE_DT_F32 || dt == MVAE_DT_BF16, "bad dtype %d", dt);
+  MVAE_REQUIRE(a->dtype == MVAE_DT_F32 || a->dtype == MVAE_DT_BF16 || x3, "bad dtype %d", a->dtype);
   MVAE_REQUIRE(G >= 1 && G <= kMaxGroups, "n_terms=%d out of range", G);
   MVAE_REQUIRE(a->params && a->workspace && a->buffers, "mnist_step: params / buffers / workspace missing");
   MVAE_REQUIRE(dt == MVAE_DT_F32 || a->params_bf16 != nullptr, "mnist_step: bf16 path needs the bf16 parameter mirror");
   const Layout L = make_layout(n);
-  const Plan P = make_plan(B, n, dt);
+  const Plan P = make_plan(B, n, a->dtype);
   MVAE_REQUIRE(a->workspace_bytes >= P.bytes, "workspace too small: %lld < %lld", (long long)a->workspace_bytes, P.bytes);
   MVAE_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "workspace must be 256-byte aligned");
   int n_img = 0, n_txt = 0;
@@ -421,6 +448,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (decode_only) n_img = n_txt = 0;  // latents are given: no encoders, no PoE
 
   const Ptrs W{static_cast<char*>(a->workspace)};
+  g_x3.a = x3 ? W.at<void>(P.x3_a) : nullptr;
+  g_x3.b = x3 ? W.at<void>(P.x3_b) : nullptr;
   float* prm = a->params;
   // GEMM weight operands: fp32 master (tf32 path) or the bf16 mirror (same offsets)
   auto wop = [&](const char* name) -> const void* {
@@ -438,7 +467,12 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     // BN order in the layout: ie.1, ie.4, id.1, id.4, te.1, td.1
     const long long t_ = training ? 1 : 0;
     const long long inc[6] = {t_ * n_img, t_ * n_img, t_ * G, t_ * G, t_ * n_txt, t_ * G};
-    if (fwd) MVAE_STEP(launch_step_prep(a->adam_step, W.at<float>(P.acc_off), P.acc_floats,
+    // two device clocks: the noise counter ticks on every forward-type call (Philox stream), Adam's bias-correction
+    // clock only on calls that open an optimizer step (do_adam, or advance_adam_step for split / accumulated steps)
+    int* adam_tick = (a->do_adam || a->advance_adam_step) ? a->adam_step : nullptr;
+    int* noise_tick = a->noise_step;
+    if (a->noise_step == nullptr && adam_tick == nullptr) noise_tick = a->adam_step;  // legacy callers: one shared clock
+    if (fwd) MVAE_STEP(launch_step_prep(adam_tick, noise_tick, W.at<float>(P.acc_off), P.acc_floats,
                                         reinterpret_cast<long long*>(a->num_batches_tracked), inc, st), "launch_step_prep");
   }
   if (fwd && bwd && a->zero_grad)
@@ -539,7 +573,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   ta.enc_img = n_img > 0 ? W.at<float>(P.enc) : nullptr;
   ta.txt_table = n_txt > 0 ? W.at<float>(P.txt_table) : nullptr;
   ta.labels = reinterpret_cast<const long long*>(a->text);
-  ta.eps = a->eps; ta.seed = a->seed; ta.step_ptr = a->adam_step; ta.training = training ? 1 : 0;
+  ta.eps = a->eps; ta.seed = a->seed; ta.step_ptr = a->noise_step != nullptr ? a->noise_step : a->adam_step; ta.training = training ? 1 : 0;
   ta.z_in = a->z_in;
   ta.wt1 = pf("text_decoder.net.0.weight"); ta.bt1 = pf("text_decoder.net.0.bias");
   ta.z = W.at<void>(P.z); ta.mu = a->out_mu; ta.logvar = a->out_logvar;
@@ -620,6 +654,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     for (int t = 0; t < G; ++t) g.epi.bce_scale[t] = a->lambda_image[t] / (static_cast<float>(B) * 784.f);
     g.epi.loss = losses;
     g.epi.probs = a->out_recon_image;
+    stamp_x3(g);
     if (fwd) MVAE_STEP(launch_gemm(g, st), "gemm_fwd_bce:image_decoder.net.6.weight");
   }
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist

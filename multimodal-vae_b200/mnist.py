@@ -18,7 +18,8 @@ import torch.nn as nn
 from . import _lib
 
 TERMS = {"joint": _lib.TERM_JOINT, "image": _lib.TERM_IMAGE, "text": _lib.TERM_TEXT}
-_DTYPES = {"tf32": _lib.DT_F32, "fp32": _lib.DT_F32, "bf16": _lib.DT_BF16}
+# "tf32x3": fp32 storage with error-compensated 3xTF32 GEMMs (hi/lo operand split) - fp32-grade parity mode
+_DTYPES = {"tf32": _lib.DT_F32, "fp32": _lib.DT_F32, "bf16": _lib.DT_BF16, "tf32x3": _lib.DT_F32X3}
 
 
 def _stream_ptr() -> C.c_void_p:
@@ -61,7 +62,8 @@ class MVAE(nn.Module):
     """Drop-in for the reference's MultimodalVAE (mnist/model.py:14-96).
 
     All parameters are views into one flat fp32 device buffer (`flat_params`), gradients into `flat_grads`.
-    `precision`: "tf32" (fp32 storage, tensor cores in tf32; the parity path) or "bf16".
+    `precision`: "tf32" (fp32 storage, tensor cores in tf32), "tf32x3" (fp32 storage, error-compensated
+    3xTF32 GEMMs: the parity mode that meets rtol 1e-3 on every gradient) or "bf16" (the fast path).
     """
 
     def __init__(self, n_latents: int = 20, precision: str = "tf32", device: Optional[torch.device] = None,
@@ -115,7 +117,11 @@ class MVAE(nn.Module):
         self.reset_parameters()
         self._ws: Dict[Tuple[int, int], torch.Tensor] = {}
         self._injected_noise = []
-        self._step_counter = torch.zeros(1, device=dev, dtype=torch.int32)
+        # two device clocks (so that CUDA graphs stay valid): [0] the Philox / noise counter, ticked by every forward-type
+        # call; [1] Adam's bias-correction step, ticked only by optimizer steps (checkpointed as "step")
+        self._counters = torch.zeros(2, device=dev, dtype=torch.int32)
+        self._step_counter = self._counters[0:1]
+        self._adam_counter = self._counters[1:2]
 
     # ------------------------------------------------------------------ parameters
     @torch.no_grad()
@@ -176,7 +182,7 @@ class MVAE(nn.Module):
         return self.workspace(batch)[off:off + nbytes].view(dtype).view(shape)
 
     def act_dtype(self) -> torch.dtype:
-        return torch.float32 if self.dtype_code == _lib.DT_F32 else torch.bfloat16
+        return torch.bfloat16 if self.dtype_code == _lib.DT_BF16 else torch.float32
 
     def to_act(self, image: torch.Tensor) -> torch.Tensor:
         """image.view(-1, 784) in the storage dtype of the tensor-core path (mnist/train.py:131)."""
@@ -184,7 +190,7 @@ class MVAE(nn.Module):
         if x.dtype == torch.uint8:
             out = torch.empty(x.shape, device=self.device_, dtype=self.act_dtype())
             xd = x.to(self.device_, non_blocking=True).contiguous()
-            f32 = out.data_ptr() if self.dtype_code == _lib.DT_F32 else None
+            f32 = out.data_ptr() if self.dtype_code != _lib.DT_BF16 else None
             b16 = out.data_ptr() if self.dtype_code == _lib.DT_BF16 else None
             _lib.check(_lib.load().mvae_u8_to_act(C.c_void_p(xd.data_ptr()), C.c_void_p(f32), C.c_void_p(b16),
                                                   C.c_int64(xd.numel()), C.c_float(1.0 / 255.0), _stream_ptr()),
@@ -227,7 +233,8 @@ class MVAE(nn.Module):
         a.num_batches_tracked = self.flat_nbt.data_ptr()
         a.grads = (self.flat_grads if grads is None else grads).data_ptr()
         a.do_backward, a.zero_grad = int(backward), int(zero_grad)
-        a.adam_step = self._step_counter.data_ptr()
+        a.adam_step = self._adam_counter.data_ptr()
+        a.noise_step = self._step_counter.data_ptr()
         a.grad_scale = float(grad_scale)
         if adam is not None:
             a.do_adam = 1
@@ -292,6 +299,7 @@ class MVAE(nn.Module):
         `loss_function`, `.backward()`, any torch optimizer) works unchanged.  eval(): running statistics, z = mu.
         The fast path for training is MVAETrainer.step, which fuses the three terms."""
         term, B, x, y = self._prep_inputs(image, text)
+        self.sync_low_precision()   # the parameters may have been stepped by a torch optimizer (bf16 GEMMs read the mirror)
         if not self.training:
             with torch.no_grad():
                 _, outs = self._run(x, y, [term], [(0.0, 0.0)], [0.0], outputs=True, extra={"eval_mode": 1})
@@ -312,6 +320,7 @@ class MVAE(nn.Module):
     def encode_image(self, x):
         """ImageEncoder (mnist/model.py:99-117): (mu, logvar) of the image expert."""
         _, B, xa, y = self._prep_inputs(x, None)
+        self.sync_low_precision()
         self._run(xa, y, [TERMS["image"]], [(0.0, 0.0)], [0.0], extra={"eval_mode": int(not self.training)})
         enc = self.debug_buffer("enc", B, (B, 2 * self.n_latents), torch.float32).clone()
         return enc[:, :self.n_latents], enc[:, self.n_latents:]
@@ -320,6 +329,7 @@ class MVAE(nn.Module):
     def encode_text(self, x):
         """TextEncoder (mnist/model.py:138-153): (mu, logvar) of the text expert."""
         _, B, xa, y = self._prep_inputs(None, x)
+        self.sync_low_precision()
         self._run(xa, y, [TERMS["text"]], [(0.0, 0.0)], [0.0], extra={"eval_mode": int(not self.training)})
         table = self.debug_buffer("txt_table", B, (10, 2 * self.n_latents), torch.float32).clone()
         out = table[y]
@@ -331,6 +341,7 @@ class MVAE(nn.Module):
         B = z.shape[0]
         x = torch.zeros(B, 784, device=self.device_, dtype=self.act_dtype())
         y = torch.zeros(B, device=self.device_, dtype=torch.int64)
+        self.sync_low_precision()
         _, outs = self._run(x, y, [TERMS["joint"]], [(0.0, 0.0)], [0.0], outputs=True,
                             extra={"eval_mode": int(not self.training), "z_in": z.data_ptr()})
         return outs[0], outs[1]
@@ -344,6 +355,7 @@ class MVAE(nn.Module):
         _, B, x, y = self._prep_inputs(image, text)
         z = z.to(self.device_, torch.float32).contiguous()
         self._keep_z = z
+        self.sync_low_precision()
         losses, _ = self._run(x, y, [TERMS["joint"]], [(1.0, 1.0)], [0.0],
                               extra={"eval_mode": int(not self.training), "z_in": z.data_ptr()})
         return losses[0, 1:3]
@@ -495,27 +507,47 @@ class MVAETrainer:
             if eps is not None:
                 e = torch.stack([eps[term_index[t]].index_select(0, idx) for t in terms]).contiguous()
             tt, klw = self._norm(terms, int(idx.numel()), annealing_factor)
-            # a distinct Philox stream per class: the device step counter is rewound below
+            # a distinct Philox stream per class; Adam's clock ticks once, with the first class that runs
             losses, _ = m._run(x.index_select(0, idx), y.index_select(0, idx), tt, lambdas, klw, eps=e, backward=True,
                                zero_grad=first, adam=None, grad_scale=self.grad_scale, workspace=ws,
-                               extra={"seed": (m.noise_seed + 0x9E3779B1 * (j + 1)) & 0x7FFFFFFFFFFFFFFF})
+                               extra={"seed": (m.noise_seed + 0x9E3779B1 * (j + 1)) & 0x7FFFFFFFFFFFFFFF,
+                                      "advance_adam_step": int(update and first)})
             out[name] = losses
             first = False
             ran += 1
-        if ran > 1:
-            m._step_counter.sub_(ran - 1)  # one optimizer step = one tick of Adam's bias-correction clock
+        self._reduce_gradients()
         if update and ran > 0:
             from . import _ops
             a = self.adam
             _ops.adam_step(m.flat_params, m.flat_grads, a["m"], a["v"], m.flat_params_bf16, m.flat_params.numel(), a["lr"],
-                           a["betas"][0], a["betas"][1], a["eps"], m._step_counter, self.grad_scale, zero_grad=False)
+                           a["betas"][0], a["betas"][1], a["eps"], m._adam_counter, self.grad_scale, zero_grad=False)
         return out
+
+    def _reduce_gradients(self) -> None:
+        """Hook between the backward of an accumulated step and its Adam update (data parallel: the all-reduce)."""
+
+    _MAX_GRAPHS = 16   # captured graphs kept per trainer (least recently used are dropped: each owns static buffers)
+
+    def _graph_cache_get(self, cache, key):
+        ent = cache.get(key)
+        if ent is not None:
+            cache[key] = cache.pop(key)   # move to the end: most recently used
+        return ent
+
+    def _graph_cache_put(self, cache, key, ent):
+        cache[key] = ent
+        while len(cache) > self._MAX_GRAPHS:
+            cache.pop(next(iter(cache)))
 
     def _graph_step(self, x, y, eps, terms, lambdas, annealing_factor, update, zero_grad):
         """Replay of the step as one CUDA graph (static input buffers; one graph per configuration)."""
         m = self.model
-        key = (x.shape[0], terms, lambdas, float(annealing_factor), bool(update), bool(zero_grad), eps is not None)
-        ent = self._graphs.get(key)
+        # every scalar that capture bakes into kernel arguments is part of the key (Adam hyper-parameters included:
+        # adjust_learning_rate / annealing schedules mutate them between steps); the cache is bounded (LRU)
+        a_ = self.adam
+        key = (x.shape[0], terms, lambdas, float(annealing_factor), bool(update), bool(zero_grad), eps is not None,
+               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), float(self.grad_scale))
+        ent = self._graph_cache_get(self._graphs, key)
         if ent is None:
             sx, sy = torch.empty_like(x), torch.empty_like(y)
             se = torch.empty_like(eps) if eps is not None else None
@@ -537,7 +569,7 @@ class MVAETrainer:
                 m._run(sx, sy, tt, lambdas, klw, **kw)
             ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses,
                    "launches": int(lib.mvae_launch_count() - before)}
-            self._graphs[key] = ent
+            self._graph_cache_put(self._graphs, key, ent)
         else:
             ent["x"].copy_(x, non_blocking=True)
             ent["y"].copy_(y, non_blocking=True)

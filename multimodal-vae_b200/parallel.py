@@ -62,6 +62,10 @@ class DataParallelTrainer(MVAETrainer):
         super().__init__(model, lr=lr, betas=betas, eps=eps, use_cuda_graph=False)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.grad_scale = 1.0 / self.world      # step_masked's Adam: gradients are summed over the ranks first
+        # every replica must draw its own reparametrisation noise: fold the rank into the Philox key
+        model.noise_seed = (int(model.noise_seed) + 0x51ED27 * self.rank) & 0x7FFFFFFFFFFFFFFF
         self.dp_graph = use_cuda_graph
         self._dp_graphs = {}
         self.overlap = overlap
@@ -80,7 +84,7 @@ class DataParallelTrainer(MVAETrainer):
         main = torch.cuda.current_stream(m.device_)
         if self.overlap and self.world > 1:
             out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses,
-                            extra={"phase": 3})
+                            extra={"phase": 3, "advance_adam_step": 1})
             self.comm_stream.wait_stream(main)
             with torch.cuda.stream(self.comm_stream):
                 allreduce_flat_(m.flat_grads[split:], self.group)
@@ -89,7 +93,8 @@ class DataParallelTrainer(MVAETrainer):
             allreduce_flat_(m.flat_grads[:split], self.group)
             main.wait_stream(self.comm_stream)
         else:
-            out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses)
+            out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses,
+                            extra={"advance_adam_step": 1})
             allreduce_flat_(m.flat_grads, self.group)
         a = self.adam
         _lib.check(_lib.load().mvae_adam_step(
@@ -97,12 +102,20 @@ class DataParallelTrainer(MVAETrainer):
             C.c_void_p(a["v"].data_ptr()),
             C.c_void_p(None if m.flat_params_bf16 is None else m.flat_params_bf16.data_ptr()),
             C.c_int64(m.flat_params.numel()), C.c_float(a["lr"]), C.c_float(a["betas"][0]), C.c_float(a["betas"][1]),
-            C.c_float(a["eps"]), C.c_void_p(m._step_counter.data_ptr()), C.c_float(1.0 / self.world), C.c_int(0),
+            C.c_float(a["eps"]), C.c_void_p(m._adam_counter.data_ptr()), C.c_float(1.0 / self.world), C.c_int(0),
             _stream_ptr()), "mvae_adam_step")
         return out
 
+    def _reduce_gradients(self) -> None:
+        """step_masked (inherited): the per-class backward passes accumulate locally, then the flat gradient buffer is
+        summed over the ranks before the one Adam update (grad_scale = 1/world)."""
+        allreduce_flat_(self.model.flat_grads, self.group)
+
     def step(self, image, text, eps=None, terms=("joint", "image", "text"), lambdas=((1.0, 1.0),) * 3,
              annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True):
+        if not update or not zero_grad or outputs:
+            raise NotImplementedError("DataParallelTrainer.step always zeroes the gradients, all-reduces and applies Adam; "
+                                      "update=False / zero_grad=False / outputs=True are not supported (use MVAETrainer)")
         m = self.model
         x = m.to_act(image)
         y = text.to(m.device_, non_blocking=True).long().contiguous()
@@ -110,8 +123,10 @@ class DataParallelTrainer(MVAETrainer):
             eps = eps.to(m.device_, torch.float32).contiguous()
         if not self.dp_graph:
             return self._local_then_reduce(x, y, eps, terms, lambdas, annealing_factor), None
-        key = (x.shape[0], tuple(terms), tuple(map(tuple, lambdas)), float(annealing_factor), eps is not None)
-        ent = self._dp_graphs.get(key)
+        a_ = self.adam
+        key = (x.shape[0], tuple(terms), tuple(map(tuple, lambdas)), float(annealing_factor), eps is not None,
+               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]))
+        ent = self._graph_cache_get(self._dp_graphs, key)
         if ent is None:
             sx, sy = x.clone(), y.clone()
             se = eps.clone() if eps is not None else None
@@ -127,7 +142,7 @@ class DataParallelTrainer(MVAETrainer):
                 self._local_then_reduce(sx, sy, se, terms, lambdas, annealing_factor, losses=losses)
             ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses,
                    "launches": int(lib.mvae_launch_count() - before)}
-            self._dp_graphs[key] = ent
+            self._graph_cache_put(self._dp_graphs, key, ent)
         else:
             ent["x"].copy_(x, non_blocking=True)
             ent["y"].copy_(y, non_blocking=True)

@@ -297,6 +297,13 @@ def reparametrize(mu, logvar, noise=None, training=True):
     return noise * std + mu
 
 
+# PoE arithmetic used by forward(): None = the reference's (mnist/model.py:180-185, variance-weighted mu, no prior);
+# ("precision", prior) = the paper's precision-weighted product with an optional N(0,1) prior expert - the
+# north-star variant.  The reference does not implement it ("parity unpinned": pinned only to the formula of
+# paper/draft.tex:88 restated in product_of_experts_precision).
+POE_VARIANT = None
+
+
 def forward(p: State, image=None, text=None, noise=None, st=None, training=True):
     """MultimodalVAE.forward, mnist/model.py:53-84.  Returns (recon_image probs, recon_text
     log-probs, mu, logvar) like the reference, plus the decoder logits."""
@@ -308,7 +315,10 @@ def forward(p: State, image=None, text=None, noise=None, st=None, training=True)
     if text is not None:
         m, l = text_encoder(p, text, st, training)
         mus.append(m); lvs.append(l)
-    mu, logvar = product_of_experts(torch.stack(mus, 0), torch.stack(lvs, 0))
+    if POE_VARIANT is None:
+        mu, logvar = product_of_experts(torch.stack(mus, 0), torch.stack(lvs, 0))
+    else:
+        mu, logvar = product_of_experts_precision(torch.stack(mus, 0), torch.stack(lvs, 0), prior=bool(POE_VARIANT[1]))
     z = _override(reparametrize(mu, logvar, noise, training), "z")
     img_logits = image_decoder_logits(p, z, st, training)
     txt_logits = text_decoder_logits(p, z, st, training)

@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in sorted(names):
         assert hasattr(lib, n), n
-    assert lib.mvae_abi_version() == 3
+    m = re.search(r"#define MVAE_ABI_VERSION (\d+)", hdr)
+    assert lib.mvae_abi_version() == int(m.group(1))
 
 
 def test_layout_matches_reference_state_dict():

@@ -271,7 +271,7 @@ def test_masked_step_mixes_paired_and_unpaired_rows():
         tr = mvae_b200.MVAETrainer(m)
         out = tr.step_masked(image.cuda(), text.cuda(), has_image, has_text, eps=torch.stack(noises).cuda(), update=update)
         torch.cuda.synchronize()
-        assert int(m._step_counter) == 1
+        assert int(m._adam_counter) == (1 if update else 0)   # Adam's clock ticks once per optimizer step only
         for name, ref in zip(("paired", "image_only", "text_only"), ref_losses):
             np.testing.assert_allclose(out[name][:, 0].cpu().numpy(), ref, rtol=3e-5)
         sd = m.state_dict()
@@ -318,4 +318,205 @@ def test_masked_step_mixes_paired_and_unpaired_rows():
         assert np.isfinite(tot)
         first = tot if first is None else first
         last = tot
-    assert int(m3._step_counter) == 30 and last < first
+    assert int(m3._adam_counter) == 30 and last < first
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Round 2: parity at the north-star tolerance and at the benchmarked configuration
+
+@pytest.mark.parametrize("B,n,seed", [(100, 64, 0), (130, 24, 5), (512, 64, 1), (4096, 64, 2)])
+def test_tf32x3_step_meets_rtol_1e3_against_the_fp32_oracle(B, n, seed):
+    """north_star: "per-tensor outputs and gradients within rtol 1e-3 for the TF32 path".  precision="tf32x3" splits every
+    GEMM operand into hi = tf32(x) and lo = x - hi and accumulates hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator, so
+    the forward differs from fp32 by ~1e-6 and no ReLU unit flips: EVERY output and EVERY gradient tensor must agree with
+    the exact-fp32 oracle (the restated reference) to relative L2 <= 1e-3 - mu / logvar included; B = 4096, n = 64 is the
+    benchmarked configuration."""
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m, _, dl, outs = run_device_step(state, image, text, noises, n, "tf32x3")
+    losses, grads, bufs, o_outs = oracle_step(state, image, text, noises)
+    np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=1e-5)
+    ri, rt, mu, lv = outs
+    for g in range(3):
+        o = o_outs[g]
+        assert rel_l2(ri[g * B:(g + 1) * B].float(), o[0]) < 1e-3
+        assert rel_l2(rt[g * B:(g + 1) * B], o[1]) < 1e-3
+        assert rel_l2(mu[g], o[2]) < 1e-3
+        assert rel_l2(lv[g], o[3]) < 1e-3
+    worst = 0.0
+    for name, p in m.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            assert float(p.grad.abs().max()) < 1e-6, name
+            continue
+        err = rel_l2(p.grad, grads[name])
+        worst = max(worst, err)
+        assert err < 1e-3, (name, err)
+    sd = m.state_dict()
+    for k, v in bufs.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=1e-4, atol=1e-5, err_msg=k)
+    print("tf32x3 B=%d n=%d: worst gradient rel-L2 %.2e" % (B, n, worst))
+
+
+@pytest.mark.parametrize("name", ["mnist_b24_n8", "mnist_b100_n64", "mnist_b32_n20_weak"])
+def test_tf32x3_step_matches_reference_golden_at_1e3(name):
+    """The same bound straight against the fixtures written by the REAL reference (oracle/gen_golden.py)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    B, n, seed = int(g["batch"]), int(g["n_latents"]), int(g["seed"])
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    mask = [bool(x) for x in g["terms"]]
+    terms = tuple(NAMES[i] for i in range(3) if mask[i])
+    lambdas = tuple(tuple(float(x) for x in g["lambdas"][i]) for i in range(3) if mask[i])
+    m, _, dl, outs = run_device_step(state, image, text, noises, n, "tf32x3", terms, lambdas)
+    ref_losses = [g["losses"][i] for i in range(3) if mask[i]]
+    np.testing.assert_allclose(dl[:, 0].numpy(), ref_losses, rtol=1e-5)
+    for pname, p in m.named_parameters():
+        if pname in O.PRE_BN_BIASES:
+            continue
+        ref_s = g["gradsample/" + pname]
+        if np.linalg.norm(ref_s) == 0.0:
+            continue
+        got_s = O.sample_flat(p.grad.cpu()).numpy()
+        err = np.linalg.norm(got_s - ref_s) / (np.linalg.norm(ref_s) + 1e-30)
+        assert err < 1e-3, (pname, err)
+        assert abs(float(p.grad.double().norm()) - float(g["gradnorm/" + pname])) <= 1e-3 * float(g["gradnorm/" + pname]) + 1e-9
+
+
+@pytest.mark.parametrize("precision,ltol,gtol,logic", [("tf32", 2e-5, 6e-2, 1.5e-3), ("bf16", 3e-4, 0.2, 8e-2)])
+def test_benchmarked_configuration_matches_oracle(precision, ltol, gtol, logic):
+    """B = 4096, n = 64 - the configuration bench.py times (BASELINE.json configs[1]) with its own tile plans (split-K
+    weight gradients, multi-wave grids, and for bf16 the slab-persistent chain kernels) against the oracle."""
+    B, n, seed = 4096, 64, 7
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    m, _, dl, outs = run_device_step(state, image, text, noises, n, precision)
+    losses, grads, bufs, o_outs = oracle_step(state, image, text, noises)
+    emu = "tf32" if precision == "tf32" else "bf16"
+    _, grads_g, _, _ = oracle_step(state, image, text, noises, emulate=emu, override=device_forward_override(m, B, text))
+    np.testing.assert_allclose(dl[:, 0].numpy(), losses, rtol=ltol)
+    ri, rt, mu, lv = outs
+    otol = 2e-3 if precision == "tf32" else 2e-2
+    for g in range(3):
+        o = o_outs[g]
+        assert rel_l2(ri[g * B:(g + 1) * B].float(), o[0]) < otol
+        assert rel_l2(rt[g * B:(g + 1) * B], o[1]) < otol
+        assert rel_l2(mu[g], o[2]) < otol
+        assert rel_l2(lv[g], o[3]) < otol
+    for name, p in m.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            continue
+        assert rel_l2(p.grad, grads_g[name]) < logic, ("logic", name, rel_l2(p.grad, grads_g[name]))
+        assert rel_l2(p.grad, grads[name]) < gtol, ("precision", name, rel_l2(p.grad, grads[name]))
+    sd = m.state_dict()
+    for k, v in bufs.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=2e-2 if precision == "bf16" else 2e-3,
+                                       atol=2e-3 if precision == "bf16" else 2e-4, err_msg=k)
+
+
+def test_in_kernel_philox_noise_is_standard_normal_and_independent():
+    """Production and bench.py draw the reparametrisation noise in-kernel (Philox4x32-10 + Box-Muller, csrc/poe.cuh).
+    Recover eps = (z - mu) / exp(logvar / 2) of a step and check: mean 0, variance 1, skewness 0, kurtosis 3 (each within
+    5 standard errors for N = 3 * 4096 * 64 draws), no correlation between the three terms' draws, between neighbouring
+    latent columns, or between consecutive steps (the device noise counter ticks), and the same (seed, step) reproduces."""
+    import mvae_b200
+    B, n = 4096, 64
+    state = O.perturbed_state(n, 3)
+    image, text, _ = O.synthetic_batch(B, n, 3)
+
+    def draw(model, tr):
+        _, outs = tr.step(image.cuda(), text.cuda(), eps=None, update=False, outputs=True)
+        torch.cuda.synchronize()
+        _, _, mu, lv = outs
+        z = model.debug_buffer("z", B, (3, B, n)).double()
+        return ((z - mu.double()) / torch.exp(0.5 * lv.double())).cpu()
+
+    m = mvae_b200.MVAE(n, precision="tf32", seed=77)
+    m.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m)
+    e1 = draw(m, tr)
+    e2 = draw(m, tr)
+    N = e1.numel()
+    x = e1.reshape(-1)
+    assert abs(float(x.mean())) < 5.0 / N ** 0.5
+    assert abs(float(x.var()) - 1.0) < 5.0 * (2.0 / N) ** 0.5
+    assert abs(float((x ** 3).mean())) < 5.0 * (15.0 / N) ** 0.5
+    assert abs(float((x ** 4).mean()) - 3.0) < 5.0 * (96.0 / N) ** 0.5
+    assert float(x.abs().max()) < 6.5 and float(x.abs().max()) > 4.0      # tails exist but nothing absurd
+
+    def corr(a, b):
+        a, b = a.reshape(-1), b.reshape(-1)
+        return abs(float(((a - a.mean()) * (b - b.mean())).mean() / (a.std() * b.std())))
+
+    lim = 5.0 / (B * n) ** 0.5
+    assert corr(e1[0], e1[1]) < lim and corr(e1[0], e1[2]) < lim and corr(e1[1], e1[2]) < lim   # across ELBO terms
+    assert corr(e1[:, :, :-1], e1[:, :, 1:]) < lim                                                # neighbouring latents
+    assert corr(e1[:, :-1], e1[:, 1:]) < lim                                                      # neighbouring samples
+    assert corr(e1, e2) < lim                                                                     # consecutive steps
+    m2 = mvae_b200.MVAE(n, precision="tf32", seed=77)
+    m2.load_state_dict(state)
+    e1b = draw(m2, mvae_b200.MVAETrainer(m2))
+    assert float((e1 - e1b).abs().max()) < 1e-4                                                   # same (seed, step)
+    m3 = mvae_b200.MVAE(n, precision="tf32", seed=78)
+    m3.load_state_dict(state)
+    assert corr(e1, draw(m3, mvae_b200.MVAETrainer(m3))) < lim                                     # another seed
+
+
+@pytest.mark.parametrize("prior", [False, True])
+def test_fused_step_in_precision_poe_mode(prior):
+    """north_star: "ProductOfExperts fusion with the prior expert" inside the fused step.  poe_mode="precision" is not the
+    reference's arithmetic - the oracle restates the paper's formula - but the FUSED path (tail kernels,
+    all three terms, backward) must implement it exactly: losses to 2e-5, every gradient to rtol 1e-3 in tf32x3."""
+    import mvae_b200
+    B, n, seed = 256, 32, 12
+    state = O.perturbed_state(n, seed)
+    image, text, noises = O.synthetic_batch(B, n, seed)
+    O.POE_VARIANT = ("precision", prior)
+    try:
+        losses, grads, _, o_outs = oracle_step(state, image, text, noises)
+    finally:
+        O.POE_VARIANT = None
+    m = mvae_b200.MVAE(n, precision="tf32x3", poe_mode="precision", prior_expert=prior)
+    m.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m)
+    dl, outs = tr.step(image.cuda(), text.cuda(), eps=torch.stack(noises).cuda(), update=False, outputs=True)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(dl[:, 0].cpu().numpy(), losses, rtol=2e-5)
+    for g in range(3):
+        assert rel_l2(outs[2][g], o_outs[g][2]) < 1e-3 and rel_l2(outs[3][g], o_outs[g][3]) < 1e-3
+    for name, p in m.named_parameters():
+        if name in O.PRE_BN_BIASES:
+            continue
+        assert rel_l2(p.grad, grads[name]) < 1e-3, (name, rel_l2(p.grad, grads[name]))
+    # and it is a different function from the reference's product: the joint-term loss must differ
+    ref_losses, _, _, _ = oracle_step(state, image, text, noises)
+    assert abs(ref_losses[0] - losses[0]) > 1e-4 * abs(ref_losses[0])
+
+
+def test_eval_and_forward_calls_do_not_advance_adams_clock():
+    """only optimizer steps tick Adam's bias-correction clock; forward-only calls tick the noise counter."""
+    import mvae_b200
+    B, n = 64, 16
+    state = O.perturbed_state(n, 1)
+    image, text, noises = O.synthetic_batch(B, n, 1)
+    m = mvae_b200.MVAE(n, precision="tf32")
+    m.load_state_dict(state)
+    tr = mvae_b200.MVAETrainer(m)
+    tr.step(image.cuda(), text.cuda())
+    m.eval()
+    for _ in range(5):
+        m(image.cuda(), text.cuda())
+        m.encode_image(image.cuda())
+    m.train()
+    with torch.no_grad():
+        m(image.cuda(), text.cuda())
+    tr.step(image.cuda(), text.cuda(), update=False)
+    tr.step(image.cuda(), text.cuda())
+    torch.cuda.synchronize()
+    assert int(m._adam_counter) == 2
+    assert int(m._step_counter) == 2 + 10 + 1 + 1

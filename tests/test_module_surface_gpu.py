@@ -122,6 +122,56 @@ def test_reference_training_loop_with_autograd():
     optimizer.step()
 
 
+def test_reference_training_loop_bf16_sees_the_optimizer_update():
+    """in bf16 the GEMMs read a bf16 mirror of the parameters; the module surface must refresh it after a
+    torch optimizer stepped the fp32 master - the loss of the reference loop has to move from step to step."""
+    import mvae_b200
+    B, n = 128, 16
+    state = O.perturbed_state(n, 4)
+    image, text, _ = O.synthetic_batch(B, n, 4)
+    vae = mvae_b200.MultimodalVAE(n_latents=n, precision="bf16")
+    vae.load_state_dict(state)
+    vae.train()
+    optimizer = torch.optim.Adam(vae.parameters(), lr=1e-2)
+    img_d, txt_d = image.cuda(), text.cuda()
+    g = torch.Generator().manual_seed(0)
+    fixed = [torch.randn(B, n, generator=g) for _ in range(3)]
+    curve = []
+    for it in range(6):
+        vae._injected_noise = [x.clone() for x in fixed]
+        optimizer.zero_grad()
+        r1, r2, r3 = vae(img_d, txt_d), vae(image=img_d), vae(text=txt_d)
+        loss = sum(mvae_b200.loss_function(r[2], r[3], recon_image=r[0], image=img_d, recon_text=r[1], text=txt_d)
+                   for r in (r1, r2, r3))
+        loss.backward()
+        optimizer.step()
+        curve.append(float(loss))
+    assert curve[-1] < curve[0] - 1e-3, curve          # the weights the GEMMs see really move
+    assert len(set(round(c, 6) for c in curve)) == len(curve), curve
+    vae.eval()
+    before = vae(img_d, txt_d)[0].float().clone()
+    with torch.no_grad():
+        for p in vae.parameters():
+            p.mul_(1.05)
+    after = vae(img_d, txt_d)[0].float()
+    assert float((before - after).abs().max()) > 1e-3   # eval forward also sees edited parameters
+
+
+def test_load_checkpoint_default_handles_reference_n_latents(tmp_path):
+    """the reference's stock checkpoint has n_latents = 20 (mnist/train.py:54,87); load_checkpoint(path) must
+    load it with its defaults (and an explicit bf16 request falls back to tf32 for it)."""
+    from mvae_b200 import checkpoint
+    state = O.init_state(20, seed=5)
+    path = str(tmp_path / "ck")
+    checkpoint.save_checkpoint({"state_dict": state, "n_latents": 20}, False, folder=path)
+    for kw in ({}, {"precision": "bf16"}):
+        vae = checkpoint.load_checkpoint(path + "/checkpoint.pth.tar", **kw)
+        assert vae.n_latents == 20 and vae.precision == "tf32"
+        sd = vae.state_dict()
+        for k, v in state.items():
+            assert torch.equal(sd[k].cpu().to(v.dtype), v), k
+
+
 def test_eval_mode_forward_and_subcalls():
     import mvae_b200
     B, n, seed = 40, 16, 7
