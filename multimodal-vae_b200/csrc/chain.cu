@@ -1,0 +1,1008 @@
+// Slab-persistent layer chains of the MNIST MVAE step (bf16): ONE CTA owns a 128-row slab of the batch and carries it
+// through a whole chain of Linear layers - the activation never leaves the SM between layers.
+//
+//   enc_fwd : image -> Linear 784->400 -> BN+ReLU -> Linear 400->200 -> BN+ReLU -> Linear 200->2n      (mnist/model.py:99-117)
+//   dec_fwd : z -> Linear n->200 -> BN+ReLU -> Linear 200->400 -> BN+ReLU -> Linear 400->784 + sigmoid/BCE/dlogits
+//                                                                            (mnist/model.py:120-135, mnist/train.py:70)
+//   dec_bwd : dlogits -> dgrad 784->400 -> ReLU/BN backward -> dgrad 400->200 -> ReLU/BN backward -> dgrad 200->n
+//   enc_bwd : d(enc) -> dgrad 2n->200 -> ReLU/BN backward -> dgrad 200->400 -> ReLU/BN backward
+//
+// Roles (320 threads): warp 0 = TMA producer (weights - and the streamed A operand of the two K = 784 layers - into a
+// SWIZZLE_128B shared-memory ring, running ahead across layer boundaries), warp 1 = tcgen05.mma issuer (fp32 accumulators
+// in TMEM, up to 512 columns = a whole layer), warps 2..9 = epilogue (one accumulator row per thread).  The epilogue of a
+// layer writes the NEXT layer's A operand straight into shared memory in the UMMA K-major swizzled layout (7 panels of
+// 128 rows x 64 columns), so `h = relu(bn(x W^T + b))` feeds the next tcgen05.mma without touching HBM; what the weight-
+// gradient GEMMs and the backward need (pre-/post-BatchNorm activations, gradients) is written to global memory once,
+// on the side.
+//
+// BatchNorm needs whole-batch statistics per ELBO term: each CTA reduces its slab's column sums (butterfly shuffles ->
+// shared atomics -> one global atomic per column), all CTAs of a term meet at a grid barrier (arrival counter in the step
+// workspace, cooperative launch guarantees co-residency), read the sums back and normalise their own slab from TMEM.
+// One barrier per BatchNorm layer and direction; everything else is CTA-local.
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace mvae {
+
+namespace {
+
+constexpr int kCThreads = 320;
+constexpr int kCEpi = 256;
+constexpr int kPanel = 16384;                  // 128 rows x 128 B: one K-major SWIZZLE_128B panel (64 bf16 columns)
+constexpr int kArenaPanels = 7;                // 448 columns >= the widest resident activation (400)
+constexpr int kArena = kArenaPanels * kPanel;  // 114688
+constexpr int kRingBytes = 4 * 26624;          // weight ring behind the arena: 4 stages of 208 rows x 128 B
+constexpr int kMain = kArena + kRingBytes;     // 221184 = 3 x 73728 (the K = 784 layers use all of it as a 3-stage ring)
+constexpr int kTabFloats = 2432;               // per-layer coefficient / statistics tables
+constexpr int kChainSmem = 1024 + kMain + kTabFloats * 4;
+constexpr int kMaxPass = 8;
+constexpr int kMaxLayer = 3;
+constexpr int kMaxChunk = 4;
+
+enum : int { CE_FWD_BN = 0, CE_FWD_STORE = 1, CE_BCE = 2, CE_DGRAD_BN = 3, CE_DGRAD_STORE = 4 };
+
+struct CRing {
+  int base, stage_bytes, stages, a_bytes;
+};
+
+// One pass of the producer / MMA pipelines: a K loop over 64-wide panels for one or two accumulator chunks.
+struct CPass {
+  int cfg;                // ring configuration
+  int k_panels;           // 64-wide contraction panels
+  int last_ksteps;        // 16-wide k-steps in the last panel (1..4)
+  int a_stream;           // tensor map of the streamed A operand (one [128 x 64] tile per stage), or -1: resident in the arena
+  int a_wait;             // 0: nothing, 1: wait for the TMA-loaded resident A, 2: wait for the A written by the epilogue
+  int b_tm;               // tensor map of B
+  int b_mn;               // 0: B tile rows are output columns (K-major); 1: MN-major 64 x 64 boxes
+  int n_chunks;
+  int c_n0[2];            // first output column of the chunk
+  int c_mma_n[2];         // UMMA N
+  int c_boxes[2];         // MN-major: 64-column boxes
+  int c_bytes[2];         // bytes TMA writes per stage for the chunk
+  int c_boff[2];          // byte offset inside the stage's B slot
+  int c_tmem[2];          // TMEM column base
+  int c_buf[2];           // accumulator barrier pair
+};
+
+struct CLayer {
+  int kind, N, n_chunks;
+  int c_n0[kMaxChunk], c_w[kMaxChunk], c_tmem[kMaxChunk], c_buf[kMaxChunk];
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* stat0;            // [G][N] forward: sum y / backward: sum dyhat
+  float* stat1;            // [G][N] forward: sum y^2 / backward: sum dyhat * xhat
+  float* save_mean;        // [G][N] forward: written; backward: read
+  float* save_rstd;
+  float* running_mean;     // forward, leader CTA
+  float* running_var;
+  int bn_updates;
+  unsigned int* counter;   // [G] grid-barrier arrivals
+  __nv_bfloat16* out_pre;  // forward BN: pre-BatchNorm activations [R][N]
+  __nv_bfloat16* out_post; // forward BN: post BN+ReLU [R][N]; backward BN: gradient at the layer's pre-BatchNorm output
+  int write_arena;         // the result is the next layer's A operand
+  const __nv_bfloat16* hpre;  // backward BN: pre-BatchNorm activations of the forward
+  float* dgamma;
+  float* dbeta;
+  float* out_f32;          // store kinds
+  int ld_out;
+  // BCE
+  const __nv_bfloat16* target;
+  int target_rows;
+  float bce_scale[3];
+  float* loss;             // [G]
+  float* dbias;            // [N] +=
+  __nv_bfloat16* dlog;
+  __nv_bfloat16* probs;
+};
+
+struct alignas(64) CParams {
+  CUtensorMap tm[5];
+  CRing ring[2];
+  CPass pass[kMaxPass];
+  CLayer layer[kMaxLayer];
+  int n_pass, n_layers;
+  int rows_per_group;     // rows of one statistics group (= batch)
+  int init_tm, init_panels;  // resident A loaded by TMA at kernel start (z / d_enc), -1: none
+  float momentum, eps;
+  unsigned int* err;      // device flag: non-zero = a wait timed out (bring-up)
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// mbarrier wait that cannot hang the GPU: after ~4 s the kernel records where it was stuck and traps.
+__device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = gtimer();
+  unsigned int spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && gtimer() - t0 > 4000000000ull) {
+      if (err != nullptr) atomicExch(err, code);
+      __threadfence();
+      asm volatile("trap;");
+    }
+  }
+}
+
+__device__ __forceinline__ void bar_epi() { ptx::named_bar_sync(1, kCEpi); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void unpack8(const uint4& t, float* o) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[2 * k] = __uint_as_float(w[k] << 16);
+    o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+
+// Column sums over the 32 lanes (rows) of a warp for 16 columns held one row per lane: a reduce-scatter butterfly
+// (16 shuffles instead of 80).  Afterwards every lane holds the warp-wide sum of column colperm(lane); lanes 2k and
+// 2k+1 hold the same column.  v is destroyed.
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+  {
+    const bool b = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = b ? v[i] : v[i + 8];
+      const float keep = b ? v[i + 8] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool b = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = b ? v[i] : v[i + 4];
+      const float keep = b ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool b = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = b ? v[i] : v[i + 2];
+      const float keep = b ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool b = (lane & 2) != 0;
+    const float send = b ? v[0] : v[1];
+    const float keep = b ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+__device__ __forceinline__ int colperm(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+// 16 consecutive bf16 of one row -> the arena (K-major SWIZZLE_128B panels): 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+__device__ __forceinline__ void arena_store16(uint32_t arena, int row, int col, const uint32_t (&w)[8]) {
+  const int panel = col >> 6, cc = (col & 63) >> 3;
+  const uint32_t base = arena + panel * kPanel + row * 128;
+  ptx::sts128(base + (((cc) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
+  ptx::sts128(base + (((cc + 1) ^ (row & 7)) << 4), w[4], w[5], w[6], w[7]);
+}
+
+// 16 bf16 of one global row (n_valid of them in range, a multiple of 8)
+__device__ __forceinline__ void gstore16(__nv_bfloat16* dst, int n_valid, const uint32_t (&w)[8]) {
+  if (n_valid >= 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  if (n_valid >= 16) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ void gload16(const __nv_bfloat16* src, int n_valid, float (&x)[16]) {
+  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+  if (n_valid >= 8) a = __ldg(reinterpret_cast<const uint4*>(src));
+  if (n_valid >= 16) b = __ldg(reinterpret_cast<const uint4*>(src + 8));
+  unpack8(a, x);
+  unpack8(b, x + 8);
+}
+
+// Grid barrier of one statistics group: arrive, then wait until all `expected` CTAs of the group have arrived.
+// Called by all 256 epilogue threads after their global atomics.  A lost CTA cannot hang the GPU: after ~2 s the wait
+// gives up and flags the error (results are then garbage, which the flag reports).
+__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int expected, unsigned int* err, int et) {
+  __threadfence();
+  bar_epi();
+  if (et == 0) {
+    atomicAdd(counter, 1u);
+    unsigned int seen = 0;
+    const unsigned long long t0 = gtimer();
+    unsigned int spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen >= expected) break;
+      if ((++spins & 255u) == 0 && gtimer() - t0 > 2000000000ull) {
+        if (err != nullptr) atomicExch(err, 0xBA00u | (seen & 0xffu));
+        break;
+      }
+      __nanosleep(40);
+    }
+    __threadfence();
+  }
+  bar_epi();
+}
+// wait (without arriving) until a group's counter is complete - the leader CTA's end-of-kernel bookkeeping
+__device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned int expected, unsigned int* err) {
+  unsigned int seen = 0;
+  const unsigned long long t0 = gtimer();
+  unsigned int spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    if (seen >= expected) break;
+    if ((++spins & 255u) == 0 && gtimer() - t0 > 2000000000ull) {
+      if (err != nullptr) atomicExch(err, 0xBB00u | (seen & 0xffu));
+      break;
+    }
+    __nanosleep(40);
+  }
+  __threadfence();
+}
+
+__global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_constant__ CParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* tab = reinterpret_cast<float*>(smem + kMain);
+  __shared__ __align__(8) uint64_t full_bar[4];
+  __shared__ __align__(8) uint64_t empty_bar[4];
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t a_tma_bar;
+  __shared__ __align__(8) uint64_t a_epi_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_loss;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * 128;
+  const int grp = m0 / p.rows_per_group;
+  const unsigned int slabs_per_group = static_cast<unsigned int>(p.rows_per_group / 128);
+  const bool group_leader = (m0 % p.rows_per_group) == 0;
+  const uint32_t smem_u = ptx::smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 5; ++i) ptx::prefetch_tmap(&p.tm[i]);
+    for (int s = 0; s < 4; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&acc_full[b], 1);
+      ptx::mbar_init(&acc_empty[b], kCEpi);
+    }
+    ptx::mbar_init(&a_tma_bar, 1);
+    ptx::mbar_init(&a_epi_bar, kCEpi);
+    ptx::fence_mbar_init();
+    s_loss = 0.f;
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // =================================================================== TMA producer
+    if (lane == 0) {
+      if (p.init_tm >= 0) {
+        ptx::mbar_expect_tx(&a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel));
+        for (int pn = 0; pn < p.init_panels; ++pn) ptx::tma_load_2d(smem + pn * kPanel, &p.tm[p.init_tm], &a_tma_bar, pn * 64, m0);
+      }
+      uint32_t fills[4] = {0, 0, 0, 0};
+      int cur_cfg = -1, cnt = 0;
+      for (int ip = 0; ip < p.n_pass; ++ip) {
+        const CPass& ps = p.pass[ip];
+        const CRing rg = p.ring[ps.cfg];
+        if (ps.cfg != cur_cfg) {
+          // the two ring geometries overlap in shared memory: everything in flight must have been consumed
+          for (int s = 0; s < 4; ++s)
+            if (fills[s] > 0) mbar_wait_b(&empty_bar[s], (fills[s] - 1) & 1, p.err, 0x100u + s);
+          cur_cfg = ps.cfg;
+          cnt = 0;
+        }
+        uint32_t bytes = ps.a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u;
+        for (int c = 0; c < ps.n_chunks; ++c) bytes += static_cast<uint32_t>(ps.c_bytes[c]);
+        for (int kp = 0; kp < ps.k_panels; ++kp) {
+          const int s = cnt % rg.stages;
+          ++cnt;
+          mbar_wait_b(&empty_bar[s], (fills[s] & 1) ^ 1, p.err, 0x110u + s);
+          ptx::mbar_expect_tx(&full_bar[s], bytes);
+          uint8_t* stage = smem + rg.base + s * rg.stage_bytes;
+          if (ps.a_stream >= 0) ptx::tma_load_2d(stage, &p.tm[ps.a_stream], &full_bar[s], kp * 64, m0);
+          uint8_t* bslot = stage + rg.a_bytes;
+          for (int c = 0; c < ps.n_chunks; ++c) {
+            if (!ps.b_mn) {
+              ptx::tma_load_2d(bslot + ps.c_boff[c], &p.tm[ps.b_tm], &full_bar[s], kp * 64, ps.c_n0[c]);
+            } else {
+              for (int j = 0; j < ps.c_boxes[c]; ++j)
+                ptx::tma_load_2d(bslot + ps.c_boff[c] + j * 8192, &p.tm[ps.b_tm], &full_bar[s], ps.c_n0[c] + j * 64, kp * 64);
+            }
+          }
+          ++fills[s];
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t uses[4] = {0, 0, 0, 0};
+      uint32_t acc_uses[2] = {0, 0};
+      uint32_t n_tma_waits = 0, n_epi_waits = 0;
+      int cur_cfg = -1, cnt = 0;
+      for (int ip = 0; ip < p.n_pass; ++ip) {
+        const CPass& ps = p.pass[ip];
+        const CRing rg = p.ring[ps.cfg];
+        if (ps.cfg != cur_cfg) {
+          cur_cfg = ps.cfg;
+          cnt = 0;
+        }
+        if (ps.a_wait == 1) {
+          mbar_wait_b(&a_tma_bar, n_tma_waits & 1, p.err, 0x200u);
+          ++n_tma_waits;
+        } else if (ps.a_wait == 2) {
+          mbar_wait_b(&a_epi_bar, n_epi_waits & 1, p.err, 0x201u);
+          ++n_epi_waits;
+        }
+        for (int c = 0; c < ps.n_chunks; ++c) {
+          const int b = ps.c_buf[c];
+          mbar_wait_b(&acc_empty[b], (acc_uses[b] & 1) ^ 1, p.err, 0x210u + b);
+        }
+        ptx::tc_fence_after();
+        uint32_t idesc[2];
+        for (int c = 0; c < ps.n_chunks; ++c) idesc[c] = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[c]);
+        for (int kp = 0; kp < ps.k_panels; ++kp) {
+          const int s = cnt % rg.stages;
+          ++cnt;
+          mbar_wait_b(&full_bar[s], uses[s] & 1, p.err, 0x220u + s);
+          ++uses[s];
+          ptx::tc_fence_after();
+          const uint32_t stage = smem_u + rg.base + s * rg.stage_bytes;
+          const uint32_t a_base = ps.a_stream >= 0 ? stage : smem_u + kp * kPanel;
+          const uint32_t bslot = stage + rg.a_bytes;
+          const int nks = (kp == ps.k_panels - 1) ? ps.last_ksteps : 4;
+          for (int ks = 0; ks < nks; ++ks) {
+            const uint64_t adesc = ptx::make_smem_desc(a_base + ks * 32, 16, 1024);
+            for (int c = 0; c < ps.n_chunks; ++c) {
+              const uint64_t bdesc = ps.b_mn ? ptx::make_smem_desc(bslot + ps.c_boff[c] + ks * 2048, 8192, 1024, 2)
+                                             : ptx::make_smem_desc(bslot + ps.c_boff[c] + ks * 32, 16, 1024);
+              ptx::umma<MVAE_BF16>(tmem_base + ps.c_tmem[c], adesc, bdesc, idesc[c], (kp | ks) != 0 ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(&empty_bar[s]);
+        }
+        for (int c = 0; c < ps.n_chunks; ++c) {
+          ptx::umma_commit(&acc_full[ps.c_buf[c]]);
+          ++acc_uses[ps.c_buf[c]];
+        }
+      }
+    }
+  } else {
+    // =================================================================== epilogue (8 warps, one accumulator row per thread)
+    const int et = threadIdx.x - 64;
+    const int q = warp & 3;               // TMEM lane quarter this warp may read
+    const int h = (warp - 2) >> 2;        // the two warps of a quarter take alternate 16-column pieces
+    const int row = q * 32 + lane;
+    const long long grow = static_cast<long long>(m0) + row;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t epi_uses[2] = {0, 0};
+    const float inv_cnt = 1.f / static_cast<float>(p.rows_per_group);
+
+    for (int il = 0; il < p.n_layers; ++il) {
+      const CLayer& L = p.layer[il];
+      const int N = L.N;
+      const int Npad = (N + 15) & ~15;
+      if (L.kind == CE_FWD_BN) {
+        float* s_bias = tab;
+        float* s_ca = tab + 800;
+        float* s_cb = tab + 1208;
+        float* s_s0 = tab + 1616;
+        float* s_s1 = tab + 2024;
+        for (int c = et; c < Npad; c += kCEpi) {
+          s_bias[c] = c < N ? L.bias[c] : 0.f;
+          s_s0[c] = 0.f;
+          s_s1[c] = 0.f;
+        }
+        bar_epi();
+        // ---- pass 1: pre-activations out, slab statistics
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          mbar_wait_b(&acc_full[b], (epi_uses[b] + 0) & 1, p.err, 0x300u + il * 16 + ci);
+          ptx::tc_fence_after();
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            ptx::tmem_ld_wait();
+            float x[16], sq[16];
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + s_bias[col + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+            gstore16(L.out_pre + grow * N + col, N - col, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sq[j] = x[j] * x[j];
+            const float a0 = colsum16(x, lane);
+            const float a1 = colsum16(sq, lane);
+            const int c = col + colperm(lane);
+            if (c < N) atomicAdd((lane & 1) ? &s_s1[c] : &s_s0[c], (lane & 1) ? a1 : a0);
+          }
+        }
+        bar_epi();
+        for (int c = et; c < N; c += kCEpi) {
+          atomicAdd(L.stat0 + grp * N + c, s_s0[c]);
+          atomicAdd(L.stat1 + grp * N + c, s_s1[c]);
+        }
+        group_barrier(L.counter + grp, slabs_per_group, p.err, et);
+        for (int c = et; c < Npad; c += kCEpi) {
+          float a_ = 0.f, b_ = 0.f;
+          if (c < N) {
+            const float mean = __ldcg(L.stat0 + grp * N + c) * inv_cnt;
+            const float var = fmaxf(__ldcg(L.stat1 + grp * N + c) * inv_cnt - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + p.eps);
+            a_ = L.gamma[c] * rstd;
+            b_ = fmaf(-mean, a_, L.beta[c]);
+            if (group_leader) {
+              L.save_mean[grp * N + c] = mean;
+              L.save_rstd[grp * N + c] = rstd;
+            }
+          }
+          s_ca[c] = a_;
+          s_cb[c] = b_;
+        }
+        bar_epi();
+        // ---- pass 2: BatchNorm + ReLU from TMEM -> next layer's A operand (+ the copy the weight gradient needs)
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            ptx::tmem_ld_wait();
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x0 = bf16_round(__uint_as_float(v[2 * j]) + s_bias[col + 2 * j]);       // what out_pre holds
+              const float x1 = bf16_round(__uint_as_float(v[2 * j + 1]) + s_bias[col + 2 * j + 1]);
+              const float y0 = fmaxf(fmaf(s_ca[col + 2 * j], x0, s_cb[col + 2 * j]), 0.f);
+              const float y1 = fmaxf(fmaf(s_ca[col + 2 * j + 1], x1, s_cb[col + 2 * j + 1]), 0.f);
+              w[j] = pack_bf16(y0, y1);
+            }
+            gstore16(L.out_post + grow * N + col, N - col, w);
+            if (L.write_arena) arena_store16(smem_u, row, col, w);
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[b]);
+          ++epi_uses[b];
+        }
+        if (L.write_arena) {
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&a_epi_bar);
+        }
+      } else if (L.kind == CE_DGRAD_BN) {
+        float* s_a = tab;
+        float* s_b = tab + 400;
+        float* s_rs = tab + 800;
+        float* s_mr = tab + 1200;
+        float* s_s0 = tab + 1600;
+        float* s_s1 = tab + 2000;
+        for (int c = et; c < Npad; c += kCEpi) {
+          float a_ = 0.f, b_ = 0.f, rs = 0.f, mr = 0.f;
+          if (c < N) {
+            const float mean = L.save_mean[grp * N + c];
+            rs = L.save_rstd[grp * N + c];
+            a_ = L.gamma[c] * rs;
+            b_ = fmaf(-mean, a_, L.beta[c]);   // the forward's own expression: bit-identical ReLU mask
+            mr = -mean * rs;
+          }
+          s_a[c] = a_; s_b[c] = b_; s_rs[c] = rs; s_mr[c] = mr;
+          s_s0[c] = 0.f; s_s1[c] = 0.f;
+        }
+        bar_epi();
+        // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
+          ptx::tc_fence_after();
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            float x[16];
+            gload16(L.hpre + grow * N + col, N - col, x);
+            ptx::tmem_ld_wait();
+            float d[16], dx[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float y = fmaf(s_a[col + j], x[j], s_b[col + j]);
+              const float xh = fmaf(x[j], s_rs[col + j], s_mr[col + j]);
+              d[j] = y > 0.f ? __uint_as_float(v[j]) : 0.f;
+              dx[j] = d[j] * xh;
+            }
+            const float a0 = colsum16(d, lane);
+            const float a1 = colsum16(dx, lane);
+            const int c = col + colperm(lane);
+            if (c < N) atomicAdd((lane & 1) ? &s_s1[c] : &s_s0[c], (lane & 1) ? a1 : a0);
+          }
+        }
+        bar_epi();
+        for (int c = et; c < N; c += kCEpi) {
+          atomicAdd(L.stat0 + grp * N + c, s_s0[c]);
+          atomicAdd(L.stat1 + grp * N + c, s_s1[c]);
+        }
+        group_barrier(L.counter + grp, slabs_per_group, p.err, et);
+        for (int c = et; c < Npad; c += kCEpi) {
+          s_s0[c] = c < N ? __ldcg(L.stat0 + grp * N + c) * inv_cnt : 0.f;
+          s_s1[c] = c < N ? __ldcg(L.stat1 + grp * N + c) * inv_cnt : 0.f;
+        }
+        bar_epi();
+        // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat))
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            float x[16];
+            gload16(L.hpre + grow * N + col, N - col, x);
+            ptx::tmem_ld_wait();
+            uint32_t w[8];
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float y = fmaf(s_a[col + j], x[j], s_b[col + j]);
+              const float xh = fmaf(x[j], s_rs[col + j], s_mr[col + j]);
+              const float d = y > 0.f ? __uint_as_float(v[j]) : 0.f;
+              o[j] = s_a[col + j] * (d - s_s0[col + j] - xh * s_s1[col + j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(o[2 * j], o[2 * j + 1]);
+            gstore16(L.out_post + grow * N + col, N - col, w);
+            if (L.write_arena) arena_store16(smem_u, row, col, w);
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[b]);
+          ++epi_uses[b];
+        }
+        if (L.write_arena) {
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&a_epi_bar);
+        }
+      } else if (L.kind == CE_FWD_STORE || L.kind == CE_DGRAD_STORE) {
+        float* s_bias = tab;
+        for (int c = et; c < Npad; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
+        bar_epi();
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
+          ptx::tc_fence_after();
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            ptx::tmem_ld_wait();
+            if (col + 16 <= N) {
+              float* dst = L.out_f32 + grow * L.ld_out + col;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(dst + j) =
+                    make_float4(__uint_as_float(v[j]) + s_bias[col + j], __uint_as_float(v[j + 1]) + s_bias[col + j + 1],
+                                __uint_as_float(v[j + 2]) + s_bias[col + j + 2], __uint_as_float(v[j + 3]) + s_bias[col + j + 3]);
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[b]);
+          ++epi_uses[b];
+        }
+      } else if (L.kind == CE_BCE) {
+        // last decoder Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70): logits never leave the SM.
+        // loss = softplus(x) - t x, dlogit = scale * (sigmoid(x) - t); also the bias gradient (column sums of dlogit).
+        float* s_bias = tab;
+        float* s_db = tab + 800;
+        for (int c = et; c < Npad; c += kCEpi) {
+          s_bias[c] = c < N ? L.bias[c] : 0.f;
+          s_db[c] = 0.f;
+        }
+        bar_epi();
+        const float scale = L.bce_scale[grp];
+        const long long trow = static_cast<long long>(m0 % L.target_rows) + row;
+        float lsum = 0.f;
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
+          ptx::tc_fence_after();
+          const int pieces = L.c_w[ci] >> 4;
+          for (int pi = h; pi < pieces; pi += 2) {
+            const int col = L.c_n0[ci] + pi * 16;
+            uint32_t v[16];
+            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
+            float tg[16];
+            gload16(L.target + trow * N + col, N - col, tg);
+            ptx::tmem_ld_wait();
+            float d[16], pr[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float x = __uint_as_float(v[j]) + s_bias[col + j];
+              const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
+              const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
+              const float pz = x >= 0.f ? inv : ex * inv;
+              pr[j] = pz;
+              d[j] = scale * (pz - tg[j]);
+              // softplus(x) - t x = max(x, 0) - t x - ln(sigmoid(|x|))
+              lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[j], x, fmaxf(x, 0.f)));
+            }
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(d[2 * j], d[2 * j + 1]);
+            gstore16(L.dlog + grow * N + col, N - col, w);
+            if (L.probs != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) w[j] = pack_bf16(pr[2 * j], pr[2 * j + 1]);
+              gstore16(L.probs + grow * N + col, N - col, w);
+            }
+            if (L.dbias != nullptr) {
+              const float a0 = colsum16(d, lane);
+              const int c = col + colperm(lane);
+              if ((lane & 1) == 0 && c < N) atomicAdd(&s_db[c], a0);
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&acc_empty[b]);
+          ++epi_uses[b];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        if (lane == 0) atomicAdd(&s_loss, lsum);
+        bar_epi();
+        if (L.dbias != nullptr)
+          for (int c = et; c < N; c += kCEpi) atomicAdd(L.dbias + c, s_db[c]);
+        if (et == 0 && L.loss != nullptr) atomicAdd(L.loss + grp, scale * s_loss);
+      }
+      bar_epi();   // the tables are reused by the next layer
+    }
+
+    // ---- leader CTA: what needs every group's statistics, in group order (one reference forward pass per group)
+    if (blockIdx.x == 0) {
+      const int groups = static_cast<int>(gridDim.x / slabs_per_group);
+      for (int il = 0; il < p.n_layers; ++il) {
+        const CLayer& L = p.layer[il];
+        if (L.kind != CE_FWD_BN && L.kind != CE_DGRAD_BN) continue;
+        if (et == 0)
+          for (int g = 0; g < groups; ++g) group_wait(L.counter + g, slabs_per_group, p.err);
+        bar_epi();
+        const int N = L.N;
+        const float cnt = static_cast<float>(p.rows_per_group);
+        for (int c = et; c < N; c += kCEpi) {
+          if (L.kind == CE_FWD_BN) {
+            if (L.running_mean == nullptr) continue;
+            float rm = L.running_mean[c], rv = L.running_var[c];
+            for (int g = 0; g < groups; ++g) {
+              const float mean = __ldcg(L.stat0 + g * N + c) / cnt;
+              const float var = fmaxf(__ldcg(L.stat1 + g * N + c) / cnt - mean * mean, 0.f);
+              const float unb = cnt > 1.f ? var * (cnt / (cnt - 1.f)) : var;
+              for (int u = 0; u < L.bn_updates; ++u) {
+                rm = (1.f - p.momentum) * rm + p.momentum * mean;
+                rv = (1.f - p.momentum) * rv + p.momentum * unb;
+              }
+            }
+            L.running_mean[c] = rm;
+            L.running_var[c] = rv;
+          } else {
+            float dg = 0.f, db = 0.f;
+            for (int g = 0; g < groups; ++g) {
+              db += __ldcg(L.stat0 + g * N + c);
+              dg += __ldcg(L.stat1 + g * N + c);
+            }
+            if (L.dgamma != nullptr) {
+              L.dgamma[c] += dg;
+              L.dbeta[c] += db;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn chain_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// bf16 matrix [rows, cols] (cols contiguous, leading dimension ld), box = box_cols x box_rows, SWIZZLE_128B, zero OOB fill
+int chain_tmap(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = chain_encode_fn();
+  MVAE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MVAE_REQUIRE(r == CUDA_SUCCESS, "chain: cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows,
+               cols, ld, box_cols, box_rows);
+  return 0;
+}
+
+void set_chunk(CPass& ps, int c, int n0, int mma_n, int boxes, int bytes, int boff, int tmem, int buf) {
+  ps.c_n0[c] = n0; ps.c_mma_n[c] = mma_n; ps.c_boxes[c] = boxes; ps.c_bytes[c] = bytes; ps.c_boff[c] = boff;
+  ps.c_tmem[c] = tmem; ps.c_buf[c] = buf;
+}
+void set_lchunk(CLayer& L, int c, int n0, int w, int tmem, int buf) {
+  L.c_n0[c] = n0; L.c_w[c] = w; L.c_tmem[c] = tmem; L.c_buf[c] = buf;
+}
+int ksteps_of(int K) { return ((K - 1) % 64) / 16 + 1; }   // 16-wide k-steps in the last 64-wide panel
+int panels_of(int K) { return (K + 63) / 64; }
+
+int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    attr_set = true;
+  }
+  static const int coop = env_int("MVAE_CHAIN_COOP", 1);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(kCThreads);
+  cfg.dynamicSmemBytes = kChainSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barriers cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel, p);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(chain_kernel)", __FILE__, __LINE__);
+  return 0;
+}
+
+void init_params(CParams& p, int rows_per_group, unsigned int* err) {
+  memset(&p, 0, sizeof(p));
+  p.rows_per_group = rows_per_group;
+  p.init_tm = -1;
+  p.momentum = 0.1f;
+  p.eps = 1e-5f;
+  p.err = err;
+  p.ring[1] = CRing{kArena, 26624, 4, 0};
+}
+
+}  // namespace
+
+// true if the chain kernels can run this step: all slabs whole, co-resident, dimensions inside the on-chip plan
+bool chain_supported(int B, int G, int n) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
+}
+
+int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
+  CParams p;
+  init_params(p, a.B, a.err);
+  const int n2 = 2 * a.n;
+  if (chain_tmap(&p.tm[0], a.image, a.B, 784, 784, 64, 128)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, 208)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, n2)) return 1;
+  p.tm[4] = p.tm[3];
+  p.ring[0] = CRing{0, kPanel + 2 * 26624, 3, kPanel};
+  p.n_pass = 3;
+  CPass& e1 = p.pass[0];
+  e1.cfg = 0; e1.k_panels = panels_of(784); e1.last_ksteps = ksteps_of(784); e1.a_stream = 0; e1.a_wait = 0; e1.b_tm = 1; e1.b_mn = 0;
+  e1.n_chunks = 2;
+  set_chunk(e1, 0, 0, 208, 0, 26624, 0, 0, 0);
+  set_chunk(e1, 1, 208, 192, 0, 26624, 26624, 256, 1);
+  CPass& e2 = p.pass[1];
+  e2.cfg = 1; e2.k_panels = panels_of(400); e2.last_ksteps = ksteps_of(400); e2.a_stream = -1; e2.a_wait = 2; e2.b_tm = 2; e2.b_mn = 0;
+  e2.n_chunks = 1;
+  set_chunk(e2, 0, 0, 208, 0, 26624, 0, 0, 0);
+  CPass& e3 = p.pass[2];
+  e3.cfg = 1; e3.k_panels = panels_of(200); e3.last_ksteps = ksteps_of(200); e3.a_stream = -1; e3.a_wait = 2; e3.b_tm = 3; e3.b_mn = 0;
+  e3.n_chunks = 1;
+  set_chunk(e3, 0, 0, n2, 0, n2 * 128, 0, 256, 1);
+  p.n_layers = 3;
+  CLayer& l1 = p.layer[0];
+  l1.kind = CE_FWD_BN; l1.N = 400; l1.n_chunks = 2;
+  set_lchunk(l1, 0, 0, 208, 0, 0);
+  set_lchunk(l1, 1, 208, 192, 256, 1);
+  l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + 400;
+  l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = a.bn_updates;
+  l1.counter = a.counters; l1.out_pre = a.h1pre; l1.out_post = a.h1; l1.write_arena = 1;
+  CLayer& l2 = p.layer[1];
+  l2.kind = CE_FWD_BN; l2.N = 200; l2.n_chunks = 1;
+  set_lchunk(l2, 0, 0, 208, 0, 0);
+  l2.bias = a.b2; l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.st2; l2.stat1 = a.st2 + 200;
+  l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + 200; l2.running_mean = a.rm2; l2.running_var = a.rv2; l2.bn_updates = a.bn_updates;
+  l2.counter = a.counters + 1; l2.out_pre = a.h2pre; l2.out_post = a.h2; l2.write_arena = 1;
+  CLayer& l3 = p.layer[2];
+  l3.kind = CE_FWD_STORE; l3.N = n2; l3.n_chunks = 1;
+  set_lchunk(l3, 0, 0, n2, 256, 1);
+  l3.bias = a.b3; l3.out_f32 = a.enc; l3.ld_out = n2;
+  note_launch(1);
+  return launch_chain(p, a.B / 128, st);
+}
+
+int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
+  CParams p;
+  const int R = a.G * a.B, G = a.G;
+  init_params(p, a.B, a.err);
+  if (chain_tmap(&p.tm[0], a.z, R, a.n, a.n, 64, 128)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, 208)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 208)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, 784, 400, 400, 64, 208)) return 1;
+  p.tm[4] = p.tm[3];
+  p.ring[0] = p.ring[1];
+  p.init_tm = 0;
+  p.init_panels = panels_of(a.n);
+  p.n_pass = 7;
+  CPass& d1 = p.pass[0];
+  d1.cfg = 1; d1.k_panels = panels_of(a.n); d1.last_ksteps = ksteps_of(a.n); d1.a_stream = -1; d1.a_wait = 1; d1.b_tm = 1; d1.b_mn = 0;
+  d1.n_chunks = 1;
+  set_chunk(d1, 0, 0, 208, 0, 26624, 0, 0, 0);
+  for (int c = 0; c < 2; ++c) {
+    CPass& d2 = p.pass[1 + c];
+    d2.cfg = 1; d2.k_panels = panels_of(200); d2.last_ksteps = ksteps_of(200); d2.a_stream = -1; d2.a_wait = c == 0 ? 2 : 0; d2.b_tm = 2;
+    d2.b_mn = 0; d2.n_chunks = 1;
+    set_chunk(d2, 0, c == 0 ? 0 : 208, c == 0 ? 208 : 192, 0, 26624, 0, c * 256, c);
+  }
+  const int n0s[4] = {0, 208, 400, 592}, ws[4] = {208, 192, 192, 192};
+  for (int c = 0; c < 4; ++c) {
+    CPass& d3 = p.pass[3 + c];
+    d3.cfg = 1; d3.k_panels = panels_of(400); d3.last_ksteps = ksteps_of(400); d3.a_stream = -1; d3.a_wait = c == 0 ? 2 : 0; d3.b_tm = 3;
+    d3.b_mn = 0; d3.n_chunks = 1;
+    set_chunk(d3, 0, n0s[c], ws[c], 0, 26624, 0, (c & 1) * 256, c & 1);
+  }
+  p.n_layers = 3;
+  CLayer& l1 = p.layer[0];
+  l1.kind = CE_FWD_BN; l1.N = 200; l1.n_chunks = 1;
+  set_lchunk(l1, 0, 0, 208, 0, 0);
+  l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + G * 200;
+  l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + G * 200; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = 1;
+  l1.counter = a.counters; l1.out_pre = a.g1pre; l1.out_post = a.g1; l1.write_arena = 1;
+  CLayer& l2 = p.layer[1];
+  l2.kind = CE_FWD_BN; l2.N = 400; l2.n_chunks = 2;
+  set_lchunk(l2, 0, 0, 208, 0, 0);
+  set_lchunk(l2, 1, 208, 192, 256, 1);
+  l2.bias = a.b2; l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.st2; l2.stat1 = a.st2 + G * 400;
+  l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + G * 400; l2.running_mean = a.rm2; l2.running_var = a.rv2; l2.bn_updates = 1;
+  l2.counter = a.counters + 3; l2.out_pre = a.g2pre; l2.out_post = a.g2; l2.write_arena = 1;
+  CLayer& l3 = p.layer[2];
+  l3.kind = CE_BCE; l3.N = 784; l3.n_chunks = 4;
+  for (int c = 0; c < 4; ++c) set_lchunk(l3, c, n0s[c], ws[c], (c & 1) * 256, c & 1);
+  l3.bias = a.b3; l3.target = a.image; l3.target_rows = a.B;
+  for (int g = 0; g < 3; ++g) l3.bce_scale[g] = a.bce_scale[g];
+  l3.loss = a.loss; l3.dbias = a.dbias3; l3.dlog = a.dlog; l3.probs = a.probs;
+  note_launch(1);
+  return launch_chain(p, R / 128, st);
+}
+
+int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
+  CParams p;
+  const int R = a.G * a.B, G = a.G;
+  init_params(p, a.B, a.err);
+  if (chain_tmap(&p.tm[0], a.dlog, R, 784, 784, 64, 128)) return 1;
+  if (chain_tmap(&p.tm[1], a.w3, 784, 400, 400, 64, 64)) return 1;   // dgrad: W[out, in] read as the MN-major B operand
+  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 64)) return 1;
+  if (chain_tmap(&p.tm[3], a.w1, 200, a.n, a.n, 64, 64)) return 1;
+  p.tm[4] = p.tm[3];
+  p.ring[0] = CRing{0, 73728, 3, kPanel};
+  p.ring[1] = CRing{kArena, 32768, 3, 0};
+  p.n_pass = 3;
+  CPass& g3 = p.pass[0];
+  g3.cfg = 0; g3.k_panels = panels_of(784); g3.last_ksteps = ksteps_of(784); g3.a_stream = 0; g3.a_wait = 0; g3.b_tm = 1; g3.b_mn = 1;
+  g3.n_chunks = 2;
+  set_chunk(g3, 0, 0, 256, 4, 32768, 0, 0, 0);
+  set_chunk(g3, 1, 256, 144, 3, 24576, 32768, 256, 1);
+  CPass& g2 = p.pass[1];
+  g2.cfg = 1; g2.k_panels = panels_of(400); g2.last_ksteps = ksteps_of(400); g2.a_stream = -1; g2.a_wait = 2; g2.b_tm = 2; g2.b_mn = 1;
+  g2.n_chunks = 1;
+  set_chunk(g2, 0, 0, 208, 4, 32768, 0, 0, 0);
+  CPass& g1 = p.pass[2];
+  const int nb = (a.n + 63) / 64;
+  g1.cfg = 1; g1.k_panels = panels_of(200); g1.last_ksteps = ksteps_of(200); g1.a_stream = -1; g1.a_wait = 2; g1.b_tm = 3; g1.b_mn = 1;
+  g1.n_chunks = 1;
+  set_chunk(g1, 0, 0, a.n, nb, nb * 8192, 0, 256, 1);
+  p.n_layers = 3;
+  CLayer& l2 = p.layer[0];
+  l2.kind = CE_DGRAD_BN; l2.N = 400; l2.n_chunks = 2;
+  set_lchunk(l2, 0, 0, 256, 0, 0);
+  set_lchunk(l2, 1, 256, 144, 256, 1);
+  l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + G * 400; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + G * 400;
+  l2.counter = a.counters; l2.hpre = a.g2pre; l2.out_post = a.dy2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
+  CLayer& l1 = p.layer[1];
+  l1.kind = CE_DGRAD_BN; l1.N = 200; l1.n_chunks = 1;
+  set_lchunk(l1, 0, 0, 208, 0, 0);
+  l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + G * 200; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + G * 200;
+  l1.counter = a.counters + 3; l1.hpre = a.g1pre; l1.out_post = a.dy1; l1.write_arena = 1; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
+  CLayer& l0 = p.layer[2];
+  l0.kind = CE_DGRAD_STORE; l0.N = a.n; l0.n_chunks = 1;
+  set_lchunk(l0, 0, 0, a.n, 256, 1);
+  l0.out_f32 = a.dz; l0.ld_out = a.n;
+  note_launch(1);
+  return launch_chain(p, R / 128, st);
+}
+
+int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
+  CParams p;
+  init_params(p, a.B, a.err);
+  const int n2 = 2 * a.n;
+  if (chain_tmap(&p.tm[0], a.denc, a.B, n2, n2, 64, 128)) return 1;
+  if (chain_tmap(&p.tm[1], a.w3, n2, 200, 200, 64, 64)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, 64)) return 1;
+  p.tm[3] = p.tm[2];
+  p.tm[4] = p.tm[2];
+  p.ring[1] = CRing{kArena, 32768, 3, 0};
+  p.ring[0] = p.ring[1];
+  p.init_tm = 0;
+  p.init_panels = panels_of(n2);
+  p.n_pass = 3;
+  CPass& g3 = p.pass[0];
+  g3.cfg = 1; g3.k_panels = panels_of(n2); g3.last_ksteps = ksteps_of(n2); g3.a_stream = -1; g3.a_wait = 1; g3.b_tm = 1; g3.b_mn = 1;
+  g3.n_chunks = 1;
+  set_chunk(g3, 0, 0, 208, 4, 32768, 0, 0, 0);
+  for (int c = 0; c < 2; ++c) {
+    CPass& g2 = p.pass[1 + c];
+    g2.cfg = 1; g2.k_panels = panels_of(200); g2.last_ksteps = ksteps_of(200); g2.a_stream = -1; g2.a_wait = c == 0 ? 2 : 0; g2.b_tm = 2;
+    g2.b_mn = 1; g2.n_chunks = 1;
+    set_chunk(g2, 0, c == 0 ? 0 : 256, c == 0 ? 256 : 144, c == 0 ? 4 : 3, c == 0 ? 32768 : 24576, 0, c * 256, c);
+  }
+  p.n_layers = 2;
+  CLayer& l2 = p.layer[0];
+  l2.kind = CE_DGRAD_BN; l2.N = 200; l2.n_chunks = 1;
+  set_lchunk(l2, 0, 0, 208, 0, 0);
+  l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + 200; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + 200;
+  l2.counter = a.counters; l2.hpre = a.h2pre; l2.out_post = a.dye2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
+  CLayer& l1 = p.layer[1];
+  l1.kind = CE_DGRAD_BN; l1.N = 400; l1.n_chunks = 2;
+  set_lchunk(l1, 0, 0, 256, 0, 0);
+  set_lchunk(l1, 1, 256, 144, 256, 1);
+  l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + 400; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400;
+  l1.counter = a.counters + 1; l1.hpre = a.h1pre; l1.out_post = a.dye1; l1.write_arena = 0; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
+  note_launch(1);
+  return launch_chain(p, a.B / 128, st);
+}
+
+}  // namespace mvae

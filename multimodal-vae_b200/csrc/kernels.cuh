@@ -138,4 +138,69 @@ int launch_poe_backward(int mode, int prior, float eps, int M, long long B, int 
                         const float* mask, const float* d_out_mu, const float* d_out_logvar, float* d_mu,
                         float* d_logvar, cudaStream_t st);
 
+// ---- chain.cu: slab-persistent layer chains of the MNIST step (bf16).  All pointers are device pointers; weights are
+// the bf16 mirror, biases / BatchNorm parameters fp32; statistics buffers are [2][G][F] (sum | sumsq resp. s0 | s1) inside
+// the zeroed accumulator region of the step workspace; counters are zeroed grid-barrier arrival counters.
+bool chain_supported(int B, int G, int n);
+struct ChainEncFwd {
+  int B = 0, n = 0, bn_updates = 1;
+  const __nv_bfloat16* image = nullptr;
+  const __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+  const float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
+  const float *gamma1 = nullptr, *beta1 = nullptr, *gamma2 = nullptr, *beta2 = nullptr;
+  float *st1 = nullptr, *st2 = nullptr, *sv1 = nullptr, *sv2 = nullptr;
+  float *rm1 = nullptr, *rv1 = nullptr, *rm2 = nullptr, *rv2 = nullptr;
+  unsigned int* counters = nullptr;   // [2]
+  __nv_bfloat16 *h1pre = nullptr, *h1 = nullptr, *h2pre = nullptr, *h2 = nullptr;
+  float* enc = nullptr;               // [B, 2n]
+  unsigned int* err = nullptr;
+};
+struct ChainDecFwd {
+  int B = 0, n = 0, G = 0;
+  const __nv_bfloat16* z = nullptr;   // [G*B, n]
+  const __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+  const float *b1 = nullptr, *b2 = nullptr, *b3 = nullptr;
+  const float *gamma1 = nullptr, *beta1 = nullptr, *gamma2 = nullptr, *beta2 = nullptr;
+  float *st1 = nullptr, *st2 = nullptr, *sv1 = nullptr, *sv2 = nullptr;
+  float *rm1 = nullptr, *rv1 = nullptr, *rm2 = nullptr, *rv2 = nullptr;
+  unsigned int* counters = nullptr;   // [6]
+  __nv_bfloat16 *g1pre = nullptr, *g1 = nullptr, *g2pre = nullptr, *g2 = nullptr, *dlog = nullptr, *probs = nullptr;
+  const __nv_bfloat16* image = nullptr;  // [B, 784] BCE target
+  float bce_scale[3] = {0, 0, 0};
+  float* loss = nullptr;              // [G] +=
+  float* dbias3 = nullptr;            // [784] += (null: no backward)
+  unsigned int* err = nullptr;
+};
+struct ChainDecBwd {
+  int B = 0, n = 0, G = 0;
+  const __nv_bfloat16* dlog = nullptr;
+  const __nv_bfloat16 *w1 = nullptr, *w2 = nullptr, *w3 = nullptr;
+  const float *gamma1 = nullptr, *beta1 = nullptr, *gamma2 = nullptr, *beta2 = nullptr;
+  float *sb1 = nullptr, *sb2 = nullptr;
+  float *sv1 = nullptr, *sv2 = nullptr;
+  unsigned int* counters = nullptr;   // [6]
+  const __nv_bfloat16 *g1pre = nullptr, *g2pre = nullptr;
+  __nv_bfloat16 *dy2 = nullptr, *dy1 = nullptr;
+  float* dz = nullptr;                // [G*B, n]
+  float *dgamma1 = nullptr, *dbeta1 = nullptr, *dgamma2 = nullptr, *dbeta2 = nullptr;
+  unsigned int* err = nullptr;
+};
+struct ChainEncBwd {
+  int B = 0, n = 0;
+  const __nv_bfloat16* denc = nullptr;  // [B, 2n]
+  const __nv_bfloat16 *w2 = nullptr, *w3 = nullptr;
+  const float *gamma1 = nullptr, *beta1 = nullptr, *gamma2 = nullptr, *beta2 = nullptr;
+  float *sb1 = nullptr, *sb2 = nullptr;
+  float *sv1 = nullptr, *sv2 = nullptr;
+  unsigned int* counters = nullptr;   // [2]
+  const __nv_bfloat16 *h1pre = nullptr, *h2pre = nullptr;
+  __nv_bfloat16 *dye2 = nullptr, *dye1 = nullptr;
+  float *dgamma1 = nullptr, *dbeta1 = nullptr, *dgamma2 = nullptr, *dbeta2 = nullptr;
+  unsigned int* err = nullptr;
+};
+int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st);
+int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st);
+int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st);
+int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st);
+
 }  // namespace mvae

@@ -125,7 +125,7 @@ struct Plan {
   long long st_e1, st_e2, st_d1, st_d2, st_t1;          // forward BN sums: [2][groups][F]
   long long sb_e1, sb_e2, sb_d1, sb_d2, sb_t1;          // backward BN sums
   long long losses;                                      // [3][kMaxGroups]: bce, ce, kl
-  long long bars;                                        // grid-barrier counters of the fused-BatchNorm GEMMs [8][2] (uint)
+  long long bars;                                        // grid-barrier arrival counters (uint): [0..15] the chain kernels' BatchNorm barriers, [31] their time-out flag
   long long d_txt_table;                                 // [10][2n]
   // saved statistics
   long long sv_e1, sv_e2, sv_d1, sv_d2;                  // [2][groups][F]: mean, rstd
@@ -160,7 +160,7 @@ Plan make_plan(int B, int n, int dtype_code) {
   p.sb_e1 = acc(2 * 400); p.sb_e2 = acc(2 * 200);
   p.sb_d1 = acc(2 * G * 200); p.sb_d2 = acc(2 * G * 400); p.sb_t1 = acc(2 * G * 10);
   p.losses = acc(3 * G);
-  p.bars = acc(16);
+  p.bars = acc(32);
   p.d_txt_table = acc(10 * 2 * n);
   p.acc_floats = f;
   off += f * 4;
@@ -446,6 +446,11 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
                "mnist_step: phase 2 needs the saved recon_image probabilities");
   const bool decode_only = a->z_in != nullptr;
   if (decode_only) n_img = n_txt = 0;  // latents are given: no encoders, no PoE
+  // bf16 training steps whose slabs are whole and co-resident run the slab-persistent chain kernels (chain.cu): one launch
+  // per encoder / decoder direction instead of a GEMM + BatchNorm launch per layer.  MVAE_CHAIN=0 restores the per-layer path.
+  static const int chain_env = env_int("MVAE_CHAIN", 1);
+  const bool use_chain = chain_env != 0 && a->dtype == MVAE_DT_BF16 && training && bwd && !module_bwd && !decode_only &&
+                         chain_supported(B, G, n);
 
   const Ptrs W{static_cast<char*>(a->workspace)};
   g_x3.a = x3 ? W.at<void>(P.x3_a) : nullptr;
@@ -485,6 +490,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   float* sv_e1 = W.at<float>(P.sv_e1); float* sv_e2 = W.at<float>(P.sv_e2);
   float* sv_d1 = W.at<float>(P.sv_d1); float* sv_d2 = W.at<float>(P.sv_d2);
   float* losses = W.at<float>(P.losses);
+  unsigned int* bars = W.at<unsigned int>(P.bars);
   const float mom = 0.1f, bn_eps = 1e-5f;
 
   // ================================================================ forward
@@ -505,7 +511,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   const bool fuse_enc = fuse_env != 0 && training;
   static const int epi_fuse_env = env_int("MVAE_FUSE_BN_EPI", 0);  // producer-side fusion (grid barrier in the GEMM epilogue): measured +-0
   const bool epi_fuse = epi_fuse_env != 0 && training && !fuse_enc;
-  unsigned int* bars = W.at<unsigned int>(P.bars);
   const bool fuse_dec = fuse_enc && (G == 1 || B % 128 == 0);
   auto make_atf = [&](float* sums, int F, int groups, int rpg, int nupd, const char* bn, float* sv, void* out) {
     GemmATransform t;
@@ -521,7 +526,27 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     t.out = out;
     return t;
   };
-  if (n_img > 0) {
+  unsigned int* chain_err = bars + 31;
+  auto wb = [&](const char* name) -> const __nv_bfloat16* { return static_cast<const __nv_bfloat16*>(a->params_bf16) + L.find(name); };
+  if (n_img > 0 && use_chain && fwd) {
+    ChainEncFwd ce;
+    ce.B = B; ce.n = n; ce.bn_updates = n_img;
+    ce.image = static_cast<const __nv_bfloat16*>(a->image);
+    ce.w1 = wb("image_encoder.net.0.weight"); ce.w2 = wb("image_encoder.net.3.weight"); ce.w3 = wb("image_encoder.net.6.weight");
+    ce.b1 = pf("image_encoder.net.0.bias"); ce.b2 = pf("image_encoder.net.3.bias"); ce.b3 = pf("image_encoder.net.6.bias");
+    ce.gamma1 = pf("image_encoder.net.1.weight"); ce.beta1 = pf("image_encoder.net.1.bias");
+    ce.gamma2 = pf("image_encoder.net.4.weight"); ce.beta2 = pf("image_encoder.net.4.bias");
+    ce.st1 = st_e1; ce.st2 = st_e2; ce.sv1 = sv_e1; ce.sv2 = sv_e2;
+    ce.rm1 = bf("image_encoder.net.1.running_mean"); ce.rv1 = bf("image_encoder.net.1.running_var");
+    ce.rm2 = bf("image_encoder.net.4.running_mean"); ce.rv2 = bf("image_encoder.net.4.running_var");
+    ce.counters = bars + 0;
+    ce.h1pre = W.at<__nv_bfloat16>(P.h1pre); ce.h1 = W.at<__nv_bfloat16>(P.h1);
+    ce.h2pre = W.at<__nv_bfloat16>(P.h2pre); ce.h2 = W.at<__nv_bfloat16>(P.h2);
+    ce.enc = W.at<float>(P.enc);
+    ce.err = chain_err;
+    MVAE_STEP(launch_chain_enc_fwd(ce, st), "chain_enc_fwd");
+  }
+  if (n_img > 0 && !use_chain) {
     // ImageEncoder (mnist/model.py:99-117), once for all terms that use it
     // BatchNorm+ReLU applied by the producing GEMM (grid barrier + second pass over the on-chip tile) when the whole
     // grid is co-resident; otherwise the GEMM publishes the sums and launch_bn_forward applies them.
@@ -598,6 +623,31 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (dep(st, s2)) return 1;  // fork: text decoder beside the image decoder
   if (fwd) MVAE_STEP(launch_textdec(td, s2), "launch_textdec");
 
+  bool bce_direct = false;
+  if (use_chain && fwd) {
+    ChainDecFwd cd;
+    cd.B = B; cd.n = n; cd.G = G;
+    cd.z = W.at<__nv_bfloat16>(P.z);
+    cd.w1 = wb("image_decoder.net.0.weight"); cd.w2 = wb("image_decoder.net.3.weight"); cd.w3 = wb("image_decoder.net.6.weight");
+    cd.b1 = pf("image_decoder.net.0.bias"); cd.b2 = pf("image_decoder.net.3.bias"); cd.b3 = pf("image_decoder.net.6.bias");
+    cd.gamma1 = pf("image_decoder.net.1.weight"); cd.beta1 = pf("image_decoder.net.1.bias");
+    cd.gamma2 = pf("image_decoder.net.4.weight"); cd.beta2 = pf("image_decoder.net.4.bias");
+    cd.st1 = st_d1; cd.st2 = st_d2; cd.sv1 = sv_d1; cd.sv2 = sv_d2;
+    cd.rm1 = bf("image_decoder.net.1.running_mean"); cd.rv1 = bf("image_decoder.net.1.running_var");
+    cd.rm2 = bf("image_decoder.net.4.running_mean"); cd.rv2 = bf("image_decoder.net.4.running_var");
+    cd.counters = bars + 2;
+    cd.g1pre = W.at<__nv_bfloat16>(P.g1pre); cd.g1 = W.at<__nv_bfloat16>(P.g1);
+    cd.g2pre = W.at<__nv_bfloat16>(P.g2pre); cd.g2 = W.at<__nv_bfloat16>(P.g2);
+    cd.dlog = W.at<__nv_bfloat16>(P.dlog);
+    cd.probs = static_cast<__nv_bfloat16*>(a->out_recon_image);
+    cd.image = static_cast<const __nv_bfloat16*>(a->image);
+    for (int t = 0; t < G; ++t) cd.bce_scale[t] = a->lambda_image[t] / (static_cast<float>(B) * 784.f);
+    cd.loss = losses;
+    cd.dbias3 = gf("image_decoder.net.6.bias");
+    cd.err = chain_err;
+    MVAE_STEP(launch_chain_dec_fwd(cd, st), "chain_dec_fwd");
+  }
+  if (!use_chain) {
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
   FusedBn fb_d1;
   fb_d1.Y = W.at<void>(P.g1); fb_d1.gamma = pf("image_decoder.net.1.weight"); fb_d1.beta = pf("image_decoder.net.1.bias");
@@ -632,7 +682,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
-  bool bce_direct = false;
   {
     // last Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70) in one kernel
     GemmDesc g;
@@ -657,6 +706,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     stamp_x3(g);
     if (fwd) MVAE_STEP(launch_gemm(g, st), "gemm_fwd_bce:image_decoder.net.6.weight");
   }
+  }  // !use_chain
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist
   if (fwd && bwd && bwd_dec && !module_bwd && bce_direct)
     if (mvae_col_stats(dt, W.at<void>(P.dlog), R, 784, 784, 0, gf("image_decoder.net.6.bias"), nullptr, s2)) return 1;
@@ -675,6 +725,28 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       MVAE_STEP(launch_textdec(td, st), "launch_textdec(bwd)");
       if (dep(st, s2)) return 1;
     }
+    if (use_chain) {
+      // ---- image decoder: the whole dgrad / ReLU / BatchNorm-backward chain in one launch; weight gradients beside it
+      MVAE_STEP(gemm_wgrad(dt, R, 784, 400, W.at<void>(P.dlog), W.at<void>(P.g2), gf("image_decoder.net.6.weight"), s2), "gemm_wgrad:image_decoder.net.6.weight#16");
+      ChainDecBwd cb;
+      cb.B = B; cb.n = n; cb.G = G;
+      cb.dlog = W.at<__nv_bfloat16>(P.dlog);
+      cb.w1 = wb("image_decoder.net.0.weight"); cb.w2 = wb("image_decoder.net.3.weight"); cb.w3 = wb("image_decoder.net.6.weight");
+      cb.gamma1 = pf("image_decoder.net.1.weight"); cb.beta1 = pf("image_decoder.net.1.bias");
+      cb.gamma2 = pf("image_decoder.net.4.weight"); cb.beta2 = pf("image_decoder.net.4.bias");
+      cb.sb1 = sb_d1; cb.sb2 = sb_d2; cb.sv1 = sv_d1; cb.sv2 = sv_d2;
+      cb.counters = bars + 8;
+      cb.g1pre = W.at<__nv_bfloat16>(P.g1pre); cb.g2pre = W.at<__nv_bfloat16>(P.g2pre);
+      cb.dy2 = W.at<__nv_bfloat16>(P.dy2); cb.dy1 = W.at<__nv_bfloat16>(P.dy1);
+      cb.dz = W.at<float>(P.dz);
+      cb.dgamma1 = gf("image_decoder.net.1.weight"); cb.dbeta1 = gf("image_decoder.net.1.bias");
+      cb.dgamma2 = gf("image_decoder.net.4.weight"); cb.dbeta2 = gf("image_decoder.net.4.bias");
+      cb.err = chain_err;
+      MVAE_STEP(launch_chain_dec_bwd(cb, st), "chain_dec_bwd");
+      if (dep(st, s2)) return 1;
+      MVAE_STEP(gemm_wgrad(dt, R, 400, 200, W.at<void>(P.dy2), W.at<void>(P.g1), gf("image_decoder.net.3.weight"), s2), "gemm_wgrad:image_decoder.net.3.weight#19");
+      MVAE_STEP(gemm_wgrad(dt, R, 200, n, W.at<void>(P.dy1), W.at<void>(P.z), gf("image_decoder.net.0.weight"), s2), "gemm_wgrad:image_decoder.net.0.weight#22");
+    } else {
     // ---- image decoder
     MVAE_STEP(gemm_dgrad(dt, R, 400, 784, W.at<void>(P.dlog), wop("image_decoder.net.6.weight"), W.at<void>(P.dy2), dt,
                    W.at<void>(P.g2pre), sv_d2, sv_d2 + G * 400, pf("image_decoder.net.4.weight"),
@@ -695,6 +767,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
                    nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1 << 30, st), "gemm_dgrad:image_decoder.net.0.weight#21");
     if (dep(st, s2)) return 1;
     MVAE_STEP(gemm_wgrad(dt, R, 200, n, W.at<void>(P.dy1), W.at<void>(P.z), gf("image_decoder.net.0.weight"), s2), "gemm_wgrad:image_decoder.net.0.weight#22");
+    }  // !use_chain
 
     // ---- tail backward (text decoder front + reparametrize + KL + PoE)
     ta.dz = W.at<float>(P.dz);
@@ -721,7 +794,27 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       MVAE_STEP(launch_textenc_backward(te, s2), "launch_textenc_backward");
     }
     // ---- image encoder
-    if (n_img > 0) {
+    if (n_img > 0 && use_chain) {
+      MVAE_STEP(gemm_wgrad(dt, B, 2 * n, 200, W.at<void>(P.denc), W.at<void>(P.h2), gf("image_encoder.net.6.weight"), s2), "gemm_wgrad:image_encoder.net.6.weight#26");
+      ChainEncBwd cb;
+      cb.B = B; cb.n = n;
+      cb.denc = W.at<__nv_bfloat16>(P.denc);
+      cb.w2 = wb("image_encoder.net.3.weight"); cb.w3 = wb("image_encoder.net.6.weight");
+      cb.gamma1 = pf("image_encoder.net.1.weight"); cb.beta1 = pf("image_encoder.net.1.bias");
+      cb.gamma2 = pf("image_encoder.net.4.weight"); cb.beta2 = pf("image_encoder.net.4.bias");
+      cb.sb1 = sb_e1; cb.sb2 = sb_e2; cb.sv1 = sv_e1; cb.sv2 = sv_e2;
+      cb.counters = bars + 14;
+      cb.h1pre = W.at<__nv_bfloat16>(P.h1pre); cb.h2pre = W.at<__nv_bfloat16>(P.h2pre);
+      cb.dye2 = W.at<__nv_bfloat16>(P.dye2); cb.dye1 = W.at<__nv_bfloat16>(P.dye1);
+      cb.dgamma1 = gf("image_encoder.net.1.weight"); cb.dbeta1 = gf("image_encoder.net.1.bias");
+      cb.dgamma2 = gf("image_encoder.net.4.weight"); cb.dbeta2 = gf("image_encoder.net.4.bias");
+      cb.err = chain_err;
+      MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
+      if (dep(st, s2)) return 1;
+      MVAE_STEP(gemm_wgrad(dt, B, 200, 400, W.at<void>(P.dye2), W.at<void>(P.h1), gf("image_encoder.net.3.weight"), s2), "gemm_wgrad:image_encoder.net.3.weight#29");
+      MVAE_STEP(gemm_wgrad(dt, B, 400, 784, W.at<void>(P.dye1), a->image, gf("image_encoder.net.0.weight"), s2), "gemm_wgrad:image_encoder.net.0.weight#31");
+    }
+    if (n_img > 0 && !use_chain) {
       MVAE_STEP(gemm_dgrad(dt, B, 200, 2 * n, W.at<void>(P.denc), wop("image_encoder.net.6.weight"), W.at<void>(P.dye2), dt,
                      W.at<void>(P.h2pre), sv_e2, sv_e2 + 200, pf("image_encoder.net.4.weight"),
                      pf("image_encoder.net.4.bias"), sb_e2, sb_e2 + 200, 1 << 30, st), "gemm_dgrad:image_encoder.net.6.weight#25");

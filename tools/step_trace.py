@@ -112,6 +112,11 @@ def run_device(state, image, text, noises, n, precision):
     dl, _ = tr.step(image.cuda(), text.cuda(), eps=torch.stack(noises).cuda(), update=False)
     torch.cuda.synchronize()
     B = image.shape[0]
+    try:
+        bars = m.debug_buffer("bars", B, (32,), torch.int32).cpu().tolist()
+        print("  chain barrier counters %s  time-out flag 0x%x" % (bars[:16], bars[31] & 0xffffffff))
+    except Exception as e:  # noqa: BLE001
+        print("  (no barrier counters: %s)" % e)
     fwd, bwd = device_buffers(m, B)
     grads = {k: p.grad.detach().float().cpu().clone() for k, p in m.named_parameters()}
     return fwd, bwd, grads, dl[:, 0].cpu().tolist()
