@@ -77,6 +77,9 @@ int mvae_gemm(const mvae_gemm_args* args, void* stream);
 /* Bring-up: GEMM launches whose epilogue kind (0 store, 1 atomic, 2 BCE, 3 dgrad-BN) equals epilogue_kind write
  * eight %globaltimer stamps per CTA into the device buffer (NULL switches it off). */
 void mvae_debug_gemm_times(void* device_int64_buffer, int epilogue_kind);
+/* Bring-up: the slab-persistent chain kernels of the MNIST step (csrc/chain.cu) write %globaltimer stamps of their
+ * producer / MMA / epilogue phases into a device buffer of 4 kernels x 148 CTAs x 32 int64 (NULL switches it off). */
+void mvae_debug_chain_times(void* device_int64_buffer);
 
 /* ------------------------------------------------------------------------------------------
  * MNIST MVAE (mnist/model.py:14-170).  All parameters live in ONE flat fp32 buffer (so that the data-

@@ -7,6 +7,7 @@
 
 #include "../../include/mvae_b200.h"
 #include "common.cuh"
+#include "kernels.cuh"
 
 namespace mvae {
 
@@ -51,6 +52,8 @@ int mvae_device_check(int device) {
                prop.minor);
   return 0;
 }
+
+void mvae_debug_chain_times(void* device_int64_buffer) { set_chain_debug_times(device_int64_buffer); }
 
 void mvae_debug_gemm_times(void* device_int64_buffer, int epilogue_kind) {
   set_gemm_debug_times(device_int64_buffer, epilogue_kind);

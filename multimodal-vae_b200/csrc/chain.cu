@@ -36,10 +36,12 @@ constexpr int kCEpi = 256;
 constexpr int kPanel = 16384;                  // 128 rows x 128 B: one K-major SWIZZLE_128B panel (64 bf16 columns)
 constexpr int kArenaPanels = 7;                // 448 columns >= the widest resident activation (400)
 constexpr int kArena = kArenaPanels * kPanel;  // 114688
-constexpr int kRingBytes = 4 * 26624;          // weight ring behind the arena: 4 stages of 208 rows x 128 B
-constexpr int kMain = kArena + kRingBytes;     // 221184 = 3 x 73728 (the K = 784 layers use all of it as a 3-stage ring)
-constexpr int kTabFloats = 2432;               // per-layer coefficient / statistics tables
-constexpr int kChainSmem = 1024 + kMain + kTabFloats * 4;
+constexpr int kStage = 8 * 4096;                // the epilogue warps' staging tiles
+constexpr int kMainF = kArena + 3 * 26624 + kStage;   // forward kernels: [arena | 3-stage K-major weight ring | staging] = 227328
+constexpr int kTabOffF = kMainF;                // forward tables: 3 x 400 floats
+constexpr int kTabOffB = 221184;                // backward kernels: behind the 3 x 72 KB streamed-operand ring; 4 x 400 floats
+constexpr int kBarOff = kTabOffF + 4800;        // 232128: mbarriers + the TMEM base address
+constexpr int kChainSmem = kBarOff + 128;       // 232256 <= 232448 (227 KB), no static shared memory
 constexpr int kMaxPass = 8;
 constexpr int kMaxLayer = 3;
 constexpr int kMaxChunk = 4;
@@ -111,6 +113,10 @@ struct alignas(64) CParams {
   int init_tm, init_panels;  // resident A loaded by TMA at kernel start (z / d_enc), -1: none
   float momentum, eps;
   unsigned int* err;      // device flag: non-zero = a wait timed out (bring-up)
+  long long* dbg;         // bring-up: [ctas][32] %globaltimer stamps (mvae_debug_chain_times), or null
+  int stg_off;            // byte offset of the epilogue warps' staging tiles (8 x 4 KB)
+  int tab_off;            // byte offset of the coefficient tables
+  int dbg_flags;          // bring-up (MVAE_CHAIN_DEBUG): 1 no statistics atomics, 2 no global stores, 4 no TMEM loads, 8 no global loads
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -201,19 +207,6 @@ __device__ __forceinline__ void arena_store16(uint32_t arena, int row, int col, 
   ptx::sts128(base + (((cc + 1) ^ (row & 7)) << 4), w[4], w[5], w[6], w[7]);
 }
 
-// 16 bf16 of one global row (n_valid of them in range, a multiple of 8)
-__device__ __forceinline__ void gstore16(__nv_bfloat16* dst, int n_valid, const uint32_t (&w)[8]) {
-  if (n_valid >= 8) *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-  if (n_valid >= 16) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-}
-__device__ __forceinline__ void gload16(const __nv_bfloat16* src, int n_valid, float (&x)[16]) {
-  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-  if (n_valid >= 8) a = __ldg(reinterpret_cast<const uint4*>(src));
-  if (n_valid >= 16) b = __ldg(reinterpret_cast<const uint4*>(src + 8));
-  unpack8(a, x);
-  unpack8(b, x + 8);
-}
-
 // Grid barrier of one statistics group: arrive, then wait until all `expected` CTAs of the group have arrived.
 // Called by all 256 epilogue threads after their global atomics.  A lost CTA cannot hang the GPU: after ~2 s the wait
 // gives up and flags the error (results are then garbage, which the flag reports).
@@ -255,18 +248,41 @@ __device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned
   __threadfence();
 }
 
+// ---------------------------------------------------------------- the epilogue's transposing tile
+// tcgen05.ld hands every lane one accumulator ROW, but everything the epilogue has to do is cheaper per COLUMN: the
+// BatchNorm / bias coefficients are per column, the statistics are column sums, and global memory wants whole 128-byte
+// lines per row.  So each epilogue warp owns a 4 KB fp32 tile (16 rows x 64 columns, 16-byte chunk c of row r stored at
+// chunk c ^ r, conflict-free both ways): half a warp's rows go in raw, straight from TMEM, and come back out with lane
+// (rsel, c) holding columns 4c..4c+3 of rows rsel, rsel+2, ... - its coefficients are then loop constants, column sums
+// accumulate in registers (one shuffle at the end), and 16 lanes cover one row's 64 columns for every global load / store.
+__device__ __forceinline__ uint32_t tile_w(uint32_t tile, int r, int c) { return tile + r * 256 + (((c ^ r) & 15) << 4); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float4 tab4(const float* t) { return *reinterpret_cast<const float4*>(t); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float v[4];
+  ptx::lds128(addr, v);
+  return make_float4(v[0], v[1], v[2], v[3]);
+}
+// four bf16 (8 bytes) of a K-major SWIZZLE_128B arena row: columns col0..col0+3 (col0 % 4 == 0) of slab row `row`
+__device__ __forceinline__ void arena_store4(uint32_t arena, int row, int col0, uint32_t w0, uint32_t w1) {
+  const int panel = col0 >> 6, cc = (col0 & 63) >> 3;
+  const uint32_t addr = arena + panel * kPanel + row * 128 + ((cc ^ (row & 7)) << 4) + ((col0 & 4) << 1);
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w0), "r"(w1) : "memory");
+}
+
 __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_constant__ CParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* tab = reinterpret_cast<float*>(smem + kMain);
-  __shared__ __align__(8) uint64_t full_bar[4];
-  __shared__ __align__(8) uint64_t empty_bar[4];
-  __shared__ __align__(8) uint64_t acc_full[2];
-  __shared__ __align__(8) uint64_t acc_empty[2];
-  __shared__ __align__(8) uint64_t a_tma_bar;
-  __shared__ __align__(8) uint64_t a_epi_bar;
-  __shared__ uint32_t tmem_slot;
-  __shared__ float s_loss;
+  // No static shared memory: the dynamic window then starts 1024-byte aligned (checked below), which the SWIZZLE_128B
+  // tiles need, and every byte of the 227 KB is planned: [arena | weight ring | staging tiles | tables | barriers].
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* tab = reinterpret_cast<float*>(smem + p.tab_off);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* empty_bar = full_bar + 4;
+  uint64_t* acc_full = full_bar + 8;
+  uint64_t* acc_empty = full_bar + 10;
+  uint64_t* a_tma_bar = full_bar + 12;
+  uint64_t* a_epi_bar = full_bar + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -274,8 +290,17 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   const unsigned int slabs_per_group = static_cast<unsigned int>(p.rows_per_group / 128);
   const bool group_leader = (m0 % p.rows_per_group) == 0;
   const uint32_t smem_u = ptx::smem_u32(smem);
+  long long* dbg = p.dbg != nullptr ? p.dbg + 32ll * blockIdx.x : nullptr;
+  auto stamp = [&](int slot) {
+    if (dbg != nullptr) dbg[slot] = static_cast<long long>(gtimer());
+  };
 
   if (threadIdx.x == 0) {
+    stamp(0);
+    if ((smem_u & 1023u) != 0u) {
+      if (p.err != nullptr) atomicExch(p.err, 0xA11Au);
+      asm volatile("trap;");
+    }
     for (int i = 0; i < 5; ++i) ptx::prefetch_tmap(&p.tm[i]);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
@@ -285,45 +310,44 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       ptx::mbar_init(&acc_full[b], 1);
       ptx::mbar_init(&acc_empty[b], kCEpi);
     }
-    ptx::mbar_init(&a_tma_bar, 1);
-    ptx::mbar_init(&a_epi_bar, kCEpi);
+    ptx::mbar_init(a_tma_bar, 1);
+    ptx::mbar_init(a_epi_bar, kCEpi);
     ptx::fence_mbar_init();
-    s_loss = 0.f;
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
+  // All per-slot / per-buffer phase bookkeeping below lives in BIT MASKS, never in indexed arrays: with the whole
+  // shared-memory carve-out taken there is almost no L1, and a local-memory array costs an L2 round trip per access.
   if (warp == 0) {
     // =================================================================== TMA producer
     if (lane == 0) {
       if (p.init_tm >= 0) {
-        ptx::mbar_expect_tx(&a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel));
-        for (int pn = 0; pn < p.init_panels; ++pn) ptx::tma_load_2d(smem + pn * kPanel, &p.tm[p.init_tm], &a_tma_bar, pn * 64, m0);
+        ptx::mbar_expect_tx(a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel));
+        for (int pn = 0; pn < p.init_panels; ++pn) ptx::tma_load_2d(smem + pn * kPanel, &p.tm[p.init_tm], a_tma_bar, pn * 64, m0);
       }
-      uint32_t fills[4] = {0, 0, 0, 0};
-      int cur_cfg = -1, cnt = 0;
+      uint32_t fill_par = 0, fill_any = 0;   // bit s: parity of the number of fills of slot s / slot ever filled
+      int cur_cfg = -1, s = 0;
       for (int ip = 0; ip < p.n_pass; ++ip) {
         const CPass& ps = p.pass[ip];
         const CRing rg = p.ring[ps.cfg];
         if (ps.cfg != cur_cfg) {
           // the two ring geometries overlap in shared memory: everything in flight must have been consumed
-          for (int s = 0; s < 4; ++s)
-            if (fills[s] > 0) mbar_wait_b(&empty_bar[s], (fills[s] - 1) & 1, p.err, 0x100u + s);
+          for (int t = 0; t < 4; ++t)
+            if ((fill_any >> t) & 1u) mbar_wait_b(&empty_bar[t], ((fill_par >> t) & 1u) ^ 1u, p.err, 0x100u + t);
           cur_cfg = ps.cfg;
-          cnt = 0;
+          s = 0;
         }
         uint32_t bytes = ps.a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u;
         for (int c = 0; c < ps.n_chunks; ++c) bytes += static_cast<uint32_t>(ps.c_bytes[c]);
         for (int kp = 0; kp < ps.k_panels; ++kp) {
-          const int s = cnt % rg.stages;
-          ++cnt;
-          mbar_wait_b(&empty_bar[s], (fills[s] & 1) ^ 1, p.err, 0x110u + s);
+          mbar_wait_b(&empty_bar[s], ((fill_par >> s) & 1u) ^ 1u, p.err, 0x110u + s);
           ptx::mbar_expect_tx(&full_bar[s], bytes);
           uint8_t* stage = smem + rg.base + s * rg.stage_bytes;
           if (ps.a_stream >= 0) ptx::tma_load_2d(stage, &p.tm[ps.a_stream], &full_bar[s], kp * 64, m0);
@@ -336,43 +360,46 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
                 ptx::tma_load_2d(bslot + ps.c_boff[c] + j * 8192, &p.tm[ps.b_tm], &full_bar[s], ps.c_n0[c] + j * 64, kp * 64);
             }
           }
-          ++fills[s];
+          fill_par ^= 1u << s;
+          fill_any |= 1u << s;
+          if (++s == rg.stages) s = 0;
         }
+        stamp(1 + ip);
       }
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      uint32_t uses[4] = {0, 0, 0, 0};
-      uint32_t acc_uses[2] = {0, 0};
+      uint32_t use_par = 0, acc_par = 0;   // bit s: parity of uses of ring slot s; bit b: parity of uses of accumulator b
       uint32_t n_tma_waits = 0, n_epi_waits = 0;
-      int cur_cfg = -1, cnt = 0;
+      int cur_cfg = -1, s = 0;
       for (int ip = 0; ip < p.n_pass; ++ip) {
         const CPass& ps = p.pass[ip];
         const CRing rg = p.ring[ps.cfg];
         if (ps.cfg != cur_cfg) {
           cur_cfg = ps.cfg;
-          cnt = 0;
+          s = 0;
         }
         if (ps.a_wait == 1) {
-          mbar_wait_b(&a_tma_bar, n_tma_waits & 1, p.err, 0x200u);
+          mbar_wait_b(a_tma_bar, n_tma_waits & 1, p.err, 0x200u);
           ++n_tma_waits;
         } else if (ps.a_wait == 2) {
-          mbar_wait_b(&a_epi_bar, n_epi_waits & 1, p.err, 0x201u);
+          mbar_wait_b(a_epi_bar, n_epi_waits & 1, p.err, 0x201u);
           ++n_epi_waits;
         }
-        for (int c = 0; c < ps.n_chunks; ++c) {
-          const int b = ps.c_buf[c];
-          mbar_wait_b(&acc_empty[b], (acc_uses[b] & 1) ^ 1, p.err, 0x210u + b);
-        }
+        const int nc = ps.n_chunks;
+        const int buf0 = ps.c_buf[0], buf1 = ps.c_buf[nc - 1];
+        mbar_wait_b(&acc_empty[buf0], ((acc_par >> buf0) & 1u) ^ 1u, p.err, 0x210u + buf0);
+        if (nc > 1) mbar_wait_b(&acc_empty[buf1], ((acc_par >> buf1) & 1u) ^ 1u, p.err, 0x210u + buf1);
         ptx::tc_fence_after();
-        uint32_t idesc[2];
-        for (int c = 0; c < ps.n_chunks; ++c) idesc[c] = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[c]);
+        const uint32_t idesc0 = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[0]);
+        const uint32_t idesc1 = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[nc - 1]);
+        const uint32_t boff0 = ps.c_boff[0], boff1 = ps.c_boff[nc - 1];
+        const uint32_t tm0 = tmem_base + ps.c_tmem[0], tm1 = tmem_base + ps.c_tmem[nc - 1];
+        const int b_mn = ps.b_mn;
         for (int kp = 0; kp < ps.k_panels; ++kp) {
-          const int s = cnt % rg.stages;
-          ++cnt;
-          mbar_wait_b(&full_bar[s], uses[s] & 1, p.err, 0x220u + s);
-          ++uses[s];
+          mbar_wait_b(&full_bar[s], (use_par >> s) & 1u, p.err, 0x220u + s);
+          use_par ^= 1u << s;
           ptx::tc_fence_after();
           const uint32_t stage = smem_u + rg.base + s * rg.stage_bytes;
           const uint32_t a_base = ps.a_stream >= 0 ? stage : smem_u + kp * kPanel;
@@ -380,80 +407,148 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           const int nks = (kp == ps.k_panels - 1) ? ps.last_ksteps : 4;
           for (int ks = 0; ks < nks; ++ks) {
             const uint64_t adesc = ptx::make_smem_desc(a_base + ks * 32, 16, 1024);
-            for (int c = 0; c < ps.n_chunks; ++c) {
-              const uint64_t bdesc = ps.b_mn ? ptx::make_smem_desc(bslot + ps.c_boff[c] + ks * 2048, 8192, 1024, 2)
-                                             : ptx::make_smem_desc(bslot + ps.c_boff[c] + ks * 32, 16, 1024);
-              ptx::umma<MVAE_BF16>(tmem_base + ps.c_tmem[c], adesc, bdesc, idesc[c], (kp | ks) != 0 ? 1u : 0u);
+            const uint32_t acc = (kp | ks) != 0 ? 1u : 0u;
+            const uint64_t bd0 = b_mn ? ptx::make_smem_desc(bslot + boff0 + ks * 2048, 8192, 1024, 2)
+                                      : ptx::make_smem_desc(bslot + boff0 + ks * 32, 16, 1024);
+            ptx::umma<MVAE_BF16>(tm0, adesc, bd0, idesc0, acc);
+            if (nc > 1) {
+              const uint64_t bd1 = b_mn ? ptx::make_smem_desc(bslot + boff1 + ks * 2048, 8192, 1024, 2)
+                                        : ptx::make_smem_desc(bslot + boff1 + ks * 32, 16, 1024);
+              ptx::umma<MVAE_BF16>(tm1, adesc, bd1, idesc1, acc);
             }
           }
           ptx::umma_commit(&empty_bar[s]);
+          if (++s == rg.stages) s = 0;
         }
-        for (int c = 0; c < ps.n_chunks; ++c) {
-          ptx::umma_commit(&acc_full[ps.c_buf[c]]);
-          ++acc_uses[ps.c_buf[c]];
+        ptx::umma_commit(&acc_full[buf0]);
+        acc_par ^= 1u << buf0;
+        if (nc > 1) {
+          ptx::umma_commit(&acc_full[buf1]);
+          acc_par ^= 1u << buf1;
         }
+        stamp(9 + ip);
       }
     }
   } else {
-    // =================================================================== epilogue (8 warps, one accumulator row per thread)
+    // =================================================================== epilogue (8 warps)
     const int et = threadIdx.x - 64;
     const int q = warp & 3;               // TMEM lane quarter this warp may read
-    const int h = (warp - 2) >> 2;        // the two warps of a quarter take alternate 16-column pieces
-    const int row = q * 32 + lane;
-    const long long grow = static_cast<long long>(m0) + row;
+    const int h = (warp - 2) >> 2;        // the two warps of a quarter take alternate 64-column blocks
+    const long long wrow0 = static_cast<long long>(m0) + q * 32;   // first global row of this warp
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t epi_uses[2] = {0, 0};
+    const uint32_t tile = smem_u + p.stg_off + (warp - 2) * 4096;  // this warp's transposing tile
+    const int rsel = lane >> 4, cq = lane & 15;                    // column phase: rows rsel + 2i, columns 4*cq .. 4*cq+3 of the block
+    uint32_t epi_par = 0;                 // bit b: parity of the accumulator-full phases consumed so far
     const float inv_cnt = 1.f / static_cast<float>(p.rows_per_group);
 
     for (int il = 0; il < p.n_layers; ++il) {
       const CLayer& L = p.layer[il];
       const int N = L.N;
       const int Npad = (N + 15) & ~15;
-      if (L.kind == CE_FWD_BN) {
-        float* s_bias = tab;
-        float* s_ca = tab + 800;
-        float* s_cb = tab + 1208;
-        float* s_s0 = tab + 1616;
-        float* s_s1 = tab + 2024;
-        for (int c = et; c < Npad; c += kCEpi) {
-          s_bias[c] = c < N ? L.bias[c] : 0.f;
-          s_s0[c] = 0.f;
-          s_s1[c] = 0.f;
-        }
-        bar_epi();
-        // ---- pass 1: pre-activations out, slab statistics
+      const int n_blocks = (Npad + 63) >> 6;
+      if (et == 0) stamp(17 + il * 4);
+      // TMEM column of layer column `col` (chunk boundaries are multiples of 16)
+      auto tmem_col = [&](int col) -> uint32_t {
+        uint32_t t = L.c_tmem[0] + col - L.c_n0[0];
+        if (L.n_chunks > 1 && col >= L.c_n0[1]) t = L.c_tmem[1] + col - L.c_n0[1];
+        if (L.n_chunks > 2 && col >= L.c_n0[2]) t = L.c_tmem[2] + col - L.c_n0[2];
+        if (L.n_chunks > 3 && col >= L.c_n0[3]) t = L.c_tmem[3] + col - L.c_n0[3];
+        return t_row + t;
+      };
+      // wait for every chunk of the layer (BatchNorm layers: the statistics need all of them anyway)
+      auto wait_all_chunks = [&]() {
+        uint32_t seen = 0;
         for (int ci = 0; ci < L.n_chunks; ++ci) {
           const int b = L.c_buf[ci];
-          mbar_wait_b(&acc_full[b], (epi_uses[b] + 0) & 1, p.err, 0x300u + il * 16 + ci);
-          ptx::tc_fence_after();
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            ptx::tmem_ld_wait();
-            float x[16], sq[16];
-            uint32_t w[8];
+          if ((seen >> b) & 1u) continue;
+          seen |= 1u << b;
+          mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
+        }
+        ptx::tc_fence_after();
+      };
+      auto release_all_chunks = [&]() {
+        ptx::tc_fence_before();
+        uint32_t seen = 0;
+        for (int ci = 0; ci < L.n_chunks; ++ci) {
+          const int b = L.c_buf[ci];
+          if ((seen >> b) & 1u) continue;
+          seen |= 1u << b;
+          ptx::mbar_arrive(&acc_empty[b]);
+          epi_par ^= 1u << b;
+        }
+      };
+      // this lane's accumulator row of block `blk` (64 columns, zero beyond the layer), raw from TMEM
+      auto load_block = [&](int blk, uint32_t (&v)[64]) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + s_bias[col + j];
+        for (int pi = 0; pi < 4; ++pi) {
+          const int col = blk * 64 + pi * 16;
+          uint32_t t[16];
+          if (col < Npad && !(p.dbg_flags & 4)) {
+            ptx::tmem_ld16(tmem_col(col), t);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
-            gstore16(L.out_pre + grow * N + col, N - col, w);
+            for (int j = 0; j < 16; ++j) t[j] = 0u;
+          }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sq[j] = x[j] * x[j];
-            const float a0 = colsum16(x, lane);
-            const float a1 = colsum16(sq, lane);
-            const int c = col + colperm(lane);
-            if (c < N) atomicAdd((lane & 1) ? &s_s1[c] : &s_s0[c], (lane & 1) ? a1 : a0);
+          for (int j = 0; j < 16; ++j) v[pi * 16 + j] = t[j];
+        }
+        ptx::tmem_ld_wait();
+      };
+      // rows [16*half, 16*half+16) of the warp go into the tile
+      auto deposit = [&](int half, const uint32_t (&v)[64]) {
+        if (rsel == half) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) ptx::sts128(tile_w(tile, cq, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        __syncwarp();
+      };
+
+      if (L.kind == CE_FWD_BN) {
+        float* s_bias = tab;
+        float* s_ca = tab + 400;
+        float* s_cb = tab + 800;
+        for (int c = et; c < 400; c += kCEpi) s_bias[c] = c < N ? L.bias[c] : 0.f;
+        bar_epi();
+        wait_all_chunks();
+        // ---- pass 1: pre-activations out (bf16), slab statistics straight into the global accumulators
+        for (int blk = h; blk < n_blocks; blk += 2) {
+          uint32_t v[64];
+          load_block(blk, v);
+          const int col0 = blk * 64 + 4 * cq;
+          const bool live = col0 < N;
+          const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (live) {
+              __nv_bfloat16* dst = L.out_pre + (wrow0 + half * 16 + rsel) * N + col0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                const float x0 = a.x + bs.x, x1 = a.y + bs.y, x2 = a.z + bs.z, x3 = a.w + bs.w;
+                s0[0] += x0; s0[1] += x1; s0[2] += x2; s0[3] += x3;
+                s1[0] = fmaf(x0, x0, s1[0]); s1[1] = fmaf(x1, x1, s1[1]); s1[2] = fmaf(x2, x2, s1[2]); s1[3] = fmaf(x3, x3, s1[3]);
+                if (!(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+              }
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 16);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+          }
+          if (live) {
+            float* dst = (rsel ? L.stat1 : L.stat0) + grp * N + col0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (!(p.dbg_flags & 1)) atomicAdd(dst + k, rsel ? s1[k] : s0[k]);
           }
         }
-        bar_epi();
-        for (int c = et; c < N; c += kCEpi) {
-          atomicAdd(L.stat0 + grp * N + c, s_s0[c]);
-          atomicAdd(L.stat1 + grp * N + c, s_s1[c]);
-        }
+        if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
-        for (int c = et; c < Npad; c += kCEpi) {
+        if (et == 0) stamp(19 + il * 4);
+        for (int c = et; c < 400; c += kCEpi) {
           float a_ = 0.f, b_ = 0.f;
           if (c < N) {
             const float mean = __ldcg(L.stat0 + grp * N + c) * inv_cnt;
@@ -471,42 +566,45 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         bar_epi();
         // ---- pass 2: BatchNorm + ReLU from TMEM -> next layer's A operand (+ the copy the weight gradient needs)
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            ptx::tmem_ld_wait();
-            uint32_t w[8];
+        for (int blk = h; blk < n_blocks; blk += 2) {
+          uint32_t v[64];
+          load_block(blk, v);
+          const int col0 = blk * 64 + 4 * cq;
+          const bool live = col0 < N, padded = col0 < Npad;
+          const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 ca = padded ? tab4(s_ca + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 cb = padded ? tab4(s_cb + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float x0 = bf16_round(__uint_as_float(v[2 * j]) + s_bias[col + 2 * j]);       // what out_pre holds
-              const float x1 = bf16_round(__uint_as_float(v[2 * j + 1]) + s_bias[col + 2 * j + 1]);
-              const float y0 = fmaxf(fmaf(s_ca[col + 2 * j], x0, s_cb[col + 2 * j]), 0.f);
-              const float y1 = fmaxf(fmaf(s_ca[col + 2 * j + 1], x1, s_cb[col + 2 * j + 1]), 0.f);
-              w[j] = pack_bf16(y0, y1);
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (padded) {
+              __nv_bfloat16* dst = L.out_post + (wrow0 + half * 16 + rsel) * N + col0;
+              const int srow = q * 32 + half * 16 + rsel;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                const float x0 = bf16_round(a.x + bs.x), x1 = bf16_round(a.y + bs.y);   // what out_pre holds
+                const float x2 = bf16_round(a.z + bs.z), x3 = bf16_round(a.w + bs.w);
+                const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
+                const uint32_t w1 = pack_bf16(fmaxf(fmaf(ca.z, x2, cb.z), 0.f), fmaxf(fmaf(ca.w, x3, cb.w), 0.f));
+                if (live && !(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(w0, w1);
+                if (L.write_arena) arena_store4(smem_u, srow + 2 * i, col0, w0, w1);
+              }
             }
-            gstore16(L.out_post + grow * N + col, N - col, w);
-            if (L.write_arena) arena_store16(smem_u, row, col, w);
+            __syncwarp();
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&acc_empty[b]);
-          ++epi_uses[b];
         }
+        release_all_chunks();
         if (L.write_arena) {
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&a_epi_bar);
+          ptx::mbar_arrive(a_epi_bar);
         }
       } else if (L.kind == CE_DGRAD_BN) {
         float* s_a = tab;
         float* s_b = tab + 400;
-        float* s_rs = tab + 800;
-        float* s_mr = tab + 1200;
-        float* s_s0 = tab + 1600;
-        float* s_s1 = tab + 2000;
-        for (int c = et; c < Npad; c += kCEpi) {
+        float* s_rs = tab + 800;    // pass 1: rstd            pass 2: k1 = a * mean(dyhat * xhat) * rstd
+        float* s_mr = tab + 1200;   // pass 1: -mean * rstd    pass 2: k2 = k1 * mean - a * mean(dyhat)
+        for (int c = et; c < 400; c += kCEpi) {
           float a_ = 0.f, b_ = 0.f, rs = 0.f, mr = 0.f;
           if (c < N) {
             const float mean = L.save_mean[grp * N + c];
@@ -516,172 +614,220 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             mr = -mean * rs;
           }
           s_a[c] = a_; s_b[c] = b_; s_rs[c] = rs; s_mr[c] = mr;
-          s_s0[c] = 0.f; s_s1[c] = 0.f;
         }
         bar_epi();
+        wait_all_chunks();
         // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
-          ptx::tc_fence_after();
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            float x[16];
-            gload16(L.hpre + grow * N + col, N - col, x);
-            ptx::tmem_ld_wait();
-            float d[16], dx[16];
+        for (int blk = h; blk < n_blocks; blk += 2) {
+          const int col0 = blk * 64 + 4 * cq;
+          const bool live = col0 < N;
+          uint2 hx[16];   // this lane's pre-BatchNorm activations of the block: [half][i] -> 4 bf16, in flight during the TMEM load
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float y = fmaf(s_a[col + j], x[j], s_b[col + j]);
-              const float xh = fmaf(x[j], s_rs[col + j], s_mr[col + j]);
-              d[j] = y > 0.f ? __uint_as_float(v[j]) : 0.f;
-              dx[j] = d[j] * xh;
+          for (int k = 0; k < 16; ++k)
+            hx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 3) * 16 + rsel + 2 * (k & 7)) * N + col0))
+                         : make_uint2(0u, 0u);
+          uint32_t v[64];
+          load_block(blk, v);
+          const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 trs = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 tmr = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                const uint2 hw = hx[half * 8 + i];
+                const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
+                const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
+                const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
+                const float d2 = fmaf(ta.z, x2, tb.z) > 0.f ? a.z : 0.f;
+                const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
+                s0[0] += d0; s0[1] += d1; s0[2] += d2; s0[3] += d3;
+                s1[0] = fmaf(d0, fmaf(x0, trs.x, tmr.x), s1[0]);
+                s1[1] = fmaf(d1, fmaf(x1, trs.y, tmr.y), s1[1]);
+                s1[2] = fmaf(d2, fmaf(x2, trs.z, tmr.z), s1[2]);
+                s1[3] = fmaf(d3, fmaf(x3, trs.w, tmr.w), s1[3]);
+              }
             }
-            const float a0 = colsum16(d, lane);
-            const float a1 = colsum16(dx, lane);
-            const int c = col + colperm(lane);
-            if (c < N) atomicAdd((lane & 1) ? &s_s1[c] : &s_s0[c], (lane & 1) ? a1 : a0);
+            __syncwarp();
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 16);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+          }
+          if (live) {
+            float* dst = (rsel ? L.stat1 : L.stat0) + grp * N + col0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (!(p.dbg_flags & 1)) atomicAdd(dst + k, rsel ? s1[k] : s0[k]);
           }
         }
-        bar_epi();
-        for (int c = et; c < N; c += kCEpi) {
-          atomicAdd(L.stat0 + grp * N + c, s_s0[c]);
-          atomicAdd(L.stat1 + grp * N + c, s_s1[c]);
-        }
+        if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
-        for (int c = et; c < Npad; c += kCEpi) {
-          s_s0[c] = c < N ? __ldcg(L.stat0 + grp * N + c) * inv_cnt : 0.f;
-          s_s1[c] = c < N ? __ldcg(L.stat1 + grp * N + c) * inv_cnt : 0.f;
+        if (et == 0) stamp(19 + il * 4);
+        for (int c = et; c < 400; c += kCEpi) {
+          if (c < N) {
+            const float c0 = __ldcg(L.stat0 + grp * N + c) * inv_cnt;
+            const float c1 = __ldcg(L.stat1 + grp * N + c) * inv_cnt;
+            const float a_ = s_a[c];
+            const float mean = L.save_mean[grp * N + c];
+            const float k1 = a_ * c1 * s_rs[c];
+            s_rs[c] = k1;
+            s_mr[c] = fmaf(k1, mean, -a_ * c0);
+          }
         }
         bar_epi();
-        // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat))
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            float x[16];
-            gload16(L.hpre + grow * N + col, N - col, x);
-            ptx::tmem_ld_wait();
-            uint32_t w[8];
-            float o[16];
+        // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) = a * dyhat - k1 * x + k2
+        for (int blk = h; blk < n_blocks; blk += 2) {
+          const int col0 = blk * 64 + 4 * cq;
+          const bool live = col0 < N, padded = col0 < Npad;
+          uint2 hx[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float y = fmaf(s_a[col + j], x[j], s_b[col + j]);
-              const float xh = fmaf(x[j], s_rs[col + j], s_mr[col + j]);
-              const float d = y > 0.f ? __uint_as_float(v[j]) : 0.f;
-              o[j] = s_a[col + j] * (d - s_s0[col + j] - xh * s_s1[col + j]);
+          for (int k = 0; k < 16; ++k)
+            hx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 3) * 16 + rsel + 2 * (k & 7)) * N + col0))
+                         : make_uint2(0u, 0u);
+          uint32_t v[64];
+          load_block(blk, v);
+          const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 k2 = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (padded) {
+              __nv_bfloat16* dst = L.out_post + (wrow0 + half * 16 + rsel) * N + col0;
+              const int srow = q * 32 + half * 16 + rsel;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                const uint2 hw = hx[half * 8 + i];
+                const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
+                const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
+                const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
+                const float d2 = fmaf(ta.z, x2, tb.z) > 0.f ? a.z : 0.f;
+                const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
+                const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
+                const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
+                if (live && !(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(w0, w1);
+                if (L.write_arena) arena_store4(smem_u, srow + 2 * i, col0, w0, w1);
+              }
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(o[2 * j], o[2 * j + 1]);
-            gstore16(L.out_post + grow * N + col, N - col, w);
-            if (L.write_arena) arena_store16(smem_u, row, col, w);
+            __syncwarp();
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&acc_empty[b]);
-          ++epi_uses[b];
         }
+        release_all_chunks();
         if (L.write_arena) {
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&a_epi_bar);
+          ptx::mbar_arrive(a_epi_bar);
         }
       } else if (L.kind == CE_FWD_STORE || L.kind == CE_DGRAD_STORE) {
         float* s_bias = tab;
-        for (int c = et; c < Npad; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
+        for (int c = et; c < 400; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
         bar_epi();
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
-          ptx::tc_fence_after();
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            ptx::tmem_ld_wait();
-            if (col + 16 <= N) {
-              float* dst = L.out_f32 + grow * L.ld_out + col;
+        wait_all_chunks();
+        for (int blk = h; blk < n_blocks; blk += 2) {
+          uint32_t v[64];
+          load_block(blk, v);
+          const int col0 = blk * 64 + 4 * cq;
+          const bool live = col0 < N;
+          const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + j) =
-                    make_float4(__uint_as_float(v[j]) + s_bias[col + j], __uint_as_float(v[j + 1]) + s_bias[col + j + 1],
-                                __uint_as_float(v[j + 2]) + s_bias[col + j + 2], __uint_as_float(v[j + 3]) + s_bias[col + j + 3]);
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (live) {
+              float* dst = L.out_f32 + (wrow0 + half * 16 + rsel) * L.ld_out + col0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                *reinterpret_cast<float4*>(dst + 2ll * i * L.ld_out) = make_float4(a.x + bs.x, a.y + bs.y, a.z + bs.z, a.w + bs.w);
+              }
             }
+            __syncwarp();
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&acc_empty[b]);
-          ++epi_uses[b];
         }
+        release_all_chunks();
       } else if (L.kind == CE_BCE) {
         // last decoder Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70): logits never leave the SM.
         // loss = softplus(x) - t x, dlogit = scale * (sigmoid(x) - t); also the bias gradient (column sums of dlogit).
         float* s_bias = tab;
-        float* s_db = tab + 800;
-        for (int c = et; c < Npad; c += kCEpi) {
-          s_bias[c] = c < N ? L.bias[c] : 0.f;
-          s_db[c] = 0.f;
-        }
+        for (int c = et; c < 800; c += kCEpi) s_bias[c] = c < N ? L.bias[c] : 0.f;
         bar_epi();
         const float scale = L.bce_scale[grp];
-        const long long trow = static_cast<long long>(m0 % L.target_rows) + row;
+        const __nv_bfloat16* tbase = L.target + (static_cast<long long>(m0 % L.target_rows) + q * 32) * N;
         float lsum = 0.f;
         for (int ci = 0; ci < L.n_chunks; ++ci) {
           const int b = L.c_buf[ci];
-          mbar_wait_b(&acc_full[b], epi_uses[b] & 1, p.err, 0x300u + il * 16 + ci);
+          const int blk0 = L.c_n0[ci] >> 6, blk1 = (L.c_n0[ci] + L.c_w[ci] + 63) >> 6;   // chunk boundaries are multiples of 64
+          const int first = blk0 + ((blk0 & 1) != h ? 1 : 0);
+          mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
           ptx::tc_fence_after();
-          const int pieces = L.c_w[ci] >> 4;
-          for (int pi = h; pi < pieces; pi += 2) {
-            const int col = L.c_n0[ci] + pi * 16;
-            uint32_t v[16];
-            ptx::tmem_ld16(t_row + L.c_tmem[ci] + pi * 16, v);
-            float tg[16];
-            gload16(L.target + trow * N + col, N - col, tg);
-            ptx::tmem_ld_wait();
-            float d[16], pr[16];
+          for (int blk = first; blk < blk1; blk += 2) {
+            const int col0 = blk * 64 + 4 * cq;
+            const bool live = col0 < N;
+            uint2 tx[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float x = __uint_as_float(v[j]) + s_bias[col + j];
-              const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
-              const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
-              const float pz = x >= 0.f ? inv : ex * inv;
-              pr[j] = pz;
-              d[j] = scale * (pz - tg[j]);
-              // softplus(x) - t x = max(x, 0) - t x - ln(sigmoid(|x|))
-              lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[j], x, fmaxf(x, 0.f)));
-            }
-            uint32_t w[8];
+            for (int k = 0; k < 16; ++k)
+              tx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(tbase + ((k >> 3) * 16 + rsel + 2 * (k & 7)) * static_cast<long long>(N) + col0))
+                           : make_uint2(0u, 0u);
+            uint32_t v[64];
+            load_block(blk, v);
+            const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+            float sd[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] = pack_bf16(d[2 * j], d[2 * j + 1]);
-            gstore16(L.dlog + grow * N + col, N - col, w);
-            if (L.probs != nullptr) {
+            for (int half = 0; half < 2; ++half) {
+              deposit(half, v);
+              if (live) {
+                const long long orow = (wrow0 + half * 16 + rsel) * N + col0;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) w[j] = pack_bf16(pr[2 * j], pr[2 * j + 1]);
-              gstore16(L.probs + grow * N + col, N - col, w);
+                for (int i = 0; i < 8; ++i) {
+                  const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                  const float av[4] = {a.x, a.y, a.z, a.w};
+                  const uint2 tw = tx[half * 8 + i];
+                  const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
+                  float d[4], pr[4];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float x = av[u] + bsv[u];
+                    const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
+                    const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
+                    pr[u] = x >= 0.f ? inv : ex * inv;
+                    d[u] = scale * (pr[u] - tv[u]);
+                    sd[u] += d[u];
+                    // softplus(x) - t x = max(x, 0) - t x - ln(sigmoid(|x|))
+                    lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tv[u], x, fmaxf(x, 0.f)));
+                  }
+                  if (!(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(L.dlog + orow + 2ll * i * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
+                  if (L.probs != nullptr)
+                    *reinterpret_cast<uint2*>(L.probs + orow + 2ll * i * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
+                }
+              }
+              __syncwarp();
             }
             if (L.dbias != nullptr) {
-              const float a0 = colsum16(d, lane);
-              const int c = col + colperm(lane);
-              if ((lane & 1) == 0 && c < N) atomicAdd(&s_db[c], a0);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 16);
+              if (live && rsel == 0) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (!(p.dbg_flags & 1)) atomicAdd(L.dbias + col0 + u, sd[u]);
+              }
             }
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[b]);
-          ++epi_uses[b];
+          epi_par ^= 1u << b;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-        if (lane == 0) atomicAdd(&s_loss, lsum);
-        bar_epi();
-        if (L.dbias != nullptr)
-          for (int c = et; c < N; c += kCEpi) atomicAdd(L.dbias + c, s_db[c]);
-        if (et == 0 && L.loss != nullptr) atomicAdd(L.loss + grp, scale * s_loss);
+        if (lane == 0 && L.loss != nullptr) atomicAdd(L.loss + grp, scale * lsum);
       }
       bar_epi();   // the tables are reused by the next layer
+      if (et == 0) stamp(20 + il * 4);
     }
 
     // ---- leader CTA: what needs every group's statistics, in group order (one reference forward pass per group)
@@ -729,6 +875,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x == 0) stamp(31);
 }
 
 // ---------------------------------------------------------------- host side
@@ -796,17 +943,26 @@ int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
   return 0;
 }
 
-void init_params(CParams& p, int rows_per_group, unsigned int* err) {
+long long* g_chain_dbg = nullptr;
+
+void init_params(CParams& p, int rows_per_group, unsigned int* err, int kind) {
   memset(&p, 0, sizeof(p));
+  p.dbg = g_chain_dbg != nullptr ? g_chain_dbg + static_cast<long long>(kind) * 148 * 32 : nullptr;
   p.rows_per_group = rows_per_group;
   p.init_tm = -1;
   p.momentum = 0.1f;
   p.eps = 1e-5f;
   p.err = err;
-  p.ring[1] = CRing{kArena, 26624, 4, 0};
+  p.ring[1] = CRing{kArena, 26624, 3, 0};
+  p.stg_off = kArena + 3 * 26624;   // [194560, 227328): behind the 3-stage weight ring
+  p.tab_off = kTabOffF;
+  p.dbg_flags = env_int("MVAE_CHAIN_DEBUG", 0);
 }
 
 }  // namespace
+
+// bring-up: %globaltimer stamps of the chain kernels go to a device buffer of 4 x 148 x 32 int64 (null switches it off)
+void set_chain_debug_times(void* ptr) { g_chain_dbg = static_cast<long long*>(ptr); }
 
 // true if the chain kernels can run this step: all slabs whole, co-resident, dimensions inside the on-chip plan
 bool chain_supported(int B, int G, int n) {
@@ -821,7 +977,7 @@ bool chain_supported(int B, int G, int n) {
 
 int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   CParams p;
-  init_params(p, a.B, a.err);
+  init_params(p, a.B, a.err, 0);
   const int n2 = 2 * a.n;
   if (chain_tmap(&p.tm[0], a.image, a.B, 784, 784, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208)) return 1;
@@ -868,7 +1024,7 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
 int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   CParams p;
   const int R = a.G * a.B, G = a.G;
-  init_params(p, a.B, a.err);
+  init_params(p, a.B, a.err, 1);
   if (chain_tmap(&p.tm[0], a.z, R, a.n, a.n, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, 208)) return 1;
   if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 208)) return 1;
@@ -888,7 +1044,7 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
     d2.b_mn = 0; d2.n_chunks = 1;
     set_chunk(d2, 0, c == 0 ? 0 : 208, c == 0 ? 208 : 192, 0, 26624, 0, c * 256, c);
   }
-  const int n0s[4] = {0, 208, 400, 592}, ws[4] = {208, 192, 192, 192};
+  const int n0s[4] = {0, 192, 384, 576}, ws[4] = {192, 192, 192, 208};   // chunk boundaries at multiples of 64 (epilogue blocks)
   for (int c = 0; c < 4; ++c) {
     CPass& d3 = p.pass[3 + c];
     d3.cfg = 1; d3.k_panels = panels_of(400); d3.last_ksteps = ksteps_of(400); d3.a_stream = -1; d3.a_wait = c == 0 ? 2 : 0; d3.b_tm = 3;
@@ -922,14 +1078,16 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
 int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   CParams p;
   const int R = a.G * a.B, G = a.G;
-  init_params(p, a.B, a.err);
+  init_params(p, a.B, a.err, 2);
   if (chain_tmap(&p.tm[0], a.dlog, R, 784, 784, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w3, 784, 400, 400, 64, 64)) return 1;   // dgrad: W[out, in] read as the MN-major B operand
   if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 64)) return 1;
   if (chain_tmap(&p.tm[3], a.w1, 200, a.n, a.n, 64, 64)) return 1;
   p.tm[4] = p.tm[3];
   p.ring[0] = CRing{0, 73728, 3, kPanel};
-  p.ring[1] = CRing{kArena, 32768, 3, 0};
+  p.ring[1] = CRing{kArena, 32768, 2, 0};
+  p.stg_off = kArena + 2 * 32768;   // [180224, 212992)
+  p.tab_off = kTabOffB;
   p.n_pass = 3;
   CPass& g3 = p.pass[0];
   g3.cfg = 0; g3.k_panels = panels_of(784); g3.last_ksteps = ksteps_of(784); g3.a_stream = 0; g3.a_wait = 0; g3.b_tm = 1; g3.b_mn = 1;
@@ -967,14 +1125,16 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
 
 int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   CParams p;
-  init_params(p, a.B, a.err);
+  init_params(p, a.B, a.err, 3);
   const int n2 = 2 * a.n;
   if (chain_tmap(&p.tm[0], a.denc, a.B, n2, n2, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w3, n2, 200, 200, 64, 64)) return 1;
   if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, 64)) return 1;
   p.tm[3] = p.tm[2];
   p.tm[4] = p.tm[2];
-  p.ring[1] = CRing{kArena, 32768, 3, 0};
+  p.ring[1] = CRing{kArena, 32768, 2, 0};
+  p.stg_off = kArena + 2 * 32768;
+  p.tab_off = kTabOffB;
   p.ring[0] = p.ring[1];
   p.init_tm = 0;
   p.init_panels = panels_of(n2);

@@ -142,6 +142,7 @@ int launch_poe_backward(int mode, int prior, float eps, int M, long long B, int 
 // the bf16 mirror, biases / BatchNorm parameters fp32; statistics buffers are [2][G][F] (sum | sumsq resp. s0 | s1) inside
 // the zeroed accumulator region of the step workspace; counters are zeroed grid-barrier arrival counters.
 bool chain_supported(int B, int G, int n);
+void set_chain_debug_times(void* ptr);
 struct ChainEncFwd {
   int B = 0, n = 0, bn_updates = 1;
   const __nv_bfloat16* image = nullptr;
