@@ -7,18 +7,25 @@
 //   dec_bwd : dlogits -> dgrad 784->400 -> ReLU/BN backward -> dgrad 400->200 -> ReLU/BN backward -> dgrad 200->n
 //   enc_bwd : d(enc) -> dgrad 2n->200 -> ReLU/BN backward -> dgrad 200->400 -> ReLU/BN backward
 //
-// Roles (320 threads): warp 0 = TMA producer (weights - and the streamed A operand of the two K = 784 layers - into a
+// Roles (576 threads): warp 0 = TMA producer (weights - and the streamed A operand of the two K = 784 layers - into a
 // SWIZZLE_128B shared-memory ring, running ahead across layer boundaries), warp 1 = tcgen05.mma issuer (fp32 accumulators
-// in TMEM, up to 512 columns = a whole layer), warps 2..9 = epilogue (one accumulator row per thread).  The epilogue of a
-// layer writes the NEXT layer's A operand straight into shared memory in the UMMA K-major swizzled layout (7 panels of
-// 128 rows x 64 columns), so `h = relu(bn(x W^T + b))` feeds the next tcgen05.mma without touching HBM; what the weight-
-// gradient GEMMs and the backward need (pre-/post-BatchNorm activations, gradients) is written to global memory once,
-// on the side.
+// in TMEM, a whole layer of up to 400 columns, or a ring of four 112-column chunks for the 784-wide layer), warps 2..17 =
+// epilogue: four warps per TMEM lane quarter, each taking every fourth 32-column unit of its 32 rows.  The epilogue of a
+// layer writes the NEXT layer's A operand straight into shared memory in the UMMA K-major swizzled layout (the "arena":
+// 7 panels of 128 rows x 64 columns), so `h = relu(bn(x W^T + b))` feeds the next tcgen05.mma without touching HBM; what
+// the weight-gradient GEMMs and the backward need (pre-/post-BatchNorm activations, gradients) is written to global
+// memory once, on the side.
 //
-// BatchNorm needs whole-batch statistics per ELBO term: each CTA reduces its slab's column sums (butterfly shuffles ->
-// shared atomics -> one global atomic per column), all CTAs of a term meet at a grid barrier (arrival counter in the step
-// workspace, cooperative launch guarantees co-residency), read the sums back and normalise their own slab from TMEM.
-// One barrier per BatchNorm layer and direction; everything else is CTA-local.
+// tcgen05.ld hands a lane one accumulator ROW; everything the epilogue does is per COLUMN (coefficients, statistics, 64-
+// byte global segments per row), so each unit is transposed through a 2 KB per-warp tile (16 rows x 32 fp32, 16-byte
+// chunks XOR-swizzled: conflict-free both ways): afterwards lane (rsel, cq) holds columns 4cq..4cq+3 of rows 4rsel..4rsel+3.
+//
+// BatchNorm needs whole-batch statistics per ELBO term: the four warps of a column unit leave their slab sums in a
+// shared table, one global atomic per column and CTA publishes them, all CTAs of a term meet at a grid barrier (arrival
+// counter in the step workspace, cooperative launch guarantees co-residency), read the sums back and normalise their own
+// slab: the forward from the bf16 pre-activations it stashed in the arena (in place), the backward from TMEM.  One
+// barrier per BatchNorm layer and direction.  One extra CTA (the "keeper") owns no slab: it waits for every group's
+// barrier and does what needs all groups (running statistics in group order, dgamma / dbeta) beside the others.
 #include <string.h>
 
 #include <algorithm>
@@ -31,20 +38,26 @@ namespace mvae {
 
 namespace {
 
-constexpr int kCThreads = 320;
-constexpr int kCEpi = 256;
-constexpr int kPanel = 16384;                  // 128 rows x 128 B: one K-major SWIZZLE_128B panel (64 bf16 columns)
-constexpr int kArenaPanels = 7;                // 448 columns >= the widest resident activation (400)
-constexpr int kArena = kArenaPanels * kPanel;  // 114688
-constexpr int kStage = 8 * 4096;                // the epilogue warps' staging tiles
-constexpr int kMainF = kArena + 3 * 26624 + kStage;   // forward kernels: [arena | 3-stage K-major weight ring | staging] = 227328
-constexpr int kTabOffF = kMainF;                // forward tables: 3 x 400 floats
-constexpr int kTabOffB = 221184;                // backward kernels: behind the 3 x 72 KB streamed-operand ring; 4 x 400 floats
-constexpr int kBarOff = kTabOffF + 4800;        // 232128: mbarriers + the TMEM base address
-constexpr int kChainSmem = kBarOff + 128;       // 232256 <= 232448 (227 KB), no static shared memory
-constexpr int kMaxPass = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kCEpi = kEpiWarps * 32;           // 512 epilogue threads
+constexpr int kCThreads = 64 + kCEpi;           // 576
+constexpr int kPanel = 16384;                   // 128 rows x 128 B: one K-major SWIZZLE_128B panel (64 bf16 columns)
+constexpr int kArenaPanels = 7;                 // 448 columns >= the widest resident activation (400)
+constexpr int kArena = kArenaPanels * kPanel;   // 114688
+constexpr int kSmemTotal = 232448;              // 227 KB, no static shared memory
+constexpr int kBarOff = kSmemTotal - 192;       // mbarriers + the TMEM base address
+constexpr int kRedStride = 800;                 // floats per TMEM lane quarter in the reduction table
+constexpr int kRedOff = kBarOff - 4 * kRedStride * 4;
+constexpr int kTabFloats = 1600;                // coefficient tables: 4 x 400 floats (or one of 800)
+constexpr int kTabOff = kRedOff - kTabFloats * 4;
+constexpr int kTileBytes = 2048;                // per epilogue warp: 16 rows x 32 fp32
+constexpr int kTileOff = kTabOff - kEpiWarps * kTileBytes;
+constexpr int kRing1Stage = 16384;              // resident-A layers: one weight chunk (<= 128 rows K-major / two 64x64 boxes MN-major)
+constexpr int kRing1Stages = 4;
+static_assert(kArena + kRing1Stages * kRing1Stage <= kTileOff, "ring 1 overlaps the epilogue tiles");
+constexpr int kMaxPass = 16;
 constexpr int kMaxLayer = 3;
-constexpr int kMaxChunk = 4;
+constexpr int kMaxChunk = 8;
 
 enum : int { CE_FWD_BN = 0, CE_FWD_STORE = 1, CE_BCE = 2, CE_DGRAD_BN = 3, CE_DGRAD_STORE = 4 };
 
@@ -73,7 +86,7 @@ struct CPass {
 
 struct CLayer {
   int kind, N, n_chunks;
-  int c_n0[kMaxChunk], c_w[kMaxChunk], c_tmem[kMaxChunk], c_buf[kMaxChunk];
+  int c_n0[kMaxChunk], c_w[kMaxChunk], c_tmem[kMaxChunk], c_buf[kMaxChunk];   // BatchNorm / store layers: TMEM column = layer column
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -81,7 +94,7 @@ struct CLayer {
   float* stat1;            // [G][N] forward: sum y^2 / backward: sum dyhat * xhat
   float* save_mean;        // [G][N] forward: written; backward: read
   float* save_rstd;
-  float* running_mean;     // forward, leader CTA
+  float* running_mean;     // forward, keeper CTA
   float* running_var;
   int bn_updates;
   unsigned int* counter;   // [G] grid-barrier arrivals
@@ -109,14 +122,12 @@ struct alignas(64) CParams {
   CPass pass[kMaxPass];
   CLayer layer[kMaxLayer];
   int n_pass, n_layers;
+  int n_slabs;            // slab CTAs; CTA n_slabs is the keeper
   int rows_per_group;     // rows of one statistics group (= batch)
   int init_tm, init_panels;  // resident A loaded by TMA at kernel start (z / d_enc), -1: none
   float momentum, eps;
   unsigned int* err;      // device flag: non-zero = a wait timed out (bring-up)
   long long* dbg;         // bring-up: [ctas][32] %globaltimer stamps (mvae_debug_chain_times), or null
-  int stg_off;            // byte offset of the epilogue warps' staging tiles (8 x 4 KB)
-  int tab_off;            // byte offset of the coefficient tables
-  int dbg_flags;          // bring-up (MVAE_CHAIN_DEBUG): 1 no statistics atomics, 2 no global stores, 4 no TMEM loads, 8 no global loads
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -145,70 +156,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ void unpack8(const uint4& t, float* o) {
-  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    o[2 * k] = __uint_as_float(w[k] << 16);
-    o[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-  }
-}
-
-// Column sums over the 32 lanes (rows) of a warp for 16 columns held one row per lane: a reduce-scatter butterfly
-// (16 shuffles instead of 80).  Afterwards every lane holds the warp-wide sum of column colperm(lane); lanes 2k and
-// 2k+1 hold the same column.  v is destroyed.
-__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
-  {
-    const bool b = (lane & 16) != 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = b ? v[i] : v[i + 8];
-      const float keep = b ? v[i + 8] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool b = (lane & 8) != 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = b ? v[i] : v[i + 4];
-      const float keep = b ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool b = (lane & 4) != 0;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = b ? v[i] : v[i + 2];
-      const float keep = b ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  {
-    const bool b = (lane & 2) != 0;
-    const float send = b ? v[0] : v[1];
-    const float keep = b ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-  return v[0];
-}
-__device__ __forceinline__ int colperm(int lane) {
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
-// 16 consecutive bf16 of one row -> the arena (K-major SWIZZLE_128B panels): 16-byte chunk c of row r lives at chunk c ^ (r & 7)
-__device__ __forceinline__ void arena_store16(uint32_t arena, int row, int col, const uint32_t (&w)[8]) {
-  const int panel = col >> 6, cc = (col & 63) >> 3;
-  const uint32_t base = arena + panel * kPanel + row * 128;
-  ptx::sts128(base + (((cc) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
-  ptx::sts128(base + (((cc + 1) ^ (row & 7)) << 4), w[4], w[5], w[6], w[7]);
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float4 tab4(const float* t) { return *reinterpret_cast<const float4*>(t); }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float v[4];
+  ptx::lds128(addr, v);
+  return make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // Grid barrier of one statistics group: arrive, then wait until all `expected` CTAs of the group have arrived.
-// Called by all 256 epilogue threads after their global atomics.  A lost CTA cannot hang the GPU: after ~2 s the wait
+// Called by all epilogue threads after their global atomics.  A lost CTA cannot hang the GPU: after ~2 s the wait
 // gives up and flags the error (results are then garbage, which the flag reports).
 __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int expected, unsigned int* err, int et) {
   __threadfence();
@@ -225,13 +183,13 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
         if (err != nullptr) atomicExch(err, 0xBA00u | (seen & 0xffu));
         break;
       }
-      __nanosleep(40);
+      __nanosleep(32);
     }
     __threadfence();
   }
   bar_epi();
 }
-// wait (without arriving) until a group's counter is complete - the leader CTA's end-of-kernel bookkeeping
+// wait (without arriving) until a group's counter is complete - the keeper CTA
 __device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned int expected, unsigned int* err) {
   unsigned int seen = 0;
   const unsigned long long t0 = gtimer();
@@ -243,52 +201,48 @@ __device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned
       if (err != nullptr) atomicExch(err, 0xBB00u | (seen & 0xffu));
       break;
     }
-    __nanosleep(40);
+    __nanosleep(100);
   }
   __threadfence();
 }
 
-// ---------------------------------------------------------------- the epilogue's transposing tile
-// tcgen05.ld hands every lane one accumulator ROW, but everything the epilogue has to do is cheaper per COLUMN: the
-// BatchNorm / bias coefficients are per column, the statistics are column sums, and global memory wants whole 128-byte
-// lines per row.  So each epilogue warp owns a 4 KB fp32 tile (16 rows x 64 columns, 16-byte chunk c of row r stored at
-// chunk c ^ r, conflict-free both ways): half a warp's rows go in raw, straight from TMEM, and come back out with lane
-// (rsel, c) holding columns 4c..4c+3 of rows rsel, rsel+2, ... - its coefficients are then loop constants, column sums
-// accumulate in registers (one shuffle at the end), and 16 lanes cover one row's 64 columns for every global load / store.
-__device__ __forceinline__ uint32_t tile_w(uint32_t tile, int r, int c) { return tile + r * 256 + (((c ^ r) & 15) << 4); }
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ float4 tab4(const float* t) { return *reinterpret_cast<const float4*>(t); }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float v[4];
-  ptx::lds128(addr, v);
-  return make_float4(v[0], v[1], v[2], v[3]);
-}
-// four bf16 (8 bytes) of a K-major SWIZZLE_128B arena row: columns col0..col0+3 (col0 % 4 == 0) of slab row `row`
-__device__ __forceinline__ void arena_store4(uint32_t arena, int row, int col0, uint32_t w0, uint32_t w1) {
+// ---------------------------------------------------------------- the epilogue's transposing tile and the arena
+// tile: 16 rows x 128 B, 16-byte chunk c of row r at chunk c ^ (r & 7)
+__device__ __forceinline__ uint32_t tile_addr(uint32_t tile, int r, int c) { return tile + r * 128 + (((c ^ r) & 7) << 4); }
+// arena: four bf16 (8 bytes) of a K-major SWIZZLE_128B panel row: columns col0..col0+3 (col0 % 4 == 0) of slab row `row`
+__device__ __forceinline__ uint32_t arena_addr(uint32_t arena, int row, int col0) {
   const int panel = col0 >> 6, cc = (col0 & 63) >> 3;
-  const uint32_t addr = arena + panel * kPanel + row * 128 + ((cc ^ (row & 7)) << 4) + ((col0 & 4) << 1);
+  return arena + panel * kPanel + row * 128 + ((cc ^ (row & 7)) << 4) + ((col0 & 4) << 1);
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t w0, uint32_t w1) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w0), "r"(w1) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr) : "memory");
+  return r;
 }
 
 __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_constant__ CParams p) {
   // No static shared memory: the dynamic window then starts 1024-byte aligned (checked below), which the SWIZZLE_128B
-  // tiles need, and every byte of the 227 KB is planned: [arena | weight ring | staging tiles | tables | barriers].
+  // tiles need, and every byte of the 227 KB is planned: [arena | weight ring | tiles | tables | reduction table | barriers].
   extern __shared__ __align__(1024) uint8_t smem[];
-  float* tab = reinterpret_cast<float*>(smem + p.tab_off);
+  float* tab = reinterpret_cast<float*>(smem + kTabOff);
+  float* red = reinterpret_cast<float*>(smem + kRedOff);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* empty_bar = full_bar + 4;
   uint64_t* acc_full = full_bar + 8;
-  uint64_t* acc_empty = full_bar + 10;
-  uint64_t* a_tma_bar = full_bar + 12;
-  uint64_t* a_epi_bar = full_bar + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 14);
+  uint64_t* acc_empty = full_bar + 12;
+  uint64_t* a_tma_bar = full_bar + 16;
+  uint64_t* a_epi_bar = full_bar + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool keeper = static_cast<int>(blockIdx.x) >= p.n_slabs;
   const int m0 = blockIdx.x * 128;
-  const int grp = m0 / p.rows_per_group;
+  const int grp = keeper ? 0 : m0 / p.rows_per_group;
   const unsigned int slabs_per_group = static_cast<unsigned int>(p.rows_per_group / 128);
-  const bool group_leader = (m0 % p.rows_per_group) == 0;
+  const bool group_leader = !keeper && (m0 % p.rows_per_group) == 0;
   const uint32_t smem_u = ptx::smem_u32(smem);
   long long* dbg = p.dbg != nullptr ? p.dbg + 32ll * blockIdx.x : nullptr;
   auto stamp = [&](int slot) {
@@ -305,10 +259,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&acc_full[b], 1);
-      ptx::mbar_init(&acc_empty[b], kCEpi);
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], kCEpi);
     }
     ptx::mbar_init(a_tma_bar, 1);
     ptx::mbar_init(a_epi_bar, kCEpi);
@@ -327,7 +279,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   // shared-memory carve-out taken there is almost no L1, and a local-memory array costs an L2 round trip per access.
   if (warp == 0) {
     // =================================================================== TMA producer
-    if (lane == 0) {
+    if (lane == 0 && !keeper) {
       if (p.init_tm >= 0) {
         ptx::mbar_expect_tx(a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel));
         for (int pn = 0; pn < p.init_panels; ++pn) ptx::tma_load_2d(smem + pn * kPanel, &p.tm[p.init_tm], a_tma_bar, pn * 64, m0);
@@ -356,20 +308,20 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             if (!ps.b_mn) {
               ptx::tma_load_2d(bslot + ps.c_boff[c], &p.tm[ps.b_tm], &full_bar[s], kp * 64, ps.c_n0[c]);
             } else {
-              for (int j = 0; j < ps.c_boxes[c]; ++j)
-                ptx::tma_load_2d(bslot + ps.c_boff[c] + j * 8192, &p.tm[ps.b_tm], &full_bar[s], ps.c_n0[c] + j * 64, kp * 64);
+              for (int jb = 0; jb < ps.c_boxes[c]; ++jb)
+                ptx::tma_load_2d(bslot + ps.c_boff[c] + jb * 8192, &p.tm[ps.b_tm], &full_bar[s], ps.c_n0[c] + jb * 64, kp * 64);
             }
           }
           fill_par ^= 1u << s;
           fill_any |= 1u << s;
           if (++s == rg.stages) s = 0;
         }
-        stamp(1 + ip);
       }
+      stamp(1);
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && !keeper) {
       uint32_t use_par = 0, acc_par = 0;   // bit s: parity of uses of ring slot s; bit b: parity of uses of accumulator b
       uint32_t n_tma_waits = 0, n_epi_waits = 0;
       int cur_cfg = -1, s = 0;
@@ -426,81 +378,78 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           ptx::umma_commit(&acc_full[buf1]);
           acc_par ^= 1u << buf1;
         }
-        stamp(9 + ip);
+        if (ip < 8) stamp(9 + ip);
       }
     }
-  } else {
-    // =================================================================== epilogue (8 warps)
+  } else if (!keeper) {
+    // =================================================================== epilogue (16 warps)
     const int et = threadIdx.x - 64;
     const int q = warp & 3;               // TMEM lane quarter this warp may read
-    const int h = (warp - 2) >> 2;        // the two warps of a quarter take alternate 64-column blocks
+    const int jw = (warp - 2) >> 2;       // the four warps of a quarter take every fourth 32-column unit
     const long long wrow0 = static_cast<long long>(m0) + q * 32;   // first global row of this warp
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t tile = smem_u + p.stg_off + (warp - 2) * 4096;  // this warp's transposing tile
-    const int rsel = lane >> 4, cq = lane & 15;                    // column phase: rows rsel + 2i, columns 4*cq .. 4*cq+3 of the block
+    const uint32_t tile = smem_u + kTileOff + (warp - 2) * kTileBytes;
+    const int rsel = lane >> 3, cq = lane & 7;   // column phase: rows 4*rsel + i of a 16-row half, columns 4*cq .. 4*cq+3 of the unit
     uint32_t epi_par = 0;                 // bit b: parity of the accumulator-full phases consumed so far
     const float inv_cnt = 1.f / static_cast<float>(p.rows_per_group);
+
+    // this lane's accumulator row of a 32-column unit, raw from TMEM (the upper 16 columns zero when `wide` is false)
+    auto load_unit = [&](uint32_t taddr, bool wide, uint32_t (&v)[32]) {
+      uint32_t lo[16], hi[16];
+      ptx::tmem_ld16(taddr, lo);
+      if (wide) {
+        ptx::tmem_ld16(taddr + 16, hi);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) hi[k] = 0u;
+      }
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        v[k] = lo[k];
+        v[16 + k] = hi[k];
+      }
+    };
+    // rows [16*half, 16*half+16) of the warp go into the tile
+    auto deposit = [&](int half, const uint32_t (&v)[32]) {
+      if ((lane >> 4) == half) {
+        const int tr = lane & 15;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ptx::sts128(tile_addr(tile, tr, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      }
+      __syncwarp();
+    };
 
     for (int il = 0; il < p.n_layers; ++il) {
       const CLayer& L = p.layer[il];
       const int N = L.N;
       const int Npad = (N + 15) & ~15;
-      const int n_blocks = (Npad + 63) >> 6;
+      const int n_units = (Npad + 31) >> 5;
       if (et == 0) stamp(17 + il * 4);
-      // TMEM column of layer column `col` (chunk boundaries are multiples of 16)
-      auto tmem_col = [&](int col) -> uint32_t {
-        uint32_t t = L.c_tmem[0] + col - L.c_n0[0];
-        if (L.n_chunks > 1 && col >= L.c_n0[1]) t = L.c_tmem[1] + col - L.c_n0[1];
-        if (L.n_chunks > 2 && col >= L.c_n0[2]) t = L.c_tmem[2] + col - L.c_n0[2];
-        if (L.n_chunks > 3 && col >= L.c_n0[3]) t = L.c_tmem[3] + col - L.c_n0[3];
-        return t_row + t;
-      };
-      // wait for every chunk of the layer (BatchNorm layers: the statistics need all of them anyway)
       auto wait_all_chunks = [&]() {
-        uint32_t seen = 0;
         for (int ci = 0; ci < L.n_chunks; ++ci) {
           const int b = L.c_buf[ci];
-          if ((seen >> b) & 1u) continue;
-          seen |= 1u << b;
           mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
         }
         ptx::tc_fence_after();
       };
       auto release_all_chunks = [&]() {
         ptx::tc_fence_before();
-        uint32_t seen = 0;
         for (int ci = 0; ci < L.n_chunks; ++ci) {
           const int b = L.c_buf[ci];
-          if ((seen >> b) & 1u) continue;
-          seen |= 1u << b;
           ptx::mbar_arrive(&acc_empty[b]);
           epi_par ^= 1u << b;
         }
       };
-      // this lane's accumulator row of block `blk` (64 columns, zero beyond the layer), raw from TMEM
-      auto load_block = [&](int blk, uint32_t (&v)[64]) {
-#pragma unroll
-        for (int pi = 0; pi < 4; ++pi) {
-          const int col = blk * 64 + pi * 16;
-          uint32_t t[16];
-          if (col < Npad && !(p.dbg_flags & 4)) {
-            ptx::tmem_ld16(tmem_col(col), t);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) t[j] = 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[pi * 16 + j] = t[j];
+      // publish the slab's column sums: red[quarter][stat][column] -> one global atomic per column and statistic
+      auto publish_stats = [&]() {
+        bar_epi();
+        for (int c = et; c < N; c += kCEpi) {
+          const float a0 = (red[c] + red[kRedStride + c]) + (red[2 * kRedStride + c] + red[3 * kRedStride + c]);
+          const float a1 = (red[400 + c] + red[kRedStride + 400 + c]) + (red[2 * kRedStride + 400 + c] + red[3 * kRedStride + 400 + c]);
+          atomicAdd(L.stat0 + grp * N + c, a0);
+          atomicAdd(L.stat1 + grp * N + c, a1);
         }
-        ptx::tmem_ld_wait();
-      };
-      // rows [16*half, 16*half+16) of the warp go into the tile
-      auto deposit = [&](int half, const uint32_t (&v)[64]) {
-        if (rsel == half) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) ptx::sts128(tile_w(tile, cq, c), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-        }
-        __syncwarp();
       };
 
       if (L.kind == CE_FWD_BN) {
@@ -510,41 +459,44 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         for (int c = et; c < 400; c += kCEpi) s_bias[c] = c < N ? L.bias[c] : 0.f;
         bar_epi();
         wait_all_chunks();
-        // ---- pass 1: pre-activations out (bf16), slab statistics straight into the global accumulators
-        for (int blk = h; blk < n_blocks; blk += 2) {
-          uint32_t v[64];
-          load_block(blk, v);
-          const int col0 = blk * 64 + 4 * cq;
-          const bool live = col0 < N;
-          const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- pass 1: slab statistics; the bf16 pre-activations are parked in the arena (the layer's own A operand is spent)
+        for (int u = jw; u < n_units; u += 4) {
+          uint32_t v[32];
+          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
+          const int col0 = 32 * u + 4 * cq;
+          const bool live = col0 < N, padded = col0 < Npad;
+          const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
-            if (live) {
-              __nv_bfloat16* dst = L.out_pre + (wrow0 + half * 16 + rsel) * N + col0;
+            if (padded) {
+              const int srow = q * 32 + half * 16 + 4 * rsel;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
                 const float x0 = a.x + bs.x, x1 = a.y + bs.y, x2 = a.z + bs.z, x3 = a.w + bs.w;
                 s0[0] += x0; s0[1] += x1; s0[2] += x2; s0[3] += x3;
                 s1[0] = fmaf(x0, x0, s1[0]); s1[1] = fmaf(x1, x1, s1[1]); s1[2] = fmaf(x2, x2, s1[2]); s1[3] = fmaf(x3, x3, s1[3]);
-                if (!(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+                sts64(arena_addr(smem_u, srow + i, col0), pack_bf16(x0, x1), pack_bf16(x2, x3));
               }
             }
             __syncwarp();
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 8);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
             s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 16);
             s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
           }
-          if (live) {
-            float* dst = (rsel ? L.stat1 : L.stat0) + grp * N + col0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (!(p.dbg_flags & 1)) atomicAdd(dst + k, rsel ? s1[k] : s0[k]);
+          if (live && rsel == 0) {
+            *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+            *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
           }
         }
+        release_all_chunks();
+        publish_stats();
         if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
         if (et == 0) stamp(19 + il * 4);
@@ -565,36 +517,30 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           s_cb[c] = b_;
         }
         bar_epi();
-        // ---- pass 2: BatchNorm + ReLU from TMEM -> next layer's A operand (+ the copy the weight gradient needs)
-        for (int blk = h; blk < n_blocks; blk += 2) {
-          uint32_t v[64];
-          load_block(blk, v);
-          const int col0 = blk * 64 + 4 * cq;
+        // ---- pass 2: BatchNorm + ReLU in place in the arena -> next layer's A operand; both copies the backward and the
+        //      weight gradients need go to global memory from here (after the barrier: nothing for its fence to wait on)
+        for (int u = jw; u < n_units; u += 4) {
+          const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
-          const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 ca = padded ? tab4(s_ca + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 cb = padded ? tab4(s_cb + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!padded) continue;
+          const float4 ca = tab4(s_ca + col0);
+          const float4 cb = tab4(s_cb + col0);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            deposit(half, v);
-            if (padded) {
-              __nv_bfloat16* dst = L.out_post + (wrow0 + half * 16 + rsel) * N + col0;
-              const int srow = q * 32 + half * 16 + rsel;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
-                const float x0 = bf16_round(a.x + bs.x), x1 = bf16_round(a.y + bs.y);   // what out_pre holds
-                const float x2 = bf16_round(a.z + bs.z), x3 = bf16_round(a.w + bs.w);
-                const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
-                const uint32_t w1 = pack_bf16(fmaxf(fmaf(ca.z, x2, cb.z), 0.f), fmaxf(fmaf(ca.w, x3, cb.w), 0.f));
-                if (live && !(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(w0, w1);
-                if (L.write_arena) arena_store4(smem_u, srow + 2 * i, col0, w0, w1);
-              }
+          for (int hi = 0; hi < 8; ++hi) {
+            const int r = (hi >> 2) * 16 + 4 * rsel + (hi & 3);
+            const uint32_t addr = arena_addr(smem_u, q * 32 + r, col0);
+            const uint2 xw = lds64(addr);
+            const float x0 = bf_lo(xw.x), x1 = bf_hi(xw.x), x2 = bf_lo(xw.y), x3 = bf_hi(xw.y);
+            const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
+            const uint32_t w1 = pack_bf16(fmaxf(fmaf(ca.z, x2, cb.z), 0.f), fmaxf(fmaf(ca.w, x3, cb.w), 0.f));
+            if (L.write_arena) sts64(addr, w0, w1);
+            if (live) {
+              const long long o = (wrow0 + r) * N + col0;
+              *reinterpret_cast<uint2*>(L.out_pre + o) = xw;
+              *reinterpret_cast<uint2*>(L.out_post + o) = make_uint2(w0, w1);
             }
-            __syncwarp();
           }
         }
-        release_all_chunks();
         if (L.write_arena) {
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(a_epi_bar);
@@ -616,18 +562,19 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           s_a[c] = a_; s_b[c] = b_; s_rs[c] = rs; s_mr[c] = mr;
         }
         bar_epi();
+        // the forward's pre-activations of this warp's units are requested before the accumulator is awaited
         wait_all_chunks();
-        // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat
-        for (int blk = h; blk < n_blocks; blk += 2) {
-          const int col0 = blk * 64 + 4 * cq;
+        // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the pre-activations are parked in the arena
+        for (int u = jw; u < n_units; u += 4) {
+          const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
-          uint2 hx[16];   // this lane's pre-BatchNorm activations of the block: [half][i] -> 4 bf16, in flight during the TMEM load
+          uint2 hx[8];   // [half][i] -> 4 bf16, in flight during the TMEM load
 #pragma unroll
-          for (int k = 0; k < 16; ++k)
-            hx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 3) * 16 + rsel + 2 * (k & 7)) * N + col0))
+          for (int k = 0; k < 8; ++k)
+            hx[k] = live ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + col0))
                          : make_uint2(0u, 0u);
-          uint32_t v[64];
-          load_block(blk, v);
+          uint32_t v[32];
+          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
           const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 trs = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -637,10 +584,12 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
             if (live) {
+              const int srow = q * 32 + half * 16 + 4 * rsel;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
-                const uint2 hw = hx[half * 8 + i];
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const uint2 hw = hx[half * 4 + i];
+                sts64(arena_addr(smem_u, srow + i, col0), hw.x, hw.y);
                 const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
                 const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
                 const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
@@ -657,15 +606,17 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 8);
+            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
             s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 16);
             s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
           }
-          if (live) {
-            float* dst = (rsel ? L.stat1 : L.stat0) + grp * N + col0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (!(p.dbg_flags & 1)) atomicAdd(dst + k, rsel ? s1[k] : s0[k]);
+          if (live && rsel == 0) {
+            *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
+            *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
           }
         }
+        publish_stats();
         if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
         if (et == 0) stamp(19 + il * 4);
@@ -682,16 +633,11 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         bar_epi();
         // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) = a * dyhat - k1 * x + k2
-        for (int blk = h; blk < n_blocks; blk += 2) {
-          const int col0 = blk * 64 + 4 * cq;
+        for (int u = jw; u < n_units; u += 4) {
+          const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
-          uint2 hx[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k)
-            hx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 3) * 16 + rsel + 2 * (k & 7)) * N + col0))
-                         : make_uint2(0u, 0u);
-          uint32_t v[64];
-          load_block(blk, v);
+          uint32_t v[32];
+          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
           const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -700,12 +646,12 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
             if (padded) {
-              __nv_bfloat16* dst = L.out_post + (wrow0 + half * 16 + rsel) * N + col0;
-              const int srow = q * 32 + half * 16 + rsel;
+              const int r0 = half * 16 + 4 * rsel;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
-                const uint2 hw = hx[half * 8 + i];
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const uint32_t addr = arena_addr(smem_u, q * 32 + r0 + i, col0);
+                const uint2 hw = live ? lds64(addr) : make_uint2(0u, 0u);
                 const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
                 const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
                 const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
@@ -713,8 +659,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
                 const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
                 const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
                 const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
-                if (live && !(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(dst + 2ll * i * N) = make_uint2(w0, w1);
-                if (L.write_arena) arena_store4(smem_u, srow + 2 * i, col0, w0, w1);
+                if (live) *reinterpret_cast<uint2*>(L.out_post + (wrow0 + r0 + i) * N + col0) = make_uint2(w0, w1);
+                if (L.write_arena) sts64(addr, w0, w1);
               }
             }
             __syncwarp();
@@ -730,21 +676,21 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         for (int c = et; c < 400; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
         bar_epi();
         wait_all_chunks();
-        for (int blk = h; blk < n_blocks; blk += 2) {
-          uint32_t v[64];
-          load_block(blk, v);
-          const int col0 = blk * 64 + 4 * cq;
+        for (int u = jw; u < n_units; u += 4) {
+          uint32_t v[32];
+          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
+          const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
           const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
             if (live) {
-              float* dst = L.out_f32 + (wrow0 + half * 16 + rsel) * L.ld_out + col0;
+              float* dst = L.out_f32 + (wrow0 + half * 16 + 4 * rsel) * L.ld_out + col0;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
-                *reinterpret_cast<float4*>(dst + 2ll * i * L.ld_out) = make_float4(a.x + bs.x, a.y + bs.y, a.z + bs.z, a.w + bs.w);
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                *reinterpret_cast<float4*>(dst + static_cast<long long>(i) * L.ld_out) = make_float4(a.x + bs.x, a.y + bs.y, a.z + bs.z, a.w + bs.w);
               }
             }
             __syncwarp();
@@ -759,23 +705,23 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         bar_epi();
         const float scale = L.bce_scale[grp];
         const __nv_bfloat16* tbase = L.target + (static_cast<long long>(m0 % L.target_rows) + q * 32) * N;
-        float lsum = 0.f;
+        float lin = 0.f, llog = 0.f;   // sum of max(x, 0) - t x  and  sum of log2 sigmoid(|x|)
         for (int ci = 0; ci < L.n_chunks; ++ci) {
           const int b = L.c_buf[ci];
-          const int blk0 = L.c_n0[ci] >> 6, blk1 = (L.c_n0[ci] + L.c_w[ci] + 63) >> 6;   // chunk boundaries are multiples of 64
-          const int first = blk0 + ((blk0 & 1) != h ? 1 : 0);
+          const int cw = L.c_w[ci];
+          const int uu = (jw - ci) & 3;   // rotate the (narrower) last unit of a chunk over the four warps of a quarter
           mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
           ptx::tc_fence_after();
-          for (int blk = first; blk < blk1; blk += 2) {
-            const int col0 = blk * 64 + 4 * cq;
-            const bool live = col0 < N;
-            uint2 tx[16];
+          if (32 * uu < cw) {
+            const int col0 = L.c_n0[ci] + 32 * uu + 4 * cq;
+            const bool live = 32 * uu + 4 * cq < cw && col0 < N;
+            uint2 tx[8];
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              tx[k] = (live && !(p.dbg_flags & 8)) ? __ldg(reinterpret_cast<const uint2*>(tbase + ((k >> 3) * 16 + rsel + 2 * (k & 7)) * static_cast<long long>(N) + col0))
+            for (int k = 0; k < 8; ++k)
+              tx[k] = live ? __ldg(reinterpret_cast<const uint2*>(tbase + ((k >> 2) * 16 + 4 * rsel + (k & 3)) * static_cast<long long>(N) + col0))
                            : make_uint2(0u, 0u);
-            uint32_t v[64];
-            load_block(blk, v);
+            uint32_t v[32];
+            load_unit(t_row + L.c_tmem[ci] + 32 * uu, 32 * uu + 16 < cw, v);
             const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
             float sd[4] = {0.f, 0.f, 0.f, 0.f};
@@ -783,89 +729,97 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             for (int half = 0; half < 2; ++half) {
               deposit(half, v);
               if (live) {
-                const long long orow = (wrow0 + half * 16 + rsel) * N + col0;
+                const long long orow = (wrow0 + half * 16 + 4 * rsel) * N + col0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  const float4 a = lds_f4(tile_w(tile, 2 * i + rsel, cq));
+                for (int i = 0; i < 4; ++i) {
+                  const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
                   const float av[4] = {a.x, a.y, a.z, a.w};
-                  const uint2 tw = tx[half * 8 + i];
+                  const uint2 tw = tx[half * 4 + i];
                   const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
                   float d[4], pr[4];
+                  float prod = 1.f;
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    const float x = av[u] + bsv[u];
+                  for (int e = 0; e < 4; ++e) {
+                    const float x = av[e] + bsv[e];
                     const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
                     const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
-                    pr[u] = x >= 0.f ? inv : ex * inv;
-                    d[u] = scale * (pr[u] - tv[u]);
-                    sd[u] += d[u];
-                    // softplus(x) - t x = max(x, 0) - t x - ln(sigmoid(|x|))
-                    lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tv[u], x, fmaxf(x, 0.f)));
+                    pr[e] = x >= 0.f ? inv : ex * inv;
+                    d[e] = scale * (pr[e] - tv[e]);
+                    sd[e] += d[e];
+                    prod *= inv;                                                           // >= 1/16: one log per four elements
+                    lin += fmaf(-tv[e], x, fmaxf(x, 0.f));                                 // softplus(x) - t x = max(x,0) - t x - ln sigmoid(|x|)
                   }
-                  if (!(p.dbg_flags & 2)) *reinterpret_cast<uint2*>(L.dlog + orow + 2ll * i * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
+                  llog += ptx::lg2_approx(prod);
+                  *reinterpret_cast<uint2*>(L.dlog + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
                   if (L.probs != nullptr)
-                    *reinterpret_cast<uint2*>(L.probs + orow + 2ll * i * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
+                    *reinterpret_cast<uint2*>(L.probs + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
                 }
               }
               __syncwarp();
             }
             if (L.dbias != nullptr) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], 16);
-              if (live && rsel == 0) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (!(p.dbg_flags & 1)) atomicAdd(L.dbias + col0 + u, sd[u]);
+              for (int e = 0; e < 4; ++e) {
+                sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 8);
+                sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 16);
               }
+              if (live && rsel == 0) *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(sd[0], sd[1], sd[2], sd[3]);
             }
           }
           ptx::tc_fence_before();
           ptx::mbar_arrive(&acc_empty[b]);
           epi_par ^= 1u << b;
         }
+        float lsum = fmaf(-0.6931471805599453f, llog, lin);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
         if (lane == 0 && L.loss != nullptr) atomicAdd(L.loss + grp, scale * lsum);
+        if (L.dbias != nullptr) {
+          bar_epi();
+          for (int c = et; c < N; c += kCEpi)
+            atomicAdd(L.dbias + c, (red[c] + red[kRedStride + c]) + (red[2 * kRedStride + c] + red[3 * kRedStride + c]));
+        }
       }
       bar_epi();   // the tables are reused by the next layer
       if (et == 0) stamp(20 + il * 4);
     }
-
-    // ---- leader CTA: what needs every group's statistics, in group order (one reference forward pass per group)
-    if (blockIdx.x == 0) {
-      const int groups = static_cast<int>(gridDim.x / slabs_per_group);
-      for (int il = 0; il < p.n_layers; ++il) {
-        const CLayer& L = p.layer[il];
-        if (L.kind != CE_FWD_BN && L.kind != CE_DGRAD_BN) continue;
-        if (et == 0)
-          for (int g = 0; g < groups; ++g) group_wait(L.counter + g, slabs_per_group, p.err);
-        bar_epi();
-        const int N = L.N;
-        const float cnt = static_cast<float>(p.rows_per_group);
-        for (int c = et; c < N; c += kCEpi) {
-          if (L.kind == CE_FWD_BN) {
-            if (L.running_mean == nullptr) continue;
-            float rm = L.running_mean[c], rv = L.running_var[c];
-            for (int g = 0; g < groups; ++g) {
-              const float mean = __ldcg(L.stat0 + g * N + c) / cnt;
-              const float var = fmaxf(__ldcg(L.stat1 + g * N + c) / cnt - mean * mean, 0.f);
-              const float unb = cnt > 1.f ? var * (cnt / (cnt - 1.f)) : var;
-              for (int u = 0; u < L.bn_updates; ++u) {
-                rm = (1.f - p.momentum) * rm + p.momentum * mean;
-                rv = (1.f - p.momentum) * rv + p.momentum * unb;
-              }
+  } else {
+    // =================================================================== keeper CTA: what needs every group's statistics,
+    // in group order (one reference forward pass per group), while the slab CTAs carry on
+    const int et = threadIdx.x - 64;
+    const int groups = p.n_slabs / static_cast<int>(slabs_per_group);
+    for (int il = 0; il < p.n_layers; ++il) {
+      const CLayer& L = p.layer[il];
+      if (L.kind != CE_FWD_BN && L.kind != CE_DGRAD_BN) continue;
+      if (et == 0)
+        for (int g = 0; g < groups; ++g) group_wait(L.counter + g, slabs_per_group, p.err);
+      bar_epi();
+      const int N = L.N;
+      const float cnt = static_cast<float>(p.rows_per_group);
+      for (int c = et; c < N; c += kCEpi) {
+        if (L.kind == CE_FWD_BN) {
+          if (L.running_mean == nullptr) continue;
+          float rm = L.running_mean[c], rv = L.running_var[c];
+          for (int g = 0; g < groups; ++g) {
+            const float mean = __ldcg(L.stat0 + g * N + c) / cnt;
+            const float var = fmaxf(__ldcg(L.stat1 + g * N + c) / cnt - mean * mean, 0.f);
+            const float unb = cnt > 1.f ? var * (cnt / (cnt - 1.f)) : var;
+            for (int u = 0; u < L.bn_updates; ++u) {
+              rm = (1.f - p.momentum) * rm + p.momentum * mean;
+              rv = (1.f - p.momentum) * rv + p.momentum * unb;
             }
-            L.running_mean[c] = rm;
-            L.running_var[c] = rv;
-          } else {
-            float dg = 0.f, db = 0.f;
-            for (int g = 0; g < groups; ++g) {
-              db += __ldcg(L.stat0 + g * N + c);
-              dg += __ldcg(L.stat1 + g * N + c);
-            }
-            if (L.dgamma != nullptr) {
-              L.dgamma[c] += dg;
-              L.dbeta[c] += db;
-            }
+          }
+          L.running_mean[c] = rm;
+          L.running_var[c] = rv;
+        } else {
+          float dg = 0.f, db = 0.f;
+          for (int g = 0; g < groups; ++g) {
+            db += __ldcg(L.stat0 + g * N + c);
+            dg += __ldcg(L.stat1 + g * N + c);
+          }
+          if (L.dgamma != nullptr) {
+            L.dgamma[c] += dg;
+            L.dbeta[c] += db;
           }
         }
       }
@@ -921,17 +875,47 @@ void set_lchunk(CLayer& L, int c, int n0, int w, int tmem, int buf) {
 int ksteps_of(int K) { return ((K - 1) % 64) / 16 + 1; }   // 16-wide k-steps in the last 64-wide panel
 int panels_of(int K) { return (K + 63) / 64; }
 
+constexpr int kFwdChunk = 112;   // K-major weight chunk of a resident-A layer: 112 rows x 128 B = 14336 B per stage
+constexpr int kBwdChunk = 128;   // MN-major: two 64 x 64 boxes = 16384 B per stage
+
+// Passes of one resident-A layer: one accumulator chunk per pass, TMEM column = layer column (BatchNorm / store layers),
+// or a ring of four 112-column buffers (`ring_tmem`, the 784-wide BCE layer).  Also fills the layer's chunk list.
+// Returns the next free pass index.
+int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bool b_mn, int first_a_wait, bool ring_tmem) {
+  const int Npad = (N + 15) & ~15;
+  const int cw = b_mn ? kBwdChunk : kFwdChunk;
+  const int nch = (Npad + cw - 1) / cw;
+  L.n_chunks = nch;
+  for (int c = 0; c < nch; ++c) {
+    CPass& ps = p.pass[ip++];
+    const int n0 = c * cw;
+    const int w = std::min(cw, Npad - n0);
+    ps.cfg = 1; ps.k_panels = panels_of(K); ps.last_ksteps = ksteps_of(K); ps.a_stream = -1;
+    ps.a_wait = c == 0 ? first_a_wait : 0; ps.b_tm = b_tm; ps.b_mn = b_mn ? 1 : 0; ps.n_chunks = 1;
+    const int tmem = ring_tmem ? (c & 3) * cw : n0;
+    const int buf = c & 3;
+    if (b_mn) {
+      const int boxes = (w + 63) / 64;
+      set_chunk(ps, 0, n0, w, boxes, boxes * 8192, 0, tmem, buf);
+    } else {
+      set_chunk(ps, 0, n0, w, 0, cw * 128, 0, tmem, buf);   // the box is always cw rows (rows beyond the matrix: zero fill)
+    }
+    set_lchunk(L, c, n0, w, tmem, buf);
+  }
+  return ip;
+}
+
 int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
   static const int coop = env_int("MVAE_CHAIN_COOP", 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(kCThreads);
-  cfg.dynamicSmemBytes = kChainSmem;
+  cfg.dynamicSmemBytes = kSmemTotal;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barriers cannot deadlock
@@ -945,18 +929,17 @@ int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
 
 long long* g_chain_dbg = nullptr;
 
-void init_params(CParams& p, int rows_per_group, unsigned int* err, int kind) {
+void init_params(CParams& p, int rows_per_group, int n_slabs, unsigned int* err, int kind) {
   memset(&p, 0, sizeof(p));
   p.dbg = g_chain_dbg != nullptr ? g_chain_dbg + static_cast<long long>(kind) * 148 * 32 : nullptr;
   p.rows_per_group = rows_per_group;
+  p.n_slabs = n_slabs;
   p.init_tm = -1;
   p.momentum = 0.1f;
   p.eps = 1e-5f;
   p.err = err;
-  p.ring[1] = CRing{kArena, 26624, 3, 0};
-  p.stg_off = kArena + 3 * 26624;   // [194560, 227328): behind the 3-stage weight ring
-  p.tab_off = kTabOffF;
-  p.dbg_flags = env_int("MVAE_CHAIN_DEBUG", 0);
+  p.ring[0] = CRing{kArena, kRing1Stage, kRing1Stages, 0};
+  p.ring[1] = p.ring[0];
 }
 
 }  // namespace
@@ -964,7 +947,7 @@ void init_params(CParams& p, int rows_per_group, unsigned int* err, int kind) {
 // bring-up: %globaltimer stamps of the chain kernels go to a device buffer of 4 x 148 x 32 int64 (null switches it off)
 void set_chain_debug_times(void* ptr) { g_chain_dbg = static_cast<long long*>(ptr); }
 
-// true if the chain kernels can run this step: all slabs whole, co-resident, dimensions inside the on-chip plan
+// true if the chain kernels can run this step: all slabs whole, co-resident (plus the keeper CTA), dimensions inside the on-chip plan
 bool chain_supported(int B, int G, int n) {
   static int sms = 0;
   if (sms == 0) {
@@ -972,197 +955,145 @@ bool chain_supported(int B, int G, int n) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
+  return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 + 1 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
 }
 
 int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   CParams p;
-  init_params(p, a.B, a.err, 0);
+  const int slabs = a.B / 128;
+  init_params(p, a.B, slabs, a.err, 0);
   const int n2 = 2 * a.n;
   if (chain_tmap(&p.tm[0], a.image, a.B, 784, 784, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208)) return 1;
-  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, 208)) return 1;
-  if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, n2)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, kFwdChunk)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, kFwdChunk)) return 1;
   p.tm[4] = p.tm[3];
-  p.ring[0] = CRing{0, kPanel + 2 * 26624, 3, kPanel};
-  p.n_pass = 3;
+  p.ring[0] = CRing{0, kPanel + 2 * 26624, 2, kPanel};   // streamed image panel + all 400 rows of W1 per 64-wide k panel
+  p.n_layers = 3;
+  CLayer& l1 = p.layer[0];
+  CLayer& l2 = p.layer[1];
+  CLayer& l3 = p.layer[2];
   CPass& e1 = p.pass[0];
   e1.cfg = 0; e1.k_panels = panels_of(784); e1.last_ksteps = ksteps_of(784); e1.a_stream = 0; e1.a_wait = 0; e1.b_tm = 1; e1.b_mn = 0;
   e1.n_chunks = 2;
   set_chunk(e1, 0, 0, 208, 0, 26624, 0, 0, 0);
-  set_chunk(e1, 1, 208, 192, 0, 26624, 26624, 256, 1);
-  CPass& e2 = p.pass[1];
-  e2.cfg = 1; e2.k_panels = panels_of(400); e2.last_ksteps = ksteps_of(400); e2.a_stream = -1; e2.a_wait = 2; e2.b_tm = 2; e2.b_mn = 0;
-  e2.n_chunks = 1;
-  set_chunk(e2, 0, 0, 208, 0, 26624, 0, 0, 0);
-  CPass& e3 = p.pass[2];
-  e3.cfg = 1; e3.k_panels = panels_of(200); e3.last_ksteps = ksteps_of(200); e3.a_stream = -1; e3.a_wait = 2; e3.b_tm = 3; e3.b_mn = 0;
-  e3.n_chunks = 1;
-  set_chunk(e3, 0, 0, n2, 0, n2 * 128, 0, 256, 1);
-  p.n_layers = 3;
-  CLayer& l1 = p.layer[0];
+  set_chunk(e1, 1, 208, 192, 0, 26624, 26624, 208, 1);
   l1.kind = CE_FWD_BN; l1.N = 400; l1.n_chunks = 2;
   set_lchunk(l1, 0, 0, 208, 0, 0);
-  set_lchunk(l1, 1, 208, 192, 256, 1);
+  set_lchunk(l1, 1, 208, 192, 208, 1);
+  int ip = 1;
+  ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false);
+  ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false);
+  p.n_pass = ip;
   l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + 400;
   l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = a.bn_updates;
   l1.counter = a.counters; l1.out_pre = a.h1pre; l1.out_post = a.h1; l1.write_arena = 1;
-  CLayer& l2 = p.layer[1];
-  l2.kind = CE_FWD_BN; l2.N = 200; l2.n_chunks = 1;
-  set_lchunk(l2, 0, 0, 208, 0, 0);
+  l2.kind = CE_FWD_BN; l2.N = 200;
   l2.bias = a.b2; l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.st2; l2.stat1 = a.st2 + 200;
   l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + 200; l2.running_mean = a.rm2; l2.running_var = a.rv2; l2.bn_updates = a.bn_updates;
   l2.counter = a.counters + 1; l2.out_pre = a.h2pre; l2.out_post = a.h2; l2.write_arena = 1;
-  CLayer& l3 = p.layer[2];
-  l3.kind = CE_FWD_STORE; l3.N = n2; l3.n_chunks = 1;
-  set_lchunk(l3, 0, 0, n2, 256, 1);
+  l3.kind = CE_FWD_STORE; l3.N = n2;
   l3.bias = a.b3; l3.out_f32 = a.enc; l3.ld_out = n2;
-  note_launch(1);
-  return launch_chain(p, a.B / 128, st);
+  return launch_chain(p, slabs + 1, st);
 }
 
 int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   CParams p;
   const int R = a.G * a.B, G = a.G;
-  init_params(p, a.B, a.err, 1);
+  init_params(p, a.B, R / 128, a.err, 1);
   if (chain_tmap(&p.tm[0], a.z, R, a.n, a.n, 64, 128)) return 1;
-  if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, 208)) return 1;
-  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 208)) return 1;
-  if (chain_tmap(&p.tm[3], a.w3, 784, 400, 400, 64, 208)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, kFwdChunk)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, kFwdChunk)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, 784, 400, 400, 64, kFwdChunk)) return 1;
   p.tm[4] = p.tm[3];
-  p.ring[0] = p.ring[1];
   p.init_tm = 0;
   p.init_panels = panels_of(a.n);
-  p.n_pass = 7;
-  CPass& d1 = p.pass[0];
-  d1.cfg = 1; d1.k_panels = panels_of(a.n); d1.last_ksteps = ksteps_of(a.n); d1.a_stream = -1; d1.a_wait = 1; d1.b_tm = 1; d1.b_mn = 0;
-  d1.n_chunks = 1;
-  set_chunk(d1, 0, 0, 208, 0, 26624, 0, 0, 0);
-  for (int c = 0; c < 2; ++c) {
-    CPass& d2 = p.pass[1 + c];
-    d2.cfg = 1; d2.k_panels = panels_of(200); d2.last_ksteps = ksteps_of(200); d2.a_stream = -1; d2.a_wait = c == 0 ? 2 : 0; d2.b_tm = 2;
-    d2.b_mn = 0; d2.n_chunks = 1;
-    set_chunk(d2, 0, c == 0 ? 0 : 208, c == 0 ? 208 : 192, 0, 26624, 0, c * 256, c);
-  }
-  const int n0s[4] = {0, 192, 384, 576}, ws[4] = {192, 192, 192, 208};   // chunk boundaries at multiples of 64 (epilogue blocks)
-  for (int c = 0; c < 4; ++c) {
-    CPass& d3 = p.pass[3 + c];
-    d3.cfg = 1; d3.k_panels = panels_of(400); d3.last_ksteps = ksteps_of(400); d3.a_stream = -1; d3.a_wait = c == 0 ? 2 : 0; d3.b_tm = 3;
-    d3.b_mn = 0; d3.n_chunks = 1;
-    set_chunk(d3, 0, n0s[c], ws[c], 0, 26624, 0, (c & 1) * 256, c & 1);
-  }
   p.n_layers = 3;
   CLayer& l1 = p.layer[0];
-  l1.kind = CE_FWD_BN; l1.N = 200; l1.n_chunks = 1;
-  set_lchunk(l1, 0, 0, 208, 0, 0);
+  CLayer& l2 = p.layer[1];
+  CLayer& l3 = p.layer[2];
+  int ip = 0;
+  ip = add_resident_layer(p, ip, l1, 200, a.n, 1, false, 1, false);
+  ip = add_resident_layer(p, ip, l2, 400, 200, 2, false, 2, false);
+  ip = add_resident_layer(p, ip, l3, 784, 400, 3, false, 2, true);
+  p.n_pass = ip;
+  l1.kind = CE_FWD_BN; l1.N = 200;
   l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + G * 200;
   l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + G * 200; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = 1;
   l1.counter = a.counters; l1.out_pre = a.g1pre; l1.out_post = a.g1; l1.write_arena = 1;
-  CLayer& l2 = p.layer[1];
-  l2.kind = CE_FWD_BN; l2.N = 400; l2.n_chunks = 2;
-  set_lchunk(l2, 0, 0, 208, 0, 0);
-  set_lchunk(l2, 1, 208, 192, 256, 1);
+  l2.kind = CE_FWD_BN; l2.N = 400;
   l2.bias = a.b2; l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.st2; l2.stat1 = a.st2 + G * 400;
   l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + G * 400; l2.running_mean = a.rm2; l2.running_var = a.rv2; l2.bn_updates = 1;
   l2.counter = a.counters + 3; l2.out_pre = a.g2pre; l2.out_post = a.g2; l2.write_arena = 1;
-  CLayer& l3 = p.layer[2];
-  l3.kind = CE_BCE; l3.N = 784; l3.n_chunks = 4;
-  for (int c = 0; c < 4; ++c) set_lchunk(l3, c, n0s[c], ws[c], (c & 1) * 256, c & 1);
+  l3.kind = CE_BCE; l3.N = 784;
   l3.bias = a.b3; l3.target = a.image; l3.target_rows = a.B;
   for (int g = 0; g < 3; ++g) l3.bce_scale[g] = a.bce_scale[g];
   l3.loss = a.loss; l3.dbias = a.dbias3; l3.dlog = a.dlog; l3.probs = a.probs;
-  note_launch(1);
-  return launch_chain(p, R / 128, st);
+  return launch_chain(p, R / 128 + 1, st);
 }
 
 int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   CParams p;
   const int R = a.G * a.B, G = a.G;
-  init_params(p, a.B, a.err, 2);
+  init_params(p, a.B, R / 128, a.err, 2);
   if (chain_tmap(&p.tm[0], a.dlog, R, 784, 784, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w3, 784, 400, 400, 64, 64)) return 1;   // dgrad: W[out, in] read as the MN-major B operand
   if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 64)) return 1;
   if (chain_tmap(&p.tm[3], a.w1, 200, a.n, a.n, 64, 64)) return 1;
   p.tm[4] = p.tm[3];
-  p.ring[0] = CRing{0, 73728, 3, kPanel};
-  p.ring[1] = CRing{kArena, 32768, 2, 0};
-  p.stg_off = kArena + 2 * 32768;   // [180224, 212992)
-  p.tab_off = kTabOffB;
-  p.n_pass = 3;
+  p.ring[0] = CRing{0, kPanel + 7 * 8192, 2, kPanel};   // streamed dlogits panel + all 400 columns of W3 per 64-wide k panel
+  p.n_layers = 3;
+  CLayer& l2 = p.layer[0];
+  CLayer& l1 = p.layer[1];
+  CLayer& l0 = p.layer[2];
   CPass& g3 = p.pass[0];
   g3.cfg = 0; g3.k_panels = panels_of(784); g3.last_ksteps = ksteps_of(784); g3.a_stream = 0; g3.a_wait = 0; g3.b_tm = 1; g3.b_mn = 1;
   g3.n_chunks = 2;
   set_chunk(g3, 0, 0, 256, 4, 32768, 0, 0, 0);
   set_chunk(g3, 1, 256, 144, 3, 24576, 32768, 256, 1);
-  CPass& g2 = p.pass[1];
-  g2.cfg = 1; g2.k_panels = panels_of(400); g2.last_ksteps = ksteps_of(400); g2.a_stream = -1; g2.a_wait = 2; g2.b_tm = 2; g2.b_mn = 1;
-  g2.n_chunks = 1;
-  set_chunk(g2, 0, 0, 208, 4, 32768, 0, 0, 0);
-  CPass& g1 = p.pass[2];
-  const int nb = (a.n + 63) / 64;
-  g1.cfg = 1; g1.k_panels = panels_of(200); g1.last_ksteps = ksteps_of(200); g1.a_stream = -1; g1.a_wait = 2; g1.b_tm = 3; g1.b_mn = 1;
-  g1.n_chunks = 1;
-  set_chunk(g1, 0, 0, a.n, nb, nb * 8192, 0, 256, 1);
-  p.n_layers = 3;
-  CLayer& l2 = p.layer[0];
   l2.kind = CE_DGRAD_BN; l2.N = 400; l2.n_chunks = 2;
   set_lchunk(l2, 0, 0, 256, 0, 0);
   set_lchunk(l2, 1, 256, 144, 256, 1);
+  int ip = 1;
+  ip = add_resident_layer(p, ip, l1, 200, 400, 2, true, 2, false);
+  ip = add_resident_layer(p, ip, l0, a.n, 200, 3, true, 2, false);
+  p.n_pass = ip;
   l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + G * 400; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + G * 400;
   l2.counter = a.counters; l2.hpre = a.g2pre; l2.out_post = a.dy2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
-  CLayer& l1 = p.layer[1];
-  l1.kind = CE_DGRAD_BN; l1.N = 200; l1.n_chunks = 1;
-  set_lchunk(l1, 0, 0, 208, 0, 0);
+  l1.kind = CE_DGRAD_BN; l1.N = 200;
   l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + G * 200; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + G * 200;
   l1.counter = a.counters + 3; l1.hpre = a.g1pre; l1.out_post = a.dy1; l1.write_arena = 1; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
-  CLayer& l0 = p.layer[2];
-  l0.kind = CE_DGRAD_STORE; l0.N = a.n; l0.n_chunks = 1;
-  set_lchunk(l0, 0, 0, a.n, 256, 1);
+  l0.kind = CE_DGRAD_STORE; l0.N = a.n;
   l0.out_f32 = a.dz; l0.ld_out = a.n;
-  note_launch(1);
-  return launch_chain(p, R / 128, st);
+  return launch_chain(p, R / 128 + 1, st);
 }
 
 int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   CParams p;
-  init_params(p, a.B, a.err, 3);
+  const int slabs = a.B / 128;
+  init_params(p, a.B, slabs, a.err, 3);
   const int n2 = 2 * a.n;
   if (chain_tmap(&p.tm[0], a.denc, a.B, n2, n2, 64, 128)) return 1;
   if (chain_tmap(&p.tm[1], a.w3, n2, 200, 200, 64, 64)) return 1;
   if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, 64)) return 1;
   p.tm[3] = p.tm[2];
   p.tm[4] = p.tm[2];
-  p.ring[1] = CRing{kArena, 32768, 2, 0};
-  p.stg_off = kArena + 2 * 32768;
-  p.tab_off = kTabOffB;
-  p.ring[0] = p.ring[1];
   p.init_tm = 0;
   p.init_panels = panels_of(n2);
-  p.n_pass = 3;
-  CPass& g3 = p.pass[0];
-  g3.cfg = 1; g3.k_panels = panels_of(n2); g3.last_ksteps = ksteps_of(n2); g3.a_stream = -1; g3.a_wait = 1; g3.b_tm = 1; g3.b_mn = 1;
-  g3.n_chunks = 1;
-  set_chunk(g3, 0, 0, 208, 4, 32768, 0, 0, 0);
-  for (int c = 0; c < 2; ++c) {
-    CPass& g2 = p.pass[1 + c];
-    g2.cfg = 1; g2.k_panels = panels_of(200); g2.last_ksteps = ksteps_of(200); g2.a_stream = -1; g2.a_wait = c == 0 ? 2 : 0; g2.b_tm = 2;
-    g2.b_mn = 1; g2.n_chunks = 1;
-    set_chunk(g2, 0, c == 0 ? 0 : 256, c == 0 ? 256 : 144, c == 0 ? 4 : 3, c == 0 ? 32768 : 24576, 0, c * 256, c);
-  }
   p.n_layers = 2;
   CLayer& l2 = p.layer[0];
-  l2.kind = CE_DGRAD_BN; l2.N = 200; l2.n_chunks = 1;
-  set_lchunk(l2, 0, 0, 208, 0, 0);
+  CLayer& l1 = p.layer[1];
+  int ip = 0;
+  ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false);
+  ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false);
+  p.n_pass = ip;
+  l2.kind = CE_DGRAD_BN; l2.N = 200;
   l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + 200; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + 200;
   l2.counter = a.counters; l2.hpre = a.h2pre; l2.out_post = a.dye2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
-  CLayer& l1 = p.layer[1];
-  l1.kind = CE_DGRAD_BN; l1.N = 400; l1.n_chunks = 2;
-  set_lchunk(l1, 0, 0, 256, 0, 0);
-  set_lchunk(l1, 1, 256, 144, 256, 1);
+  l1.kind = CE_DGRAD_BN; l1.N = 400;
   l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + 400; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400;
   l1.counter = a.counters + 1; l1.hpre = a.h1pre; l1.out_post = a.dye1; l1.write_arena = 0; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
-  note_launch(1);
-  return launch_chain(p, a.B / 128, st);
+  return launch_chain(p, slabs + 1, st);
 }
 
 }  // namespace mvae
