@@ -29,6 +29,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -52,12 +53,11 @@ constexpr int kTabFloats = 1600;                // coefficient tables: 4 x 400 f
 constexpr int kTabOff = kRedOff - kTabFloats * 4;
 constexpr int kTileBytes = 2048;                // per epilogue warp: 16 rows x 32 fp32
 constexpr int kTileOff = kTabOff - kEpiWarps * kTileBytes;
-constexpr int kRing1Stage = 16384;              // resident-A layers: one weight chunk (<= 128 rows K-major / two 64x64 boxes MN-major)
-constexpr int kRing1Stages = 4;
+constexpr int kRing1Stage = 32768;              // resident-A layers: one weight chunk (<= 224 rows K-major / four 64x64 boxes MN-major)
+constexpr int kRing1Stages = 2;
 static_assert(kArena + kRing1Stages * kRing1Stage <= kTileOff, "ring 1 overlaps the epilogue tiles");
 constexpr int kMaxPass = 16;
 constexpr int kMaxLayer = 3;
-constexpr int kMaxChunk = 8;
 
 enum : int { CE_FWD_BN = 0, CE_FWD_STORE = 1, CE_BCE = 2, CE_DGRAD_BN = 3, CE_DGRAD_STORE = 4 };
 
@@ -85,8 +85,9 @@ struct CPass {
 };
 
 struct CLayer {
-  int kind, N, n_chunks;
-  int c_n0[kMaxChunk], c_w[kMaxChunk], c_tmem[kMaxChunk], c_buf[kMaxChunk];   // BatchNorm / store layers: TMEM column = layer column
+  int kind, N, n_chunks;   // accumulator chunk ci uses barrier pair ci (BatchNorm / store layers: TMEM column = layer column)
+  int u1, u2, u3;          // BCE layer: first 32-column unit of chunks 1, 2, 3 (chunk ci sits in TMEM buffer ci & 1)
+  int buf_cols;            // BCE layer: TMEM columns per accumulator buffer
   const float* bias;
   const float* gamma;
   const float* beta;
@@ -148,6 +149,39 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, unsi
       asm volatile("trap;");
     }
   }
+}
+
+// the same for the 16 epilogue warps: they back off between polls, so that their spinning does not take issue slots from
+// the producer / MMA threads that share their schedulers
+__device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned int code) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = gtimer();
+  unsigned int spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if ((++spins & 255u) == 0 && gtimer() - t0 > 4000000000ull) {
+      if (err != nullptr) atomicExch(err, code);
+      __threadfence();
+      asm volatile("trap;");
+    }
+  }
+}
+
+// tcgen05.mma (bf16 x bf16 -> fp32) from shared-memory descriptors given as (low word, shared high word): SWIZZLE_128B,
+// 8-row groups 1024 bytes apart, descriptor version 1.  The low word is (address >> 4) | (leading byte offset >> 4) << 16.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __device__ __forceinline__ void bar_epi() { ptx::named_bar_sync(1, kCEpi); }
@@ -223,6 +257,10 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   return r;
 }
 
+// The layer kinds are template parameters and the layer sequence is unrolled at compile time: `p.layer[il].x` is then a
+// direct constant-bank operand (an indexed constant load behind an asm statement costs hundreds of cycles on the long
+// scoreboard), and every instantiation carries only the epilogues it runs.
+template <int kKind0, int kKind1, int kKind2>
 __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_constant__ CParams p) {
   // No static shared memory: the dynamic window then starts 1024-byte aligned (checked below), which the SWIZZLE_128B
   // tiles need, and every byte of the 227 KB is planned: [arena | weight ring | tiles | tables | reduction table | barriers].
@@ -296,28 +334,35 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           cur_cfg = ps.cfg;
           s = 0;
         }
-        uint32_t bytes = ps.a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u;
-        for (int c = 0; c < ps.n_chunks; ++c) bytes += static_cast<uint32_t>(ps.c_bytes[c]);
-        for (int kp = 0; kp < ps.k_panels; ++kp) {
+        // everything the k loop needs lives in registers: a parameter read behind an asm statement is an indexed constant load
+        const int k_panels = ps.k_panels, a_stream = ps.a_stream, b_mn = ps.b_mn, nch = ps.n_chunks;
+        const int n0_0 = ps.c_n0[0], n0_1 = ps.c_n0[1], boff_0 = ps.c_boff[0], boff_1 = ps.c_boff[1];
+        const int boxes_0 = ps.c_boxes[0], boxes_1 = ps.c_boxes[1];
+        const CUtensorMap* tm_a = &p.tm[a_stream >= 0 ? a_stream : 0];
+        const CUtensorMap* tm_b = &p.tm[ps.b_tm];
+        const int ring_base = rg.base, stage_bytes = rg.stage_bytes, a_bytes = rg.a_bytes;
+        const uint32_t bytes = (a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u) + static_cast<uint32_t>(ps.c_bytes[0]) +
+                               (nch > 1 ? static_cast<uint32_t>(ps.c_bytes[1]) : 0u);
+        for (int kp = 0; kp < k_panels; ++kp) {
           mbar_wait_b(&empty_bar[s], ((fill_par >> s) & 1u) ^ 1u, p.err, 0x110u + s);
           ptx::mbar_expect_tx(&full_bar[s], bytes);
-          uint8_t* stage = smem + rg.base + s * rg.stage_bytes;
-          if (ps.a_stream >= 0) ptx::tma_load_2d(stage, &p.tm[ps.a_stream], &full_bar[s], kp * 64, m0);
-          uint8_t* bslot = stage + rg.a_bytes;
-          for (int c = 0; c < ps.n_chunks; ++c) {
-            if (!ps.b_mn) {
-              ptx::tma_load_2d(bslot + ps.c_boff[c], &p.tm[ps.b_tm], &full_bar[s], kp * 64, ps.c_n0[c]);
-            } else {
-              for (int jb = 0; jb < ps.c_boxes[c]; ++jb)
-                ptx::tma_load_2d(bslot + ps.c_boff[c] + jb * 8192, &p.tm[ps.b_tm], &full_bar[s], ps.c_n0[c] + jb * 64, kp * 64);
-            }
+          uint8_t* stage = smem + ring_base + s * stage_bytes;
+          if (a_stream >= 0) ptx::tma_load_2d(stage, tm_a, &full_bar[s], kp * 64, m0);
+          uint8_t* bslot = stage + a_bytes;
+          if (!b_mn) {
+            ptx::tma_load_2d(bslot + boff_0, tm_b, &full_bar[s], kp * 64, n0_0);
+            if (nch > 1) ptx::tma_load_2d(bslot + boff_1, tm_b, &full_bar[s], kp * 64, n0_1);
+          } else {
+            for (int jb = 0; jb < boxes_0; ++jb) ptx::tma_load_2d(bslot + boff_0 + jb * 8192, tm_b, &full_bar[s], n0_0 + jb * 64, kp * 64);
+            if (nch > 1)
+              for (int jb = 0; jb < boxes_1; ++jb) ptx::tma_load_2d(bslot + boff_1 + jb * 8192, tm_b, &full_bar[s], n0_1 + jb * 64, kp * 64);
           }
           fill_par ^= 1u << s;
           fill_any |= 1u << s;
           if (++s == rg.stages) s = 0;
         }
+        if (ip < 8) stamp(1 + ip);
       }
-      stamp(1);
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
@@ -348,25 +393,28 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         const uint32_t idesc1 = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[nc - 1]);
         const uint32_t boff0 = ps.c_boff[0], boff1 = ps.c_boff[nc - 1];
         const uint32_t tm0 = tmem_base + ps.c_tmem[0], tm1 = tmem_base + ps.c_tmem[nc - 1];
-        const int b_mn = ps.b_mn;
-        for (int kp = 0; kp < ps.k_panels; ++kp) {
+        const int b_mn = ps.b_mn, k_panels = ps.k_panels, last_ksteps = ps.last_ksteps, a_stream = ps.a_stream;
+        const int ring_base = rg.base, stage_bytes = rg.stage_bytes, a_bytes = rg.a_bytes;
+        const uint32_t b_lbo = b_mn ? ((8192u >> 4) << 16) : (1u << 16);   // MN-major: 64-column boxes 8 KB apart
+        const uint32_t b_kstep = b_mn ? (2048u >> 4) : 2u;                 // 16 k-rows of an MN-major box / 32 bytes of a K-major row
+        for (int kp = 0; kp < k_panels; ++kp) {
           mbar_wait_b(&full_bar[s], (use_par >> s) & 1u, p.err, 0x220u + s);
           use_par ^= 1u << s;
           ptx::tc_fence_after();
-          const uint32_t stage = smem_u + rg.base + s * rg.stage_bytes;
-          const uint32_t a_base = ps.a_stream >= 0 ? stage : smem_u + kp * kPanel;
-          const uint32_t bslot = stage + rg.a_bytes;
-          const int nks = (kp == ps.k_panels - 1) ? ps.last_ksteps : 4;
-          for (int ks = 0; ks < nks; ++ks) {
-            const uint64_t adesc = ptx::make_smem_desc(a_base + ks * 32, 16, 1024);
-            const uint32_t acc = (kp | ks) != 0 ? 1u : 0u;
-            const uint64_t bd0 = b_mn ? ptx::make_smem_desc(bslot + boff0 + ks * 2048, 8192, 1024, 2)
-                                      : ptx::make_smem_desc(bslot + boff0 + ks * 32, 16, 1024);
-            ptx::umma<MVAE_BF16>(tm0, adesc, bd0, idesc0, acc);
-            if (nc > 1) {
-              const uint64_t bd1 = b_mn ? ptx::make_smem_desc(bslot + boff1 + ks * 2048, 8192, 1024, 2)
-                                        : ptx::make_smem_desc(bslot + boff1 + ks * 32, 16, 1024);
-              ptx::umma<MVAE_BF16>(tm1, adesc, bd1, idesc1, acc);
+          const uint32_t stage = smem_u + ring_base + s * stage_bytes;
+          const uint32_t a_base = a_stream >= 0 ? stage : smem_u + kp * kPanel;
+          const uint32_t bslot = stage + a_bytes;
+          const int nks = (kp == k_panels - 1) ? last_ksteps : 4;
+          // descriptors are built once per stage; a k-step only advances their 16-byte-unit address fields
+          const uint32_t a_lo = ((a_base & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t b0_lo = (((bslot + boff0) & 0x3FFFFu) >> 4) | b_lbo;
+          const uint32_t b1_lo = (((bslot + boff1) & 0x3FFFFu) >> 4) | b_lbo;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (ks < nks) {
+              const uint32_t acc = (kp | ks) != 0 ? 1u : 0u;
+              umma_bf16_lohi(tm0, a_lo + 2 * ks, b0_lo + b_kstep * ks, kDescHi, idesc0, acc);
+              if (nc > 1) umma_bf16_lohi(tm1, a_lo + 2 * ks, b1_lo + b_kstep * ks, kDescHi, idesc1, acc);
             }
           }
           ptx::umma_commit(&empty_bar[s]);
@@ -420,25 +468,23 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       __syncwarp();
     };
 
-    for (int il = 0; il < p.n_layers; ++il) {
+    auto run_layer = [&](auto kind_c, auto il_c) {
+      constexpr int kKind = decltype(kind_c)::value;
+      constexpr int il = decltype(il_c)::value;
       const CLayer& L = p.layer[il];
       const int N = L.N;
       const int Npad = (N + 15) & ~15;
       const int n_units = (Npad + 31) >> 5;
       if (et == 0) stamp(17 + il * 4);
       auto wait_all_chunks = [&]() {
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
-        }
+        for (int ci = 0; ci < L.n_chunks; ++ci) mbar_wait_epi(&acc_full[ci], (epi_par >> ci) & 1u, p.err, 0x300u + il * 16 + ci);
         ptx::tc_fence_after();
       };
       auto release_all_chunks = [&]() {
         ptx::tc_fence_before();
         for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          ptx::mbar_arrive(&acc_empty[b]);
-          epi_par ^= 1u << b;
+          ptx::mbar_arrive(&acc_empty[ci]);
+          epi_par ^= 1u << ci;
         }
       };
       // publish the slab's column sums: red[quarter][stat][column] -> one global atomic per column and statistic
@@ -452,7 +498,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
       };
 
-      if (L.kind == CE_FWD_BN) {
+      if constexpr (kKind == CE_FWD_BN) {
         float* s_bias = tab;
         float* s_ca = tab + 400;
         float* s_cb = tab + 800;
@@ -545,7 +591,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(a_epi_bar);
         }
-      } else if (L.kind == CE_DGRAD_BN) {
+      } else if constexpr (kKind == CE_DGRAD_BN) {
         float* s_a = tab;
         float* s_b = tab + 400;
         float* s_rs = tab + 800;    // pass 1: rstd            pass 2: k1 = a * mean(dyhat * xhat) * rstd
@@ -671,7 +717,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(a_epi_bar);
         }
-      } else if (L.kind == CE_FWD_STORE || L.kind == CE_DGRAD_STORE) {
+      } else if constexpr (kKind == CE_FWD_STORE || kKind == CE_DGRAD_STORE) {
         float* s_bias = tab;
         for (int c = et; c < 400; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
         bar_epi();
@@ -697,79 +743,100 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
         }
         release_all_chunks();
-      } else if (L.kind == CE_BCE) {
+      } else if constexpr (kKind == CE_BCE) {
         // last decoder Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70): logits never leave the SM.
         // loss = softplus(x) - t x, dlogit = scale * (sigmoid(x) - t); also the bias gradient (column sums of dlogit).
         float* s_bias = tab;
         for (int c = et; c < 800; c += kCEpi) s_bias[c] = c < N ? L.bias[c] : 0.f;
         bar_epi();
-        const float scale = L.bce_scale[grp];
+        const float scale = grp == 0 ? L.bce_scale[0] : (grp == 1 ? L.bce_scale[1] : L.bce_scale[2]);
         const __nv_bfloat16* tbase = L.target + (static_cast<long long>(m0 % L.target_rows) + q * 32) * N;
         float lin = 0.f, llog = 0.f;   // sum of max(x, 0) - t x  and  sum of log2 sigmoid(|x|)
-        for (int ci = 0; ci < L.n_chunks; ++ci) {
-          const int b = L.c_buf[ci];
-          const int cw = L.c_w[ci];
-          const int uu = (jw - ci) & 3;   // rotate the (narrower) last unit of a chunk over the four warps of a quarter
-          mbar_wait_b(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci);
-          ptx::tc_fence_after();
-          if (32 * uu < cw) {
-            const int col0 = L.c_n0[ci] + 32 * uu + 4 * cq;
-            const bool live = 32 * uu + 4 * cq < cw && col0 < N;
-            uint2 tx[8];
+        // The accumulator arrives in chunks (TMEM buffer = chunk & 1) while the MMA warp works on the next one; the 32-column
+        // units of the whole layer go round-robin over the four warps of a quarter.  Every warp waits for and releases every
+        // chunk in order (an arrival on a buffer's "empty" barrier must follow this warp's wait on its "full" phase).
+        const int u1 = L.u1, u2 = L.u2, u3 = L.u3, n_chunks = L.n_chunks, buf_cols = L.buf_cols;
+        int ci_waited = -1;
+        for (int u = jw; u < n_units; u += 4) {
+          const int ci = (u >= u1 ? 1 : 0) + (u >= u2 ? 1 : 0) + (u >= u3 ? 1 : 0);
+          const int ustart = ci == 0 ? 0 : (ci == 1 ? u1 : (ci == 2 ? u2 : u3));
+          const int col0 = 32 * u + 4 * cq;
+          const bool live = col0 < N;
+          uint2 tx[8];   // [half][i] -> 4 bf16 targets, in flight during the barrier wait and the TMEM load
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              tx[k] = live ? __ldg(reinterpret_cast<const uint2*>(tbase + ((k >> 2) * 16 + 4 * rsel + (k & 3)) * static_cast<long long>(N) + col0))
-                           : make_uint2(0u, 0u);
-            uint32_t v[32];
-            load_unit(t_row + L.c_tmem[ci] + 32 * uu, 32 * uu + 16 < cw, v);
-            const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
-            float sd[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              deposit(half, v);
-              if (live) {
-                const long long orow = (wrow0 + half * 16 + 4 * rsel) * N + col0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
-                  const float av[4] = {a.x, a.y, a.z, a.w};
-                  const uint2 tw = tx[half * 4 + i];
-                  const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
-                  float d[4], pr[4];
-                  float prod = 1.f;
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float x = av[e] + bsv[e];
-                    const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
-                    const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
-                    pr[e] = x >= 0.f ? inv : ex * inv;
-                    d[e] = scale * (pr[e] - tv[e]);
-                    sd[e] += d[e];
-                    prod *= inv;                                                           // >= 1/16: one log per four elements
-                    lin += fmaf(-tv[e], x, fmaxf(x, 0.f));                                 // softplus(x) - t x = max(x,0) - t x - ln sigmoid(|x|)
-                  }
-                  llog += ptx::lg2_approx(prod);
-                  *reinterpret_cast<uint2*>(L.dlog + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
-                  if (L.probs != nullptr)
-                    *reinterpret_cast<uint2*>(L.probs + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
-                }
-              }
-              __syncwarp();
+          for (int k = 0; k < 8; ++k)
+            tx[k] = live ? __ldg(reinterpret_cast<const uint2*>(tbase + ((k >> 2) * 16 + 4 * rsel + (k & 3)) * static_cast<long long>(N) + col0))
+                         : make_uint2(0u, 0u);
+          while (ci_waited < ci) {
+            if (ci_waited >= 0) {   // done with chunk ci_waited
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
             }
-            if (L.dbias != nullptr) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 8);
-                sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 16);
-              }
-              if (live && rsel == 0) *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(sd[0], sd[1], sd[2], sd[3]);
-            }
+            ++ci_waited;
+            const int b = ci_waited & 1;
+            mbar_wait_epi(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci_waited);
+            epi_par ^= 1u << b;
+            ptx::tc_fence_after();
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&acc_empty[b]);
+          uint32_t v[32];
+          load_unit(t_row + (ci & 1) * buf_cols + 32 * (u - ustart), 32 * u + 16 < Npad, v);
+          const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+          float sd[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            deposit(half, v);
+            if (live) {
+              const long long orow = (wrow0 + half * 16 + 4 * rsel) * N + col0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const float av[4] = {a.x, a.y, a.z, a.w};
+                const uint2 tw = tx[half * 4 + i];
+                const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
+                float d[4], pr[4];
+                float prod = 1.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float x = av[e] + bsv[e];
+                  const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
+                  const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
+                  pr[e] = x >= 0.f ? inv : ex * inv;
+                  d[e] = scale * (pr[e] - tv[e]);
+                  sd[e] += d[e];
+                  prod *= inv;                                                           // >= 1/16: one log per four elements
+                  lin += fmaf(-tv[e], x, fmaxf(x, 0.f));                                 // softplus(x) - t x = max(x,0) - t x - ln sigmoid(|x|)
+                }
+                llog += ptx::lg2_approx(prod);
+                *reinterpret_cast<uint2*>(L.dlog + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
+                if (L.probs != nullptr)
+                  *reinterpret_cast<uint2*>(L.probs + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
+              }
+            }
+            __syncwarp();
+          }
+          if (L.dbias != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 8);
+              sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 16);
+            }
+            if (live && rsel == 0) *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+          }
+        }
+        // the remaining chunks (this warp has no more units in them)
+        while (ci_waited < n_chunks - 1) {
+          if (ci_waited >= 0) {
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
+          }
+          ++ci_waited;
+          const int b = ci_waited & 1;
+          mbar_wait_epi(&acc_full[b], (epi_par >> b) & 1u, p.err, 0x300u + il * 16 + ci_waited);
           epi_par ^= 1u << b;
         }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
         float lsum = fmaf(-0.6931471805599453f, llog, lin);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
@@ -782,7 +849,10 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       }
       bar_epi();   // the tables are reused by the next layer
       if (et == 0) stamp(20 + il * 4);
-    }
+    };
+    run_layer(std::integral_constant<int, kKind0>{}, std::integral_constant<int, 0>{});
+    run_layer(std::integral_constant<int, kKind1>{}, std::integral_constant<int, 1>{});
+    if constexpr (kKind2 >= 0) run_layer(std::integral_constant<int, kKind2>{}, std::integral_constant<int, 2>{});
   } else {
     // =================================================================== keeper CTA: what needs every group's statistics,
     // in group order (one reference forward pass per group), while the slab CTAs carry on
@@ -869,46 +939,66 @@ void set_chunk(CPass& ps, int c, int n0, int mma_n, int boxes, int bytes, int bo
   ps.c_n0[c] = n0; ps.c_mma_n[c] = mma_n; ps.c_boxes[c] = boxes; ps.c_bytes[c] = bytes; ps.c_boff[c] = boff;
   ps.c_tmem[c] = tmem; ps.c_buf[c] = buf;
 }
-void set_lchunk(CLayer& L, int c, int n0, int w, int tmem, int buf) {
-  L.c_n0[c] = n0; L.c_w[c] = w; L.c_tmem[c] = tmem; L.c_buf[c] = buf;
-}
 int ksteps_of(int K) { return ((K - 1) % 64) / 16 + 1; }   // 16-wide k-steps in the last 64-wide panel
 int panels_of(int K) { return (K + 63) / 64; }
 
-constexpr int kFwdChunk = 112;   // K-major weight chunk of a resident-A layer: 112 rows x 128 B = 14336 B per stage
-constexpr int kBwdChunk = 128;   // MN-major: two 64 x 64 boxes = 16384 B per stage
+constexpr int kFwdChunk = 224;   // K-major weight chunk of a resident-A layer: 224 rows x 128 B = 28672 B per stage
+constexpr int kBwdChunk = 256;   // MN-major: four 64 x 64 boxes = 32768 B per stage
 
-// Passes of one resident-A layer: one accumulator chunk per pass, TMEM column = layer column (BatchNorm / store layers),
-// or a ring of four 112-column buffers (`ring_tmem`, the 784-wide BCE layer).  Also fills the layer's chunk list.
-// Returns the next free pass index.
-int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bool b_mn, int first_a_wait, bool ring_tmem) {
+// Passes of one resident-A layer: one accumulator chunk per pass (wide chunks: a tcgen05.commit costs the issuing thread
+// ~0.25 us, so a stage has to carry a few hundred cycles of MMA work).  BatchNorm / store layers: TMEM column = layer
+// column, barrier pair = chunk index.  BCE layer (784 columns): chunk widths are multiples of 32 (whole epilogue units),
+// two TMEM buffers of 224 columns alternate.  Also fills the layer's chunk description.  Returns the next free pass index.
+int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bool b_mn, int first_a_wait, bool bce) {
   const int Npad = (N + 15) & ~15;
-  const int cw = b_mn ? kBwdChunk : kFwdChunk;
-  const int nch = (Npad + cw - 1) / cw;
+  int widths[4] = {0, 0, 0, 0};
+  int nch = 0;
+  if (bce) {
+    int left = Npad;
+    widths[nch++] = std::min(left, 224);
+    left -= widths[0];
+    while (left > 0 && nch < 4) {
+      widths[nch] = std::min(left, 192);
+      left -= widths[nch++];
+    }
+  } else {
+    const int cw = b_mn ? kBwdChunk : kFwdChunk;
+    int left = Npad;
+    while (left > 0 && nch < 4) {
+      widths[nch] = std::min(left, cw);
+      left -= widths[nch++];
+    }
+  }
   L.n_chunks = nch;
+  L.buf_cols = 224;
+  L.u1 = L.u2 = L.u3 = 1 << 20;
+  int n0 = 0;
   for (int c = 0; c < nch; ++c) {
     CPass& ps = p.pass[ip++];
-    const int n0 = c * cw;
-    const int w = std::min(cw, Npad - n0);
+    const int w = widths[c];
     ps.cfg = 1; ps.k_panels = panels_of(K); ps.last_ksteps = ksteps_of(K); ps.a_stream = -1;
     ps.a_wait = c == 0 ? first_a_wait : 0; ps.b_tm = b_tm; ps.b_mn = b_mn ? 1 : 0; ps.n_chunks = 1;
-    const int tmem = ring_tmem ? (c & 3) * cw : n0;
-    const int buf = c & 3;
+    const int tmem = bce ? (c & 1) * 224 : n0;
+    const int buf = bce ? (c & 1) : c;
     if (b_mn) {
       const int boxes = (w + 63) / 64;
       set_chunk(ps, 0, n0, w, boxes, boxes * 8192, 0, tmem, buf);
     } else {
-      set_chunk(ps, 0, n0, w, 0, cw * 128, 0, tmem, buf);   // the box is always cw rows (rows beyond the matrix: zero fill)
+      set_chunk(ps, 0, n0, w, 0, kFwdChunk * 128, 0, tmem, buf);   // the box is always kFwdChunk rows (rows beyond the matrix: zero fill)
     }
-    set_lchunk(L, c, n0, w, tmem, buf);
+    if (c == 1) L.u1 = n0 / 32;
+    if (c == 2) L.u2 = n0 / 32;
+    if (c == 3) L.u3 = n0 / 32;
+    n0 += w;
   }
   return ip;
 }
 
+template <int kKind0, int kKind1, int kKind2>
 int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel<kKind0, kKind1, kKind2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
   static const int coop = env_int("MVAE_CHAIN_COOP", 1);
@@ -922,7 +1012,7 @@ int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = coop ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel<kKind0, kKind1, kKind2>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(chain_kernel)", __FILE__, __LINE__);
   return 0;
 }
@@ -979,8 +1069,6 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   set_chunk(e1, 0, 0, 208, 0, 26624, 0, 0, 0);
   set_chunk(e1, 1, 208, 192, 0, 26624, 26624, 208, 1);
   l1.kind = CE_FWD_BN; l1.N = 400; l1.n_chunks = 2;
-  set_lchunk(l1, 0, 0, 208, 0, 0);
-  set_lchunk(l1, 1, 208, 192, 208, 1);
   int ip = 1;
   ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false);
   ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false);
@@ -994,7 +1082,7 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   l2.counter = a.counters + 1; l2.out_pre = a.h2pre; l2.out_post = a.h2; l2.write_arena = 1;
   l3.kind = CE_FWD_STORE; l3.N = n2;
   l3.bias = a.b3; l3.out_f32 = a.enc; l3.ld_out = n2;
-  return launch_chain(p, slabs + 1, st);
+  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_FWD_STORE>(p, slabs + 1, st);
 }
 
 int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
@@ -1029,7 +1117,7 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   l3.bias = a.b3; l3.target = a.image; l3.target_rows = a.B;
   for (int g = 0; g < 3; ++g) l3.bce_scale[g] = a.bce_scale[g];
   l3.loss = a.loss; l3.dbias = a.dbias3; l3.dlog = a.dlog; l3.probs = a.probs;
-  return launch_chain(p, R / 128 + 1, st);
+  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_BCE>(p, R / 128 + 1, st);
 }
 
 int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
@@ -1052,8 +1140,6 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   set_chunk(g3, 0, 0, 256, 4, 32768, 0, 0, 0);
   set_chunk(g3, 1, 256, 144, 3, 24576, 32768, 256, 1);
   l2.kind = CE_DGRAD_BN; l2.N = 400; l2.n_chunks = 2;
-  set_lchunk(l2, 0, 0, 256, 0, 0);
-  set_lchunk(l2, 1, 256, 144, 256, 1);
   int ip = 1;
   ip = add_resident_layer(p, ip, l1, 200, 400, 2, true, 2, false);
   ip = add_resident_layer(p, ip, l0, a.n, 200, 3, true, 2, false);
@@ -1065,7 +1151,7 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   l1.counter = a.counters + 3; l1.hpre = a.g1pre; l1.out_post = a.dy1; l1.write_arena = 1; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
   l0.kind = CE_DGRAD_STORE; l0.N = a.n;
   l0.out_f32 = a.dz; l0.ld_out = a.n;
-  return launch_chain(p, R / 128 + 1, st);
+  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, CE_DGRAD_STORE>(p, R / 128 + 1, st);
 }
 
 int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
@@ -1093,7 +1179,7 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   l1.kind = CE_DGRAD_BN; l1.N = 400;
   l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + 400; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400;
   l1.counter = a.counters + 1; l1.hpre = a.h1pre; l1.out_post = a.dye1; l1.write_arena = 0; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
-  return launch_chain(p, slabs + 1, st);
+  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, -1>(p, slabs + 1, st);
 }
 
 }  // namespace mvae
