@@ -308,6 +308,7 @@ namespace {
 // works under CUDA-graph capture (the side stream is pulled into the capture by the event dependencies).
 struct SideStream {
   cudaStream_t s = nullptr;
+  cudaStream_t s3 = nullptr;   // second side stream: the text encoder's backward, one of the two last weight gradients
   cudaEvent_t ev[16];
   int next = 0;
   bool ok = false;
@@ -319,6 +320,7 @@ SideStream* side_stream_for_current_device() {
   SideStream* ss = &table[dev];
   if (!ss->ok) {
     if (cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithFlags(&ss->s3, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     for (int i = 0; i < 16; ++i)
       if (cudaEventCreateWithFlags(&ss->ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     ss->ok = true;
@@ -410,6 +412,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   const bool x3 = a->dtype == MVAE_DT_F32X3;  // fp32 storage, error-compensated 3xTF32 GEMMs (shared split scratch: one stream)
   SideStream* ss = (use_side && !debug_sync && !g_prof.on && !x3) ? side_stream_for_current_device() : nullptr;
   cudaStream_t s2 = ss != nullptr ? ss->s : st;  // side stream (or the main one when disabled)
+  cudaStream_t s3 = ss != nullptr ? ss->s3 : st; // second side stream
   auto dep = [&](cudaStream_t from, cudaStream_t to) -> int { return (ss != nullptr && from != to) ? stream_dep(ss, from, to) : 0; };
   const int B = a->batch, n = a->n_latents, dt = x3 ? MVAE_DT_F32 : a->dtype, G = a->n_terms;
   MVAE_REQUIRE(n > 0 && n % 4 == 0, "n_latents=%d must be a positive multiple of 4", n);
@@ -502,8 +505,11 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   te.running_mean = bf("text_encoder.net.1.running_mean"); te.running_var = bf("text_encoder.net.1.running_var");
   te.updates = n_txt; te.momentum = mom; te.bn_eps = bn_eps; te.training = training ? 1 : 0;
   te.table = W.at<float>(P.txt_table); te.save = W.at<float>(P.txt_save);
-  if (dep(st, s2)) return 1;  // fork: the per-label text encoder runs beside the image encoder
-  if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s2), "launch_textenc_forward");
+  // Streams: st carries the critical path; s3 the text networks (per-label encoder, decoder, their backward); s2 the
+  // weight-gradient GEMMs.  A join waits for everything queued on the joined stream, so what the critical path joins on
+  // (the text decoder before the tail backward) must not share a stream with work that is enqueued earlier but may run later.
+  if (dep(st, s3)) return 1;  // fork: the per-label text encoder runs beside the image encoder
+  if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s3), "launch_textenc_forward");
 
   // BatchNorm+ReLU between two Linears is folded into the CONSUMING GEMM's A-operand path (gemm.cu, A transform)
   // when the statistics groups are tile-aligned; the separate apply kernel remains for ragged batches and eval.
@@ -586,7 +592,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, fuse_enc ? W.at<void>(P.h2pre) : W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
                  pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st, fuse_enc ? &atf_e2 : nullptr), "gemm_fwd:image_encoder.net.6.weight#7");
   }
-  if (dep(s2, st)) return 1;  // join: the tail needs both experts
+  if (dep(s3, st)) return 1;  // join: the tail needs both experts
   TailArgs ta;
   ta.B = B; ta.n = n; ta.G = G;
   for (int g = 0; g < G; ++g) {
@@ -620,8 +626,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   td.logp = a->out_recon_text; td.ce = losses + kMaxGroups;
   td.dyhat = W.at<float>(P.dyt); td.s0 = sb_t1; td.s1 = sb_t1 + G * 10;
   td.d_w2 = gf("text_decoder.net.3.weight"); td.d_b2 = gf("text_decoder.net.3.bias");
-  if (dep(st, s2)) return 1;  // fork: text decoder beside the image decoder
-  if (fwd) MVAE_STEP(launch_textdec(td, s2), "launch_textdec");
+  if (dep(st, s3)) return 1;  // fork: text decoder beside the image decoder
+  if (fwd) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
 
   bool bce_direct = false;
   if (use_chain && fwd) {
@@ -708,6 +714,14 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   }
   }  // !use_chain
   if (dep(st, s2)) return 1;  // the side stream may start the weight gradients once dlogits exist
+  // ---- losses out: [G][4] = total, bce, ce, kl (all three partial sums are final once the decoders' forward is done;
+  //      on the side stream the tiny kernel is off the critical path)
+  bool losses_packed = false;
+  if (a->out_losses != nullptr && fwd && ss != nullptr) {
+    if (dep(st, s3)) return 1;   // behind the text decoder (cross entropy) and the image decoder (BCE)
+    MVAE_STEP(launch_loss_pack(losses, a->out_losses, G, s3), "launch_loss_pack#32");
+    losses_packed = true;
+  }
   if (fwd && bwd && bwd_dec && !module_bwd && bce_direct)
     if (mvae_col_stats(dt, W.at<void>(P.dlog), R, 784, 784, 0, gf("image_decoder.net.6.bias"), nullptr, s2)) return 1;
   // ================================================================ backward
@@ -779,19 +793,21 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     ta.d_txt_table = W.at<float>(P.d_txt_table);
     ta.d_wt1 = gf("text_decoder.net.0.weight");
     ta.d_t1_gamma = gf("text_decoder.net.1.weight"); ta.d_t1_beta = gf("text_decoder.net.1.bias");
-    if (dep(s2, st)) return 1;  // join: text decoder results
+    if (dep(s3, st)) return 1;  // join: text decoder results
     MVAE_STEP(launch_tail_backward(ta, st), "launch_tail_backward");
-    if (dep(st, s2)) return 1;  // fork: text encoder backward + encoder weight gradients
+    if (dep(st, s2)) return 1;  // fork: encoder weight gradients
+    if (dep(st, s3)) return 1;  // fork: text encoder backward
   }
   if (bwd && bwd_enc) {
     if (!bwd_dec && dep(st, s2)) return 1;
+    if (!bwd_dec && dep(st, s3)) return 1;
     // ---- text encoder
     if (n_txt > 0) {
       te.d_table = W.at<float>(P.d_txt_table);
       te.d_emb = gf("text_encoder.net.0.weight");
       te.d_gamma = gf("text_encoder.net.1.weight"); te.d_beta = gf("text_encoder.net.1.bias");
       te.d_w = gf("text_encoder.net.3.weight"); te.d_b = gf("text_encoder.net.3.bias");
-      MVAE_STEP(launch_textenc_backward(te, s2), "launch_textenc_backward");
+      MVAE_STEP(launch_textenc_backward(te, s3), "launch_textenc_backward");
     }
     // ---- image encoder
     if (n_img > 0 && use_chain) {
@@ -811,8 +827,10 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       cb.err = chain_err;
       MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
       if (dep(st, s2)) return 1;
-      MVAE_STEP(gemm_wgrad(dt, B, 200, 400, W.at<void>(P.dye2), W.at<void>(P.h1), gf("image_encoder.net.3.weight"), s2), "gemm_wgrad:image_encoder.net.3.weight#29");
+      if (dep(st, s3)) return 1;
+      // the last two weight gradients are what is left of the step: side by side on the two side streams
       MVAE_STEP(gemm_wgrad(dt, B, 400, 784, W.at<void>(P.dye1), a->image, gf("image_encoder.net.0.weight"), s2), "gemm_wgrad:image_encoder.net.0.weight#31");
+      MVAE_STEP(gemm_wgrad(dt, B, 200, 400, W.at<void>(P.dye2), W.at<void>(P.h1), gf("image_encoder.net.3.weight"), s3), "gemm_wgrad:image_encoder.net.3.weight#29");
     }
     if (n_img > 0 && !use_chain) {
       MVAE_STEP(gemm_dgrad(dt, B, 200, 2 * n, W.at<void>(P.denc), wop("image_encoder.net.6.weight"), W.at<void>(P.dye2), dt,
@@ -836,8 +854,9 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   }
 
   if (dep(s2, st)) return 1;  // join everything before the loss read-out / optimizer
+  if (dep(s3, st)) return 1;
   // ---- losses out: [G][4] = total, bce, ce, kl
-  if (a->out_losses != nullptr && fwd)
+  if (a->out_losses != nullptr && fwd && !losses_packed)
     MVAE_STEP(launch_loss_pack(losses, a->out_losses, G, st), "launch_loss_pack#32");
 
   if (bwd && bwd_enc && a->do_adam) {

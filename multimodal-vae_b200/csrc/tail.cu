@@ -620,31 +620,54 @@ __global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
   }
 }
 
+// Backward of the per-label text encoder.  Everything it touches (d_table [10][2n], W [2n][50], the saved activations) is
+// staged in shared memory with coalesced loads first: the contractions then run out of shared memory instead of
+// chains of dependent global loads (42 -> a few us; single block, off the critical path on a side stream).
+constexpr int kTextMaxOut = 128;   // shared-memory staging covers 2n <= 128; wider latents read global memory
 __global__ void __launch_bounds__(256) textenc_bwd_kernel(const TextEncArgs a) {
   pdl_enter();
   __shared__ float s_dh[kTD][kEmb];
+  __shared__ float s_dt[kTD][kTextMaxOut];
+  __shared__ float s_w[kTextMaxOut][kEmb + 1];
+  __shared__ float s_h[kTD][kEmb];
   const float* sv_cnt = a.save;
   const float* sv_xh = a.save + kTD;
   const float* sv_h = sv_xh + kTD * kEmb;
   const float* sv_rstd = sv_h + kTD * kEmb + kEmb;
   const int tid = threadIdx.x;
   const int two_n = 2 * a.n;
+  const bool staged = two_n <= kTextMaxOut;
+  if (staged) {
+    for (int i = tid; i < kTD * two_n; i += blockDim.x) s_dt[i / two_n][i % two_n] = a.d_table[i];
+    for (int i = tid; i < two_n * kEmb; i += blockDim.x) s_w[i / kEmb][i % kEmb] = a.w[i];
+    for (int i = tid; i < kTD * kEmb; i += blockDim.x) s_h[i / kEmb][i % kEmb] = sv_h[i];
+    __syncthreads();
+  }
   // Linear(50 -> 2n): dW[o][f] = sum_l dT[l][o] h[l][f]; db[o] = sum_l dT[l][o]; dh[l][f] = sum_o dT[l][o] W[o][f]
   for (int i = tid; i < two_n * kEmb; i += blockDim.x) {
     const int o = i / kEmb, f = i % kEmb;
     float acc = 0.f;
-    for (int l = 0; l < kTD; ++l) acc = fmaf(a.d_table[l * two_n + o], sv_h[l * kEmb + f], acc);
-    a.d_w[i] += acc;
+    if (staged) {
+#pragma unroll
+      for (int l = 0; l < kTD; ++l) acc = fmaf(s_dt[l][o], s_h[l][f], acc);
+    } else {
+      for (int l = 0; l < kTD; ++l) acc = fmaf(a.d_table[l * two_n + o], sv_h[l * kEmb + f], acc);
+    }
+    atomicAdd(a.d_w + i, acc);   // one owner per address: a reduction without a load to wait for
   }
   for (int o = tid; o < two_n; o += blockDim.x) {
     float acc = 0.f;
-    for (int l = 0; l < kTD; ++l) acc += a.d_table[l * two_n + o];
-    a.d_b[o] += acc;
+    for (int l = 0; l < kTD; ++l) acc += staged ? s_dt[l][o] : a.d_table[l * two_n + o];
+    atomicAdd(a.d_b + o, acc);
   }
   for (int i = tid; i < kTD * kEmb; i += blockDim.x) {
     const int l = i / kEmb, f = i % kEmb;
     float acc = 0.f;
-    for (int o = 0; o < two_n; ++o) acc = fmaf(a.d_table[l * two_n + o], a.w[o * kEmb + f], acc);
+    if (staged) {
+      for (int o = 0; o < two_n; ++o) acc = fmaf(s_dt[l][o], s_w[o][f], acc);
+    } else {
+      for (int o = 0; o < two_n; ++o) acc = fmaf(a.d_table[l * two_n + o], a.w[o * kEmb + f], acc);
+    }
     s_dh[l][f] = sv_h[i] > 0.f ? acc : 0.f;  // ReLU mask; this is dyhat aggregated over the label's samples
   }
   __syncthreads();
@@ -655,12 +678,12 @@ __global__ void __launch_bounds__(256) textenc_bwd_kernel(const TextEncArgs a) {
       s0 += s_dh[l][f];
       s1 += s_dh[l][f] * sv_xh[l * kEmb + f];
     }
-    a.d_gamma[f] += s1;
-    a.d_beta[f] += s0;
+    atomicAdd(a.d_gamma + f, s1);
+    atomicAdd(a.d_beta + f, s0);
     const float gr = a.gamma[f] * sv_rstd[f];
     for (int l = 0; l < kTD; ++l) {
       const float c = sv_cnt[l] / a.B;
-      a.d_emb[l * kEmb + f] += gr * (s_dh[l][f] - c * s0 - c * sv_xh[l * kEmb + f] * s1);
+      atomicAdd(a.d_emb + l * kEmb + f, gr * (s_dh[l][f] - c * s0 - c * sv_xh[l * kEmb + f] * s1));
     }
   }
 }

@@ -1,7 +1,7 @@
 # chain kernels: parity tests that exercise them, phase timeline, bench line (run on the B200 box)
 set -x
-timeout 600 python -m pytest tests/test_mnist_step_gpu.py -q -x -k "bf16 or benchmarked or masked or split" 2>&1 | tail -15 > gpurun_out/r2_chain_tests.log; cat gpurun_out/r2_chain_tests.log
-timeout 120 python tools/chain_timeline.py > gpurun_out/r2_chain_timeline.log 2>&1; tail -40 gpurun_out/r2_chain_timeline.log
+timeout 900 python -m pytest tests/test_mnist_step_gpu.py tests/test_module_surface_gpu.py -q -x ${PYTEST_K:+-k "$PYTEST_K"} 2>&1 | tail -15 > gpurun_out/r2_chain_tests.log; cat gpurun_out/r2_chain_tests.log
+timeout 120 python tools/chain_timeline.py > gpurun_out/r2_chain_timeline.log 2>&1; grep -c . gpurun_out/r2_chain_timeline.log
 timeout 300 python bench.py --steps 300 --warmup 20 --no-cpu-baseline > gpurun_out/r2_bench_chain.json 2> gpurun_out/r2_bench_chain.err; tail -3 gpurun_out/r2_bench_chain.err; python - <<'P'
 import json
 d = json.loads(open("gpurun_out/r2_bench_chain.json").read().strip().splitlines()[-1])
