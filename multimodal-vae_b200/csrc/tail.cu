@@ -367,6 +367,198 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
   }
 }
 
+// ================================================================= tail backward, one warp per SAMPLE (n <= 64)
+// The warp carries its sample through all ELBO terms: both experts are loaded once, the terms' contributions to the image
+// expert's gradient are summed in registers (no shared-memory combine, no block barrier inside the loop), the text expert's
+// gradient goes into a per-warp private [10][2n] table (plain shared-memory adds), and the text decoder's first Linear
+// keeps its weights in shared memory and its weight gradient in per-lane registers.  Same arithmetic as tail_bwd_kernel.
+constexpr int kBwd2Warps = 8;
+template <typename ZT>
+__global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const TailArgs a) {
+  pdl_enter();
+  extern __shared__ float sm[];
+  const int n = a.n, two_n = 2 * a.n, G = a.G;
+  // layout: per-warp text-expert tables [warps][10][2n] | Wt1 [10][n] | t1 coefficients [G][4][10] | d_wt1 [10][n] | d_enc_bias [2n]
+  float* s_tab = sm;
+  float* s_w = s_tab + kBwd2Warps * kTD * two_n;
+  float* s_co = s_w + kTD * n;
+  float* s_dw = s_co + kMaxGroups * 4 * kTD;
+  float* s_eb = s_dw + kTD * n;
+  const int total = kBwd2Warps * kTD * two_n + kTD * n + kMaxGroups * 4 * kTD + kTD * n + two_n;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const bool text_dec = a.t1_dyhat != nullptr;
+  if (text_dec) {
+    for (int i = threadIdx.x; i < kTD * n; i += blockDim.x) s_w[i] = a.wt1[i];
+    if (threadIdx.x < G * kTD) {
+      const int gg = threadIdx.x / kTD, j = threadIdx.x % kTD;
+      const float mean = a.t1_sum[gg * kTD + j] / a.B;
+      const float var = fmaxf(a.t1_sumsq[gg * kTD + j] / a.B - mean * mean, 0.f);
+      s_co[(gg * 4 + 0) * kTD + j] = mean;
+      s_co[(gg * 4 + 1) * kTD + j] = rsqrtf(var + 1e-5f);
+      s_co[(gg * 4 + 2) * kTD + j] = a.t1_s0[gg * kTD + j] / a.B;
+      s_co[(gg * 4 + 3) * kTD + j] = a.t1_s1[gg * kTD + j] / a.B;
+    }
+  }
+  __syncthreads();
+  const uint32_t step = a.step_ptr != nullptr ? static_cast<uint32_t>(*a.step_ptr) : 0u;
+  bool any_img = false, any_txt = false;
+  for (int g = 0; g < G; ++g) {
+    any_img |= a.group_type[g] != TERM_TEXT;
+    any_txt |= a.group_type[g] != TERM_IMAGE;
+  }
+  const int k = lane * 2;
+  const bool act = k < n;
+  float r_w1[kTD][2], r_eb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) r_w1[j][0] = r_w1[j][1] = 0.f;
+  float* my_tab = s_tab + warp * kTD * two_n;
+
+  for (int b = blockIdx.x * kBwd2Warps + warp; b < a.B; b += gridDim.x * kBwd2Warps) {
+    const int label = any_txt ? static_cast<int>(a.labels[b]) : 0;
+    // text decoder: gradient at its first Linear's output (BatchNorm backward apply) for every term: lane = term * 10 + feature
+    float dt_mine = 0.f;
+    if (text_dec && lane < G * kTD) {
+      const int gg = lane / kTD, j = lane - gg * kTD;
+      const long long row = static_cast<long long>(gg) * a.B + b;
+      const float rstd = s_co[(gg * 4 + 1) * kTD + j];
+      const float x = a.t1pre[row * kTD + j];
+      const float xh = (x - s_co[(gg * 4 + 0) * kTD + j]) * rstd;
+      const float dy = a.t1_dyhat[row * kTD + j];
+      dt_mine = a.t1_gamma[j] * rstd * (dy - s_co[(gg * 4 + 2) * kTD + j] - xh * s_co[(gg * 4 + 3) * kTD + j]);
+    }
+    float mi[2] = {0.f, 0.f}, li[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f}, lt[2] = {0.f, 0.f};
+    if (act && any_img) {
+      const float2 m2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + k);
+      const float2 l2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + n + k);
+      mi[0] = m2.x; mi[1] = m2.y; li[0] = l2.x; li[1] = l2.y;
+    }
+    if (act && any_txt) {
+      const float2 m2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + k);
+      const float2 l2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + n + k);
+      mt[0] = m2.x; mt[1] = m2.y; lt[0] = l2.x; lt[1] = l2.y;
+    }
+    float a_mi[2] = {0.f, 0.f}, a_li[2] = {0.f, 0.f}, a_mt[2] = {0.f, 0.f}, a_lt[2] = {0.f, 0.f};
+    for (int g = 0; g < G; ++g) {
+      const int ty = a.group_type[g];
+      const bool present[2] = {ty != TERM_TEXT, ty != TERM_IMAGE};
+      const float c_kl = a.kl_weight[g];
+      const long long row = static_cast<long long>(g) * a.B + b;
+      float2 e2 = make_float2(0.f, 0.f), dz2 = make_float2(0.f, 0.f), dmu_up = make_float2(0.f, 0.f), dlv_up = make_float2(0.f, 0.f);
+      if (act) {
+        if (a.training) {
+          if (a.eps != nullptr)
+            e2 = *reinterpret_cast<const float2*>(a.eps + row * n + k);
+          else
+            e2 = normal_pair(a.seed, step, (row * n + k) >> 1);
+        }
+        if (a.dz != nullptr) dz2 = *reinterpret_cast<const float2*>(a.dz + row * n + k);
+        if (a.dmu_up != nullptr) dmu_up = *reinterpret_cast<const float2*>(a.dmu_up + row * n + k);
+        if (a.dlogvar_up != nullptr) dlv_up = *reinterpret_cast<const float2*>(a.dlogvar_up + row * n + k);
+      }
+      const float ee[2] = {e2.x, e2.y};
+      float dzz[2] = {dz2.x, dz2.y};
+      const float dmu_u[2] = {dmu_up.x, dmu_up.y}, dlv_u[2] = {dlv_up.x, dlv_up.y};
+      Poe r[2];
+      float zz[2], sd[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float m[2] = {present[0] ? mi[c] : 0.f, present[1] ? mt[c] : 0.f};
+        const float lv[2] = {present[0] ? li[c] : 0.f, present[1] ? lt[c] : 0.f};
+        r[c] = poe_eval<false>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
+        sd[c] = sqrtf(r[c].pd_var);
+        zz[c] = a.training ? ee[c] * sd[c] + r[c].mu : r[c].mu;
+      }
+      // text decoder first Linear: dz += dT1 * Wt1, dWt1 += dT1^T z
+      if (text_dec) {
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) {
+          const float dj = __shfl_sync(0xffffffffu, dt_mine, g * kTD + j);
+          if (act) {
+            const float2 w = *reinterpret_cast<const float2*>(s_w + j * n + k);
+            dzz[0] = fmaf(dj, w.x, dzz[0]);
+            dzz[1] = fmaf(dj, w.y, dzz[1]);
+            r_w1[j][0] = fmaf(dj, zz[0], r_w1[j][0]);
+            r_w1[j][1] = fmaf(dj, zz[1], r_w1[j][1]);
+          }
+        }
+      }
+      if (act) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          // z = mu + eps*exp(logvar/2);  KL = c * -0.5 * sum(1 + logvar - mu^2 - exp(logvar))
+          const float dmu = dzz[c] + dmu_u[c] + c_kl * r[c].mu;
+          float dlv = dlv_u[c] + 0.5f * c_kl * (r[c].pd_var - 1.f);
+          if (a.training) dlv += dzz[c] * 0.5f * ee[c] * sd[c];
+          float dm = 0.f, dl = 0.f;
+          if (present[0]) {
+            poe_grad(a.poe_mode, a.poe_eps, r[c], 0, mi[c], dmu, dlv, dm, dl);
+            a_mi[c] += dm;
+            a_li[c] += dl;
+          }
+          if (present[1]) {
+            poe_grad(a.poe_mode, a.poe_eps, r[c], 1, mt[c], dmu, dlv, dm, dl);
+            a_mt[c] += dm;
+            a_lt[c] += dl;
+          }
+        }
+      }
+    }
+    if (act) {
+      if (any_img && a.enc_img != nullptr && a.d_enc != nullptr) {
+        ZT* de = reinterpret_cast<ZT*>(a.d_enc) + static_cast<long long>(b) * two_n;
+        store_pair(de + k, a_mi[0], a_mi[1]);
+        store_pair(de + n + k, a_li[0], a_li[1]);
+        r_eb[0] += a_mi[0]; r_eb[1] += a_mi[1]; r_eb[2] += a_li[0]; r_eb[3] += a_li[1];
+      }
+      if (any_txt) {
+        float2* tm = reinterpret_cast<float2*>(my_tab + label * two_n + k);
+        float2* tl = reinterpret_cast<float2*>(my_tab + label * two_n + n + k);
+        float2 vm = *tm, vl = *tl;
+        vm.x += a_mt[0]; vm.y += a_mt[1]; vl.x += a_lt[0]; vl.y += a_lt[1];
+        *tm = vm;
+        *tl = vl;
+      }
+    }
+  }
+  if (act) {
+    if (text_dec) {
+#pragma unroll
+      for (int j = 0; j < kTD; ++j) {
+        atomicAdd(&s_dw[j * n + k], r_w1[j][0]);
+        atomicAdd(&s_dw[j * n + k + 1], r_w1[j][1]);
+      }
+    }
+    atomicAdd(&s_eb[k], r_eb[0]);
+    atomicAdd(&s_eb[k + 1], r_eb[1]);
+    atomicAdd(&s_eb[n + k], r_eb[2]);
+    atomicAdd(&s_eb[n + k + 1], r_eb[3]);
+  }
+  __syncthreads();
+  if (a.d_txt_table != nullptr && a.txt_table != nullptr)
+    for (int i = threadIdx.x; i < kTD * two_n; i += blockDim.x) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBwd2Warps; ++w) v += s_tab[w * kTD * two_n + i];
+      if (v != 0.f) atomicAdd(a.d_txt_table + i, v);
+    }
+  if (text_dec && a.d_wt1 != nullptr)
+    for (int i = threadIdx.x; i < kTD * n; i += blockDim.x) atomicAdd(a.d_wt1 + i, s_dw[i]);
+  if (a.d_enc_bias != nullptr && a.enc_img != nullptr)
+    for (int i = threadIdx.x; i < two_n; i += blockDim.x) atomicAdd(a.d_enc_bias + i, s_eb[i]);
+  // BatchNorm affine gradients of the text decoder: dgamma = sum_g S1, dbeta = sum_g S0 (block 0 only)
+  if (text_dec && blockIdx.x == 0 && threadIdx.x < kTD && a.d_t1_gamma != nullptr) {
+    float dg = 0.f, db = 0.f;
+    for (int gg = 0; gg < G; ++gg) {
+      dg += a.t1_s1[gg * kTD + threadIdx.x];
+      db += a.t1_s0[gg * kTD + threadIdx.x];
+    }
+    a.d_t1_gamma[threadIdx.x] += dg;
+    a.d_t1_beta[threadIdx.x] += db;
+  }
+}
+
 // ================================================================= text decoder (BN -> ReLU -> Linear -> log_softmax -> NLL)
 // One thread per decoder row.  Forward + (optionally) the fused NLL loss and the backward down to the
 // BatchNorm output: dyhat, its two per-group column sums, and the gradients of the second Linear.
@@ -799,6 +991,20 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
 
 int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
   if (check_tail(a)) return 1;
+  if (a.n <= 64 && a.n % 2 == 0) {
+    // one warp per sample (all terms): the fast path for the latent sizes the MNIST configurations use
+    const int smem2 = (kBwd2Warps * kTD * 2 * a.n + kTD * a.n + kMaxGroups * 4 * kTD + kTD * a.n + 2 * a.n) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set = true;
+    }
+    int blocks2 = std::min((a.B + kBwd2Warps - 1) / kBwd2Warps, 148 * 2);
+    if (blocks2 < 1) blocks2 = 1;
+    if (a.z_dtype == MVAE_F32) return launch_pdl(tail_bwd2_kernel<float>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
+    return launch_pdl(tail_bwd2_kernel<__nv_bfloat16>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
+  }
   const int smem_floats = kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD +
                           2 * kBwdRows * kMaxGroups * 2 * a.n + kBwdRows;
   const int smem = smem_floats * 4;
