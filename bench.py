@@ -206,7 +206,8 @@ def run_device(args):
     B = args.batch
     model = MVAE(N_LATENTS, precision=args.precision, device=dev, seed=1234 + rank)
     if world > 1:
-        trainer = DataParallelTrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph, overlap=not args.no_overlap)
+        trainer = DataParallelTrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph, overlap=not args.no_overlap,
+                                      fused=os.environ.get("MVAE_DP_FUSED", "1") != "0")
     else:
         trainer = MVAETrainer(model, lr=1e-3, use_cuda_graph=not args.no_graph)
 
@@ -224,6 +225,17 @@ def run_device(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    _align_buf = torch.zeros(8, device=dev) if world > 1 else None
+
+    def align_ranks():
+        """Device-side alignment right before a timed region: every rank's stream first spins for ~3 ms (so that the host
+        has the whole timed loop enqueued before the device gets there), then meets the others in a tiny all-reduce.  The
+        start event recorded behind it fires at the same moment on every rank - host-side skew between the ranks (process
+        scheduling, the clock sampler's start-up) cannot land inside the timed window."""
+        if world > 1:
+            torch.cuda._sleep(6_000_000)
+            dist.all_reduce(_align_buf)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -263,6 +275,7 @@ def run_device(args):
     sampler.start()
     l0 = lib.mvae_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    align_ranks()
     e0.record()
     for i in range(args.steps):
         losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], **step_kwargs())
@@ -288,6 +301,7 @@ def run_device(args):
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
+    align_ranks()
     t0.record()
     n_read = 0
     for l_host in pipe.run(((host_x[i % len(host_x)], host_y[i % len(host_y)]) for i in range(e2e_steps))):
@@ -402,6 +416,8 @@ def run_device(args):
         "config": {"workload": "MNIST MVAE (784-400-200-2n MLP + label text, BatchNorm+ReLU), n_latents=64, "
                                "batch %d per GPU, fused PoE + 3-term subsampled ELBO, fwd+bwd+Adam" % B,
                    "batch_per_gpu": B, "global_batch": B * world, "n_latents": N_LATENTS, "parallelism": "dp%d" % world,
+                   "gradient_exchange": ("fused NVLink reduce-scatter + all-gather + Adam kernel (csrc/dp.cu)" if getattr(trainer, "fused", False)
+                                         else ("NCCL all-reduce + Adam kernel" if world > 1 else "none")),
                    "l2_policy": "inputs rotate through a pool of %d distinct batches (%.0f MB > 2x L2)" % (
                        n_slots, n_slots * B * 784 * es / 1e6),
                    "cuda_graph": not args.no_graph, "precision": args.precision,

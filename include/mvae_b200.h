@@ -182,6 +182,26 @@ int mvae_adam_step(float* params, float* grads, float* m, float* v, void* params
                    float beta1, float beta2, float eps, const int* step_counter, float grad_scale, int zero_grad,
                    void* stream);
 int mvae_cast_f32_to_bf16(const float* in, void* out, int64_t count, void* stream);
+/* Data-parallel training: gradient all-reduce over NVLink peer memory fused with the Adam update of one bucket
+ * [lo, hi) of the flat buffers, ONE launch per rank (csrc/dp.cu): barrier -> reduce-scatter (peer loads) -> all-gather
+ * (peer stores) -> barrier -> Adam(grad_scale).  grads[r] / flags[r] are the peer pointers of rank r's flat fp32 gradient
+ * buffer and of its zero-initialised uint32[32] flag array (symmetric memory); params / moments / bf16 mirror are local.
+ * A collective: every rank must enqueue the same sequence of calls.  Replaces mnist/train.py:152-153 on one device. */
+typedef struct mvae_dp_reduce_adam_args {
+  int world, rank;
+  void* grads[8];
+  void* flags[8];
+  float* params;
+  float* adam_m;
+  float* adam_v;
+  void* params_bf16;      /* optional bf16 mirror of params */
+  int64_t lo, hi;         /* bucket (elements, multiples of 4) */
+  float lr, beta1, beta2, eps, grad_scale;
+  const int* adam_step;   /* device: 1-based step */
+  int blocks;             /* 0: default grid */
+} mvae_dp_reduce_adam_args;
+int mvae_dp_reduce_adam(const mvae_dp_reduce_adam_args* args, void* stream);
+
 /* uint8 pixels -> [0,1] activations (image.view(-1,784) of ToTensor(), mnist/train.py:106,131) */
 int mvae_u8_to_act(const uint8_t* in, float* out_f32, void* out_bf16, int64_t count, float scale, void* stream);
 

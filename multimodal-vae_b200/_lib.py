@@ -56,6 +56,7 @@ def load():
         lib.mvae_mnist_workspace_offset.argtypes = [C.c_char_p, c_int, c_int, c_int]
         lib.mvae_adam_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
                                        c_float, c_float, c_void_p, c_float, c_int, c_void_p]
+        lib.mvae_dp_reduce_adam.argtypes = [C.POINTER(DpReduceAdamArgs), c_void_p]
         _conv_argtypes(lib)
         _lib = lib
         return lib
@@ -201,6 +202,14 @@ class ConvTClass(C.Structure):
         ("taps_h", c_int), ("taps_w", c_int), ("pad_h", c_int), ("pad_w", c_int),
         ("kh", c_int * 8), ("kw", c_int * 8),
     ]
+
+
+class DpReduceAdamArgs(C.Structure):
+    """mvae_dp_reduce_adam_args (include/mvae_b200.h)."""
+    _fields_ = [("world", c_int), ("rank", c_int), ("grads", c_void_p * 8), ("flags", c_void_p * 8),
+                ("params", c_void_p), ("adam_m", c_void_p), ("adam_v", c_void_p), ("params_bf16", c_void_p),
+                ("lo", c_int64), ("hi", c_int64), ("lr", c_float), ("beta1", c_float), ("beta2", c_float),
+                ("eps", c_float), ("grad_scale", c_float), ("adam_step", c_void_p), ("blocks", c_int)]
 
 
 def _conv_argtypes(lib) -> None:

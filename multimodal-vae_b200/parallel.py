@@ -58,7 +58,7 @@ class DataParallelTrainer(MVAETrainer):
     """MVAETrainer whose step is: local fused fwd+bwd -> all-reduce(flat grads) -> fused Adam(1/world)."""
 
     def __init__(self, model: MVAE, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 use_cuda_graph: bool = False, group=None, overlap: bool = True):
+                 use_cuda_graph: bool = False, group=None, overlap: bool = True, fused: bool = True):
         super().__init__(model, lr=lr, betas=betas, eps=eps, use_cuda_graph=False)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -73,6 +73,64 @@ class DataParallelTrainer(MVAETrainer):
         from .mnist import sizes
         self.enc_floats = int(sizes(model.n_latents, 2, model.dtype_code).encoder_param_floats)
         broadcast_model_(model, 0, group)
+        # Gradient exchange: by default ONE fused kernel per bucket over NVLink peer memory (reduce-scatter + all-gather +
+        # Adam, csrc/dp.cu); fused=False (or a failed symmetric-memory rendezvous) keeps the NCCL all-reduce + Adam kernel.
+        self.fused = False
+        if fused and self.world > 1 and self.world <= 8:
+            try:
+                self._setup_peer_memory()
+                self.fused = True
+            except Exception as exc:   # no peer access / symmetric memory unavailable: NCCL carries the gradients
+                self.fused_error = repr(exc)
+
+    def _setup_peer_memory(self) -> None:
+        """Re-home the flat gradient buffer into symmetric memory and exchange the peer pointers."""
+        import torch.distributed._symmetric_memory as symm_mem
+        m = self.model
+        grp = self.group if self.group is not None else dist.group.WORLD
+        name = grp.group_name
+        try:
+            symm_mem.enable_symm_mem_for_group(name)   # older torch releases need the explicit opt-in
+        except Exception:
+            pass
+        g = symm_mem.empty(m.flat_grads.numel(), dtype=torch.float32, device=m.device_)
+        f = symm_mem.empty(64, dtype=torch.int32, device=m.device_)
+        hg = symm_mem.rendezvous(g, name)
+        hf = symm_mem.rendezvous(f, name)
+        g.copy_(m.flat_grads)
+        f.zero_()
+        m.flat_grads = g
+        for pname, kind, shape, off in m._table:
+            if kind != 0:
+                continue
+            numel = 1
+            for s_ in shape:
+                numel *= s_
+            block, _, idx, leaf = pname.split(".")
+            getattr(getattr(getattr(m, block).net, idx), leaf).grad = g[off:off + numel].view(shape)
+        self._peer_grads = [int(x) for x in hg.buffer_ptrs]
+        self._peer_flags = [int(x) for x in hf.buffer_ptrs]
+        self._symm = (g, f, hg, hf)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def _reduce_adam(self, lo: int, hi: int) -> None:
+        """Enqueue the fused exchange + update of bucket [lo, hi) on the current stream (a collective)."""
+        m, a = self.model, self.adam
+        args = _lib.DpReduceAdamArgs()
+        args.world, args.rank = self.world, self.rank
+        for r in range(self.world):
+            args.grads[r] = self._peer_grads[r]
+            args.flags[r] = self._peer_flags[r]
+        args.params = m.flat_params.data_ptr()
+        args.adam_m, args.adam_v = a["m"].data_ptr(), a["v"].data_ptr()
+        args.params_bf16 = None if m.flat_params_bf16 is None else m.flat_params_bf16.data_ptr()
+        args.lo, args.hi = lo, hi
+        args.lr, args.beta1, args.beta2, args.eps = a["lr"], a["betas"][0], a["betas"][1], a["eps"]
+        args.grad_scale = 1.0 / self.world
+        args.adam_step = m._adam_counter.data_ptr()
+        args.blocks = 0
+        _lib.check(_lib.load().mvae_dp_reduce_adam(C.byref(args), _stream_ptr()), "mvae_dp_reduce_adam")
 
     def _local_then_reduce(self, x, y, eps, terms, lambdas, annealing_factor, losses=None):
         """fwd + decoder backward -> [all-reduce(decoder bucket) on the comm stream || encoder backward]
@@ -82,6 +140,25 @@ class DataParallelTrainer(MVAETrainer):
         tt, klw = self._norm(terms, x.shape[0], annealing_factor)
         split = self.enc_floats
         main = torch.cuda.current_stream(m.device_)
+        total = m.flat_params.numel()
+        if self.fused and self.world > 1:
+            # forward + decoder-side backward; the decoder bucket is exchanged and updated on the communication stream
+            # while the encoder-side backward runs; the encoder bucket follows on the main stream.  No NCCL, no separate Adam.
+            out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses,
+                            extra={"phase": 3, "advance_adam_step": 1})
+            if self.overlap:
+                self.comm_stream.wait_stream(main)
+                with torch.cuda.stream(self.comm_stream):
+                    self._reduce_adam(split, total)
+            m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=False, adam=None, losses=losses,
+                   extra={"phase": 4})
+            if self.overlap:
+                # the two calls share one set of flags: strictly one after the other on every rank
+                main.wait_stream(self.comm_stream)
+                self._reduce_adam(0, split)
+            else:
+                self._reduce_adam(0, total)
+            return out
         if self.overlap and self.world > 1:
             out, _ = m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=True, adam=None, losses=losses,
                             extra={"phase": 3, "advance_adam_step": 1})
