@@ -126,14 +126,15 @@ def run_reference(args):
     vel = {k: torch.zeros_like(v) for k, v in state.items() if not O.is_buffer(k)}
     # bounded sample: at ~0.25 s per step the whole run must end within minutes
     steps = min(args.steps, 40)
-    warmup = min(args.warmup, 3)
+    warmup = max(3, min(args.warmup, 50))   # --warmup is honoured (capped: a CPU step takes ~0.1 s)
     p = state
     step_no = 0
+    noise_pool = [[torch.randn_like(n) for n in noises] for _ in range(8)]   # drawn outside the timed loop
 
     def one():
         nonlocal p, step_no
         step_no += 1
-        _, grads, bufs, _ = O.train_step(p, image, text, [torch.randn_like(n) for n in noises])
+        _, grads, bufs, _ = O.train_step(p, image, text, noise_pool[step_no % len(noise_pool)])
         p = O.adam_step(p, grads, mom, vel, step_no)
         p.update(bufs)
 
@@ -180,6 +181,156 @@ def cpu_baseline(torch, budget_s=12.0):
         n += 1
     return {"value": B * n / t_used, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d steps of batch %d (oracle/mnist_oracle.py, fp32, %d threads)" % (n, B, torch.get_num_threads())}
+
+
+def torch_gpu_baseline(torch, dev, budget_steps=30):
+    """BASELINE.md section 2 comparator: the reference's step as stock PyTorch on the same B200 (the oracle port's
+    modules / autograd / Adam moved to the device, library kernels only - cuBLAS, ATen), fp32 and TF32, eager and
+    replayed as one CUDA graph.  A baseline leg: nothing of this repo's CUDA path is on it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mnist_oracle as O
+    B = BATCH_PER_GPU
+    image, text, noises = O.synthetic_batch(B, N_LATENTS, 0)
+    image, text = image.to(dev), text.to(dev)
+    noises = [n.to(dev) for n in noises]
+    out = {"batch": B, "what": "oracle/mnist_oracle.py train_step + adam_step on cuda (ATen / cuBLAS), same synthetic batch"}
+
+    def fresh():
+        st = {k: v.to(dev) for k, v in O.init_state(N_LATENTS, seed=1234).items()}
+        mom = {k: torch.zeros_like(v) for k, v in st.items() if not O.is_buffer(k)}
+        vel = {k: torch.zeros_like(v) for k, v in st.items() if not O.is_buffer(k)}
+        return st, mom, vel
+
+    def one(st, mom, vel, i):
+        # O.train_step without its float(loss) host read-backs (they would serialise the eager run and break graph capture)
+        work = {k: (v.clone() if O.is_buffer(k) else v.detach().clone().requires_grad_(True)) for k, v in st.items()}
+        losses, _ = O.train_step_losses(work, image, text, noises, work)
+        names = [k for k in work if not O.is_buffer(k)]
+        gs = torch.autograd.grad(losses[0] + losses[1] + losses[2], [work[k] for k in names], allow_unused=True)
+        grads = {k: (torch.zeros_like(work[k]) if g is None else g) for k, g in zip(names, gs)}
+        new = O.adam_step(st, grads, mom, vel, i)
+        new.update({k: v for k, v in work.items() if O.is_buffer(k)})
+        return new
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return B * n / (e0.elapsed_time(e1) * 1e-3)
+
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, tf32 in (("fp32_eager", False), ("tf32_eager", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            st, mom, vel = fresh()
+            box = {"st": st}
+            for i in range(3):
+                box["st"] = one(box["st"], mom, vel, i + 1)
+
+            def step(i, box=box, mom=mom, vel=vel):
+                box["st"] = one(box["st"], mom, vel, i + 4)
+            out[name] = timed(step, budget_steps)
+        # one CUDA graph per step (static inputs: every replay recomputes the same step - the work is identical)
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = True
+            st, mom, vel = fresh()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    one(st, mom, vel, i + 1)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one(st, mom, vel, 4)
+            out["tf32_cuda_graph"] = timed(lambda i: graph.replay(), budget_steps)
+        except Exception as exc:   # capture of the autograd step is best effort
+            out["tf32_cuda_graph"] = None
+            out["cuda_graph_error"] = repr(exc)[:200]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out["unit"] = "samples/s"
+    return out
+
+
+def other_configs(torch, dev, log):
+    """Short single-GPU rows for the other BASELINE.json configurations (the driver only runs this script): MNIST in tf32
+    and with the weak-supervision term flips (configs[4] rule), CelebA (configs[3]) and MultiMNIST (configs[2]) at
+    batch 256.  Same timing rules as the headline (CUDA events, warm-up, CUDA-graph replay, rotating inputs)."""
+    import numpy as np
+    from mvae_b200 import MVAE, MVAETrainer
+    out = {}
+
+    def timed(step, warm, n):
+        for i in range(warm):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(warm + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    B = BATCH_PER_GPU
+    g = torch.Generator().manual_seed(5)
+    slots = 24
+    try:
+        xs32 = [torch.rand(B, 784, generator=g).to(dev) for _ in range(slots)]
+        ys = [torch.randint(0, 10, (B,), generator=g).to(dev) for _ in range(slots)]
+        m = MVAE(N_LATENTS, precision="tf32", device=dev, seed=1)
+        tr = MVAETrainer(m, lr=1e-3, use_cuda_graph=True)
+        ms = timed(lambda i: tr.step(xs32[i % slots], ys[i % slots]), 5, 40)
+        out["mnist_tf32_b4096"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "precision": "tf32 (per-layer tcgen05 GEMM path)"}
+        del m, tr
+        m = MVAE(N_LATENTS, precision="bf16", device=dev, seed=1)
+        tr = MVAETrainer(m, lr=1e-3, use_cuda_graph=True)
+        xs16 = [m.to_act(x) for x in xs32]
+        flips = np.random.RandomState(42)
+
+        def weak(i):
+            terms, lams = ["joint"], [(1.0, 1.0)]
+            if flips.random_sample() < 0.5:
+                terms.append("image"); lams.append((1.0, 1.0))
+            if flips.random_sample() < 0.5:
+                terms.append("text"); lams.append((0.0, 1.0))
+            tr.step(xs16[i % slots], ys[i % slots], terms=tuple(terms), lambdas=tuple(lams))
+        ms = timed(weak, 24, 60)
+        out["mnist_weak_0.5_0.5_b4096"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "precision": "bf16",
+                                           "rule": "mnist/modal_weak.py:60-97, per-batch flips from np.random.seed(42)"}
+        del m, tr, xs32, xs16
+    except Exception as exc:
+        out["mnist_error"] = repr(exc)[:300]
+    for name in ("celeba", "multimnist"):
+        try:
+            Bc, n = 256, 100
+            if name == "celeba":
+                from mvae_b200.celeba import MultimodalVAE, CelebATrainer as Trainer
+                shape = (3, 64, 64)
+                other = lambda: (torch.rand(Bc, 18, generator=g) > 0.5).float()
+            else:
+                from mvae_b200.multimnist import MultimodalVAE, MultiMNISTTrainer as Trainer
+                shape = (1, 50, 50)
+                other = lambda: torch.randint(0, 12, (Bc, 4), generator=g)
+            model = MultimodalVAE(n_latents=n, precision="bf16", device=dev, seed=1)
+            tr = Trainer(model, use_cuda_graph=True)
+            nb = max(4, (2 * L2_BYTES) // (Bc * shape[0] * shape[1] * shape[2] * 4) + 1)
+            pool = [(torch.rand(Bc, *shape, generator=g).to(dev), other().to(dev)) for _ in range(nb)]
+            ms = timed(lambda i: tr.step(*pool[i % nb]), 5, 30)
+            out["%s_b256" % name] = {"ms_per_step": ms, "samples_per_s": Bc / (ms * 1e-3), "precision": "bf16", "n_latents": n,
+                                     "gpu_launches_per_step": tr.last_graph_launches}
+            del model, tr, pool
+        except Exception as exc:
+            out["%s_error" % name] = repr(exc)[:300]
+        log("other_configs %s done" % name)
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------- device arm
@@ -356,6 +507,12 @@ def run_device(args):
         "image_decoder.net.3.weight": (R3, 400, 200), "image_decoder.net.6.weight": (R3, 784, 400)}
     bn_feats = {"image_encoder.net.1.weight": (B, 400), "image_encoder.net.4.weight": (B, 200),
                 "image_decoder.net.1.weight": (R3, 200), "image_decoder.net.4.weight": (R3, 400)}
+    # slab-persistent chain kernels (csrc/chain.cu): algorithmic FLOPs of the Linears each launch contains
+    enc_mac = 784 * 400 + 400 * 200 + 200 * 2 * n_lat
+    dec_mac = n_lat * 200 + 200 * 400 + 400 * 784
+    chain_flops = {"chain_enc_fwd": 2.0 * B * enc_mac, "chain_dec_fwd": 2.0 * R3 * dec_mac, "chain_dec_bwd": 2.0 * R3 * dec_mac,
+                   "chain_enc_bwd": 2.0 * B * (200 * 2 * n_lat + 400 * 200)}
+    tc_burst = peaks["bf16_tflops"] if args.precision == "bf16" else peaks["bf16_tflops"] / 2   # launches are timed in isolation
     hbm_peak = peaks["hbm_gbs"]
     tc_peak = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
     per_launch = []
@@ -376,6 +533,10 @@ def run_device(args):
             by = r_ * f_ * es_ * (2 if kind == "launch_bn_forward" else 3)
             row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1),
                        frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
+        elif kind in chain_flops:
+            fl = chain_flops[kind]
+            row.update(bound="tensor", gflop=round(fl / 1e9, 3), tflops=round(fl / (us * 1e-6) / 1e12, 1),
+                       frac=round(fl / (us * 1e-6) / 1e12 / tc_burst, 4))
         elif kind == "launch_tail_forward":
             by = 4096.0 * B
             row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1), frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
@@ -386,23 +547,32 @@ def run_device(args):
             by = 4.0 * 7 * model.flat_params.numel() + (2 * model.flat_params.numel() if args.precision == "bf16" else 0)
             row.update(bound="hbm", mbytes=round(by / 1e6, 2), gbs=round(by / (us * 1e-6) / 1e9, 1), frac=round(by / (us * 1e-6) / 1e9 / hbm_peak, 4))
         per_launch.append(row)
-    gemm_ms = sum(v for k, v in agg.items() if k.startswith("gemm"))
-    gemm_launches = sum(1 for label, _ in prof_runs[-1] if label.startswith("gemm"))
+    gemm_ms = sum(v for k, v in agg.items() if k.startswith("gemm") or k.startswith("chain"))
+    gemm_launches = sum(1 for label, _ in prof_runs[-1] if label.startswith("gemm") or label.startswith("chain"))
     serial_ms = sum(agg.values())
     flops = F_ALG_PER_SAMPLE * B
     family_tf = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else peaks["bf16_tflops_sustained"] / 2
     # dominant kernel = the single most expensive launch: the last decoder Linear with the fused sigmoid/BCE/dlogits
     # epilogue (gemm_kernel<bf16, BCE>), [3B,400] x [784,400]^T
-    dom_ms = agg.get("gemm_fwd_bce", 0.0)
-    dom_flops = 2.0 * 3 * B * 784 * 400
+    chained = "chain_dec_fwd" in agg
+    if chained:
+        # the decoder's forward chain: three Linears with in-kernel BatchNorm grid barriers + sigmoid/BCE/dlogits epilogue
+        dom_label, dom_ms, dom_flops = "chain_dec_fwd", agg["chain_dec_fwd"], chain_flops["chain_dec_fwd"]
+        dom_name = ("mvae::chain_kernel<FWD_BN, FWD_BN, BCE> (slab-persistent decoder forward: Linear n-200, 200-400, 400-784 on "
+                    "tcgen05/TMA with in-kernel BatchNorm grid barriers + fused sigmoid/BCE/dlogits epilogue; the most expensive launch)")
+    else:
+        dom_label, dom_ms, dom_flops = "gemm_fwd_bce", agg.get("gemm_fwd_bce", 0.0), 2.0 * 3 * B * 784 * 400
+        dom_name = ("mvae::gemm_kernel<BCE> (tcgen05/TMA GEMM [3B,400]x[784,400]^T + fused sigmoid/BCE/dlogits epilogue; the most "
+                    "expensive launch of the per-layer path)")
     achieved_tf = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_gemm_kernel_sample.json")) as f:
+    traffic, traffic_source = None, "no ncu summary for this kernel under profiles/"
+    try:   # DRAM traffic of the same kernel from the committed ncu --set full summary (stamped with the commit it was taken at)
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_chain_summary.json")) as f:
             prof = json.load(f)
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = sum(float(prof[k][0]) * scale[prof[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        k = prof["kernels"][dom_label]
+        traffic = float(k["dram_bytes_read"]) + float(k["dram_bytes_write"])
+        traffic_source = "profiles/r02_ncu_chain_summary.json (ncu --set full, commit %s)" % prof.get("commit", "?")
     except Exception:
         pass
     t_roof_us = flops / (peaks["bf16_tflops"] * 1e12) * 1e6 + Q_TAIL_PER_SAMPLE * B / (peaks["hbm_gbs"] * 1e9) * 1e6
@@ -433,11 +603,10 @@ def run_device(args):
                 "path": "HostPipeline(MVAETrainer).run(pinned uint8 images, int64 labels) -> pinned host losses, "
                         "copies overlapped with compute"},
         "roofline": {"bound": "tensor",
-                     "kernel": "mvae::gemm_kernel<bf16, BCE> (tcgen05/TMA GEMM [3B,400]x[784,400]^T + fused sigmoid/BCE/"
-                               "dlogits epilogue; the most expensive launch of the step)",
-                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "traffic": traffic, "traffic_source": "profiles/r01_ncu_full_gemm_kernel_sample.json (ncu --set full)",
-                     "peak_source": peaks["source"] + " (sustained bf16 GEMM peak; tf32 = half)",
+                     "kernel": dom_name,
+                     "achieved": achieved_tf, "peak": tc_burst, "unit": "TFLOP/s", "frac": achieved_tf / tc_burst,
+                     "traffic": traffic, "traffic_source": traffic_source,
+                     "peak_source": peaks["source"] + " (burst bf16 GEMM peak: the launch is timed in isolation; tf32 = half)",
                      "flops_per_launch": dom_flops, "launch_ms": dom_ms,
                      "note": "duration = CUDA events around the launch on its stream (includes ~5 us launch latency)"},
         "gemm_family": {"launches_per_step": gemm_launches, "flops_per_step": flops, "ms_per_step_serialised": gemm_ms,
@@ -451,6 +620,10 @@ def run_device(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(torch)
+    if world == 1 and not args.no_extra:
+        trainer._graphs.clear()
+        line["torch_gpu_baseline"] = torch_gpu_baseline(torch, dev)
+        line["other_configs"] = other_configs(torch, dev, log)
     print(json.dumps(line), flush=True)
     teardown()
     return 0
@@ -467,6 +640,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the whole backward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the torch_gpu_baseline and other_configs legs")
     ap.add_argument("--weak", type=float, nargs=2, default=None, metavar=("P_IMAGE", "P_TEXT"),
                     help="MNIST weak supervision (mnist/modal_weak.py): per-batch probabilities of the image-only / text-only terms")
     ap.add_argument("--workload", default="mnist", choices=["mnist", "celeba", "multimnist"],
