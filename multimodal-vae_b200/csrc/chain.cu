@@ -610,7 +610,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         bar_epi();
         // the forward's pre-activations of this warp's units are requested before the accumulator is awaited
         wait_all_chunks();
-        // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the pre-activations are parked in the arena
+        // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the masked gradient dyhat is parked in the arena (bf16):
+        //      pass 2 then needs neither TMEM nor the transposing tile nor the mask again
         for (int u = jw; u < n_units; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
@@ -635,12 +636,12 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
               for (int i = 0; i < 4; ++i) {
                 const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
                 const uint2 hw = hx[half * 4 + i];
-                sts64(arena_addr(smem_u, srow + i, col0), hw.x, hw.y);
                 const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
                 const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
                 const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
                 const float d2 = fmaf(ta.z, x2, tb.z) > 0.f ? a.z : 0.f;
                 const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
+                sts64(arena_addr(smem_u, srow + i, col0), pack_bf16(d0, d1), pack_bf16(d2, d3));
                 s0[0] += d0; s0[1] += d1; s0[2] += d2; s0[3] += d3;
                 s1[0] = fmaf(d0, fmaf(x0, trs.x, tmr.x), s1[0]);
                 s1[1] = fmaf(d1, fmaf(x1, trs.y, tmr.y), s1[1]);
@@ -662,7 +663,20 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
           }
         }
+        release_all_chunks();
         publish_stats();
+        // this lane's pre-activations of a unit: [half * 4 + i] -> 4 bf16; pass 2 reads them again (L2), one unit ahead,
+        // the first unit's request crosses the grid barrier
+        auto load_hpre = [&](int u, uint2 (&h)[8]) {
+          const int c0 = 32 * u + 4 * cq;
+          const bool lv = u < n_units && c0 < N;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            h[k] = lv ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + c0))
+                      : make_uint2(0u, 0u);
+        };
+        uint2 hx2[8];
+        load_hpre(jw, hx2);
         if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
         if (et == 0) stamp(19 + il * 4);
@@ -678,41 +692,34 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
         }
         bar_epi();
-        // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) = a * dyhat - k1 * x + k2
+        // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) = a * dyhat - k1 * x + k2,
+        //      in place in the arena (the next dgrad's A operand) and to global memory (the weight gradient's operand)
         for (int u = jw; u < n_units; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
-          uint32_t v[32];
-          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
-          const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 k2 = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+          uint2 hn[8];
+          load_hpre(u + 4, hn);
+          if (padded) {
+            const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 k2 = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            deposit(half, v);
-            if (padded) {
-              const int r0 = half * 16 + 4 * rsel;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
-                const uint32_t addr = arena_addr(smem_u, q * 32 + r0 + i, col0);
-                const uint2 hw = live ? lds64(addr) : make_uint2(0u, 0u);
-                const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
-                const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
-                const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
-                const float d2 = fmaf(ta.z, x2, tb.z) > 0.f ? a.z : 0.f;
-                const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
-                const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
-                const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
-                if (live) *reinterpret_cast<uint2*>(L.out_post + (wrow0 + r0 + i) * N + col0) = make_uint2(w0, w1);
-                if (L.write_arena) sts64(addr, w0, w1);
-              }
+            for (int hi = 0; hi < 8; ++hi) {
+              const int r = (hi >> 2) * 16 + 4 * rsel + (hi & 3);
+              const uint32_t addr = arena_addr(smem_u, q * 32 + r, col0);
+              const uint2 dw = live ? lds64(addr) : make_uint2(0u, 0u);
+              const uint2 hw = hx2[hi];
+              const float d0 = bf_lo(dw.x), d1 = bf_hi(dw.x), d2 = bf_lo(dw.y), d3 = bf_hi(dw.y);
+              const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
+              const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
+              const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
+              if (live) *reinterpret_cast<uint2*>(L.out_post + (wrow0 + r) * N + col0) = make_uint2(w0, w1);
+              if (L.write_arena) sts64(addr, w0, w1);
             }
-            __syncwarp();
           }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hx2[k] = hn[k];
         }
-        release_all_chunks();
         if (L.write_arena) {
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(a_epi_bar);
