@@ -152,13 +152,15 @@ class ConvMVAEBase:
         # kernels of the main stream; fork / join are stream-ordered events (valid under CUDA-graph capture)
         self.side_stream = torch.cuda.Stream(device=dev)
         self.use_side_stream = True
-        # implicit GEMM (mvae_conv_gemm): patch matrices of layers with >= 8 bf16 channels are gathered inside the GEMM
-        # instead of being written by mvae_im2col and read back (MVAE_IMPLICIT_CONV=0 restores the explicit path)
-        self.implicit_conv = self.act_dtype == torch.bfloat16 and os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
-        # the col2im side through mvae_convt_class_gemm (one gather GEMM per output-parity class): the op is parity-tested,
-        # the hosts' use of it has not been run end to end yet - off unless MVAE_IMPLICIT_COL2IM=1
-        self.implicit_col2im = self.implicit_conv and os.environ.get("MVAE_IMPLICIT_COL2IM", "0") == "1"
-        self.convt_merged = os.environ.get("MVAE_CONVT_MERGED", "0") == "1"   # all parity classes in one launch (draft)
+        # implicit GEMM: patch matrices of layers with >= 8 bf16 channels are never materialised.  The im2col side
+        # (Conv2d forward, ConvTranspose2d input gradient, both weight gradients) gathers its operand inside mvae_conv_gemm;
+        # the col2im side (ConvTranspose2d forward, Conv2d input gradient) runs as stride^2 output-parity classes in ONE
+        # launch of mvae_convt_gemm (classes of unequal shape fall back to one launch per class).  tf32 keeps the explicit
+        # im2col / col2im kernels (the gather writes bf16 operand tiles).  Measured on a B200, B = 256 (profiles/r02_conv_*):
+        # CelebA 121.7 k -> 132.0 k samples/s, MultiMNIST 152.6 k -> 160.2 k with the col2im side implicit.
+        self.implicit_conv = self.act_dtype == torch.bfloat16
+        self.implicit_col2im = self.implicit_conv
+        self.convt_merged = True
         # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
         # own stream beside the image networks
         self.mod_stream = torch.cuda.Stream(device=dev)

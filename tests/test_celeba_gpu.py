@@ -130,8 +130,6 @@ def test_transposed_conv_implicit_matches_torch(cfg):
     assert rel(out.float(), ref) < 4e-3
 
 
-@pytest.mark.skipif(os.environ.get("MVAE_TEST_CONVT_MERGED") != "1",
-                    reason="draft entry mvae_convt_gemm (all parity classes in one launch): not yet run on a B200")
 @pytest.mark.parametrize("cfg", [(4, 8, 128, 64, 4, 2, 1), (3, 5, 256, 128, 4, 1, 0), (2, 2, 256, 128, 4, 2, 0),
                                  (2, 12, 64, 32, 5, 2, 1), (5, 16, 64, 32, 4, 2, 1)])
 def test_transposed_conv_merged_classes_matches_torch(cfg):
