@@ -418,7 +418,7 @@ def run_device(args):
             trainer.step(pool_x[0], pool_y[0], terms=terms, lambdas=lams)
     # ---- device-resident throughput ("value")
     for i in range(max(args.warmup, 3)):
-        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], **step_kwargs())
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], ready=True, **step_kwargs())
     log("warmup done")
     barrier()
     log("barrier done")
@@ -429,7 +429,7 @@ def run_device(args):
     align_ranks()
     e0.record()
     for i in range(args.steps):
-        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], **step_kwargs())
+        losses, _ = trainer.step(pool_x[i % n_slots], pool_y[i % n_slots], ready=True, **step_kwargs())
     e1.record()
     log("timed loop enqueued")
     barrier()

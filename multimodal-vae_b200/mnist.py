@@ -443,6 +443,45 @@ class MVAETrainer:
         self.grad_scale = grad_scale
         self._graphs = {}
         self.last_graph_launches = 0
+        # graph replay: two sets of static input buffers (and one captured graph per set) alternate, so that the next
+        # step's inputs are staged on a copy stream while the current step still reads its own
+        self._slot = 0
+        self._stage_stream = None
+
+    def _graph_input(self, image):
+        """What the captured graph takes as its image input: a uint8 device batch goes in as it is (the conversion to
+        the activation dtype is the graph's first node - the step consumes uint8), anything else through to_act()."""
+        if image.dtype == torch.uint8 and image.is_cuda:
+            return image.reshape(-1, 784).contiguous()
+        return self.model.to_act(image)
+
+    def _stage(self, ent, x, y, eps, ready=None):
+        """Copy the step's inputs into the entry's static buffers on the staging stream: behind the last replay that
+        used this entry (two steps ago), i.e. beside the previous step - provided the caller says when the inputs are
+        complete: `ready` = a torch.cuda.Event recorded by their producer, True (complete since long, e.g. a resident
+        pool), or None: ordered behind everything enqueued on the current stream so far (always safe, no overlap)."""
+        dev = self.model.device_
+        if self._stage_stream is None:
+            self._stage_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        st = self._stage_stream
+        if ent.get("fresh") or ready is None:
+            st.wait_stream(main)
+        else:
+            st.wait_event(ent["free"])
+            if ready is not True:
+                st.wait_event(ready)
+        with torch.cuda.stream(st):
+            ent["x"].copy_(x, non_blocking=True)
+            ent["y"].copy_(y, non_blocking=True)
+            if eps is not None:
+                ent["eps"].copy_(eps, non_blocking=True)
+            ent["ready"].record(st)
+        for t in (x, y, eps):
+            if t is not None:
+                t.record_stream(st)
+        main.wait_event(ent["ready"])
+        ent["fresh"] = False
 
     @staticmethod
     def mnist_kl_weight(batch: int, annealing_factor: float = 1.0) -> float:
@@ -454,17 +493,18 @@ class MVAETrainer:
         return tt, [self.mnist_kl_weight(batch, annealing_factor)] * len(tt)
 
     def step(self, image, text, eps=None, terms=("joint", "image", "text"), lambdas=((1.0, 1.0),) * 3,
-             annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True):
+             annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True, ready=None):
         """One training step.  Returns (losses [n_terms, 4] device tensor: total / image / text / KL per term,
-        outputs or None).  `image`: [B,784] (or [B,1,28,28]) uint8 / float32 / storage dtype, host or device."""
+        outputs or None).  `image`: [B,784] (or [B,1,28,28]) uint8 / float32 / storage dtype, host or device.
+        `ready` (graph replay only): when the device inputs are complete - see _stage()."""
         m = self.model
-        x = m.to_act(image)
         y = text.to(m.device_, non_blocking=True).long().contiguous()
         if eps is not None:
             eps = eps.to(m.device_, torch.float32).contiguous()
         if self.use_cuda_graph and not outputs:
-            return self._graph_step(x, y, eps, tuple(terms), tuple(map(tuple, lambdas)), annealing_factor, update,
-                                    zero_grad), None
+            return self._graph_step(self._graph_input(image), y, eps, tuple(terms), tuple(map(tuple, lambdas)),
+                                    annealing_factor, update, zero_grad, ready=ready), None
+        x = m.to_act(image)
         tt, klw = self._norm(terms, x.shape[0], annealing_factor)
         return m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=zero_grad,
                       adam=self.adam if update else None, outputs=outputs, grad_scale=self.grad_scale)
@@ -526,7 +566,7 @@ class MVAETrainer:
     def _reduce_gradients(self) -> None:
         """Hook between the backward of an accumulated step and its Adam update (data parallel: the all-reduce)."""
 
-    _MAX_GRAPHS = 16   # captured graphs kept per trainer (least recently used are dropped: each owns static buffers)
+    _MAX_GRAPHS = 32   # captured graphs kept per trainer (least recently used are dropped: each owns static buffers)
 
     def _graph_cache_get(self, cache, key):
         ent = cache.get(key)
@@ -539,22 +579,19 @@ class MVAETrainer:
         while len(cache) > self._MAX_GRAPHS:
             cache.pop(next(iter(cache)))
 
-    def _graph_step(self, x, y, eps, terms, lambdas, annealing_factor, update, zero_grad):
+    def _graph_step(self, x, y, eps, terms, lambdas, annealing_factor, update, zero_grad, ready=None):
         """Replay of the step as one CUDA graph (static input buffers; one graph per configuration)."""
         m = self.model
         # every scalar that capture bakes into kernel arguments is part of the key (Adam hyper-parameters included:
         # adjust_learning_rate / annealing schedules mutate them between steps); the cache is bounded (LRU)
         a_ = self.adam
+        self._slot ^= 1
         key = (x.shape[0], terms, lambdas, float(annealing_factor), bool(update), bool(zero_grad), eps is not None,
-               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), float(self.grad_scale))
+               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), float(self.grad_scale), x.dtype, self._slot)
         ent = self._graph_cache_get(self._graphs, key)
         if ent is None:
             sx, sy = torch.empty_like(x), torch.empty_like(y)
             se = torch.empty_like(eps) if eps is not None else None
-            sx.copy_(x)
-            sy.copy_(y)
-            if se is not None:
-                se.copy_(eps)
             losses = torch.empty(len(terms), 4, device=m.device_, dtype=torch.float32)
             tt, klw = self._norm(terms, x.shape[0], annealing_factor)
             kw = dict(eps=se, backward=True, zero_grad=zero_grad, adam=self.adam if update else None,
@@ -566,16 +603,14 @@ class MVAETrainer:
             before = lib.mvae_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                m._run(sx, sy, tt, lambdas, klw, **kw)
-            ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses,
-                   "launches": int(lib.mvae_launch_count() - before)}
+                m._run(m.to_act(sx), sy, tt, lambdas, klw, **kw)   # uint8 input: the conversion kernel is the first node
+            ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses, "fresh": True,
+                   "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
+                   "launches": int(lib.mvae_launch_count() - before) + (1 if x.dtype == torch.uint8 else 0)}
             self._graph_cache_put(self._graphs, key, ent)
-        else:
-            ent["x"].copy_(x, non_blocking=True)
-            ent["y"].copy_(y, non_blocking=True)
-            if eps is not None:
-                ent["eps"].copy_(eps, non_blocking=True)
+        self._stage(ent, x, y, eps, ready)
         ent["graph"].replay()
+        ent["free"].record(torch.cuda.current_stream(m.device_))
         self.last_graph_launches = ent["launches"]
         return ent["losses"]
 
@@ -635,8 +670,12 @@ class HostPipeline:
             idx += 1
         while pending:
             sl = pending.pop(0)
-            main.wait_event(sl["ready"])
-            losses, _ = self.trainer.step(sl["x"], sl["y"], **step_kwargs)
+            if getattr(self.trainer, "use_cuda_graph", False) or getattr(self.trainer, "dp_graph", False):
+                # graph replay: the trainer stages the batch into its static buffers behind the upload's own event
+                losses, _ = self.trainer.step(sl["x"], sl["y"], ready=sl["ready"], **step_kwargs)
+            else:
+                main.wait_event(sl["ready"])
+                losses, _ = self.trainer.step(sl["x"], sl["y"], **step_kwargs)
             sl["free"].record(main)
             if sl["loss_host"] is None or sl["loss_host"].shape != losses.shape:
                 sl["loss_host"] = torch.empty(losses.shape, dtype=losses.dtype).pin_memory()

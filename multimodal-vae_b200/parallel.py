@@ -189,24 +189,25 @@ class DataParallelTrainer(MVAETrainer):
         allreduce_flat_(self.model.flat_grads, self.group)
 
     def step(self, image, text, eps=None, terms=("joint", "image", "text"), lambdas=((1.0, 1.0),) * 3,
-             annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True):
+             annealing_factor: float = 1.0, update: bool = True, outputs: bool = False, zero_grad: bool = True, ready=None):
         if not update or not zero_grad or outputs:
             raise NotImplementedError("DataParallelTrainer.step always zeroes the gradients, all-reduces and applies Adam; "
                                       "update=False / zero_grad=False / outputs=True are not supported (use MVAETrainer)")
         m = self.model
-        x = m.to_act(image)
         y = text.to(m.device_, non_blocking=True).long().contiguous()
         if eps is not None:
             eps = eps.to(m.device_, torch.float32).contiguous()
         if not self.dp_graph:
-            return self._local_then_reduce(x, y, eps, terms, lambdas, annealing_factor), None
+            return self._local_then_reduce(m.to_act(image), y, eps, terms, lambdas, annealing_factor), None
+        x = self._graph_input(image)
         a_ = self.adam
+        self._slot ^= 1
         key = (x.shape[0], tuple(terms), tuple(map(tuple, lambdas)), float(annealing_factor), eps is not None,
-               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]))
+               float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), x.dtype, self._slot)
         ent = self._graph_cache_get(self._dp_graphs, key)
         if ent is None:
-            sx, sy = x.clone(), y.clone()
-            se = eps.clone() if eps is not None else None
+            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            se = torch.empty_like(eps) if eps is not None else None
             losses = torch.empty(len(terms), 4, device=m.device_, dtype=torch.float32)
             # NCCL must have been used once outside capture (communicator setup is not capturable)
             allreduce_flat_(torch.zeros(8, device=m.device_), self.group)
@@ -216,15 +217,13 @@ class DataParallelTrainer(MVAETrainer):
             before = lib.mvae_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._local_then_reduce(sx, sy, se, terms, lambdas, annealing_factor, losses=losses)
-            ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses,
-                   "launches": int(lib.mvae_launch_count() - before)}
+                self._local_then_reduce(m.to_act(sx), sy, se, terms, lambdas, annealing_factor, losses=losses)
+            ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses, "fresh": True,
+                   "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
+                   "launches": int(lib.mvae_launch_count() - before) + (1 if x.dtype == torch.uint8 else 0)}
             self._graph_cache_put(self._dp_graphs, key, ent)
-        else:
-            ent["x"].copy_(x, non_blocking=True)
-            ent["y"].copy_(y, non_blocking=True)
-            if eps is not None:
-                ent["eps"].copy_(eps, non_blocking=True)
+        self._stage(ent, x, y, eps, ready)
         ent["graph"].replay()
+        ent["free"].record(torch.cuda.current_stream(m.device_))
         self.last_graph_launches = ent["launches"] + 1
         return ent["losses"], None

@@ -33,10 +33,12 @@ for r in data:
     grid = r[ix["launch__grid_size"]] if "launch__grid_size" in ix else ""
     key = None
     if "chain_kernel" in name:
-        g = int(float(grid)) if grid else 0
-        order = ["chain_enc_fwd", "chain_dec_fwd", "chain_dec_bwd", "chain_enc_bwd"]
-        key = order[seen_chain % 4]
-        seen_chain += 1
+        import re
+        m = re.search(r"chain_kernel<\(?(?:int\))?\s*(-?\d+),\s*(?:\(int\))?\s*(-?\d+),\s*(?:\(int\))?\s*(-?\d+)", name)
+        kinds = tuple(int(x) for x in m.groups()) if m else None
+        key = {(0, 0, 1): "chain_enc_fwd", (0, 0, 2): "chain_dec_fwd", (3, 3, 4): "chain_dec_bwd", (3, 3, -1): "chain_enc_bwd"}.get(kinds)
+        if key is None:
+            continue
     elif "tail_fwd" in name:
         key = "tail_forward"
     elif "tail_bwd" in name:
