@@ -119,6 +119,8 @@ struct CLayer {
 
 struct alignas(64) CParams {
   CUtensorMap tm[5];
+  CUtensorMap tmo[4];     // outputs written by TMA from the arena: [2 * layer] pre-BatchNorm / [2 * layer + 1] post (forward),
+                          // [2 * layer + 1] gradient at the pre-BatchNorm output (backward); boxes of 64 columns x 128 rows
   CRing ring[2];
   CPass pass[kMaxPass];
   CLayer layer[kMaxLayer];
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       asm volatile("trap;");
     }
     for (int i = 0; i < 5; ++i) ptx::prefetch_tmap(&p.tm[i]);
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.tmo[i]);
     for (int s = 0; s < 4; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -487,6 +490,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           epi_par ^= 1u << ci;
         }
       };
+      // the arena's panels of this layer -> global memory through an output tensor map (one thread; asynchronous: the
+      // epilogue warps issue no global stores for the activations, and the copy runs under whatever comes next)
+      auto store_arena = [&](const CUtensorMap* om) {
+        const int n_panels = (N + 63) >> 6;
+        for (int pn = 0; pn < n_panels; ++pn) ptx::tma_store_2d(om, smem + pn * kPanel, pn * 64, m0);
+        ptx::bulk_commit_group();
+      };
       // publish the slab's column sums: red[quarter][stat][column] -> one global atomic per column and statistic
       auto publish_stats = [&]() {
         bar_epi();
@@ -503,6 +513,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         float* s_ca = tab + 400;
         float* s_cb = tab + 800;
         for (int c = et; c < 400; c += kCEpi) s_bias[c] = c < N ? L.bias[c] : 0.f;
+        if (et == 0) ptx::bulk_wait_read_all();   // the previous layer's output copy has left the arena
         bar_epi();
         wait_all_chunks();
         // ---- pass 1: slab statistics; the bf16 pre-activations are parked in the arena (the layer's own A operand is spent)
@@ -542,7 +553,9 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
         }
         release_all_chunks();
-        publish_stats();
+        ptx::fence_proxy_async_smem();             // the parked pre-activations are read by the TMA store below
+        publish_stats();                           // (starts with a barrier of the epilogue warps)
+        if (et == 0) store_arena(&p.tmo[2 * il]);  // pre-BatchNorm activations -> global (the backward reads them)
         if (et == 0) stamp(18 + il * 4);
         group_barrier(L.counter + grp, slabs_per_group, p.err, et);
         if (et == 0) stamp(19 + il * 4);
@@ -562,13 +575,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           s_ca[c] = a_;
           s_cb[c] = b_;
         }
+        if (et == 0) ptx::bulk_wait_read_all();    // pass 2 overwrites the arena in place
         bar_epi();
         // ---- pass 2: BatchNorm + ReLU in place in the arena -> next layer's A operand; both copies the backward and the
         //      weight gradients need go to global memory from here (after the barrier: nothing for its fence to wait on)
         for (int u = jw; u < n_units; u += 4) {
           const int col0 = 32 * u + 4 * cq;
-          const bool live = col0 < N, padded = col0 < Npad;
-          if (!padded) continue;
+          if (!(col0 < Npad)) continue;
           const float4 ca = tab4(s_ca + col0);
           const float4 cb = tab4(s_cb + col0);
 #pragma unroll
@@ -579,18 +592,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             const float x0 = bf_lo(xw.x), x1 = bf_hi(xw.x), x2 = bf_lo(xw.y), x3 = bf_hi(xw.y);
             const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
             const uint32_t w1 = pack_bf16(fmaxf(fmaf(ca.z, x2, cb.z), 0.f), fmaxf(fmaf(ca.w, x3, cb.w), 0.f));
-            if (L.write_arena) sts64(addr, w0, w1);
-            if (live) {
-              const long long o = (wrow0 + r) * N + col0;
-              *reinterpret_cast<uint2*>(L.out_pre + o) = xw;
-              *reinterpret_cast<uint2*>(L.out_post + o) = make_uint2(w0, w1);
-            }
+            sts64(addr, w0, w1);
           }
         }
-        if (L.write_arena) {
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(a_epi_bar);
-        }
+        ptx::fence_proxy_async_smem();
+        if (L.write_arena) ptx::mbar_arrive(a_epi_bar);
+        bar_epi();
+        if (et == 0) store_arena(&p.tmo[2 * il + 1]);   // post-BatchNorm activations -> global (the next weight gradient's operand)
       } else if constexpr (kKind == CE_DGRAD_BN) {
         float* s_a = tab;
         float* s_b = tab + 400;
@@ -607,6 +615,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
           s_a[c] = a_; s_b[c] = b_; s_rs[c] = rs; s_mr[c] = mr;
         }
+        if (et == 0) ptx::bulk_wait_read_all();   // the previous layer's output copy has left the arena
         bar_epi();
         // the forward's pre-activations of this warp's units are requested before the accumulator is awaited
         wait_all_chunks();
@@ -713,17 +722,16 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
               const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
               const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
               const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
-              if (live) *reinterpret_cast<uint2*>(L.out_post + (wrow0 + r) * N + col0) = make_uint2(w0, w1);
-              if (L.write_arena) sts64(addr, w0, w1);
+              sts64(addr, w0, w1);
             }
           }
 #pragma unroll
           for (int k = 0; k < 8; ++k) hx2[k] = hn[k];
         }
-        if (L.write_arena) {
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(a_epi_bar);
-        }
+        ptx::fence_proxy_async_smem();
+        if (L.write_arena) ptx::mbar_arrive(a_epi_bar);
+        bar_epi();
+        if (et == 0) store_arena(&p.tmo[2 * il + 1]);   // gradient at the pre-BatchNorm output -> global (weight gradient operand)
       } else if constexpr (kKind == CE_FWD_STORE || kKind == CE_DGRAD_STORE) {
         float* s_bias = tab;
         for (int c = et; c < 400; c += kCEpi) s_bias[c] = (L.bias != nullptr && c < N) ? L.bias[c] : 0.f;
@@ -860,6 +868,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     run_layer(std::integral_constant<int, kKind0>{}, std::integral_constant<int, 0>{});
     run_layer(std::integral_constant<int, kKind1>{}, std::integral_constant<int, 1>{});
     if constexpr (kKind2 >= 0) run_layer(std::integral_constant<int, kKind2>{}, std::integral_constant<int, 2>{});
+    if (et == 0) ptx::bulk_wait_all();   // the arena's output copies are complete before the CTA gives up its shared memory
   } else {
     // =================================================================== keeper CTA: what needs every group's statistics,
     // in group order (one reference forward pass per group), while the slab CTAs carry on
@@ -1080,6 +1089,10 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false);
   ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false);
   p.n_pass = ip;
+  if (chain_tmap(&p.tmo[0], a.h1pre, a.B, 400, 400, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[1], a.h1, a.B, 400, 400, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[2], a.h2pre, a.B, 200, 200, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[3], a.h2, a.B, 200, 200, 64, 128)) return 1;
   l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + 400;
   l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = a.bn_updates;
   l1.counter = a.counters; l1.out_pre = a.h1pre; l1.out_post = a.h1; l1.write_arena = 1;
@@ -1112,6 +1125,10 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   ip = add_resident_layer(p, ip, l2, 400, 200, 2, false, 2, false);
   ip = add_resident_layer(p, ip, l3, 784, 400, 3, false, 2, true);
   p.n_pass = ip;
+  if (chain_tmap(&p.tmo[0], a.g1pre, R, 200, 200, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[1], a.g1, R, 200, 200, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[2], a.g2pre, R, 400, 400, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[3], a.g2, R, 400, 400, 64, 128)) return 1;
   l1.kind = CE_FWD_BN; l1.N = 200;
   l1.bias = a.b1; l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.st1; l1.stat1 = a.st1 + G * 200;
   l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + G * 200; l1.running_mean = a.rm1; l1.running_var = a.rv1; l1.bn_updates = 1;
@@ -1151,6 +1168,10 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   ip = add_resident_layer(p, ip, l1, 200, 400, 2, true, 2, false);
   ip = add_resident_layer(p, ip, l0, a.n, 200, 3, true, 2, false);
   p.n_pass = ip;
+  if (chain_tmap(&p.tmo[1], a.dy2, R, 400, 400, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[3], a.dy1, R, 200, 200, 64, 128)) return 1;
+  p.tmo[0] = p.tmo[1];
+  p.tmo[2] = p.tmo[3];
   l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + G * 400; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + G * 400;
   l2.counter = a.counters; l2.hpre = a.g2pre; l2.out_post = a.dy2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
   l1.kind = CE_DGRAD_BN; l1.N = 200;
@@ -1180,6 +1201,10 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false);
   ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false);
   p.n_pass = ip;
+  if (chain_tmap(&p.tmo[1], a.dye2, a.B, 200, 200, 64, 128)) return 1;
+  if (chain_tmap(&p.tmo[3], a.dye1, a.B, 400, 400, 64, 128)) return 1;
+  p.tmo[0] = p.tmo[1];
+  p.tmo[2] = p.tmo[3];
   l2.kind = CE_DGRAD_BN; l2.N = 200;
   l2.gamma = a.gamma2; l2.beta = a.beta2; l2.stat0 = a.sb2; l2.stat1 = a.sb2 + 200; l2.save_mean = a.sv2; l2.save_rstd = a.sv2 + 200;
   l2.counter = a.counters; l2.hpre = a.h2pre; l2.out_post = a.dye2; l2.write_arena = 1; l2.dgamma = a.dgamma2; l2.dbeta = a.dbeta2;
