@@ -617,18 +617,27 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         if (et == 0) ptx::bulk_wait_read_all();   // the previous layer's output copy has left the arena
         bar_epi();
-        // the forward's pre-activations of this warp's units are requested before the accumulator is awaited
+        // this lane's pre-activations of a unit: [half * 4 + i] -> 4 bf16.  Both passes request them one unit ahead (an
+        // L2 round trip is ~1 us); the first request of pass 1 is in flight while the accumulator is awaited, the first
+        // request of pass 2 crosses the grid barrier.
+        auto load_hpre = [&](int u, uint2 (&h)[8]) {
+          const int c0 = 32 * u + 4 * cq;
+          const bool lv = u < n_units && c0 < N;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            h[k] = lv ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + c0))
+                      : make_uint2(0u, 0u);
+        };
+        uint2 hx[8];
+        load_hpre(jw, hx);
         wait_all_chunks();
         // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the masked gradient dyhat is parked in the arena (bf16):
         //      pass 2 then needs neither TMEM nor the transposing tile nor the mask again
         for (int u = jw; u < n_units; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
-          uint2 hx[8];   // [half][i] -> 4 bf16, in flight during the TMEM load
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            hx[k] = live ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + col0))
-                         : make_uint2(0u, 0u);
+          uint2 hnext[8];
+          load_hpre(u + 4, hnext);
           uint32_t v[32];
           load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
           const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -671,19 +680,11 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
             *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
           }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) hx[k] = hnext[k];
         }
         release_all_chunks();
         publish_stats();
-        // this lane's pre-activations of a unit: [half * 4 + i] -> 4 bf16; pass 2 reads them again (L2), one unit ahead,
-        // the first unit's request crosses the grid barrier
-        auto load_hpre = [&](int u, uint2 (&h)[8]) {
-          const int c0 = 32 * u + 4 * cq;
-          const bool lv = u < n_units && c0 < N;
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            h[k] = lv ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + c0))
-                      : make_uint2(0u, 0u);
-        };
         uint2 hx2[8];
         load_hpre(jw, hx2);
         if (et == 0) stamp(18 + il * 4);
