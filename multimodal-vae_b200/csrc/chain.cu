@@ -245,11 +245,7 @@ __device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned
 // ---------------------------------------------------------------- the epilogue's transposing tile and the arena
 // tile: 16 rows x 128 B, 16-byte chunk c of row r at chunk c ^ (r & 7)
 __device__ __forceinline__ uint32_t tile_addr(uint32_t tile, int r, int c) { return tile + r * 128 + (((c ^ r) & 7) << 4); }
-// arena: four bf16 (8 bytes) of a K-major SWIZZLE_128B panel row: columns col0..col0+3 (col0 % 4 == 0) of slab row `row`
-__device__ __forceinline__ uint32_t arena_addr(uint32_t arena, int row, int col0) {
-  const int panel = col0 >> 6, cc = (col0 & 63) >> 3;
-  return arena + panel * kPanel + row * 128 + ((cc ^ (row & 7)) << 4) + ((col0 & 4) << 1);
-}
+// arena: K-major SWIZZLE_128B panels of 128 rows x 128 bytes; 16-byte chunk c of row r lives at chunk c ^ (r & 7)
 __device__ __forceinline__ void sts64(uint32_t addr, uint32_t w0, uint32_t w1) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(w0), "r"(w1) : "memory");
 }
@@ -445,21 +441,30 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     const float inv_cnt = 1.f / static_cast<float>(p.rows_per_group);
 
     // this lane's accumulator row of a 32-column unit, raw from TMEM (the upper 16 columns zero when `wide` is false)
-    auto load_unit = [&](uint32_t taddr, bool wide, uint32_t (&v)[32]) {
+    // This lane's accumulator row of a 32-column unit, raw from TMEM.  Columns beyond the layer hold whatever TMEM holds:
+    // no live lane consumes them (the allocation is 512 columns, the read never leaves it).
+    auto load_unit = [&](uint32_t taddr, uint32_t (&v)[32]) {
       uint32_t lo[16], hi[16];
       ptx::tmem_ld16(taddr, lo);
-      if (wide) {
-        ptx::tmem_ld16(taddr + 16, hi);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) hi[k] = 0u;
-      }
+      ptx::tmem_ld16(taddr + 16, hi);
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         v[k] = lo[k];
         v[16 + k] = hi[k];
       }
+    };
+    // Addresses that depend on the lane only are computed once: the transposed reads of the tile (rows 4 rsel + i, chunk cq)
+    // and the per-row part of an arena address (row q*32 + 4 rsel + i of a panel; a 16-row half adds 2048 bytes).
+    const uint32_t trd0 = tile_addr(tile, 4 * rsel + 0, cq), trd1 = tile_addr(tile, 4 * rsel + 1, cq);
+    const uint32_t trd2 = tile_addr(tile, 4 * rsel + 2, cq), trd3 = tile_addr(tile, 4 * rsel + 3, cq);
+    const uint32_t arow = smem_u + (q * 32 + 4 * rsel) * 128;   // rows (q*32 + 4 rsel + i): + i * 128; row & 7 = 4 (rsel & 1) + i
+    // arena address of (row q*32 + half*16 + 4 rsel + i, columns col0..col0+3) = ua[i] + half * 2048
+    auto unit_arena = [&](int col0, uint32_t (&ua)[4]) {
+      const uint32_t base = arow + (col0 >> 6) * kPanel + ((col0 & 4) << 1);
+      const uint32_t cx = static_cast<uint32_t>((((col0 & 63) >> 3) ^ (4 * (rsel & 1))) << 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ua[i] = base + i * 128 + (cx ^ (i << 4));
     };
     // rows [16*half, 16*half+16) of the warp go into the tile
     auto deposit = [&](int half, const uint32_t (&v)[32]) {
@@ -519,23 +524,24 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         // ---- pass 1: slab statistics; the bf16 pre-activations are parked in the arena (the layer's own A operand is spent)
         for (int u = jw; u < n_units; u += 4) {
           uint32_t v[32];
-          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
+          load_unit(t_row + 32 * u, v);
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
           const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ua[4];
+          unit_arena(col0, ua);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
             if (padded) {
-              const int srow = q * 32 + half * 16 + 4 * rsel;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
                 const float x0 = a.x + bs.x, x1 = a.y + bs.y, x2 = a.z + bs.z, x3 = a.w + bs.w;
                 s0[0] += x0; s0[1] += x1; s0[2] += x2; s0[3] += x3;
                 s1[0] = fmaf(x0, x0, s1[0]); s1[1] = fmaf(x1, x1, s1[1]); s1[2] = fmaf(x2, x2, s1[2]); s1[3] = fmaf(x3, x3, s1[3]);
-                sts64(arena_addr(smem_u, srow + i, col0), pack_bf16(x0, x1), pack_bf16(x2, x3));
+                sts64(ua[i] + half * 2048, pack_bf16(x0, x1), pack_bf16(x2, x3));
               }
             }
             __syncwarp();
@@ -584,10 +590,11 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           if (!(col0 < Npad)) continue;
           const float4 ca = tab4(s_ca + col0);
           const float4 cb = tab4(s_cb + col0);
+          uint32_t ua[4];
+          unit_arena(col0, ua);
 #pragma unroll
           for (int hi = 0; hi < 8; ++hi) {
-            const int r = (hi >> 2) * 16 + 4 * rsel + (hi & 3);
-            const uint32_t addr = arena_addr(smem_u, q * 32 + r, col0);
+            const uint32_t addr = ua[hi & 3] + (hi >> 2) * 2048;
             const uint2 xw = lds64(addr);
             const float x0 = bf_lo(xw.x), x1 = bf_hi(xw.x), x2 = bf_lo(xw.y), x3 = bf_hi(xw.y);
             const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
@@ -617,9 +624,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         if (et == 0) ptx::bulk_wait_read_all();   // the previous layer's output copy has left the arena
         bar_epi();
-        // this lane's pre-activations of a unit: [half * 4 + i] -> 4 bf16.  Both passes request them one unit ahead (an
-        // L2 round trip is ~1 us); the first request of pass 1 is in flight while the accumulator is awaited, the first
-        // request of pass 2 crosses the grid barrier.
+        // this lane's pre-activations of a unit: [half * 4 + i] -> 4 bf16 (pass 2 requests them one unit ahead: an L2 round
+        // trip is ~1 us; pass 1 has no registers left for that)
         auto load_hpre = [&](int u, uint2 (&h)[8]) {
           const int c0 = 32 * u + 4 * cq;
           const bool lv = u < n_units && c0 < N;
@@ -628,43 +634,38 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             h[k] = lv ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + c0))
                       : make_uint2(0u, 0u);
         };
-        uint2 hx[8];
-        load_hpre(jw, hx);
         wait_all_chunks();
         // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the masked gradient dyhat is parked in the arena (bf16):
-        //      pass 2 then needs neither TMEM nor the transposing tile nor the mask again
+        //      pass 2 then needs neither TMEM nor the transposing tile nor the mask again.
+        //      sum dyhat * xhat = rstd * sum(dyhat * x) - mean * rstd * sum(dyhat): the loop accumulates sum(dyhat * x)
         for (int u = jw; u < n_units; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
-          uint2 hnext[8];
-          load_hpre(u + 4, hnext);
+          uint2 hx[8];
+          load_hpre(u, hx);   // in flight during the TMEM load and the first deposit
           uint32_t v[32];
-          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
+          load_unit(t_row + 32 * u, v);
           const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 trs = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 tmr = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+          float s0[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ua[4];
+          unit_arena(col0, ua);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
             if (live) {
-              const int srow = q * 32 + half * 16 + 4 * rsel;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
                 const uint2 hw = hx[half * 4 + i];
                 const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
                 const float d0 = fmaf(ta.x, x0, tb.x) > 0.f ? a.x : 0.f;
                 const float d1 = fmaf(ta.y, x1, tb.y) > 0.f ? a.y : 0.f;
                 const float d2 = fmaf(ta.z, x2, tb.z) > 0.f ? a.z : 0.f;
                 const float d3 = fmaf(ta.w, x3, tb.w) > 0.f ? a.w : 0.f;
-                sts64(arena_addr(smem_u, srow + i, col0), pack_bf16(d0, d1), pack_bf16(d2, d3));
+                sts64(ua[i] + half * 2048, pack_bf16(d0, d1), pack_bf16(d2, d3));
                 s0[0] += d0; s0[1] += d1; s0[2] += d2; s0[3] += d3;
-                s1[0] = fmaf(d0, fmaf(x0, trs.x, tmr.x), s1[0]);
-                s1[1] = fmaf(d1, fmaf(x1, trs.y, tmr.y), s1[1]);
-                s1[2] = fmaf(d2, fmaf(x2, trs.z, tmr.z), s1[2]);
-                s1[3] = fmaf(d3, fmaf(x3, trs.w, tmr.w), s1[3]);
+                sx[0] = fmaf(d0, x0, sx[0]); sx[1] = fmaf(d1, x1, sx[1]); sx[2] = fmaf(d2, x2, sx[2]); sx[3] = fmaf(d3, x3, sx[3]);
               }
             }
             __syncwarp();
@@ -672,16 +673,17 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 8);
-            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
+            sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], 8);
             s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 16);
-            s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+            sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], 16);
           }
           if (live && rsel == 0) {
+            const float4 trs = tab4(s_rs + col0), tmr = tab4(s_mr + col0);
             *reinterpret_cast<float4*>(red + q * kRedStride + col0) = make_float4(s0[0], s0[1], s0[2], s0[3]);
-            *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) = make_float4(s1[0], s1[1], s1[2], s1[3]);
+            *reinterpret_cast<float4*>(red + q * kRedStride + 400 + col0) =
+                make_float4(fmaf(trs.x, sx[0], tmr.x * s0[0]), fmaf(trs.y, sx[1], tmr.y * s0[1]), fmaf(trs.z, sx[2], tmr.z * s0[2]),
+                            fmaf(trs.w, sx[3], tmr.w * s0[3]));
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) hx[k] = hnext[k];
         }
         release_all_chunks();
         publish_stats();
@@ -713,10 +715,11 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 k2 = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t ua[4];
+            unit_arena(col0, ua);
 #pragma unroll
             for (int hi = 0; hi < 8; ++hi) {
-              const int r = (hi >> 2) * 16 + 4 * rsel + (hi & 3);
-              const uint32_t addr = arena_addr(smem_u, q * 32 + r, col0);
+              const uint32_t addr = ua[hi & 3] + (hi >> 2) * 2048;
               const uint2 dw = live ? lds64(addr) : make_uint2(0u, 0u);
               const uint2 hw = hx2[hi];
               const float d0 = bf_lo(dw.x), d1 = bf_hi(dw.x), d2 = bf_lo(dw.y), d3 = bf_hi(dw.y);
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         wait_all_chunks();
         for (int u = jw; u < n_units; u += 4) {
           uint32_t v[32];
-          load_unit(t_row + 32 * u, 32 * u + 16 < Npad, v);
+          load_unit(t_row + 32 * u, v);
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
           const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -751,7 +754,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
               float* dst = L.out_f32 + (wrow0 + half * 16 + 4 * rsel) * L.ld_out + col0;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
                 *reinterpret_cast<float4*>(dst + static_cast<long long>(i) * L.ld_out) = make_float4(a.x + bs.x, a.y + bs.y, a.z + bs.z, a.w + bs.w);
               }
             }
@@ -795,7 +798,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             ptx::tc_fence_after();
           }
           uint32_t v[32];
-          load_unit(t_row + (ci & 1) * buf_cols + 32 * (u - ustart), 32 * u + 16 < Npad, v);
+          load_unit(t_row + (ci & 1) * buf_cols + 32 * (u - ustart), v);
           const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
           float sd[4] = {0.f, 0.f, 0.f, 0.f};
@@ -806,7 +809,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
               const long long orow = (wrow0 + half * 16 + 4 * rsel) * N + col0;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 a = lds_f4(tile_addr(tile, 4 * rsel + i, cq));
+                const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
                 const float av[4] = {a.x, a.y, a.z, a.w};
                 const uint2 tw = tx[half * 4 + i];
                 const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
