@@ -264,8 +264,8 @@ int mvae_conv_gemm(const mvae_gemm_args* args, const mvae_conv_geometry* geometr
  * x: channels-last bf16 [batch, in_h, in_w, channels] (channels % 64 == 0); weight: bf16 [channels, kernel*kernel, out_channels]
  * (ld_tap elements between taps); out: channels-last image [batch, out_h, out_w, ldc] (bf16 / fp32, ldc % 8 == 0).
  * The host loops over the stride*stride classes; mvae_b200._ops.transposed_conv_classes() derives the fields.
- * Parity: test_transposed_conv_implicit_matches_torch (5 geometries).  The shipped hosts still use mvae_gemm + mvae_col2im for
- * this side (MVAE_IMPLICIT_COL2IM=1 switches them over; that wiring has not been run end to end or measured yet). */
+ * Parity: test_transposed_conv_implicit_matches_torch (5 geometries).  The bf16 hosts call this entry (one launch per class)
+ * for geometries whose classes differ in shape (k5 s2), and mvae_convt_gemm (all classes in one launch) otherwise. */
 typedef struct mvae_convt_class {
   int batch, in_h, in_w, channels;
   int out_h, out_w, out_channels;
@@ -277,8 +277,8 @@ typedef struct mvae_convt_class {
 } mvae_convt_class;
 int mvae_convt_class_gemm(const mvae_convt_class* c, int dtype, const void* x, const void* weight, int64_t ld_tap, void* out,
                           int64_t ldc, int out_dtype, void* stream);
-/* DRAFT (compiles; not yet run on a B200, on no product path; its parity test needs MVAE_TEST_CONVT_MERGED=1):
- * the whole transposed convolution in ONE launch - grid.z enumerates the stride*stride parity classes of
+/* The whole transposed convolution in ONE launch (the bf16 hosts' default; parity:
+ * test_transposed_conv_merged_classes_matches_torch) - grid.z enumerates the stride*stride parity classes of
  * mvae_convt_class_gemm.  Only for geometries whose classes have equal shape (kernel % stride == 0 and an output size
  * divisible by the stride, e.g. k4 s2 p1, or stride 1); returns 4 without launching otherwise (callers then loop over
  * mvae_convt_class_gemm).  x [batch, in_h, in_w, channels] bf16, weight [channels, kernel*kernel, out_channels] bf16,

@@ -56,8 +56,6 @@ struct GemmEpilogue {
   float bce_scale[4] = {0, 0, 0, 0};
   float* loss = nullptr;   // [groups]
   void* probs = nullptr;   // optional sigmoid(x) output, same layout/dtype as C
-  int bce_direct = 0;      // EPI_BCE without the bias-gradient column sums (stat0 must be null; the caller reduces dlogits
-                           // itself): every thread owns one accumulator row, no shared-memory staging pass
   // EPI_DGRAD_BN: C = acc * 1[gamma*xhat+beta > 0], xhat = (hpre - mean[g])*rstd[g]
   const void* hpre = nullptr;
   long long ldh = 0;
@@ -65,40 +63,6 @@ struct GemmEpilogue {
   const float* bn_rstd = nullptr;  // [groups][N]
   const float* bn_gamma = nullptr; // [N]
   const float* bn_beta = nullptr;  // [N]
-  // EPI_STORE + fuse_bn: BatchNorm(+ReLU) of the layer applied by the SAME kernel.  After its column sums are published
-  // every CTA arrives at a grid-wide barrier (all CTAs are co-resident - checked on the host), then normalises its own
-  // tile straight from the on-chip staging buffer: Y = relu(a * round(C) + b), a = gamma*rstd, b = beta - mean*a.
-  // Needs stat0/stat1, bn_gamma/bn_beta, statistics groups aligned to the 128-row tiles.
-  int fuse_bn = 0;
-  void* Y = nullptr;               // [M, N] BatchNorm output, dtype and leading dimension of C
-  float* save_mean = nullptr;      // [groups][N] out
-  float* save_rstd = nullptr;
-  float* running_mean = nullptr;   // [N] in/out (may be null)
-  float* running_var = nullptr;
-  int bn_updates = 1;              // running-statistics updates each group stands for
-  float bn_momentum = 0.1f, bn_eps = 1e-5f;
-  int bn_relu = 1;
-  unsigned int* grid_barrier = nullptr;  // [2] zeroed before the launch: arrivals, time-out flag
-};
-
-// Optional transform of the A operand on its way to the tensor core: A' = relu(BatchNorm(A)) with train-mode
-// batch statistics - the BatchNorm1d + ReLU between two Linear layers (mnist/model.py:105-106 etc.) folded into
-// the consuming GEMM instead of a separate elementwise pass.  A is the pre-BatchNorm activation [M, K]
-// (K-major); statistics are per (group, feature k) column sums produced by the previous GEMM's epilogue.
-struct GemmATransform {
-  int enabled = 0;
-  const float* sum = nullptr;      // [groups][K]
-  const float* sumsq = nullptr;    // [groups][K]
-  const float* gamma = nullptr;    // [K]
-  const float* beta = nullptr;     // [K]
-  int rows_per_group = 1 << 30;    // every 128-row tile must lie inside one group
-  float eps = 1e-5f, momentum = 0.1f;
-  int updates_per_group = 1;       // running-statistics updates this pass stands for
-  float* save_mean = nullptr;      // [groups][K] out (block (0,0))
-  float* save_rstd = nullptr;      // [groups][K] out
-  float* running_mean = nullptr;   // [K] in/out (block (0,0)), may be null
-  float* running_var = nullptr;
-  void* out = nullptr;             // [M, K] materialised A' (storage dtype), written by the blockIdx.x == 0 tiles
 };
 
 // Implicit patch-matrix operand (implicit GEMM for the convolutions): instead of reading a materialised im2col
@@ -148,14 +112,11 @@ struct GemmDesc {
   int x3 = 0;
   void* x3_a = nullptr;
   void* x3_b = nullptr;
-  GemmATransform atf;
   GemmEpilogue epi;
   ConvGather gather;
 };
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
-// true if launch_gemm can honour g.epi.fuse_bn (every CTA of the grid co-resident); nothing is launched
-bool gemm_bn_fusable(const GemmDesc& g);
 void set_gemm_debug_times(void* ptr, int epi_kind);
 
 // Tuning knobs readable from the environment (debug / bench sweeps only).
@@ -165,34 +126,15 @@ int env_int(const char* name, int dflt);
 void note_launch(int n = 1);
 long long noted_launches();
 
-// Programmatic dependent launch (PDL).  Every kernel of the step starts with pdl_enter(): it lets the NEXT kernel
-// in the stream be scheduled as soon as all CTAs of this one are resident (its prologue - barrier init, TMEM
-// allocation, tensor-map prefetch - then overlaps this kernel's execution) and blocks until the PREVIOUS
-// kernel has completed and flushed its memory.  Because every kernel waits on its predecessor, completion is
-// transitive along the stream.  Launches go through launch_pdl(), which sets the stream-serialization attribute
-// (also honoured under CUDA-graph capture).  Measured on B200 (bench.py, graph replay): no gain (355 vs 349 us
-// per step), so plain launches are the default; MVAE_PDL=1 switches it on.
+// One launch helper for every kernel of the library (error-checked cudaLaunchKernelEx).
 #ifdef __CUDACC__
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_enter() {
-  pdl_launch_dependents();
-  pdl_wait();
-}
-
 template <typename... KArgs, typename... Args>
-int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-  static const int use_pdl = env_int("MVAE_PDL", 0);
+int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx", __FILE__, __LINE__);
   return 0;

@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(kEwThreads)
                   const float* __restrict__ beta, float* __restrict__ save_mean, float* __restrict__ save_rstd,
                   float* __restrict__ running_mean, float* __restrict__ running_var, int updates_per_group,
                   float momentum, float eps, int relu) {
-  pdl_enter();
   constexpr int N = Vec16<T>::N;
   const int lane = threadIdx.x & 31, tr = threadIdx.x >> 5;
   const int f = (blockIdx.x * 32 + lane) * N;
@@ -204,7 +203,6 @@ __global__ void __launch_bounds__(kEwThreads)
                   int rows_per_group, int groups, const float* __restrict__ s0, const float* __restrict__ s1,
                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  pdl_enter();
   constexpr int N = Vec16<T>::N;
   const int lane = threadIdx.x & 31, tr = threadIdx.x >> 5;
   const int f = (blockIdx.x * 32 + lane) * N;
@@ -298,7 +296,6 @@ __global__ void __launch_bounds__(kEwThreads)
     adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 __nv_bfloat16* __restrict__ p16, long long n4, float lr, float b1, float b2, float eps,
                 const int* __restrict__ step_ptr, float grad_scale, int zero_grad) {
-  pdl_enter();
   // The step count lives on the device so that a captured CUDA graph stays valid from step to step.
   const float step = static_cast<float>(*step_ptr);
   const float bc1 = 1.f - powf(b1, step);
@@ -350,10 +347,10 @@ int launch_bn_forward(int dtype, const void* x, void* y, int rows, int F, int ro
   const int groups = (rows + rows_per_group - 1) / rows_per_group;
   const dim3 grid = bn_grid(rows, F, vec);
   if (dtype == MVAE_F32)
-    return launch_pdl(bn_fwd_kernel<float>, grid, dim3(kEwThreads), 0, st, static_cast<const float*>(x),
+    return launch_kernel(bn_fwd_kernel<float>, grid, dim3(kEwThreads), 0, st, static_cast<const float*>(x),
                       static_cast<float*>(y), rows, F, rows_per_group, groups, sum, sumsq, gamma, beta, save_mean,
                       save_rstd, running_mean, running_var, updates_per_group, momentum, eps, relu);
-  return launch_pdl(bn_fwd_kernel<__nv_bfloat16>, grid, dim3(kEwThreads), 0, st, static_cast<const __nv_bfloat16*>(x),
+  return launch_kernel(bn_fwd_kernel<__nv_bfloat16>, grid, dim3(kEwThreads), 0, st, static_cast<const __nv_bfloat16*>(x),
                     static_cast<__nv_bfloat16*>(y), rows, F, rows_per_group, groups, sum, sumsq, gamma, beta, save_mean,
                     save_rstd, running_mean, running_var, updates_per_group, momentum, eps, relu);
 }
@@ -367,10 +364,10 @@ int launch_bn_backward(int dtype, const void* dyhat, const void* x, void* dx, in
   const int groups = (rows + rows_per_group - 1) / rows_per_group;
   const dim3 grid = bn_grid(rows, F, vec);
   if (dtype == MVAE_F32)
-    return launch_pdl(bn_bwd_kernel<float>, grid, dim3(kEwThreads), 0, st, static_cast<const float*>(dyhat),
+    return launch_kernel(bn_bwd_kernel<float>, grid, dim3(kEwThreads), 0, st, static_cast<const float*>(dyhat),
                       static_cast<const float*>(x), static_cast<float*>(dx), rows, F, rows_per_group, groups, s0, s1, mean,
                       rstd, gamma, dgamma, dbeta);
-  return launch_pdl(bn_bwd_kernel<__nv_bfloat16>, grid, dim3(kEwThreads), 0, st,
+  return launch_kernel(bn_bwd_kernel<__nv_bfloat16>, grid, dim3(kEwThreads), 0, st,
                     static_cast<const __nv_bfloat16*>(dyhat), static_cast<const __nv_bfloat16*>(x),
                     static_cast<__nv_bfloat16*>(dx), rows, F, rows_per_group, groups, s0, s1, mean, rstd, gamma, dgamma,
                     dbeta);
@@ -401,7 +398,7 @@ int launch_adam(float* p, float* g, float* m, float* v, void* p16, long long n, 
   MVAE_REQUIRE(n % 4 == 0 && step_ptr != nullptr, "adam: n=%lld must be a multiple of 4 and step_ptr non-null", n);
   const long long n4 = n / 4;
   const int blocks = static_cast<int>(std::min<long long>((n4 + kEwThreads - 1) / kEwThreads, 4ll * sm_count()));
-  return launch_pdl(adam_kernel, dim3(blocks), dim3(kEwThreads), 0, st, p, g, m, v, static_cast<__nv_bfloat16*>(p16), n4,
+  return launch_kernel(adam_kernel, dim3(blocks), dim3(kEwThreads), 0, st, p, g, m, v, static_cast<__nv_bfloat16*>(p16), n4,
                     lr, b1, b2, eps, step_ptr, grad_scale, zero_grad);
 }
 
@@ -412,7 +409,6 @@ struct NbtInc {
 };
 __global__ void __launch_bounds__(kEwThreads)
     step_prep_kernel(int* step_ptr, int* step_ptr2, float4* zero_buf, long long n4, long long* nbt, NbtInc inc) {
-  pdl_enter();
   if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr != nullptr) *step_ptr += 1;
   if (blockIdx.x == 0 && threadIdx.x == 0 && step_ptr2 != nullptr && step_ptr2 != step_ptr) *step_ptr2 += 1;
   if (blockIdx.x == 0 && threadIdx.x < 6 && nbt != nullptr) nbt[threadIdx.x] += inc.v[threadIdx.x];
@@ -429,13 +425,12 @@ int launch_step_prep(int* step_ptr, int* step_ptr2, float* zero_buf, long long z
   if (blocks < 1) blocks = 1;
   NbtInc i;
   for (int k = 0; k < 6; ++k) i.v[k] = inc[k];
-  return launch_pdl(step_prep_kernel, dim3(blocks), dim3(kEwThreads), 0, st, step_ptr, step_ptr2, reinterpret_cast<float4*>(zero_buf),
+  return launch_kernel(step_prep_kernel, dim3(blocks), dim3(kEwThreads), 0, st, step_ptr, step_ptr2, reinterpret_cast<float4*>(zero_buf),
                     n4, nbt, i);
 }
 
 // losses [3][kMaxGroups] (bce, ce, kl) -> out [G][4] (total, bce, ce, kl)
 __global__ void loss_pack_kernel(const float* __restrict__ acc, float* __restrict__ out, int G) {
-  pdl_enter();
   const int g = threadIdx.x;
   if (g < G) {
     const float b = acc[g], c = acc[kMaxGroups + g], k = acc[2 * kMaxGroups + g];
@@ -446,7 +441,7 @@ __global__ void loss_pack_kernel(const float* __restrict__ acc, float* __restric
   }
 }
 int launch_loss_pack(const float* acc, float* out, int G, cudaStream_t st) {
-  return launch_pdl(loss_pack_kernel, dim3(1), dim3(32), 0, st, acc, out, G);
+  return launch_kernel(loss_pack_kernel, dim3(1), dim3(32), 0, st, acc, out, G);
 }
 
 // ---------------------------------------------------------------- sigmoid backward (module / autograd path)

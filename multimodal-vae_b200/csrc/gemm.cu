@@ -47,15 +47,10 @@ struct GemmKParams {
   int b_tx_bytes;     // bytes TMA actually writes per stage for B
   int vec_ok;         // all epilogue tensors allow 4-element vector access
   int direct_store;   // plain STORE epilogue without statistics: TMEM -> registers -> global, no staging pass
-  int direct_bce;     // BCE epilogue, one accumulator row per thread (no staging, no column sums)
   int aux_off;        // byte offset (dynamic smem) of the prefetched auxiliary tile, or -1
   int red_off;        // byte offset (dynamic smem) of the [2][8][block_n] column-statistics scratch, or -1
   int stat_group_stride;
-  int coef_off;       // byte offset (dynamic smem) of the A-transform coefficient table [2][kb_total*BK], or -1
-  int bnco_off;       // byte offset (dynamic smem) of the fused-BatchNorm coefficient table [2][block_n], or -1
-  unsigned int grid_ctas;  // CTAs of the launch (fused-BatchNorm grid barrier)
   long long* dbg;  // optional per-CTA timestamps (MVAE_GEMM_DEBUG_TIMES), 8 slots per CTA
-  GemmATransform atf;
   GemmEpilogue epi;
   ConvGather gather;  // implicit patch-matrix operand (mode 0: none)
 };
@@ -305,7 +300,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t ready_bar[kMaxStages];  // A-transform: stage transformed, MMA may read it
+  __shared__ __align__(8) uint64_t ready_bar[kMaxStages];  // gathered operand: the stage's gathered half is in place, MMA may read it
   __shared__ __align__(8) uint64_t accum_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_loss[4];
@@ -343,7 +338,7 @@ __global__ void __launch_bounds__(kGemmThreads)
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
-      ptx::mbar_init(&ready_bar[s], kGather != 0 ? 64 : 128);  // A-transform: 128 threads; gather: one 64-thread group
+      ptx::mbar_init(&ready_bar[s], 64);  // gather: one 64-thread group per ring slot
     }
     ptx::mbar_init(&accum_bar, 1);
     ptx::fence_mbar_init();
@@ -357,56 +352,6 @@ __global__ void __launch_bounds__(kGemmThreads)
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) stamp(1);
-  // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel;
-  // from here on global memory written by it is touched.
-  pdl_enter();
-
-  // A-transform coefficients for this tile's statistics group: a = gamma*rstd, b = beta - mean*a (0 beyond K so
-  // that TMA's zero fill stays zero).  Block (0,0) also finalises the BatchNorm layer: saved mean/rstd for the
-  // backward and the running statistics, group by group in order (one reference forward pass per group).
-  if (p.coef_off >= 0) {
-    const GemmATransform& t = p.atf;
-    float* coef_a = reinterpret_cast<float*>(smem + p.coef_off);
-    float* coef_b = coef_a + p.kb_total * BK;
-    const int g = m0 / t.rows_per_group;
-    const int cnt = min(p.M - g * t.rows_per_group, t.rows_per_group);
-    const float inv_cnt = 1.f / cnt;
-    for (int k = threadIdx.x; k < p.kb_total * BK; k += kGemmThreads) {
-      float a = 0.f, b = 0.f;
-      if (k < p.K) {
-        const float mean = t.sum[static_cast<long long>(g) * p.K + k] * inv_cnt;
-        const float var = fmaxf(t.sumsq[static_cast<long long>(g) * p.K + k] * inv_cnt - mean * mean, 0.f);
-        a = t.gamma[k] * rsqrtf(var + t.eps);
-        b = fmaf(-mean, a, t.beta[k]);
-      }
-      coef_a[k] = a;
-      coef_b[k] = b;
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t.save_mean != nullptr) {
-      const int groups = (p.M + t.rows_per_group - 1) / t.rows_per_group;
-      for (int k = threadIdx.x; k < p.K; k += kGemmThreads) {
-        float rm = t.running_mean != nullptr ? t.running_mean[k] : 0.f;
-        float rv = t.running_var != nullptr ? t.running_var[k] : 0.f;
-        for (int gg = 0; gg < groups; ++gg) {
-          const int c2 = min(p.M - gg * t.rows_per_group, t.rows_per_group);
-          const float mean = t.sum[static_cast<long long>(gg) * p.K + k] / c2;
-          const float var = fmaxf(t.sumsq[static_cast<long long>(gg) * p.K + k] / c2 - mean * mean, 0.f);
-          t.save_mean[static_cast<long long>(gg) * p.K + k] = mean;
-          t.save_rstd[static_cast<long long>(gg) * p.K + k] = rsqrtf(var + t.eps);
-          const float unb = c2 > 1 ? var * (static_cast<float>(c2) / (c2 - 1)) : var;
-          for (int u = 0; u < t.updates_per_group; ++u) {
-            rm = (1.f - t.momentum) * rm + t.momentum * mean;
-            rv = (1.f - t.momentum) * rv + t.momentum * unb;
-          }
-        }
-        if (t.running_mean != nullptr) {
-          t.running_mean[k] = rm;
-          t.running_var[k] = rv;
-        }
-      }
-    }
-    __syncthreads();
-  }
 
   // Auxiliary epilogue operand (BCE: the target image tile; dgrad: the pre-BatchNorm activations): every thread
   // copies exactly the elements its own row pass will consume into shared memory with cp.async NOW, so the
@@ -493,7 +438,7 @@ __global__ void __launch_bounds__(kGemmThreads)
           ptx::mbar_wait(&full_bar[s], ph);
           ptx::mbar_wait(&ready_bar[s], ph);
         } else {
-          ptx::mbar_wait(p.coef_off >= 0 ? &ready_bar[s] : &full_bar[s], ph);
+          ptx::mbar_wait(&full_bar[s], ph);
         }
         ptx::tc_fence_after();
         if (i == 0) stamp(2);
@@ -514,69 +459,6 @@ __global__ void __launch_bounds__(kGemmThreads)
       }
       ptx::umma_commit(&accum_bar);  // accumulator complete
       stamp(3);
-    }
-  } else if (warp >= 4 && p.coef_off >= 0) {
-    // ------------------------------------------------------------ A-operand transform (warps 4..7)
-    // relu(a[k]*x + b[k]) applied in place to every landed A stage (BatchNorm + ReLU of the previous layer),
-    // then handed to the MMA warp through ready_bar.  A warp covers 4 rows x 8 16-byte chunks = 512 contiguous
-    // bytes per access (conflict-free); SWIZZLE_128B puts logical chunk (c ^ (row & 7)) at physical chunk c.
-    constexpr int CE = 16 / ESZ;  // elements per 16-byte chunk
-    const float* coef_a = reinterpret_cast<const float*>(smem + p.coef_off);
-    const float* coef_b = coef_a + p.kb_total * BK;
-    const int tt = threadIdx.x - 128;
-    const int c = tt & 7, rbase = tt >> 3;
-    act_t* out = reinterpret_cast<act_t*>(p.atf.out);
-    const bool write_out = out != nullptr && blockIdx.x == 0;
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % S;
-      const uint32_t ph = (i / S) & 1;
-      ptx::mbar_wait(&full_bar[s], ph);
-      const uint32_t a_base = ptx::smem_u32(smem + s * stage_bytes);
-      const int kblk = (kb0 + i) * BK;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = rbase + 16 * j;
-        const int lc = c ^ (r & 7);
-        const int k = kblk + lc * CE;
-        const uint32_t addr = a_base + r * 128 + c * 16;
-        uint32_t w[4];
-        ptx::lds128_u32(addr, w);
-        float ca[CE], cb[CE], x[CE];
-#pragma unroll
-        for (int e4 = 0; e4 < CE; e4 += 4) {
-          const float4 t0 = *reinterpret_cast<const float4*>(coef_a + k + e4);
-          const float4 t1 = *reinterpret_cast<const float4*>(coef_b + k + e4);
-          ca[e4] = t0.x; ca[e4 + 1] = t0.y; ca[e4 + 2] = t0.z; ca[e4 + 3] = t0.w;
-          cb[e4] = t1.x; cb[e4 + 1] = t1.y; cb[e4 + 2] = t1.z; cb[e4 + 3] = t1.w;
-        }
-        if constexpr (ESZ == 4) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) x[q] = __uint_as_float(w[q]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            x[2 * q] = __uint_as_float(w[q] << 16);
-            x[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < CE; ++q) x[q] = fmaxf(fmaf(ca[q], x[q], cb[q]), 0.f);
-        if constexpr (ESZ == 4) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[q] = __float_as_uint(x[q]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
-            w[q] = *reinterpret_cast<const uint32_t*>(&h);
-          }
-        }
-        ptx::sts128(addr, w[0], w[1], w[2], w[3]);
-        if (write_out && m0 + r < p.M && k < p.K)
-          *reinterpret_cast<uint4*>(out + static_cast<long long>(m0 + r) * p.K + k) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-      ptx::mbar_arrive(&ready_bar[s]);
     }
   } else if (kGather == 3 && warp >= 4) {
     // ------------------------------------------------------------ all parity classes in one launch (warps 4..7)
@@ -840,121 +722,6 @@ __global__ void __launch_bounds__(kGemmThreads)
       }
     }
   }
-  if constexpr (kEpi == EPI_BCE) {
-    if (p.direct_bce) {
-      // Row-per-thread BCE epilogue: logits = acc + bias straight from TMEM, 16 columns per tcgen05.ld; the thread reads
-      // its row's 16 targets (one 32/64-byte run), writes 16 dlogits, keeps the loss partial in a register.  No staging
-      // tile, no auxiliary tile, no column sums (the bias gradient is a separate reduction over dlogits).
-      stored_directly = true;
-      float* s_bias = reinterpret_cast<float*>(smem + p.bnco_off);
-      for (int c = threadIdx.x; c < p.block_n; c += kGemmThreads)
-        s_bias[c] = (e.bias != nullptr && n0 + c < p.N) ? e.bias[n0 + c] : 0.f;
-      __syncthreads();
-      const int q = warp & 3;
-      const int row = m0 + q * 32 + lane;
-      const bool valid = row < p.M;
-      const int g = valid ? row / e.rows_per_group : 0;
-      const float g_scale = e.bce_scale[g & 3];
-      const int trow = valid ? row % e.target_rows : 0;
-      const uint32_t t_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-      const act_t* tptr = reinterpret_cast<const act_t*>(e.target) + static_cast<long long>(trow) * e.ldt;
-      float lsum = 0.f;
-      for (int c = (warp >> 2) * 16; c < p.block_n; c += 32) {
-        uint32_t v[16];
-        ptx::tmem_ld16(t_base + c, v);
-        ptx::tmem_ld_wait();
-        const int cn = n0 + c;
-        if (!valid || cn >= p.N) continue;
-        const bool full = cn + 16 <= p.N;
-        float tg[16], d[16], pr[16];
-        if (full && p.vec_ok) {
-          if constexpr (ESZ == 4) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 t4 = __ldg(reinterpret_cast<const float4*>(tptr + cn + j));
-              tg[j] = t4.x; tg[j + 1] = t4.y; tg[j + 2] = t4.z; tg[j + 3] = t4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(tptr + cn + j));
-              const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                tg[j + 2 * k] = __uint_as_float(w4[k] << 16);
-                tg[j + 2 * k + 1] = __uint_as_float(w4[k] & 0xffff0000u);
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) tg[j] = (cn + j < p.N) ? to_f(tptr[cn + j]) : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x = __uint_as_float(v[j]) + s_bias[c + j];
-          const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));  // exp(-|x|) in (0, 1]
-          const float dd = 1.f + ex;
-          float inv = fmaf(-0.47058823529f, dd, 1.41176470588f);             // 1/dd: linear seed + 3 Newton steps (FMA pipe)
-          inv = inv * fmaf(-dd, inv, 2.f);
-          inv = inv * fmaf(-dd, inv, 2.f);
-          inv = inv * fmaf(-dd, inv, 2.f);
-          const float pz = x >= 0.f ? inv : ex * inv;
-          pr[j] = pz;
-          d[j] = g_scale * (pz - tg[j]);
-          if (full || cn + j < p.N)
-            lsum += fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg[j], x, fmaxf(x, 0.f)));
-        }
-        act_t* dst = reinterpret_cast<act_t*>(e.C) + static_cast<long long>(row) * e.ldc + cn;
-        act_t* pdst = e.probs != nullptr ? reinterpret_cast<act_t*>(e.probs) + static_cast<long long>(row) * e.ldc + cn : nullptr;
-        if (full && p.vec_ok) {
-          if constexpr (ESZ == 4) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + j) = make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]);
-              if (pdst != nullptr)
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(pdst) + j) = make_float4(pr[j], pr[j + 1], pr[j + 2], pr[j + 3]);
-            }
-          } else {
-            uint32_t w[8], wp[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
-              const __nv_bfloat162 hp = __floats2bfloat162_rn(pr[2 * j], pr[2 * j + 1]);
-              w[j] = *reinterpret_cast<const uint32_t*>(&h);
-              wp[j] = *reinterpret_cast<const uint32_t*>(&hp);
-            }
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-            if (pdst != nullptr) {
-              *reinterpret_cast<uint4*>(pdst) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(pdst) + 8) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (cn + j < p.N) {
-              if constexpr (ESZ == 4) reinterpret_cast<float*>(dst)[j] = d[j];
-              else reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(d[j]);
-              if (pdst != nullptr) {
-                if constexpr (ESZ == 4) reinterpret_cast<float*>(pdst)[j] = pr[j];
-                else reinterpret_cast<__nv_bfloat16*>(pdst)[j] = __float2bfloat16_rn(pr[j]);
-              }
-            }
-        }
-      }
-      // per-term loss: every thread belongs to one term; warp-reduce per term, one shared atomic per warp per term
-      lsum *= g_scale;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float vv = (valid && (g & 3) == t) ? lsum : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, o);
-        if (lane == 0 && vv != 0.f) atomicAdd(&s_loss[t], vv);
-      }
-    }
-  }
   if (!stored_directly) {
   {
     const int q = warp & 3;
@@ -1041,115 +808,6 @@ __global__ void __launch_bounds__(kGemmThreads)
   }
   }  // !stored_directly
 
-  if constexpr (kEpi == EPI_STORE) {
-    if (e.fuse_bn) {
-      using CT = act_t;  // fused BatchNorm writes the activation dtype (C and Y share dtype and leading dimension)
-      // ---- (3) grid-wide barrier: every CTA has published its column sums (atomics above)
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(e.grid_barrier, 1u);
-        unsigned int seen = 0;
-        long long spins = 0;
-        while (true) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(e.grid_barrier) : "memory");
-          if (seen >= p.grid_ctas) break;
-          if (++spins > (1ll << 21)) {  // ~0.2 s: a co-residency bug must not hang the GPU; flag it instead
-            e.grid_barrier[1] = 0xdeadu;
-            break;
-          }
-          __nanosleep(64);
-        }
-        __threadfence();
-      }
-      __syncthreads();
-      // ---- (4) coefficients of this CTA's columns (the tile lies inside one statistics group)
-      float* s_co = reinterpret_cast<float*>(smem + p.bnco_off);
-      const int groups = (p.M + e.rows_per_group - 1) / e.rows_per_group;
-      const int g = m0 / e.rows_per_group;
-      for (int c = threadIdx.x; c < p.block_n; c += kGemmThreads) {
-        const int n = n0 + c;
-        float a_ = 0.f, b_ = 0.f;
-        if (n < p.N) {
-          const float ga = e.bn_gamma[n], be = e.bn_beta[n];
-          const int cnt = min(p.M, (g + 1) * e.rows_per_group) - g * e.rows_per_group;
-          const float inv = 1.f / static_cast<float>(cnt);
-          const float mean = __ldcg(e.stat0 + static_cast<long long>(g) * p.stat_group_stride + n) * inv;
-          const float var = fmaxf(__ldcg(e.stat1 + static_cast<long long>(g) * p.stat_group_stride + n) * inv - mean * mean, 0.f);
-          const float rstd = rsqrtf(var + e.bn_eps);
-          a_ = ga * rstd;
-          b_ = fmaf(-mean, a_, be);
-          if (blockIdx.y == 0) {
-            // the first row of tiles also publishes the saved / running statistics of ALL groups, in group order
-            float rm = e.running_mean != nullptr ? e.running_mean[n] : 0.f;
-            float rv = e.running_var != nullptr ? e.running_var[n] : 0.f;
-            for (int gg = 0; gg < groups; ++gg) {
-              const int cn_ = min(p.M, (gg + 1) * e.rows_per_group) - gg * e.rows_per_group;
-              const float iv = 1.f / static_cast<float>(cn_);
-              const float m2 = __ldcg(e.stat0 + static_cast<long long>(gg) * p.stat_group_stride + n) * iv;
-              const float v2 = fmaxf(__ldcg(e.stat1 + static_cast<long long>(gg) * p.stat_group_stride + n) * iv - m2 * m2, 0.f);
-              if (e.save_mean != nullptr) {
-                e.save_mean[static_cast<long long>(gg) * p.N + n] = m2;
-                e.save_rstd[static_cast<long long>(gg) * p.N + n] = rsqrtf(v2 + e.bn_eps);
-              }
-              const float unb = cn_ > 1 ? v2 * (static_cast<float>(cn_) / static_cast<float>(cn_ - 1)) : v2;
-              for (int u = 0; u < e.bn_updates; ++u) {
-                rm = (1.f - e.bn_momentum) * rm + e.bn_momentum * m2;
-                rv = (1.f - e.bn_momentum) * rv + e.bn_momentum * unb;
-              }
-            }
-            if (e.running_mean != nullptr) {
-              e.running_mean[n] = rm;
-              e.running_var[n] = rv;
-            }
-          }
-        }
-        s_co[c] = a_;
-        s_co[p.block_n + c] = b_;
-      }
-      __syncthreads();
-      // ---- (5) second row pass over the staged tile: Y = relu(a * round(acc + bias) + b)
-      {
-        const int r_begin = warp * 16;
-        const int rows_here = min(16, p.M - m0 - r_begin);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          const int col = ch * 128 + lane * 4;
-          const int cn = n0 + col;
-          int nv = 0;
-          if (col < p.block_n) nv = min(4, p.N - cn);
-          if (nv <= 0 || rows_here <= 0) continue;
-          const bool fast = (nv == 4) && (p.vec_ok != 0);
-          float ca[4], cb[4], bs[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            ca[i] = s_co[col + i];
-            cb[i] = s_co[p.block_n + col + i];
-            bs[i] = (e.bias != nullptr && i < nv) ? e.bias[cn + i] : 0.f;
-          }
-          uint32_t saddr = stage_addr + static_cast<uint32_t>(r_begin * ldst + col) * 4u;
-          CT* yrow = reinterpret_cast<CT*>(e.Y) + static_cast<long long>(m0 + r_begin) * e.ldc + cn;
-#pragma unroll 4
-          for (int r = 0; r < rows_here; ++r) {
-            float v[4];
-            ptx::lds128(saddr, v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float x = v[i] + bs[i];
-              if constexpr (sizeof(CT) == 2) x = __bfloat162float(__float2bfloat16_rn(x));  // what C holds
-              const float y = fmaf(ca[i], x, cb[i]);
-              v[i] = e.bn_relu ? fmaxf(y, 0.f) : y;
-            }
-            store4(yrow, fast, nv, v);
-            saddr += ldst * 4;
-            yrow += e.ldc;
-          }
-        }
-      }
-    }
-  }
-
   ptx::tc_fence_before();
   __syncthreads();
   if (kEpi == EPI_BCE && threadIdx.x < 4 && p.epi.loss != nullptr && s_loss[threadIdx.x] != 0.f)
@@ -1234,7 +892,7 @@ template <int kKind, int kEpi, int kGather = 0>
 int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmKParams& kp, dim3 grid, int dyn_smem,
                 cudaStream_t stream) {
   if (int rc = ensure_smem<kKind, kEpi, kGather>(dyn_smem)) return rc;
-  return launch_pdl(gemm_kernel<kKind, kEpi, kGather>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
+  return launch_kernel(gemm_kernel<kKind, kEpi, kGather>, grid, dim3(kGemmThreads), static_cast<size_t>(dyn_smem), stream, ta, tb, kp);
 }
 
 int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
@@ -1249,7 +907,7 @@ void set_gemm_debug_times(void* ptr, int epi_kind) {
   g_dbg_epi = epi_kind;
 }
 
-static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run);
+static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream);
 
 // ---- 3xTF32: operand split.  dst holds three copies of the [R, Cc] source - parts (p0, p1, p2), each the tf32-rounded
 // value (hi, round to nearest even on the 10-bit mantissa) or the exact remainder x - hi (lo) - side by side along the
@@ -1294,9 +952,8 @@ static int launch_split3(const void* src, long long ld, int major, long long row
 }
 
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
-  if (!g.x3) return launch_gemm_impl(g, stream, false);
-  MVAE_REQUIRE(g.kind == MVAE_F32 && g.gather.mode == 0 && !g.atf.enabled && !(g.epi.kind == EPI_STORE && g.epi.fuse_bn),
-               "gemm: 3xTF32 needs fp32 storage and a plain (non-gather, non-fused-BatchNorm) GEMM");
+  if (!g.x3) return launch_gemm_impl(g, stream);
+  MVAE_REQUIRE(g.kind == MVAE_F32 && g.gather.mode == 0, "gemm: 3xTF32 needs fp32 storage and a plain (non-gather) GEMM");
   MVAE_REQUIRE(g.x3_a != nullptr && g.x3_b != nullptr, "gemm: 3xTF32 needs the two split-operand scratch buffers");
   GemmDesc h = g;
   h.x3 = 0;
@@ -1318,13 +975,10 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     static const int part = env_int("MVAE_X3_SPLIT_ELEMS", 384);
     h.split_k = std::max(1, (h.K + part - 1) / part);
   }
-  return launch_gemm_impl(h, stream, false);
+  return launch_gemm_impl(h, stream);
 }
-bool gemm_bn_fusable(const GemmDesc& g) { return launch_gemm_impl(g, nullptr, true) == 0; }
 
-// rc 3: g.epi.fuse_bn was requested but the grid cannot be made co-resident (nothing launched; the caller falls back
-// to the separate BatchNorm kernel).
-static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run) {
+static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
   const int esz = g.kind == MVAE_F32 ? 4 : 2;
   const int BK = 128 / esz;
   MVAE_REQUIRE(g.kind == MVAE_F32 || g.kind == MVAE_BF16, "gemm: bad kind %d", g.kind);
@@ -1343,7 +997,6 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     MVAE_REQUIRE(cg.C > 0 && cg.C % 8 == 0 && cg.sn % 8 == 0 && cg.sh % 8 == 0 && cg.sw % 8 == 0,
                  "gemm: gather needs channels and strides that are multiples of 8 (16-byte chunks never straddle a tap)");
     MVAE_REQUIRE(cg.ksize > 0 && cg.stride > 0 && cg.Ho > 0 && cg.Wo > 0, "gemm: bad gather geometry");
-    MVAE_REQUIRE(!g.atf.enabled && !(e.kind == EPI_STORE && e.fuse_bn), "gemm: gather excludes the A transform / fused BatchNorm");
     MVAE_REQUIRE(e.kind == EPI_STORE || e.kind == EPI_ATOMIC, "gemm: gather supports the store / accumulate epilogues");
     MVAE_REQUIRE(static_cast<long long>(cg.Ho) * cg.Wo < 65536 && cg.H < 16384 && cg.W < 16384 && cg.pad < 4096,
                  "gemm: gather geometry too large for the packed coordinates");
@@ -1375,39 +1028,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   // ANOTHER CTA on the same SM - so shallow rings (2 stages) with 2-3 co-resident CTAs beat deep rings.
   const bool atomic = e.kind == EPI_ATOMIC;
   const int sms = 148;
-  const bool atf_on = g.atf.enabled != 0;
-  if (atf_on) {
-    MVAE_REQUIRE(!g.a_mn && e.kind != EPI_ATOMIC, "gemm: the A transform needs a K-major A and no split-K");
-    MVAE_REQUIRE(g.atf.sum && g.atf.sumsq && g.atf.gamma && g.atf.beta, "gemm: A-transform statistics missing");
-    MVAE_REQUIRE(g.atf.rows_per_group >= g.M || g.atf.rows_per_group % kBlockM == 0,
-                 "gemm: A-transform needs statistics groups aligned to %d rows", kBlockM);
-    MVAE_REQUIRE(g.lda == g.K && g.K % (16 / esz) == 0, "gemm: A-transform needs a dense A with K a multiple of %d", 16 / esz);
-  }
-  const int coef_bytes = atf_on ? 2 * kb_total * BK * 4 : 0;
-  const bool fuse = e.kind == EPI_STORE && e.fuse_bn != 0;
-  if (fuse) {
-    MVAE_REQUIRE(e.stat0 && e.stat1 && e.bn_gamma && e.bn_beta && e.Y && e.grid_barrier, "gemm: fused BatchNorm needs statistics buffers, gamma/beta, Y and a barrier counter");
-    MVAE_REQUIRE(e.c_dtype == g.kind, "gemm: fused BatchNorm writes the activation dtype");
-    MVAE_REQUIRE(!atf_on, "gemm: fused BatchNorm and the A transform are exclusive");
-    if (!(e.rows_per_group >= g.M || e.rows_per_group % kBlockM == 0)) return 3;
-  }
-  const bool want_direct_bce = e.kind == EPI_BCE && e.bce_direct != 0;
-  if (want_direct_bce) MVAE_REQUIRE(e.stat0 == nullptr, "gemm: the direct BCE epilogue produces no column sums (stat0 must be null)");
-  auto bnco_bytes = [&](int bn) -> int { return fuse ? 2 * bn * 4 : (want_direct_bce ? bn * 4 : 0); };
-  int sm_count = 148;
-  {
-    static int cached = 0;
-    if (cached == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || cached <= 0) cached = 148;
-    }
-    sm_count = cached;
-  }
   static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
   auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
   bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
-  if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz) && !(e.bce_direct != 0);
+  if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz);
   if (e.kind == EPI_DGRAD_BN) aux_ok = aux_ok && (e.ldh % 4 == 0) && al0(e.hpre, 4 * esz);
   auto aux_bytes = [&](int bn) -> int { return aux_ok ? kBlockM * bn * esz : 0; };
   static const int use_red = env_int("MVAE_GEMM_CTA_REDUCE", 1);
@@ -1438,7 +1062,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     while (stages > 1 && stages * stage_bytes + 1024 > max_dyn) --stages;
     int dyn = stages * stage_bytes;
     if (dyn < staging) dyn = staging;
-    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn) + coef_bytes + bnco_bytes(bn);
+    dyn = (dyn + 15) / 16 * 16 + aux_bytes(bn) + red_bytes(bn);
     dyn += 1024;
     split_o = split; stages_o = stages; dyn_o = dyn; bstage_o = b_stage; btx_o = b_tx;
     if (dyn > max_dyn + 1024) return 1e30;
@@ -1448,8 +1072,6 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
     if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
     if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
-    // the fused-BatchNorm grid barrier needs every CTA resident at once (256 threads x ~110 registers: at most 2 per SM)
-    if (fuse && ctas > static_cast<long long>(sm_count) * (occ > 2 ? 2 : occ)) return 1e30;
     const double slots = static_cast<double>(sms) * occ;
     const double waves = static_cast<double>((ctas + static_cast<long long>(slots) - 1) / static_cast<long long>(slots));
     // operand bytes streamed from L2 by all CTAs
@@ -1491,7 +1113,6 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
       }
     }
   }
-  if (fuse && (block_n <= 0 || plan_for(block_n, split, stages, dyn, b_stage, b_tx) >= 1e29)) return 3;
   MVAE_REQUIRE(block_n >= 16 && block_n <= 256 && block_n % 16 == 0, "gemm: block_n %d invalid", block_n);
   MVAE_REQUIRE(plan_for(block_n, split, stages, dyn, b_stage, b_tx) < 1e29, "gemm: tile %d does not fit in shared memory", block_n);
   const int tiles_n = ceil_div(g.N, block_n);
@@ -1541,20 +1162,12 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   {
     static const int use_direct = env_int("MVAE_GEMM_DIRECT_STORE", 1);
     const int cvec = e.c_dtype == MVAE_F32 ? 4 : 8;   // elements per 16-byte store
-    kp.direct_store = (use_direct != 0 && e.kind == EPI_STORE && e.stat0 == nullptr && !fuse && !atf_on &&
+    kp.direct_store = (use_direct != 0 && e.kind == EPI_STORE && e.stat0 == nullptr &&
                        e.ldc % cvec == 0 && al(e.C, 16)) ? 1 : 0;
   }
-  const int tail0 = dyn - 1024 - coef_bytes - bnco_bytes(block_n) - aux_bytes(block_n) - red_bytes(block_n);
+  const int tail0 = dyn - 1024 - aux_bytes(block_n) - red_bytes(block_n);
   kp.aux_off = (aux_ok && vec) ? tail0 : -1;
   kp.red_off = red_ok ? tail0 + aux_bytes(block_n) : -1;
-  kp.coef_off = atf_on ? tail0 + aux_bytes(block_n) + red_bytes(block_n) : -1;
-  kp.bnco_off = (fuse || want_direct_bce) ? tail0 + aux_bytes(block_n) + red_bytes(block_n) + coef_bytes : -1;
-  // 16-byte row runs: leading dimensions and bases must be 16-byte multiples, else the staged path runs (still without sums)
-  const bool bce_aligned = (e.ldc * esz) % 16 == 0 && (e.ldt * esz) % 16 == 0 && al(e.C, 16) && al(e.target, 16) && al(e.probs, 16);
-  kp.direct_bce = (want_direct_bce && bce_aligned) ? 1 : 0;
-  if (kp.direct_bce) kp.aux_off = -1;   // targets are read straight from global memory, one row run per thread
-  kp.grid_ctas = static_cast<unsigned int>(tiles_n) * tiles_m * split;
-  kp.atf = g.atf;
   kp.gather = cg;
   if (cg.mode >= 3) {
     kp.gather.mode = 1;  // inside the kernel: A is the gathered operand (instantiation kGather = 2 / 3)
@@ -1570,25 +1183,6 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream, bool dry_run
   MVAE_REQUIRE(e.rows_per_group > 0, "gemm: rows_per_group must be positive");
 
   dim3 grid(tiles_n, tiles_m, cg.mode == 4 ? cg.sc_stride * cg.sc_stride : split);  // mode 4: z = parity class (split is 1)
-  if (fuse) {
-    // authoritative co-residency check with the real register / shared-memory footprint of the kernel
-    int occ = 0;
-    if (g.kind == MVAE_F32) {
-      if (int rc = ensure_smem<MVAE_F32, EPI_STORE>(dyn)) return rc;
-      MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_kernel<MVAE_F32, EPI_STORE>, kGemmThreads, dyn));
-    } else {
-      if (int rc = ensure_smem<MVAE_BF16, EPI_STORE>(dyn)) return rc;
-      MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemm_kernel<MVAE_BF16, EPI_STORE>, kGemmThreads, dyn));
-    }
-    int tmem_cols = 32;
-    while (tmem_cols < block_n) tmem_cols <<= 1;
-    if (env_int("MVAE_GEMM_VERBOSE", 0))
-      fprintf(stderr, "[mvae gemm] fused BatchNorm: occupancy %d (tmem limit %d), %u CTAs, %d SMs\n", occ, 512 / tmem_cols,
-              kp.grid_ctas, sm_count);
-    if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
-    if (static_cast<long long>(kp.grid_ctas) > static_cast<long long>(occ) * sm_count) return 3;
-  }
-  if (dry_run) return 0;
   if (cg.mode == 3) return launch_inst<MVAE_BF16, EPI_STORE, 2>(ta, tb, kp, grid, dyn, stream);
   if (cg.mode == 4) return launch_inst<MVAE_BF16, EPI_STORE, 3>(ta, tb, kp, grid, dyn, stream);
   if (cg.mode != 0) {  // bf16 store / accumulate only (validated above)

@@ -200,16 +200,6 @@ struct Ptrs {
   }
 };
 
-// BatchNorm(+ReLU) applied by the producing GEMM itself (gemm.cu, fuse_bn): what launch_bn_forward would be given.
-struct FusedBn {
-  void* Y = nullptr;
-  const float* gamma = nullptr; const float* beta = nullptr;
-  float* save_mean = nullptr; float* save_rstd = nullptr;
-  float* running_mean = nullptr; float* running_var = nullptr;
-  int updates = 1; float momentum = 0.1f, eps = 1e-5f;
-  unsigned int* barrier = nullptr;
-};
-
 // 3xTF32 mode of the current mvae_mnist_step call (set at its start; the helpers below stamp it on every GEMM)
 struct X3Scratch {
   void* a = nullptr;
@@ -224,33 +214,9 @@ void stamp_x3(GemmDesc& g) {
   }
 }
 
-GemmDesc fwd_desc(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
-                  float* st_sum, float* st_sumsq, int rows_per_group, const FusedBn* fb) {
-  GemmDesc g;
-  g.kind = dtype; g.M = M; g.N = N; g.K = K;
-  g.A = A; g.lda = K; g.a_mn = 0;
-  g.B = W; g.ldb = K; g.b_mn = 0;
-  g.epi.kind = EPI_STORE;
-  g.epi.C = C; g.epi.ldc = N; g.epi.c_dtype = c_dtype;
-  g.epi.bias = bias;
-  g.epi.stat0 = st_sum; g.epi.stat1 = st_sumsq;
-  g.epi.rows_per_group = rows_per_group;
-  if (fb != nullptr) {
-    g.epi.fuse_bn = 1;
-    g.epi.Y = fb->Y;
-    g.epi.bn_gamma = fb->gamma; g.epi.bn_beta = fb->beta;
-    g.epi.save_mean = fb->save_mean; g.epi.save_rstd = fb->save_rstd;
-    g.epi.running_mean = fb->running_mean; g.epi.running_var = fb->running_var;
-    g.epi.bn_updates = fb->updates; g.epi.bn_momentum = fb->momentum; g.epi.bn_eps = fb->eps; g.epi.bn_relu = 1;
-    g.epi.grid_barrier = fb->barrier;
-  }
-  return g;
-}
-
 int gemm_fwd(int dtype, int M, int N, int K, const void* A, const void* W, void* C, int c_dtype, const float* bias,
-             float* st_sum, float* st_sumsq, int rows_per_group, cudaStream_t st, const GemmATransform* atf = nullptr) {
+             float* st_sum, float* st_sumsq, int rows_per_group, cudaStream_t st) {
   GemmDesc g;
-  if (atf != nullptr) g.atf = *atf;
   g.kind = dtype; g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = K; g.a_mn = 0;
   g.B = W; g.ldb = K; g.b_mn = 0;
@@ -511,27 +477,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (dep(st, s3)) return 1;  // fork: the per-label text encoder runs beside the image encoder
   if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s3), "launch_textenc_forward");
 
-  // BatchNorm+ReLU between two Linears is folded into the CONSUMING GEMM's A-operand path (gemm.cu, A transform)
-  // when the statistics groups are tile-aligned; the separate apply kernel remains for ragged batches and eval.
-  static const int fuse_env = env_int("MVAE_FUSE_BN", 0);  // measured slower: every N tile redoes the transform
-  const bool fuse_enc = fuse_env != 0 && training;
-  static const int epi_fuse_env = env_int("MVAE_FUSE_BN_EPI", 0);  // producer-side fusion (grid barrier in the GEMM epilogue): measured +-0
-  const bool epi_fuse = epi_fuse_env != 0 && training && !fuse_enc;
-  const bool fuse_dec = fuse_enc && (G == 1 || B % 128 == 0);
-  auto make_atf = [&](float* sums, int F, int groups, int rpg, int nupd, const char* bn, float* sv, void* out) {
-    GemmATransform t;
-    t.enabled = 1;
-    t.sum = sums; t.sumsq = sums + groups * F;
-    char nm[96];
-    snprintf(nm, sizeof(nm), "%s.weight", bn); t.gamma = pf(nm);
-    snprintf(nm, sizeof(nm), "%s.bias", bn); t.beta = pf(nm);
-    snprintf(nm, sizeof(nm), "%s.running_mean", bn); t.running_mean = bf(nm);
-    snprintf(nm, sizeof(nm), "%s.running_var", bn); t.running_var = bf(nm);
-    t.rows_per_group = rpg; t.eps = bn_eps; t.momentum = mom; t.updates_per_group = nupd;
-    t.save_mean = sv; t.save_rstd = sv + groups * F;
-    t.out = out;
-    return t;
-  };
   unsigned int* chain_err = bars + 31;
   auto wb = [&](const char* name) -> const __nv_bfloat16* { return static_cast<const __nv_bfloat16*>(a->params_bf16) + L.find(name); };
   if (n_img > 0 && use_chain && fwd) {
@@ -553,44 +498,22 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     MVAE_STEP(launch_chain_enc_fwd(ce, st), "chain_enc_fwd");
   }
   if (n_img > 0 && !use_chain) {
-    // ImageEncoder (mnist/model.py:99-117), once for all terms that use it
-    // BatchNorm+ReLU applied by the producing GEMM (grid barrier + second pass over the on-chip tile) when the whole
-    // grid is co-resident; otherwise the GEMM publishes the sums and launch_bn_forward applies them.
-    FusedBn fb_e1;
-    fb_e1.Y = W.at<void>(P.h1); fb_e1.gamma = pf("image_encoder.net.1.weight"); fb_e1.beta = pf("image_encoder.net.1.bias");
-    fb_e1.save_mean = sv_e1; fb_e1.save_rstd = sv_e1 + 400;
-    fb_e1.running_mean = bf("image_encoder.net.1.running_mean"); fb_e1.running_var = bf("image_encoder.net.1.running_var");
-    fb_e1.updates = n_img; fb_e1.momentum = mom; fb_e1.eps = bn_eps; fb_e1.barrier = bars + 0;
-    const GemmDesc gd_e1 = fwd_desc(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
-                                    pf("image_encoder.net.0.bias"), st_e1, st_e1 + 400, 1 << 30, &fb_e1);
-    const bool fz_e1 = epi_fuse && gemm_bn_fusable(gd_e1);
-    if (fwd && fz_e1) MVAE_STEP(launch_gemm(gd_e1, st), "gemm_fwd_bn:image_encoder.net.0.weight#3");
-    if (fwd && !fz_e1) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
+    // ImageEncoder (mnist/model.py:99-117), once for all terms that use it: every Linear publishes its column sums from
+    // the GEMM epilogue, launch_bn_forward applies BatchNorm + ReLU
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 400, 784, a->image, wop("image_encoder.net.0.weight"), W.at<void>(P.h1pre), dt,
                  pf("image_encoder.net.0.bias"), training ? st_e1 : nullptr, training ? st_e1 + 400 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.0.weight#3");
-    const GemmATransform atf_e1 = make_atf(st_e1, 400, 1, 1 << 30, n_img, "image_encoder.net.1", sv_e1, W.at<void>(P.h1));
-    if (fwd && !fuse_enc && !fz_e1) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
+    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h1pre), W.at<void>(P.h1), B, 400, B, training ? st_e1 : nullptr, st_e1 + 400,
                           pf("image_encoder.net.1.weight"), pf("image_encoder.net.1.bias"), sv_e1, sv_e1 + 400,
                           bf("image_encoder.net.1.running_mean"), bf("image_encoder.net.1.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.1.weight#4");
-    FusedBn fb_e2;
-    fb_e2.Y = W.at<void>(P.h2); fb_e2.gamma = pf("image_encoder.net.4.weight"); fb_e2.beta = pf("image_encoder.net.4.bias");
-    fb_e2.save_mean = sv_e2; fb_e2.save_rstd = sv_e2 + 200;
-    fb_e2.running_mean = bf("image_encoder.net.4.running_mean"); fb_e2.running_var = bf("image_encoder.net.4.running_var");
-    fb_e2.updates = n_img; fb_e2.momentum = mom; fb_e2.eps = bn_eps; fb_e2.barrier = bars + 2;
-    const GemmDesc gd_e2 = fwd_desc(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
-                                    pf("image_encoder.net.3.bias"), st_e2, st_e2 + 200, 1 << 30, &fb_e2);
-    const bool fz_e2 = epi_fuse && gemm_bn_fusable(gd_e2);
-    if (fwd && fz_e2) MVAE_STEP(launch_gemm(gd_e2, st), "gemm_fwd_bn:image_encoder.net.3.weight#5");
-    if (fwd && !fz_e2) MVAE_STEP(gemm_fwd(dt, B, 200, 400, fuse_enc ? W.at<void>(P.h1pre) : W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
-                 pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st,
-                 fuse_enc ? &atf_e1 : nullptr), "gemm_fwd:image_encoder.net.3.weight#5");
-    const GemmATransform atf_e2 = make_atf(st_e2, 200, 1, 1 << 30, n_img, "image_encoder.net.4", sv_e2, W.at<void>(P.h2));
-    if (fwd && !fuse_enc && !fz_e2) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 200, 400, W.at<void>(P.h1), wop("image_encoder.net.3.weight"), W.at<void>(P.h2pre), dt,
+                 pf("image_encoder.net.3.bias"), training ? st_e2 : nullptr, training ? st_e2 + 200 : nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.3.weight#5");
+    if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.h2pre), W.at<void>(P.h2), B, 200, B, training ? st_e2 : nullptr, st_e2 + 200,
                           pf("image_encoder.net.4.weight"), pf("image_encoder.net.4.bias"), sv_e2, sv_e2 + 200,
                           bf("image_encoder.net.4.running_mean"), bf("image_encoder.net.4.running_var"), n_img, mom,
                           bn_eps, 1, st), "launch_bn_forward:image_encoder.net.4.weight#6");
-    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, fuse_enc ? W.at<void>(P.h2pre) : W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
-                 pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st, fuse_enc ? &atf_e2 : nullptr), "gemm_fwd:image_encoder.net.6.weight#7");
+    if (fwd) MVAE_STEP(gemm_fwd(dt, B, 2 * n, 200, W.at<void>(P.h2), wop("image_encoder.net.6.weight"), W.at<void>(P.enc), MVAE_F32,
+                 pf("image_encoder.net.6.bias"), nullptr, nullptr, 1 << 30, st), "gemm_fwd:image_encoder.net.6.weight#7");
   }
   if (dep(s3, st)) return 1;  // join: the tail needs both experts
   TailArgs ta;
@@ -629,7 +552,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   if (dep(st, s3)) return 1;  // fork: text decoder beside the image decoder
   if (fwd) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
 
-  bool bce_direct = false;
   if (use_chain && fwd) {
     ChainDecFwd cd;
     cd.B = B; cd.n = n; cd.G = G;
@@ -655,36 +577,15 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   }
   if (!use_chain) {
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
-  FusedBn fb_d1;
-  fb_d1.Y = W.at<void>(P.g1); fb_d1.gamma = pf("image_decoder.net.1.weight"); fb_d1.beta = pf("image_decoder.net.1.bias");
-  fb_d1.save_mean = sv_d1; fb_d1.save_rstd = sv_d1 + G * 200;
-  fb_d1.running_mean = bf("image_decoder.net.1.running_mean"); fb_d1.running_var = bf("image_decoder.net.1.running_var");
-  fb_d1.updates = 1; fb_d1.momentum = mom; fb_d1.eps = bn_eps; fb_d1.barrier = bars + 4;
-  const GemmDesc gd_d1 = fwd_desc(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
-                                  pf("image_decoder.net.0.bias"), st_d1, st_d1 + G * 200, B, &fb_d1);
-  const bool fz_d1 = epi_fuse && gemm_bn_fusable(gd_d1);
-  if (fwd && fz_d1) MVAE_STEP(launch_gemm(gd_d1, st), "gemm_fwd_bn:image_decoder.net.0.weight#9");
-  if (fwd && !fz_d1) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
+  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
                pf("image_decoder.net.0.bias"), training ? st_d1 : nullptr, training ? st_d1 + G * 200 : nullptr, B, st), "gemm_fwd:image_decoder.net.0.weight#9");
-  const GemmATransform atf_d1 = make_atf(st_d1, 200, G, B, 1, "image_decoder.net.1", sv_d1, W.at<void>(P.g1));
-  if (fwd && !fuse_dec && !fz_d1) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
+  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g1pre), W.at<void>(P.g1), R, 200, B, training ? st_d1 : nullptr, st_d1 + G * 200,
                         pf("image_decoder.net.1.weight"), pf("image_decoder.net.1.bias"), sv_d1, sv_d1 + G * 200,
                         bf("image_decoder.net.1.running_mean"), bf("image_decoder.net.1.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.1.weight#10");
-  FusedBn fb_d2;
-  fb_d2.Y = W.at<void>(P.g2); fb_d2.gamma = pf("image_decoder.net.4.weight"); fb_d2.beta = pf("image_decoder.net.4.bias");
-  fb_d2.save_mean = sv_d2; fb_d2.save_rstd = sv_d2 + G * 400;
-  fb_d2.running_mean = bf("image_decoder.net.4.running_mean"); fb_d2.running_var = bf("image_decoder.net.4.running_var");
-  fb_d2.updates = 1; fb_d2.momentum = mom; fb_d2.eps = bn_eps; fb_d2.barrier = bars + 6;
-  const GemmDesc gd_d2 = fwd_desc(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
-                                  pf("image_decoder.net.3.bias"), st_d2, st_d2 + G * 400, B, &fb_d2);
-  const bool fz_d2 = epi_fuse && gemm_bn_fusable(gd_d2);
-  if (fwd && fz_d2) MVAE_STEP(launch_gemm(gd_d2, st), "gemm_fwd_bn:image_decoder.net.3.weight#11");
-  if (fwd && !fz_d2) MVAE_STEP(gemm_fwd(dt, R, 400, 200, fuse_dec ? W.at<void>(P.g1pre) : W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
-               pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st,
-               fuse_dec ? &atf_d1 : nullptr), "gemm_fwd:image_decoder.net.3.weight#11");
-  const GemmATransform atf_d2 = make_atf(st_d2, 400, G, B, 1, "image_decoder.net.4", sv_d2, W.at<void>(P.g2));
-  if (fwd && !fuse_dec && !fz_d2) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
+  if (fwd) MVAE_STEP(gemm_fwd(dt, R, 400, 200, W.at<void>(P.g1), wop("image_decoder.net.3.weight"), W.at<void>(P.g2pre), dt,
+               pf("image_decoder.net.3.bias"), training ? st_d2 : nullptr, training ? st_d2 + G * 400 : nullptr, B, st), "gemm_fwd:image_decoder.net.3.weight#11");
+  if (fwd) MVAE_STEP(launch_bn_forward(dt, W.at<void>(P.g2pre), W.at<void>(P.g2), R, 400, B, training ? st_d2 : nullptr, st_d2 + G * 400,
                         pf("image_decoder.net.4.weight"), pf("image_decoder.net.4.bias"), sv_d2, sv_d2 + G * 400,
                         bf("image_decoder.net.4.running_mean"), bf("image_decoder.net.4.running_var"), 1, mom, bn_eps,
                         1, st), "launch_bn_forward:image_decoder.net.4.weight#12");
@@ -692,18 +593,12 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     // last Linear + sigmoid + BCE (mnist/model.py:130,135 + mnist/train.py:70) in one kernel
     GemmDesc g;
     g.kind = dt; g.M = R; g.N = 784; g.K = 400;
-    g.A = fuse_dec ? W.at<void>(P.g2pre) : W.at<void>(P.g2); g.lda = 400; g.a_mn = 0;
-    if (fuse_dec) g.atf = atf_d2;
+    g.A = W.at<void>(P.g2); g.lda = 400; g.a_mn = 0;
     g.B = wop("image_decoder.net.6.weight"); g.ldb = 400; g.b_mn = 0;
     g.epi.kind = EPI_BCE;
     g.epi.C = W.at<void>(P.dlog); g.epi.ldc = 784; g.epi.c_dtype = dt;
     g.epi.bias = pf("image_decoder.net.6.bias");
-    // row-per-thread BCE epilogue (no column sums): the last Linear's bias gradient is then one column reduction over
-    // dlogits on the side stream, off the critical path
-    static const int bce_direct_env = env_int("MVAE_GEMM_DIRECT_BCE", 0);  // measured: kernel 51.1 -> 48.0 us, step 358 -> 396 us
-    bce_direct = bce_direct_env != 0 && !fuse_dec;
-    g.epi.bce_direct = bce_direct ? 1 : 0;
-    g.epi.stat0 = (bwd && !bce_direct) ? gf("image_decoder.net.6.bias") : nullptr;
+    g.epi.stat0 = bwd ? gf("image_decoder.net.6.bias") : nullptr;
     g.epi.rows_per_group = B;
     g.epi.target = a->image; g.epi.ldt = 784; g.epi.target_rows = B;
     for (int t = 0; t < G; ++t) g.epi.bce_scale[t] = a->lambda_image[t] / (static_cast<float>(B) * 784.f);
@@ -722,8 +617,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     MVAE_STEP(launch_loss_pack(losses, a->out_losses, G, s3), "launch_loss_pack#32");
     losses_packed = true;
   }
-  if (fwd && bwd && bwd_dec && !module_bwd && bce_direct)
-    if (mvae_col_stats(dt, W.at<void>(P.dlog), R, 784, 784, 0, gf("image_decoder.net.6.bias"), nullptr, s2)) return 1;
   // ================================================================ backward
   if (bwd && bwd_dec) {
     if (module_bwd) {

@@ -49,7 +49,6 @@ __device__ __forceinline__ void store_pair(T* p, float a, float b) {
 // One warp per (term, sample): lanes own latent pairs.
 template <typename ZT>
 __global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArgs a) {
-  pdl_enter();
   __shared__ float s_stat[kMaxGroups][2][kTD];
   __shared__ float s_kl[kMaxGroups];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,7 +155,6 @@ __global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArg
 constexpr int kBwdRows = 4;
 template <typename ZT>
 __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel(const TailArgs a, int smem_floats) {
-  pdl_enter();
   extern __shared__ float sm[];
   // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] |
   //         image-expert combine [rows][G][2n] | text-expert combine [rows][G][2n] | labels [rows]
@@ -375,7 +373,6 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
 constexpr int kBwd2Warps = 8;
 template <typename ZT>
 __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const TailArgs a) {
-  pdl_enter();
   extern __shared__ float sm[];
   const int n = a.n, two_n = 2 * a.n, G = a.G;
   // layout: per-warp text-expert tables [warps][10][2n] | Wt1 [10][n] | t1 coefficients [G][4][10] | d_wt1 [10][n] | d_enc_bias [2n]
@@ -563,7 +560,6 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
 // One thread per decoder row.  Forward + (optionally) the fused NLL loss and the backward down to the
 // BatchNorm output: dyhat, its two per-group column sums, and the gradients of the second Linear.
 __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
-  pdl_enter();
   __shared__ float s_mean[kMaxGroups][kTD], s_rstd[kMaxGroups][kTD];
   __shared__ float s_w2[kTD][kTD], s_b2[kTD], s_gamma[kTD], s_beta[kTD];
   __shared__ float s_dw2[kTD][kTD], s_db2[kTD], s_s0[kMaxGroups][kTD], s_s1[kMaxGroups][kTD], s_ce[kMaxGroups];
@@ -736,7 +732,6 @@ __global__ void __launch_bounds__(256) textdec_kernel(const TextDecArgs a) {
 // kernel gathers from.  Single block.
 constexpr int kEmb = 50;
 __global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
-  pdl_enter();
   __shared__ float s_cnt[kTD];
   __shared__ float s_h[kTD][kEmb];
   float* sv_cnt = a.save;
@@ -817,7 +812,6 @@ __global__ void __launch_bounds__(256) textenc_fwd_kernel(const TextEncArgs a) {
 // chains of dependent global loads (42 -> a few us; single block, off the critical path on a side stream).
 constexpr int kTextMaxOut = 128;   // shared-memory staging covers 2n <= 128; wider latents read global memory
 __global__ void __launch_bounds__(256) textenc_bwd_kernel(const TextEncArgs a) {
-  pdl_enter();
   __shared__ float s_dh[kTD][kEmb];
   __shared__ float s_dt[kTD][kTextMaxOut];
   __shared__ float s_w[kTextMaxOut][kEmb + 1];
@@ -985,8 +979,8 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
   const long long items = static_cast<long long>(a.G) * a.B;
   int blocks = static_cast<int>(std::min<long long>((items + kTailWarps - 1) / kTailWarps, 148 * 8));
   if (blocks < 1) blocks = 1;
-  if (a.z_dtype == MVAE_F32) return launch_pdl(tail_fwd_kernel<float>, dim3(blocks), dim3(kTailThreads), 0, st, a);
-  return launch_pdl(tail_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(kTailThreads), 0, st, a);
+  if (a.z_dtype == MVAE_F32) return launch_kernel(tail_fwd_kernel<float>, dim3(blocks), dim3(kTailThreads), 0, st, a);
+  return launch_kernel(tail_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(kTailThreads), 0, st, a);
 }
 
 int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
@@ -1002,8 +996,8 @@ int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
     }
     int blocks2 = std::min((a.B + kBwd2Warps - 1) / kBwd2Warps, 148 * 2);
     if (blocks2 < 1) blocks2 = 1;
-    if (a.z_dtype == MVAE_F32) return launch_pdl(tail_bwd2_kernel<float>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
-    return launch_pdl(tail_bwd2_kernel<__nv_bfloat16>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
+    if (a.z_dtype == MVAE_F32) return launch_kernel(tail_bwd2_kernel<float>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
+    return launch_kernel(tail_bwd2_kernel<__nv_bfloat16>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
   }
   const int smem_floats = kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD +
                           2 * kBwdRows * kMaxGroups * 2 * a.n + kBwdRows;
@@ -1013,8 +1007,8 @@ int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
   int blocks = std::min(row_blocks, 148 * 2);
   const int threads = 32 * a.G * kBwdRows;
   if (a.z_dtype == MVAE_F32)
-    return launch_pdl(tail_bwd_kernel<float>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
-  return launch_pdl(tail_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
+    return launch_kernel(tail_bwd_kernel<float>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
+  return launch_kernel(tail_bwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), smem, st, a, smem_floats);
 }
 
 int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
@@ -1028,19 +1022,19 @@ int launch_textdec(const TextDecArgs& a, cudaStream_t st) {
   }
   const long long rows = static_cast<long long>(a.G) * a.B;
   const int blocks = static_cast<int>((rows + 255) / 256);
-  return launch_pdl(textdec_kernel, dim3(blocks), dim3(256), 0, st, a);
+  return launch_kernel(textdec_kernel, dim3(blocks), dim3(256), 0, st, a);
 }
 
 int launch_textenc_forward(const TextEncArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.B > 0 && a.n > 0 && a.labels && a.emb && a.gamma && a.beta && a.w && a.b && a.table && a.save,
                "textenc_forward: missing arguments");
-  return launch_pdl(textenc_fwd_kernel, dim3(1), dim3(256), 0, st, a);
+  return launch_kernel(textenc_fwd_kernel, dim3(1), dim3(256), 0, st, a);
 }
 
 int launch_textenc_backward(const TextEncArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.d_table && a.d_emb && a.d_gamma && a.d_beta && a.d_w && a.d_b && a.save && a.w && a.gamma,
                "textenc_backward: missing arguments");
-  return launch_pdl(textenc_bwd_kernel, dim3(1), dim3(256), 0, st, a);
+  return launch_kernel(textenc_bwd_kernel, dim3(1), dim3(256), 0, st, a);
 }
 
 int launch_poe_forward(int mode, int prior, float eps, int M, long long B, int D, const float* mu, const float* logvar,
