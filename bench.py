@@ -304,7 +304,19 @@ def other_configs(torch, dev, log):
         ms = timed(weak, 24, 60)
         out["mnist_weak_0.5_0.5_b4096"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "precision": "bf16",
                                            "rule": "mnist/modal_weak.py:60-97, per-batch flips from np.random.seed(42)"}
-        del m, tr, xs32, xs16
+        del m, tr, xs16
+        # north-star MLP instantiation (policy 3: "second benchmark row"): Linear+Swish 784-512-512-2n, no
+        # normalisation, precision PoE with the prior expert; per-layer tcgen05 GEMMs with bias / Swish / sigmoid-BCE epilogues
+        from mvae_b200.mlp import MVAE as SwishMVAE, MVAETrainer as SwishTrainer
+        ms_model = SwishMVAE(N_LATENTS, hidden=512, precision="bf16", device=dev, seed=1)
+        ms_tr = SwishTrainer(ms_model, use_cuda_graph=True)
+        ms = timed(lambda i: ms_tr.step(xs32[i % slots], ys[i % slots]), 5, 40)
+        flops = 6.0 * sum(o * i * r for o, i, r in ms_model.linear_shapes(3, 2)) * B
+        out["mnist_swish_mlp_512_b4096"] = {"ms_per_step": ms, "samples_per_s": B / (ms * 1e-3), "precision": "bf16",
+                                            "model": "784-512-512-2n Linear+Swish, PRECISION PoE + prior expert, n_latents=64",
+                                            "gpu_launches_per_step": ms_tr.last_graph_launches,
+                                            "gemm_tflops": flops / (ms * 1e-3) / 1e12}
+        del ms_model, ms_tr, xs32
     except Exception as exc:
         out["mnist_error"] = repr(exc)[:300]
     for name in ("celeba", "multimnist"):

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MVAE_ABI_VERSION 4
+#define MVAE_ABI_VERSION 5
 
 #define MVAE_DT_F32 0
 #define MVAE_DT_BF16 1
@@ -72,6 +72,25 @@ typedef struct mvae_gemm_args {
   void* debug_times;  /* NULL, or device int64 [ctas][8] receiving %globaltimer stamps (bring-up only) */
   void* x3_scratch;   /* MVAE_DT_F32X3 only: device scratch for the split operands, >= 12 * (M + N + 8) * (K + 4) bytes */
   int64_t x3_scratch_bytes;
+  /* Activation fused into the epilogue (ABI 5; the north-star's Linear+Swish stacks).  act = MVAE_ACT_SWISH with
+   *   act_out != NULL: C = A B^T + bias (the pre-activation, kept for the backward; C may be NULL) and
+   *                    act_out = swish(C), same dtype / leading dimension as C            (forward of Linear + Swish)
+   *   act_pre != NULL: C = (A B^T) * swish'(act_pre) and col_sum[n] += sum_m C[m, n]      (input gradient arriving at the
+   *                    previous Linear's pre-activation act_pre [M, N], dtype of A; col_sum = that Linear's bias gradient)
+   * act = MVAE_ACT_NONE (0): plain GEMM as above. */
+  int act;
+  void* act_out;
+  const void* act_pre; int64_t ld_act_pre;
+  /* sigmoid + binary cross entropy fused into the epilogue (ABI 5; mnist/model.py:135 + mnist/train.py:70 - the logits never
+   * reach memory).  bce_target != NULL ([bce_target_rows, N], dtype of A; row m compares with bce_target[m % bce_target_rows]):
+   *   x = A B^T + bias;  bce_loss[g] += bce_scale[g] * sum over the rows of group g = m / rows_per_group (<= 4 groups) of
+   *   softplus(x) - t x  (= BCE(sigmoid(x), t));
+   *   C = bce_scale[g] * (sigmoid(x) - t)  (the gradient at the logits);  col_sum[n] += sum_m C[m, n]  (one group: the bias
+   *   gradient);  bce_probs (optional, layout / dtype of C) = sigmoid(x). */
+  const void* bce_target; int64_t ld_bce_target; int bce_target_rows;
+  float bce_scale[4];
+  float* bce_loss;
+  void* bce_probs;
 } mvae_gemm_args;
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
 /* Bring-up: GEMM launches whose epilogue kind (0 store, 1 atomic, 2 BCE, 3 dgrad-BN) equals epilogue_kind write

@@ -32,6 +32,9 @@ class GemmArgs(C.Structure):
         ("block_n", c_int), ("split_k", c_int), ("stages", c_int),
         ("debug_times", c_void_p),
         ("x3_scratch", c_void_p), ("x3_scratch_bytes", c_int64),
+        ("act", c_int), ("act_out", c_void_p), ("act_pre", c_void_p), ("ld_act_pre", c_int64),
+        ("bce_target", c_void_p), ("ld_bce_target", c_int64), ("bce_target_rows", c_int), ("bce_scale", c_float * 4),
+        ("bce_loss", c_void_p), ("bce_probs", c_void_p),
     ]
 
 

@@ -23,10 +23,13 @@ def _p(t: Optional[torch.Tensor]):
 
 
 def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, accumulate=False, col_sum=None,
-         col_sumsq=None, rows_per_group=0, patch=None, split_k=0, block_n=0, stages=0):
+         col_sumsq=None, rows_per_group=0, patch=None, split_k=0, block_n=0, stages=0, act=0, act_out=None, act_pre=None,
+         ld_act_pre=0, bce=None):
     """Cout[M,N] (+)= A[M,K] * B[N,K]^T (+ bias).  A and B share one storage dtype (bf16 -> kind::f16, fp32 -> tf32).
     `patch=(geometry, operand)`: implicit GEMM - operand 1: A is the channels-last image whose patch matrix is the real A
-    (lda ignored); operand 2: likewise for B (b_major must be 1).  See mvae_conv_gemm."""
+    (lda ignored); operand 2: likewise for B (b_major must be 1).  See mvae_conv_gemm.
+    `act` (ACT_SWISH) fuses the activation into the epilogue: with `act_out` the forward (Cout = pre-activation or None,
+    act_out = swish(pre)); with `act_pre` the backward (Cout = (A B^T) * swish'(act_pre), col_sum += its column sums)."""
     if A.dtype != B.dtype:
         raise TypeError("gemm operands differ in dtype: %s vs %s" % (A.dtype, B.dtype))
     a = _lib.GemmArgs()
@@ -34,7 +37,14 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, ac
     a.M, a.N, a.K = int(M), int(N), int(K)
     a.A, a.lda, a.a_major = A.data_ptr(), int(lda), int(a_major)
     a.B, a.ldb, a.b_major = B.data_ptr(), int(ldb), int(b_major)
-    a.C, a.ldc, a.c_dtype = Cout.data_ptr(), int(ldc), DT[Cout.dtype]
+    cref = Cout if Cout is not None else act_out
+    a.C, a.ldc, a.c_dtype = _p(Cout), int(ldc), DT[cref.dtype]
+    a.act, a.act_out, a.act_pre, a.ld_act_pre = int(act), _p(act_out), _p(act_pre), int(ld_act_pre)
+    if bce is not None:   # dict(target, ld_target, target_rows, scale=[per group], loss, probs=None): see mvae_gemm_args
+        a.bce_target, a.ld_bce_target, a.bce_target_rows = bce["target"].data_ptr(), int(bce["ld_target"]), int(bce["target_rows"])
+        for i, v in enumerate(bce["scale"]):
+            a.bce_scale[i] = float(v)
+        a.bce_loss, a.bce_probs = _p(bce.get("loss")), _p(bce.get("probs"))
     a.bias = _p(bias)
     a.accumulate = 1 if accumulate else 0
     a.col_sum, a.col_sumsq = _p(col_sum), _p(col_sumsq)

@@ -702,7 +702,8 @@ class ConvMVAETrainer:
     def _enqueue(self, ws, image, other, term_types, lambdas, eps, adam: bool) -> None:
         m = self.model
         B = ws.B
-        _ops.step_begin(m._step_counter, ws.acc.view(-1), m.flat_nbt, self._increments(term_types))
+        # everything that accumulates over the step is zeroed here: the loss sums (ws.acc) or a workspace-defined region around them
+        _ops.step_begin(m._step_counter, getattr(ws, "zero_region", ws.acc.view(-1)), m.flat_nbt, self._increments(term_types))
         klw = [self.kl_lambda / B] * len(term_types)
         m.run_forward(ws, image, other, term_types, eps, True, lambdas, klw, False, True)
         m.backward_decoders(ws)

@@ -199,6 +199,32 @@ static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int
   g.epi.stat0 = a->col_sum; g.epi.stat1 = a->col_sumsq;
   g.epi.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : (1 << 30);
   g.dbg = reinterpret_cast<long long*>(a->debug_times);
+  if (a->act != MVAE_ACT_NONE) {
+    MVAE_REQUIRE(a->act == MVAE_ACT_SWISH && !a->accumulate && cg == nullptr, "mvae_gemm: fused activation = Swish on a plain, non-accumulating GEMM");
+    MVAE_REQUIRE((a->act_out != nullptr) != (a->act_pre != nullptr), "mvae_gemm: fused activation needs exactly one of act_out / act_pre");
+    if (a->act_out != nullptr) {
+      MVAE_REQUIRE(a->col_sum == nullptr && a->col_sumsq == nullptr, "mvae_gemm: no column statistics with a fused forward activation");
+      g.epi.kind = EPI_STORE_ACT;
+      g.epi.probs = a->act_out;
+    } else {
+      MVAE_REQUIRE(a->bias == nullptr && a->col_sumsq == nullptr, "mvae_gemm: activation backward takes no bias / col_sumsq");
+      g.epi.kind = EPI_DGRAD_ACT;
+      g.epi.hpre = a->act_pre;
+      g.epi.ldh = a->ld_act_pre;
+      g.epi.rows_per_group = 1 << 30;
+    }
+  }
+  if (a->bce_target != nullptr) {
+    MVAE_REQUIRE(a->act == MVAE_ACT_NONE && !a->accumulate && cg == nullptr && a->col_sumsq == nullptr,
+                 "mvae_gemm: the BCE epilogue needs a plain, non-accumulating GEMM without activation / col_sumsq");
+    MVAE_REQUIRE(a->bce_target_rows > 0 && a->rows_per_group > 0 && (a->M + a->rows_per_group - 1) / a->rows_per_group <= 4,
+                 "mvae_gemm: the BCE epilogue needs target rows and at most 4 row groups");
+    g.epi.kind = EPI_BCE;
+    g.epi.target = a->bce_target; g.epi.ldt = a->ld_bce_target; g.epi.target_rows = a->bce_target_rows;
+    for (int t = 0; t < 4; ++t) g.epi.bce_scale[t] = a->bce_scale[t];
+    g.epi.loss = a->bce_loss;
+    g.epi.probs = a->bce_probs;
+  }
   note_launch(1);
   return launch_gemm(g, static_cast<cudaStream_t>(stream));
 }

@@ -32,7 +32,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 enum : int { MVAE_F32 = 0, MVAE_BF16 = 1 };
 
 // ---------------------------------------------------------------- GEMM (tcgen05)
-enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_BCE = 2, EPI_DGRAD_BN = 3 };
+enum : int { EPI_STORE = 0, EPI_ATOMIC = 1, EPI_BCE = 2, EPI_DGRAD_BN = 3, EPI_STORE_ACT = 4, EPI_DGRAD_ACT = 5 };
 
 struct GemmEpilogue {
   int kind = EPI_STORE;
@@ -56,6 +56,10 @@ struct GemmEpilogue {
   float bce_scale[4] = {0, 0, 0, 0};
   float* loss = nullptr;   // [groups]
   void* probs = nullptr;   // optional sigmoid(x) output, same layout/dtype as C
+  // EPI_STORE_ACT (Linear + bias + Swish in one pass): C = pre = acc + bias (kept for the backward, may be null),
+  //   probs = pre * sigmoid(pre) - the next layer's operand (same layout/dtype as C)
+  // EPI_DGRAD_ACT (input gradient through a Swish): C = acc * swish'(hpre), stat0[col] += sum_rows C (= the bias
+  //   gradient of the Linear that produced hpre)
   // EPI_DGRAD_BN: C = acc * 1[gamma*xhat+beta > 0], xhat = (hpre - mean[g])*rstd[g]
   const void* hpre = nullptr;
   long long ldh = 0;

@@ -135,10 +135,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
   int seg_left = static_cast<int>(min(static_cast<long long>(g + 1) * e.rows_per_group - m, 1ll << 20));
   int trow = (kEpi == EPI_BCE) ? (m % e.target_rows) : 0;
   CT* cptr = reinterpret_cast<CT*>(e.C) + static_cast<long long>(m) * e.ldc + cn;
-  CT* pptr = (kEpi == EPI_BCE && e.probs != nullptr) ? reinterpret_cast<CT*>(e.probs) + static_cast<long long>(m) * e.ldc + cn
-                                                     : nullptr;
-  const act_t* hptr =
-      (kEpi == EPI_DGRAD_BN) ? reinterpret_cast<const act_t*>(e.hpre) + static_cast<long long>(m) * e.ldh + cn : nullptr;
+  CT* pptr = ((kEpi == EPI_BCE || kEpi == EPI_STORE_ACT) && e.probs != nullptr)
+                 ? reinterpret_cast<CT*>(e.probs) + static_cast<long long>(m) * e.ldc + cn
+                 : nullptr;
+  const act_t* hptr = (kEpi == EPI_DGRAD_BN || kEpi == EPI_DGRAD_ACT)
+                          ? reinterpret_cast<const act_t*>(e.hpre) + static_cast<long long>(m) * e.ldh + cn
+                          : nullptr;
   int done = 0;
   while (done < rows) {
     const int seg = min(rows - done, seg_left);
@@ -162,7 +164,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
       for (int u = 0; u < kRB; ++u) {
         if (it + u < seg) {
           ptx::lds128(saddr + u * ldst * 4, v[u]);
-          if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN) {
+          if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN || kEpi == EPI_DGRAD_ACT) {
             if (kFast && aux_saddr != 0) {
               ptx::lds_act4<act_t>(aux_saddr + (it + u) * aux_ld_bytes, aux[u]);  // prefetched during the main loop
             } else if constexpr (kEpi == EPI_BCE) {
@@ -235,6 +237,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
             acc1[i] = fmaf(d[i], xh, acc1[i]);
           }
           store4(crow, kFast, nv, d);
+        } else if constexpr (kEpi == EPI_STORE_ACT) {
+          // Linear + bias + Swish (x * sigmoid(x), multimnist/model.py:379-381): the pre-activation is kept for the
+          // backward, the activation is the next layer's operand
+          float y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[u][i] += bias[i];
+            y[i] = v[u][i] * __fdividef(1.f, 1.f + __expf(-v[u][i]));
+          }
+          if (e.C != nullptr) store4(crow, kFast, nv, v[u]);
+          store4(pptr + static_cast<long long>(u) * e.ldc, kFast, nv, y);
+        } else if constexpr (kEpi == EPI_DGRAD_ACT) {
+          // d pre = d act * swish'(pre), swish'(x) = s + x s (1 - s); its column sums are the producing Linear's bias gradient
+          float d[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x = aux[u][i];
+            const float sg = __fdividef(1.f, 1.f + __expf(-x));
+            d[i] = v[u][i] * fmaf(x * sg, 1.f - sg, sg);
+            acc0[i] += d[i];
+          }
+          store4(crow, kFast, nv, d);
         }
       }
       const int adv = min(kRB, seg - it);  // a segment may end inside a batch (statistics-group boundary)
@@ -245,7 +269,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
         if (trow >= e.target_rows) trow -= e.target_rows;
         if (pptr != nullptr) pptr += static_cast<long long>(adv) * e.ldc;
       }
-      if constexpr (kEpi == EPI_DGRAD_BN) hptr += static_cast<long long>(adv) * e.ldh;
+      if constexpr (kEpi == EPI_STORE_ACT) pptr += static_cast<long long>(adv) * e.ldc;
+      if constexpr (kEpi == EPI_DGRAD_BN || kEpi == EPI_DGRAD_ACT) hptr += static_cast<long long>(adv) * e.ldh;
     }
     if constexpr (kEpi == EPI_BCE) lsum *= g_scale;
     // ---- statistics-group boundary (or end of this warp's rows): publish the column partials
@@ -356,7 +381,7 @@ __global__ void __launch_bounds__(kGemmThreads)
   // Auxiliary epilogue operand (BCE: the target image tile; dgrad: the pre-BatchNorm activations): every thread
   // copies exactly the elements its own row pass will consume into shared memory with cp.async NOW, so the
   // L2 latency is hidden behind the main loop (the epilogue threads are otherwise idle until the accumulator is done).
-  if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN) {
+  if constexpr (kEpi == EPI_BCE || kEpi == EPI_DGRAD_BN || kEpi == EPI_DGRAD_ACT) {
     if (p.aux_off >= 0) {
       const GemmEpilogue& ee = p.epi;
       const act_t* src = reinterpret_cast<const act_t*>(kEpi == EPI_BCE ? ee.target : ee.hpre);
@@ -1016,7 +1041,9 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
                      "gemm: merged transposed-conv classes need stride <= 4 and equal class grids inside the output image");
     }
   }
-  MVAE_REQUIRE(e.C != nullptr, "gemm: null output");
+  MVAE_REQUIRE(e.C != nullptr || (e.kind == EPI_STORE_ACT && e.probs != nullptr), "gemm: null output");
+  if (e.kind == EPI_STORE_ACT) MVAE_REQUIRE(e.probs != nullptr, "gemm: the activation epilogue needs its output");
+  if (e.kind == EPI_DGRAD_ACT) MVAE_REQUIRE(e.hpre != nullptr, "gemm: the activation-backward epilogue needs the pre-activations");
   MVAE_REQUIRE(e.kind != EPI_ATOMIC || e.c_dtype == MVAE_F32, "gemm: atomic epilogue needs fp32 output");
 
   const int tiles_m = ceil_div(g.M, kBlockM);
@@ -1030,9 +1057,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
   const int sms = 148;
   static const int use_aux = env_int("MVAE_GEMM_AUX", 1);
   auto al0 = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
-  bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) && (e.ldc % 4 == 0);
+  const bool dgrad_aux = e.kind == EPI_DGRAD_BN || e.kind == EPI_DGRAD_ACT;
+  bool aux_ok = use_aux != 0 && (e.kind == EPI_BCE || dgrad_aux) && (e.ldc % 4 == 0);
   if (e.kind == EPI_BCE) aux_ok = aux_ok && (e.ldt % 4 == 0) && al0(e.target, 4 * esz);
-  if (e.kind == EPI_DGRAD_BN) aux_ok = aux_ok && (e.ldh % 4 == 0) && al0(e.hpre, 4 * esz);
+  if (dgrad_aux) aux_ok = aux_ok && (e.ldh % 4 == 0) && al0(e.hpre, 4 * esz);
   auto aux_bytes = [&](int bn) -> int { return aux_ok ? kBlockM * bn * esz : 0; };
   static const int use_red = env_int("MVAE_GEMM_CTA_REDUCE", 1);
   const bool red_ok = use_red != 0 && e.stat0 != nullptr && e.kind != EPI_ATOMIC;
@@ -1083,7 +1111,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
     // ~5.5 us up to 128 columns, ~9 us beyond); the dgrad pass reads one more tensor
     double t_epi = (0.35 + 0.0105 * bn) * (atomic ? 1.3 : 1.0);
     if (e.kind == EPI_BCE) t_epi = bn <= 128 ? 6.5 : 12.0;
-    if (e.kind == EPI_DGRAD_BN) t_epi = 0.5 + 0.016 * bn;
+    if (dgrad_aux || e.kind == EPI_STORE_ACT) t_epi = 0.5 + 0.016 * bn;
     const double per_sm_ctas = static_cast<double>(ctas) / active_sms;
     // with co-residency the epilogues hide behind other CTAs' loads; one epilogue is always exposed
     const double t_epi_total = occ > 1 ? t_epi * (1.0 + 0.35 * (per_sm_ctas - 1.0)) : t_epi * per_sm_ctas;
@@ -1102,7 +1130,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
     const int n_cap = 16 * ceil_div(g.N, 16);
     // heavy epilogues (BCE, dgrad+BatchNorm statistics) carry an auxiliary tile in shared memory and are bound by
     // SFU / issue rate per row, not per column: measured best at <= 128 columns (2 CTAs per SM, full lanes)
-    const int bn_max = (e.kind == EPI_BCE || e.kind == EPI_DGRAD_BN) ? 128 : 256;
+    const int bn_max = (e.kind == EPI_BCE || dgrad_aux) ? 128 : 256;
     for (int bn = 32; bn <= bn_max; bn += 16) {
       if (bn > n_cap && bn != 32) break;
       int sp, st, dy, bs, bt;
@@ -1157,7 +1185,7 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
   bool vec = (e.ldc % 4 == 0) && al(e.C, ea) && al(e.probs, ea);
   const int aa = 4 * esz;
   if (e.kind == EPI_BCE) vec = vec && (e.ldt % 4 == 0) && al(e.target, aa);
-  if (e.kind == EPI_DGRAD_BN) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
+  if (dgrad_aux) vec = vec && (e.ldh % 4 == 0) && al(e.hpre, aa);
   kp.vec_ok = vec ? 1 : 0;
   {
     static const int use_direct = env_int("MVAE_GEMM_DIRECT_STORE", 1);
@@ -1199,6 +1227,10 @@ static int launch_gemm_impl(const GemmDesc& g, cudaStream_t stream) {
   MVAE_GEMM_CASE(MVAE_BF16, EPI_ATOMIC)
   MVAE_GEMM_CASE(MVAE_BF16, EPI_BCE)
   MVAE_GEMM_CASE(MVAE_BF16, EPI_DGRAD_BN)
+  MVAE_GEMM_CASE(MVAE_F32, EPI_STORE_ACT)
+  MVAE_GEMM_CASE(MVAE_F32, EPI_DGRAD_ACT)
+  MVAE_GEMM_CASE(MVAE_BF16, EPI_STORE_ACT)
+  MVAE_GEMM_CASE(MVAE_BF16, EPI_DGRAD_ACT)
 #undef MVAE_GEMM_CASE
   set_error("gemm: unsupported kind/epilogue %d/%d", g.kind, e.kind);
   return 1;

@@ -66,12 +66,15 @@ __global__ void __launch_bounds__(kThreads) embed_fwd_kernel(const long long* __
     st_any(out, out_dtype, m * ldo + j, act_f(act, table[c * width + j]));
   }
 }
-// dtable[idx[m], j] += dout[m, j] * act'(table[idx[m], j]); a block first sums its rows per character in shared memory
+// dtable[idx[m], j] += dout[m, j] * act'(table[idx[m], j]); a block first sums its rows per character in shared memory.
+// blockIdx.y selects a tile of up to kThreads columns (tables wider than a block).
 __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const long long* __restrict__ idx, long long idx_stride,
-                                                             const float* __restrict__ table, int vocab, int width, int act,
+                                                             const float* __restrict__ table, int vocab, int full_width, int act,
                                                              const void* dout, int dout_dtype, long long ldd, long long rows,
                                                              float* __restrict__ dtable) {
   extern __shared__ float s_acc[];  // [lanes][vocab, width]
+  const int col0 = blockIdx.y * kThreads;
+  const int width = min(kThreads, full_width - col0);
   const int lanes = max(1, min(kThreads / width, 4));   // row lanes per column
   const int vw = vocab * width;
   for (int i = threadIdx.x; i < lanes * vw; i += kThreads) s_acc[i] = 0.f;
@@ -84,14 +87,15 @@ __global__ void __launch_bounds__(kThreads) embed_bwd_kernel(const long long* __
     for (long long m = r0 + lane; m < r1; m += lanes) {
       long long c = idx[m * idx_stride];
       c = c < 0 ? 0 : (c >= vocab ? vocab - 1 : c);
-      mine[c * width + j] += ld_any(dout, dout_dtype, m * ldd + j) * act_g(act, table[c * width + j]);
+      mine[c * width + j] += ld_any(dout, dout_dtype, m * ldd + col0 + j) * act_g(act, table[c * full_width + col0 + j]);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < vw; i += kThreads) {
     float v = 0.f;
     for (int l = 0; l < lanes; ++l) v += s_acc[l * vw + i];
-    if (v != 0.f) atomicAdd(dtable + i, v);
+    const int c = i / width, jj = i - c * width;
+    if (v != 0.f) atomicAdd(dtable + static_cast<long long>(c) * full_width + col0 + jj, v);
   }
 }
 
@@ -278,12 +282,12 @@ int mvae_embed_backward(const int64_t* indices, int64_t index_stride, const floa
                         int dout_dtype, const void* dout, int64_t ld_dout, int64_t rows, float* dtable, void* stream) {
   MVAE_REQUIRE(indices != nullptr && table != nullptr && dout != nullptr && dtable != nullptr, "embed_backward: null tensor");
   MVAE_REQUIRE(rows > 0 && width > 0 && vocab > 0 && vocab <= kMaxVocab, "embed_backward: vocabulary %d outside [1, %d]", vocab, kMaxVocab);
-  MVAE_REQUIRE(width <= kThreads, "embed_backward: width %d > %d", width, kThreads);
-  const int lanes = std::max(1, std::min(kThreads / width, 4));
-  const size_t smem = static_cast<size_t>(lanes) * vocab * width * sizeof(float);
+  const int tile = std::min(width, kThreads);           // columns per block (blockIdx.y walks the tiles of wider tables)
+  const int lanes = std::max(1, std::min(kThreads / tile, 4));
+  const size_t smem = static_cast<size_t>(lanes) * vocab * tile * sizeof(float);
   MVAE_REQUIRE(smem <= 48 * 1024, "embed_backward: table too large for shared memory");
   const int blocks = static_cast<int>(std::min<long long>((rows + 15) / 16, 592));
-  embed_bwd_kernel<<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+  embed_bwd_kernel<<<dim3(blocks, (width + kThreads - 1) / kThreads), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(indices), index_stride, table, vocab, width, act, dout, dout_dtype, ld_dout, rows, dtable);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
