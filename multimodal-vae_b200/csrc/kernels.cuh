@@ -43,6 +43,8 @@ struct TailArgs {
   unsigned long long seed = 0;
   const int* step_ptr = nullptr;
   int training = 1;  // 0: z = mu (mnist/model.py:29-30)
+  float* noise_buf = nullptr;  // [G, B, n] optional: the forward leaves the draws it used here, the backward reads them back
+                               // instead of re-running Philox (and stays correct if the step counter has moved on since)
   const float* z_in = nullptr;  // [G*B, n]: latents given by the caller (decode only; experts are ignored)
   float kl_weight[kMaxGroups] = {0, 0, 0};
   // text decoder layer 1 (Linear n -> 10), fused because z is in registers here

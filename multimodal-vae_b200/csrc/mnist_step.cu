@@ -131,6 +131,7 @@ struct Plan {
   long long sv_e1, sv_e2, sv_d1, sv_d2;                  // [2][groups][F]: mean, rstd
   long long txt_table, txt_save;
   // activations
+  long long noise;                                       // [G*B][n] fp32: the reparametrize draws of the forward, re-read by the tail backward
   long long h1pre, h1, h2pre, h2, enc, z, t1pre, g1pre, g1, g2pre, g2, dlog, dyt, dy2, dy1, dz, denc, dye2, dye1;
   long long x3_a = -1, x3_b = -1;                        // 3xTF32 split-operand scratch (MVAE_DT_F32X3 only)
 };
@@ -173,6 +174,7 @@ Plan make_plan(int B, int n, int dtype_code) {
   p.h2pre = take(B * 200 * es); p.h2 = take(B * 200 * es);
   p.enc = take(B * 2 * n * 4);
   p.z = take(R * n * es);
+  p.noise = take(R * n * 4);
   p.t1pre = take(R * 10 * 4);
   p.g1pre = take(R * 200 * es); p.g1 = take(R * 200 * es);
   p.g2pre = take(R * 400 * es); p.g2 = take(R * 400 * es);
@@ -421,6 +423,9 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   const bool use_chain = chain_env != 0 && a->dtype == MVAE_DT_BF16 && training && bwd && !module_bwd && !decode_only &&
                          chain_supported(B, G, n);
 
+  // one call = the whole step with the optimizer: the decoder bucket's Adam runs beside the encoder backward
+  const bool adam_split = bwd && bwd_dec && bwd_enc && a->do_adam && !module_bwd && ss != nullptr && L.enc_floats % 4 == 0;
+
   const Ptrs W{static_cast<char*>(a->workspace)};
   g_x3.a = x3 ? W.at<void>(P.x3_a) : nullptr;
   g_x3.b = x3 ? W.at<void>(P.x3_b) : nullptr;
@@ -529,6 +534,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   ta.labels = reinterpret_cast<const long long*>(a->text);
   ta.eps = a->eps; ta.seed = a->seed; ta.step_ptr = a->noise_step != nullptr ? a->noise_step : a->adam_step; ta.training = training ? 1 : 0;
   ta.z_in = a->z_in;
+  ta.noise_buf = W.at<float>(P.noise);
   ta.wt1 = pf("text_decoder.net.0.weight"); ta.bt1 = pf("text_decoder.net.0.bias");
   ta.z = W.at<void>(P.z); ta.mu = a->out_mu; ta.logvar = a->out_logvar;
   ta.kl = losses + 2 * kMaxGroups;
@@ -690,6 +696,16 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     MVAE_STEP(launch_tail_backward(ta, st), "launch_tail_backward");
     if (dep(st, s2)) return 1;  // fork: encoder weight gradients
     if (dep(st, s3)) return 1;  // fork: text encoder backward
+    // Every decoder-side gradient is final now (the decoder weight gradients sit ahead on the side stream, everything else
+    // was joined into the tail backward): the decoder bucket is updated on the side stream while the encoder chain runs,
+    // and only the encoder bucket is left for the end of the step.
+    if (adam_split) {
+      MVAE_REQUIRE(a->adam_m && a->adam_v && a->adam_step, "mnist_step: Adam state missing");
+      const long long e0 = L.enc_floats, nd = L.param_floats - L.enc_floats;
+      MVAE_STEP(launch_adam(prm + e0, a->grads + e0, a->adam_m + e0, a->adam_v + e0,
+                            a->params_bf16 ? static_cast<__nv_bfloat16*>(a->params_bf16) + e0 : nullptr, nd, a->lr, a->beta1, a->beta2,
+                            a->adam_eps, a->adam_step, a->grad_scale, 0, s2), "launch_adam(decoders)");
+    }
   }
   if (bwd && bwd_enc) {
     if (!bwd_dec && dep(st, s2)) return 1;
@@ -754,8 +770,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
 
   if (bwd && bwd_enc && a->do_adam) {
     MVAE_REQUIRE(a->adam_m && a->adam_v && a->adam_step, "mnist_step: Adam state missing");
-    MVAE_STEP(launch_adam(prm, a->grads, a->adam_m, a->adam_v, a->params_bf16, L.param_floats, a->lr, a->beta1, a->beta2,
-                    a->adam_eps, a->adam_step, a->grad_scale, 0, st), "launch_adam#33");
+    MVAE_STEP(launch_adam(prm, a->grads, a->adam_m, a->adam_v, a->params_bf16, adam_split ? L.enc_floats : L.param_floats, a->lr,
+                    a->beta1, a->beta2, a->adam_eps, a->adam_step, a->grad_scale, 0, st), "launch_adam#33");
   }
   return 0;
 }

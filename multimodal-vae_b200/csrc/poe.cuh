@@ -79,6 +79,45 @@ __device__ __forceinline__ Poe poe_eval(int mode, int prior, float eps, const fl
   r.logvar = kNeedLogvar ? flog(r.pd_var) : 0.f;
   return r;
 }
+// The same product from per-expert parts computed once (var_i = exp(logvar_i) + eps, 1/var_i): a kernel that evaluates several
+// ELBO terms on one sample shares the transcendentals between the terms.  Same operations in the same order as poe_eval, so
+// the results are bit-identical.
+struct PoePart {
+  float var, inv;
+};
+__device__ __forceinline__ PoePart poe_part(float lv, float eps) {
+  PoePart p;
+  p.var = fexp(lv) + eps;
+  p.inv = frcp(p.var);
+  return p;
+}
+template <bool kNeedLogvar>
+__device__ __forceinline__ Poe poe_combine(int mode, int prior, const float (&m)[2], const PoePart (&pt)[2], const bool (&present)[2]) {
+  Poe r;
+  r.var[0] = r.var[1] = 1.f;
+  r.inv[0] = r.inv[1] = 1.f;
+  float num = 0.f, S = 0.f, P = (mode == MVAE_POE_PRECISION && prior) ? 1.f : 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+    if (present[i]) {
+      r.var[i] = pt[i].var;
+      r.inv[i] = pt[i].inv;
+      num += m[i] * (mode == MVAE_POE_REF ? pt[i].var : pt[i].inv);
+      S += pt[i].var;
+      P += pt[i].inv;
+    }
+  r.pd_var = frcp(P);
+  if (mode == MVAE_POE_REF) {
+    r.invS = frcp(S);
+    r.mu = num * r.invS;
+  } else {
+    r.invS = r.pd_var;
+    r.mu = num * r.pd_var;
+  }
+  r.logvar = kNeedLogvar ? flog(r.pd_var) : 0.f;
+  return r;
+}
+
 // Gradients w.r.t. expert i's (mu_i, logvar_i) given d(mu), d(logvar) of the product.
 __device__ __forceinline__ void poe_grad(int mode, float eps, const Poe& r, int i, float m_i, float dmu, float dlv,
                                          float& dm_i, float& dlv_i) {

@@ -149,6 +149,137 @@ __global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArg
     atomicAdd(a.kl + threadIdx.x, -0.5f * a.kl_weight[threadIdx.x] * s_kl[threadIdx.x]);
 }
 
+// ================================================================= tail forward, one warp per SAMPLE (n <= 64)
+// The warp carries its sample through all ELBO terms: both experts are loaded and exponentiated once, the text decoder's
+// first Linear keeps its weights in registers and all (term, feature) dot products are reduced in ONE transposing butterfly
+// (31 shuffles for up to 32 values instead of five per value), the KL partials stay in registers until the warp is done.
+// Same arithmetic per element as tail_fwd_kernel (poe_combine == poe_eval bit for bit, same Philox stream).
+template <typename ZT, int kFwd2Warps>
+__global__ void __launch_bounds__(32 * kFwd2Warps, 28 / kFwd2Warps) tail_fwd2_kernel(const TailArgs a) {
+  __shared__ float s_stat[kMaxGroups][2][kTD];
+  __shared__ float s_kl[kMaxGroups];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kMaxGroups * 2 * kTD; i += blockDim.x) (&s_stat[0][0][0])[i] = 0.f;
+  if (threadIdx.x < kMaxGroups) s_kl[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const int n = a.n, two_n = 2 * a.n, G = a.G;
+  const uint32_t step = a.step_ptr != nullptr ? static_cast<uint32_t>(*a.step_ptr) : 0u;
+  const int k = lane * 2;
+  const bool act = k < n;
+  bool any_img = false, any_txt = false;
+  for (int g = 0; g < G; ++g) {
+    any_img |= a.group_type[g] != TERM_TEXT;
+    any_txt |= a.group_type[g] != TERM_IMAGE;
+  }
+  any_img = any_img && a.enc_img != nullptr && a.z_in == nullptr;
+  any_txt = any_txt && a.txt_table != nullptr && a.z_in == nullptr;
+  const bool text_dec = a.wt1 != nullptr;
+  float2 w[kTD];
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) w[j] = (text_dec && act) ? *reinterpret_cast<const float2*>(a.wt1 + j * n + k) : make_float2(0.f, 0.f);
+  float klacc[kMaxGroups] = {0.f, 0.f, 0.f};
+
+  for (int b = blockIdx.x * kFwd2Warps + warp; b < a.B; b += gridDim.x * kFwd2Warps) {
+    float mi[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f};
+    PoePart pi[2] = {{1.f, 1.f}, {1.f, 1.f}}, pt[2] = {{1.f, 1.f}, {1.f, 1.f}};
+    if (act && any_img) {
+      const float2 m2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + k);
+      const float2 l2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + n + k);
+      mi[0] = m2.x; mi[1] = m2.y;
+      pi[0] = poe_part(l2.x, a.poe_eps); pi[1] = poe_part(l2.y, a.poe_eps);
+    }
+    if (act && any_txt) {
+      const int label = static_cast<int>(a.labels[b]);
+      const float2 m2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + k);
+      const float2 l2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + n + k);
+      mt[0] = m2.x; mt[1] = m2.y;
+      pt[0] = poe_part(l2.x, a.poe_eps); pt[1] = poe_part(l2.y, a.poe_eps);
+    }
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (g >= G) break;
+      const int ty = a.group_type[g];
+      const bool present[2] = {ty != TERM_TEXT && any_img, ty != TERM_IMAGE && any_txt};
+      const long long it = static_cast<long long>(g) * a.B + b;
+      float zz[2] = {0.f, 0.f}, mm[2] = {0.f, 0.f}, ll[2] = {0.f, 0.f};
+      if (act) {
+        if (a.z_in != nullptr) {  // decode_image / decode_text: the caller's latents, no experts
+          const float2 zi = *reinterpret_cast<const float2*>(a.z_in + it * n + k);
+          zz[0] = zi.x;
+          zz[1] = zi.y;
+        } else {
+          float2 e2 = make_float2(0.f, 0.f);
+          if (a.training) {
+            if (a.eps != nullptr) {
+              e2 = *reinterpret_cast<const float2*>(a.eps + it * n + k);
+            } else {
+              e2 = normal_pair(a.seed, step, (it * n + k) >> 1);
+              if (a.noise_buf != nullptr) *reinterpret_cast<float2*>(a.noise_buf + it * n + k) = e2;
+            }
+          }
+          const float ee[2] = {e2.x, e2.y};
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float m[2] = {mi[c], mt[c]};
+            const PoePart parts[2] = {pi[c], pt[c]};
+            const Poe r = poe_combine<true>(a.poe_mode, a.prior_expert, m, parts, present);
+            mm[c] = r.mu;
+            ll[c] = r.logvar;
+            zz[c] = a.training ? ee[c] * sqrtf(r.pd_var) + r.mu : r.mu;   // reparametrize (mnist/model.py:25-28)
+            klacc[g] += 1.f + r.logvar - r.mu * r.mu - r.pd_var;          // KL integrand of mnist/train.py:79
+          }
+        }
+        store_pair(reinterpret_cast<ZT*>(a.z) + it * n + k, zz[0], zz[1]);
+        if (a.mu != nullptr) {
+          *reinterpret_cast<float2*>(a.mu + it * n + k) = make_float2(mm[0], mm[1]);
+          *reinterpret_cast<float2*>(a.logvar + it * n + k) = make_float2(ll[0], ll[1]);
+        }
+      }
+      if (text_dec) {
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) v[g * kTD + j] = fmaf(zz[0], w[j].x, zz[1] * w[j].y);
+      }
+    }
+    if (text_dec) {
+      // transposing butterfly: afterwards lane L holds the warp-wide sum of value L (= term L / 10, feature L % 10)
+#pragma unroll
+      for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = up ? v[i] : v[i + h];
+          const float keep = up ? v[i + h] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+      }
+      if (lane < G * kTD) {
+        const int g = lane / kTD, j = lane - g * kTD;
+        const float t = v[0] + a.bt1[j];
+        a.t1pre[(static_cast<long long>(g) * a.B + b) * kTD + j] = t;
+        atomicAdd(&s_stat[g][0][j], t);
+        atomicAdd(&s_stat[g][1][j], t * t);
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    const float ks = warp_sum(klacc[g]);
+    if (lane == 0 && g < G) atomicAdd(&s_kl[g], ks);
+  }
+  __syncthreads();
+  if (text_dec)
+    for (int i = threadIdx.x; i < G * 2 * kTD; i += blockDim.x) {
+      const int g = i / (2 * kTD), ww = (i / kTD) % 2, j = i % kTD;
+      if (s_stat[g][ww][j] != 0.f) atomicAdd((ww == 0 ? a.t1_sum : a.t1_sumsq) + g * kTD + j, s_stat[g][ww][j]);
+    }
+  if (threadIdx.x < G && a.kl != nullptr && s_kl[threadIdx.x] != 0.f)
+    atomicAdd(a.kl + threadIdx.x, -0.5f * a.kl_weight[threadIdx.x] * s_kl[threadIdx.x]);
+}
+
 // ================================================================= tail backward
 // Block = kBwdRows samples x G terms, one warp per (sample, term); the terms' contributions to one sample's
 // encoder-output gradient are combined through shared memory (no global atomics on activations).
@@ -366,22 +497,22 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
 }
 
 // ================================================================= tail backward, one warp per SAMPLE (n <= 64)
-// The warp carries its sample through all ELBO terms: both experts are loaded once, the terms' contributions to the image
+// The warp carries its sample through all ELBO terms: both experts are loaded and exponentiated once (poe_part / poe_combine),
+// the draws of the forward are read back from noise_buf (no second Philox pass), the terms' contributions to the image
 // expert's gradient are summed in registers (no shared-memory combine, no block barrier inside the loop), the text expert's
-// gradient goes into a per-warp private [10][2n] table (plain shared-memory adds), and the text decoder's first Linear
-// keeps its weights in shared memory and its weight gradient in per-lane registers.  Same arithmetic as tail_bwd_kernel.
-constexpr int kBwd2Warps = 8;
-template <typename ZT>
-__global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const TailArgs a) {
+// gradient goes into the block's [10][2n] table with shared-memory adds, and the text decoder's first Linear keeps its weights
+// in shared memory and its weight gradient in per-lane registers.  Same arithmetic as tail_bwd_kernel.
+template <typename ZT, int kBwd2Warps>
+__global__ void __launch_bounds__(32 * kBwd2Warps, 28 / kBwd2Warps) tail_bwd2_kernel(const TailArgs a) {
   extern __shared__ float sm[];
   const int n = a.n, two_n = 2 * a.n, G = a.G;
-  // layout: per-warp text-expert tables [warps][10][2n] | Wt1 [10][n] | t1 coefficients [G][4][10] | d_wt1 [10][n] | d_enc_bias [2n]
+  // layout: text-expert table [10][2n] | Wt1 [10][n] | t1 coefficients [G][4][10] | d_wt1 [10][n] | d_enc_bias [2n]
   float* s_tab = sm;
-  float* s_w = s_tab + kBwd2Warps * kTD * two_n;
+  float* s_w = s_tab + kTD * two_n;
   float* s_co = s_w + kTD * n;
   float* s_dw = s_co + kMaxGroups * 4 * kTD;
   float* s_eb = s_dw + kTD * n;
-  const int total = kBwd2Warps * kTD * two_n + kTD * n + kMaxGroups * 4 * kTD + kTD * n + two_n;
+  const int total = kTD * two_n + kTD * n + kMaxGroups * 4 * kTD + kTD * n + two_n;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < total; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
@@ -410,34 +541,48 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
   float r_w1[kTD][2], r_eb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int j = 0; j < kTD; ++j) r_w1[j][0] = r_w1[j][1] = 0.f;
-  float* my_tab = s_tab + warp * kTD * two_n;
+  // this lane's (term, feature) of the text decoder's BatchNorm backward: loop constants
+  float co_mean = 0.f, co_rstd = 0.f, co_s0 = 0.f, co_s1 = 0.f, co_gamma = 0.f;
+  int my_g = 0, my_j = 0;
+  if (text_dec && lane < G * kTD) {
+    my_g = lane / kTD;
+    my_j = lane - my_g * kTD;
+    co_mean = s_co[(my_g * 4 + 0) * kTD + my_j];
+    co_rstd = s_co[(my_g * 4 + 1) * kTD + my_j];
+    co_s0 = s_co[(my_g * 4 + 2) * kTD + my_j];
+    co_s1 = s_co[(my_g * 4 + 3) * kTD + my_j];
+    co_gamma = a.t1_gamma[my_j];
+  }
 
   for (int b = blockIdx.x * kBwd2Warps + warp; b < a.B; b += gridDim.x * kBwd2Warps) {
     const int label = any_txt ? static_cast<int>(a.labels[b]) : 0;
     // text decoder: gradient at its first Linear's output (BatchNorm backward apply) for every term: lane = term * 10 + feature
     float dt_mine = 0.f;
     if (text_dec && lane < G * kTD) {
-      const int gg = lane / kTD, j = lane - gg * kTD;
-      const long long row = static_cast<long long>(gg) * a.B + b;
-      const float rstd = s_co[(gg * 4 + 1) * kTD + j];
-      const float x = a.t1pre[row * kTD + j];
-      const float xh = (x - s_co[(gg * 4 + 0) * kTD + j]) * rstd;
-      const float dy = a.t1_dyhat[row * kTD + j];
-      dt_mine = a.t1_gamma[j] * rstd * (dy - s_co[(gg * 4 + 2) * kTD + j] - xh * s_co[(gg * 4 + 3) * kTD + j]);
+      const long long row = static_cast<long long>(my_g) * a.B + b;
+      const float x = a.t1pre[row * kTD + my_j];
+      const float xh = (x - co_mean) * co_rstd;
+      const float dy = a.t1_dyhat[row * kTD + my_j];
+      dt_mine = co_gamma * co_rstd * (dy - co_s0 - xh * co_s1);
     }
-    float mi[2] = {0.f, 0.f}, li[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f}, lt[2] = {0.f, 0.f};
+    float mi[2] = {0.f, 0.f}, mt[2] = {0.f, 0.f};
+    PoePart pi[2] = {{1.f, 1.f}, {1.f, 1.f}}, pt[2] = {{1.f, 1.f}, {1.f, 1.f}};
     if (act && any_img) {
       const float2 m2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + k);
       const float2 l2 = *reinterpret_cast<const float2*>(a.enc_img + static_cast<long long>(b) * two_n + n + k);
-      mi[0] = m2.x; mi[1] = m2.y; li[0] = l2.x; li[1] = l2.y;
+      mi[0] = m2.x; mi[1] = m2.y;
+      pi[0] = poe_part(l2.x, a.poe_eps); pi[1] = poe_part(l2.y, a.poe_eps);
     }
     if (act && any_txt) {
       const float2 m2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + k);
       const float2 l2 = *reinterpret_cast<const float2*>(a.txt_table + label * two_n + n + k);
-      mt[0] = m2.x; mt[1] = m2.y; lt[0] = l2.x; lt[1] = l2.y;
+      mt[0] = m2.x; mt[1] = m2.y;
+      pt[0] = poe_part(l2.x, a.poe_eps); pt[1] = poe_part(l2.y, a.poe_eps);
     }
     float a_mi[2] = {0.f, 0.f}, a_li[2] = {0.f, 0.f}, a_mt[2] = {0.f, 0.f}, a_lt[2] = {0.f, 0.f};
-    for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (g >= G) break;
       const int ty = a.group_type[g];
       const bool present[2] = {ty != TERM_TEXT, ty != TERM_IMAGE};
       const float c_kl = a.kl_weight[g];
@@ -447,6 +592,8 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
         if (a.training) {
           if (a.eps != nullptr)
             e2 = *reinterpret_cast<const float2*>(a.eps + row * n + k);
+          else if (a.noise_buf != nullptr)
+            e2 = *reinterpret_cast<const float2*>(a.noise_buf + row * n + k);
           else
             e2 = normal_pair(a.seed, step, (row * n + k) >> 1);
         }
@@ -462,8 +609,8 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const float m[2] = {present[0] ? mi[c] : 0.f, present[1] ? mt[c] : 0.f};
-        const float lv[2] = {present[0] ? li[c] : 0.f, present[1] ? lt[c] : 0.f};
-        r[c] = poe_eval<false>(a.poe_mode, a.prior_expert, a.poe_eps, m, lv, present);
+        const PoePart parts[2] = {pi[c], pt[c]};
+        r[c] = poe_combine<false>(a.poe_mode, a.prior_expert, m, parts, present);
         sd[c] = sqrtf(r[c].pd_var);
         zz[c] = a.training ? ee[c] * sd[c] + r[c].mu : r[c].mu;
       }
@@ -510,12 +657,11 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
         r_eb[0] += a_mi[0]; r_eb[1] += a_mi[1]; r_eb[2] += a_li[0]; r_eb[3] += a_li[1];
       }
       if (any_txt) {
-        float2* tm = reinterpret_cast<float2*>(my_tab + label * two_n + k);
-        float2* tl = reinterpret_cast<float2*>(my_tab + label * two_n + n + k);
-        float2 vm = *tm, vl = *tl;
-        vm.x += a_mt[0]; vm.y += a_mt[1]; vl.x += a_lt[0]; vl.y += a_lt[1];
-        *tm = vm;
-        *tl = vl;
+        float* tm = s_tab + label * two_n + k;
+        atomicAdd(tm, a_mt[0]);
+        atomicAdd(tm + 1, a_mt[1]);
+        atomicAdd(tm + n, a_lt[0]);
+        atomicAdd(tm + n + 1, a_lt[1]);
       }
     }
   }
@@ -534,18 +680,300 @@ __global__ void __launch_bounds__(32 * kBwd2Warps, 3) tail_bwd2_kernel(const Tai
   }
   __syncthreads();
   if (a.d_txt_table != nullptr && a.txt_table != nullptr)
-    for (int i = threadIdx.x; i < kTD * two_n; i += blockDim.x) {
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < kBwd2Warps; ++w) v += s_tab[w * kTD * two_n + i];
-      if (v != 0.f) atomicAdd(a.d_txt_table + i, v);
-    }
+    for (int i = threadIdx.x; i < kTD * two_n; i += blockDim.x)
+      if (s_tab[i] != 0.f) atomicAdd(a.d_txt_table + i, s_tab[i]);
   if (text_dec && a.d_wt1 != nullptr)
     for (int i = threadIdx.x; i < kTD * n; i += blockDim.x) atomicAdd(a.d_wt1 + i, s_dw[i]);
   if (a.d_enc_bias != nullptr && a.enc_img != nullptr)
     for (int i = threadIdx.x; i < two_n; i += blockDim.x) atomicAdd(a.d_enc_bias + i, s_eb[i]);
   // BatchNorm affine gradients of the text decoder: dgamma = sum_g S1, dbeta = sum_g S0 (block 0 only)
   if (text_dec && blockIdx.x == 0 && threadIdx.x < kTD && a.d_t1_gamma != nullptr) {
+    float dg = 0.f, db = 0.f;
+    for (int gg = 0; gg < G; ++gg) {
+      dg += a.t1_s1[gg * kTD + threadIdx.x];
+      db += a.t1_s0[gg * kTD + threadIdx.x];
+    }
+    a.d_t1_gamma[threadIdx.x] += dg;
+    a.d_t1_beta[threadIdx.x] += db;
+  }
+}
+
+// ================================================================= the hot configuration, specialised (n == 64, training)
+// tail_fwd3 / tail_bwd3: what tail_fwd2 / tail_bwd2 do, with everything that is uniform in the benchmarked step resolved at
+// compile time - n = 64 (every lane owns one float2 of latents; shared-memory and row offsets are immediates), train mode, the
+// PoE arithmetic as a template parameter, the text decoder's first Linear present, both experts present in the workspace, no
+// caller-provided latents / upstream gradients / mu-logvar outputs.  The generic kernels spend ~80 % of their ~2 200
+// instructions per sample on address arithmetic, constant-bank loads and branches around those options (ncu source view).
+// No shared-memory atomics (fp32 adds on shared memory are compare-and-swap loops on this architecture): per-lane registers
+// and per-warp tables, reduced across the block's warps once at the end.
+constexpr int kT3Warps = 14;   // 2 blocks x 14 warps per SM: the 4096 samples of the benchmarked batch are resident at once
+constexpr int kT3N = 64;
+
+template <typename ZT, int kMode>
+__global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailArgs a) {
+  constexpr int n = kT3N, two_n = 2 * kT3N;
+  __shared__ float s_red[kT3Warps][64 + kMaxGroups];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.G, B = a.B, k = lane * 2;
+  const uint32_t step = a.step_ptr != nullptr ? static_cast<uint32_t>(*a.step_ptr) : 0u;
+  bool p_img[kMaxGroups], p_txt[kMaxGroups];
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    p_img[g] = g < G && a.group_type[g] != TERM_TEXT;
+    p_txt[g] = g < G && a.group_type[g] != TERM_IMAGE;
+  }
+  const float poe_eps = a.poe_eps;
+  const int prior = a.prior_expert;
+  const float* __restrict__ enc_img = a.enc_img;
+  const float* __restrict__ txt_table = a.txt_table;
+  const long long* __restrict__ labels = a.labels;
+  const float* __restrict__ eps = a.eps;
+  float* __restrict__ noise_buf = a.noise_buf;
+  ZT* __restrict__ zout = reinterpret_cast<ZT*>(a.z);
+  float2 w[kTD];
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) w[j] = *reinterpret_cast<const float2*>(a.wt1 + j * n + k);
+  // lane L < 10 G owns (term L / 10, feature L % 10) of the text decoder's first Linear after the butterfly
+  const bool owner = lane < G * kTD;
+  const int my_g = owner ? lane / kTD : 0, my_j = owner ? lane - my_g * kTD : 0;
+  const float my_bias = owner ? a.bt1[my_j] : 0.f;
+  float* __restrict__ my_t1 = a.t1pre + static_cast<long long>(my_g) * B * kTD + my_j;
+  float st_sum = 0.f, st_sq = 0.f;
+  float klacc[kMaxGroups] = {0.f, 0.f, 0.f};
+
+  for (int b = blockIdx.x * kT3Warps + warp; b < B; b += gridDim.x * kT3Warps) {
+    const float2 im = *reinterpret_cast<const float2*>(enc_img + static_cast<long long>(b) * two_n + k);
+    const float2 il = *reinterpret_cast<const float2*>(enc_img + static_cast<long long>(b) * two_n + n + k);
+    const int label = static_cast<int>(labels[b]);
+    const float2 tm = *reinterpret_cast<const float2*>(txt_table + label * two_n + k);
+    const float2 tl = *reinterpret_cast<const float2*>(txt_table + label * two_n + n + k);
+    const float mi[2] = {im.x, im.y}, mt[2] = {tm.x, tm.y};
+    const PoePart pi[2] = {poe_part(il.x, poe_eps), poe_part(il.y, poe_eps)};
+    const PoePart pt[2] = {poe_part(tl.x, poe_eps), poe_part(tl.y, poe_eps)};
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (g < G) {
+        const long long e_off = (static_cast<long long>(g) * B + b) * n + k;
+        float2 e2;
+        if (eps != nullptr) {
+          e2 = *reinterpret_cast<const float2*>(eps + e_off);
+        } else {
+          e2 = normal_pair(a.seed, step, e_off >> 1);
+          *reinterpret_cast<float2*>(noise_buf + e_off) = e2;
+        }
+        const float ee[2] = {e2.x, e2.y};
+        const bool present[2] = {p_img[g], p_txt[g]};
+        float zz[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float m[2] = {mi[c], mt[c]};
+          const PoePart parts[2] = {pi[c], pt[c]};
+          const Poe r = poe_combine<true>(kMode, prior, m, parts, present);
+          zz[c] = ee[c] * sqrtf(r.pd_var) + r.mu;                    // reparametrize (mnist/model.py:25-28)
+          klacc[g] += 1.f + r.logvar - r.mu * r.mu - r.pd_var;       // KL integrand of mnist/train.py:79
+        }
+        store_pair(zout + e_off, zz[0], zz[1]);
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) v[g * kTD + j] = fmaf(zz[0], w[j].x, zz[1] * w[j].y);
+      }
+    }
+    // transposing butterfly: afterwards lane L holds the warp-wide sum of value L
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+      const bool up = (lane & h) != 0;
+#pragma unroll
+      for (int i = 0; i < h; ++i) {
+        const float send = up ? v[i] : v[i + h];
+        const float keep = up ? v[i + h] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+      }
+    }
+    if (owner) {
+      const float t = v[0] + my_bias;
+      my_t1[static_cast<long long>(b) * kTD] = t;
+      st_sum += t;
+      st_sq = fmaf(t, t, st_sq);
+    }
+  }
+  // block reduction of the BatchNorm statistics of the text decoder and of the KL partials, one global atomic per address
+  s_red[warp][lane] = st_sum;
+  s_red[warp][32 + lane] = st_sq;
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    const float ks = warp_sum(klacc[g]);
+    if (lane == 0) s_red[warp][64 + g] = ks;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 + kMaxGroups) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kT3Warps; ++ww) t += s_red[ww][threadIdx.x];
+    const int i = threadIdx.x;
+    if (i < 64) {
+      const int l = i & 31;
+      if (l < G * kTD && t != 0.f) atomicAdd((i < 32 ? a.t1_sum : a.t1_sumsq) + l, t);   // [G][10] == lane index
+    } else if (i - 64 < G && a.kl != nullptr && t != 0.f) {
+      atomicAdd(a.kl + (i - 64), -0.5f * a.kl_weight[i - 64] * t);
+    }
+  }
+}
+
+template <typename ZT, int kMode>
+__global__ void __launch_bounds__(32 * kT3Warps, 2) tail_bwd3_kernel(const TailArgs a) {
+  constexpr int n = kT3N, two_n = 2 * kT3N;
+  constexpr int kTab = kTD * two_n;   // floats per warp table
+  extern __shared__ float sm[];       // per-warp text-expert tables [warps][10][2n] | Wt1 [10][n]
+  float* s_w = sm + kT3Warps * kTab;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = a.G, B = a.B, k = lane * 2;
+  for (int i = threadIdx.x; i < kT3Warps * kTab; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < kTD * n; i += blockDim.x) s_w[i] = a.wt1[i];
+  __syncthreads();
+  bool p_img[kMaxGroups], p_txt[kMaxGroups];
+  float c_kl[kMaxGroups];
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    p_img[g] = g < G && a.group_type[g] != TERM_TEXT;
+    p_txt[g] = g < G && a.group_type[g] != TERM_IMAGE;
+    c_kl[g] = g < G ? a.kl_weight[g] : 0.f;
+  }
+  const float poe_eps = a.poe_eps;
+  const int prior = a.prior_expert;
+  const float* __restrict__ enc_img = a.enc_img;
+  const float* __restrict__ txt_table = a.txt_table;
+  const long long* __restrict__ labels = a.labels;
+  const float* __restrict__ noise = a.eps != nullptr ? a.eps : a.noise_buf;
+  const float* __restrict__ dz = a.dz;
+  ZT* __restrict__ d_enc = reinterpret_cast<ZT*>(a.d_enc);
+  // this lane's (term, feature) of the text decoder's BatchNorm backward: dT1 = gamma rstd (dy - S0/B - xhat S1/B)
+  const bool owner = lane < G * kTD;
+  const int my_g = owner ? lane / kTD : 0, my_j = owner ? lane - my_g * kTD : 0;
+  float co_mean = 0.f, co_rstd = 0.f, co_s0 = 0.f, co_s1 = 0.f, co_gr = 0.f;
+  if (owner) {
+    const float inv_b = 1.f / static_cast<float>(B);
+    co_mean = a.t1_sum[lane] / B;
+    const float var = fmaxf(a.t1_sumsq[lane] / B - co_mean * co_mean, 0.f);
+    co_rstd = rsqrtf(var + 1e-5f);
+    co_s0 = a.t1_s0[lane] / B;
+    co_s1 = a.t1_s1[lane] / B;
+    co_gr = a.t1_gamma[my_j] * co_rstd;
+    (void)inv_b;
+  }
+  const float* __restrict__ my_t1 = a.t1pre + static_cast<long long>(my_g) * B * kTD + my_j;
+  const float* __restrict__ my_dy = a.t1_dyhat + static_cast<long long>(my_g) * B * kTD + my_j;
+  float r_w1[kTD][2], r_eb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < kTD; ++j) r_w1[j][0] = r_w1[j][1] = 0.f;
+  float* my_tab = sm + warp * kTab + k;
+
+  for (int b = blockIdx.x * kT3Warps + warp; b < B; b += gridDim.x * kT3Warps) {
+    float dt_mine = 0.f;
+    if (owner) {
+      const float x = my_t1[static_cast<long long>(b) * kTD];
+      const float dy = my_dy[static_cast<long long>(b) * kTD];
+      const float xh = (x - co_mean) * co_rstd;
+      dt_mine = co_gr * (dy - co_s0 - xh * co_s1);
+    }
+    const float2 im = *reinterpret_cast<const float2*>(enc_img + static_cast<long long>(b) * two_n + k);
+    const float2 il = *reinterpret_cast<const float2*>(enc_img + static_cast<long long>(b) * two_n + n + k);
+    const int label = static_cast<int>(labels[b]);
+    const float2 tm = *reinterpret_cast<const float2*>(txt_table + label * two_n + k);
+    const float2 tl = *reinterpret_cast<const float2*>(txt_table + label * two_n + n + k);
+    const float mi[2] = {im.x, im.y}, mt[2] = {tm.x, tm.y};
+    const PoePart pi[2] = {poe_part(il.x, poe_eps), poe_part(il.y, poe_eps)};
+    const PoePart pt[2] = {poe_part(tl.x, poe_eps), poe_part(tl.y, poe_eps)};
+    float a_mi[2] = {0.f, 0.f}, a_li[2] = {0.f, 0.f}, a_mt[2] = {0.f, 0.f}, a_lt[2] = {0.f, 0.f};
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (g < G) {
+        const long long e_off = (static_cast<long long>(g) * B + b) * n + k;
+        const float2 e2 = *reinterpret_cast<const float2*>(noise + e_off);
+        const float2 dz2 = *reinterpret_cast<const float2*>(dz + e_off);
+        const float ee[2] = {e2.x, e2.y};
+        float dzz[2] = {dz2.x, dz2.y};
+        const bool present[2] = {p_img[g], p_txt[g]};
+        Poe r[2];
+        float zz[2], sd[2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float m[2] = {present[0] ? mi[c] : 0.f, present[1] ? mt[c] : 0.f};
+          const PoePart parts[2] = {pi[c], pt[c]};
+          r[c] = poe_combine<false>(kMode, prior, m, parts, present);
+          sd[c] = sqrtf(r[c].pd_var);
+          zz[c] = ee[c] * sd[c] + r[c].mu;
+        }
+        // text decoder first Linear: dz += dT1 * Wt1, dWt1 += dT1^T z
+#pragma unroll
+        for (int j = 0; j < kTD; ++j) {
+          const float dj = __shfl_sync(0xffffffffu, dt_mine, g * kTD + j);
+          const float2 wj = *reinterpret_cast<const float2*>(s_w + j * n + k);
+          dzz[0] = fmaf(dj, wj.x, dzz[0]);
+          dzz[1] = fmaf(dj, wj.y, dzz[1]);
+          r_w1[j][0] = fmaf(dj, zz[0], r_w1[j][0]);
+          r_w1[j][1] = fmaf(dj, zz[1], r_w1[j][1]);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          // z = mu + eps*exp(logvar/2);  KL = c * -0.5 * sum(1 + logvar - mu^2 - exp(logvar))
+          const float dmu = dzz[c] + 0.f + c_kl[g] * r[c].mu;
+          float dlv = 0.f + 0.5f * c_kl[g] * (r[c].pd_var - 1.f);
+          dlv += dzz[c] * 0.5f * ee[c] * sd[c];
+          float dm = 0.f, dl = 0.f;
+          if (present[0]) {
+            poe_grad(kMode, poe_eps, r[c], 0, mi[c], dmu, dlv, dm, dl);
+            a_mi[c] += dm;
+            a_li[c] += dl;
+          }
+          if (present[1]) {
+            poe_grad(kMode, poe_eps, r[c], 1, mt[c], dmu, dlv, dm, dl);
+            a_mt[c] += dm;
+            a_lt[c] += dl;
+          }
+        }
+      }
+    }
+    ZT* de = d_enc + static_cast<long long>(b) * two_n + k;
+    store_pair(de, a_mi[0], a_mi[1]);
+    store_pair(de + n, a_li[0], a_li[1]);
+    r_eb[0] += a_mi[0]; r_eb[1] += a_mi[1]; r_eb[2] += a_li[0]; r_eb[3] += a_li[1];
+    float2* tmp_m = reinterpret_cast<float2*>(my_tab + label * two_n);
+    float2* tmp_l = reinterpret_cast<float2*>(my_tab + label * two_n + n);
+    float2 vm = *tmp_m, vl = *tmp_l;
+    vm.x += a_mt[0]; vm.y += a_mt[1]; vl.x += a_lt[0]; vl.y += a_lt[1];
+    *tmp_m = vm;
+    *tmp_l = vl;
+  }
+  __syncthreads();
+  // the block's text-expert table: sum of the warps' tables, one global reduction per touched entry
+  for (int i = threadIdx.x; i < kTab; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kT3Warps; ++ww) t += sm[ww * kTab + i];
+    if (t != 0.f) atomicAdd(a.d_txt_table + i, t);
+  }
+  __syncthreads();
+  // weight gradient of the text decoder's first Linear [10][n] and the bias gradient of the image encoder's last Linear [2n]:
+  // per-lane registers -> this warp's (now free) table -> sum over the warps
+  {
+    float* mine = sm + warp * kTab;
+#pragma unroll
+    for (int j = 0; j < kTD; ++j) *reinterpret_cast<float2*>(mine + j * n + k) = make_float2(r_w1[j][0], r_w1[j][1]);
+    *reinterpret_cast<float2*>(mine + kTD * n + k) = make_float2(r_eb[0], r_eb[1]);
+    *reinterpret_cast<float2*>(mine + kTD * n + n + k) = make_float2(r_eb[2], r_eb[3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kTD * n + two_n; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kT3Warps; ++ww) t += sm[ww * kTab + i];
+    if (i < kTD * n) atomicAdd(a.d_wt1 + i, t);
+    else if (a.d_enc_bias != nullptr) atomicAdd(a.d_enc_bias + (i - kTD * n), t);
+  }
+  // BatchNorm affine gradients of the text decoder: dgamma = sum_g S1, dbeta = sum_g S0 (block 0 only)
+  if (blockIdx.x == 0 && threadIdx.x < kTD && a.d_t1_gamma != nullptr) {
     float dg = 0.f, db = 0.f;
     for (int gg = 0; gg < G; ++gg) {
       dg += a.t1_s1[gg * kTD + threadIdx.x];
@@ -976,6 +1404,29 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
   if (check_tail(a)) return 1;
   MVAE_REQUIRE(a.z != nullptr, "tail_forward: z output missing");
   MVAE_REQUIRE(a.wt1 == nullptr || (a.bt1 && a.t1pre && a.t1_sum && a.t1_sumsq), "tail_forward: text decoder buffers missing");
+  static const int use_fast = env_int("MVAE_TAIL_FAST", 1);
+  if (use_fast && a.n == kT3N && a.training && a.z_in == nullptr && a.mu == nullptr && a.wt1 != nullptr && a.enc_img != nullptr &&
+      a.txt_table != nullptr && a.labels != nullptr && (a.eps != nullptr || a.noise_buf != nullptr)) {
+    const int blocks3 = std::max(1, std::min((a.B + kT3Warps - 1) / kT3Warps, 148 * 2));
+    const bool ref = a.poe_mode == MVAE_POE_REF;
+    if (a.z_dtype == MVAE_F32)
+      return ref ? launch_kernel(tail_fwd3_kernel<float, MVAE_POE_REF>, dim3(blocks3), dim3(32 * kT3Warps), 0, st, a)
+                 : launch_kernel(tail_fwd3_kernel<float, MVAE_POE_PRECISION>, dim3(blocks3), dim3(32 * kT3Warps), 0, st, a);
+    return ref ? launch_kernel(tail_fwd3_kernel<__nv_bfloat16, MVAE_POE_REF>, dim3(blocks3), dim3(32 * kT3Warps), 0, st, a)
+               : launch_kernel(tail_fwd3_kernel<__nv_bfloat16, MVAE_POE_PRECISION>, dim3(blocks3), dim3(32 * kT3Warps), 0, st, a);
+  }
+  if (a.n <= 64) {
+    // one warp per sample (all terms): every warp resident at once for the batch sizes of the MNIST configurations
+    static const int wpb = env_int("MVAE_TAIL_WARPS", 14);
+    if (wpb == 14) {
+      const int blocks2 = std::max(1, std::min((a.B + 13) / 14, 148 * 2));
+      if (a.z_dtype == MVAE_F32) return launch_kernel(tail_fwd2_kernel<float, 14>, dim3(blocks2), dim3(32 * 14), 0, st, a);
+      return launch_kernel(tail_fwd2_kernel<__nv_bfloat16, 14>, dim3(blocks2), dim3(32 * 14), 0, st, a);
+    }
+    const int blocks2 = std::max(1, std::min((a.B + 3) / 4, 148 * 7));
+    if (a.z_dtype == MVAE_F32) return launch_kernel(tail_fwd2_kernel<float, 4>, dim3(blocks2), dim3(32 * 4), 0, st, a);
+    return launch_kernel(tail_fwd2_kernel<__nv_bfloat16, 4>, dim3(blocks2), dim3(32 * 4), 0, st, a);
+  }
   const long long items = static_cast<long long>(a.G) * a.B;
   int blocks = static_cast<int>(std::min<long long>((items + kTailWarps - 1) / kTailWarps, 148 * 8));
   if (blocks < 1) blocks = 1;
@@ -985,19 +1436,39 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
 
 int launch_tail_backward(const TailArgs& a, cudaStream_t st) {
   if (check_tail(a)) return 1;
+  static const int use_fast = env_int("MVAE_TAIL_FAST", 1);
+  if (use_fast && a.n == kT3N && a.training && a.z_in == nullptr && a.dz != nullptr && a.dmu_up == nullptr && a.dlogvar_up == nullptr &&
+      a.t1_dyhat != nullptr && a.enc_img != nullptr && a.txt_table != nullptr && a.labels != nullptr && a.d_enc != nullptr &&
+      a.d_txt_table != nullptr && a.d_wt1 != nullptr && (a.eps != nullptr || a.noise_buf != nullptr)) {
+    const int smem3 = (kT3Warps * kTD * 2 * kT3N + kTD * kT3N) * 4;
+    static bool attr3 = false;
+    if (!attr3) {
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd3_kernel<float, MVAE_POE_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd3_kernel<float, MVAE_POE_PRECISION>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd3_kernel<__nv_bfloat16, MVAE_POE_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd3_kernel<__nv_bfloat16, MVAE_POE_PRECISION>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+      attr3 = true;
+    }
+    const int blocks3 = std::max(1, std::min((a.B + kT3Warps - 1) / kT3Warps, 148 * 2));
+    const bool ref = a.poe_mode == MVAE_POE_REF;
+    if (a.z_dtype == MVAE_F32)
+      return ref ? launch_kernel(tail_bwd3_kernel<float, MVAE_POE_REF>, dim3(blocks3), dim3(32 * kT3Warps), smem3, st, a)
+                 : launch_kernel(tail_bwd3_kernel<float, MVAE_POE_PRECISION>, dim3(blocks3), dim3(32 * kT3Warps), smem3, st, a);
+    return ref ? launch_kernel(tail_bwd3_kernel<__nv_bfloat16, MVAE_POE_REF>, dim3(blocks3), dim3(32 * kT3Warps), smem3, st, a)
+               : launch_kernel(tail_bwd3_kernel<__nv_bfloat16, MVAE_POE_PRECISION>, dim3(blocks3), dim3(32 * kT3Warps), smem3, st, a);
+  }
   if (a.n <= 64 && a.n % 2 == 0) {
     // one warp per sample (all terms): the fast path for the latent sizes the MNIST configurations use
-    const int smem2 = (kBwd2Warps * kTD * 2 * a.n + kTD * a.n + kMaxGroups * 4 * kTD + kTD * a.n + 2 * a.n) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd2_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      MVAE_CUDA(cudaFuncSetAttribute(tail_bwd2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_set = true;
+    const int smem2 = (kTD * 2 * a.n + kTD * a.n + kMaxGroups * 4 * kTD + kTD * a.n + 2 * a.n) * 4;
+    static const int wpb = env_int("MVAE_TAIL_WARPS", 14);
+    if (wpb == 14) {
+      const int blocks2 = std::max(1, std::min((a.B + 13) / 14, 148 * 2));
+      if (a.z_dtype == MVAE_F32) return launch_kernel(tail_bwd2_kernel<float, 14>, dim3(blocks2), dim3(32 * 14), smem2, st, a);
+      return launch_kernel(tail_bwd2_kernel<__nv_bfloat16, 14>, dim3(blocks2), dim3(32 * 14), smem2, st, a);
     }
-    int blocks2 = std::min((a.B + kBwd2Warps - 1) / kBwd2Warps, 148 * 2);
-    if (blocks2 < 1) blocks2 = 1;
-    if (a.z_dtype == MVAE_F32) return launch_kernel(tail_bwd2_kernel<float>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
-    return launch_kernel(tail_bwd2_kernel<__nv_bfloat16>, dim3(blocks2), dim3(32 * kBwd2Warps), smem2, st, a);
+    const int blocks2 = std::max(1, std::min((a.B + 3) / 4, 148 * 7));
+    if (a.z_dtype == MVAE_F32) return launch_kernel(tail_bwd2_kernel<float, 4>, dim3(blocks2), dim3(32 * 4), smem2, st, a);
+    return launch_kernel(tail_bwd2_kernel<__nv_bfloat16, 4>, dim3(blocks2), dim3(32 * 4), smem2, st, a);
   }
   const int smem_floats = kTD * 2 * a.n + kTD * a.n + 2 * a.n + kMaxGroups * 4 * kTD +
                           2 * kBwdRows * kMaxGroups * 2 * a.n + kBwdRows;
