@@ -34,6 +34,25 @@ __device__ __forceinline__ float2 normal_pair(unsigned long long seed, uint32_t 
   return make_float2(rad * c, rad * s);
 }
 
+// Four standard normals from ONE Philox call (all four output words): two Box-Muller pairs.  `tag` separates streams.
+__device__ __forceinline__ float4 normal_quad(unsigned long long seed, uint32_t step, unsigned long long index, uint32_t tag) {
+  uint32_t r[4];
+  philox4x32(static_cast<uint32_t>(index), static_cast<uint32_t>(index >> 32), step, tag, static_cast<uint32_t>(seed),
+             static_cast<uint32_t>(seed >> 32), r);
+  float o[4];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float u1 = (static_cast<float>(r[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = (static_cast<float>(r[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * __logf(u1));
+    float sn, cs;
+    __sincosf(6.283185307179586f * u2, &sn, &cs);
+    o[2 * h] = rad * cs;
+    o[2 * h + 1] = rad * sn;
+  }
+  return make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // Fast SFU forms (ex2/lg2/rcp.approx + one FMA): relative error ~1e-6 for the magnitudes that occur here
 // (|logvar| < ~20), far inside the parity tolerances; the tail kernels are instruction-bound, these cut the
 // transcendental cost 5x.

@@ -730,6 +730,8 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailA
   const float* __restrict__ eps = a.eps;
   float* __restrict__ noise_buf = a.noise_buf;
   ZT* __restrict__ zout = reinterpret_cast<ZT*>(a.z);
+  float* __restrict__ mu_out = a.mu;
+  float* __restrict__ lv_out = a.logvar;
   float2 w[kTD];
 #pragma unroll
   for (int j = 0; j < kTD; ++j) w[j] = *reinterpret_cast<const float2*>(a.wt1 + j * n + k);
@@ -750,6 +752,26 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailA
     const float mi[2] = {im.x, im.y}, mt[2] = {tm.x, tm.y};
     const PoePart pi[2] = {poe_part(il.x, poe_eps), poe_part(il.y, poe_eps)};
     const PoePart pt[2] = {poe_part(tl.x, poe_eps), poe_part(tl.y, poe_eps)};
+    // the draws of all terms: injected, or two Philox calls per lane (four normals each: terms 0 and 1, term 2)
+    float2 e_all[kMaxGroups];
+    if (eps != nullptr) {
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g)
+        e_all[g] = g < G ? *reinterpret_cast<const float2*>(eps + (static_cast<long long>(g) * B + b) * n + k) : make_float2(0.f, 0.f);
+    } else {
+      const unsigned long long pair = (static_cast<unsigned long long>(b) * n + k) >> 1;
+      const float4 q = normal_quad(a.seed, step, pair, 0x6d766166u);
+      e_all[0] = make_float2(q.x, q.y);
+      e_all[1] = make_float2(q.z, q.w);
+      e_all[2] = make_float2(0.f, 0.f);
+      if (G > 2) {
+        const float4 q2 = normal_quad(a.seed, step, pair, 0x6d766167u);
+        e_all[2] = make_float2(q2.x, q2.y);
+      }
+#pragma unroll
+      for (int g = 0; g < kMaxGroups; ++g)
+        if (g < G) *reinterpret_cast<float2*>(noise_buf + (static_cast<long long>(g) * B + b) * n + k) = e_all[g];
+    }
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -757,25 +779,25 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailA
     for (int g = 0; g < kMaxGroups; ++g) {
       if (g < G) {
         const long long e_off = (static_cast<long long>(g) * B + b) * n + k;
-        float2 e2;
-        if (eps != nullptr) {
-          e2 = *reinterpret_cast<const float2*>(eps + e_off);
-        } else {
-          e2 = normal_pair(a.seed, step, e_off >> 1);
-          *reinterpret_cast<float2*>(noise_buf + e_off) = e2;
-        }
+        const float2 e2 = e_all[g];
         const float ee[2] = {e2.x, e2.y};
         const bool present[2] = {p_img[g], p_txt[g]};
-        float zz[2];
+        float zz[2], mm[2], ll[2];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           const float m[2] = {mi[c], mt[c]};
           const PoePart parts[2] = {pi[c], pt[c]};
           const Poe r = poe_combine<true>(kMode, prior, m, parts, present);
+          mm[c] = r.mu;
+          ll[c] = r.logvar;
           zz[c] = ee[c] * sqrtf(r.pd_var) + r.mu;                    // reparametrize (mnist/model.py:25-28)
           klacc[g] += 1.f + r.logvar - r.mu * r.mu - r.pd_var;       // KL integrand of mnist/train.py:79
         }
         store_pair(zout + e_off, zz[0], zz[1]);
+        if (mu_out != nullptr) {
+          *reinterpret_cast<float2*>(mu_out + e_off) = make_float2(mm[0], mm[1]);
+          *reinterpret_cast<float2*>(lv_out + e_off) = make_float2(ll[0], ll[1]);
+        }
 #pragma unroll
         for (int j = 0; j < kTD; ++j) v[g * kTD + j] = fmaf(zz[0], w[j].x, zz[1] * w[j].y);
       }
@@ -870,6 +892,14 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_bwd3_kernel(const TailA
   float* my_tab = sm + warp * kTab + k;
 
   for (int b = blockIdx.x * kT3Warps + warp; b < B; b += gridDim.x * kT3Warps) {
+    // every global load of the sample is issued before the first use (one sample per warp: nothing else hides the latency)
+    float2 e_all[kMaxGroups], dz_all[kMaxGroups];
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+      const long long e_off = (static_cast<long long>(g < G ? g : 0) * B + b) * n + k;
+      e_all[g] = *reinterpret_cast<const float2*>(noise + e_off);
+      dz_all[g] = *reinterpret_cast<const float2*>(dz + e_off);
+    }
     float dt_mine = 0.f;
     if (owner) {
       const float x = my_t1[static_cast<long long>(b) * kTD];
@@ -889,9 +919,8 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_bwd3_kernel(const TailA
 #pragma unroll
     for (int g = 0; g < kMaxGroups; ++g) {
       if (g < G) {
-        const long long e_off = (static_cast<long long>(g) * B + b) * n + k;
-        const float2 e2 = *reinterpret_cast<const float2*>(noise + e_off);
-        const float2 dz2 = *reinterpret_cast<const float2*>(dz + e_off);
+        const float2 e2 = e_all[g];
+        const float2 dz2 = dz_all[g];
         const float ee[2] = {e2.x, e2.y};
         float dzz[2] = {dz2.x, dz2.y};
         const bool present[2] = {p_img[g], p_txt[g]};
@@ -1405,8 +1434,10 @@ int launch_tail_forward(const TailArgs& a, cudaStream_t st) {
   MVAE_REQUIRE(a.z != nullptr, "tail_forward: z output missing");
   MVAE_REQUIRE(a.wt1 == nullptr || (a.bt1 && a.t1pre && a.t1_sum && a.t1_sumsq), "tail_forward: text decoder buffers missing");
   static const int use_fast = env_int("MVAE_TAIL_FAST", 1);
-  if (use_fast && a.n == kT3N && a.training && a.z_in == nullptr && a.mu == nullptr && a.wt1 != nullptr && a.enc_img != nullptr &&
+  if (use_fast && a.n == kT3N && a.training && a.z_in == nullptr && a.wt1 != nullptr && a.enc_img != nullptr &&
       a.txt_table != nullptr && a.labels != nullptr && (a.eps != nullptr || a.noise_buf != nullptr)) {
+    // (without injected draws this kernel uses its own Philox stream - normal_quad - and always leaves the draws in noise_buf:
+    //  every backward kernel reads them from there)
     const int blocks3 = std::max(1, std::min((a.B + kT3Warps - 1) / kT3Warps, 148 * 2));
     const bool ref = a.poe_mode == MVAE_POE_REF;
     if (a.z_dtype == MVAE_F32)
