@@ -454,8 +454,14 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     if (fwd) MVAE_STEP(launch_step_prep(adam_tick, noise_tick, W.at<float>(P.acc_off), P.acc_floats,
                                         reinterpret_cast<long long*>(a->num_batches_tracked), inc, st), "launch_step_prep");
   }
-  if (fwd && bwd && a->zero_grad)
-    MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, st));
+  // zero_grad: nothing adds into the gradient buffer before the decoders run, so the memset goes beside the encoder forward
+  // (side stream, joined after the tail forward)
+  bool grads_zeroing = false;
+  if (fwd && bwd && a->zero_grad) {
+    if (dep(st, s2)) return 1;
+    MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, s2));
+    grads_zeroing = s2 != st;
+  }
 
   float* st_e1 = W.at<float>(P.st_e1); float* st_e2 = W.at<float>(P.st_e2);
   float* st_d1 = W.at<float>(P.st_d1); float* st_d2 = W.at<float>(P.st_d2); float* st_t1 = W.at<float>(P.st_t1);
@@ -540,6 +546,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   ta.kl = losses + 2 * kMaxGroups;
   ta.t1pre = W.at<float>(P.t1pre); ta.t1_sum = st_t1; ta.t1_sumsq = st_t1 + G * 10;
   if (fwd) MVAE_STEP(launch_tail_forward(ta, st), "launch_tail_forward#8");
+  if (grads_zeroing && dep(s2, st)) return 1;   // join: the gradient buffer is clear before the first kernel that adds into it
 
   TextDecArgs td;
   td.B = B; td.G = G;
@@ -707,6 +714,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
                             a->adam_eps, a->adam_step, a->grad_scale, 0, s2), "launch_adam(decoders)");
     }
   }
+  long long e1w_floats = 0, adam_tail_floats = 0;   // > 0: the final Adam launch only covers [0, adam_tail_floats)
   if (bwd && bwd_enc) {
     if (!bwd_dec && dep(st, s2)) return 1;
     if (!bwd_dec && dep(st, s3)) return 1;
@@ -738,8 +746,19 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       if (dep(st, s2)) return 1;
       if (dep(st, s3)) return 1;
       // the last two weight gradients are what is left of the step: side by side on the two side streams
+      if (adam_split && dep(s2, s3)) return 1;   // (the weight gradient of the last encoder Linear sits on s2)
       MVAE_STEP(gemm_wgrad(dt, B, 400, 784, W.at<void>(P.dye1), a->image, gf("image_encoder.net.0.weight"), s2), "gemm_wgrad:image_encoder.net.0.weight#31");
       MVAE_STEP(gemm_wgrad(dt, B, 200, 400, W.at<void>(P.dye2), W.at<void>(P.h1), gf("image_encoder.net.3.weight"), s3), "gemm_wgrad:image_encoder.net.3.weight#29");
+      // every encoder gradient except the first Linear's weight is final once that GEMM is done: their Adam runs here, beside
+      // the last weight gradient, and only the first Linear's weight (the head of the encoder bucket) is left for the end
+      e1w_floats = L.find("image_encoder.net.0.weight") == 0 ? round_up(400ll * 784, kAlignFloats) : 0;
+      if (adam_split && e1w_floats > 0) {
+        const long long e0 = e1w_floats, ne = L.enc_floats - e1w_floats;
+        MVAE_STEP(launch_adam(prm + e0, a->grads + e0, a->adam_m + e0, a->adam_v + e0,
+                              a->params_bf16 ? static_cast<__nv_bfloat16*>(a->params_bf16) + e0 : nullptr, ne, a->lr, a->beta1, a->beta2,
+                              a->adam_eps, a->adam_step, a->grad_scale, 0, s3), "launch_adam(encoders but the first weight)");
+        adam_tail_floats = e1w_floats;
+      }
     }
     if (n_img > 0 && !use_chain) {
       MVAE_STEP(gemm_dgrad(dt, B, 200, 2 * n, W.at<void>(P.denc), wop("image_encoder.net.6.weight"), W.at<void>(P.dye2), dt,
@@ -770,7 +789,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
 
   if (bwd && bwd_enc && a->do_adam) {
     MVAE_REQUIRE(a->adam_m && a->adam_v && a->adam_step, "mnist_step: Adam state missing");
-    MVAE_STEP(launch_adam(prm, a->grads, a->adam_m, a->adam_v, a->params_bf16, adam_split ? L.enc_floats : L.param_floats, a->lr,
+    MVAE_STEP(launch_adam(prm, a->grads, a->adam_m, a->adam_v, a->params_bf16, adam_tail_floats > 0 ? adam_tail_floats : (adam_split ? L.enc_floats : L.param_floats), a->lr,
                     a->beta1, a->beta2, a->adam_eps, a->adam_step, a->grad_scale, 0, st), "launch_adam#33");
   }
   return 0;
