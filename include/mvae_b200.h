@@ -91,6 +91,8 @@ typedef struct mvae_gemm_args {
   float bce_scale[4];
   float* bce_loss;
   void* bce_probs;
+  const float* bce_row_weight; /* optional [M] fp32: row m's loss and gradient are scaled by bce_row_weight[m] (per-sample
+                                  missing-modality masks: 0 switches the row off, B / present-rows renormalises the mean) */
 } mvae_gemm_args;
 int mvae_gemm(const mvae_gemm_args* args, void* stream);
 /* Bring-up: GEMM launches whose epilogue kind (0 store, 1 atomic, 2 BCE, 3 dgrad-BN) equals epilogue_kind write
@@ -393,9 +395,18 @@ typedef struct mvae_latent_args {
   int dz_dtype; const void* dz; int64_t ld_dz;
   const float* d_mu; const float* d_logvar; /* optional upstream gradients [n_terms, batch, n_latents] */
   int d_dtype; void* d_expert_a; int64_t ld_da; void* d_expert_b; int64_t ld_db;
+  const float* row_weight;   /* optional [n_terms * batch] fp32: scales kl_weight[g] for row (g, b) (per-sample masks) */
 } mvae_latent_args;
 int mvae_latent_forward(const mvae_latent_args* args, void* stream);
 int mvae_latent_backward(const mvae_latent_args* args, void* stream);
+
+/* Per-sample missing-modality masks -> per-(term, row) weights, on the device (no host sync, CUDA-graph capturable):
+ *   term g is ACTIVE on row b iff the modalities it needs are present (joint: both, image: has_image, text: has_text);
+ *   weight[g * batch + b] = active ? batch / count_g : 0, count_g = active rows of term g (weight 0 everywhere if count_g = 0),
+ * so that a loss kernel scaling by lambda / batch * weight yields the mean over the term's own rows
+ * (mnist/paired_weak.py:82-104 per row instead of per batch).  counts (optional) [n_terms] receives count_g as floats. */
+int mvae_mask_weights(const uint8_t* has_image, const uint8_t* has_text, int64_t batch, int n_terms, const int* term_type,
+                      float* weight, float* counts, void* stream);
 
 /* dst[r, c] = src[r, c] for c < cols, 0 for cols <= c < ld_dst: GEMM-operand copies of weights whose row length does
  * not meet the 16-byte TMA stride rule (e.g. Linear(18, 64), Linear(100, 6400) in bf16). */
@@ -453,6 +464,7 @@ typedef struct mvae_logsoftmax_nll_args {
   float* logp; int64_t ld_logp;
   int64_t* argmax;
   int grad_dtype; void* dlogits; int64_t ld_dlogits;
+  const float* row_weight;   /* optional [rows] fp32: scales row m's loss and gradient (per-sample masks) */
 } mvae_logsoftmax_nll_args;
 int mvae_logsoftmax_nll(const mvae_logsoftmax_nll_args* args, void* stream);
 

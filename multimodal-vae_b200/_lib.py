@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
         ("x3_scratch", c_void_p), ("x3_scratch_bytes", c_int64),
         ("act", c_int), ("act_out", c_void_p), ("act_pre", c_void_p), ("ld_act_pre", c_int64),
         ("bce_target", c_void_p), ("ld_bce_target", c_int64), ("bce_target_rows", c_int), ("bce_scale", c_float * 4),
-        ("bce_loss", c_void_p), ("bce_probs", c_void_p),
+        ("bce_loss", c_void_p), ("bce_probs", c_void_p), ("bce_row_weight", c_void_p),
     ]
 
 
@@ -169,7 +169,7 @@ class LatentArgs(C.Structure):
                 ("dz_dtype", c_int), ("dz", c_void_p), ("ld_dz", c_int64),
                 ("d_mu", c_void_p), ("d_logvar", c_void_p),
                 ("d_dtype", c_int), ("d_expert_a", c_void_p), ("ld_da", c_int64),
-                ("d_expert_b", c_void_p), ("ld_db", c_int64)]
+                ("d_expert_b", c_void_p), ("ld_db", c_int64), ("row_weight", c_void_p)]
 
 
 class GruCellArgs(C.Structure):
@@ -191,7 +191,7 @@ class LogSoftmaxNllArgs(C.Structure):
                 ("target", c_void_p), ("target_stride", c_int64), ("target_rows", c_int64),
                 ("grad_scale", c_float * 3), ("loss", c_void_p),
                 ("logp", c_void_p), ("ld_logp", c_int64), ("argmax", c_void_p),
-                ("grad_dtype", c_int), ("dlogits", c_void_p), ("ld_dlogits", c_int64)]
+                ("grad_dtype", c_int), ("dlogits", c_void_p), ("ld_dlogits", c_int64), ("row_weight", c_void_p)]
 
 
 class ConvTClass(C.Structure):

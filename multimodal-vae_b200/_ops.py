@@ -44,7 +44,7 @@ def gemm(A, B, Cout, M, N, K, lda, ldb, ldc, a_major=0, b_major=0, bias=None, ac
         a.bce_target, a.ld_bce_target, a.bce_target_rows = bce["target"].data_ptr(), int(bce["ld_target"]), int(bce["target_rows"])
         for i, v in enumerate(bce["scale"]):
             a.bce_scale[i] = float(v)
-        a.bce_loss, a.bce_probs = _p(bce.get("loss")), _p(bce.get("probs"))
+        a.bce_loss, a.bce_probs, a.bce_row_weight = _p(bce.get("loss")), _p(bce.get("probs")), _p(bce.get("row_weight"))
     a.bias = _p(bias)
     a.accumulate = 1 if accumulate else 0
     a.col_sum, a.col_sumsq = _p(col_sum), _p(col_sumsq)
@@ -204,6 +204,14 @@ def sigmoid_bce(logits, ld_logits, rows, cols, rows_per_group=0, target=None, ld
     _lib.check(_lib.load().mvae_sigmoid_bce(C.byref(a), stream()), "mvae_sigmoid_bce")
 
 
+def mask_weights(has_image, has_text, batch, term_types, weight, counts=None):
+    """Per-(term, row) loss weights batch / count from uint8 presence masks, on the device (mvae_mask_weights)."""
+    tt = (C.c_int * len(term_types))(*[int(t) for t in term_types])
+    _lib.check(_lib.load().mvae_mask_weights(C.c_void_p(has_image.data_ptr()), C.c_void_p(has_text.data_ptr()), C.c_int64(int(batch)),
+                                             len(term_types), tt, C.c_void_p(weight.data_ptr()), C.c_void_p(_p(counts) or 0), stream()),
+               "mvae_mask_weights")
+
+
 def cast_pad_2d(src, rows, cols, ld_src, dst, ld_dst):
     _lib.check(_lib.load().mvae_cast_pad_2d(src.data_ptr(), int(rows), int(cols), int(ld_src), DT[dst.dtype], dst.data_ptr(),
                                             int(ld_dst), stream()), "mvae_cast_pad_2d")
@@ -270,7 +278,7 @@ def gru_cell_backward(a: _lib.GruCellArgs, dh_a, ld_dh_a, dh_b, ld_dh_b, dgi, dg
 
 def logsoftmax_nll(logits, ld_logits, rows, classes, rows_per_group=0, target=None, target_offset=0, target_stride=1,
                    target_rows=0, grad_scale=(0.0, 0.0, 0.0), loss=None, logp=None, logp_offset=0, ld_logp=0, argmax=None,
-                   dlogits=None, ld_dlogits=0):
+                   dlogits=None, ld_dlogits=0, row_weight=None):
     a = _lib.LogSoftmaxNllArgs()
     a.rows, a.classes, a.rows_per_group = int(rows), int(classes), int(rows_per_group)
     a.logits, a.ld_logits = logits.data_ptr(), int(ld_logits)
@@ -284,6 +292,7 @@ def logsoftmax_nll(logits, ld_logits, rows, classes, rows_per_group=0, target=No
     a.argmax = _p(argmax)
     if dlogits is not None:
         a.grad_dtype, a.dlogits, a.ld_dlogits = DT[dlogits.dtype], dlogits.data_ptr(), int(ld_dlogits)
+    a.row_weight = _p(row_weight)
     _lib.check(_lib.load().mvae_logsoftmax_nll(C.byref(a), stream()), "mvae_logsoftmax_nll")
 
 

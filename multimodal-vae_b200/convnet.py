@@ -585,6 +585,8 @@ class ConvMVAEBase:
         la.eps = None if eps is None else eps.data_ptr()
         la.seed, la.step_counter = self.noise_seed, self._step_counter.data_ptr()
         la.training = 1 if training else 0
+        rw = getattr(ws, "row_weight", None)                 # per-(term, row) weights of a masked step, or None
+        la.row_weight = None if rw is None else rw.data_ptr()
         la.z_dtype, la.z, la.ld_z = _ops.DT[self.act_dtype], ws.z.data_ptr(), ws.ld_z
         la.mu, la.logvar, la.kl = ws.mu.data_ptr(), ws.logvar.data_ptr(), ws.acc[2].data_ptr()
         ws.latent = la
@@ -708,7 +710,9 @@ class ConvMVAETrainer:
         m.run_forward(ws, image, other, term_types, eps, True, lambdas, klw, False, True)
         m.backward_decoders(ws)
         split = m.encoder_param_floats
-        if self.world > 1 and self.overlap:
+        if getattr(self, "_defer_reduce", False):
+            m.backward_encoders(ws)       # accumulated step (step_masked): the caller reduces once, after the last class
+        elif self.world > 1 and self.overlap:
             main = torch.cuda.current_stream(m.device)
             self.comm_stream.wait_stream(main)
             with torch.cuda.stream(self.comm_stream):
@@ -746,7 +750,7 @@ class ConvMVAETrainer:
         # every scalar baked into the captured kernel arguments is part of the key (anneal_kl / adjust_learning_rate of
         # multimnist/train.py:227-241 mutate kl_lambda / lr between steps); the cache is bounded
         key = (B, tt, lambdas, eps is not None, adam, float(self.kl_lambda), float(self.lr), tuple(map(float, self.betas)),
-               float(self.eps))
+               float(self.eps), getattr(self, "_key_extra", None))
         if key not in self._graphs:
             while len(self._graphs) >= 16:
                 self._graphs.pop(next(iter(self._graphs)))
@@ -777,6 +781,57 @@ class ConvMVAETrainer:
             st_eps.copy_(eps, non_blocking=True)
         g.replay()
         return ws.acc
+
+    # (class, term indices into list(model.TERMS), lambdas): celeba has no paired_weak script; these are the per-class loss calls
+    # of multimnist/paired_weak.py:85-110 (paired rows: three terms; unpaired rows: each modality's own term)
+    _MASK_CLASSES = (("paired", (0, 1, 2), ((1.0, 1.0), (1.0, 1.0), (0.0, 1.0))),
+                     ("image_only", (1,), ((1.0, 0.0),)),
+                     ("other_only", (2,), ((0.0, 1.0),)))
+
+    def step_masked(self, image, other, has_image, has_other, eps: Optional[torch.Tensor] = None, update: bool = True):
+        """One optimizer step over a batch that MIXES paired and unpaired samples (the reference flips a coin per
+        batch, multimnist/paired_weak.py:85-110).  `has_image`, `has_other`: [B] bool.  Rows are compacted by presence class on
+        the device and each class runs the step on its own rows - paired rows: joint + image + second-modality terms, image-only
+        rows: the image term, other-only rows: the second modality's term; rows with neither are skipped - so every loss is a mean
+        over its own rows and BatchNorm only ever sees present rows, exactly what the reference computes when it is fed the three
+        subsets as three batches; the gradients accumulate, the data-parallel all-reduce and ONE Adam update follow.  Eager (the
+        class sizes are data dependent and train-mode BatchNorm statistics need compacted rows: one host sync per class); classes
+        with fewer than two rows are skipped (BatchNorm).  `eps`: optional [3, B, n].  Returns {class: losses()}."""
+        m = self.model
+        names = list(m.TERMS)
+        dev = m.device
+        hi = torch.as_tensor(has_image).to(dev).bool().reshape(-1)
+        ho = torch.as_tensor(has_other).to(dev).bool().reshape(-1)
+        image, other = self._prepare(image, other)
+        if hi.numel() != image.shape[0] or ho.numel() != image.shape[0]:
+            raise ValueError("has_image / has_other must have one entry per sample")
+        if eps is not None:
+            eps = eps.to(dev, torch.float32)
+        rows = {"paired": hi & ho, "image_only": hi & ~ho, "other_only": ~hi & ho}
+        out = {}
+        m.flat_grads.zero_()
+        self._defer_reduce = True
+        try:
+            for cname, term_idx, lambdas in self._MASK_CLASSES:
+                idx = torch.nonzero(rows[cname]).reshape(-1)
+                if idx.numel() < 2:
+                    continue
+                e = None if eps is None else torch.stack([eps[t].index_select(0, idx) for t in term_idx]).contiguous()
+                tt = tuple(m.TERMS[names[t]] for t in term_idx)
+                ws = m._make_workspace(int(idx.numel()), len(tt))   # private: the class sizes change from step to step
+                self._last = (ws, tt, lambdas)
+                self._enqueue(ws, image.index_select(0, idx).contiguous(), other.index_select(0, idx).contiguous(), tt, lambdas, e,
+                              adam=False)
+                out[cname] = self.losses()
+        finally:
+            self._defer_reduce = False
+        if self.world > 1:
+            dist.all_reduce(m.flat_grads, op=dist.ReduceOp.SUM, group=self.group)
+        if update and out:
+            _ops.step_begin(m._adam_counter)
+            _ops.adam_step(m.flat_params, m.flat_grads, self.adam_m, self.adam_v, m.flat_params_bf16, m.param_floats, self.lr,
+                           self.betas[0], self.betas[1], self.eps, m._adam_counter, 1.0 / self.world, True)
+        return out
 
     def teardown(self) -> None:
         self._graphs.clear()

@@ -224,6 +224,7 @@ static int gemm_entry(const mvae_gemm_args* a, const mvae_conv_geometry* cg, int
     for (int t = 0; t < 4; ++t) g.epi.bce_scale[t] = a->bce_scale[t];
     g.epi.loss = a->bce_loss;
     g.epi.probs = a->bce_probs;
+    g.epi.row_w = a->bce_row_weight;
   }
   note_launch(1);
   return launch_gemm(g, static_cast<cudaStream_t>(stream));

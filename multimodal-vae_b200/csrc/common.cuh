@@ -56,6 +56,7 @@ struct GemmEpilogue {
   float bce_scale[4] = {0, 0, 0, 0};
   float* loss = nullptr;   // [groups]
   void* probs = nullptr;   // optional sigmoid(x) output, same layout/dtype as C
+  const float* row_w = nullptr;  // EPI_BCE: optional [M] per-row weight of loss and gradient (per-sample masks)
   // EPI_STORE_ACT (Linear + bias + Swish in one pass): C = pre = acc + bias (kept for the backward, may be null),
   //   probs = pre * sigmoid(pre) - the next layer's operand (same layout/dtype as C)
   // EPI_DGRAD_ACT (input gradient through a Swish): C = acc * swish'(hpre), stat0[col] += sum_rows C (= the bias

@@ -840,6 +840,7 @@ struct LatentArgs {
   const float* dmu_up; const float* dlogvar_up;      // optional [G, B, n]
   void* d_enc_a; long long ld_da; int d_dtype;       // rows like enc_a
   void* d_enc_b; long long ld_db;
+  const float* row_w;                                // optional [G * B]: scales kl_weight[g] per row
 };
 
 template <bool kBackward>
@@ -873,6 +874,7 @@ __global__ void __launch_bounds__(kThreads) latent_kernel(const LatentArgs a) {
       }
       const Poe r = poe_eval<true>(a.poe_mode, a.prior, a.poe_eps, m, lv, present);
       const long long e = (static_cast<long long>(g) * a.B + b) * a.n + j;
+      const float klw = a.row_w != nullptr ? a.kl_weight[g] * a.row_w[static_cast<long long>(g) * a.B + b] : a.kl_weight[g];
       float noise = 0.f;
       if (a.training) {
         if (a.eps != nullptr) {
@@ -893,14 +895,13 @@ __global__ void __launch_bounds__(kThreads) latent_kernel(const LatentArgs a) {
           a.logvar[e] = r.logvar;
         }
         // -0.5 * (1 + logvar - mu^2 - exp(logvar)), celeba/train.py:79
-        klacc[g] += a.kl_weight[g] * (-0.5f) * (1.f + r.logvar - r.mu * r.mu - r.pd_var);
+        klacc[g] += klw * (-0.5f) * (1.f + r.logvar - r.mu * r.mu - r.pd_var);
       } else {
         const long long row = static_cast<long long>(g) * a.B + b;
         float dzv = 0.f;
         if (a.dz != nullptr) dzv = ld_any(a.dz, a.dz_dtype, row * a.lddz + j);
-        float dmu = dzv + a.kl_weight[g] * r.mu;
-        float dlv = (a.training ? dzv * 0.5f * noise * sd : 0.f) + a.kl_weight[g] * 0.5f * (r.pd_var - 1.f);
-        if (!a.training) dmu = dzv + a.kl_weight[g] * r.mu;
+        float dmu = dzv + klw * r.mu;
+        float dlv = (a.training ? dzv * 0.5f * noise * sd : 0.f) + klw * 0.5f * (r.pd_var - 1.f);
         if (a.dmu_up != nullptr) {
           dmu += a.dmu_up[e];
           dlv += a.dlogvar_up[e];
@@ -1275,6 +1276,7 @@ static int latent_fill(const mvae_latent_args* p, LatentArgs& a) {
   a.z = p->z; a.ldz = p->ld_z; a.z_dtype = p->z_dtype; a.mu = p->mu; a.logvar = p->logvar; a.kl = p->kl;
   a.dz = p->dz; a.lddz = p->ld_dz; a.dz_dtype = p->dz_dtype; a.dmu_up = p->d_mu; a.dlogvar_up = p->d_logvar;
   a.d_enc_a = p->d_expert_a; a.ld_da = p->ld_da; a.d_enc_b = p->d_expert_b; a.ld_db = p->ld_db; a.d_dtype = p->d_dtype;
+  a.row_w = p->row_weight;
   return 0;
 }
 
@@ -1292,6 +1294,56 @@ int mvae_latent_backward(const mvae_latent_args* p, void* stream) {
   if (int rc = latent_fill(p, a)) return rc;
   MVAE_REQUIRE(a.d_enc_a != nullptr || a.d_enc_b != nullptr, "latent_backward: no gradient output");
   latent_kernel<true><<<grid_for(a.B * a.n, 4), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  MVAE_CUDA(cudaGetLastError());
+  note_launch(1);
+  return 0;
+}
+
+// Per-sample presence masks -> per-(term, row) weights batch / count (one block; see include/mvae_b200.h).
+__global__ void __launch_bounds__(1024) mask_weights_kernel(const uint8_t* __restrict__ hi, const uint8_t* __restrict__ ht, long long B,
+                                                            int G, int t0, int t1, int t2, float* __restrict__ w,
+                                                            float* __restrict__ counts) {
+  __shared__ int s_cnt[kMaxGroups];
+  if (threadIdx.x < kMaxGroups) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int ty[kMaxGroups] = {t0, t1, t2};
+  int cnt[kMaxGroups] = {0, 0, 0};
+  for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+    const bool i = hi[b] != 0, t = ht[b] != 0;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g)
+      if (g < G) cnt[g] += (ty[g] == MVAE_TERM_JOINT ? (i && t) : ty[g] == MVAE_TERM_IMAGE ? i : t) ? 1 : 0;
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxGroups; ++g) {
+    int v = cnt[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&s_cnt[g], v);
+  }
+  __syncthreads();
+  for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+    const bool i = hi[b] != 0, t = ht[b] != 0;
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g)
+      if (g < G) {
+        const bool on = ty[g] == MVAE_TERM_JOINT ? (i && t) : ty[g] == MVAE_TERM_IMAGE ? i : t;
+        w[static_cast<long long>(g) * B + b] = (on && s_cnt[g] > 0) ? static_cast<float>(B) / static_cast<float>(s_cnt[g]) : 0.f;
+      }
+  }
+  if (counts != nullptr && threadIdx.x < G) counts[threadIdx.x] = static_cast<float>(s_cnt[threadIdx.x]);
+}
+
+int mvae_mask_weights(const uint8_t* has_image, const uint8_t* has_text, int64_t batch, int n_terms, const int* term_type,
+                      float* weight, float* counts, void* stream) {
+  MVAE_REQUIRE(has_image != nullptr && has_text != nullptr && weight != nullptr && term_type != nullptr, "mask_weights: null argument");
+  MVAE_REQUIRE(batch > 0 && n_terms >= 1 && n_terms <= kMaxGroups, "mask_weights: batch / n_terms out of range");
+  int t[kMaxGroups] = {0, 0, 0};
+  for (int g = 0; g < n_terms; ++g) {
+    MVAE_REQUIRE(term_type[g] >= 0 && term_type[g] <= 2, "mask_weights: bad term type %d", term_type[g]);
+    t[g] = term_type[g];
+  }
+  mask_weights_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(has_image, has_text, batch, n_terms, t[0], t[1], t[2], weight, counts);
   MVAE_CUDA(cudaGetLastError());
   note_launch(1);
   return 0;

@@ -201,6 +201,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
           // BCE on logits: loss = softplus(x) - t*x, d/dx = sigmoid(x) - t  (reference: sigmoid then
           // F.binary_cross_entropy, mnist/model.py:135 + mnist/train.py:70; identical for |x| < ~17).
           float d[4], pr[4];
+          const float rw = e.row_w != nullptr ? __ldg(e.row_w + m + done + it + u) : 1.f;
+          const float gs = g_scale * rw;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float x = v[u][i] + bias[i];
@@ -215,11 +217,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmKParams& p, uint32_t sad
             inv = inv * fmaf(-dd, inv, 2.f);
             const float pz = x >= 0.f ? inv : ex * inv;
             pr[i] = pz;
-            d[i] = g_scale * (pz - tg);
+            d[i] = gs * (pz - tg);
             if (kFast || i < nv) {
               // softplus(x) - t*x = max(x,0) - t*x + log(1+exp(-|x|)),  log(1+exp(-|x|)) = -ln(inv)
               const float sp = fmaf(-0.6931471805599453f, ptx::lg2_approx(inv), fmaf(-tg, x, fmaxf(x, 0.f)));
-              lsum += sp;
+              lsum = fmaf(rw, sp, lsum);
               acc0[i] += d[i];
             }
           }

@@ -185,6 +185,7 @@ struct LsmArgs {
   float* logp; long long ldp;        // optional output
   long long* argmax;                 // optional [rows]
   void* dlogits; int g_dtype; long long ldd;   // scale[g] * (softmax - onehot), columns [classes, ldd) zeroed
+  const float* row_w;                // optional [rows]: weight of row m's loss and gradient
 };
 __global__ void __launch_bounds__(kThreads) logsoftmax_nll_kernel(const LsmArgs a) {
   __shared__ float s_loss[kMaxGroups];
@@ -208,10 +209,11 @@ __global__ void __launch_bounds__(kThreads) logsoftmax_nll_kernel(const LsmArgs 
       const int g = static_cast<int>(m / a.rows_per_group);
       long long t = a.target[(m % a.target_rows) * a.target_stride];
       t = t < 0 ? 0 : (t >= a.classes ? a.classes - 1 : t);
-      const float l = lse - x[t];
+      const float rw = a.row_w != nullptr ? a.row_w[m] : 1.f;
+      const float l = rw * (lse - x[t]);
       if (g == 0) acc[0] += l; else if (g == 1) acc[1] += l; else acc[2] += l;
       if (a.dlogits != nullptr) {
-        const float sc = a.scale[g];
+        const float sc = a.scale[g] * rw;
         for (int c = 0; c < a.classes; ++c)
           st_any(a.dlogits, a.g_dtype, m * a.ldd + c, sc * (expf(x[c] - lse) - (c == t ? 1.f : 0.f)));
         for (long long c = a.classes; c < a.ldd; ++c) st_any(a.dlogits, a.g_dtype, m * a.ldd + c, 0.f);
@@ -348,6 +350,7 @@ int mvae_logsoftmax_nll(const mvae_logsoftmax_nll_args* p, void* stream) {
   a.loss = p->loss; a.logp = p->logp; a.ldp = p->ld_logp;
   a.argmax = reinterpret_cast<long long*>(p->argmax);
   a.dlogits = p->dlogits; a.g_dtype = p->grad_dtype; a.ldd = p->ld_dlogits;
+  a.row_w = p->row_weight;
   MVAE_REQUIRE(a.dlogits == nullptr || a.ldd >= a.classes, "logsoftmax_nll: ld_dlogits < classes");
   logsoftmax_nll_kernel<<<grid_for(a.rows), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
   MVAE_CUDA(cudaGetLastError());

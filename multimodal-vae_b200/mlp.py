@@ -114,6 +114,12 @@ class MVAE(ConvMVAEBase):
         ws.ds2pre, ws.ds1pre = buf(M3 * h), buf(M3 * h)
         ws.tlogits, ws.logp = buf(M3 * N_CLASSES, dtype=f32), buf(M3 * N_CLASSES, dtype=f32)
         ws.dtlog = buf(M3 * ws.ld_cls)
+        # per-sample missing-modality masks (MVAETrainer.step(has_image=, has_text=)): presence flags in, per-(term, row) weights
+        ws.mask_image = torch.ones(B, device=dev, dtype=torch.uint8)
+        ws.mask_text = torch.ones(B, device=dev, dtype=torch.uint8)
+        ws.mask_weights = buf(M3, dtype=f32)
+        ws.mask_counts = buf(4, dtype=f32)
+        ws.row_weight = None          # = ws.mask_weights while a masked step runs
         return ws
 
     # ------------------------------------------------------------------ Linear (+ Swish) helpers
@@ -141,6 +147,8 @@ class MVAE(ConvMVAEBase):
         use_txt = any(t != _lib.TERM_IMAGE for t in term_types)
         ws.training, ws.use_img, ws.use_txt = training, use_img, use_txt
         ws.text = text
+        if ws.row_weight is not None:   # masks -> weights on the device: no host sync, fixed launch shapes (graph capturable)
+            _ops.mask_weights(ws.mask_image, ws.mask_text, B, term_types, ws.mask_weights, ws.mask_counts)
         if image is not None:
             _ops.cast_pad_2d(image, B, N_PIXELS, N_PIXELS, ws.x, N_PIXELS)
         ws.have_image = image is not None
@@ -176,7 +184,7 @@ class MVAE(ConvMVAEBase):
             _ops.gemm(ws.d2, w, ws.dlog, M3, N_PIXELS, h, h, ldw, N_PIXELS, bias=self.P("image_decoder.fc3.bias"),
                       col_sum=self.G("image_decoder.fc3.bias"), rows_per_group=B,
                       bce=dict(target=ws.x, ld_target=N_PIXELS, target_rows=B, scale=sx, loss=ws.acc[0],
-                               probs=None))
+                               probs=None, row_weight=ws.row_weight))
         else:
             _ops.gemm(ws.d2, w, ws.logits, M3, N_PIXELS, h, h, ldw, N_PIXELS, bias=self.P("image_decoder.fc3.bias"))
             if want_probs:
@@ -193,7 +201,8 @@ class MVAE(ConvMVAEBase):
         _ops.logsoftmax_nll(ws.tlogits, N_CLASSES, M3, N_CLASSES, rows_per_group=B,
                             target=ws.text if with_loss else None, target_rows=B, grad_scale=sy,
                             loss=ws.acc[1] if with_loss else None, logp=ws.logp, ld_logp=N_CLASSES,
-                            dlogits=ws.dtlog if with_loss else None, ld_dlogits=ws.ld_cls)
+                            dlogits=ws.dtlog if with_loss else None, ld_dlogits=ws.ld_cls,
+                            row_weight=ws.row_weight if with_loss else None)
 
     # ------------------------------------------------------------------ backward
     def backward_decoders(self, ws) -> None:
@@ -329,8 +338,32 @@ class MVAETrainer(ConvMVAETrainer):
                 text.to(m.device, torch.int64).contiguous())
 
     def step(self, image, text, terms: Sequence[str] = ("joint", "image", "text"),
-             lambdas: Sequence[Tuple[float, float]] = ((1.0, 1.0),) * 3, eps: Optional[torch.Tensor] = None, adam: bool = True):
+             lambdas: Sequence[Tuple[float, float]] = ((1.0, 1.0),) * 3, eps: Optional[torch.Tensor] = None, adam: bool = True,
+             has_image: Optional[torch.Tensor] = None, has_text: Optional[torch.Tensor] = None):
+        """`has_image`, `has_text` ([B] bool, optional): per-SAMPLE missing-modality masks (the reference flips a coin
+        per batch, mnist/paired_weak.py:82-104).  Term g counts only the rows that have the modalities it needs (joint: both, image:
+        has_image, text: has_text) and its loss is the mean over those rows; the other (term, row) pairs get zero loss and zero
+        gradient.  The model has no normalisation layer, so rows are independent: the masks become per-(term, row) weights on the
+        device (mvae_mask_weights) inside the same fixed-shape launches - no host sync, CUDA-graph replay and data parallelism work
+        unchanged (each rank normalises by its own row counts, like the per-rank batch means of the unmasked step)."""
+        m = self.model
+        B = image.shape[0]
+        ws = m.workspace(B, len(terms))
+        masked = has_image is not None or has_text is not None
+        if masked:
+            for dst, src in ((ws.mask_image, has_image), (ws.mask_text, has_text)):
+                if src is None:
+                    dst.fill_(1)
+                else:
+                    dst.copy_(torch.as_tensor(src).reshape(-1).to(torch.uint8), non_blocking=True)
+        ws.row_weight = ws.mask_weights if masked else None
+        self._key_extra = masked
         return super().step(image, text, terms, lambdas, eps, adam)
+
+    def mask_counts(self) -> List[float]:
+        """Rows that counted in each term of the last masked step (one small D2H copy)."""
+        ws, tt, _ = self._last
+        return ws.mask_counts[:len(tt)].cpu().tolist()
 
     def losses(self) -> List[Tuple[float, float, float, float]]:
         """Per-term (total, lambda_image * BCE, lambda_text * CE, annealing * KL), each a mean over the batch."""

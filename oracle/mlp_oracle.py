@@ -120,17 +120,35 @@ def elbo_loss(recon_image, image, recon_text, text, mu, logvar, lambda_image=1.0
 TERMS = ("joint", "image", "text")
 
 
+def elbo_rows(recon_image, image, recon_text, text, mu, logvar, lambda_image=1.0, lambda_text=1.0, annealing_factor=1.0):
+    """Per-row parts of elbo_loss (its value is their mean over the batch): (lambda_image * BCE, lambda_text * CE, annealing * KL)."""
+    B = mu.shape[0]
+    bce = lambda_image * F.binary_cross_entropy(recon_image, image.reshape(B, 784), reduction="none").sum(1)
+    ce = lambda_text * F.nll_loss(recon_text, text, reduction="none")
+    kl = annealing_factor * (-0.5) * (1 + logvar - mu.pow(2) - logvar.exp()).sum(1)
+    return bce, ce, kl
+
+
 def train_step(p: State, image, text, noises: Sequence[torch.Tensor], terms=TERMS, lambdas=((1.0, 1.0),) * 3,
-               annealing_factor=1.0, prior: bool = True):
-    """The three-term step of mnist/train.py:132-153 on this model: returns (per-term (total, bce, ce, kl), outputs, grads)."""
+               annealing_factor=1.0, prior: bool = True, has_image=None, has_text=None):
+    """The three-term step of mnist/train.py:132-153 on this model: returns (per-term (total, bce, ce, kl), outputs, grads).
+    With per-sample presence masks (has_image / has_text, [B] bool) term g only counts the rows that have the modalities it
+    needs (joint: both, image: image, text: text) and its loss is the mean over those rows - mnist/paired_weak.py:82-104 applied
+    per row instead of per batch (there is no normalisation layer, so rows are independent)."""
     q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    B = image.shape[0]
+    hi = torch.ones(B, dtype=torch.bool) if has_image is None else has_image.bool()
+    ht = torch.ones(B, dtype=torch.bool) if has_text is None else has_text.bool()
     losses, outs = [], []
     total = None
     for g, t in enumerate(terms):
         im = image if t != "text" else None
         tx = text if t != "image" else None
         ri, rt, mu, lv = forward(q, im, tx, noises[g], True, prior)
-        l = elbo_loss(ri, image, rt, text, mu, lv, lambdas[g][0], lambdas[g][1], annealing_factor)
+        on = (hi & ht) if t == "joint" else (hi if t == "image" else ht)
+        w = on.float() / max(int(on.sum()), 1)
+        parts = [(w * v).sum() for v in elbo_rows(ri, image, rt, text, mu, lv, lambdas[g][0], lambdas[g][1], annealing_factor)]
+        l = (parts[0] + parts[1] + parts[2], parts[0], parts[1], parts[2])
         losses.append(tuple(float(v.detach()) for v in l))
         outs.append((ri.detach(), rt.detach(), mu.detach(), lv.detach()))
         total = l[0] if total is None else total + l[0]

@@ -81,7 +81,7 @@ def test_loss_function_matches_reference_semantics():
         dleaves = [t.cuda().requires_grad_(True) for t in (mu, lv, ri, rt)]
         got = mvae_b200.loss_function(dleaves[0], dleaves[1], dleaves[2], img.cuda(), dleaves[3], txt.cuda(), lam[0], lam[1])
         got.backward()
-        assert float(got) == pytest.approx(float(ref), rel=2e-6)
+        assert float(got.detach()) == pytest.approx(float(ref.detach()), rel=2e-6)
         for a, b in zip(dleaves, leaves):
             np.testing.assert_allclose(a.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-4, atol=1e-8)
     e = mvae_b200.elbo_loss(ri.cuda(), img.cuda(), rt.cuda(), txt.cuda(), mu.cuda(), lv.cuda(), 1.0, 1.0, 0.25)

@@ -67,3 +67,24 @@ def test_text_encoder_is_a_function_of_the_label_only():
     mu, lv = O.text_encoder(st, text)
     tmu, tlv = O.text_encoder(st, torch.arange(10))
     assert torch.equal(mu, tmu[text]) and torch.equal(lv, tlv[text])
+
+
+def test_masked_step_equals_the_step_on_each_terms_own_rows():
+    """Per-sample masks: term g of the masked step == the same term of an unmasked step fed only the rows that have the
+    modalities the term needs (rows are independent: no normalisation layer), losses and gradients."""
+    n, h, B = 4, 8, 12
+    st = O.init_state(n, h, seed=7)
+    image, text, noises = O.synthetic_batch(B, n, 2)
+    g = torch.Generator().manual_seed(1)
+    hi, ht = torch.rand(B, generator=g) < 0.6, torch.rand(B, generator=g) < 0.6
+    hi[:2], ht[:2] = True, True
+    lambdas = ((1.0, 2.0), (1.0, 0.0), (0.0, 3.0))
+    losses, _, grads = O.train_step(st, image, text, noises, lambdas=lambdas, has_image=hi, has_text=ht)
+    total = {k: torch.zeros_like(v) for k, v in st.items()}
+    for t, name, rows in ((0, "joint", hi & ht), (1, "image", hi), (2, "text", ht)):
+        idx = torch.nonzero(rows).reshape(-1)
+        l, _, gr = O.train_step(st, image[idx], text[idx], [noises[t][idx]], terms=(name,), lambdas=(lambdas[t],))
+        assert abs(l[0][0] - losses[t][0]) <= 1e-5 * abs(l[0][0])
+        total = {k: total[k] + gr[k] for k in total}
+    for k in grads:
+        assert torch.allclose(grads[k], total[k], rtol=1e-4, atol=1e-6), k
