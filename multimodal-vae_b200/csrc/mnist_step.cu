@@ -456,12 +456,19 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   }
   // zero_grad: nothing adds into the gradient buffer before the decoders run, so the memset goes beside the encoder forward
   // (side stream, joined after the tail forward)
+  // Launch ORDER matters beside the dependencies: a chain kernel needs whole SMs (227 KB of shared memory, cooperative launch), and
+  // an SM that is running blocks of another kernel cannot take one until they drain.  So at every fork the event is recorded
+  // first, then the chain kernel is enqueued, and only then its side-stream siblings (they fill the SMs the chain leaves free).
   bool grads_zeroing = false;
-  if (fwd && bwd && a->zero_grad) {
-    if (dep(st, s2)) return 1;
-    MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, s2));
-    grads_zeroing = s2 != st;
-  }
+  const bool want_grad_zero = fwd && bwd && a->zero_grad;
+  if (want_grad_zero && dep(st, s2)) return 1;
+  auto zero_grads_aside = [&]() -> int {
+    if (want_grad_zero && !grads_zeroing) {
+      MVAE_CUDA(cudaMemsetAsync(a->grads, 0, static_cast<size_t>(L.param_floats) * 4, s2));
+      grads_zeroing = s2 != st;
+    }
+    return 0;
+  };
 
   float* st_e1 = W.at<float>(P.st_e1); float* st_e2 = W.at<float>(P.st_e2);
   float* st_d1 = W.at<float>(P.st_d1); float* st_d2 = W.at<float>(P.st_d2); float* st_t1 = W.at<float>(P.st_t1);
@@ -486,7 +493,14 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   // weight-gradient GEMMs.  A join waits for everything queued on the joined stream, so what the critical path joins on
   // (the text decoder before the tail backward) must not share a stream with work that is enqueued earlier but may run later.
   if (dep(st, s3)) return 1;  // fork: the per-label text encoder runs beside the image encoder
-  if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s3), "launch_textenc_forward");
+  auto text_encoder_aside = [&]() -> int {
+    if (fwd && n_txt > 0) MVAE_STEP(launch_textenc_forward(te, s3), "launch_textenc_forward");
+    return 0;
+  };
+  if (!(n_img > 0 && use_chain && fwd)) {
+    if (text_encoder_aside()) return 1;
+    if (zero_grads_aside()) return 1;
+  }
 
   unsigned int* chain_err = bars + 31;
   auto wb = [&](const char* name) -> const __nv_bfloat16* { return static_cast<const __nv_bfloat16*>(a->params_bf16) + L.find(name); };
@@ -507,6 +521,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     ce.enc = W.at<float>(P.enc);
     ce.err = chain_err;
     MVAE_STEP(launch_chain_enc_fwd(ce, st), "chain_enc_fwd");
+    if (text_encoder_aside()) return 1;
+    if (zero_grads_aside()) return 1;
   }
   if (n_img > 0 && !use_chain) {
     // ImageEncoder (mnist/model.py:99-117), once for all terms that use it: every Linear publishes its column sums from
@@ -563,7 +579,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   td.dyhat = W.at<float>(P.dyt); td.s0 = sb_t1; td.s1 = sb_t1 + G * 10;
   td.d_w2 = gf("text_decoder.net.3.weight"); td.d_b2 = gf("text_decoder.net.3.bias");
   if (dep(st, s3)) return 1;  // fork: text decoder beside the image decoder
-  if (fwd) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
+  if (fwd && !use_chain) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
 
   if (use_chain && fwd) {
     ChainDecFwd cd;
@@ -588,6 +604,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     cd.err = chain_err;
     MVAE_STEP(launch_chain_dec_fwd(cd, st), "chain_dec_fwd");
   }
+  if (fwd && use_chain) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
   if (!use_chain) {
   // ImageDecoder (mnist/model.py:120-135) on the stacked [G*B, n] latents, per-term BN statistics
   if (fwd) MVAE_STEP(gemm_fwd(dt, R, 200, n, W.at<void>(P.z), wop("image_decoder.net.0.weight"), W.at<void>(P.g1pre), dt,
@@ -631,6 +648,25 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     losses_packed = true;
   }
   // ================================================================ backward
+  bool enc_chain_launched = false;
+  auto launch_encoder_chain_backward = [&]() -> int {
+    ChainEncBwd cb;
+    cb.B = B; cb.n = n;
+    cb.denc = W.at<__nv_bfloat16>(P.denc);
+    cb.w2 = wb("image_encoder.net.3.weight"); cb.w3 = wb("image_encoder.net.6.weight");
+    cb.gamma1 = pf("image_encoder.net.1.weight"); cb.beta1 = pf("image_encoder.net.1.bias");
+    cb.gamma2 = pf("image_encoder.net.4.weight"); cb.beta2 = pf("image_encoder.net.4.bias");
+    cb.sb1 = sb_e1; cb.sb2 = sb_e2; cb.sv1 = sv_e1; cb.sv2 = sv_e2;
+    cb.counters = bars + 14;
+    cb.h1pre = W.at<__nv_bfloat16>(P.h1pre); cb.h2pre = W.at<__nv_bfloat16>(P.h2pre);
+    cb.dye2 = W.at<__nv_bfloat16>(P.dye2); cb.dye1 = W.at<__nv_bfloat16>(P.dye1);
+    cb.dgamma1 = gf("image_encoder.net.1.weight"); cb.dbeta1 = gf("image_encoder.net.1.bias");
+    cb.dgamma2 = gf("image_encoder.net.4.weight"); cb.dbeta2 = gf("image_encoder.net.4.bias");
+    cb.err = chain_err;
+    MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
+    enc_chain_launched = true;
+    return 0;
+  };
   if (bwd && bwd_dec) {
     if (module_bwd) {
       // autograd path: dlogits = d(recon_image) * p * (1 - p) from the probabilities the forward returned
@@ -647,7 +683,6 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     }
     if (use_chain) {
       // ---- image decoder: the whole dgrad / ReLU / BatchNorm-backward chain in one launch; weight gradients beside it
-      MVAE_STEP(gemm_wgrad(dt, R, 784, 400, W.at<void>(P.dlog), W.at<void>(P.g2), gf("image_decoder.net.6.weight"), s2), "gemm_wgrad:image_decoder.net.6.weight#16");
       ChainDecBwd cb;
       cb.B = B; cb.n = n; cb.G = G;
       cb.dlog = W.at<__nv_bfloat16>(P.dlog);
@@ -663,6 +698,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       cb.dgamma2 = gf("image_decoder.net.4.weight"); cb.dbeta2 = gf("image_decoder.net.4.bias");
       cb.err = chain_err;
       MVAE_STEP(launch_chain_dec_bwd(cb, st), "chain_dec_bwd");
+      MVAE_STEP(gemm_wgrad(dt, R, 784, 400, W.at<void>(P.dlog), W.at<void>(P.g2), gf("image_decoder.net.6.weight"), s2), "gemm_wgrad:image_decoder.net.6.weight#16");
       if (dep(st, s2)) return 1;
       MVAE_STEP(gemm_wgrad(dt, R, 400, 200, W.at<void>(P.dy2), W.at<void>(P.g1), gf("image_decoder.net.3.weight"), s2), "gemm_wgrad:image_decoder.net.3.weight#19");
       MVAE_STEP(gemm_wgrad(dt, R, 200, n, W.at<void>(P.dy1), W.at<void>(P.z), gf("image_decoder.net.0.weight"), s2), "gemm_wgrad:image_decoder.net.0.weight#22");
@@ -703,6 +739,8 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     MVAE_STEP(launch_tail_backward(ta, st), "launch_tail_backward");
     if (dep(st, s2)) return 1;  // fork: encoder weight gradients
     if (dep(st, s3)) return 1;  // fork: text encoder backward
+    // (the encoder chain goes in before its side-stream siblings: see "launch ORDER" above)
+    if (bwd_enc && n_img > 0 && use_chain && launch_encoder_chain_backward()) return 1;
     // Every decoder-side gradient is final now (the decoder weight gradients sit ahead on the side stream, everything else
     // was joined into the tail backward): the decoder bucket is updated on the side stream while the encoder chain runs,
     // and only the encoder bucket is left for the end of the step.
@@ -729,20 +767,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     // ---- image encoder
     if (n_img > 0 && use_chain) {
       MVAE_STEP(gemm_wgrad(dt, B, 2 * n, 200, W.at<void>(P.denc), W.at<void>(P.h2), gf("image_encoder.net.6.weight"), s2), "gemm_wgrad:image_encoder.net.6.weight#26");
-      ChainEncBwd cb;
-      cb.B = B; cb.n = n;
-      cb.denc = W.at<__nv_bfloat16>(P.denc);
-      cb.w2 = wb("image_encoder.net.3.weight"); cb.w3 = wb("image_encoder.net.6.weight");
-      cb.gamma1 = pf("image_encoder.net.1.weight"); cb.beta1 = pf("image_encoder.net.1.bias");
-      cb.gamma2 = pf("image_encoder.net.4.weight"); cb.beta2 = pf("image_encoder.net.4.bias");
-      cb.sb1 = sb_e1; cb.sb2 = sb_e2; cb.sv1 = sv_e1; cb.sv2 = sv_e2;
-      cb.counters = bars + 14;
-      cb.h1pre = W.at<__nv_bfloat16>(P.h1pre); cb.h2pre = W.at<__nv_bfloat16>(P.h2pre);
-      cb.dye2 = W.at<__nv_bfloat16>(P.dye2); cb.dye1 = W.at<__nv_bfloat16>(P.dye1);
-      cb.dgamma1 = gf("image_encoder.net.1.weight"); cb.dbeta1 = gf("image_encoder.net.1.bias");
-      cb.dgamma2 = gf("image_encoder.net.4.weight"); cb.dbeta2 = gf("image_encoder.net.4.bias");
-      cb.err = chain_err;
-      MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
+      if (!enc_chain_launched && launch_encoder_chain_backward()) return 1;
       if (dep(st, s2)) return 1;
       if (dep(st, s3)) return 1;
       // the last two weight gradients are what is left of the step: side by side on the two side streams
