@@ -143,9 +143,10 @@ def test_adam_update_matches_oracle():
         assert float((sd[k].cpu() - v).abs().max()) < 2e-6, k
 
 
-def test_term_masking_and_zero_lambda():
+@pytest.mark.parametrize("n", [16, 64])     # 64: the specialised tail kernels with fewer than three terms
+def test_term_masking_and_zero_lambda(n):
     """Weak-supervision variants (mnist/modal_weak.py:76-97): dropped terms, lambda = 0."""
-    B, n, seed = 48, 16, 6
+    B, seed = 48, 6
     state = O.perturbed_state(n, seed)
     image, text, noises = O.synthetic_batch(B, n, seed)
     for terms, lambdas in [(("joint",), ((1., 1.),)), (("joint", "image"), ((1., 1.), (1., 0.))),
@@ -477,13 +478,14 @@ def test_in_kernel_philox_noise_is_standard_normal_and_independent():
     assert corr(e1, draw(m3, mvae_b200.MVAETrainer(m3))) < lim                                     # another seed
 
 
+@pytest.mark.parametrize("n", [32, 64])     # 64: the specialised tail kernels (tail_fwd3 / tail_bwd3), 32: the generic ones
 @pytest.mark.parametrize("prior", [False, True])
-def test_fused_step_in_precision_poe_mode(prior):
+def test_fused_step_in_precision_poe_mode(prior, n):
     """north_star: "ProductOfExperts fusion with the prior expert" inside the fused step.  poe_mode="precision" is not the
     reference's arithmetic - the oracle restates the paper's formula - but the FUSED path (tail kernels,
     all three terms, backward) must implement it exactly: losses to 2e-5, every gradient to rtol 1e-3 in tf32x3."""
     import mvae_b200
-    B, n, seed = 256, 32, 12
+    B, seed = 256, 12
     state = O.perturbed_state(n, seed)
     image, text, noises = O.synthetic_batch(B, n, seed)
     O.POE_VARIANT = ("precision", prior)
