@@ -82,6 +82,7 @@ struct CPass {
   int c_boff[2];          // byte offset inside the stage's B slot
   int c_tmem[2];          // TMEM column base
   int c_buf[2];           // accumulator barrier pair
+  int c_half[2];          // CTA pairs: output columns of the chunk each CTA supplies as B operand (c_mma_n / 2), else 0
 };
 
 struct CLayer {
@@ -140,11 +141,17 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 // mbarrier wait that cannot hang the GPU: after ~4 s the kernel records where it was stuck and traps.
+template <bool kPair = false>
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  if constexpr (kPair) return ptx::mbar_try_wait_cluster(bar, parity);   // arrivals come from both CTAs of the pair
+  else return ptx::mbar_try_wait(bar, parity);
+}
+template <bool kPair = false>
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned int code) {
-  if (ptx::mbar_try_wait(bar, parity)) return;
+  if (mbar_try<kPair>(bar, parity)) return;
   const unsigned long long t0 = gtimer();
   unsigned int spins = 0;
-  while (!ptx::mbar_try_wait(bar, parity)) {
+  while (!mbar_try<kPair>(bar, parity)) {
     if ((++spins & 1023u) == 0 && gtimer() - t0 > 4000000000ull) {
       if (err != nullptr) atomicExch(err, code);
       __threadfence();
@@ -181,6 +188,22 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
       "mov.b64 db, {%2, %3};\n\t"
       "setp.ne.b32 p, %5, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// the same for a CTA pair (cta_group::2, M = 256): issued by the leader, A = each CTA's own 128 rows at the same shared-memory
+// offset, B = N / 2 output columns from each CTA, D = 128 lanes x N columns of TMEM in each CTA
+__device__ __forceinline__ void umma_bf16_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -258,7 +281,14 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 // The layer kinds are template parameters and the layer sequence is unrolled at compile time: `p.layer[il].x` is then a
 // direct constant-bank operand (an indexed constant load behind an asm statement costs hundreds of cycles on the long
 // scoreboard), and every instantiation carries only the epilogues it runs.
-template <int kKind0, int kKind1, int kKind2>
+//
+// kPair: two slab CTAs on neighbouring SMs (a cluster of two) run every Linear as ONE cta_group::2 tcgen05.mma of M = 256:
+// each CTA keeps its own 128 rows (A operand, accumulator, epilogue - all as before) but loads only HALF of every weight
+// tile, the tensor core reads the other half from the partner's shared memory.  The weight ring then holds twice the
+// stages in the same bytes: the rings are latency-bound (a stage's turn-around is ~1.7 us whatever its size), so the
+// weight streams run twice as fast, and the L2 -> SM traffic of the weights halves.  The leader (cluster rank 0) issues
+// the MMAs and owns the barriers the MMA thread waits on; commits arrive on both CTAs' barriers (multicast).
+template <int kKind0, int kKind1, int kKind2, bool kPair>
 __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_constant__ CParams p) {
   // No static shared memory: the dynamic window then starts 1024-byte aligned (checked below), which the SWIZZLE_128B
   // tiles need, and every byte of the 227 KB is planned: [arena | weight ring | tiles | tables | reduction table | barriers].
@@ -274,11 +304,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool keeper = static_cast<int>(blockIdx.x) >= p.n_slabs;
+  const bool slab = static_cast<int>(blockIdx.x) < p.n_slabs;
+  const bool keeper = static_cast<int>(blockIdx.x) == p.n_slabs;   // (pairs: one more CTA fills the keeper's cluster and idles)
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
   const int m0 = blockIdx.x * 128;
-  const int grp = keeper ? 0 : m0 / p.rows_per_group;
+  const int grp = slab ? m0 / p.rows_per_group : 0;
   const unsigned int slabs_per_group = static_cast<unsigned int>(p.rows_per_group / 128);
-  const bool group_leader = !keeper && (m0 % p.rows_per_group) == 0;
+  const bool group_leader = slab && (m0 % p.rows_per_group) == 0;
   const uint32_t smem_u = ptx::smem_u32(smem);
   long long* dbg = p.dbg != nullptr ? p.dbg + 32ll * blockIdx.x : nullptr;
   auto stamp = [&](int slot) {
@@ -297,18 +329,24 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], kCEpi);
+      ptx::mbar_init(&acc_empty[s], kPair ? 2 * kEpiWarps : kCEpi);   // pairs: one arrival per epilogue warp of both CTAs
     }
     ptx::mbar_init(a_tma_bar, 1);
-    ptx::mbar_init(a_epi_bar, kCEpi);
+    ptx::mbar_init(a_epi_bar, kPair ? 2 * kEpiWarps : kCEpi);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) {
+      ptx::tmem_alloc_pair(tmem_slot, 512);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync();   // the partner's barriers are initialised before anything arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -316,10 +354,17 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   // shared-memory carve-out taken there is almost no L1, and a local-memory array costs an L2 round trip per access.
   if (warp == 0) {
     // =================================================================== TMA producer
-    if (lane == 0 && !keeper) {
+    if (lane == 0 && slab) {
+      // pairs: both CTAs load (their own A rows, their half of B); the bytes of both are counted on the LEADER's barrier
+      const uint32_t full_l = kPair ? ptx::mapa(ptx::smem_u32(full_bar), 0) : 0u;   // + 8 * slot
+      auto load2d = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, uint32_t bar_l, int c0, int c1) {
+        if constexpr (kPair) ptx::tma_load_2d_pair(dst, tm, bar_l, c0, c1);
+        else ptx::tma_load_2d(dst, tm, bar, c0, c1);
+      };
       if (p.init_tm >= 0) {
-        ptx::mbar_expect_tx(a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel));
-        for (int pn = 0; pn < p.init_panels; ++pn) ptx::tma_load_2d(smem + pn * kPanel, &p.tm[p.init_tm], a_tma_bar, pn * 64, m0);
+        if (rank == 0) ptx::mbar_expect_tx(a_tma_bar, static_cast<uint32_t>(p.init_panels * kPanel) * (kPair ? 2u : 1u));
+        const uint32_t a_tma_l = kPair ? ptx::mapa(ptx::smem_u32(a_tma_bar), 0) : 0u;
+        for (int pn = 0; pn < p.init_panels; ++pn) load2d(smem + pn * kPanel, &p.tm[p.init_tm], a_tma_bar, a_tma_l, pn * 64, m0);
       }
       uint32_t fill_par = 0, fill_any = 0;   // bit s: parity of the number of fills of slot s / slot ever filled
       int cur_cfg = -1, s = 0;
@@ -335,26 +380,29 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         // everything the k loop needs lives in registers: a parameter read behind an asm statement is an indexed constant load
         const int k_panels = ps.k_panels, a_stream = ps.a_stream, b_mn = ps.b_mn, nch = ps.n_chunks;
-        const int n0_0 = ps.c_n0[0], n0_1 = ps.c_n0[1], boff_0 = ps.c_boff[0], boff_1 = ps.c_boff[1];
+        const int n0_0 = ps.c_n0[0] + static_cast<int>(rank) * ps.c_half[0], n0_1 = ps.c_n0[1] + static_cast<int>(rank) * ps.c_half[1];
+        const int boff_0 = ps.c_boff[0], boff_1 = ps.c_boff[1];
         const int boxes_0 = ps.c_boxes[0], boxes_1 = ps.c_boxes[1];
         const CUtensorMap* tm_a = &p.tm[a_stream >= 0 ? a_stream : 0];
         const CUtensorMap* tm_b = &p.tm[ps.b_tm];
         const int ring_base = rg.base, stage_bytes = rg.stage_bytes, a_bytes = rg.a_bytes;
-        const uint32_t bytes = (a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u) + static_cast<uint32_t>(ps.c_bytes[0]) +
-                               (nch > 1 ? static_cast<uint32_t>(ps.c_bytes[1]) : 0u);
+        const uint32_t bytes = ((a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u) + static_cast<uint32_t>(ps.c_bytes[0]) +
+                                (nch > 1 ? static_cast<uint32_t>(ps.c_bytes[1]) : 0u)) * (kPair ? 2u : 1u);
         for (int kp = 0; kp < k_panels; ++kp) {
           mbar_wait_b(&empty_bar[s], ((fill_par >> s) & 1u) ^ 1u, p.err, 0x110u + s);
-          ptx::mbar_expect_tx(&full_bar[s], bytes);
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], bytes);
+          uint64_t* fb = &full_bar[s];
+          const uint32_t fl = full_l + 8u * s;
           uint8_t* stage = smem + ring_base + s * stage_bytes;
-          if (a_stream >= 0) ptx::tma_load_2d(stage, tm_a, &full_bar[s], kp * 64, m0);
+          if (a_stream >= 0) load2d(stage, tm_a, fb, fl, kp * 64, m0);
           uint8_t* bslot = stage + a_bytes;
           if (!b_mn) {
-            ptx::tma_load_2d(bslot + boff_0, tm_b, &full_bar[s], kp * 64, n0_0);
-            if (nch > 1) ptx::tma_load_2d(bslot + boff_1, tm_b, &full_bar[s], kp * 64, n0_1);
+            load2d(bslot + boff_0, tm_b, fb, fl, kp * 64, n0_0);
+            if (nch > 1) load2d(bslot + boff_1, tm_b, fb, fl, kp * 64, n0_1);
           } else {
-            for (int jb = 0; jb < boxes_0; ++jb) ptx::tma_load_2d(bslot + boff_0 + jb * 8192, tm_b, &full_bar[s], n0_0 + jb * 64, kp * 64);
+            for (int jb = 0; jb < boxes_0; ++jb) load2d(bslot + boff_0 + jb * 8192, tm_b, fb, fl, n0_0 + jb * 64, kp * 64);
             if (nch > 1)
-              for (int jb = 0; jb < boxes_1; ++jb) ptx::tma_load_2d(bslot + boff_1 + jb * 8192, tm_b, &full_bar[s], n0_1 + jb * 64, kp * 64);
+              for (int jb = 0; jb < boxes_1; ++jb) load2d(bslot + boff_1 + jb * 8192, tm_b, fb, fl, n0_1 + jb * 64, kp * 64);
           }
           fill_par ^= 1u << s;
           fill_any |= 1u << s;
@@ -365,10 +413,14 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // =================================================================== MMA issuer
-    if (lane == 0 && !keeper) {
+    if (lane == 0 && slab && rank == 0) {
       uint32_t use_par = 0, acc_par = 0;   // bit s: parity of uses of ring slot s; bit b: parity of uses of accumulator b
       uint32_t n_tma_waits = 0, n_epi_waits = 0;
       int cur_cfg = -1, s = 0;
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (kPair) ptx::umma_commit_pair(bar);   // arrives in both CTAs
+        else ptx::umma_commit(bar);
+      };
       for (int ip = 0; ip < p.n_pass; ++ip) {
         const CPass& ps = p.pass[ip];
         const CRing rg = p.ring[ps.cfg];
@@ -377,19 +429,19 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           s = 0;
         }
         if (ps.a_wait == 1) {
-          mbar_wait_b(a_tma_bar, n_tma_waits & 1, p.err, 0x200u);
+          mbar_wait_b<kPair>(a_tma_bar, n_tma_waits & 1, p.err, 0x200u);
           ++n_tma_waits;
         } else if (ps.a_wait == 2) {
-          mbar_wait_b(a_epi_bar, n_epi_waits & 1, p.err, 0x201u);
+          mbar_wait_b<kPair>(a_epi_bar, n_epi_waits & 1, p.err, 0x201u);
           ++n_epi_waits;
         }
         const int nc = ps.n_chunks;
         const int buf0 = ps.c_buf[0], buf1 = ps.c_buf[nc - 1];
-        mbar_wait_b(&acc_empty[buf0], ((acc_par >> buf0) & 1u) ^ 1u, p.err, 0x210u + buf0);
-        if (nc > 1) mbar_wait_b(&acc_empty[buf1], ((acc_par >> buf1) & 1u) ^ 1u, p.err, 0x210u + buf1);
+        mbar_wait_b<kPair>(&acc_empty[buf0], ((acc_par >> buf0) & 1u) ^ 1u, p.err, 0x210u + buf0);
+        if (nc > 1) mbar_wait_b<kPair>(&acc_empty[buf1], ((acc_par >> buf1) & 1u) ^ 1u, p.err, 0x210u + buf1);
         ptx::tc_fence_after();
-        const uint32_t idesc0 = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[0]);
-        const uint32_t idesc1 = ptx::make_idesc(1, 0, ps.b_mn, 128, ps.c_mma_n[nc - 1]);
+        const uint32_t idesc0 = ptx::make_idesc(1, 0, ps.b_mn, kPair ? 256 : 128, ps.c_mma_n[0]);
+        const uint32_t idesc1 = ptx::make_idesc(1, 0, ps.b_mn, kPair ? 256 : 128, ps.c_mma_n[nc - 1]);
         const uint32_t boff0 = ps.c_boff[0], boff1 = ps.c_boff[nc - 1];
         const uint32_t tm0 = tmem_base + ps.c_tmem[0], tm1 = tmem_base + ps.c_tmem[nc - 1];
         const int b_mn = ps.b_mn, k_panels = ps.k_panels, last_ksteps = ps.last_ksteps, a_stream = ps.a_stream;
@@ -397,7 +449,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         const uint32_t b_lbo = b_mn ? ((8192u >> 4) << 16) : (1u << 16);   // MN-major: 64-column boxes 8 KB apart
         const uint32_t b_kstep = b_mn ? (2048u >> 4) : 2u;                 // 16 k-rows of an MN-major box / 32 bytes of a K-major row
         for (int kp = 0; kp < k_panels; ++kp) {
-          mbar_wait_b(&full_bar[s], (use_par >> s) & 1u, p.err, 0x220u + s);
+          mbar_wait_b<kPair>(&full_bar[s], (use_par >> s) & 1u, p.err, 0x220u + s);
           use_par ^= 1u << s;
           ptx::tc_fence_after();
           const uint32_t stage = smem_u + ring_base + s * stage_bytes;
@@ -412,23 +464,28 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < nks) {
               const uint32_t acc = (kp | ks) != 0 ? 1u : 0u;
-              umma_bf16_lohi(tm0, a_lo + 2 * ks, b0_lo + b_kstep * ks, kDescHi, idesc0, acc);
-              if (nc > 1) umma_bf16_lohi(tm1, a_lo + 2 * ks, b1_lo + b_kstep * ks, kDescHi, idesc1, acc);
+              if constexpr (kPair) {
+                umma_bf16_lohi_pair(tm0, a_lo + 2 * ks, b0_lo + b_kstep * ks, kDescHi, idesc0, acc);
+                if (nc > 1) umma_bf16_lohi_pair(tm1, a_lo + 2 * ks, b1_lo + b_kstep * ks, kDescHi, idesc1, acc);
+              } else {
+                umma_bf16_lohi(tm0, a_lo + 2 * ks, b0_lo + b_kstep * ks, kDescHi, idesc0, acc);
+                if (nc > 1) umma_bf16_lohi(tm1, a_lo + 2 * ks, b1_lo + b_kstep * ks, kDescHi, idesc1, acc);
+              }
             }
           }
-          ptx::umma_commit(&empty_bar[s]);
+          commit(&empty_bar[s]);
           if (++s == rg.stages) s = 0;
         }
-        ptx::umma_commit(&acc_full[buf0]);
+        commit(&acc_full[buf0]);
         acc_par ^= 1u << buf0;
         if (nc > 1) {
-          ptx::umma_commit(&acc_full[buf1]);
+          commit(&acc_full[buf1]);
           acc_par ^= 1u << buf1;
         }
         if (ip < 8) stamp(9 + ip);
       }
     }
-  } else if (!keeper) {
+  } else if (slab) {
     // =================================================================== epilogue (16 warps)
     const int et = threadIdx.x - 64;
     const int q = warp & 3;               // TMEM lane quarter this warp may read
@@ -439,6 +496,16 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     const int rsel = lane >> 3, cq = lane & 7;   // column phase: rows 4*rsel + i of a 16-row half, columns 4*cq .. 4*cq+3 of the unit
     uint32_t epi_par = 0;                 // bit b: parity of the accumulator-full phases consumed so far
     const float inv_cnt = 1.f / static_cast<float>(p.rows_per_group);
+    // "this warp is done with ..." for the MMA thread: per thread on the CTA's own barrier, or - pairs - one arrival per warp
+    // on the leader's barrier (the MMA thread there waits for the epilogues of both CTAs)
+    auto epi_arrive = [&](uint64_t* bar) {
+      if constexpr (kPair) {
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(bar), 0));
+      } else {
+        ptx::mbar_arrive(bar);
+      }
+    };
 
     // this lane's accumulator row of a 32-column unit, raw from TMEM (the upper 16 columns zero when `wide` is false)
     // This lane's accumulator row of a 32-column unit, raw from TMEM.  Columns beyond the layer hold whatever TMEM holds:
@@ -491,7 +558,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       auto release_all_chunks = [&]() {
         ptx::tc_fence_before();
         for (int ci = 0; ci < L.n_chunks; ++ci) {
-          ptx::mbar_arrive(&acc_empty[ci]);
+          epi_arrive(&acc_empty[ci]);
           epi_par ^= 1u << ci;
         }
       };
@@ -603,7 +670,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           }
         }
         ptx::fence_proxy_async_smem();
-        if (L.write_arena) ptx::mbar_arrive(a_epi_bar);
+        if (L.write_arena) epi_arrive(a_epi_bar);
         bar_epi();
         if (et == 0) store_arena(&p.tmo[2 * il + 1]);   // post-BatchNorm activations -> global (the next weight gradient's operand)
       } else if constexpr (kKind == CE_DGRAD_BN) {
@@ -733,7 +800,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           for (int k = 0; k < 8; ++k) hx2[k] = hn[k];
         }
         ptx::fence_proxy_async_smem();
-        if (L.write_arena) ptx::mbar_arrive(a_epi_bar);
+        if (L.write_arena) epi_arrive(a_epi_bar);
         bar_epi();
         if (et == 0) store_arena(&p.tmo[2 * il + 1]);   // gradient at the pre-BatchNorm output -> global (weight gradient operand)
       } else if constexpr (kKind == CE_FWD_STORE || kKind == CE_DGRAD_STORE) {
@@ -789,7 +856,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           while (ci_waited < ci) {
             if (ci_waited >= 0) {   // done with chunk ci_waited
               ptx::tc_fence_before();
-              ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
+              epi_arrive(&acc_empty[ci_waited & 1]);
             }
             ++ci_waited;
             const int b = ci_waited & 1;
@@ -847,7 +914,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         while (ci_waited < n_chunks - 1) {
           if (ci_waited >= 0) {
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
+            epi_arrive(&acc_empty[ci_waited & 1]);
           }
           ++ci_waited;
           const int b = ci_waited & 1;
@@ -855,7 +922,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           epi_par ^= 1u << b;
         }
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&acc_empty[ci_waited & 1]);
+        epi_arrive(&acc_empty[ci_waited & 1]);
         float lsum = fmaf(-0.6931471805599453f, llog, lin);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
@@ -873,7 +940,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
     run_layer(std::integral_constant<int, kKind1>{}, std::integral_constant<int, 1>{});
     if constexpr (kKind2 >= 0) run_layer(std::integral_constant<int, kKind2>{}, std::integral_constant<int, 2>{});
     if (et == 0) ptx::bulk_wait_all();   // the arena's output copies are complete before the CTA gives up its shared memory
-  } else {
+  } else if (keeper) {
     // =================================================================== keeper CTA: what needs every group's statistics,
     // in group order (one reference forward pass per group), while the slab CTAs carry on
     const int et = threadIdx.x - 64;
@@ -917,8 +984,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   }
   __syncwarp();
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if constexpr (kPair) {
+    ptx::cluster_sync();   // the partner's MMAs have read this CTA's shared memory, its epilogue has arrived on our barriers
+    if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 512);
+  } else {
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  }
   if (threadIdx.x == 0) stamp(31);
 }
 
@@ -955,9 +1027,10 @@ int chain_tmap(CUtensorMap* out, const void* base, long long rows, long long col
   return 0;
 }
 
-void set_chunk(CPass& ps, int c, int n0, int mma_n, int boxes, int bytes, int boff, int tmem, int buf) {
+// `boxes` / `bytes`: what ONE CTA loads per stage for the chunk (pairs: its half of the chunk's output columns)
+void set_chunk(CPass& ps, int c, int n0, int mma_n, int boxes, int bytes, int boff, int tmem, int buf, bool pair = false) {
   ps.c_n0[c] = n0; ps.c_mma_n[c] = mma_n; ps.c_boxes[c] = boxes; ps.c_bytes[c] = bytes; ps.c_boff[c] = boff;
-  ps.c_tmem[c] = tmem; ps.c_buf[c] = buf;
+  ps.c_tmem[c] = tmem; ps.c_buf[c] = buf; ps.c_half[c] = pair ? mma_n / 2 : 0;
 }
 int ksteps_of(int K) { return ((K - 1) % 64) / 16 + 1; }   // 16-wide k-steps in the last 64-wide panel
 int panels_of(int K) { return (K + 63) / 64; }
@@ -969,7 +1042,7 @@ constexpr int kBwdChunk = 256;   // MN-major: four 64 x 64 boxes = 32768 B per s
 // ~0.25 us, so a stage has to carry a few hundred cycles of MMA work).  BatchNorm / store layers: TMEM column = layer
 // column, barrier pair = chunk index.  BCE layer (784 columns): chunk widths are multiples of 32 (whole epilogue units),
 // two TMEM buffers of 224 columns alternate.  Also fills the layer's chunk description.  Returns the next free pass index.
-int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bool b_mn, int first_a_wait, bool bce) {
+int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bool b_mn, int first_a_wait, bool bce, bool pair) {
   const int Npad = (N + 15) & ~15;
   int widths[4] = {0, 0, 0, 0};
   int nch = 0;
@@ -1001,10 +1074,11 @@ int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bo
     const int tmem = bce ? (c & 1) * 224 : n0;
     const int buf = bce ? (c & 1) : c;
     if (b_mn) {
-      const int boxes = (w + 63) / 64;
-      set_chunk(ps, 0, n0, w, boxes, boxes * 8192, 0, tmem, buf);
+      const int boxes = ((pair ? w / 2 : w) + 63) / 64;
+      set_chunk(ps, 0, n0, w, boxes, boxes * 8192, 0, tmem, buf, pair);
     } else {
-      set_chunk(ps, 0, n0, w, 0, kFwdChunk * 128, 0, tmem, buf);   // the box is always kFwdChunk rows (rows beyond the matrix: zero fill)
+      // the box is always kFwdChunk rows - half of that per CTA of a pair (rows beyond the matrix: zero fill)
+      set_chunk(ps, 0, n0, w, 0, kFwdChunk * 128 / (pair ? 2 : 1), 0, tmem, buf, pair);
     }
     if (c == 1) L.u1 = n0 / 32;
     if (c == 2) L.u2 = n0 / 32;
@@ -1014,28 +1088,50 @@ int add_resident_layer(CParams& p, int ip, CLayer& L, int N, int K, int b_tm, bo
   return ip;
 }
 
-template <int kKind0, int kKind1, int kKind2>
-int launch_chain(const CParams& p, int ctas, cudaStream_t st) {
+template <int kKind0, int kKind1, int kKind2, bool kPair>
+int launch_chain_v(const CParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel<kKind0, kKind1, kKind2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    MVAE_CUDA(cudaFuncSetAttribute(chain_kernel<kKind0, kKind1, kKind2, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
     attr_set = true;
   }
   static const int coop = env_int("MVAE_CHAIN_COOP", 1);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ctas);
+  cfg.gridDim = dim3(p.n_slabs + (kPair ? 2 : 1));   // slabs + keeper (+ one idle CTA that completes the keeper's cluster)
   cfg.blockDim = dim3(kCThreads);
   cfg.dynamicSmemBytes = kSmemTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barriers cannot deadlock
-  attr[0].val.cooperative = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (kPair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (coop) {
+    attr[na].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barriers cannot deadlock
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = coop ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel<kKind0, kKind1, kKind2>, p);
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel<kKind0, kKind1, kKind2, kPair>, p);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(chain_kernel)", __FILE__, __LINE__);
   return 0;
 }
+template <int kKind0, int kKind1, int kKind2>
+int launch_chain(const CParams& p, bool pair, cudaStream_t st) {
+  return pair ? launch_chain_v<kKind0, kKind1, kKind2, true>(p, st) : launch_chain_v<kKind0, kKind1, kKind2, false>(p, st);
+}
+// CTA pairs (cta_group::2): an even number of slabs, and room for the keeper's cluster
+bool chain_pair(int n_slabs) {
+  static const int on = env_int("MVAE_CHAIN_PAIR", 1);
+  return on != 0 && n_slabs % 2 == 0 && n_slabs + 2 <= 148;
+}
+constexpr int kPairStage = 16384;   // resident-A layers of a pair: half a weight chunk per CTA, four stages in the same 64 KB
+void pair_rings(CParams& p) { p.ring[1] = CRing{kArena, kPairStage, 4, 0}; }
 
 long long* g_chain_dbg = nullptr;
 
@@ -1065,7 +1161,7 @@ bool chain_supported(int B, int G, int n) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 + 1 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
+  return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 + 2 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
 }
 
 int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
@@ -1073,12 +1169,16 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   const int slabs = a.B / 128;
   init_params(p, a.B, slabs, a.err, 0);
   const int n2 = 2 * a.n;
+  const bool pair = chain_pair(slabs);
+  const int hv = pair ? 2 : 1;   // a CTA of a pair loads half of every weight tile
   if (chain_tmap(&p.tm[0], a.image, a.B, 784, 784, 64, 128)) return 1;
-  if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208)) return 1;
-  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, kFwdChunk)) return 1;
-  if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, kFwdChunk)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208 / hv)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, kFwdChunk / hv)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, kFwdChunk / hv)) return 1;
   p.tm[4] = p.tm[3];
-  p.ring[0] = CRing{0, kPanel + 2 * 26624, 2, kPanel};   // streamed image panel + all 400 rows of W1 per 64-wide k panel
+  // streamed image panel + all 400 rows of W1 per 64-wide k panel: 2 stages of 68 KB, or - pairs - 4 stages of 42 KB
+  p.ring[0] = CRing{0, kPanel + 2 * 26624 / hv, pair ? 4 : 2, kPanel};
+  if (pair) pair_rings(p);
   p.n_layers = 3;
   CLayer& l1 = p.layer[0];
   CLayer& l2 = p.layer[1];
@@ -1086,12 +1186,12 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   CPass& e1 = p.pass[0];
   e1.cfg = 0; e1.k_panels = panels_of(784); e1.last_ksteps = ksteps_of(784); e1.a_stream = 0; e1.a_wait = 0; e1.b_tm = 1; e1.b_mn = 0;
   e1.n_chunks = 2;
-  set_chunk(e1, 0, 0, 208, 0, 26624, 0, 0, 0);
-  set_chunk(e1, 1, 208, 192, 0, 26624, 26624, 208, 1);
+  set_chunk(e1, 0, 0, 208, 0, 26624 / hv, 0, 0, 0, pair);
+  set_chunk(e1, 1, 208, 192, 0, 26624 / hv, 26624 / hv, 208, 1, pair);
   l1.kind = CE_FWD_BN; l1.N = 400; l1.n_chunks = 2;
   int ip = 1;
-  ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false);
-  ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false);
+  ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false, pair);
+  ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false, pair);
   p.n_pass = ip;
   if (chain_tmap(&p.tmo[0], a.h1pre, a.B, 400, 400, 64, 128)) return 1;
   if (chain_tmap(&p.tmo[1], a.h1, a.B, 400, 400, 64, 128)) return 1;
@@ -1106,17 +1206,20 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   l2.counter = a.counters + 1; l2.out_pre = a.h2pre; l2.out_post = a.h2; l2.write_arena = 1;
   l3.kind = CE_FWD_STORE; l3.N = n2;
   l3.bias = a.b3; l3.out_f32 = a.enc; l3.ld_out = n2;
-  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_FWD_STORE>(p, slabs + 1, st);
+  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_FWD_STORE>(p, pair, st);
 }
 
 int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   CParams p;
   const int R = a.G * a.B, G = a.G;
   init_params(p, a.B, R / 128, a.err, 1);
+  const bool pair = chain_pair(R / 128);
+  const int hv = pair ? 2 : 1;
+  if (pair) pair_rings(p);
   if (chain_tmap(&p.tm[0], a.z, R, a.n, a.n, 64, 128)) return 1;
-  if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, kFwdChunk)) return 1;
-  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, kFwdChunk)) return 1;
-  if (chain_tmap(&p.tm[3], a.w3, 784, 400, 400, 64, kFwdChunk)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 200, a.n, a.n, 64, kFwdChunk / hv)) return 1;
+  if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, kFwdChunk / hv)) return 1;
+  if (chain_tmap(&p.tm[3], a.w3, 784, 400, 400, 64, kFwdChunk / hv)) return 1;
   p.tm[4] = p.tm[3];
   p.init_tm = 0;
   p.init_panels = panels_of(a.n);
@@ -1125,9 +1228,9 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   CLayer& l2 = p.layer[1];
   CLayer& l3 = p.layer[2];
   int ip = 0;
-  ip = add_resident_layer(p, ip, l1, 200, a.n, 1, false, 1, false);
-  ip = add_resident_layer(p, ip, l2, 400, 200, 2, false, 2, false);
-  ip = add_resident_layer(p, ip, l3, 784, 400, 3, false, 2, true);
+  ip = add_resident_layer(p, ip, l1, 200, a.n, 1, false, 1, false, pair);
+  ip = add_resident_layer(p, ip, l2, 400, 200, 2, false, 2, false, pair);
+  ip = add_resident_layer(p, ip, l3, 784, 400, 3, false, 2, true, pair);
   p.n_pass = ip;
   if (chain_tmap(&p.tmo[0], a.g1pre, R, 200, 200, 64, 128)) return 1;
   if (chain_tmap(&p.tmo[1], a.g1, R, 200, 200, 64, 128)) return 1;
@@ -1145,7 +1248,7 @@ int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st) {
   l3.bias = a.b3; l3.target = a.image; l3.target_rows = a.B;
   for (int g = 0; g < 3; ++g) l3.bce_scale[g] = a.bce_scale[g];
   l3.loss = a.loss; l3.dbias = a.dbias3; l3.dlog = a.dlog; l3.probs = a.probs;
-  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_BCE>(p, R / 128 + 1, st);
+  return launch_chain<CE_FWD_BN, CE_FWD_BN, CE_BCE>(p, pair, st);
 }
 
 int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
@@ -1157,7 +1260,10 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   if (chain_tmap(&p.tm[2], a.w2, 400, 200, 200, 64, 64)) return 1;
   if (chain_tmap(&p.tm[3], a.w1, 200, a.n, a.n, 64, 64)) return 1;
   p.tm[4] = p.tm[3];
-  p.ring[0] = CRing{0, kPanel + 7 * 8192, 2, kPanel};   // streamed dlogits panel + all 400 columns of W3 per 64-wide k panel
+  // streamed dlogits panel + all 400 columns of W3 per 64-wide k panel: 2 stages of 72 KB, or - pairs - 3 stages of 48 KB
+  const bool pair = chain_pair(R / 128);
+  p.ring[0] = pair ? CRing{0, kPanel + 4 * 8192, 3, kPanel} : CRing{0, kPanel + 7 * 8192, 2, kPanel};
+  if (pair) pair_rings(p);
   p.n_layers = 3;
   CLayer& l2 = p.layer[0];
   CLayer& l1 = p.layer[1];
@@ -1165,12 +1271,17 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   CPass& g3 = p.pass[0];
   g3.cfg = 0; g3.k_panels = panels_of(784); g3.last_ksteps = ksteps_of(784); g3.a_stream = 0; g3.a_wait = 0; g3.b_tm = 1; g3.b_mn = 1;
   g3.n_chunks = 2;
-  set_chunk(g3, 0, 0, 256, 4, 32768, 0, 0, 0);
-  set_chunk(g3, 1, 256, 144, 3, 24576, 32768, 256, 1);
+  if (pair) {   // per CTA: 128 + 72 columns = 2 + 2 boxes
+    set_chunk(g3, 0, 0, 256, 2, 16384, 0, 0, 0, true);
+    set_chunk(g3, 1, 256, 144, 2, 16384, 16384, 256, 1, true);
+  } else {
+    set_chunk(g3, 0, 0, 256, 4, 32768, 0, 0, 0);
+    set_chunk(g3, 1, 256, 144, 3, 24576, 32768, 256, 1);
+  }
   l2.kind = CE_DGRAD_BN; l2.N = 400; l2.n_chunks = 2;
   int ip = 1;
-  ip = add_resident_layer(p, ip, l1, 200, 400, 2, true, 2, false);
-  ip = add_resident_layer(p, ip, l0, a.n, 200, 3, true, 2, false);
+  ip = add_resident_layer(p, ip, l1, 200, 400, 2, true, 2, false, pair);
+  ip = add_resident_layer(p, ip, l0, a.n, 200, 3, true, 2, false, pair);
   p.n_pass = ip;
   if (chain_tmap(&p.tmo[1], a.dy2, R, 400, 400, 64, 128)) return 1;
   if (chain_tmap(&p.tmo[3], a.dy1, R, 200, 200, 64, 128)) return 1;
@@ -1183,7 +1294,7 @@ int launch_chain_dec_bwd(const ChainDecBwd& a, cudaStream_t st) {
   l1.counter = a.counters + 3; l1.hpre = a.g1pre; l1.out_post = a.dy1; l1.write_arena = 1; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
   l0.kind = CE_DGRAD_STORE; l0.N = a.n;
   l0.out_f32 = a.dz; l0.ld_out = a.n;
-  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, CE_DGRAD_STORE>(p, R / 128 + 1, st);
+  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, CE_DGRAD_STORE>(p, pair, st);
 }
 
 int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
@@ -1202,8 +1313,10 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   CLayer& l2 = p.layer[0];
   CLayer& l1 = p.layer[1];
   int ip = 0;
-  ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false);
-  ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false);
+  const bool pair = chain_pair(slabs);
+  if (pair) pair_rings(p);
+  ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false, pair);
+  ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false, pair);
   p.n_pass = ip;
   if (chain_tmap(&p.tmo[1], a.dye2, a.B, 200, 200, 64, 128)) return 1;
   if (chain_tmap(&p.tmo[3], a.dye1, a.B, 400, 400, 64, 128)) return 1;
@@ -1215,7 +1328,7 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   l1.kind = CE_DGRAD_BN; l1.N = 400;
   l1.gamma = a.gamma1; l1.beta = a.beta1; l1.stat0 = a.sb1; l1.stat1 = a.sb1 + 400; l1.save_mean = a.sv1; l1.save_rstd = a.sv1 + 400;
   l1.counter = a.counters + 1; l1.hpre = a.h1pre; l1.out_post = a.dye1; l1.write_arena = 0; l1.dgamma = a.dgamma1; l1.dbeta = a.dbeta1;
-  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, -1>(p, slabs + 1, st);
+  return launch_chain<CE_DGRAD_BN, CE_DGRAD_BN, -1>(p, pair, st);
 }
 
 }  // namespace mvae
