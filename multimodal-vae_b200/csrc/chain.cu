@@ -126,7 +126,13 @@ struct alignas(64) CParams {
   CPass pass[kMaxPass];
   CLayer layer[kMaxLayer];
   int n_pass, n_layers;
-  int n_slabs;            // slab CTAs; CTA n_slabs is the keeper
+  int n_slabs;            // slabs; CTA n_slabs * parts is the keeper
+  // Column split of ONE layer (enc_bwd's last: no later layer needs its output on chip): `parts` CTAs share a slab, CTA
+  // `n_slabs * part + slab` takes columns [part_n0, part_n0 + part_n) of the split layer.  The layers before it are
+  // computed by every part on its own (redundantly, on SMs that would idle otherwise) - only part 0 publishes their
+  // statistics and results - so no activation ever moves between CTAs.
+  int parts, split_layer, split_pass;
+  int part_n0[4], part_n[4];
   int rows_per_group;     // rows of one statistics group (= batch)
   int init_tm, init_panels;  // resident A loaded by TMA at kernel start (z / d_enc), -1: none
   float momentum, eps;
@@ -227,11 +233,11 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 // Grid barrier of one statistics group: arrive, then wait until all `expected` CTAs of the group have arrived.
 // Called by all epilogue threads after their global atomics.  A lost CTA cannot hang the GPU: after ~2 s the wait
 // gives up and flags the error (results are then garbage, which the flag reports).
-__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int expected, unsigned int* err, int et) {
+__device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned int expected, unsigned int* err, int et, bool arrive = true) {
   __threadfence();
   bar_epi();
   if (et == 0) {
-    atomicAdd(counter, 1u);
+    if (arrive) atomicAdd(counter, 1u);
     unsigned int seen = 0;
     const unsigned long long t0 = gtimer();
     unsigned int spins = 0;
@@ -304,13 +310,15 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool slab = static_cast<int>(blockIdx.x) < p.n_slabs;
-  const bool keeper = static_cast<int>(blockIdx.x) == p.n_slabs;   // (pairs: one more CTA fills the keeper's cluster and idles)
+  const int n_slab_ctas = p.n_slabs * p.parts;
+  const bool slab = static_cast<int>(blockIdx.x) < n_slab_ctas;
+  const bool keeper = static_cast<int>(blockIdx.x) == n_slab_ctas;   // (pairs: one more CTA fills the keeper's cluster and idles)
   const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
-  const int m0 = blockIdx.x * 128;
+  const int part = slab ? static_cast<int>(blockIdx.x) / p.n_slabs : 0;
+  const int m0 = (static_cast<int>(blockIdx.x) % p.n_slabs) * 128;
   const int grp = slab ? m0 / p.rows_per_group : 0;
   const unsigned int slabs_per_group = static_cast<unsigned int>(p.rows_per_group / 128);
-  const bool group_leader = slab && (m0 % p.rows_per_group) == 0;
+  const bool group_leader = slab && part == 0 && (m0 % p.rows_per_group) == 0;
   const uint32_t smem_u = ptx::smem_u32(smem);
   long long* dbg = p.dbg != nullptr ? p.dbg + 32ll * blockIdx.x : nullptr;
   auto stamp = [&](int slot) {
@@ -380,13 +388,18 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         // everything the k loop needs lives in registers: a parameter read behind an asm statement is an indexed constant load
         const int k_panels = ps.k_panels, a_stream = ps.a_stream, b_mn = ps.b_mn, nch = ps.n_chunks;
-        const int n0_0 = ps.c_n0[0] + static_cast<int>(rank) * ps.c_half[0], n0_1 = ps.c_n0[1] + static_cast<int>(rank) * ps.c_half[1];
+        const int n0_0 = (ip == p.split_pass ? p.part_n0[part] : ps.c_n0[0]) + static_cast<int>(rank) * ps.c_half[0];
+        const int n0_1 = ps.c_n0[1] + static_cast<int>(rank) * ps.c_half[1];
         const int boff_0 = ps.c_boff[0], boff_1 = ps.c_boff[1];
-        const int boxes_0 = ps.c_boxes[0], boxes_1 = ps.c_boxes[1];
+        int boxes_0 = ps.c_boxes[0];
+        const int boxes_1 = ps.c_boxes[1];
+        const bool split_ps = ip == p.split_pass;
+        if (split_ps) boxes_0 = (p.part_n[part] + 63) >> 6;
         const CUtensorMap* tm_a = &p.tm[a_stream >= 0 ? a_stream : 0];
         const CUtensorMap* tm_b = &p.tm[ps.b_tm];
         const int ring_base = rg.base, stage_bytes = rg.stage_bytes, a_bytes = rg.a_bytes;
-        const uint32_t bytes = ((a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u) + static_cast<uint32_t>(ps.c_bytes[0]) +
+        const uint32_t bytes = ((a_stream >= 0 ? static_cast<uint32_t>(kPanel) : 0u) +
+                                static_cast<uint32_t>(split_ps && b_mn ? boxes_0 * 8192 : ps.c_bytes[0]) +
                                 (nch > 1 ? static_cast<uint32_t>(ps.c_bytes[1]) : 0u)) * (kPair ? 2u : 1u);
         for (int kp = 0; kp < k_panels; ++kp) {
           mbar_wait_b(&empty_bar[s], ((fill_par >> s) & 1u) ^ 1u, p.err, 0x110u + s);
@@ -440,7 +453,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         mbar_wait_b<kPair>(&acc_empty[buf0], ((acc_par >> buf0) & 1u) ^ 1u, p.err, 0x210u + buf0);
         if (nc > 1) mbar_wait_b<kPair>(&acc_empty[buf1], ((acc_par >> buf1) & 1u) ^ 1u, p.err, 0x210u + buf1);
         ptx::tc_fence_after();
-        const uint32_t idesc0 = ptx::make_idesc(1, 0, ps.b_mn, kPair ? 256 : 128, ps.c_mma_n[0]);
+        const uint32_t idesc0 = ptx::make_idesc(1, 0, ps.b_mn, kPair ? 256 : 128, ip == p.split_pass ? p.part_n[part] : ps.c_mma_n[0]);
         const uint32_t idesc1 = ptx::make_idesc(1, 0, ps.b_mn, kPair ? 256 : 128, ps.c_mma_n[nc - 1]);
         const uint32_t boff0 = ps.c_boff[0], boff1 = ps.c_boff[nc - 1];
         const uint32_t tm0 = tmem_base + ps.c_tmem[0], tm1 = tmem_base + ps.c_tmem[nc - 1];
@@ -550,6 +563,15 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       const int N = L.N;
       const int Npad = (N + 15) & ~15;
       const int n_units = (Npad + 31) >> 5;
+      // column split (see CParams): this CTA's units [u_lo, u_hi) / columns [n_lo, n_hi) of the layer; TMEM column = column - n_lo.
+      // `shadow`: a part > 0 in a layer before the split one - it computes, but publishes nothing.
+      const bool split = il == p.split_layer;
+      const bool shadow = part > 0 && !split;
+      const int n_lo = split ? p.part_n0[part] : 0;
+      const int n_hi = split ? min(N, n_lo + p.part_n[part]) : N;
+      const int u_lo = n_lo >> 5;
+      const int u_hi = split ? (((n_hi + 15) & ~15) + 31) >> 5 : n_units;
+      const unsigned int arrivals = slabs_per_group * (split ? static_cast<unsigned int>(p.parts) : 1u);
       if (et == 0) stamp(17 + il * 4);
       auto wait_all_chunks = [&]() {
         for (int ci = 0; ci < L.n_chunks; ++ci) mbar_wait_epi(&acc_full[ci], (epi_par >> ci) & 1u, p.err, 0x300u + il * 16 + ci);
@@ -565,14 +587,16 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       // the arena's panels of this layer -> global memory through an output tensor map (one thread; asynchronous: the
       // epilogue warps issue no global stores for the activations, and the copy runs under whatever comes next)
       auto store_arena = [&](const CUtensorMap* om) {
-        const int n_panels = (N + 63) >> 6;
-        for (int pn = 0; pn < n_panels; ++pn) ptx::tma_store_2d(om, smem + pn * kPanel, pn * 64, m0);
+        if (shadow) return;
+        const int pn_hi = (n_hi + 63) >> 6;
+        for (int pn = n_lo >> 6; pn < pn_hi; ++pn) ptx::tma_store_2d(om, smem + pn * kPanel, pn * 64, m0);
         ptx::bulk_commit_group();
       };
       // publish the slab's column sums: red[quarter][stat][column] -> one global atomic per column and statistic
       auto publish_stats = [&]() {
         bar_epi();
-        for (int c = et; c < N; c += kCEpi) {
+        if (shadow) return;
+        for (int c = n_lo + et; c < n_hi; c += kCEpi) {
           const float a0 = (red[c] + red[kRedStride + c]) + (red[2 * kRedStride + c] + red[3 * kRedStride + c]);
           const float a1 = (red[400 + c] + red[kRedStride + 400 + c]) + (red[2 * kRedStride + 400 + c] + red[3 * kRedStride + 400 + c]);
           atomicAdd(L.stat0 + grp * N + c, a0);
@@ -695,7 +719,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         // trip is ~1 us; pass 1 has no registers left for that)
         auto load_hpre = [&](int u, uint2 (&h)[8]) {
           const int c0 = 32 * u + 4 * cq;
-          const bool lv = u < n_units && c0 < N;
+          const bool lv = u < u_hi && c0 < N;
 #pragma unroll
           for (int k = 0; k < 8; ++k)
             h[k] = lv ? __ldg(reinterpret_cast<const uint2*>(L.hpre + (wrow0 + (k >> 2) * 16 + 4 * rsel + (k & 3)) * N + c0))
@@ -705,13 +729,13 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         // ---- pass 1: ReLU mask, slab sums of dyhat and dyhat * xhat; the masked gradient dyhat is parked in the arena (bf16):
         //      pass 2 then needs neither TMEM nor the transposing tile nor the mask again.
         //      sum dyhat * xhat = rstd * sum(dyhat * x) - mean * rstd * sum(dyhat): the loop accumulates sum(dyhat * x)
-        for (int u = jw; u < n_units; u += 4) {
+        for (int u = u_lo + jw; u < u_hi; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N;
           uint2 hx[8];
           load_hpre(u, hx);   // in flight during the TMEM load and the first deposit
           uint32_t v[32];
-          load_unit(t_row + 32 * u, v);
+          load_unit(t_row + 32 * (u - u_lo), v);
           const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 tb = live ? tab4(s_b + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
           float s0[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
@@ -755,9 +779,9 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         release_all_chunks();
         publish_stats();
         uint2 hx2[8];
-        load_hpre(jw, hx2);
+        load_hpre(u_lo + jw, hx2);
         if (et == 0) stamp(18 + il * 4);
-        group_barrier(L.counter + grp, slabs_per_group, p.err, et);
+        group_barrier(L.counter + grp, arrivals, p.err, et, !shadow);
         if (et == 0) stamp(19 + il * 4);
         for (int c = et; c < 400; c += kCEpi) {
           if (c < N) {
@@ -773,7 +797,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         bar_epi();
         // ---- pass 2: dx = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) = a * dyhat - k1 * x + k2,
         //      in place in the arena (the next dgrad's A operand) and to global memory (the weight gradient's operand)
-        for (int u = jw; u < n_units; u += 4) {
+        for (int u = u_lo + jw; u < u_hi; u += 4) {
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
           uint2 hn[8];
@@ -949,7 +973,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
       const CLayer& L = p.layer[il];
       if (L.kind != CE_FWD_BN && L.kind != CE_DGRAD_BN) continue;
       if (et == 0)
-        for (int g = 0; g < groups; ++g) group_wait(L.counter + g, slabs_per_group, p.err);
+        for (int g = 0; g < groups; ++g)
+          group_wait(L.counter + g, slabs_per_group * (il == p.split_layer ? static_cast<unsigned int>(p.parts) : 1u), p.err);
       bar_epi();
       const int N = L.N;
       const float cnt = static_cast<float>(p.rows_per_group);
@@ -995,6 +1020,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------- host side
+int chain_sms();
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1097,7 +1123,7 @@ int launch_chain_v(const CParams& p, cudaStream_t st) {
   }
   static const int coop = env_int("MVAE_CHAIN_COOP", 1);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.n_slabs + (kPair ? 2 : 1));   // slabs + keeper (+ one idle CTA that completes the keeper's cluster)
+  cfg.gridDim = dim3(p.n_slabs * p.parts + (kPair ? 2 : 1));   // slab CTAs + keeper (+ one idle CTA that completes the keeper's cluster)
   cfg.blockDim = dim3(kCThreads);
   cfg.dynamicSmemBytes = kSmemTotal;
   cfg.stream = st;
@@ -1128,7 +1154,7 @@ int launch_chain(const CParams& p, bool pair, cudaStream_t st) {
 // CTA pairs (cta_group::2): an even number of slabs, and room for the keeper's cluster
 bool chain_pair(int n_slabs) {
   static const int on = env_int("MVAE_CHAIN_PAIR", 1);
-  return on != 0 && n_slabs % 2 == 0 && n_slabs + 2 <= 148;
+  return on != 0 && n_slabs % 2 == 0 && n_slabs + 2 <= chain_sms();
 }
 constexpr int kPairStage = 16384;   // resident-A layers of a pair: half a weight chunk per CTA, four stages in the same 64 KB
 void pair_rings(CParams& p) { p.ring[1] = CRing{kArena, kPairStage, 4, 0}; }
@@ -1141,6 +1167,9 @@ void init_params(CParams& p, int rows_per_group, int n_slabs, unsigned int* err,
   p.rows_per_group = rows_per_group;
   p.n_slabs = n_slabs;
   p.init_tm = -1;
+  p.parts = 1;
+  p.split_layer = -1;
+  p.split_pass = -1;
   p.momentum = 0.1f;
   p.eps = 1e-5f;
   p.err = err;
@@ -1154,13 +1183,19 @@ void init_params(CParams& p, int rows_per_group, int n_slabs, unsigned int* err,
 void set_chain_debug_times(void* ptr) { g_chain_dbg = static_cast<long long*>(ptr); }
 
 // true if the chain kernels can run this step: all slabs whole, co-resident (plus the keeper CTA), dimensions inside the on-chip plan
-bool chain_supported(int B, int G, int n) {
+namespace {
+int chain_sms() {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
+  return sms;
+}
+}  // namespace
+bool chain_supported(int B, int G, int n) {
+  const int sms = chain_sms();
   return B >= 128 && B % 128 == 0 && G >= 1 && G <= 3 && (G * B) / 128 + 2 <= sms && n >= 16 && n <= 64 && n % 16 == 0;
 }
 
@@ -1313,10 +1348,27 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   CLayer& l2 = p.layer[0];
   CLayer& l1 = p.layer[1];
   int ip = 0;
-  const bool pair = chain_pair(slabs);
+  // 33 of 148 SMs would carry this kernel: the last layer's 400 columns are split over up to four CTAs per slab instead
+  // (each repeats the small first layer on its own), which is worth more here than pairing the slabs
+  static const int split_on = env_int("MVAE_CHAIN_SPLIT", 1);
+  const int parts = !split_on ? 1 : (4 * slabs + 1 <= chain_sms() ? 4 : (2 * slabs + 1 <= chain_sms() ? 2 : 1));
+  const bool pair = parts == 1 && chain_pair(slabs);
   if (pair) pair_rings(p);
   ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false, pair);
-  ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false, pair);
+  if (parts > 1) {
+    p.parts = parts;
+    p.split_layer = 1;
+    p.split_pass = ip;
+    const int n0_4[4] = {0, 128, 256, 320}, n_4[4] = {128, 128, 64, 80};
+    const int n0_2[4] = {0, 256, 0, 0}, n_2[4] = {256, 144, 0, 0};
+    for (int j = 0; j < 4; ++j) {
+      p.part_n0[j] = parts == 4 ? n0_4[j] : n0_2[j];
+      p.part_n[j] = parts == 4 ? n_4[j] : n_2[j];
+    }
+    ip = add_resident_layer(p, ip, l1, p.part_n[0], 200, 2, true, 2, false, false);   // one chunk per part, widths from part_n
+  } else {
+    ip = add_resident_layer(p, ip, l1, 400, 200, 2, true, 2, false, pair);
+  }
   p.n_pass = ip;
   if (chain_tmap(&p.tmo[1], a.dye2, a.B, 200, 200, 64, 128)) return 1;
   if (chain_tmap(&p.tmo[3], a.dye1, a.B, 400, 400, 64, 128)) return 1;
