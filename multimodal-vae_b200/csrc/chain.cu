@@ -1351,7 +1351,7 @@ int launch_chain_enc_bwd(const ChainEncBwd& a, cudaStream_t st) {
   // 33 of 148 SMs would carry this kernel: the last layer's 400 columns are split over up to four CTAs per slab instead
   // (each repeats the small first layer on its own), which is worth more here than pairing the slabs
   static const int split_on = env_int("MVAE_CHAIN_SPLIT", 1);
-  const int parts = !split_on ? 1 : (4 * slabs + 1 <= chain_sms() ? 4 : (2 * slabs + 1 <= chain_sms() ? 2 : 1));
+  const int parts = !split_on ? 1 : (a.max_parts >= 4 && 4 * slabs + 1 <= chain_sms() ? 4 : (a.max_parts >= 2 && 2 * slabs + 1 <= chain_sms() ? 2 : 1));
   const bool pair = parts == 1 && chain_pair(slabs);
   if (pair) pair_rings(p);
   ip = add_resident_layer(p, ip, l2, 200, n2, 1, true, 1, false, pair);

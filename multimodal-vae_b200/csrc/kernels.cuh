@@ -200,6 +200,7 @@ struct ChainEncBwd {
   __nv_bfloat16 *dye2 = nullptr, *dye1 = nullptr;
   float *dgamma1 = nullptr, *dbeta1 = nullptr, *dgamma2 = nullptr, *dbeta2 = nullptr;
   unsigned int* err = nullptr;
+  int max_parts = 4;   // column split of the last layer: CTAs per slab (fewer when another kernel needs SMs beside this one)
 };
 int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st);
 int launch_chain_dec_fwd(const ChainDecFwd& a, cudaStream_t st);

@@ -663,6 +663,10 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     cb.dgamma1 = gf("image_encoder.net.1.weight"); cb.dbeta1 = gf("image_encoder.net.1.bias");
     cb.dgamma2 = gf("image_encoder.net.4.weight"); cb.dbeta2 = gf("image_encoder.net.4.bias");
     cb.err = chain_err;
+    // phase 4 = the data-parallel trainer's encoder side: the decoder bucket's exchange kernel runs beside this launch and
+    // needs SMs of its own
+    static const int dp_parts = env_int("MVAE_CHAIN_SPLIT_DP", 2);
+    cb.max_parts = a->phase == 4 ? dp_parts : 4;
     MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
     enc_chain_launched = true;
     return 0;

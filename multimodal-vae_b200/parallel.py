@@ -9,6 +9,7 @@ shards equals the gradient of the global mean.  There is no other exchange on th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Sequence, Tuple
 
 import torch
@@ -69,6 +70,7 @@ class DataParallelTrainer(MVAETrainer):
         self.dp_graph = use_cuda_graph
         self._dp_graphs = {}
         self.overlap = overlap
+        self.dec_exchange_blocks = int(os.environ.get("MVAE_DP_DEC_BLOCKS", "32"))
         self.comm_stream = torch.cuda.Stream(device=model.device_)
         from .mnist import sizes
         self.enc_floats = int(sizes(model.n_latents, 2, model.dtype_code).encoder_param_floats)
@@ -114,8 +116,9 @@ class DataParallelTrainer(MVAETrainer):
         torch.cuda.synchronize()
         dist.barrier(group=self.group)
 
-    def _reduce_adam(self, lo: int, hi: int) -> None:
-        """Enqueue the fused exchange + update of bucket [lo, hi) on the current stream (a collective)."""
+    def _reduce_adam(self, lo: int, hi: int, blocks: int = 0) -> None:
+        """Enqueue the fused exchange + update of bucket [lo, hi) on the current stream (a collective).  `blocks`: grid size
+        (0 = the library's default)."""
         m, a = self.model, self.adam
         args = _lib.DpReduceAdamArgs()
         args.world, args.rank = self.world, self.rank
@@ -129,7 +132,7 @@ class DataParallelTrainer(MVAETrainer):
         args.lr, args.beta1, args.beta2, args.eps = a["lr"], a["betas"][0], a["betas"][1], a["eps"]
         args.grad_scale = 1.0 / self.world
         args.adam_step = m._adam_counter.data_ptr()
-        args.blocks = 0
+        args.blocks = int(blocks)
         _lib.check(_lib.load().mvae_dp_reduce_adam(C.byref(args), _stream_ptr()), "mvae_dp_reduce_adam")
 
     def _local_then_reduce(self, x, y, eps, terms, lambdas, annealing_factor, losses=None):
@@ -149,7 +152,10 @@ class DataParallelTrainer(MVAETrainer):
             if self.overlap:
                 self.comm_stream.wait_stream(main)
                 with torch.cuda.stream(self.comm_stream):
-                    self._reduce_adam(split, total)
+                    # a small grid: the encoder-side backward beside it spreads over 65 SMs (csrc/chain.cu: column split, two
+                    # parts per slab in phase 4) and a chain CTA needs an SM to itself - these blocks stay out of its way
+                    # (2 GPUs, us/step: no split / 96 blocks 274; 2 parts / 19..48 blocks 267; 4 parts: 266..290)
+                    self._reduce_adam(split, total, blocks=self.dec_exchange_blocks)
             m._run(x, y, tt, lambdas, klw, eps=eps, backward=True, zero_grad=False, adam=None, losses=losses,
                    extra={"phase": 4})
             if self.overlap:
