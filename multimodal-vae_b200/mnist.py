@@ -184,11 +184,13 @@ class MVAE(nn.Module):
     def act_dtype(self) -> torch.dtype:
         return torch.bfloat16 if self.dtype_code == _lib.DT_BF16 else torch.float32
 
-    def to_act(self, image: torch.Tensor) -> torch.Tensor:
-        """image.view(-1, 784) in the storage dtype of the tensor-core path (mnist/train.py:131)."""
+    def to_act(self, image: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """image.view(-1, 784) in the storage dtype of the tensor-core path (mnist/train.py:131).  `out`: uint8 pixels are
+        converted straight into this buffer (the graph trainer's static input)."""
         x = image.reshape(-1, 784)
         if x.dtype == torch.uint8:
-            out = torch.empty(x.shape, device=self.device_, dtype=self.act_dtype())
+            if out is None:
+                out = torch.empty(x.shape, device=self.device_, dtype=self.act_dtype())
             xd = x.to(self.device_, non_blocking=True).contiguous()
             f32 = out.data_ptr() if self.dtype_code != _lib.DT_BF16 else None
             b16 = out.data_ptr() if self.dtype_code == _lib.DT_BF16 else None
@@ -449,8 +451,8 @@ class MVAETrainer:
         self._stage_stream = None
 
     def _graph_input(self, image):
-        """What the captured graph takes as its image input: a uint8 device batch goes in as it is (the conversion to
-        the activation dtype is the graph's first node - the step consumes uint8), anything else through to_act()."""
+        """What a graph step takes as its image input: a uint8 device batch goes in as it is (_stage converts it straight
+        into the graph's static activation buffer, beside the previous step), anything else through to_act()."""
         if image.dtype == torch.uint8 and image.is_cuda:
             return image.reshape(-1, 784).contiguous()
         return self.model.to_act(image)
@@ -472,7 +474,10 @@ class MVAETrainer:
             if ready is not True:
                 st.wait_event(ready)
         with torch.cuda.stream(st):
-            ent["x"].copy_(x, non_blocking=True)
+            if x.dtype == torch.uint8 and ent["x"].dtype != torch.uint8:
+                self.model.to_act(x, out=ent["x"])   # mvae_u8_to_act on the staging stream
+            else:
+                ent["x"].copy_(x, non_blocking=True)
             ent["y"].copy_(y, non_blocking=True)
             if eps is not None:
                 ent["eps"].copy_(eps, non_blocking=True)
@@ -590,7 +595,10 @@ class MVAETrainer:
                float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), float(self.grad_scale), x.dtype, self._slot)
         ent = self._graph_cache_get(self._graphs, key)
         if ent is None:
-            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            # uint8 pixels never enter the graph: the conversion to the storage dtype IS the staging copy (stage stream,
+            # beside the previous step), so the step's first node is the encoder chain itself
+            sx = torch.empty(x.shape, device=m.device_, dtype=m.act_dtype()) if x.dtype == torch.uint8 else torch.empty_like(x)
+            sy = torch.empty_like(y)
             se = torch.empty_like(eps) if eps is not None else None
             losses = torch.empty(len(terms), 4, device=m.device_, dtype=torch.float32)
             tt, klw = self._norm(terms, x.shape[0], annealing_factor)
@@ -603,7 +611,7 @@ class MVAETrainer:
             before = lib.mvae_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                m._run(m.to_act(sx), sy, tt, lambdas, klw, **kw)   # uint8 input: the conversion kernel is the first node
+                m._run(sx, sy, tt, lambdas, klw, **kw)
             ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses, "fresh": True,
                    "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
                    "launches": int(lib.mvae_launch_count() - before) + (1 if x.dtype == torch.uint8 else 0)}
@@ -628,6 +636,7 @@ class HostPipeline:
         self.trainer = trainer
         self.dev = trainer.model.device_
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.d2h_stream = torch.cuda.Stream(device=self.dev)   # loss read-back: not between two steps on the main stream
         self.depth = depth
         self._slots = []
 
@@ -679,8 +688,13 @@ class HostPipeline:
             sl["free"].record(main)
             if sl["loss_host"] is None or sl["loss_host"].shape != losses.shape:
                 sl["loss_host"] = torch.empty(losses.shape, dtype=losses.dtype).pin_memory()
-            sl["loss_host"].copy_(losses, non_blocking=True)
-            sl["loss_evt"].record(main)
+            # (graph trainers hand out one of two alternating static loss buffers: this copy is complete - the generator
+            # synchronises on it one step later - before the buffer's next step is enqueued)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(sl["free"])
+                sl["loss_host"].copy_(losses, non_blocking=True)
+                sl["loss_evt"].record(self.d2h_stream)
+            losses.record_stream(self.d2h_stream)
             inflight.append(sl)
             b = next(it, None)
             if b is not None:

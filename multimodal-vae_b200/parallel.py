@@ -212,7 +212,9 @@ class DataParallelTrainer(MVAETrainer):
                float(a_["lr"]), tuple(map(float, a_["betas"])), float(a_["eps"]), x.dtype, self._slot)
         ent = self._graph_cache_get(self._dp_graphs, key)
         if ent is None:
-            sx, sy = torch.empty_like(x), torch.empty_like(y)
+            # uint8 pixels are converted by the staging copy (MVAETrainer._stage), not by a node of the graph
+            sx = torch.empty(x.shape, device=m.device_, dtype=m.act_dtype()) if x.dtype == torch.uint8 else torch.empty_like(x)
+            sy = torch.empty_like(y)
             se = torch.empty_like(eps) if eps is not None else None
             losses = torch.empty(len(terms), 4, device=m.device_, dtype=torch.float32)
             # NCCL must have been used once outside capture (communicator setup is not capturable)
@@ -223,7 +225,7 @@ class DataParallelTrainer(MVAETrainer):
             before = lib.mvae_launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._local_then_reduce(m.to_act(sx), sy, se, terms, lambdas, annealing_factor, losses=losses)
+                self._local_then_reduce(sx, sy, se, terms, lambdas, annealing_factor, losses=losses)
             ent = {"graph": graph, "x": sx, "y": sy, "eps": se, "losses": losses, "fresh": True,
                    "free": torch.cuda.Event(), "ready": torch.cuda.Event(),
                    "launches": int(lib.mvae_launch_count() - before) + (1 if x.dtype == torch.uint8 else 0)}
