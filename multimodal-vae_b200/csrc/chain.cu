@@ -140,6 +140,9 @@ struct alignas(64) CParams {
   long long* dbg;         // bring-up: [ctas][32] %globaltimer stamps (mvae_debug_chain_times), or null
 };
 
+// time-outs of the waits below count SM cycles (%clock64 is SM-local and cheap; %globaltimer is a slow read that would
+// sit in every blocking wait): ~1.9 GHz, so 8e9 cycles ~ 4 s
+__device__ __forceinline__ unsigned long long cyc() { return static_cast<unsigned long long>(clock64()); }
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -155,10 +158,10 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 template <bool kPair = false>
 __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned int code) {
   if (mbar_try<kPair>(bar, parity)) return;
-  const unsigned long long t0 = gtimer();
+  const unsigned long long t0 = cyc();
   unsigned int spins = 0;
   while (!mbar_try<kPair>(bar, parity)) {
-    if ((++spins & 1023u) == 0 && gtimer() - t0 > 4000000000ull) {
+    if ((++spins & 1023u) == 0 && cyc() - t0 > 8000000000ull) {
       if (err != nullptr) atomicExch(err, code);
       __threadfence();
       asm volatile("trap;");
@@ -170,11 +173,11 @@ __device__ __forceinline__ void mbar_wait_b(uint64_t* bar, uint32_t parity, unsi
 // the producer / MMA threads that share their schedulers
 __device__ __forceinline__ void mbar_wait_epi(uint64_t* bar, uint32_t parity, unsigned int* err, unsigned int code) {
   if (ptx::mbar_try_wait(bar, parity)) return;
-  const unsigned long long t0 = gtimer();
+  const unsigned long long t0 = cyc();
   unsigned int spins = 0;
   while (!ptx::mbar_try_wait(bar, parity)) {
     __nanosleep(64);
-    if ((++spins & 255u) == 0 && gtimer() - t0 > 4000000000ull) {
+    if ((++spins & 255u) == 0 && cyc() - t0 > 8000000000ull) {
       if (err != nullptr) atomicExch(err, code);
       __threadfence();
       asm volatile("trap;");
@@ -239,12 +242,12 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
   if (et == 0) {
     if (arrive) atomicAdd(counter, 1u);
     unsigned int seen = 0;
-    const unsigned long long t0 = gtimer();
+    const unsigned long long t0 = cyc();
     unsigned int spins = 0;
     while (true) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
       if (seen >= expected) break;
-      if ((++spins & 255u) == 0 && gtimer() - t0 > 2000000000ull) {
+      if ((++spins & 255u) == 0 && cyc() - t0 > 4000000000ull) {
         if (err != nullptr) atomicExch(err, 0xBA00u | (seen & 0xffu));
         break;
       }
@@ -257,12 +260,12 @@ __device__ __forceinline__ void group_barrier(unsigned int* counter, unsigned in
 // wait (without arriving) until a group's counter is complete - the keeper CTA
 __device__ __forceinline__ void group_wait(const unsigned int* counter, unsigned int expected, unsigned int* err) {
   unsigned int seen = 0;
-  const unsigned long long t0 = gtimer();
+  const unsigned long long t0 = cyc();
   unsigned int spins = 0;
   while (true) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
     if (seen >= expected) break;
-    if ((++spins & 255u) == 0 && gtimer() - t0 > 2000000000ull) {
+    if ((++spins & 255u) == 0 && cyc() - t0 > 4000000000ull) {
       if (err != nullptr) atomicExch(err, 0xBB00u | (seen & 0xffu));
       break;
     }
@@ -613,9 +616,9 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         bar_epi();
         wait_all_chunks();
         // ---- pass 1: slab statistics; the bf16 pre-activations are parked in the arena (the layer's own A operand is spent)
-        for (int u = jw; u < n_units; u += 4) {
+        for (int u = u_lo + jw; u < u_hi; u += 4) {
           uint32_t v[32];
-          load_unit(t_row + 32 * u, v);
+          load_unit(t_row + 32 * (u - u_lo), v);
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
           const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -653,9 +656,22 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         ptx::fence_proxy_async_smem();             // the parked pre-activations are read by the TMA store below
         publish_stats();                           // (starts with a barrier of the epilogue warps)
         if (et == 0) store_arena(&p.tmo[2 * il]);  // pre-BatchNorm activations -> global (the backward reads them)
+        // column split: the other parts of this slab fetch these columns from there after the barrier - the copy has to be
+        // complete (not just read out of the arena) before this CTA arrives
+        const bool exchange = split && p.parts > 1;
+        if (exchange && et == 0) ptx::bulk_wait_all();
         if (et == 0) stamp(18 + il * 4);
-        group_barrier(L.counter + grp, slabs_per_group, p.err, et);
+        group_barrier(L.counter + grp, arrivals, p.err, et, !shadow);
         if (et == 0) stamp(19 + il * 4);
+        if (exchange && et == 0) {
+          // the partners' pre-activations: their panels of the same rows, global (L2) -> this CTA's arena; every part then
+          // normalises the whole slab itself (pass 2 below), so the next layer finds its full A operand on chip
+          ptx::fence_proxy_async_all();
+          const int pn_lo = n_lo >> 6, pn_hi = (n_hi + 63) >> 6, pn_all = (N + 63) >> 6;
+          ptx::mbar_expect_tx(a_tma_bar, static_cast<uint32_t>((pn_all - (pn_hi - pn_lo)) * kPanel));
+          for (int pn = 0; pn < pn_all; ++pn)
+            if (pn < pn_lo || pn >= pn_hi) ptx::tma_load_2d(smem + pn * kPanel, &p.tmo[2 * il], a_tma_bar, pn * 64, m0);
+        }
         for (int c = et; c < 400; c += kCEpi) {
           float a_ = 0.f, b_ = 0.f;
           if (c < N) {
@@ -673,6 +689,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           s_cb[c] = b_;
         }
         if (et == 0) ptx::bulk_wait_read_all();    // pass 2 overwrites the arena in place
+        if (exchange) mbar_wait_epi(a_tma_bar, 0, p.err, 0x3F0u + il);   // (one split layer per kernel: phase 0)
         bar_epi();
         // ---- pass 2: BatchNorm + ReLU in place in the arena -> next layer's A operand; both copies the backward and the
         //      weight gradients need go to global memory from here (after the barrier: nothing for its fence to wait on)
@@ -841,7 +858,7 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
-            if (live) {
+            if (live && !shadow) {
               float* dst = L.out_f32 + (wrow0 + half * 16 + 4 * rsel) * L.ld_out + col0;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -1204,15 +1221,22 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   const int slabs = a.B / 128;
   init_params(p, a.B, slabs, a.err, 0);
   const int n2 = 2 * a.n;
-  const bool pair = chain_pair(slabs);
+  // The first layer (75 % of the kernel's FLOPs, tensor-bound on 32 SMs) split by columns over four CTAs per slab: each
+  // part computes its columns of x W1^T, the parts swap pre-activations through L2 behind the BatchNorm barrier they
+  // share anyway, and each normalises the whole slab; the two small layers after it are repeated by every part.
+  static const int split_want = env_int("MVAE_CHAIN_SPLIT_FWD", 4);
+  const int parts = split_want >= 4 && 4 * slabs + 1 <= chain_sms() ? 4 : (split_want >= 2 && 2 * slabs + 1 <= chain_sms() ? 2 : 1);
+  const bool pair = parts == 1 && chain_pair(slabs);
   const int hv = pair ? 2 : 1;   // a CTA of a pair loads half of every weight tile
   if (chain_tmap(&p.tm[0], a.image, a.B, 784, 784, 64, 128)) return 1;
-  if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, 208 / hv)) return 1;
+  if (chain_tmap(&p.tm[1], a.w1, 400, 784, 784, 64, parts == 4 ? 128 : (parts == 2 ? 256 : 208 / hv))) return 1;
   if (chain_tmap(&p.tm[2], a.w2, 200, 400, 400, 64, kFwdChunk / hv)) return 1;
   if (chain_tmap(&p.tm[3], a.w3, n2, 200, 200, 64, kFwdChunk / hv)) return 1;
   p.tm[4] = p.tm[3];
   // streamed image panel + all 400 rows of W1 per 64-wide k panel: 2 stages of 68 KB, or - pairs - 4 stages of 42 KB
   p.ring[0] = CRing{0, kPanel + 2 * 26624 / hv, pair ? 4 : 2, kPanel};
+  if (parts == 4) p.ring[0] = CRing{0, 2 * kPanel, 4, kPanel};   // image panel + up to 128 rows of W1
+  if (parts == 2) p.ring[0] = CRing{0, 3 * kPanel, 3, kPanel};   // image panel + up to 256 rows of W1
   if (pair) pair_rings(p);
   p.n_layers = 3;
   CLayer& l1 = p.layer[0];
@@ -1224,6 +1248,20 @@ int launch_chain_enc_fwd(const ChainEncFwd& a, cudaStream_t st) {
   set_chunk(e1, 0, 0, 208, 0, 26624 / hv, 0, 0, 0, pair);
   set_chunk(e1, 1, 208, 192, 0, 26624 / hv, 26624 / hv, 208, 1, pair);
   l1.kind = CE_FWD_BN; l1.N = 400; l1.n_chunks = 2;
+  if (parts > 1) {
+    p.parts = parts;
+    p.split_layer = 0;
+    p.split_pass = 0;
+    const int n0_4[4] = {0, 128, 256, 320}, n_4[4] = {128, 128, 64, 80};   // whole 64-column panels (TMA stores / loads)
+    const int n0_2[4] = {0, 256, 0, 0}, n_2[4] = {256, 144, 0, 0};
+    for (int j = 0; j < 4; ++j) {
+      p.part_n0[j] = parts == 4 ? n0_4[j] : n0_2[j];
+      p.part_n[j] = parts == 4 ? n_4[j] : n_2[j];
+    }
+    e1.n_chunks = 1;
+    set_chunk(e1, 0, 0, p.part_n[0], 0, p.part_n[0] * 128, 0, 0, 0);
+    l1.n_chunks = 1;
+  }
   int ip = 1;
   ip = add_resident_layer(p, ip, l2, 200, 400, 2, false, 2, false, pair);
   ip = add_resident_layer(p, ip, l3, n2, 200, 3, false, 2, false, pair);
