@@ -226,6 +226,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// packed fp32 pairs (sm_100 add / mul / fma .f32x2: one issue slot for two lanes of arithmetic)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 __device__ __forceinline__ float4 tab4(const float* t) { return *reinterpret_cast<const float4*>(t); }
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float v[4];
@@ -878,7 +901,10 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         bar_epi();
         const float scale = grp == 0 ? L.bce_scale[0] : (grp == 1 ? L.bce_scale[1] : L.bce_scale[2]);
         const __nv_bfloat16* tbase = L.target + (static_cast<long long>(m0 % L.target_rows) + q * 32) * N;
-        float lin = 0.f, llog = 0.f;   // sum of max(x, 0) - t x  and  sum of log2 sigmoid(|x|)
+        // sums of max(x, 0), of t x (pairs of lanes: packed arithmetic) and of log2 sigmoid(|x|)
+        f2 macc = pk2(0.f, 0.f), txacc = pk2(0.f, 0.f);
+        float llog = 0.f;
+        const f2 one2 = pk2(1.f, 1.f), sc2 = pk2(scale, scale), nsc2 = pk2(-scale, -scale);
         // The accumulator arrives in chunks (TMEM buffer = chunk & 1) while the MMA warp works on the next one; the 32-column
         // units of the whole layer go round-robin over the four warps of a quarter.  Every warp waits for and releases every
         // chunk in order (an arrival on a buffer's "empty" barrier must follow this warp's wait on its "full" phase).
@@ -908,8 +934,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           uint32_t v[32];
           load_unit(t_row + (ci & 1) * buf_cols + 32 * (u - ustart), v);
           const float4 bs = live ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float bsv[4] = {bs.x, bs.y, bs.z, bs.w};
-          float sd[4] = {0.f, 0.f, 0.f, 0.f};
+          const f2 bs01 = pk2(bs.x, bs.y), bs23 = pk2(bs.z, bs.w);
+          f2 sd01 = pk2(0.f, 0.f), sd23 = pk2(0.f, 0.f);
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             deposit(half, v);
@@ -918,31 +944,52 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
-                const float av[4] = {a.x, a.y, a.z, a.w};
                 const uint2 tw = tx[half * 4 + i];
-                const float tv[4] = {bf_lo(tw.x), bf_hi(tw.x), bf_lo(tw.y), bf_hi(tw.y)};
-                float d[4], pr[4];
-                float prod = 1.f;
+                uint32_t dw[2], pw[2];
+                f2 prod2;
+                // softplus(x) - t x = max(x, 0) - t x - ln sigmoid(|x|); two elements per packed operation
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float x = av[e] + bsv[e];
-                  const float ex = ptx::ex2_approx(-1.4426950408889634f * fabsf(x));   // exp(-|x|) in (0, 1]
-                  const float inv = ptx::rcp_approx(1.f + ex);                          // sigmoid(|x|) in [0.5, 1)
-                  pr[e] = x >= 0.f ? inv : ex * inv;
-                  d[e] = scale * (pr[e] - tv[e]);
-                  sd[e] += d[e];
-                  prod *= inv;                                                           // >= 1/16: one log per four elements
-                  lin += fmaf(-tv[e], x, fmaxf(x, 0.f));                                 // softplus(x) - t x = max(x,0) - t x - ln sigmoid(|x|)
+                for (int h2 = 0; h2 < 2; ++h2) {
+                  const uint32_t tword = h2 == 0 ? tw.x : tw.y;
+                  const f2 t2 = pk2(bf_lo(tword), bf_hi(tword));
+                  const f2 x2 = add2(h2 == 0 ? pk2(a.x, a.y) : pk2(a.z, a.w), h2 == 0 ? bs01 : bs23);
+                  float x0, x1;
+                  upk2(x2, x0, x1);
+                  const float e0 = ptx::ex2_approx(-1.4426950408889634f * fabsf(x0));   // exp(-|x|) in (0, 1]
+                  const float e1 = ptx::ex2_approx(-1.4426950408889634f * fabsf(x1));
+                  const f2 ex2v = pk2(e0, e1);
+                  float den0, den1;
+                  upk2(add2(ex2v, one2), den0, den1);
+                  const float i0 = ptx::rcp_approx(den0), i1 = ptx::rcp_approx(den1);    // sigmoid(|x|) in [0.5, 1)
+                  const f2 inv2 = pk2(i0, i1);
+                  float q0, q1;
+                  upk2(mul2(ex2v, inv2), q0, q1);
+                  const f2 p2 = pk2(x0 >= 0.f ? i0 : q0, x1 >= 0.f ? i1 : q1);
+                  const f2 d2 = fma2(t2, nsc2, mul2(p2, sc2));                           // scale * (p - t)
+                  if (h2 == 0) sd01 = add2(sd01, d2);
+                  else sd23 = add2(sd23, d2);
+                  prod2 = h2 == 0 ? inv2 : mul2(prod2, inv2);                            // >= 1/16 per lane: one log per four elements
+                  macc = add2(macc, pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+                  txacc = fma2(t2, x2, txacc);
+                  float d0, d1, p0, p1;
+                  upk2(d2, d0, d1);
+                  upk2(p2, p0, p1);
+                  dw[h2] = pack_bf16(d0, d1);
+                  pw[h2] = pack_bf16(p0, p1);
                 }
-                llog += ptx::lg2_approx(prod);
-                *reinterpret_cast<uint2*>(L.dlog + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(d[0], d[1]), pack_bf16(d[2], d[3]));
-                if (L.probs != nullptr)
-                  *reinterpret_cast<uint2*>(L.probs + orow + static_cast<long long>(i) * N) = make_uint2(pack_bf16(pr[0], pr[1]), pack_bf16(pr[2], pr[3]));
+                float pl, ph;
+                upk2(prod2, pl, ph);
+                llog += ptx::lg2_approx(pl * ph);
+                *reinterpret_cast<uint2*>(L.dlog + orow + static_cast<long long>(i) * N) = make_uint2(dw[0], dw[1]);
+                if (L.probs != nullptr) *reinterpret_cast<uint2*>(L.probs + orow + static_cast<long long>(i) * N) = make_uint2(pw[0], pw[1]);
               }
             }
             __syncwarp();
           }
           if (L.dbias != nullptr) {
+            float sd[4];
+            upk2(sd01, sd[0], sd[1]);
+            upk2(sd23, sd[2], sd[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               sd[e] += __shfl_xor_sync(0xffffffffu, sd[e], 8);
@@ -964,7 +1011,10 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         }
         ptx::tc_fence_before();
         epi_arrive(&acc_empty[ci_waited & 1]);
-        float lsum = fmaf(-0.6931471805599453f, llog, lin);
+        float m_lo, m_hi, tx_lo, tx_hi;
+        upk2(macc, m_lo, m_hi);
+        upk2(txacc, tx_lo, tx_hi);
+        float lsum = fmaf(-0.6931471805599453f, llog, (m_lo + m_hi) - (tx_lo + tx_hi));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
         if (lane == 0 && L.loss != nullptr) atomicAdd(L.loss + grp, scale * lsum);
