@@ -579,8 +579,9 @@ def run_device(args):
     if chained:
         # the decoder's forward chain: three Linears with in-kernel BatchNorm grid barriers + sigmoid/BCE/dlogits epilogue
         dom_label, dom_ms, dom_flops = "chain_dec_fwd", agg["chain_dec_fwd"], chain_flops["chain_dec_fwd"]
-        dom_name = ("mvae::chain_kernel<FWD_BN, FWD_BN, BCE> (slab-persistent decoder forward: Linear n-200, 200-400, 400-784 on "
-                    "tcgen05/TMA with in-kernel BatchNorm grid barriers + fused sigmoid/BCE/dlogits epilogue; the most expensive launch)")
+        dom_name = ("mvae::chain_kernel<FWD_BN, FWD_BN, BCE, pair> (slab-persistent decoder forward: Linear n-200, 200-400, 400-784 on "
+                    "tcgen05 cta_group::2 / TMA with in-kernel BatchNorm grid barriers + fused sigmoid/BCE/dlogits epilogue; the most "
+                    "expensive launch)")
     else:
         dom_label, dom_ms, dom_flops = "gemm_fwd_bce", agg.get("gemm_fwd_bce", 0.0), 2.0 * 3 * B * 784 * 400
         dom_name = ("mvae::gemm_kernel<BCE> (tcgen05/TMA GEMM [3B,400]x[784,400]^T + fused sigmoid/BCE/dlogits epilogue; the most "

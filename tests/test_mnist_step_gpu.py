@@ -97,8 +97,11 @@ def test_tf32_step_matches_reference_golden(name):
                 np.testing.assert_allclose(sd[nm].cpu().numpy(), g[key], rtol=2e-3, atol=2e-4, err_msg=nm)
 
 
-def test_bf16_step_close_to_oracle():
-    B, n, seed = 256, 64, 2
+@pytest.mark.parametrize("B,n", [(256, 64), (384, 32), (128, 16)])
+def test_bf16_step_close_to_oracle(B, n):
+    """The slab-persistent chain kernels in their instantiations: B = 256 - CTA pairs for the decoder (6 slabs), four column
+    parts per encoder slab; B = 384 / 128 - an odd number of decoder slabs (9 / 3): the single-CTA kernels."""
+    seed = 2
     state = O.perturbed_state(n, seed)
     image, text, noises = O.synthetic_batch(B, n, seed)
     m, _, dl, _ = run_device_step(state, image, text, noises, n, "bf16")
