@@ -161,6 +161,9 @@ class ConvMVAEBase:
         self.implicit_conv = self.act_dtype == torch.bfloat16
         self.implicit_col2im = self.implicit_conv
         self.convt_merged = True
+        # BatchNorm batch statistics of the encoder's conv layers from the conv GEMM's epilogue (col_sum / col_sumsq of
+        # mvae_gemm) instead of a reduction pass over the stored pre-activations
+        self.epilogue_bn_stats = os.environ.get("MVAE_CONV_EPI_STATS", "1") != "0"
         # the second modality's networks (attribute MLPs / GRU text encoder + decoder: many latency-sized launches) run on their
         # own stream beside the image networks
         self.mod_stream = torch.cuda.Stream(device=dev)
@@ -380,6 +383,9 @@ class ConvMVAEBase:
         """The image encoder's conv stack (celeba/model.py:101-113, multimnist/model.py:159-171): ws.enc_act[-1] is the
         NHWC bottleneck [B, FLAT_HW * FLAT_C]."""
         src = image
+        epi_stats = training and self.epilogue_bn_stats
+        if epi_stats:
+            ws.enc_stats.zero_()
         for li, (pre, ci, co, k, s, p, hin, bn) in enumerate(self.ENC_CONVS):
             ho = _ops.out_size(hin, k, s, p)
             K = k * k * ci
@@ -388,15 +394,18 @@ class ConvMVAEBase:
             g = _ops.geometry(B, hin, hin, ci, k, s, p, strides)
             rows = B * ho * ho
             w, ldw = self.operand(pre + ".weight", co, K)
+            # BatchNorm batch statistics (celeba/model.py:104-111) = column sums of the conv GEMM's output: from its epilogue
+            st = dict(col_sum=ws.enc_sum[li], col_sumsq=ws.enc_sumsq[li], rows_per_group=rows) if (bn and epi_stats) else {}
             if self._implicit(ci, li > 0, rows, B * hin * hin * ci):
-                _ops.gemm(src, w, ws.enc_pre[li], rows, co, K, 0, ldw, co, patch=(g, 1))
+                _ops.gemm(src, w, ws.enc_pre[li], rows, co, K, 0, ldw, co, patch=(g, 1), **st)
             else:
                 _ops.im2col(g, src, ws.enc_col[li], ldk)
-                _ops.gemm(ws.enc_col[li], w, ws.enc_pre[li], rows, co, K, ldk, ldw, co)
+                _ops.gemm(ws.enc_col[li], w, ws.enc_pre[li], rows, co, K, ldk, ldw, co, **st)
             if bn:
                 rm, rv = self.running(bn)
                 a = _ops.bn_args(ws.enc_pre[li], rows, co, rows, SWISH, training, self.P(bn + ".weight"), self.P(bn + ".bias"),
-                                 ws.enc_sum[li], ws.enc_sumsq[li], ws.enc_mean[li], ws.enc_rstd[li], rm, rv, updates=updates)
+                                 ws.enc_sum[li], ws.enc_sumsq[li], ws.enc_mean[li], ws.enc_rstd[li], rm, rv, updates=updates,
+                                 stats_ready=bool(st))
                 _ops.bn_act_forward(a, ws.enc_act[li])
             else:
                 _ops.act_forward(SWISH, ws.enc_pre[li], ws.enc_act[li], rows, co)
@@ -533,6 +542,15 @@ class ConvMVAEBase:
                 lst.append(buf(co, dtype=f32))
             if li > 0:
                 colmax = max(colmax, rows * ldk)
+        # the forward statistics of the encoder's BatchNorm layers come out of the conv GEMMs' epilogues (column sums added
+        # with atomics): their accumulators live in ONE buffer that a single memset clears
+        tot = sum(co for (_, _, co, *_r) in self.ENC_CONVS)
+        ws.enc_stats = buf(2 * tot, dtype=f32)
+        off = 0
+        for li, (pre, ci, co, *_r) in enumerate(self.ENC_CONVS):
+            ws.enc_sum[li] = ws.enc_stats[off:off + co]
+            ws.enc_sumsq[li] = ws.enc_stats[tot + off:tot + off + co]
+            off += co
         F = self.flat_feat
         ws.u1pre, ws.u1, ws.du1, ws.du1pre = buf(M3 * F), buf(M3 * F), buf(M3 * F), buf(M3 * F)
         ws.dec_pre, ws.dec_act, ws.dec_dact, ws.dec_dpre, ws.dec_ldk = [], [], [], [], []
