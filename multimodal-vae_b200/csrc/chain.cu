@@ -1203,8 +1203,12 @@ int launch_chain_v(const CParams& p, cudaStream_t st) {
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (coop) {
-    attr[na].id = cudaLaunchAttributeCooperative;   // every CTA resident at once: the grid barriers cannot deadlock
+  // Cooperative launch (every CTA resident at once: the grid barriers cannot deadlock) - except for the clustered kernels:
+  // a launch that is cooperative AND clustered cannot be replayed by ncu (LaunchFailed), and it is not needed: the grid is
+  // smaller than the SM count, one CTA fills an SM, and whatever holds an SM beside this kernel (weight-gradient GEMMs, the
+  // text kernels, Adam, the data-parallel exchange) never waits for it - a CTA that finds no SM at first gets one when they end.
+  if (coop && !kPair) {
+    attr[na].id = cudaLaunchAttributeCooperative;
     attr[na].val.cooperative = 1;
     ++na;
   }
