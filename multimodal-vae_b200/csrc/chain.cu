@@ -645,7 +645,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           const int col0 = 32 * u + 4 * cq;
           const bool live = col0 < N, padded = col0 < Npad;
           const float4 bs = padded ? tab4(s_bias + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+          const f2 bs01 = pk2(bs.x, bs.y), bs23 = pk2(bs.z, bs.w);
+          f2 s0a = pk2(0.f, 0.f), s0b = s0a, s1a = s0a, s1b = s0a;   // packed pairs: columns (0, 1) and (2, 3)
           uint32_t ua[4];
           unit_arena(col0, ua);
 #pragma unroll
@@ -655,14 +656,19 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 a = lds_f4(i == 0 ? trd0 : (i == 1 ? trd1 : (i == 2 ? trd2 : trd3)));
-                const float x0 = a.x + bs.x, x1 = a.y + bs.y, x2 = a.z + bs.z, x3 = a.w + bs.w;
-                s0[0] += x0; s0[1] += x1; s0[2] += x2; s0[3] += x3;
-                s1[0] = fmaf(x0, x0, s1[0]); s1[1] = fmaf(x1, x1, s1[1]); s1[2] = fmaf(x2, x2, s1[2]); s1[3] = fmaf(x3, x3, s1[3]);
+                const f2 x01 = add2(pk2(a.x, a.y), bs01), x23 = add2(pk2(a.z, a.w), bs23);
+                s0a = add2(s0a, x01); s0b = add2(s0b, x23);
+                s1a = fma2(x01, x01, s1a); s1b = fma2(x23, x23, s1b);
+                float x0, x1, x2, x3;
+                upk2(x01, x0, x1); upk2(x23, x2, x3);
                 sts64(ua[i] + half * 2048, pack_bf16(x0, x1), pack_bf16(x2, x3));
               }
             }
             __syncwarp();
           }
+          float s0[4], s1[4];
+          upk2(s0a, s0[0], s0[1]); upk2(s0b, s0[2], s0[3]);
+          upk2(s1a, s1[0], s1[1]); upk2(s1b, s1[2], s1[3]);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], 8);
@@ -721,16 +727,17 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
           if (!(col0 < Npad)) continue;
           const float4 ca = tab4(s_ca + col0);
           const float4 cb = tab4(s_cb + col0);
+          const f2 ca01 = pk2(ca.x, ca.y), ca23 = pk2(ca.z, ca.w), cb01 = pk2(cb.x, cb.y), cb23 = pk2(cb.z, cb.w);
           uint32_t ua[4];
           unit_arena(col0, ua);
 #pragma unroll
           for (int hi = 0; hi < 8; ++hi) {
             const uint32_t addr = ua[hi & 3] + (hi >> 2) * 2048;
             const uint2 xw = lds64(addr);
-            const float x0 = bf_lo(xw.x), x1 = bf_hi(xw.x), x2 = bf_lo(xw.y), x3 = bf_hi(xw.y);
-            const uint32_t w0 = pack_bf16(fmaxf(fmaf(ca.x, x0, cb.x), 0.f), fmaxf(fmaf(ca.y, x1, cb.y), 0.f));
-            const uint32_t w1 = pack_bf16(fmaxf(fmaf(ca.z, x2, cb.z), 0.f), fmaxf(fmaf(ca.w, x3, cb.w), 0.f));
-            sts64(addr, w0, w1);
+            float y0, y1, y2, y3;
+            upk2(fma2(ca01, pk2(bf_lo(xw.x), bf_hi(xw.x)), cb01), y0, y1);
+            upk2(fma2(ca23, pk2(bf_lo(xw.y), bf_hi(xw.y)), cb23), y2, y3);
+            sts64(addr, pack_bf16(fmaxf(y0, 0.f), fmaxf(y1, 0.f)), pack_bf16(fmaxf(y2, 0.f), fmaxf(y3, 0.f)));
           }
         }
         ptx::fence_proxy_async_smem();
@@ -846,6 +853,8 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
             const float4 ta = live ? tab4(s_a + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 k1 = live ? tab4(s_rs + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 k2 = live ? tab4(s_mr + col0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const f2 ta01 = pk2(ta.x, ta.y), ta23 = pk2(ta.z, ta.w), nk01 = pk2(-k1.x, -k1.y), nk23 = pk2(-k1.z, -k1.w);
+            const f2 k201 = pk2(k2.x, k2.y), k223 = pk2(k2.z, k2.w);
             uint32_t ua[4];
             unit_arena(col0, ua);
 #pragma unroll
@@ -853,11 +862,10 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
               const uint32_t addr = ua[hi & 3] + (hi >> 2) * 2048;
               const uint2 dw = live ? lds64(addr) : make_uint2(0u, 0u);
               const uint2 hw = hx2[hi];
-              const float d0 = bf_lo(dw.x), d1 = bf_hi(dw.x), d2 = bf_lo(dw.y), d3 = bf_hi(dw.y);
-              const float x0 = bf_lo(hw.x), x1 = bf_hi(hw.x), x2 = bf_lo(hw.y), x3 = bf_hi(hw.y);
-              const uint32_t w0 = pack_bf16(fmaf(ta.x, d0, fmaf(-k1.x, x0, k2.x)), fmaf(ta.y, d1, fmaf(-k1.y, x1, k2.y)));
-              const uint32_t w1 = pack_bf16(fmaf(ta.z, d2, fmaf(-k1.z, x2, k2.z)), fmaf(ta.w, d3, fmaf(-k1.w, x3, k2.w)));
-              sts64(addr, w0, w1);
+              float y0, y1, y2, y3;   // a * dyhat - k1 * x + k2 on packed pairs
+              upk2(fma2(ta01, pk2(bf_lo(dw.x), bf_hi(dw.x)), fma2(nk01, pk2(bf_lo(hw.x), bf_hi(hw.x)), k201)), y0, y1);
+              upk2(fma2(ta23, pk2(bf_lo(dw.y), bf_hi(dw.y)), fma2(nk23, pk2(bf_lo(hw.y), bf_hi(hw.y)), k223)), y2, y3);
+              sts64(addr, pack_bf16(y0, y1), pack_bf16(y2, y3));
             }
           }
 #pragma unroll
