@@ -29,6 +29,8 @@ static std::atomic<long long> g_noted_launches{0};
 void note_launch(int n) { g_noted_launches.fetch_add(n, std::memory_order_relaxed); }
 long long noted_launches() { return g_noted_launches.load(std::memory_order_relaxed); }
 
+thread_local int g_pdl_next = 0;
+
 int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   if (s == nullptr || *s == 0) return dflt;

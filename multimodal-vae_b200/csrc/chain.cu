@@ -383,6 +383,9 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above touched shared memory / TMEM / the kernel parameters only.  Under a programmatic launch the previous
+  // kernel of the stream may still be running: nothing of global memory is read or written before it has completed.
+  ptx::griddep_wait();
 
   // All per-slot / per-buffer phase bookkeeping below lives in BIT MASKS, never in indexed arrays: with the whole
   // shared-memory carve-out taken there is almost no L1, and a local-memory array costs an L2 round trip per access.
@@ -450,6 +453,9 @@ __global__ void __launch_bounds__(kCThreads, 1) chain_kernel(const __grid_consta
         if (ip < 8) stamp(1 + ip);
       }
     }
+    // every load of this CTA is issued (keeper / idle CTA: nothing to issue): the next kernel of the stream may be scheduled
+    // onto SMs as they drain (it waits in its own griddep_wait for this grid to complete)
+    if (lane == 0) ptx::griddep_launch();
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0 && slab && rank == 0) {
@@ -1202,8 +1208,14 @@ int launch_chain_v(const CParams& p, cudaStream_t st) {
   cfg.blockDim = dim3(kCThreads);
   cfg.dynamicSmemBytes = kSmemTotal;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int na = 0;
+  if (g_pdl_next) {   // the kernel's prologue (barriers, TMEM, tensor-map prefetch) may run while the previous kernel drains
+    g_pdl_next = 0;
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   if (kPair) {
     attr[na].id = cudaLaunchAttributeClusterDimension;
     attr[na].val.clusterDim.x = 2;

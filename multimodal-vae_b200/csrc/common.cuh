@@ -131,6 +131,11 @@ int env_int(const char* name, int dflt);
 void note_launch(int n = 1);
 long long noted_launches();
 
+// Set by the step orchestration right before the launch of a kernel that begins with ptx::griddep_wait(): that ONE launch
+// carries the programmatic-stream-serialization attribute (its CTAs may be scheduled while the previous kernel of the stream
+// drains) and clears the flag.  Never set it for a kernel without the wait: it would run beside its predecessor.
+extern thread_local int g_pdl_next;
+
 // One launch helper for every kernel of the library (error-checked cudaLaunchKernelEx).
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
@@ -140,6 +145,14 @@ int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, 
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  cudaLaunchAttribute pdl_attr[1];
+  if (g_pdl_next) {
+    g_pdl_next = 0;
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = 1;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx", __FILE__, __LINE__);
   return 0;

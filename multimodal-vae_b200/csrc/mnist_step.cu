@@ -322,7 +322,9 @@ static StepProfile g_prof;
 #define MVAE_STEP(call, lab)                                                           \
   do {                                                                                 \
     if (g_prof.on && g_prof.n < 96) cudaEventRecord(g_prof.ev[2 * g_prof.n], st);      \
-    if (call) return 1;                                                                \
+    const int rc_ = (call);                                                            \
+    g_pdl_next = 0; /* a programmatic-launch mark never outlives the launch it was set for */ \
+    if (rc_) return 1;                                                                 \
     ++g_launches;                                                                      \
     if (g_prof.on && g_prof.n < 96) {                                                  \
       cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st);                                \
@@ -423,6 +425,12 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   const bool use_chain = chain_env != 0 && a->dtype == MVAE_DT_BF16 && training && bwd && !module_bwd && !decode_only &&
                          chain_supported(B, G, n);
 
+  // Programmatic dependent launch along the critical path of the chain step (enc_fwd -> tail -> dec_fwd -> dec_bwd -> tail ->
+  // enc_bwd): each of these kernels starts with griddep_wait, so its CTAs may be scheduled - and run their prologue - while the
+  // previous kernel of the stream drains.  Cross-stream joins stay ordinary (full) dependencies.
+  static const int pdl_env = env_int("MVAE_PDL", 14);   // bits: 0 enc_fwd, 1 tail_fwd, 2 dec_fwd, 3 dec_bwd, 4 tail_bwd, 5 enc_bwd
+  const bool use_pdl = pdl_env != 0 && use_chain && !g_prof.on && !debug_sync;
+  auto pdl_mark = [&](int bit) { g_pdl_next = (use_pdl && ((pdl_env >> bit) & 1)) ? 1 : 0; };   // MVAE_PDL: one bit per launch
   // one call = the whole step with the optimizer: the decoder bucket's Adam runs beside the encoder backward
   const bool adam_split = bwd && bwd_dec && bwd_enc && a->do_adam && !module_bwd && ss != nullptr && L.enc_floats % 4 == 0;
 
@@ -520,6 +528,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     ce.h2pre = W.at<__nv_bfloat16>(P.h2pre); ce.h2 = W.at<__nv_bfloat16>(P.h2);
     ce.enc = W.at<float>(P.enc);
     ce.err = chain_err;
+    pdl_mark(0);
     MVAE_STEP(launch_chain_enc_fwd(ce, st), "chain_enc_fwd");
     if (text_encoder_aside()) return 1;
     if (zero_grads_aside()) return 1;
@@ -561,7 +570,10 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
   ta.z = W.at<void>(P.z); ta.mu = a->out_mu; ta.logvar = a->out_logvar;
   ta.kl = losses + 2 * kMaxGroups;
   ta.t1pre = W.at<float>(P.t1pre); ta.t1_sum = st_t1; ta.t1_sumsq = st_t1 + G * 10;
-  if (fwd) MVAE_STEP(launch_tail_forward(ta, st), "launch_tail_forward#8");
+  if (fwd) {
+    pdl_mark(1);
+    MVAE_STEP(launch_tail_forward(ta, st), "launch_tail_forward#8");
+  }
   if (grads_zeroing && dep(s2, st)) return 1;   // join: the gradient buffer is clear before the first kernel that adds into it
 
   TextDecArgs td;
@@ -602,6 +614,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     cd.loss = losses;
     cd.dbias3 = gf("image_decoder.net.6.bias");
     cd.err = chain_err;
+    pdl_mark(2);
     MVAE_STEP(launch_chain_dec_fwd(cd, st), "chain_dec_fwd");
   }
   if (fwd && use_chain) MVAE_STEP(launch_textdec(td, s3), "launch_textdec");
@@ -667,6 +680,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     // needs SMs of its own
     static const int dp_parts = env_int("MVAE_CHAIN_SPLIT_DP", 2);
     cb.max_parts = a->phase == 4 ? dp_parts : 4;
+    pdl_mark(5);
     MVAE_STEP(launch_chain_enc_bwd(cb, st), "chain_enc_bwd");
     enc_chain_launched = true;
     return 0;
@@ -701,6 +715,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
       cb.dgamma1 = gf("image_decoder.net.1.weight"); cb.dbeta1 = gf("image_decoder.net.1.bias");
       cb.dgamma2 = gf("image_decoder.net.4.weight"); cb.dbeta2 = gf("image_decoder.net.4.bias");
       cb.err = chain_err;
+      pdl_mark(3);
       MVAE_STEP(launch_chain_dec_bwd(cb, st), "chain_dec_bwd");
       MVAE_STEP(gemm_wgrad(dt, R, 784, 400, W.at<void>(P.dlog), W.at<void>(P.g2), gf("image_decoder.net.6.weight"), s2), "gemm_wgrad:image_decoder.net.6.weight#16");
       if (dep(st, s2)) return 1;
@@ -740,6 +755,7 @@ int mvae_mnist_step(const mvae_mnist_step_args* a, void* stream_v) {
     ta.d_wt1 = gf("text_decoder.net.0.weight");
     ta.d_t1_gamma = gf("text_decoder.net.1.weight"); ta.d_t1_beta = gf("text_decoder.net.1.bias");
     if (dep(s3, st)) return 1;  // join: text decoder results
+    pdl_mark(4);
     MVAE_STEP(launch_tail_backward(ta, st), "launch_tail_backward");
     if (dep(st, s2)) return 1;  // fork: encoder weight gradients
     if (dep(st, s3)) return 1;  // fork: text encoder backward

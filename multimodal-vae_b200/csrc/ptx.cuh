@@ -235,6 +235,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Generic-proxy writes to smem made visible to the async proxy (TMA / UMMA reads).
 // ... for every state space (global data another SM's TMA wrote, about to be read by this thread's TMA)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// Programmatic dependent launch (the launch attribute cudaLaunchAttributeProgrammaticStreamSerialization): `griddep_wait` blocks
+// until every grid this one depends on has completed and its memory is visible (a no-op without the attribute);
+// `griddep_launch` lets the dependent grid's CTAs be scheduled once every CTA of this grid has issued it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "poe.cuh"
+#include "ptx.cuh"
 #include "../../include/mvae_b200.h"
 
 namespace mvae {
@@ -49,6 +50,8 @@ __device__ __forceinline__ void store_pair(T* p, float a, float b) {
 // One warp per (term, sample): lanes own latent pairs.
 template <typename ZT>
 __global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArgs a) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   __shared__ float s_stat[kMaxGroups][2][kTD];
   __shared__ float s_kl[kMaxGroups];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,6 +159,8 @@ __global__ void __launch_bounds__(kTailThreads, 3) tail_fwd_kernel(const TailArg
 // Same arithmetic per element as tail_fwd_kernel (poe_combine == poe_eval bit for bit, same Philox stream).
 template <typename ZT, int kFwd2Warps>
 __global__ void __launch_bounds__(32 * kFwd2Warps, 28 / kFwd2Warps) tail_fwd2_kernel(const TailArgs a) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   __shared__ float s_stat[kMaxGroups][2][kTD];
   __shared__ float s_kl[kMaxGroups];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,6 +291,8 @@ __global__ void __launch_bounds__(32 * kFwd2Warps, 28 / kFwd2Warps) tail_fwd2_ke
 constexpr int kBwdRows = 4;
 template <typename ZT>
 __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel(const TailArgs a, int smem_floats) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   extern __shared__ float sm[];
   // layout: d_txt_table [10][2n] | d_wt1 [10][n] | d_enc_bias [2n] | t1 coefficients [G][4][10] |
   //         image-expert combine [rows][G][2n] | text-expert combine [rows][G][2n] | labels [rows]
@@ -504,6 +511,8 @@ __global__ void __launch_bounds__(32 * kMaxGroups * kBwdRows, 2) tail_bwd_kernel
 // in shared memory and its weight gradient in per-lane registers.  Same arithmetic as tail_bwd_kernel.
 template <typename ZT, int kBwd2Warps>
 __global__ void __launch_bounds__(32 * kBwd2Warps, 28 / kBwd2Warps) tail_bwd2_kernel(const TailArgs a) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   extern __shared__ float sm[];
   const int n = a.n, two_n = 2 * a.n, G = a.G;
   // layout: text-expert table [10][2n] | Wt1 [10][n] | t1 coefficients [G][4][10] | d_wt1 [10][n] | d_enc_bias [2n]
@@ -711,6 +720,8 @@ constexpr int kT3N = 64;
 
 template <typename ZT, int kMode>
 __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailArgs a) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   constexpr int n = kT3N, two_n = 2 * kT3N;
   __shared__ float s_red[kT3Warps][64 + kMaxGroups];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -845,6 +856,8 @@ __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_fwd3_kernel(const TailA
 
 template <typename ZT, int kMode>
 __global__ void __launch_bounds__(32 * kT3Warps, 2) tail_bwd3_kernel(const TailArgs a) {
+  ptx::griddep_launch();   // programmatic launch (common.cuh, g_pdl_next): the next kernel's prologue may overlap this one
+  ptx::griddep_wait();     // ... and this one starts while its predecessor drains; no global access before this line
   constexpr int n = kT3N, two_n = 2 * kT3N;
   constexpr int kTab = kTD * two_n;   // floats per warp table
   extern __shared__ float sm[];       // per-warp text-expert tables [warps][10][2n] | Wt1 [10][n]
