@@ -37,7 +37,7 @@ print("# SASS mnemonic counts per kernel of libmvae_b200.so (cuobjdump -sass, sm
 print("# tools/sass_mnemonics.py).  tcgen05.mma = UTCHMMA, tcgen05.ld = LDTM, TMA load / store = UTMALDG / UTMASTG, tcgen05.commit =")
 print("# UTCBAR, '2CTA' = instructions carrying the .2CTA modifier (cta_group::2 MMA / TMA / commit / TMEM allocation), F*2 = packed")
 print("# fp32 pairs (FADD2 + FMUL2 + FFMA2), UCGABAR = cluster barrier.  chain_kernel<K0, K1, K2, pair>: kinds 0 FWD_BN, 1 FWD_STORE,")
-print("# 2 BCE, 3 DGRAD_BN, 4 DGRAD_STORE.")
+print("# 2 BCE, 3 DGRAD_BN, 4 DGRAD_STORE.  ACQBULK / PREEXIT = griddepcontrol.wait / .launch_dependents (programmatic launches).")
 for mangled, d in zip(names, demangled):
     if not keep.search(d):
         continue
@@ -46,6 +46,6 @@ for mangled, d in zip(names, demangled):
 
     def n(pat):
         return sum(1 for o in op if re.match(pat, o))
-    print("%-44s instr %6d  UTCHMMA %3d  LDTM %3d  UTMALDG %3d  UTMASTG %3d  UTCBAR %3d  2CTA %3d  MUFU %4d  F*2 %4d  UCGABAR %2d" % (
+    print("%-44s instr %6d  UTCHMMA %3d  LDTM %3d  UTMALDG %3d  UTMASTG %3d  UTCBAR %3d  2CTA %3d  MUFU %4d  F*2 %4d  UCGABAR %2d  ACQBULK %d  PREEXIT %d" % (
         short(d), len(ins), n(r"UTC[A-Z]*MMA"), n(r"LDTM"), n(r"UTMALDG"), n(r"UTMASTG"), n(r"UTCBAR"),
-        sum(1 for o in op if ".2CTA" in o), n(r"MUFU"), n(r"(FADD2|FMUL2|FFMA2)"), n(r"UCGABAR")))
+        sum(1 for o in op if ".2CTA" in o), n(r"MUFU"), n(r"(FADD2|FMUL2|FFMA2)"), n(r"UCGABAR"), n(r"ACQBULK"), n(r"PREEXIT")))
