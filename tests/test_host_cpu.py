@@ -28,6 +28,28 @@ def test_library_exports_every_declared_symbol():
     assert lib.mvae_abi_version() == int(m.group(1))
 
 
+def test_library_sass_is_tcgen05_tma_native():
+    """The built library is sm_100a code on the Blackwell tensor path: its SASS carries tcgen05.mma (UTC*MMA), tcgen05.ld
+    (LDTM), TMA loads (UTMALDG), the cta_group::2 forms of the pair kernels and the programmatic-launch instructions -
+    and nothing falls back to mma.sync (HMMA) tiles.  (cuobjdump only; no GPU.)"""
+    import shutil
+    import subprocess
+    from mvae_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _lib.load()
+    so = os.path.join(ROOT, "multimodal-vae_b200", "libmvae_b200.so")
+    elf = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf, elf
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    count = lambda pat: len(re.findall(pat, sass))
+    assert count(r"\bUTC[A-Z]*MMA") >= 64          # every GEMM / chain instantiation issues tcgen05.mma
+    assert count(r"\bLDTM") >= 64 and count(r"\bUTMALDG") >= 64
+    assert count(r"\bUTC[A-Z]*MMA\.2CTA|\.2CTA") >= 8   # CTA-pair chain kernels
+    assert count(r"\bACQBULK") >= 8 and count(r"\bPREEXIT") >= 8
+    assert count(r"\bHMMA\.") == 0
+
+
 def test_layout_matches_reference_state_dict():
     import mvae_b200
     from mvae_b200 import mnist
